@@ -1,0 +1,243 @@
+/* ref_dump.c -- TEST INFRASTRUCTURE ONLY (never linked into the product).
+ *
+ * A small driver over the UNMODIFIED reference library (oracle/_ref/libHYPRE_ref.so,
+ * compiled in place from /root/reference/src by oracle/build_ref.py).  It runs the
+ * same call sequence as the reference driver for `ij -laplacian ... -solver 1`
+ * (src/test/ij.c:3891-4010 create/set, :4013-4050 setup/solve) through the public
+ * HYPRE_* API and then dumps, for parity tests, what the reference built:
+ *   per level l:  A_l (diag CSR), CF_marker_l, S_l (strength, recomputed with the
+ *                 reference's hypre_BoomerAMGCreateS), P_l (diag CSR), l1 norms,
+ *   and the PCG residual history, iteration count and final relative residual.
+ *
+ * Output: a flat binary stream of records
+ *     [u32 namelen][name][u32 dtype 0=i32 1=f64][u64 count][payload]
+ * read by tests/refio.py.
+ *
+ * Flags follow ij.c's spelling: -n nx ny nz, -27pt, -c cx cy cz, -pmis, -rlx T,
+ * -Pmx K, -agg_nl L, -mod_rap2 B, -keepT B, -th theta, -tol t, -interptype I,
+ * -mxrs r (max_row_sum), -o FILE, -matvec K (time K SpMVs, ij -solver -1 analogue),
+ * -nodump (timing only).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#include <time.h>
+#include "_hypre_utilities.h"
+#include "HYPRE.h"
+#include "HYPRE_parcsr_mv.h"
+#include "HYPRE_parcsr_ls.h"
+#include "_hypre_parcsr_mv.h"
+#include "_hypre_parcsr_ls.h"
+#include "HYPRE_krylov.h"
+
+static FILE *g_out;
+
+static void put(const char *name, int dtype, const void *p, size_t n)
+{
+   unsigned int nl = (unsigned int) strlen(name), dt = (unsigned int) dtype;
+   unsigned long long cnt = n;
+   if (!g_out) return;
+   fwrite(&nl, 4, 1, g_out); fwrite(name, 1, nl, g_out);
+   fwrite(&dt, 4, 1, g_out); fwrite(&cnt, 8, 1, g_out);
+   if (n) fwrite(p, dtype ? 8 : 4, n, g_out);
+}
+static void put_csr(const char *pre, int l, hypre_CSRMatrix *M, int with_data)
+{
+   char nm[64];
+   int n = hypre_CSRMatrixNumRows(M);
+   int nnz = hypre_CSRMatrixI(M)[n];
+   int dims[3] = { n, hypre_CSRMatrixNumCols(M), nnz };
+   sprintf(nm, "%s%d.dims", pre, l); put(nm, 0, dims, 3);
+   sprintf(nm, "%s%d.i", pre, l);    put(nm, 0, hypre_CSRMatrixI(M), n + 1);
+   sprintf(nm, "%s%d.j", pre, l);    put(nm, 0, hypre_CSRMatrixJ(M), nnz);
+   if (with_data) { sprintf(nm, "%s%d.a", pre, l); put(nm, 1, hypre_CSRMatrixData(M), nnz); }
+}
+static double now(void)
+{
+   struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
+   return ts.tv_sec + 1e-9 * ts.tv_nsec;
+}
+
+int main(int argc, char **argv)
+{
+   int nx = 10, ny = 10, nz = 10, pt27 = 0, pmis = 0, rlx = -1, Pmx = 4, agg_nl = 0;
+   int mod_rap2 = 0, keepT = 0, interp_type = 6, nodump = 0, matvec = 0, max_iter = 100;
+   double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
+   const char *ofile = NULL;
+   int i;
+   for (i = 1; i < argc; i++)
+   {
+      if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
+      else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
+      else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-pmis")) pmis = 1;
+      else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-Pmx")) Pmx = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-agg_nl")) agg_nl = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-mod_rap2")) mod_rap2 = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-keepT")) keepT = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-interptype")) interp_type = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-th")) th = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-tol")) tol = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-mxrs")) mxrs = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-max_iter")) max_iter = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-matvec")) matvec = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-nodump")) nodump = 1;
+      else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
+      else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
+   }
+   hypre_MPI_Init(&argc, &argv);
+   HYPRE_Init();
+   if (ofile && !nodump) g_out = fopen(ofile, "wb");
+
+   /* matrix: same generator calls and stencil values as ij.c:7788-7810 / :9078-9086 */
+   HYPRE_ParCSRMatrix A;
+   double t0 = now();
+   if (pt27)
+   {
+      HYPRE_Real values[2];
+      values[0] = 26.0;
+      if (nx == 1 || ny == 1 || nz == 1) values[0] = 8.0;
+      if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
+      values[1] = -1.;
+      A = (HYPRE_ParCSRMatrix) GenerateLaplacian27pt(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+   }
+   else
+   {
+      HYPRE_Real values[4];
+      values[1] = -cx; values[2] = -cy; values[3] = -cz; values[0] = 0.;
+      if (nx > 1) values[0] += 2.0 * cx;
+      if (ny > 1) values[0] += 2.0 * cy;
+      if (nz > 1) values[0] += 2.0 * cz;
+      A = (HYPRE_ParCSRMatrix) GenerateLaplacian(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+   }
+   double t_gen = now() - t0;
+   hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
+   int N = hypre_CSRMatrixNumRows(hypre_ParCSRMatrixDiag(pA));
+   HYPRE_BigInt *row_starts = hypre_ParCSRMatrixRowStarts(pA);
+
+   hypre_ParVector *b = hypre_ParVectorCreate(hypre_MPI_COMM_WORLD, N, row_starts);
+   hypre_ParVectorSetPartitioningOwner(b, 0);
+   hypre_ParVectorInitialize(b);
+   hypre_ParVectorSetConstantValues(b, 1.0);       /* ij.c:2714-2748 build_rhs_type 2 */
+   hypre_ParVector *x = hypre_ParVectorCreate(hypre_MPI_COMM_WORLD, N, row_starts);
+   hypre_ParVectorSetPartitioningOwner(x, 0);
+   hypre_ParVectorInitialize(x);
+   hypre_ParVectorSetConstantValues(x, 0.0);
+
+   printf("ref_dump: n=%d %d %d rows=%d nnz=%d threads=%d gen=%.3fs\n", nx, ny, nz, N,
+          hypre_CSRMatrixI(hypre_ParCSRMatrixDiag(pA))[N], hypre_NumThreads(), t_gen);
+
+   if (matvec > 0)
+   {  /* ij -solver -1 analogue (ij.c:3206-3243): y = A x repeated */
+      hypre_ParVectorSetConstantValues(x, 1.0);
+      hypre_ParCSRMatrixMatvec(1.0, pA, x, 0.0, b);
+      t0 = now();
+      for (i = 0; i < matvec; i++) hypre_ParCSRMatrixMatvec(1.0, pA, x, 0.0, b);
+      double dt = (now() - t0) / matvec;
+      printf("ref_dump: matvec_ms=%.6f reps=%d\n", dt * 1e3, matvec);
+      HYPRE_Finalize(); hypre_MPI_Finalize();
+      return 0;
+   }
+
+   HYPRE_Solver pcg, amg;
+   HYPRE_ParCSRPCGCreate(hypre_MPI_COMM_WORLD, &pcg);
+   HYPRE_PCGSetMaxIter(pcg, 1000);
+   HYPRE_PCGSetTol(pcg, tol);
+   HYPRE_PCGSetTwoNorm(pcg, 1);
+   HYPRE_PCGSetRelChange(pcg, 0);
+   HYPRE_PCGSetPrintLevel(pcg, 0);
+   HYPRE_PCGSetLogging(pcg, 1);
+
+   HYPRE_BoomerAMGCreate(&amg);
+   HYPRE_BoomerAMGSetInterpType(amg, interp_type);
+   HYPRE_BoomerAMGSetTol(amg, 0.);
+   HYPRE_BoomerAMGSetCoarsenType(amg, pmis ? 8 : 10);
+   HYPRE_BoomerAMGSetStrongThreshold(amg, th);
+   HYPRE_BoomerAMGSetMaxCoarseSize(amg, 9);
+   HYPRE_BoomerAMGSetTruncFactor(amg, 0.);
+   HYPRE_BoomerAMGSetPMaxElmts(amg, Pmx);
+   HYPRE_BoomerAMGSetPrintLevel(amg, 0);
+   HYPRE_BoomerAMGSetMaxIter(amg, 1);
+   HYPRE_BoomerAMGSetCycleType(amg, 1);
+   HYPRE_BoomerAMGSetNumSweeps(amg, 1);
+   if (rlx > -1) HYPRE_BoomerAMGSetRelaxType(amg, rlx);
+   HYPRE_BoomerAMGSetRelaxOrder(amg, 0);
+   HYPRE_BoomerAMGSetRelaxWt(amg, 1.0);
+   HYPRE_BoomerAMGSetOuterWt(amg, 1.0);
+   HYPRE_BoomerAMGSetMaxLevels(amg, 25);
+   HYPRE_BoomerAMGSetMaxRowSum(amg, mxrs);
+   HYPRE_BoomerAMGSetNumFunctions(amg, 1);
+   HYPRE_BoomerAMGSetAggNumLevels(amg, agg_nl);
+   HYPRE_BoomerAMGSetAggInterpType(amg, 4);
+   HYPRE_BoomerAMGSetCycleNumSweeps(amg, 1, 3);
+   HYPRE_BoomerAMGSetRAP2(amg, 0);
+   HYPRE_BoomerAMGSetModuleRAP2(amg, mod_rap2);
+   HYPRE_BoomerAMGSetKeepTranspose(amg, keepT);
+   HYPRE_PCGSetMaxIter(pcg, max_iter);
+   HYPRE_PCGSetPrecond(pcg, (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSolve,
+                       (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSetup, amg);
+
+   t0 = now();
+   HYPRE_PCGSetup(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+   double t_setup = now() - t0;
+   t0 = now();
+   HYPRE_PCGSolve(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+   double t_solve = now() - t0;
+
+   HYPRE_Int its; HYPRE_Real relres;
+   HYPRE_PCGGetNumIterations(pcg, &its);
+   HYPRE_PCGGetFinalRelativeResidualNorm(pcg, &relres);
+
+   hypre_ParAMGData *ad = (hypre_ParAMGData *) amg;
+   int nl = hypre_ParAMGDataNumLevels(ad);
+   printf("ref_dump: levels=%d iterations=%d relres=%.6e setup_s=%.4f solve_s=%.4f\n",
+          nl, (int) its, relres, t_setup, t_solve);
+   for (i = 0; i < nl; i++)
+   {
+      hypre_ParCSRMatrix *Al = hypre_ParAMGDataAArray(ad)[i];
+      int n = hypre_CSRMatrixNumRows(hypre_ParCSRMatrixDiag(Al));
+      printf("ref_dump: level %d rows=%d nnz=%d\n", i, n, hypre_CSRMatrixI(hypre_ParCSRMatrixDiag(Al))[n]);
+   }
+
+   if (g_out)
+   {
+      int hdr[8] = { nx, ny, nz, nl, (int) its, pt27, Pmx, rlx };
+      put("hdr", 0, hdr, 8);
+      put("relres", 1, &relres, 1);
+      /* residual history (pcg.c:597-600 norms[]) */
+      hypre_PCGData *pd = (hypre_PCGData *) pcg;
+      put("norms", 1, pd->norms, its + 1);
+      put("x", 1, hypre_VectorData(hypre_ParVectorLocalVector(x)), N);
+      for (i = 0; i < nl; i++)
+      {
+         char nm[64];
+         hypre_ParCSRMatrix *Al = hypre_ParAMGDataAArray(ad)[i];
+         int n = hypre_CSRMatrixNumRows(hypre_ParCSRMatrixDiag(Al));
+         put_csr("A", i, hypre_ParCSRMatrixDiag(Al), 1);
+         if (hypre_ParAMGDataL1Norms(ad) && hypre_ParAMGDataL1Norms(ad)[i])
+         {
+            sprintf(nm, "l1_%d", i);
+            put(nm, 1, hypre_VectorData(hypre_ParAMGDataL1Norms(ad)[i]), n);
+         }
+         if (i < nl - 1)
+         {
+            hypre_ParCSRMatrix *S = NULL;
+            sprintf(nm, "CF%d", i);
+            put(nm, 0, hypre_ParAMGDataCFMarkerArray(ad)[i], n);
+            put_csr("P", i, hypre_ParCSRMatrixDiag(hypre_ParAMGDataPArray(ad)[i]), 1);
+            if (agg_nl == 0 || i >= agg_nl)
+            {
+               hypre_BoomerAMGCreateS(Al, th, mxrs, 1, NULL, &S);
+               put_csr("S", i, hypre_ParCSRMatrixDiag(S), 0);
+               hypre_ParCSRMatrixDestroy(S);
+            }
+         }
+      }
+      fclose(g_out);
+   }
+   HYPRE_Finalize();
+   hypre_MPI_Finalize();
+   return 0;
+}
