@@ -1,0 +1,409 @@
+"""hypre_ve_b200 -- Python binding (ctypes) of libhypre_b200.so, the B200-native implementation of
+BoomerAMG's data-parallel hot path.  The product is the shared library and its C-ABI
+(include/hypre_b200.h); this module only loads it for tests and bench.py.
+
+There is NO CPU fallback: loading fails loudly when the CUDA library has not been built, and
+every call raises B200Error when the device path reports an error.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhypre_b200.so")
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+_vp, _i, _d, _sz = C.c_void_p, C.c_int, C.c_double, C.c_size_t
+_ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+
+# name -> (restype, argtypes): mirrors include/hypre_b200.h one to one
+SIGNATURES = {
+    "b200_init": (_i, [_i, C.POINTER(_vp)]),
+    "b200_finalize": (_i, [_vp]),
+    "b200_last_error": (C.c_char_p, []),
+    "b200_stream": (_vp, [_vp]),
+    "b200_sync": (_i, [_vp]),
+    "b200_malloc": (_i, [_vp, C.POINTER(_vp), _sz]),
+    "b200_free": (_i, [_vp, _vp]),
+    "b200_memcpy_h2d": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memcpy_d2h": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memcpy_d2d": (_i, [_vp, _vp, _vp, _sz]),
+    "b200_memset": (_i, [_vp, _vp, _i, _sz]),
+    "b200_launch_count": (C.c_longlong, []),
+    "b200_timer_start": (_i, [_vp]),
+    "b200_timer_stop_ms": (_i, [_vp, _dp]),
+    "b200_csr_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
+    "b200_csr_create_from_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_csr_destroy": (_i, [_vp, _vp]),
+    "b200_csr_dims": (_i, [_vp, _ip, _ip, _ip]),
+    "b200_csr_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200_csr_matvec": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_csr_transpose": (_i, [_vp, _vp, C.POINTER(_vp)]),
+    "b200_csr_multiply": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_vec_fill": (_i, [_vp, _i, _d, _vp]),
+    "b200_vec_copy": (_i, [_vp, _i, _vp, _vp]),
+    "b200_vec_scale": (_i, [_vp, _i, _d, _vp]),
+    "b200_vec_axpy": (_i, [_vp, _i, _d, _vp, _vp]),
+    "b200_vec_dot": (_i, [_vp, _i, _vp, _vp, _dp]),
+    "b200_generate_laplacian": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_generate_laplacian27": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_parcsr_create_from_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_parcsr_destroy": (_i, [_vp, _vp]),
+    "b200_parcsr_local_rows": (_i, [_vp, _ip, _ip, _ip, _ip]),
+    "b200_parcsr_diag": (_vp, [_vp]),
+    "b200_parcsr_offd": (_vp, [_vp]),
+    "b200_parcsr_matvec": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_amg_create": (_i, [C.POINTER(_vp)]),
+    "b200_amg_destroy": (_i, [_vp, _vp]),
+    "b200_amg_set_int": (_i, [_vp, C.c_char_p, _i]),
+    "b200_amg_set_real": (_i, [_vp, C.c_char_p, _d]),
+    "b200_amg_setup": (_i, [_vp, _vp, _vp]),
+    "b200_amg_solve": (_i, [_vp, _vp, _vp, _vp]),
+    "b200_amg_num_levels": (_i, [_vp]),
+    "b200_amg_level_A": (_vp, [_vp, _i]),
+    "b200_amg_level_P": (_vp, [_vp, _i]),
+    "b200_amg_level_S": (_vp, [_vp, _i]),
+    "b200_amg_level_CF": (_vp, [_vp, _i]),
+    "b200_amg_level_l1": (_vp, [_vp, _i]),
+    "b200_amg_setup_times": (_i, [_vp, _dp]),
+    "b200_strength": (_i, [_vp, _vp, _d, _d, C.POINTER(_vp)]),
+    "b200_pmis": (_i, [_vp, _vp, _i, _vp]),
+    "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
+    "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
+    "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
+}
+
+
+def load_library(path=None):
+    """dlopen libhypre_b200.so and attach the C-ABI signatures.  Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or LIB_PATH
+    if not os.path.exists(path):
+        raise B200Error(
+            "libhypre_b200.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "there is no CPU fallback." % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)           # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise B200Error(_lib.b200_last_error().decode())
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(_vp)
+
+
+class DeviceArray:
+    """A device buffer owned by a Handle (stream-ordered pool allocation)."""
+
+    def __init__(self, handle, n, dtype):
+        self.h = handle
+        self.n = int(n)
+        self.dtype = np.dtype(dtype)
+        p = _vp()
+        _chk(_lib.b200_malloc(handle.p, C.byref(p), max(1, self.n) * self.dtype.itemsize))
+        self.ptr = p
+
+    @classmethod
+    def from_numpy(cls, handle, a):
+        a = np.ascontiguousarray(a)
+        d = cls(handle, a.size, a.dtype)
+        if a.size:
+            _chk(_lib.b200_memcpy_h2d(handle.p, d.ptr, _np_ptr(a), a.nbytes))
+        return d
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.size == self.n
+        if a.size:
+            _chk(_lib.b200_memcpy_h2d(self.h.p, self.ptr, _np_ptr(a), a.nbytes))
+
+    def numpy(self):
+        out = np.empty(self.n, dtype=self.dtype)
+        if self.n:
+            _chk(_lib.b200_memcpy_d2h(self.h.p, _np_ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            _chk(_lib.b200_free(self.h.p, self.ptr))
+            self.ptr = None
+
+
+def _download_raw(handle, ptr, n, dtype):
+    out = np.empty(int(n), dtype=dtype)
+    if n:
+        _chk(_lib.b200_memcpy_d2h(handle.p, _np_ptr(out), _vp(ptr) if not isinstance(ptr, _vp) else ptr, out.nbytes))
+    return out
+
+
+class Csr:
+    def __init__(self, handle, p, owned=True):
+        self.h, self.p, self.owned = handle, p, owned
+
+    @classmethod
+    def from_host(cls, handle, indptr, indices, data):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = None if data is None else np.ascontiguousarray(data, dtype=np.float64)
+        p = _vp()
+        nrows = indptr.size - 1
+        ncols = int(indices.max()) + 1 if indices.size else 0
+        _chk(_lib.b200_csr_create_from_host(handle.p, nrows, ncols, indices.size, _np_ptr(indptr), _np_ptr(indices),
+                                            _np_ptr(data) if data is not None else None, C.byref(p)))
+        return cls(handle, p)
+
+    def set_ncols(self, n):
+        pass
+
+    @property
+    def dims(self):
+        a, b, c = _i(), _i(), _i()
+        _chk(_lib.b200_csr_dims(self.p, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def download(self, with_data=True):
+        n, _, nnz = self.dims
+        i = np.empty(n + 1, np.int32)
+        j = np.empty(nnz, np.int32)
+        a = np.empty(nnz, np.float64) if with_data else None
+        _chk(_lib.b200_csr_download(self.h.p, self.p, _np_ptr(i), _np_ptr(j), _np_ptr(a) if with_data else None))
+        return i, j, a
+
+    def matvec(self, alpha, x, beta, b, y):
+        _chk(_lib.b200_csr_matvec(self.h.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def transpose(self):
+        p = _vp()
+        _chk(_lib.b200_csr_transpose(self.h.p, self.p, C.byref(p)))
+        return Csr(self.h, p)
+
+    def multiply(self, other):
+        p = _vp()
+        _chk(_lib.b200_csr_multiply(self.h.p, self.p, other.p, C.byref(p)))
+        return Csr(self.h, p)
+
+    def destroy(self):
+        if self.owned and self.p:
+            _chk(_lib.b200_csr_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class ParCsr:
+    def __init__(self, handle, p):
+        self.h, self.p = handle, p
+
+    @classmethod
+    def laplacian(cls, handle, nx, ny, nz, P=1, Q=1, R=1, p=0, q=0, r=0, c=(1.0, 1.0, 1.0)):
+        """ij.c:7788-7810: values = [2(cx+cy+cz) over active dims, -cx, -cy, -cz]"""
+        v = (C.c_double * 4)()
+        v[1], v[2], v[3] = -c[0], -c[1], -c[2]
+        v[0] = (2.0 * c[0] if nx > 1 else 0.0) + (2.0 * c[1] if ny > 1 else 0.0) + (2.0 * c[2] if nz > 1 else 0.0)
+        out = _vp()
+        _chk(_lib.b200_generate_laplacian(handle.p, nx, ny, nz, P, Q, R, p, q, r, v, C.byref(out)))
+        return cls(handle, out)
+
+    @classmethod
+    def laplacian27(cls, handle, nx, ny, nz, P=1, Q=1, R=1, p=0, q=0, r=0):
+        """ij.c:9078-9086"""
+        v = (C.c_double * 2)()
+        v[0] = 26.0
+        if nx == 1 or ny == 1 or nz == 1:
+            v[0] = 8.0
+        if nx * ny == 1 or nx * nz == 1 or ny * nz == 1:
+            v[0] = 2.0
+        v[1] = -1.0
+        out = _vp()
+        _chk(_lib.b200_generate_laplacian27(handle.p, nx, ny, nz, P, Q, R, p, q, r, v, C.byref(out)))
+        return cls(handle, out)
+
+    @classmethod
+    def from_host(cls, handle, indptr, indices, data, ncols=None):
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        out = _vp()
+        n = indptr.size - 1
+        _chk(_lib.b200_parcsr_create_from_host(handle.p, n, n if ncols is None else ncols, indices.size,
+                                               _np_ptr(indptr), _np_ptr(indices), _np_ptr(data), C.byref(out)))
+        return cls(handle, out)
+
+    @property
+    def local(self):
+        a, b, c, d = _i(), _i(), _i(), _i()
+        _chk(_lib.b200_parcsr_local_rows(self.p, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    @property
+    def diag(self):
+        return Csr(self.h, _vp(_lib.b200_parcsr_diag(self.p)), owned=False)
+
+    @property
+    def offd(self):
+        return Csr(self.h, _vp(_lib.b200_parcsr_offd(self.p)), owned=False)
+
+    def matvec(self, alpha, x, beta, b, y):
+        _chk(_lib.b200_parcsr_matvec(self.h.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def destroy(self):
+        if self.p:
+            _chk(_lib.b200_parcsr_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class Amg:
+    """BoomerAMG hierarchy (mirror of the HYPRE_BoomerAMG* solver object)."""
+
+    def __init__(self, handle, **params):
+        self.h = handle
+        p = _vp()
+        _chk(_lib.b200_amg_create(C.byref(p)))
+        self.p = p
+        for k, v in params.items():
+            self.set(k, v)
+
+    def set(self, name, value):
+        if isinstance(value, float):
+            _chk(_lib.b200_amg_set_real(self.p, name.encode(), value))
+        else:
+            _chk(_lib.b200_amg_set_int(self.p, name.encode(), int(value)))
+
+    def setup(self, A):
+        _chk(_lib.b200_amg_setup(self.h.p, self.p, A.p))
+
+    def solve(self, f, u):
+        _chk(_lib.b200_amg_solve(self.h.p, self.p, f.ptr, u.ptr))
+
+    @property
+    def num_levels(self):
+        return _lib.b200_amg_num_levels(self.p)
+
+    def level_A(self, l):
+        return Csr(self.h, _vp(_lib.b200_amg_level_A(self.p, l)), owned=False)
+
+    def level_P(self, l):
+        return Csr(self.h, _vp(_lib.b200_amg_level_P(self.p, l)), owned=False)
+
+    def level_S(self, l):
+        q = _lib.b200_amg_level_S(self.p, l)
+        return Csr(self.h, _vp(q), owned=False) if q else None
+
+    def level_CF(self, l):
+        n = self.level_A(l).dims[0]
+        return _download_raw(self.h, _lib.b200_amg_level_CF(self.p, l), n, np.int32)
+
+    def level_l1(self, l):
+        n = self.level_A(l).dims[0]
+        q = _lib.b200_amg_level_l1(self.p, l)
+        return _download_raw(self.h, q, n, np.float64) if q else None
+
+    def setup_times(self):
+        t = (C.c_double * 8)()
+        _chk(_lib.b200_amg_setup_times(self.p, t))
+        return list(t)
+
+    def destroy(self):
+        if self.p:
+            _chk(_lib.b200_amg_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class Handle:
+    def __init__(self, device=0):
+        load_library()
+        p = _vp()
+        _chk(_lib.b200_init(device, C.byref(p)))
+        self.p = p
+
+    def sync(self):
+        _chk(_lib.b200_sync(self.p))
+
+    def array(self, a):
+        return DeviceArray.from_numpy(self, a)
+
+    def empty(self, n, dtype=np.float64):
+        return DeviceArray(self, n, dtype)
+
+    def zeros(self, n, dtype=np.float64):
+        d = DeviceArray(self, n, dtype)
+        _chk(_lib.b200_memset(self.p, d.ptr, 0, max(1, d.n) * d.dtype.itemsize))
+        return d
+
+    def dot(self, x, y):
+        r = _d()
+        _chk(_lib.b200_vec_dot(self.p, x.n, x.ptr, y.ptr, C.byref(r)))
+        return r.value
+
+    def axpy(self, a, x, y):
+        _chk(_lib.b200_vec_axpy(self.p, x.n, a, x.ptr, y.ptr))
+
+    def scale(self, a, y):
+        _chk(_lib.b200_vec_scale(self.p, y.n, a, y.ptr))
+
+    def fill(self, x, v):
+        _chk(_lib.b200_vec_fill(self.p, x.n, v, x.ptr))
+
+    def copy(self, x, y):
+        _chk(_lib.b200_vec_copy(self.p, x.n, x.ptr, y.ptr))
+
+    def timer_start(self):
+        _chk(_lib.b200_timer_start(self.p))
+
+    def timer_stop_ms(self):
+        ms = _d()
+        _chk(_lib.b200_timer_stop_ms(self.p, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self):
+        return _lib.b200_launch_count()
+
+    def strength(self, A, theta=0.25, max_row_sum=1.0):
+        p = _vp()
+        _chk(_lib.b200_strength(self.p, A.p, theta, max_row_sum, C.byref(p)))
+        return Csr(self, p)
+
+    def pmis(self, S, seed=2747):
+        n = S.dims[0]
+        cf = self.zeros(n, np.int32)
+        _chk(_lib.b200_pmis(self.p, S.p, seed, cf.ptr))
+        return cf
+
+    def extpi_interp(self, A, S, cf, trunc_factor=0.0, max_elmts=4):
+        p = _vp()
+        _chk(_lib.b200_extpi_interp(self.p, A.p, S.p, cf.ptr, trunc_factor, max_elmts, C.byref(p)))
+        return Csr(self, p)
+
+    def l1_norms(self, A, option=1):
+        n = A.dims[0]
+        d = self.empty(n)
+        _chk(_lib.b200_l1_norms(self.p, A.p, option, d.ptr))
+        return d
+
+    def pcg(self, A, amg, b, x, tol=1e-8, max_iter=100):
+        its = _i()
+        rel = _d()
+        norms = np.zeros(max_iter + 2, np.float64)
+        _chk(_lib.b200_pcg_solve(self.p, A.p, amg.p if amg is not None else None, b.ptr, x.ptr, tol, max_iter,
+                                 C.byref(its), C.byref(rel), _np_ptr(norms)))
+        return its.value, rel.value, norms[: its.value + 1]
+
+    def close(self):
+        if self.p:
+            _chk(_lib.b200_finalize(self.p))
+            self.p = None

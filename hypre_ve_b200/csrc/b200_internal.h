@@ -1,0 +1,95 @@
+// b200_internal.h -- shared declarations of libhypre_b200 (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include "../../include/hypre_b200.h"
+
+#define B200_NUM_SM_FALLBACK 148
+
+struct b200_handle_s {
+  int device = 0;
+  int num_sm = B200_NUM_SM_FALLBACK;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // scratch for reductions (dot products): partial sums + pinned host landing zone
+  double *d_partials = nullptr;
+  double *h_pinned = nullptr;   // 64 doubles, pinned
+  int     n_partials = 0;
+};
+
+// Device CSR block.  Arrays are over-allocated by B200_PAD entries so kernels may issue aligned
+// 128-bit loads that straddle the logical end.
+#define B200_PAD 8
+struct b200_csr_s {
+  int nrows = 0, ncols = 0, nnz = 0;
+  int *i = nullptr;       // [nrows+1]
+  int *j = nullptr;       // [nnz (+pad)]
+  double *a = nullptr;    // [nnz (+pad)]  (nullptr for pattern-only matrices such as S)
+  bool owns = true;
+  // streaming-SpMV plan: block b owns rows [blk_row[b], blk_row[b+1])
+  int *blk_row = nullptr;
+  int  nblk = 0;
+  int  group = 1;         // threads cooperating on one row in the reduce phase
+  int  max_row = 0;
+};
+
+struct b200_halo_s;   // multi-rank halo plan (b200_parcsr.cu)
+
+struct b200_parcsr_s {
+  int global_rows = 0, global_cols = 0;
+  int first_row = 0, first_col = 0;          // this rank's first global row / col
+  b200_csr diag = nullptr;
+  b200_csr offd = nullptr;                   // may have 0 cols
+  int *col_map_offd = nullptr;               // device, sorted global ids [ncols_offd]
+  std::vector<int> h_col_map_offd;
+  b200_halo_s *halo = nullptr;
+  double *x_ghost = nullptr;                 // [ncols_offd]
+};
+
+extern thread_local std::string g_b200_err;
+extern long long g_b200_launches;
+
+int b200_set_error(const char *file, int line, const char *msg);
+
+#define B200_FAIL(msg) return b200_set_error(__FILE__, __LINE__, (msg))
+#define B200_CUDA(call)                                                         \
+  do {                                                                          \
+    cudaError_t e__ = (call);                                                   \
+    if (e__ != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+#define B200_TRY(call)                  \
+  do {                                  \
+    int rc__ = (call);                  \
+    if (rc__) return rc__;              \
+  } while (0)
+#define B200_LAUNCH_CHECK()                                                      \
+  do {                                                                           \
+    ++g_b200_launches;                                                           \
+    cudaError_t e__ = cudaGetLastError();                                        \
+    if (e__ != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); \
+  } while (0)
+
+// stream-ordered allocation helpers (cudaMallocAsync pool; freed memory stays cached in the pool)
+template <class T>
+static inline int b200_dalloc(b200_handle h, T **p, size_t count) {
+  *p = nullptr;
+  if (count == 0) count = 1;
+  B200_CUDA(cudaMallocAsync((void **)p, count * sizeof(T), h->stream));
+  return 0;
+}
+static inline int b200_dfree(b200_handle h, void *p) {
+  if (p) B200_CUDA(cudaFreeAsync(p, h->stream));
+  return 0;
+}
+static inline int b200_grid(size_t n, int block) { return (int)((n + block - 1) / block); }
+
+// internal cross-file entry points
+int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data, b200_csr *A);
+int b200_csr_build_plan(b200_handle h, b200_csr A);
+int b200_exclusive_scan_inplace(b200_handle h, int *d_data, size_t n);   // d_data[n] entries, in place
+int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);

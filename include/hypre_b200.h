@@ -1,0 +1,144 @@
+/* hypre_b200.h -- C-ABI of libhypre_b200.so: the B200-native (sm_100a) implementation of
+ * BoomerAMG's data-parallel hot path.
+ *
+ * Plain C, plain pointers and sizes: this is what a host build of hypre binds in place of its
+ * own `XDevice` operator seam (boundary B3).  Each entry point cites the reference
+ * function (file:line under /root/reference/src) whose behaviour it reproduces.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on error (b200_last_error() has the text);
+ *    there is NO CPU fallback: if the device or the kernels are unavailable the call fails.
+ *  - "d_" pointers are device pointers, "h_" pointers are host pointers.
+ *  - all reals are FP64 (HYPRE_Real=double), all indices int32 (HYPRE_Int=HYPRE_BigInt=int),
+ *    matching the reference configuration (utilities/HYPRE_utilities.h:48-49).
+ *  - all work is enqueued on the handle's CUDA stream; calls that return host scalars synchronise.
+ */
+#ifndef HYPRE_B200_H
+#define HYPRE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200_handle_s *b200_handle;
+typedef struct b200_csr_s    *b200_csr;     /* device CSR block            (seq_mv/csr_matrix.h:25-56)   */
+typedef struct b200_parcsr_s *b200_parcsr;  /* row-partitioned ParCSR      (parcsr_mv/par_csr_matrix.h:27-95) */
+typedef struct b200_amg_s    *b200_amg;     /* BoomerAMG hierarchy + parms (parcsr_ls/par_amg.h:18-271)  */
+
+/* ---- runtime (utilities/hypre_general.c:128 HYPRE_Init, hypre_memory.c) -------------------- */
+int         b200_init(int device, b200_handle *h);
+int         b200_finalize(b200_handle h);
+const char *b200_last_error(void);
+void       *b200_stream(b200_handle h);                 /* cudaStream_t */
+int         b200_sync(b200_handle h);
+int         b200_malloc(b200_handle h, void **d_ptr, size_t bytes);
+int         b200_free(b200_handle h, void *d_ptr);
+int         b200_memcpy_h2d(b200_handle h, void *d_dst, const void *h_src, size_t bytes);
+int         b200_memcpy_d2h(b200_handle h, void *h_dst, const void *d_src, size_t bytes);
+int         b200_memcpy_d2d(b200_handle h, void *d_dst, const void *d_src, size_t bytes);
+int         b200_memset(b200_handle h, void *d_dst, int byte, size_t bytes);
+/* number of kernels this library has launched since b200_init (bench.py gpu_launches) */
+long long   b200_launch_count(void);
+/* device-side elapsed-time helpers on the handle's stream (cudaEvent based) */
+int         b200_timer_start(b200_handle h);
+int         b200_timer_stop_ms(b200_handle h, double *ms);
+
+/* ---- sequential CSR kernels (seq_mv) ------------------------------------------------------- */
+/* wrap/copy device CSR arrays; builds the row-block plan the streaming SpMV uses */
+int b200_csr_create(b200_handle h, int nrows, int ncols, int nnz,
+                    const int *d_i, const int *d_j, const double *d_a, int copy, b200_csr *A);
+int b200_csr_create_from_host(b200_handle h, int nrows, int ncols, int nnz,
+                              const int *h_i, const int *h_j, const double *h_a, b200_csr *A);
+int b200_csr_destroy(b200_handle h, b200_csr A);
+int b200_csr_dims(b200_csr A, int *nrows, int *ncols, int *nnz);
+int b200_csr_download(b200_handle h, b200_csr A, int *h_i, int *h_j, double *h_a);
+/* y = alpha*A*x + beta*b, x != y.   hypre_CSRMatrixMatvecOutOfPlace (seq_mv/csr_matvec.c:24-412),
+ * device seam hypre_CSRMatrixMatvecDevice (seq_mv/csr_matvec_device.c:56-120). b may equal y. */
+int b200_csr_matvec(b200_handle h, double alpha, b200_csr A, const double *d_x,
+                    double beta, const double *d_b, double *d_y);
+/* AT = A^T with rows ordered by source row (stable counting sort semantics).
+ * hypre_CSRMatrixTransposeHost (seq_mv/csr_matop.c:578-779) */
+int b200_csr_transpose(b200_handle h, b200_csr A, b200_csr *AT);
+/* C = A*B, Gustavson row order: columns in first-touch order, values summed left to right,
+ * diagonal placed first when C is square.  hypre_CSRMatrixMultiplyHost (seq_mv/csr_matop.c:295-473) */
+int b200_csr_multiply(b200_handle h, b200_csr A, b200_csr B, b200_csr *C);
+
+/* ---- vector kernels (seq_mv/vector.c:238,:321,:394,:451,:511) ------------------------------ */
+int b200_vec_fill(b200_handle h, int n, double value, double *d_x);           /* SetConstantValues */
+int b200_vec_copy(b200_handle h, int n, const double *d_x, double *d_y);      /* Copy   */
+int b200_vec_scale(b200_handle h, int n, double alpha, double *d_y);          /* Scale  */
+int b200_vec_axpy(b200_handle h, int n, double alpha, const double *d_x, double *d_y); /* Axpy */
+int b200_vec_dot(b200_handle h, int n, const double *d_x, const double *d_y, double *h_result); /* InnerProd */
+
+/* ---- problem generators (parcsr_ls/par_laplace.c:15-357, par_laplace_27pt.c:15) ------------- */
+/* Row partition (P,Q,R) process grid, this rank at (p,q,r); same entry order as the reference:
+ * diagonal first, then z-,y-,x-,x+,y+,z+ (7-pt) resp. the 27-pt lexicographic order. */
+int b200_generate_laplacian(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
+                            int p, int q, int r, const double values[4], b200_parcsr *A);
+int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
+                              int p, int q, int r, const double values[2], b200_parcsr *A);
+
+/* ---- ParCSR (parcsr_mv) -------------------------------------------------------------------- */
+/* single-rank ParCSR from a host CSR (diag block = whole matrix); diagonal entry must be first
+ * in each row as in the reference's diag block (csr_matrix.h, relied on by relax/strength). */
+int b200_parcsr_create_from_host(b200_handle h, int nrows, int ncols, int nnz,
+                                 const int *h_i, const int *h_j, const double *h_a, b200_parcsr *A);
+int b200_parcsr_destroy(b200_handle h, b200_parcsr A);
+int b200_parcsr_local_rows(b200_parcsr A, int *nrows, int *nnz_diag, int *nnz_offd, int *ncols_offd);
+b200_csr b200_parcsr_diag(b200_parcsr A);
+b200_csr b200_parcsr_offd(b200_parcsr A);
+/* y = alpha*A*x + beta*b over diag+offd with halo exchange of x.
+ * hypre_ParCSRMatrixMatvecOutOfPlace (parcsr_mv/par_csr_matvec.c:22-359) */
+int b200_parcsr_matvec(b200_handle h, double alpha, b200_parcsr A, const double *d_x,
+                       double beta, const double *d_b, double *d_y);
+
+/* ---- BoomerAMG (parcsr_ls) ------------------------------------------------------------------ */
+int b200_amg_create(b200_amg *amg);                      /* HYPRE_BoomerAMGCreate  (HYPRE_parcsr_amg.c:15)  */
+int b200_amg_destroy(b200_handle h, b200_amg amg);       /* HYPRE_BoomerAMGDestroy (:32) */
+/* integer / real parameters by the reference setter's name without the HYPRE_BoomerAMGSet prefix:
+ * "CoarsenType","InterpType","PMaxElmts","RelaxType","MaxLevels","MaxCoarseSize","NumSweeps",
+ * "AggNumLevels","ModuleRAP2","KeepTranspose","RelaxOrder","MaxIter" / "StrongThreshold",
+ * "MaxRowSum","TruncFactor","RelaxWt","Tol".  Unsupported values are rejected at setup. */
+int b200_amg_set_int(b200_amg amg, const char *name, int value);
+int b200_amg_set_real(b200_amg amg, const char *name, double value);
+/* hypre_BoomerAMGSetup (par_amg_setup.c:27-3518) for the in-scope configuration */
+int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr A);
+/* one application of the preconditioner: hypre_BoomerAMGSolve with MaxIter=1, Tol=0
+ * (par_amg_solve.c:21) = one hypre_BoomerAMGCycle (par_cycle.c:22-641); u is overwritten */
+int b200_amg_solve(b200_handle h, b200_amg amg, const double *d_f, double *d_u);
+int b200_amg_num_levels(b200_amg amg);
+/* hierarchy access for parity tests (device objects owned by amg) */
+b200_csr b200_amg_level_A(b200_amg amg, int level);
+b200_csr b200_amg_level_P(b200_amg amg, int level);
+b200_csr b200_amg_level_S(b200_amg amg, int level);      /* kept only if "KeepS" = 1 */
+const int    *b200_amg_level_CF(b200_amg amg, int level); /* device int[nrows_l]  */
+const double *b200_amg_level_l1(b200_amg amg, int level); /* device double[nrows_l] */
+/* per-phase device times of the last setup, ms: strength, pmis, interp, trunc, transpose, rap, other */
+int b200_amg_setup_times(b200_amg amg, double times[8]);
+
+/* individual setup stages, exposed so each can be parity-tested against the reference */
+/* hypre_BoomerAMGCreateSHost (par_strength.c:80-530): S has no diagonal, A's column order */
+int b200_strength(b200_handle h, b200_csr A, double theta, double max_row_sum, b200_csr *S);
+/* hypre_BoomerAMGCoarsenPMISHost (par_coarsen.c:2031-2738) + IndepSetInit (par_indepset.c:32-63)
+ * + hypre_Rand (utilities/random.c:49-106); writes CF marker {1,-1,-3} */
+int b200_pmis(b200_handle h, b200_csr S, int seed, int *d_cf);
+/* hypre_BoomerAMGBuildExtPIInterpHost (par_lr_interp.c:1040-1925) followed by
+ * hypre_BoomerAMGInterpTruncation (par_interp.c:2718 -> par_csr_matrix.c:2671-3060) */
+int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf,
+                      double trunc_factor, int max_elmts, b200_csr *P);
+/* hypre_ParCSRComputeL1Norms (ams.c:571-760), options 1 and 4 */
+int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
+
+/* ---- PCG (krylov/pcg.c:271-757 via HYPRE_ParCSRPCGSolve) ------------------------------------- */
+/* Solves A x = b with BoomerAMG-preconditioned CG (amg may be NULL: unpreconditioned).
+ * two_norm=1 convergence test ||r||_2/||b||_2 < tol as ij.c:3894 sets.  h_norms (may be NULL)
+ * receives ||r_k||_2 for k=0..iters (needs max_iter+1 doubles). */
+int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x,
+                   double tol, int max_iter, int *iters, double *final_rel_res, double *h_norms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYPRE_B200_H */
