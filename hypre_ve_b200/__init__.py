@@ -158,13 +158,14 @@ class Csr:
         self.h, self.p, self.owned = handle, p, owned
 
     @classmethod
-    def from_host(cls, handle, indptr, indices, data):
+    def from_host(cls, handle, indptr, indices, data, ncols=None):
         indptr = np.ascontiguousarray(indptr, dtype=np.int32)
         indices = np.ascontiguousarray(indices, dtype=np.int32)
         data = None if data is None else np.ascontiguousarray(data, dtype=np.float64)
         p = _vp()
         nrows = indptr.size - 1
-        ncols = int(indices.max()) + 1 if indices.size else 0
+        if ncols is None:
+            ncols = int(indices.max()) + 1 if indices.size else 0
         _chk(_lib.b200_csr_create_from_host(handle.p, nrows, ncols, indices.size, _np_ptr(indptr), _np_ptr(indices),
                                             _np_ptr(data) if data is not None else None, C.byref(p)))
         return cls(handle, p)

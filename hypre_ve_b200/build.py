@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Build libhypre_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Setup kernels (b200_setup*.cu) are compiled with -fmad=false: the reference CPU build
-(gcc -O2, x86-64 baseline) emits no fused multiply-adds, and bit-exact interpolation
-sparsity needs bit-exact weights.
+Everything is compiled with -fmad=false: the reference CPU build (gcc -O2, x86-64 baseline)
+emits no fused multiply-adds, and bit-exact interpolation sparsity needs bit-exact weights
+(SURVEY.md 7.3-1).  The solve kernels are HBM-bound, so separate mul/add costs nothing there and
+keeps the residual history closer to the reference's.
 """
 import concurrent.futures as cf
 import glob
@@ -37,7 +38,7 @@ def build(verbose=False, force=False):
         o = os.path.join(OBJ, os.path.basename(s).rsplit(".", 1)[0] + ".o")
         objs.append(o)
         if force or newer(s, o, deps):
-            extra = ["-fmad=false"] if "setup" in os.path.basename(s) else []
+            extra = ["-fmad=false"]
             if verbose:
                 extra += ["-Xptxas", "-v"]
             jobs.append([NVCC] + ARCH + COMMON + extra + ["-x", "cu", "-c", s, "-o", o])

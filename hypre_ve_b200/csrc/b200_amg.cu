@@ -1,23 +1,475 @@
-// placeholder: filled in by the AMG milestone
+// b200_amg.cu -- BoomerAMG hierarchy driver, V-cycle and PCG on the device.
+//
+// Reference: hypre_BoomerAMGSetup (parcsr_ls/par_amg_setup.c:27-3518), hypre_BoomerAMGCycle
+// (par_cycle.c:22-641), l1-Jacobi hypre_ParCSRRelax type 1 (ams.c:41-100), hypre_GaussElimSetup /
+// Solve (par_gauss_elim.c:20-330, gselim.h), hypre_PCGSolve (krylov/pcg.c:271-757).
+//
+// In-scope configuration (everything else is rejected loudly at setup):
+//   coarsen_type 8 (PMIS), interp_type 6 (ext+i) with trunc_factor / P_max_elmts,
+//   Galerkin product by two SpGEMMs (hypre_ParCSRMatrixRAPKT, mod_rap2 path),
+//   relax_type 18 (l1-Jacobi, relax_order 0) on all levels, relax 9 (Gaussian elimination)
+//   on the coarsest, V(1,1) cycle, explicit restriction R = P^T (keepTranspose semantics).
 #include "b200_internal.h"
-#define NI(name) B200_FAIL(name ": not implemented yet")
-extern "C" int b200_csr_transpose(b200_handle, b200_csr, b200_csr *) { NI("transpose"); }
-extern "C" int b200_csr_multiply(b200_handle, b200_csr, b200_csr, b200_csr *) { NI("multiply"); }
-extern "C" int b200_amg_create(b200_amg *) { NI("amg"); }
-extern "C" int b200_amg_destroy(b200_handle, b200_amg) { NI("amg"); }
-extern "C" int b200_amg_set_int(b200_amg, const char *, int) { NI("amg"); }
-extern "C" int b200_amg_set_real(b200_amg, const char *, double) { NI("amg"); }
-extern "C" int b200_amg_setup(b200_handle, b200_amg, b200_parcsr) { NI("amg"); }
-extern "C" int b200_amg_solve(b200_handle, b200_amg, const double *, double *) { NI("amg"); }
-extern "C" int b200_amg_num_levels(b200_amg) { return 0; }
-extern "C" b200_csr b200_amg_level_A(b200_amg, int) { return nullptr; }
-extern "C" b200_csr b200_amg_level_P(b200_amg, int) { return nullptr; }
-extern "C" b200_csr b200_amg_level_S(b200_amg, int) { return nullptr; }
-extern "C" const int *b200_amg_level_CF(b200_amg, int) { return nullptr; }
-extern "C" const double *b200_amg_level_l1(b200_amg, int) { return nullptr; }
-extern "C" int b200_amg_setup_times(b200_amg, double *) { NI("amg"); }
-extern "C" int b200_strength(b200_handle, b200_csr, double, double, b200_csr *) { NI("strength"); }
-extern "C" int b200_pmis(b200_handle, b200_csr, int, int *) { NI("pmis"); }
-extern "C" int b200_extpi_interp(b200_handle, b200_csr, b200_csr, const int *, double, int, b200_csr *) { NI("interp"); }
-extern "C" int b200_l1_norms(b200_handle, b200_csr, int, double *) { NI("l1"); }
-extern "C" int b200_pcg_solve(b200_handle, b200_parcsr, b200_amg, const double *, double *, double, int, int *, double *, double *) { NI("pcg"); }
+#include <cmath>
+#include <map>
+
+int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha,
+                      double beta, const double *b, const double *d);
+int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int *d_cf, int *iterations);
+int b200_vec_dot_dev(b200_handle h, int n, const double *x, const double *y, double *d_out);
+
+struct b200_level {
+  b200_csr A = nullptr;     // owned except level 0 (borrowed from the caller's ParCSR diag block)
+  b200_csr P = nullptr;     // interpolation to this level from the next coarser one
+  b200_csr R = nullptr;     // P^T
+  b200_csr S = nullptr;     // kept only when KeepS
+  int *cf = nullptr;        // CF marker {1,-1}
+  double *l1 = nullptr;     // l1 norms
+  double *F = nullptr, *U = nullptr, *T = nullptr;   // rhs, iterate, ping-pong iterate (levels >= 1; T also level 0)
+  int n = 0;
+};
+
+struct b200_amg_s {
+  std::map<std::string, int> ip;
+  std::map<std::string, double> rp;
+  std::vector<b200_level> lv;
+  double *Vtemp = nullptr;        // residual scratch, size of level 0
+  double *ge_A = nullptr;         // dense coarsest matrix (row-major n x n) + work copy + rhs
+  int ge_n = 0;
+  bool coarse_ge = false;
+  double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool is_setup = false;
+  b200_amg_s() {
+    // library defaults that matter on this path = the values ij.c passes for `-solver 1`
+    // (test/ij.c:203-330, :1181-1205) with the north-star choices -pmis -rlx 18 -mod_rap2 1
+    ip = {{"CoarsenType", 8}, {"InterpType", 6}, {"PMaxElmts", 4}, {"RelaxType", 18}, {"MaxLevels", 25},
+          {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"NumSweeps", 1}, {"AggNumLevels", 0}, {"ModuleRAP2", 1},
+          {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
+          {"NumFunctions", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
+    rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
+          {"OuterWt", 1.0}, {"Tol", 0.0}};
+  }
+};
+
+namespace {
+
+__global__ void fix_cf_kernel(int n, int *cf) {                     // par_lr_interp.c:1888-1894
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && cf[i] == -3) cf[i] = -1;
+}
+__global__ void count_c_kernel(int n, const int *__restrict__ cf, int *count) {   // par_coarse_parms.c:83-86
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int g = (i < n && cf[i] == 1) ? 1 : 0;
+  unsigned b = __ballot_sync(0xffffffffu, g);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
+__global__ void dense_from_csr_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                      const double *__restrict__ A_a, double *__restrict__ M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < n; k++) M[i * n + k] = 0.0;
+  for (int jj = A_i[i]; jj < A_i[i + 1]; jj++) M[i * n + A_j[jj]] = A_a[jj];     // par_gauss_elim.c:100-115
+}
+// hypre_gselim (sstruct_ls/gselim.h) on a scratch copy; one thread, n <= MaxCoarseSize
+__global__ void gselim_kernel(int n, const double *__restrict__ A_mat, double *__restrict__ A, const double *__restrict__ f,
+                              double *__restrict__ x) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < n * n; i++) A[i] = A_mat[i];
+  for (int i = 0; i < n; i++) x[i] = f[i];
+  if (n == 1) {
+    if (A[0] != 0.0) x[0] = x[0] / A[0];
+    return;
+  }
+  for (int k = 0; k < n - 1; k++) {
+    if (A[k * n + k] != 0.0) {
+      double divA = 1.0 / A[k * n + k];
+      for (int j = k + 1; j < n; j++) {
+        if (A[j * n + k] != 0.0) {
+          double factor = A[j * n + k] * divA;
+          for (int m = k + 1; m < n; m++) A[j * n + m] -= factor * A[k * n + m];
+          x[j] -= factor * x[k];
+        }
+      }
+    }
+  }
+  for (int k = n - 1; k > 0; --k) {
+    if (A[k * n + k] != 0.0) {
+      x[k] /= A[k * n + k];
+      for (int j = 0; j < k; j++)
+        if (A[j * n + k] != 0.0) x[j] -= x[k] * A[j * n + k];
+    }
+  }
+  if (A[0] != 0.0) x[0] /= A[0];
+}
+// u = f / l1  (l1-Jacobi sweep from a zero iterate: u + w*(f - A*0)/l1, exact)
+__global__ void jacobi_zero_kernel(size_t n, double w, const double *__restrict__ f, const double *__restrict__ l1,
+                                   double *__restrict__ u) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) u[i] = 0.0 + w * f[i] / l1[i];
+}
+// PCG vector updates with device-resident scalars (no host round trip between kernels)
+// sc[0]=gamma sc[1]=sdotp sc[2]=gamma_old sc[3]=i_prod sc[4]=alpha sc[5]=beta
+__global__ void pcg_alpha_kernel(double *sc) {
+  sc[4] = sc[0] / sc[1];          // alpha = gamma / <s,p>         (pcg.c:522)
+  sc[2] = sc[0];                  // gamma_old = gamma             (pcg.c:530)
+}
+__global__ void pcg_update_xr_kernel(size_t n, const double *__restrict__ sc, const double *__restrict__ p,
+                                     const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
+  const double alpha = sc[4];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    x[i] += alpha * p[i];         // pcg.c:534
+    r[i] += -alpha * s[i];        // pcg.c:539
+  }
+}
+__global__ void pcg_beta_kernel(double *sc) { sc[5] = sc[0] / sc[2]; }   // beta = gamma / gamma_old (pcg.c:729)
+__global__ void pcg_update_p_kernel(size_t n, const double *__restrict__ sc, const double *__restrict__ s,
+                                    double *__restrict__ p) {
+  const double beta = sc[5];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = beta * p[i] + 1.0 * s[i];   // Scale then Axpy (pcg.c:734-735)
+}
+
+inline int vgrid(b200_handle h, size_t n) {
+  size_t g = (n + 255) / 256, cap = (size_t)h->num_sm * 8;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+struct PhaseTimer {
+  b200_handle h;
+  cudaEvent_t a, b;
+  PhaseTimer(b200_handle hh) : h(hh) { cudaEventCreate(&a); cudaEventCreate(&b); }
+  ~PhaseTimer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+  void start() { cudaEventRecord(a, h->stream); }
+  double stop() {
+    cudaEventRecord(b, h->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+  }
+};
+
+}  // namespace
+
+extern "C" int b200_amg_create(b200_amg *out) {
+  *out = new b200_amg_s();
+  return 0;
+}
+
+static int free_levels(b200_handle h, b200_amg amg) {
+  for (size_t l = 0; l < amg->lv.size(); l++) {
+    b200_level &L = amg->lv[l];
+    if (l > 0) B200_TRY(b200_csr_destroy(h, L.A));
+    B200_TRY(b200_csr_destroy(h, L.P));
+    B200_TRY(b200_csr_destroy(h, L.R));
+    B200_TRY(b200_csr_destroy(h, L.S));
+    B200_TRY(b200_dfree(h, L.cf)); B200_TRY(b200_dfree(h, L.l1));
+    B200_TRY(b200_dfree(h, L.F)); B200_TRY(b200_dfree(h, L.U)); B200_TRY(b200_dfree(h, L.T));
+  }
+  amg->lv.clear();
+  B200_TRY(b200_dfree(h, amg->Vtemp)); amg->Vtemp = nullptr;
+  B200_TRY(b200_dfree(h, amg->ge_A)); amg->ge_A = nullptr;
+  amg->is_setup = false;
+  return 0;
+}
+
+extern "C" int b200_amg_destroy(b200_handle h, b200_amg amg) {
+  if (!amg) return 0;
+  B200_TRY(free_levels(h, amg));
+  delete amg;
+  return 0;
+}
+
+extern "C" int b200_amg_set_int(b200_amg amg, const char *name, int value) {
+  if (!amg) B200_FAIL("null amg");
+  if (!amg->ip.count(name)) B200_FAIL((std::string("unknown integer parameter ") + name).c_str());
+  amg->ip[name] = value;
+  return 0;
+}
+extern "C" int b200_amg_set_real(b200_amg amg, const char *name, double value) {
+  if (!amg) B200_FAIL("null amg");
+  if (!amg->rp.count(name)) B200_FAIL((std::string("unknown real parameter ") + name).c_str());
+  amg->rp[name] = value;
+  return 0;
+}
+
+extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
+  if (!amg || !Apar) B200_FAIL("amg_setup: null argument");
+  if (Apar->offd->ncols > 0) B200_FAIL("amg_setup: multi-rank setup not built yet (offd block must be empty)");
+  auto &ip = amg->ip;
+  auto &rp = amg->rp;
+  if (ip["CoarsenType"] != 8) B200_FAIL("only CoarsenType 8 (PMIS) is implemented on the B200 path");
+  if (ip["InterpType"] != 6) B200_FAIL("only InterpType 6 (extended+i) is implemented on the B200 path");
+  if (ip["RelaxType"] != 18) B200_FAIL("only RelaxType 18 (l1-Jacobi) is implemented on the B200 path");
+  if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
+  if (ip["AggNumLevels"] != 0) B200_FAIL("aggressive coarsening is not implemented on the B200 path");
+  if (ip["NumSweeps"] != 1 || ip["CycleType"] != 1) B200_FAIL("only V(1,1) cycles are implemented");
+  if (ip["NumFunctions"] != 1) B200_FAIL("only scalar problems (NumFunctions 1)");
+  if (!(ip["ModuleRAP2"] == 1 && ip["RAP2"] == 0))
+    B200_FAIL("only the modularized Galerkin product (ModuleRAP2 1, RAP2 0: hypre_ParCSRMatrixRAPKT) is implemented");
+  B200_TRY(free_levels(h, amg));
+  for (double &t : amg->times) t = 0;
+  PhaseTimer tm(h), total(h);
+  total.start();
+
+  const double theta = rp["StrongThreshold"], mrs = rp["MaxRowSum"], trunc = rp["TruncFactor"];
+  const int pmax = ip["PMaxElmts"], max_levels = ip["MaxLevels"], max_coarse = ip["MaxCoarseSize"];
+  const int min_coarse = ip["MinCoarseSize"], keepS = ip["KeepS"], seed = ip["Seed"];
+
+  b200_level L0;
+  L0.A = Apar->diag;
+  L0.n = Apar->diag->nrows;
+  amg->lv.push_back(L0);
+  int level = 0;
+  bool not_finished = max_levels > 1;
+  int *d_count = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &d_count, 1));
+  while (not_finished) {                                   // par_amg_setup.c:889
+    b200_level &L = amg->lv[level];
+    const int fine_size = L.n;
+    b200_csr S = nullptr;
+    tm.start();
+    B200_TRY(b200_strength(h, L.A, theta, mrs, &S));       // :1035
+    amg->times[0] += tm.stop();
+    int *cf = nullptr;
+    B200_TRY(b200_dalloc<int>(h, &cf, fine_size));
+    tm.start();
+    B200_TRY(b200_pmis_rows(h, S, seed, 0, cf, nullptr));  // :1114
+    amg->times[1] += tm.stop();
+    B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
+    count_c_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf, d_count);
+    B200_LAUNCH_CHECK();
+    int coarse_size = 0;
+    B200_CUDA(cudaMemcpyAsync(&coarse_size, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (coarse_size == 0 || coarse_size == fine_size || coarse_size < min_coarse) {   // :1487-1560
+      B200_TRY(b200_csr_destroy(h, S));
+      B200_TRY(b200_dfree(h, cf));
+      break;
+    }
+    tm.start();
+    b200_csr P = nullptr;
+    B200_TRY(b200_extpi_interp(h, L.A, S, cf, trunc, pmax, &P));   // :1989
+    amg->times[2] += tm.stop();
+    fix_cf_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf);
+    B200_LAUNCH_CHECK();
+    L.cf = cf;
+    L.P = P;
+    if (keepS) L.S = S; else B200_TRY(b200_csr_destroy(h, S));
+    // Galerkin product, hypre_ParCSRMatrixRAPKTHost single-rank branch (par_csr_triplemat.c:872-888):
+    //   Q = A*P ; RT = P^T ; C = RT*Q
+    tm.start();
+    b200_csr R = nullptr;
+    B200_TRY(b200_csr_transpose(h, P, &R));
+    amg->times[4] += tm.stop();
+    tm.start();
+    b200_csr Q = nullptr, AH = nullptr;
+    B200_TRY(b200_csr_multiply(h, L.A, P, &Q));
+    B200_TRY(b200_csr_multiply(h, R, Q, &AH));
+    B200_TRY(b200_csr_destroy(h, Q));
+    amg->times[5] += tm.stop();
+    L.R = R;
+    b200_level Ln;
+    Ln.A = AH;
+    Ln.n = AH->nrows;
+    amg->lv.push_back(Ln);
+    ++level;
+    if (level == max_levels - 1 || coarse_size <= max_coarse) not_finished = false;   // :2884-2888
+    if (not_finished && (double)coarse_size >= 0.75 * (double)fine_size)              // :2873-2877
+      B200_FAIL("coarsening stalled (coarse >= 0.75 fine): the reference switches to CLJP here, which is out of scope");
+  }
+  B200_TRY(b200_dfree(h, d_count));
+
+  const int nl = (int)amg->lv.size();
+  // coarsest level: Gaussian elimination if small enough, else fall back to the smoother (:2909-2921)
+  b200_level &Lc = amg->lv[nl - 1];
+  amg->coarse_ge = Lc.n <= max_coarse && Lc.n > 0;
+  if (amg->coarse_ge) {
+    amg->ge_n = Lc.n;
+    B200_TRY(b200_dalloc<double>(h, &amg->ge_A, (size_t)2 * Lc.n * Lc.n));
+    dense_from_csr_kernel<<<b200_grid(Lc.n, 128), 128, 0, h->stream>>>(Lc.n, Lc.A->i, Lc.A->j, Lc.A->a, amg->ge_A);
+    B200_LAUNCH_CHECK();
+  }
+  // l1 norms, option 1 for relax 18 (:3045-3060)
+  tm.start();
+  for (int l = 0; l < nl; l++) {
+    b200_level &L = amg->lv[l];
+    if (l < nl - 1 || !amg->coarse_ge) {
+      B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
+      B200_TRY(b200_l1_norms(h, L.A, 1, L.l1));
+    }
+    if (l > 0) {
+      B200_TRY(b200_dalloc<double>(h, &L.F, L.n));
+      B200_TRY(b200_dalloc<double>(h, &L.U, L.n));
+    }
+    B200_TRY(b200_dalloc<double>(h, &L.T, L.n));
+  }
+  B200_TRY(b200_dalloc<double>(h, &amg->Vtemp, amg->lv[0].n));
+  amg->times[6] += tm.stop();
+  amg->times[7] = total.stop();
+  amg->is_setup = true;
+  return 0;
+}
+
+extern "C" int b200_amg_num_levels(b200_amg amg) { return amg ? (int)amg->lv.size() : 0; }
+extern "C" b200_csr b200_amg_level_A(b200_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].A : nullptr; }
+extern "C" b200_csr b200_amg_level_P(b200_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].P : nullptr; }
+extern "C" b200_csr b200_amg_level_S(b200_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].S : nullptr; }
+extern "C" const int *b200_amg_level_CF(b200_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].cf : nullptr; }
+extern "C" const double *b200_amg_level_l1(b200_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].l1 : nullptr; }
+extern "C" int b200_amg_setup_times(b200_amg amg, double *t) {
+  if (!amg) B200_FAIL("null amg");
+  for (int i = 0; i < 8; i++) t[i] = amg->times[i];
+  return 0;
+}
+
+// One l1-Jacobi sweep u_out = u_in + w (f - A u_in) / l1   (ams.c:72-92, fused into one pass over A)
+static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const double *u_in, double *u_out) {
+  return b200_csr_spmv_epi(h, L.A, u_in, u_out, 1, w, 0.0, f, L.l1);
+}
+
+// One V(1,1) cycle (par_cycle.c:255-622). u_zero: the caller guarantees u == 0 on entry
+// (PCG clears the vector before every preconditioner application, pcg.c:434,:568), which lets
+// the first sweep on every level skip its SpMV: u + (f - A*0)/l1 == f/l1 exactly.
+static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bool u_zero) {
+  const int nl = (int)amg->lv.size();
+  const double w = amg->rp["RelaxWt"];
+  // level 0 buffers: the final post-smoothing sweep must land in the caller's u
+  std::vector<const double *> F(nl);
+  std::vector<double *> U(nl);          // current iterate per level after pre-smoothing
+  F[0] = f;
+  for (int l = 1; l < nl; l++) F[l] = amg->lv[l].F;
+  if (nl == 1) {
+    b200_level &L = amg->lv[0];
+    if (amg->coarse_ge) {
+      gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, f, u);
+      B200_LAUNCH_CHECK();
+      return 0;
+    }
+    B200_TRY(jacobi(h, L, w, f, u, L.T));
+    B200_TRY(b200_vec_copy(h, L.n, L.T, u));
+    return 0;
+  }
+  for (int l = 0; l < nl - 1; l++) {
+    b200_level &L = amg->lv[l];
+    b200_level &Lc = amg->lv[l + 1];
+    double *ucur;
+    const bool zero = (l > 0) || u_zero;          // coarse iterates start at 0 (par_cycle.c:538)
+    if (l == 0) {
+      ucur = L.T;                                 // pre-smoothed iterate lives in T so the last sweep can write u
+      if (zero) {
+        jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, f, L.l1, ucur);
+        B200_LAUNCH_CHECK();
+      } else {
+        B200_TRY(jacobi(h, L, w, f, u, ucur));
+      }
+    } else {
+      ucur = L.U;
+      jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, ucur);
+      B200_LAUNCH_CHECK();
+    }
+    U[l] = ucur;
+    // Vtemp = F - A U (par_cycle.c:549) ; F_{l+1} = R Vtemp (:566)
+    B200_TRY(b200_csr_spmv_epi(h, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
+    B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr));
+  }
+  // coarsest level
+  {
+    b200_level &L = amg->lv[nl - 1];
+    if (amg->coarse_ge) {
+      gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, L.F, L.U);
+      B200_LAUNCH_CHECK();
+    } else {
+      jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, L.F, L.l1, L.U);
+      B200_LAUNCH_CHECK();
+    }
+    U[nl - 1] = L.U;
+  }
+  for (int l = nl - 2; l >= 0; l--) {
+    b200_level &L = amg->lv[l];
+    // U_l += P U_{l+1} (:602), in place: row r reads and writes only U_l[r]
+    B200_TRY(b200_csr_spmv_epi(h, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));
+    // post-smoothing sweep
+    double *dst = (l == 0) ? u : L.T;
+    B200_TRY(jacobi(h, L, w, F[l], U[l], dst));
+    if (l > 0) { std::swap(L.U, L.T); U[l] = L.U; }
+  }
+  return 0;
+}
+
+extern "C" int b200_amg_solve(b200_handle h, b200_amg amg, const double *d_f, double *d_u) {
+  if (!amg || !amg->is_setup) B200_FAIL("amg_solve: setup has not been called");
+  if (amg->ip["MaxIter"] != 1 || amg->rp["Tol"] != 0.0)
+    B200_FAIL("amg_solve: only the preconditioner configuration MaxIter 1 / Tol 0 is implemented");
+  return amg_cycle(h, amg, d_f, d_u, false);
+}
+
+// hypre_PCGSolve (krylov/pcg.c:271-757), two_norm = 1, rel_change = 0, default stop criteria.
+extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x, double tol,
+                              int max_iter, int *iters_out, double *final_rel_res, double *h_norms) {
+  if (!A) B200_FAIL("pcg: null matrix");
+  if (A->offd->ncols > 0) B200_FAIL("pcg: multi-rank solve not built yet");
+  if (amg && !amg->is_setup) B200_FAIL("pcg: preconditioner has not been set up");
+  const int n = A->diag->nrows;
+  double *p = nullptr, *s = nullptr, *r = nullptr, *sc = nullptr;
+  B200_TRY(b200_dalloc<double>(h, &p, n));
+  B200_TRY(b200_dalloc<double>(h, &s, n));
+  B200_TRY(b200_dalloc<double>(h, &r, n));
+  B200_TRY(b200_dalloc<double>(h, &sc, 8));
+  double *hs = h->h_pinned;
+  auto precond = [&](const double *rhs, double *out) -> int {
+    if (amg) return amg_cycle(h, amg, rhs, out, true);    // ClearVector + precond (pcg.c:434-435,:568-569)
+    return b200_vec_copy(h, n, rhs, out);                 // identity preconditioner
+  };
+  int rc = 0, i = 0;
+  double bi_prod = 0, i_prod = 0, eps = 0;
+  do {
+    if ((rc = b200_vec_dot(h, n, d_b, d_b, &bi_prod))) break;             // :347
+    eps = tol * tol;                                                        // :383, a_tol = 0
+    if (!(bi_prod > 0.0)) {                                                 // :403-416  b == 0 -> x = b
+      if ((rc = b200_vec_copy(h, n, d_b, d_x))) break;
+      if (h_norms) h_norms[0] = 0.0;
+      break;
+    }
+    // r = b - A x (:428-430)
+    if ((rc = b200_parcsr_matvec(h, -1.0, A, d_x, 1.0, d_b, r))) break;
+    if ((rc = precond(r, p))) break;                                        // p = C r
+    if ((rc = b200_vec_dot_dev(h, n, r, p, sc + 0))) break;                 // gamma = <r,p> (:438)
+    if (h_norms) {
+      double i_prod_0 = 0;
+      if ((rc = b200_vec_dot(h, n, r, r, &i_prod_0))) break;                // :466
+      h_norms[0] = std::sqrt(i_prod_0);
+    }
+    while ((i + 1) <= max_iter) {                                           // :498
+      i++;
+      if ((rc = b200_parcsr_matvec(h, 1.0, A, p, 0.0, nullptr, s))) break;  // s = A p (:512)
+      if ((rc = b200_vec_dot_dev(h, n, s, p, sc + 1))) break;               // sdotp (:515)
+      pcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
+      ++g_b200_launches;
+      pcg_update_xr_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, p, s, d_x, r);
+      ++g_b200_launches;
+      if ((rc = precond(r, s))) break;                                      // s = C r (:568-569)
+      if ((rc = b200_vec_dot_dev(h, n, r, s, sc + 0))) break;               // gamma = <r,s> (:572)
+      if ((rc = b200_vec_dot_dev(h, n, r, r, sc + 3))) break;               // i_prod = <r,r> (:590)
+      cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+      if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = b200_set_error(__FILE__, __LINE__, "pcg sync failed"); break; }
+      const double gamma = hs[0], sdotp = hs[1];
+      i_prod = hs[3];
+      if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }   // :516-521
+      if (h_norms) h_norms[i] = std::sqrt(i_prod);
+      if (i_prod / bi_prod < eps) break;                                    // converged (:634, :672-676)
+      if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
+      pcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
+      ++g_b200_launches;
+      pcg_update_p_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, s, p);
+      ++g_b200_launches;
+    }
+  } while (0);
+  if (!rc) {
+    if (iters_out) *iters_out = i;
+    if (final_rel_res) *final_rel_res = bi_prod > 0.0 ? std::sqrt(i_prod / bi_prod) : 0.0;   // :751-754
+  }
+  b200_dfree(h, p); b200_dfree(h, s); b200_dfree(h, r); b200_dfree(h, sc);
+  return rc;
+}
