@@ -1,0 +1,560 @@
+/* amg_oracle.c -- CPU RESTATEMENT (port) of the reference's hot path.  TEST INFRASTRUCTURE ONLY:
+ * nothing under hypre_ve_b200/ includes, links or executes this file.
+ *
+ * A plain sequential C restatement of BoomerAMG-PCG for the in-scope configuration
+ * (single rank, PMIS, ext+i interpolation with P_max_elmts truncation, modularized Galerkin
+ * product, l1-Jacobi V(1,1), Gaussian elimination on the coarsest grid, PCG with the 2-norm test).
+ * Every routine cites the reference lines it follows (paths under /root/reference/src).
+ *
+ * PINNED: tests/test_oracle.py checks this program's output bit for bit (integers AND doubles)
+ * against the golden dumps in tests/golden/, which were produced by the reference's own CPU build
+ * (oracle/_ref/ref_dump, see tests/golden/make_golden.py), and -- where oracle/_ref exists --
+ * against live reference runs.
+ *
+ * CLI and output format are those of oracle/ref_dump.c so the two can be diffed record by record.
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off: no FMA, like the reference's x86-64 build)
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+typedef struct { int n, m, nnz; int *i, *j; double *a; } csr_t;
+
+static void *xmalloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fprintf(stderr, "oom\n"); exit(1); } return p; }
+static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) { fprintf(stderr, "oom\n"); exit(1); } return p; }
+static csr_t csr_new(int n, int m, int nnz, int with_data)
+{
+   csr_t A; A.n = n; A.m = m; A.nnz = nnz;
+   A.i = (int *) xcalloc((size_t) n + 1, sizeof(int));
+   A.j = (int *) xmalloc(sizeof(int) * (size_t) nnz);
+   A.a = with_data ? (double *) xmalloc(sizeof(double) * (size_t) nnz) : NULL;
+   return A;
+}
+static void csr_free(csr_t *A) { free(A->i); free(A->j); free(A->a); A->i = A->j = NULL; A->a = NULL; }
+
+/* ---- generators: parcsr_ls/par_laplace.c:124-300 (7-pt: centre, z-,y-,x-,x+,y+,z+) and
+ *      parcsr_ls/par_laplace_27pt.c fill pass (centre, then (dz,dy,dx) lexicographic), 1 rank ---- */
+static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
+{
+   int n = nx * ny * nz, pass, ix, iy, iz, k;
+   csr_t A; memset(&A, 0, sizeof A);
+   for (pass = 0; pass < 2; pass++)
+   {
+      int cnt = 0, row = 0;
+      for (iz = 0; iz < nz; iz++) for (iy = 0; iy < ny; iy++) for (ix = 0; ix < nx; ix++, row++)
+      {
+         if (pass) A.i[row] = cnt;
+         int ns = pt27 ? 27 : 7;
+         for (k = 0; k < ns; k++)
+         {
+            int dx, dy, dz; double val;
+            if (!pt27)
+            {
+               static const int ox[7] = {0, 0, 0, -1, 1, 0, 0}, oy[7] = {0, 0, -1, 0, 0, 1, 0}, oz[7] = {0, -1, 0, 0, 0, 0, 1};
+               static const int vi[7] = {0, 3, 2, 1, 1, 2, 3};
+               dx = ox[k]; dy = oy[k]; dz = oz[k]; val = v[vi[k]];
+            }
+            else
+            {
+               if (k == 0) { dx = dy = dz = 0; val = v[0]; }
+               else { int m = k - 1; if (m >= 13) m++; dz = m / 9 - 1; dy = (m / 3) % 3 - 1; dx = m % 3 - 1; val = v[1]; }
+            }
+            int jx = ix + dx, jy = iy + dy, jz = iz + dz;
+            if (jx < 0 || jx >= nx || jy < 0 || jy >= ny || jz < 0 || jz >= nz) continue;
+            if (pass) { A.j[cnt] = (jz * ny + jy) * nx + jx; A.a[cnt] = val; }
+            cnt++;
+         }
+      }
+      if (!pass) A = csr_new(n, n, cnt, 1); else A.i[n] = cnt;
+   }
+   return A;
+}
+
+/* ---- y = alpha*A*x + beta*b : seq_mv/csr_matvec.c:195-328 (row sums left to right, seeded
+ *      with the scaled b term exactly as the optimized branch does) ---- */
+static void matvec(double alpha, const csr_t *A, const double *x, double beta, const double *b, double *y)
+{
+   int i, jj;
+   if (alpha == 0.0) { for (i = 0; i < A->n; i++) y[i] = beta * b[i]; return; }
+   double temp = beta / alpha;
+   for (i = 0; i < A->n; i++)
+   {
+      double t;
+      if (temp == 0.0) t = 0.0;
+      else if (temp == -1.0) t = (alpha == -1.0) ? b[i] : -b[i];
+      else if (temp == 1.0) t = (alpha == -1.0) ? -b[i] : b[i];
+      else t = (alpha == -1.0) ? -b[i] * temp : b[i] * temp;
+      if (alpha == -1.0) for (jj = A->i[i]; jj < A->i[i + 1]; jj++) t -= A->a[jj] * x[A->j[jj]];
+      else               for (jj = A->i[i]; jj < A->i[i + 1]; jj++) t += A->a[jj] * x[A->j[jj]];
+      y[i] = (alpha == 1.0 || alpha == -1.0) ? t : alpha * t;
+   }
+}
+static double dot(int n, const double *x, const double *y)     /* seq_mv/vector.c:511-545 */
+{ double r = 0.0; int i; for (i = 0; i < n; i++) r += y[i] * x[i]; return r; }
+
+/* ---- strength: parcsr_ls/par_strength.c:231-504 (num_functions 1, no offd) ---- */
+static csr_t strength(const csr_t *A, double theta, double max_row_sum)
+{
+   int n = A->n, i, jA, pass;
+   csr_t S; memset(&S, 0, sizeof S);
+   for (pass = 0; pass < 2; pass++)
+   {
+      int cnt = 0;
+      for (i = 0; i < n; i++)
+      {
+         if (pass) S.i[i] = cnt;
+         int b = A->i[i], e = A->i[i + 1];
+         if (b == e) continue;
+         double diag = A->a[b], row_scale = 0.0, row_sum = diag;
+         for (jA = b + 1; jA < e; jA++)
+         {
+            double v = A->a[jA];
+            if (diag < 0) row_scale = (row_scale < v) ? v : row_scale; else row_scale = (row_scale < v) ? row_scale : v;
+            row_sum += v;
+         }
+         if ((fabs(row_sum) > fabs(diag) * max_row_sum) && (max_row_sum < 1.0)) continue;   /* all weak */
+         for (jA = b + 1; jA < e; jA++)
+         {
+            int weak = diag < 0 ? (A->a[jA] <= theta * row_scale) : (A->a[jA] >= theta * row_scale);
+            if (!weak) { if (pass) S.j[cnt] = A->j[jA]; cnt++; }
+         }
+      }
+      if (!pass) S = csr_new(n, n, cnt, 0); else S.i[n] = cnt;
+   }
+   return S;
+}
+
+/* ---- hypre_Rand: utilities/random.c:71-106 (Schrage form of 16807*seed mod 2^31-1) ---- */
+static int g_seed = 13579;
+static double hrand(void)
+{
+   int high = g_seed / 127773, low = g_seed % 127773, test = 16807 * low - 2836 * high;
+   g_seed = test > 0 ? test : test + 2147483647;
+   return (double) g_seed / 2147483647;
+}
+
+/* ---- PMIS: parcsr_ls/par_coarsen.c:2159-2700, CF_init 0, one rank; measures from
+ *      par_indepset.c:44-59 (seed 2747, one draw per row in row order) ---- */
+static int *pmis(const csr_t *S)
+{
+   int n = S->n, i, k, jS;
+   double *m = (double *) xcalloc(n, sizeof(double));
+   int *cf = (int *) xcalloc(n, sizeof(int)), *graph = (int *) xmalloc(sizeof(int) * n), gsize = 0;
+   for (k = 0; k < S->nnz; k++) m[S->j[k]] += 1.0;
+   g_seed = 2747;
+   for (i = 0; i < n; i++) m[i] += hrand();
+   for (i = 0; i < n; i++)
+   {
+      cf[i] = 0;
+      if (S->i[i + 1] - S->i[i] == 0) { cf[i] = -3; m[i] = 0; } else graph[gsize++] = i;
+   }
+   while (gsize > 0)
+   {
+      int ig;
+      for (ig = 0; ig < gsize; ig++) { i = graph[ig]; if (m[i] > 1) cf[i] = 1; }
+      for (ig = 0; ig < gsize; ig++)
+      {
+         i = graph[ig];
+         if (m[i] > 1)
+            for (jS = S->i[i]; jS < S->i[i + 1]; jS++)
+            {
+               int j = S->j[jS];
+               if (m[j] > 1) { if (m[i] > m[j]) cf[j] = 0; else if (m[j] > m[i]) cf[i] = 0; }
+            }
+      }
+      for (ig = 0; ig < gsize; ig++)
+      {
+         i = graph[ig];
+         if (m[i] < 1) cf[i] = -1;
+         if (cf[i] > 0) cf[i] = 1;
+         else for (jS = S->i[i]; jS < S->i[i + 1]; jS++) if (cf[S->j[jS]] > 0) cf[i] = -1;
+      }
+      int g2 = 0;
+      for (ig = 0; ig < gsize; ig++) { i = graph[ig]; if (cf[i] != 0) m[i] = 0; else graph[g2++] = i; }
+      gsize = g2;
+   }
+   free(m); free(graph);
+   return cf;
+}
+
+/* ---- utilities/hypre_qsort.c:367-387 ---- */
+static void swap2(int *v, double *w, int i, int j) { int t = v[i]; v[i] = v[j]; v[j] = t; double s = w[i]; w[i] = w[j]; w[j] = s; }
+static void qsort2_abs(int *v, double *w, int left, int right)
+{
+   int i, last;
+   if (left >= right) return;
+   swap2(v, w, left, (left + right) / 2);
+   last = left;
+   for (i = left + 1; i <= right; i++) if (fabs(w[i]) > fabs(w[left])) swap2(v, w, ++last, i);
+   swap2(v, w, left, last);
+   qsort2_abs(v, w, left, last - 1);
+   qsort2_abs(v, w, last + 1, right);
+}
+
+/* ---- ext+i interpolation: parcsr_ls/par_lr_interp.c:1301-1416 (C-hat discovery) and
+ *      :1523-1803 (weights); truncation parcsr_mv/par_csr_matrix.c:2906-3020 (rescale 1) ---- */
+static csr_t extpi(const csr_t *A, const csr_t *S, const int *cf, int max_elmts, int *ncoarse_out)
+{
+   int n = A->n, i, jj, kk, jj1, nc = 0;
+   int *f2c = (int *) xmalloc(sizeof(int) * n);
+   /* the reference's P_marker / strong_f_marker bookkeeping (par_lr_interp.c:1547-1605) restated as
+    * "owner[c] == i" (c was touched while building row i) + pos_of[c] (>=0: slot in C-hat_i, -2: strong F) */
+   int *owner = (int *) xmalloc(sizeof(int) * n), *pos_of = (int *) xmalloc(sizeof(int) * n);
+   for (i = 0; i < n; i++) { f2c[i] = cf[i] >= 0 ? nc++ : -1; owner[i] = -1; pos_of[i] = -1; }
+   /* rows are built one at a time into a row buffer, truncated, then appended */
+   int cap = 16 * n + 64, cnt = 0;
+   csr_t P = csr_new(n, nc, cap, 1);
+   int rowcap = 1024; int *rj = (int *) xmalloc(sizeof(int) * rowcap); double *ra = (double *) xmalloc(sizeof(double) * rowcap);
+   for (i = 0; i < n; i++)
+   {
+      int len = 0;
+      P.i[i] = cnt;
+      if (cf[i] >= 0) { rj[0] = f2c[i]; ra[0] = 1.0; len = 1; }
+      else if (cf[i] != -3)
+      {
+         #define IN_CHAT(c) (owner[c] == i && pos_of[c] >= 0)
+         #define IS_SF(c) (owner[c] == i && pos_of[c] == -2)
+         #define PUSH(c) do { if (!(owner[c] == i)) { owner[c] = i; pos_of[c] = len; \
+               if (len >= rowcap) { rowcap *= 2; rj = (int *) realloc(rj, sizeof(int) * rowcap); ra = (double *) realloc(ra, sizeof(double) * rowcap); } \
+               rj[len] = f2c[c]; ra[len] = 0.0; len++; } } while (0)
+         for (jj = S->i[i]; jj < S->i[i + 1]; jj++)
+         {
+            int i1 = S->j[jj];
+            if (cf[i1] >= 0) PUSH(i1);
+            else if (cf[i1] != -3)
+            {
+               owner[i1] = i; pos_of[i1] = -2;
+               for (kk = S->i[i1]; kk < S->i[i1 + 1]; kk++) { int k1 = S->j[kk]; if (cf[k1] >= 0) PUSH(k1); }
+            }
+         }
+         double diagonal = A->a[A->i[i]];
+         for (jj = A->i[i] + 1; jj < A->i[i + 1]; jj++)
+         {
+            int i1 = A->j[jj];
+            if (IN_CHAT(i1)) ra[pos_of[i1]] += A->a[jj];
+            else if (IS_SF(i1))
+            {
+               double sum = 0.0; int sgn = 1;
+               if (A->a[A->i[i1]] < 0) sgn = -1;
+               for (jj1 = A->i[i1] + 1; jj1 < A->i[i1 + 1]; jj1++)
+               {
+                  int i2 = A->j[jj1];
+                  if ((IN_CHAT(i2) || i2 == i) && (sgn * A->a[jj1]) < 0) sum += A->a[jj1];
+               }
+               if (sum != 0)
+               {
+                  double distribute = A->a[jj] / sum;
+                  for (jj1 = A->i[i1] + 1; jj1 < A->i[i1 + 1]; jj1++)
+                  {
+                     int i2 = A->j[jj1];
+                     if (IN_CHAT(i2) && (sgn * A->a[jj1]) < 0) ra[pos_of[i2]] += distribute * A->a[jj1];
+                     if (i2 == i && (sgn * A->a[jj1]) < 0) diagonal += distribute * A->a[jj1];
+                  }
+               }
+               else diagonal += A->a[jj];
+            }
+            else if (cf[i1] != -3) diagonal += A->a[jj];
+         }
+         if (diagonal) for (jj = 0; jj < len; jj++) ra[jj] /= -diagonal;
+         #undef IN_CHAT
+         #undef IS_SF
+         #undef PUSH
+         /* truncation to max_elmts largest |w|, kept in sorted order, rescaled to the row sum */
+         if (max_elmts > 0 && len > max_elmts)
+         {
+            double row_sum = 0, scale = 0;
+            for (jj = 0; jj < len; jj++) row_sum += ra[jj];
+            qsort2_abs(rj, ra, 0, len - 1);
+            for (jj = 0; jj < max_elmts; jj++) scale += ra[jj];
+            len = max_elmts;
+            if (scale != 0. && scale != row_sum) { scale = row_sum / scale; for (jj = 0; jj < len; jj++) ra[jj] *= scale; }
+         }
+      }
+      if (cnt + len > cap) { cap = 2 * (cnt + len); P.j = (int *) realloc(P.j, sizeof(int) * cap); P.a = (double *) realloc(P.a, sizeof(double) * cap); }
+      memcpy(P.j + cnt, rj, sizeof(int) * len); memcpy(P.a + cnt, ra, sizeof(double) * len);
+      cnt += len;
+   }
+   P.i[n] = cnt; P.nnz = cnt;
+   free(f2c); free(owner); free(pos_of); free(rj); free(ra);
+   *ncoarse_out = nc;
+   return P;
+}
+
+/* ---- transpose: seq_mv/csr_matop.c:651-773 (stable counting sort by column) ---- */
+static csr_t transpose(const csr_t *A)
+{
+   csr_t T = csr_new(A->m, A->n, A->nnz, 1);
+   int i, k;
+   for (k = 0; k < A->nnz; k++) T.i[A->j[k] + 1]++;
+   for (i = 0; i < A->m; i++) T.i[i + 1] += T.i[i];
+   int *next = (int *) xmalloc(sizeof(int) * (A->m + 1)); memcpy(next, T.i, sizeof(int) * (A->m + 1));
+   for (i = 0; i < A->n; i++) for (k = A->i[i]; k < A->i[i + 1]; k++) { int p = next[A->j[k]]++; T.j[p] = i; T.a[p] = A->a[k]; }
+   free(next);
+   return T;
+}
+
+/* ---- C = A*B: seq_mv/csr_matop.c:375-468 (diagonal first when square, first-touch column order) ---- */
+static csr_t multiply(const csr_t *A, const csr_t *B)
+{
+   int allsquare = A->n == B->m, ic, ia, ib, pass;
+   int *mark = (int *) xmalloc(sizeof(int) * B->m);
+   csr_t C; memset(&C, 0, sizeof C);
+   for (pass = 0; pass < 2; pass++)
+   {
+      int cnt = 0;
+      for (ib = 0; ib < B->m; ib++) mark[ib] = -1;
+      for (ic = 0; ic < A->n; ic++)
+      {
+         int row_start = cnt;
+         if (pass) C.i[ic] = cnt;
+         if (allsquare) { mark[ic] = cnt; if (pass) { C.j[cnt] = ic; C.a[cnt] = 0; } cnt++; }
+         for (ia = A->i[ic]; ia < A->i[ic + 1]; ia++)
+         {
+            int ja = A->j[ia]; double a = A->a[ia];
+            for (ib = B->i[ja]; ib < B->i[ja + 1]; ib++)
+            {
+               int jb = B->j[ib];
+               if (mark[jb] < row_start) { mark[jb] = cnt; if (pass) { C.j[cnt] = jb; C.a[cnt] = a * B->a[ib]; } cnt++; }
+               else if (pass) C.a[mark[jb]] += a * B->a[ib];
+            }
+         }
+      }
+      if (!pass) C = csr_new(A->n, B->m, cnt, 1); else C.i[A->n] = cnt;
+   }
+   free(mark);
+   return C;
+}
+
+/* ---- l1 norms option 1: parcsr_ls/ams.c:648-657,:739-769 + csr_matop.c:1326-1352 ---- */
+static double *l1_norms(const csr_t *A)
+{
+   double *l1 = (double *) xmalloc(sizeof(double) * A->n); int i, j;
+   for (i = 0; i < A->n; i++)
+   {
+      double s = 0.0, d = 0.0;
+      for (j = A->i[i]; j < A->i[i + 1]; j++) s += 1.0 * fabs(A->a[j]);
+      for (j = A->i[i]; j < A->i[i + 1]; j++) if (A->j[j] == i) { d = A->a[j]; break; }
+      l1[i] = d < 0.0 ? -s : s;
+   }
+   return l1;
+}
+
+/* ---- sstruct_ls/gselim.h ---- */
+static void gselim(double *A, double *x, int n)
+{
+   int j, k, m;
+   if (n == 1) { if (A[0] != 0.0) x[0] = x[0] / A[0]; return; }
+   for (k = 0; k < n - 1; k++) if (A[k * n + k] != 0.0)
+   {
+      double divA = 1.0 / A[k * n + k];
+      for (j = k + 1; j < n; j++) if (A[j * n + k] != 0.0)
+      {
+         double factor = A[j * n + k] * divA;
+         for (m = k + 1; m < n; m++) A[j * n + m] -= factor * A[k * n + m];
+         x[j] -= factor * x[k];
+      }
+   }
+   for (k = n - 1; k > 0; --k) if (A[k * n + k] != 0.0)
+   {
+      x[k] /= A[k * n + k];
+      for (j = 0; j < k; j++) if (A[j * n + k] != 0.0) x[j] -= x[k] * A[j * n + k];
+   }
+   if (A[0] != 0.0) x[0] /= A[0];
+}
+
+#define MAXLEV 25
+typedef struct { int nl; csr_t A[MAXLEV], P[MAXLEV], R[MAXLEV], S[MAXLEV]; int *cf[MAXLEV]; double *l1[MAXLEV];
+                 double *F[MAXLEV], *U[MAXLEV], *V; double *ge; int ge_n; } amg_t;
+
+/* ---- setup loop: parcsr_ls/par_amg_setup.c:889-2890 for coarsen 8 / interp 6 / mod_rap2 1 ---- */
+static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
+{
+   int l = 0, i;
+   memset(g, 0, sizeof *g);
+   g->A[0] = A0;
+   while (1)
+   {
+      csr_t S = strength(&g->A[l], theta, mrs);
+      int *cf = pmis(&S), n = g->A[l].n, nc = 0;
+      for (i = 0; i < n; i++) if (cf[i] == 1) nc++;
+      if (nc == 0 || nc == n) { csr_free(&S); free(cf); break; }
+      g->P[l] = extpi(&g->A[l], &S, cf, pmax, &nc);
+      for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;            /* par_lr_interp.c:1888-1894 */
+      g->cf[l] = cf; g->S[l] = S;
+      g->R[l] = transpose(&g->P[l]);                                  /* par_csr_triplemat.c:874-876 */
+      csr_t Q = multiply(&g->A[l], &g->P[l]);
+      g->A[l + 1] = multiply(&g->R[l], &Q);
+      csr_free(&Q);
+      l++;
+      if (l == MAXLEV - 1 || nc <= max_coarse) break;
+   }
+   g->nl = l + 1;
+   for (i = 0; i < g->nl; i++)
+   {
+      int n = g->A[i].n;
+      g->l1[i] = l1_norms(&g->A[i]);
+      g->F[i] = (double *) xcalloc(n, sizeof(double)); g->U[i] = (double *) xcalloc(n, sizeof(double));
+   }
+   g->V = (double *) xcalloc(g->A[0].n, sizeof(double));
+   csr_t *Ac = &g->A[g->nl - 1];
+   if (Ac->n <= max_coarse)
+   {  /* par_gauss_elim.c:100-115 */
+      int n = Ac->n, jj; g->ge_n = n; g->ge = (double *) xcalloc((size_t) n * n, sizeof(double));
+      for (i = 0; i < n; i++) for (jj = Ac->i[i]; jj < Ac->i[i + 1]; jj++) g->ge[i * n + Ac->j[jj]] = Ac->a[jj];
+   }
+}
+
+/* l1-Jacobi sweep: parcsr_ls/ams.c:72-92 (v=f; v=-A u + v; u += v/l1) */
+static void relax(amg_t *g, int l, const double *f, double *u)
+{
+   int n = g->A[l].n, i; double *v = g->V;
+   matvec(-1.0, &g->A[l], u, 1.0, f, v);
+   for (i = 0; i < n; i++) u[i] += v[i] / g->l1[l][i];
+}
+/* V(1,1): parcsr_ls/par_cycle.c:255-622 */
+static void cycle(amg_t *g, const double *f, double *u)
+{
+   int l, i, nl = g->nl;
+   const double *F; double *U;
+   for (l = 0; l < nl - 1; l++)
+   {
+      F = l ? g->F[l] : f; U = l ? g->U[l] : u;
+      relax(g, l, F, U);
+      matvec(-1.0, &g->A[l], U, 1.0, F, g->V);
+      matvec(1.0, &g->R[l], g->V, 0.0, g->V, g->F[l + 1]);
+      for (i = 0; i < g->A[l + 1].n; i++) g->U[l + 1][i] = 0.0;
+   }
+   F = (nl > 1) ? g->F[nl - 1] : f; U = (nl > 1) ? g->U[nl - 1] : u;
+   if (g->ge)
+   {
+      int n = g->ge_n; double *T = (double *) xmalloc(sizeof(double) * n * n), *b = (double *) xmalloc(sizeof(double) * n);
+      memcpy(T, g->ge, sizeof(double) * n * n); memcpy(b, F, sizeof(double) * n);
+      gselim(T, b, n);
+      memcpy(U, b, sizeof(double) * n); free(T); free(b);
+   }
+   else relax(g, nl - 1, F, U);
+   for (l = nl - 2; l >= 0; l--)
+   {
+      F = l ? g->F[l] : f; U = l ? g->U[l] : u;
+      matvec(1.0, &g->P[l], g->U[l + 1], 1.0, U, U);
+      relax(g, l, F, U);
+   }
+}
+
+/* ---- output in ref_dump.c's record format ---- */
+static FILE *g_out;
+static void put(const char *name, int dtype, const void *p, size_t n)
+{
+   unsigned int nl = (unsigned int) strlen(name), dt = (unsigned int) dtype; unsigned long long cnt = n;
+   if (!g_out) return;
+   fwrite(&nl, 4, 1, g_out); fwrite(name, 1, nl, g_out); fwrite(&dt, 4, 1, g_out); fwrite(&cnt, 8, 1, g_out);
+   if (n) fwrite(p, dtype ? 8 : 4, n, g_out);
+}
+static void put_csr(const char *pre, int l, const csr_t *M, int with_data)
+{
+   char nm[64]; int dims[3] = { M->n, M->m, M->i[M->n] };
+   sprintf(nm, "%s%d.dims", pre, l); put(nm, 0, dims, 3);
+   sprintf(nm, "%s%d.i", pre, l); put(nm, 0, M->i, M->n + 1);
+   sprintf(nm, "%s%d.j", pre, l); put(nm, 0, M->j, M->i[M->n]);
+   if (with_data) { sprintf(nm, "%s%d.a", pre, l); put(nm, 1, M->a, M->i[M->n]); }
+}
+static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+
+int main(int argc, char **argv)
+{
+   int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0;
+   double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
+   const char *ofile = NULL;
+   for (i = 1; i < argc; i++)
+   {
+      if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
+      else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
+      else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-Pmx")) Pmx = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-th")) th = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-tol")) tol = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-mxrs")) mxrs = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-max_iter")) max_iter = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-matvec")) matvec_reps = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
+      else if (!strcmp(argv[i], "-pmis") || !strcmp(argv[i], "-nodump")) { }
+      else if (!strcmp(argv[i], "-rlx") || !strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
+      else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
+   }
+   double v[4];
+   if (pt27) { v[0] = 26.0; if (nx == 1 || ny == 1 || nz == 1) v[0] = 8.0; if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) v[0] = 2.0; v[1] = -1.; }
+   else { v[1] = -cx; v[2] = -cy; v[3] = -cz; v[0] = 0.; if (nx > 1) v[0] += 2.0 * cx; if (ny > 1) v[0] += 2.0 * cy; if (nz > 1) v[0] += 2.0 * cz; }
+   csr_t A = gen_laplace(nx, ny, nz, pt27, v);
+   int N = A.n;
+   double *b = (double *) xmalloc(sizeof(double) * N), *x = (double *) xcalloc(N, sizeof(double));
+   for (i = 0; i < N; i++) b[i] = 1.0;
+   if (matvec_reps > 0)
+   {
+      double *y = (double *) xcalloc(N, sizeof(double)), t0;
+      matvec(1.0, &A, b, 0.0, y, y); t0 = now();
+      for (i = 0; i < matvec_reps; i++) matvec(1.0, &A, b, 0.0, y, y);
+      printf("amg_oracle: matvec_ms=%.6f reps=%d\n", (now() - t0) / matvec_reps * 1e3, matvec_reps);
+      return 0;
+   }
+   amg_t g;
+   double t0 = now();
+   amg_setup(&g, A, th, mxrs, Pmx, 9);
+   double t_setup = now() - t0;
+
+   /* PCG: krylov/pcg.c:347-757, two_norm 1 */
+   double *p = (double *) xcalloc(N, sizeof(double)), *s = (double *) xcalloc(N, sizeof(double)), *r = (double *) xmalloc(sizeof(double) * N);
+   double *norms = (double *) xcalloc(max_iter + 2, sizeof(double));
+   t0 = now();
+   double bi_prod = dot(N, b, b), eps = tol * tol, i_prod = 0, gamma, gamma_old;
+   int it = 0;
+   memcpy(r, b, sizeof(double) * N);
+   matvec(-1.0, &A, x, 1.0, r, r);
+   memset(p, 0, sizeof(double) * N); cycle(&g, r, p);
+   gamma = dot(N, r, p);
+   norms[0] = sqrt(dot(N, r, r));
+   while (it + 1 <= max_iter)
+   {
+      it++;
+      matvec(1.0, &A, p, 0.0, s, s);
+      double sdotp = dot(N, s, p);
+      if (sdotp == 0.0) break;
+      double alpha = gamma / sdotp;
+      gamma_old = gamma;
+      for (i = 0; i < N; i++) x[i] += alpha * p[i];
+      for (i = 0; i < N; i++) r[i] += -alpha * s[i];
+      memset(s, 0, sizeof(double) * N); cycle(&g, r, s);
+      gamma = dot(N, r, s);
+      i_prod = dot(N, r, r);
+      norms[it] = sqrt(i_prod);
+      if (i_prod / bi_prod < eps) break;
+      double beta = gamma / gamma_old;
+      for (i = 0; i < N; i++) p[i] *= beta;
+      for (i = 0; i < N; i++) p[i] += 1.0 * s[i];
+   }
+   double t_solve = now() - t0, relres = sqrt(i_prod / bi_prod);
+   printf("amg_oracle: n=%d %d %d rows=%d nnz=%d\n", nx, ny, nz, N, A.nnz);
+   printf("amg_oracle: levels=%d iterations=%d relres=%.6e setup_s=%.4f solve_s=%.4f\n", g.nl, it, relres, t_setup, t_solve);
+   for (i = 0; i < g.nl; i++) printf("amg_oracle: level %d rows=%d nnz=%d\n", i, g.A[i].n, g.A[i].i[g.A[i].n]);
+   if (ofile)
+   {
+      g_out = fopen(ofile, "wb");
+      int hdr[8] = { nx, ny, nz, g.nl, it, pt27, Pmx, 18 };
+      put("hdr", 0, hdr, 8); put("relres", 1, &relres, 1); put("norms", 1, norms, it + 1); put("x", 1, x, N);
+      for (i = 0; i < g.nl; i++)
+      {
+         char nm[64];
+         put_csr("A", i, &g.A[i], 1);
+         if (i < g.nl - 1 || !g.ge) { sprintf(nm, "l1_%d", i); put(nm, 1, g.l1[i], g.A[i].n); }   /* par_amg_setup.c:3045-3060 */
+         if (i < g.nl - 1)
+         {
+            sprintf(nm, "CF%d", i); put(nm, 0, g.cf[i], g.A[i].n);
+            put_csr("P", i, &g.P[i], 1);
+            put_csr("S", i, &g.S[i], 0);
+         }
+      }
+      fclose(g_out);
+   }
+   return 0;
+}

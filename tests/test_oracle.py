@@ -1,0 +1,118 @@
+"""CPU tests (-m "not gpu"): pin the restatement oracle (oracle/amg_oracle.c) against the golden dumps
+produced by the reference's own CPU build, check the reference build (when present) against the
+survey's known answers, and check that the C-ABI library loads and exports every declared symbol."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import refio
+
+ROOT = refio.ROOT
+ORACLE = os.path.join(ROOT, "oracle", "_build", "amg_oracle")
+
+GOLDEN_ARGS = {
+    "lap7_20_pmis_rlx18_modrap.bin": ["-n", "20", "20", "20"],
+    "lap7_13x9x11_pmis_rlx18_modrap.bin": ["-n", "13", "9", "11"],
+    "lap27_10_pmis_rlx18_modrap.bin": ["-n", "10", "10", "10", "-27pt"],
+    "aniso_12_pmis_rlx18_modrap.bin": ["-n", "12", "12", "12", "-c", "1", "1", "0.001"],
+}
+
+
+@pytest.fixture(scope="session")
+def oracle_bin():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+    assert os.path.exists(ORACLE)
+    return ORACLE
+
+
+def run_oracle(binary, args):
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "o.bin")
+        out = subprocess.run([binary] + [str(a) for a in args] + ["-pmis", "-rlx", "18", "-mod_rap2", "1", "-o", path],
+                             check=True, capture_output=True, text=True).stdout
+        return refio.read_dump(path), out
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN_ARGS))
+def test_restatement_matches_reference_golden_bit_for_bit(oracle_bin, name):
+    gold = refio.read_dump(os.path.join(refio.GOLDEN, name))
+    mine, _ = run_oracle(oracle_bin, GOLDEN_ARGS[name])
+    assert set(gold) == set(mine)
+    for k in gold:
+        assert np.array_equal(gold[k], mine[k]), k      # ints and doubles, hierarchy and residual history
+
+
+def test_golden_known_answers():
+    """iteration counts recorded when the fixtures were generated (make_golden.py output)"""
+    want = {"lap7_20_pmis_rlx18_modrap.bin": (6, 13), "lap7_13x9x11_pmis_rlx18_modrap.bin": (5, 12),
+            "lap27_10_pmis_rlx18_modrap.bin": (4, 11), "aniso_12_pmis_rlx18_modrap.bin": (6, 12)}
+    for name, (levels, its) in want.items():
+        d = refio.read_dump(os.path.join(refio.GOLDEN, name))
+        assert int(d["hdr"][3]) == levels and int(d["hdr"][4]) == its
+        assert len(d["norms"]) == its + 1
+        # structural invariants of the reference output the GPU path relies on
+        for l in range(levels - 1):
+            i, j, a, (n, m) = refio.csr(d, "A", l)
+            assert np.all(j[i[:-1]] == np.arange(n))             # diagonal stored first in every row
+            cf = d["CF%d" % l]
+            assert set(np.unique(cf)) <= {-1, 1}
+            pi, pj, pa, (pn, pm) = refio.csr(d, "P", l)
+            assert pm == int((cf == 1).sum()) and np.all(np.diff(pi) <= 4)   # P_max_elmts = 4
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built (no /root/reference here)")
+def test_reference_build_reproduces_survey_known_answer():
+    """ij -n 50 50 50 -solver 1 -pmis -rlx 18 -> 15 its, 4.192356e-09, level table"""
+    _, out = refio.run_ref(["-n", 50, 50, 50, "-pmis", "-rlx", 18, "-mod_rap2", 1], dump=False)
+    assert "iterations=15 relres=4.192356e-09" in out
+    rows = [int(x) for x in re.findall(r"level \d+ rows=(\d+)", out)]
+    nnz = [int(x) for x in re.findall(r"level \d+ rows=\d+ nnz=(\d+)", out)]
+    assert rows == [125000, 39654, 5595, 674, 117, 22, 3]
+    assert nnz == [860000, 1091990, 342947, 43682, 5005, 344, 9]
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args", [["-n", 17, 23, 9], ["-n", 14, 14, 14, "-27pt"], ["-n", 1, 40, 40], ["-n", 30, 30, 30]])
+def test_restatement_matches_live_reference(oracle_bin, args):
+    gold, _ = refio.run_ref(args + ["-pmis", "-rlx", 18, "-mod_rap2", 1])
+    mine, _ = run_oracle(oracle_bin, args)
+    for k in gold:
+        assert np.array_equal(gold[k], mine[k]), k
+
+
+def test_library_exports_every_declared_symbol():
+    """include/hypre_b200.h <-> libhypre_b200.so <-> ctypes table agree (no compute calls: no GPU here)"""
+    import hypre_ve_b200 as hb
+    lib = hb.load_library()
+    hdr = open(os.path.join(ROOT, "include", "hypre_b200.h")).read()
+    declared = set(re.findall(r"\b(b200_[A-Za-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in the header but not exported" % name
+        assert name in hb.SIGNATURES, "symbol %s has no ctypes signature" % name
+    assert set(hb.SIGNATURES) <= declared
+
+
+def test_no_cpu_fallback_without_device():
+    import hypre_ve_b200 as hb
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(hb.B200Error, match="no CUDA device"):
+        hb.Handle(0)
+
+
+def test_product_does_not_reference_the_oracle():
+    """the product tree must never import, link or execute anything under oracle/"""
+    pkg = os.path.join(ROOT, "hypre_ve_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep)[-1:]:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".c")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle/" not in txt and "amg_oracle" not in txt and "ref_dump" not in txt, os.path.join(dirpath, f)
