@@ -11,8 +11,11 @@
 
 #define B200_NUM_SM_FALLBACK 148
 
+struct b200_pool_s;   // slab sub-allocator (b200_runtime.cu)
+
 struct b200_handle_s {
   int device = 0;
+  b200_pool_s *pool = nullptr;
   int num_sm = B200_NUM_SM_FALLBACK;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -74,16 +77,18 @@ int b200_set_error(const char *file, int line, const char *msg);
     if (e__ != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); \
   } while (0)
 
-// stream-ordered allocation helpers (cudaMallocAsync pool; freed memory stays cached in the pool)
+// device allocation: slab sub-allocator owned by the handle.  All work of a handle runs on one
+// stream, so a freed block may be handed out again immediately (stream order keeps it safe).
+int b200_pool_alloc(b200_handle h, void **p, size_t bytes);
+int b200_pool_free(b200_handle h, void *p);
 template <class T>
 static inline int b200_dalloc(b200_handle h, T **p, size_t count) {
   *p = nullptr;
   if (count == 0) count = 1;
-  B200_CUDA(cudaMallocAsync((void **)p, count * sizeof(T), h->stream));
-  return 0;
+  return b200_pool_alloc(h, (void **)p, count * sizeof(T));
 }
 static inline int b200_dfree(b200_handle h, void *p) {
-  if (p) B200_CUDA(cudaFreeAsync(p, h->stream));
+  if (p) return b200_pool_free(h, p);
   return 0;
 }
 static inline int b200_grid(size_t n, int block) { return (int)((n + block - 1) / block); }

@@ -3,6 +3,95 @@
 // (utilities/hypre_general.c:128-197, utilities/hypre_memory.c) for the B200 path.
 #include "b200_internal.h"
 #include <cub/device/device_scan.cuh>
+#include <map>
+
+// ------------------------------------------------------------------------------------------
+// Slab sub-allocator.  BoomerAMG setup allocates and frees hundreds of temporaries, several of
+// them gigabytes; going to the driver for each (cudaMalloc / cudaMallocAsync pool growth and
+// remapping) cost more than the kernels (profiles/README.md r1_b).  Slabs are cudaMalloc'd once
+// (>= 1 GiB, or the request if larger), carved best-fit with address-ordered coalescing of free
+// blocks, and only returned to the driver at b200_finalize.
+// ------------------------------------------------------------------------------------------
+struct b200_pool_s {
+  static constexpr size_t ALIGN = 512;
+  static constexpr size_t SLAB = (size_t)1 << 30;
+  std::vector<void *> slabs;
+  std::map<char *, size_t> free_by_addr;              // address -> size
+  std::multimap<size_t, char *> free_by_size;         // size -> address
+  std::map<char *, size_t> used;                      // address -> size
+  size_t total = 0, in_use = 0, peak = 0;
+
+  void add_free(char *p, size_t n) {
+    // coalesce with the neighbours (never across slabs: slab ends are not adjacent free blocks by construction
+    // unless the driver returned adjacent ranges, which is harmless for a single-owner pool)
+    auto next = free_by_addr.lower_bound(p);
+    if (next != free_by_addr.end() && p + n == next->first && !is_slab_start(next->first)) {
+      n += next->second;
+      erase_size(next->second, next->first);
+      next = free_by_addr.erase(next);
+    }
+    if (next != free_by_addr.begin()) {
+      auto prev = std::prev(next);
+      if (prev->first + prev->second == p && !is_slab_start(p)) {
+        p = prev->first;
+        n += prev->second;
+        erase_size(prev->second, prev->first);
+        free_by_addr.erase(prev);
+      }
+    }
+    free_by_addr[p] = n;
+    free_by_size.emplace(n, p);
+  }
+  bool is_slab_start(char *p) const {
+    for (void *s : slabs) if (s == (void *)p) return true;
+    return false;
+  }
+  void erase_size(size_t n, char *p) {
+    auto r = free_by_size.equal_range(n);
+    for (auto it = r.first; it != r.second; ++it)
+      if (it->second == p) { free_by_size.erase(it); return; }
+  }
+};
+
+int b200_pool_alloc(b200_handle h, void **out, size_t bytes) {
+  b200_pool_s *P = h->pool;
+  size_t n = (bytes + b200_pool_s::ALIGN - 1) / b200_pool_s::ALIGN * b200_pool_s::ALIGN;
+  auto it = P->free_by_size.lower_bound(n);
+  if (it == P->free_by_size.end()) {
+    size_t slab = n > b200_pool_s::SLAB ? n : b200_pool_s::SLAB;
+    void *s = nullptr;
+    cudaError_t e = cudaMalloc(&s, slab);
+    if (e != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e));
+    P->slabs.push_back(s);
+    P->total += slab;
+    P->free_by_addr[(char *)s] = slab;
+    it = P->free_by_size.emplace(slab, (char *)s);
+  }
+  char *p = it->second;
+  size_t have = it->first;
+  P->free_by_size.erase(it);
+  P->free_by_addr.erase(p);
+  if (have > n) {
+    P->free_by_addr[p + n] = have - n;
+    P->free_by_size.emplace(have - n, p + n);
+  }
+  P->used[p] = n;
+  P->in_use += n;
+  if (P->in_use > P->peak) P->peak = P->in_use;
+  *out = p;
+  return 0;
+}
+
+int b200_pool_free(b200_handle h, void *ptr) {
+  b200_pool_s *P = h->pool;
+  auto it = P->used.find((char *)ptr);
+  if (it == P->used.end()) return b200_set_error(__FILE__, __LINE__, "free of a pointer this handle did not allocate");
+  size_t n = it->second;
+  P->used.erase(it);
+  P->in_use -= n;
+  P->add_free((char *)ptr, n);
+  return 0;
+}
 
 thread_local std::string g_b200_err;
 long long g_b200_launches = 0;
@@ -33,11 +122,7 @@ extern "C" int b200_init(int device, b200_handle *out) {
   B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
   B200_CUDA(cudaEventCreate(&h->ev0));
   B200_CUDA(cudaEventCreate(&h->ev1));
-  // keep freed blocks cached in the pool: setup allocates and frees many temporaries
-  cudaMemPool_t pool;
-  B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t thr = UINT64_MAX;
-  B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+  h->pool = new b200_pool_s();
   h->n_partials = 4096;
   B200_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * h->n_partials));
   B200_CUDA(cudaMallocHost(&h->h_pinned, sizeof(double) * 64));
@@ -51,6 +136,8 @@ extern "C" int b200_finalize(b200_handle h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->d_partials);
   cudaFreeHost(h->h_pinned);
+  for (void *s : h->pool->slabs) cudaFree(s);
+  delete h->pool;
   cudaEventDestroy(h->ev0);
   cudaEventDestroy(h->ev1);
   cudaStreamDestroy(h->stream);

@@ -665,9 +665,22 @@ int b200_coarse_map(b200_handle h, int n, const int *d_cf, int **f2c_out, int *n
   return 0;
 }
 
+int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor, int max_elmts,
+                           b200_csr *out, int *done);
+int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, b200_csr *out, int *done);
+static bool force_general() {
+  const char *e = getenv("B200_FORCE_GENERAL_SETUP");   // test hook: exercise the HBM-scratch kernels
+  return e && e[0] == '1';
+}
+
 extern "C" int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor,
                                  int max_elmts, b200_csr *out) {
   if (!A || !A->a || !S) B200_FAIL("interp: bad arguments");
+  if (!force_general()) {
+    int done = 0;
+    B200_TRY(b200_extpi_interp_warp(h, A, S, d_cf, trunc_factor, max_elmts, out, &done));
+    if (done) return 0;
+  }
   const int n = A->nrows;
   int *f2c = nullptr, ncoarse = 0;
   B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
@@ -771,6 +784,11 @@ extern "C" int b200_csr_transpose(b200_handle h, b200_csr A, b200_csr *out) {
 extern "C" int b200_csr_multiply(b200_handle h, b200_csr A, b200_csr B, b200_csr *out) {
   if (!A || !B || !A->a || !B->a) B200_FAIL("multiply: matrices with values required");
   if (A->ncols != B->nrows) B200_FAIL("multiply: incompatible matrix dimensions");   // csr_matop.c:334-338
+  if (!force_general()) {
+    int done = 0;
+    B200_TRY(b200_csr_multiply_warp(h, A, B, out, &done));
+    if (done) return 0;
+  }
   const int n = A->nrows;
   const int allsquare = (A->nrows == B->ncols) ? 1 : 0;
   int *cap = nullptr;

@@ -1,0 +1,633 @@
+// b200_setup_warp.cu -- warp-per-row, shared-memory versions of the two heavy setup stages:
+// ext+i interpolation (+ truncation) and the Gustavson SpGEMM.   Compiled with -fmad=false.
+//
+// Why these stay bit-identical to the reference while 32 lanes cooperate on a row:
+//   * the reference's outer loops (over the entries of row i of S / A) are kept sequential;
+//   * its inner loops run over the entries of ONE other row (S_{i1}, A_{i1} or B_{ja}), whose
+//     column indices are distinct, so the 32 lanes of a chunk touch distinct hash keys and distinct
+//     accumulators: no two additions to the same target are reordered;
+//   * first-touch positions inside a chunk are handed out by ballot + prefix popcount, i.e. in
+//     entry order, exactly the order the sequential loop would have assigned;
+//   * the one true reduction (the `sum` of par_lr_interp.c:1673-1693) is accumulated in lane
+//     order with 32 shuffles, adding 0.0 for non-qualifying entries (an exact no-op).
+// Each warp owns a private hash table (column -> slot) and the row under construction in shared
+// memory; a row that does not fit raises a device flag and the caller redoes the stage with the
+// general HBM-scratch kernels of b200_setup.cu.
+#include "b200_internal.h"
+
+namespace {
+
+constexpr int WPB = 4;                 // warps per CTA
+constexpr int NOTFOUND = -1;
+constexpr int STRONG_F = -2;
+constexpr int SELF = -3;
+constexpr int PENDING = -1;            // row not produced yet (per-row overflow protocol)
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned hslot(int key, int cap) { return (((unsigned)key * 0x9E3779B1u) >> 9) & (unsigned)(cap - 1); }
+
+template <int CAP>
+__device__ __forceinline__ int wt_find(const int *keys, const int *vals, int key) {
+  unsigned s = hslot(key, CAP);
+  while (true) {
+    int kk = keys[s];
+    if (kk == key) return vals[s];
+    if (kk == -1) return NOTFOUND;
+    s = (s + 1) & (CAP - 1);
+  }
+}
+template <int CAP>
+__device__ __forceinline__ int wt_insert(int *keys, int key, bool *is_new) {
+  unsigned s = hslot(key, CAP);
+  while (true) {
+    int prev = atomicCAS(&keys[s], -1, key);
+    if (prev == -1) { *is_new = true; return (int)s; }
+    if (prev == key) { *is_new = false; return (int)s; }
+    s = (s + 1) & (CAP - 1);
+  }
+}
+
+// lane-0 replay of hypre_qsort2_abs (utilities/hypre_qsort.c:367-387) on shared-memory arrays
+__device__ void qsort2_abs_smem(int *v, double *w, int left, int right) {
+  int stack_l[40], stack_r[40];
+  int sp = 0;
+  while (true) {
+    while (left < right) {
+      int mid = (left + right) / 2;
+      int tv = v[left]; v[left] = v[mid]; v[mid] = tv;
+      double tw = w[left]; w[left] = w[mid]; w[mid] = tw;
+      int last = left;
+      const double piv = fabs(w[left]);
+      for (int i = left + 1; i <= right; i++) {
+        if (fabs(w[i]) > piv) {
+          ++last;
+          tv = v[last]; v[last] = v[i]; v[i] = tv;
+          tw = w[last]; w[last] = w[i]; w[i] = tw;
+        }
+      }
+      tv = v[left]; v[left] = v[last]; v[last] = tv;
+      tw = w[left]; w[left] = w[last]; w[last] = tw;
+      int l1 = left, r1 = last - 1, l2 = last + 1, r2 = right;
+      if (r1 - l1 > r2 - l2) {
+        if (l1 < r1) { stack_l[sp] = l1; stack_r[sp] = r1; sp++; }
+        left = l2; right = r2;
+      } else {
+        if (l2 < r2) { stack_l[sp] = l2; stack_r[sp] = r2; sp++; }
+        left = l1; right = r1;
+      }
+    }
+    if (sp == 0) break;
+    --sp;
+    left = stack_l[sp]; right = stack_r[sp];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// ext+i interpolation + truncation, one warp per fine row, output rows of <= pmax entries
+// written with stride pmax (par_lr_interp.c:1301-1416, :1523-1803; par_csr_matrix.c:2768-3020)
+// ------------------------------------------------------------------------------------------
+template <int CAP>
+__global__ void __launch_bounds__(32 * WPB)
+extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                  const int *__restrict__ S_i, const int *__restrict__ S_j, const int *__restrict__ cf,
+                  const int *__restrict__ f2c, double trunc_tol, int pmax, int *__restrict__ out_j,
+                  double *__restrict__ out_a, int *__restrict__ out_cnt, int *__restrict__ overflow,
+                  const int *__restrict__ rows) {
+  constexpr int LIMIT = CAP / 2;      // max occupied slots (C-hat members + strong-F markers)
+  extern __shared__ unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // per-warp layout: ra[LIMIT] doubles | keys[CAP] | vals[CAP] | rj[LIMIT]
+  unsigned char *base = smem_raw + (size_t)warp * (sizeof(double) * LIMIT + sizeof(int) * (2 * CAP + LIMIT));
+  double *ra = reinterpret_cast<double *>(base);
+  int *keys = reinterpret_cast<int *>(base + sizeof(double) * LIMIT);
+  int *vals = keys + CAP;
+  int *rj = vals + CAP;
+  const unsigned ltmask = (1u << lane) - 1u;
+  const int nwarps = gridDim.x * WPB;
+  for (int idx = blockIdx.x * WPB + warp; idx < n; idx += nwarps) {
+    const int i = rows ? rows[idx] : idx;         // second pass: list of rows still pending
+    if (out_cnt[i] != PENDING) continue;          // finished by an earlier (smaller-table) pass
+    const int c = cf[i];
+    if (c >= 0) {
+      if (lane == 0) { out_j[(size_t)i * pmax] = f2c[i]; out_a[(size_t)i * pmax] = 1.0; out_cnt[i] = 1; }
+      continue;
+    }
+    if (c == -3) { if (lane == 0) out_cnt[i] = 0; continue; }
+    for (int s = lane; s < CAP; s += 32) keys[s] = -1;
+    __syncwarp();
+    int count = 0, used = 0;
+    bool over = false;
+    // ---- discovery of C-hat_i in the reference's order -----------------------------------
+    for (int jj = S_i[i]; jj < S_i[i + 1] && !over; jj++) {
+      const int i1 = S_j[jj];
+      const int c1 = cf[i1];
+      if (c1 >= 0) {
+        if (used + 1 > LIMIT) { over = true; break; }
+        int isn = 0;
+        if (lane == 0) {
+          bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
+          if (nw) { vals[slot] = count; rj[count] = f2c[i1]; ra[count] = 0.0; isn = 1; }
+        }
+        isn = __shfl_sync(FULL, isn, 0);
+        count += isn; used += isn;
+        __syncwarp();
+      } else if (c1 != -3) {
+        if (used + 1 > LIMIT) { over = true; break; }
+        int isn = 0;
+        if (lane == 0) {
+          bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
+          if (nw) { vals[slot] = STRONG_F; isn = 1; }
+        }
+        isn = __shfl_sync(FULL, isn, 0);
+        used += isn;
+        __syncwarp();
+        const int e1 = S_i[i1 + 1];
+        for (int kk0 = S_i[i1]; kk0 < e1; kk0 += 32) {
+          if (used + min(32, e1 - kk0) > LIMIT) { over = true; break; }
+          const int kk = kk0 + lane;
+          int k1 = -1;
+          bool want = false;
+          if (kk < e1) { k1 = S_j[kk]; want = cf[k1] >= 0; }
+          bool nw = false;
+          int slot = 0;
+          if (want) slot = wt_insert<CAP>(keys, k1, &nw);
+          const unsigned newmask = __ballot_sync(FULL, nw);
+          if (nw) {
+            const int pos = count + __popc(newmask & ltmask);
+            vals[slot] = pos; rj[pos] = f2c[k1]; ra[pos] = 0.0;
+          }
+          const int nn = __popc(newmask);
+          count += nn; used += nn;
+          __syncwarp();
+        }
+      }
+    }
+    if (over) {                                   // stays PENDING for the next, larger pass
+      if (lane == 0) atomicExch(overflow, 1);
+      __syncwarp();
+      continue;
+    }
+    if (count == 0) { if (lane == 0) out_cnt[i] = 0; __syncwarp(); continue; }
+    // ---- weights, reference accumulation order ---------------------------------------------
+    double diagonal = A_a[A_i[i]];
+    const int eA = A_i[i + 1];
+    for (int jj = A_i[i] + 1; jj < eA; jj++) {
+      const int i1 = A_j[jj];
+      const double aij = A_a[jj];
+      const int m1 = wt_find<CAP>(keys, vals, i1);
+      if (m1 >= 0) {
+        if (lane == 0) ra[m1] += aij;
+      } else if (m1 == STRONG_F) {
+        const int b1 = A_i[i1] + 1, e1 = A_i[i1 + 1];
+        const int sgn = (A_a[A_i[i1]] < 0) ? -1 : 1;
+        double sum = 0.0;
+        for (int k0 = b1; k0 < e1; k0 += 32) {
+          const int k = k0 + lane;
+          double contrib = 0.0;
+          if (k < e1) {
+            const double a = A_a[k];
+            if ((sgn * a) < 0) {
+              const int i2 = A_j[k];
+              if (i2 == i || wt_find<CAP>(keys, vals, i2) >= 0) contrib = a;
+            }
+          }
+          const unsigned any = __ballot_sync(FULL, contrib != 0.0);
+          if (any) {
+#pragma unroll
+            for (int l = 0; l < 32; l++) sum += __shfl_sync(FULL, contrib, l);   // lane order == entry order
+          }
+        }
+        if (sum != 0) {
+          const double distribute = aij / sum;
+          for (int k0 = b1; k0 < e1; k0 += 32) {
+            const int k = k0 + lane;
+            int q = NOTFOUND;
+            double a = 0.0;
+            if (k < e1) {
+              a = A_a[k];
+              if ((sgn * a) < 0) {
+                const int i2 = A_j[k];
+                q = (i2 == i) ? SELF : wt_find<CAP>(keys, vals, i2);
+              }
+            }
+            if (q >= 0) ra[q] += distribute * a;            // distinct q across the lanes of one row
+            const unsigned selfmask = __ballot_sync(FULL, q == SELF);
+            if (selfmask) {
+              const double d = __shfl_sync(FULL, distribute * a, __ffs(selfmask) - 1);
+              diagonal += d;
+            }
+          }
+        } else {
+          diagonal += aij;
+        }
+      } else if (cf[i1] != -3) {
+        diagonal += aij;
+      }
+      __syncwarp();
+    }
+    if (diagonal) {
+      for (int p = lane; p < count; p += 32) ra[p] /= -diagonal;
+    }
+    __syncwarp();
+    // ---- truncation (lane 0 replays the sequential algorithm on the shared row) -------------
+    int len = count;
+    if (lane == 0) {
+      if (trunc_tol > 0) {
+        double row_nrm = 0;
+        for (int j = 0; j < len; j++) row_nrm = (row_nrm < fabs(ra[j])) ? fabs(ra[j]) : row_nrm;
+        const double drop = trunc_tol * row_nrm;
+        double row_sum = 0, scale = 0;
+        int keep = 0;
+        for (int j = 0; j < len; j++) {
+          row_sum += ra[j];
+          if (!(fabs(ra[j]) < drop)) { scale += ra[j]; ra[keep] = ra[j]; rj[keep] = rj[j]; keep++; }
+        }
+        len = keep;
+        if (scale != 0. && scale != row_sum) {
+          scale = row_sum / scale;
+          for (int j = 0; j < len; j++) ra[j] *= scale;
+        }
+      }
+      if (len > pmax) {
+        double row_sum = 0;
+        for (int j = 0; j < len; j++) row_sum += ra[j];
+        qsort2_abs_smem(rj, ra, 0, len - 1);
+        double scale = 0;
+        for (int j = 0; j < pmax; j++) scale += ra[j];
+        len = pmax;
+        if (scale != 0. && scale != row_sum) {
+          scale = row_sum / scale;
+          for (int j = 0; j < len; j++) ra[j] *= scale;
+        }
+      }
+      out_cnt[i] = len;
+    }
+    len = __shfl_sync(FULL, len, 0);
+    __syncwarp();
+    for (int p = lane; p < len; p += 32) { out_j[(size_t)i * pmax + p] = rj[p]; out_a[(size_t)i * pmax + p] = ra[p]; }
+    __syncwarp();
+  }
+}
+
+__global__ void strided_to_csr_kernel(int n, int stride, const int *__restrict__ P_i, const int *__restrict__ sj,
+                                      const double *__restrict__ sa, int *__restrict__ P_j, double *__restrict__ P_a) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int d = P_i[r], len = P_i[r + 1] - d;
+  for (int k = 0; k < len; k++) { P_j[d + k] = sj[(size_t)r * stride + k]; P_a[d + k] = sa[(size_t)r * stride + k]; }
+}
+
+// ------------------------------------------------------------------------------------------
+// SpGEMM, one warp per row of C (csr_matop.c:375-468).
+// GB lanes serve one entry a_{ic,ja} and walk row ja of B; 32/GB entries of A are in flight per
+// step.  GB < 32 is used only when every row of B has at most GB entries, so a step holds whole
+// B rows and the products of a step are in the reference's (ia, ib) order across lanes.
+// Products of one step that hit the same column are found with __match_any_sync and applied in
+// lane order; new columns take their first-touch positions from a ballot prefix.
+// ------------------------------------------------------------------------------------------
+template <int CAP, int GB, bool NUMERIC>
+__global__ void __launch_bounds__(32 * WPB)
+spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                   const int *__restrict__ B_i, const int *__restrict__ B_j, const double *__restrict__ B_a,
+                   int allsquare, const int *__restrict__ rows, int *__restrict__ cnt,
+                   const int *__restrict__ C_i, int *__restrict__ C_j, double *__restrict__ C_a,
+                   int *__restrict__ overflow) {
+  constexpr int LIMIT = CAP / 2;
+  constexpr int APS = 32 / GB;                      // A entries per step
+  extern __shared__ unsigned char smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t per_warp = NUMERIC ? (sizeof(double) * LIMIT + sizeof(int) * (2 * CAP + LIMIT)) : (sizeof(int) * CAP);
+  unsigned char *base = smem_raw + (size_t)warp * per_warp;
+  double *acc = reinterpret_cast<double *>(base);
+  int *keys = NUMERIC ? reinterpret_cast<int *>(base + sizeof(double) * LIMIT) : reinterpret_cast<int *>(base);
+  int *vals = keys + CAP;
+  int *cols = vals + CAP;
+  const unsigned ltmask = (1u << lane) - 1u;
+  const int nwarps = gridDim.x * WPB;
+  const int sub = lane % GB, grp_id = lane / GB;
+  for (int idx = blockIdx.x * WPB + warp; idx < n; idx += nwarps) {
+    const int ic = rows ? rows[idx] : idx;          // rows of one size class / rows still pending
+    if (!NUMERIC && cnt[ic] != PENDING) continue;
+    for (int s = lane; s < CAP; s += 32) keys[s] = -1;
+    __syncwarp();
+    int count = 0;
+    bool over = false;
+    if (allsquare) {                                // diagonal first (:384-388, :442-448)
+      if (lane == 0) {
+        bool nw; int slot = wt_insert<CAP>(keys, ic, &nw);
+        if (NUMERIC) { vals[slot] = 0; cols[0] = ic; acc[0] = 0.0; }
+      }
+      count = 1;
+      __syncwarp();
+    }
+    const int eA = A_i[ic + 1];
+    for (int ia0 = A_i[ic]; ia0 < eA && !over; ia0 += APS) {
+      const int ia = ia0 + grp_id;
+      int ja = -1, bB = 0, eB = 0;
+      double a = 0.0;
+      if (ia < eA) { ja = A_j[ia]; bB = B_i[ja]; eB = B_i[ja + 1]; if (NUMERIC) a = A_a[ia]; }
+      // GB == 32: one A entry per step, B row walked in chunks of 32 (order preserved: chunks are sequential)
+      int maxlen = eB - bB;
+      if (GB == 32) maxlen = __shfl_sync(FULL, maxlen, 0);
+      const int nchunk = (GB == 32) ? (maxlen + 31) / 32 : 1;
+      for (int ch = 0; ch < nchunk; ch++) {
+        const int ib = bB + ch * GB + sub;
+        const bool valid = ib < eB;
+        const unsigned vm = __ballot_sync(FULL, valid);
+        if (vm == 0) continue;
+        if (!NUMERIC && count + __popc(vm) > LIMIT) { over = true; break; }   // numeric tables are sized from the symbolic count
+        int jb = -1;
+        double prod = 0.0;
+        if (valid) { jb = B_j[ib]; if (NUMERIC) prod = a * B_a[ib]; }
+        unsigned grp = 0;
+        if (valid) grp = __match_any_sync(vm, jb);
+        const int leader = valid ? (__ffs(grp) - 1) : lane;
+        const bool is_leader = valid && leader == lane;
+        bool nw = false;
+        int slot = 0;
+        if (is_leader) slot = wt_insert<CAP>(keys, jb, &nw);
+        const unsigned newmask = __ballot_sync(FULL, nw);
+        if (NUMERIC) {
+          if (nw) {
+            const int pos = count + __popc(newmask & ltmask);
+            vals[slot] = pos; cols[pos] = jb; acc[pos] = 0.0;      // 0 + a*b == a*b: same as the first-touch store
+          }
+          slot = __shfl_sync(FULL, slot, leader);
+          __syncwarp();
+          const int rank = __popc(grp & ltmask);
+          int maxrank = valid ? __popc(grp) : 0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) maxrank = max(maxrank, __shfl_xor_sync(FULL, maxrank, off));
+          for (int r = 0; r < maxrank; r++) {
+            if (valid && rank == r) acc[vals[slot]] += prod;
+            __syncwarp();
+          }
+        }
+        count += __popc(newmask);
+        __syncwarp();
+      }
+    }
+    if (over) {
+      if (lane == 0) atomicExch(overflow, 1);       // symbolic: row stays PENDING; numeric never overflows (sized by cnt)
+      __syncwarp();
+      continue;
+    }
+    if (!NUMERIC) {
+      if (lane == 0) cnt[ic] = count;
+    } else {
+      const int start = C_i[ic];
+      for (int p = lane; p < count; p += 32) { C_j[start + p] = cols[p]; C_a[start + p] = acc[p]; }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void max_rowlen_kernel(int n, const int *__restrict__ A_i, int *__restrict__ out_max) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = i < n ? A_i[i + 1] - A_i[i] : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_down_sync(FULL, len, off));
+  if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out_max, len);
+}
+__global__ void extpi_max_ub_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ S_j,
+                                    const int *__restrict__ cf, int *__restrict__ out_max) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int ub = 0;
+  if (i < n && cf[i] < 0 && cf[i] != -3) {
+    for (int jj = S_i[i]; jj < S_i[i + 1]; jj++) {
+      int i1 = S_j[jj];
+      ub += 1;
+      if (cf[i1] < 0 && cf[i1] != -3) ub += S_i[i1 + 1] - S_i[i1];
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) ub = max(ub, __shfl_down_sync(FULL, ub, off));
+  if ((threadIdx.x & 31) == 0 && ub > 0) atomicMax(out_max, ub);
+}
+__global__ void fill_int_kernel(size_t n, int v, int *x) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = v;
+}
+
+// flag[i] = 1 when lo < cnt[i] <= hi  (pending rows: lo = hi = PENDING selects cnt == PENDING)
+__global__ void class_flag_kernel(int n, const int *__restrict__ cnt, int lo, int hi, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { flag[n] = 0; return; }
+  const int c = cnt[i];
+  flag[i] = (lo == PENDING && hi == PENDING) ? (c == PENDING) : (c > lo && c <= hi);
+}
+__global__ void class_scatter_kernel(int n, const int *__restrict__ cnt, int lo, int hi, const int *__restrict__ pos,
+                                     int *__restrict__ list) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cnt[i];
+  const bool in = (lo == PENDING && hi == PENDING) ? (c == PENDING) : (c > lo && c <= hi);
+  if (in) list[pos[i]] = i;
+}
+
+template <class K>
+int set_smem(K kernel, size_t bytes) {
+  if (bytes > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+inline int warp_grid(b200_handle h, int n, int blocks_per_sm) {
+  long long need = ((long long)n + WPB - 1) / WPB;
+  long long cap = (long long)h->num_sm * blocks_per_sm;
+  return (int)(need < cap ? (need > 0 ? need : 1) : cap);
+}
+inline int fill_grid(b200_handle h, size_t n) {
+  size_t g = (n + 255) / 256, cap = (size_t)h->num_sm * 8;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+// order-preserving list of the rows whose count lies in (lo, hi] (or is PENDING)
+int build_row_list(b200_handle h, int n, const int *cnt, int lo, int hi, int **list_out, int *count_out) {
+  int *pos = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &pos, (size_t)n + 1));
+  class_flag_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, cnt, lo, hi, pos);
+  B200_LAUNCH_CHECK();
+  B200_TRY(b200_exclusive_scan_inplace(h, pos, (size_t)n + 1));
+  int m = 0;
+  B200_CUDA(cudaMemcpyAsync(&m, pos + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  int *list = nullptr;
+  if (m > 0) {
+    B200_TRY(b200_dalloc<int>(h, &list, m));
+    class_scatter_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, cnt, lo, hi, pos, list);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_dfree(h, pos));
+  *list_out = list;
+  *count_out = m;
+  return 0;
+}
+
+}  // namespace
+
+int b200_coarse_map(b200_handle h, int n, const int *d_cf, int **f2c_out, int *ncoarse);
+
+// returns 0 and *done = 1 when the warp path produced P; *done = 0 -> caller must use the general path
+int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor, int max_elmts,
+                           b200_csr *out, int *done) {
+  *done = 0;
+  if (max_elmts <= 0) return 0;                       // unbounded rows: general path
+  const int n = A->nrows;
+  if (n == 0) return 0;
+  // stencil-sized rows: the dependent-load chain per row is short and thread-per-row keeps 32x more
+  // rows in flight than a warp per row -> the general kernels win there (profiles/README.md r1_b)
+  if ((double)A->nnz / n <= 10.0) return 0;
+  int *d_flag = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
+  int *f2c = nullptr, ncoarse = 0;
+  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
+  int *sj = nullptr, *cnt = nullptr;
+  double *sa = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &sj, (size_t)n * max_elmts));
+  B200_TRY(b200_dalloc<double>(h, &sa, (size_t)n * max_elmts));
+  B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
+  fill_int_kernel<<<fill_grid(h, n), 256, 0, h->stream>>>((size_t)n, PENDING, cnt);
+  B200_LAUNCH_CHECK();
+  B200_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), h->stream));
+  int flag = 1;
+  for (int pass = 0; pass < 2 && flag; pass++) {
+    B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+    int *rows = nullptr, m = n;
+    if (pass == 1) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
+#define B200_EXTPI_LAUNCH(CAPV, BPS)                                                                              \
+    {                                                                                                             \
+      constexpr int CAP = CAPV;                                                                                   \
+      const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));        \
+      B200_TRY(set_smem(extpi_warp_kernel<CAP>, bytes));                                                          \
+      extpi_warp_kernel<CAP><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                               \
+          m, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor, max_elmts, sj, sa, cnt, d_flag, rows);        \
+    }
+    if (m > 0) {
+      if (pass == 0) B200_EXTPI_LAUNCH(256, 16)
+      else B200_EXTPI_LAUNCH(1024, 3)
+      B200_LAUNCH_CHECK();
+    }
+#undef B200_EXTPI_LAUNCH
+    B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, rows));
+  }
+  if (flag) {                                         // some row outgrew even the large shared table
+    B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa)); B200_TRY(b200_dfree(h, cnt));
+    B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, d_flag));
+    return 0;
+  }
+  B200_TRY(b200_exclusive_scan_inplace(h, cnt, (size_t)n + 1));
+  int nnz = 0;
+  B200_CUDA(cudaMemcpyAsync(&nnz, cnt + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  b200_csr P = nullptr;
+  B200_TRY(b200_csr_alloc(h, n, ncoarse, nnz, true, &P));
+  B200_CUDA(cudaMemcpyAsync(P->i, cnt, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+  strided_to_csr_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, max_elmts, P->i, sj, sa, P->j, P->a);
+  B200_LAUNCH_CHECK();
+  B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa)); B200_TRY(b200_dfree(h, cnt));
+  B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, d_flag));
+  B200_TRY(b200_csr_build_plan(h, P));
+  *out = P;
+  *done = 1;
+  return 0;
+}
+
+template <int GB>
+static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare, b200_csr *out, int *done) {
+  const int n = A->nrows;
+  int *cnt = nullptr, *d_flag = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
+  B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
+  fill_int_kernel<<<fill_grid(h, n), 256, 0, h->stream>>>((size_t)n, PENDING, cnt);
+  B200_LAUNCH_CHECK();
+  B200_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), h->stream));
+  // symbolic: small tables first, rows that overflow are retried with the large table
+  int flag = 1;
+  for (int pass = 0; pass < 2 && flag; pass++) {
+    B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+    if (pass == 0) {
+      constexpr int CAP = 256;
+      const size_t bytes = (size_t)WPB * sizeof(int) * CAP;
+      spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, n, 16), 32 * WPB, bytes, h->stream>>>(
+          n, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, nullptr, cnt, nullptr, nullptr, nullptr, d_flag);
+      B200_LAUNCH_CHECK();
+    } else {
+      constexpr int CAP = 2048;
+      const size_t bytes = (size_t)WPB * sizeof(int) * CAP;
+      int *rows = nullptr, m = 0;
+      B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
+      if (m > 0) {
+        spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, m, 6), 32 * WPB, bytes, h->stream>>>(
+            m, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, rows, cnt, nullptr, nullptr, nullptr, d_flag);
+        B200_LAUNCH_CHECK();
+      }
+      B200_TRY(b200_dfree(h, rows));
+    }
+    B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (flag) { B200_TRY(b200_dfree(h, cnt)); B200_TRY(b200_dfree(h, d_flag)); return 0; }
+  int *C_i = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &C_i, (size_t)n + 1));
+  B200_CUDA(cudaMemcpyAsync(C_i, cnt, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+  B200_TRY(b200_exclusive_scan_inplace(h, C_i, (size_t)n + 1));
+  int nnz = 0;
+  B200_CUDA(cudaMemcpyAsync(&nnz, C_i + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  b200_csr C = nullptr;
+  B200_TRY(b200_csr_alloc(h, n, B->ncols, nnz, true, &C));
+  B200_CUDA(cudaMemcpyAsync(C->i, C_i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+  B200_TRY(b200_dfree(h, C_i));
+  // numeric: one launch per size class (order-preserving row lists), each with the smallest table that holds the row
+#define B200_SPGEMM_NUMERIC(CAPV, LO, BPS)                                                                        \
+  {                                                                                                               \
+    constexpr int CAP = CAPV;                                                                                     \
+    const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));          \
+    int *rows = nullptr, m = 0;                                                                                   \
+    B200_TRY(build_row_list(h, n, cnt, LO, CAP / 2, &rows, &m));                                                  \
+    if (m > 0) {                                                                                                  \
+      B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, true>, bytes));                                               \
+      spgemm_warp_kernel<CAP, GB, true><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                    \
+          m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, rows, cnt, C->i, C->j, C->a, d_flag);                 \
+      B200_LAUNCH_CHECK();                                                                                        \
+    }                                                                                                             \
+    B200_TRY(b200_dfree(h, rows));                                                                                \
+  }
+  B200_SPGEMM_NUMERIC(128, 0, 16)        // rows of 1..64 entries
+  B200_SPGEMM_NUMERIC(512, 64, 7)        // 65..256
+  B200_SPGEMM_NUMERIC(2048, 256, 1)      // 257..1024 (the symbolic pass guarantees <= 1024)
+#undef B200_SPGEMM_NUMERIC
+  B200_TRY(b200_dfree(h, cnt)); B200_TRY(b200_dfree(h, d_flag));
+  B200_TRY(b200_csr_build_plan(h, C));
+  *out = C;
+  *done = 1;
+  return 0;
+}
+
+int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, b200_csr *out, int *done) {
+  *done = 0;
+  const int n = A->nrows;
+  if (n == 0) return 0;
+  const int allsquare = (A->nrows == B->ncols) ? 1 : 0;
+  int *d_max = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &d_max, 1));
+  B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+  if (B->nrows) {
+    max_rowlen_kernel<<<b200_grid(B->nrows, 256), 256, 0, h->stream>>>(B->nrows, B->i, d_max);
+    B200_LAUNCH_CHECK();
+  }
+  int maxlen = 0;
+  B200_CUDA(cudaMemcpyAsync(&maxlen, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  B200_TRY(b200_dfree(h, d_max));
+  if (maxlen <= 4) return spgemm_warp_run<4>(h, A, B, allsquare, out, done);
+  if (maxlen <= 8) return spgemm_warp_run<8>(h, A, B, allsquare, out, done);
+  if (maxlen <= 16) return spgemm_warp_run<16>(h, A, B, allsquare, out, done);
+  return spgemm_warp_run<32>(h, A, B, allsquare, out, done);
+}

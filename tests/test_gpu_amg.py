@@ -223,3 +223,25 @@ def test_unsupported_configurations_fail_loudly(handle):
             amg.setup(A)
         amg.destroy()
     A.destroy()
+
+
+def test_general_hbm_scratch_path_is_identical(handle, monkeypatch):
+    """b200_setup.cu's thread-per-row kernels (used when a row outgrows the warp kernels' shared memory)
+    must give the same bits as the warp-per-row kernels."""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(["-n", 22, 19, 17, "-pmis", "-rlx", 18, "-mod_rap2", 1, "-keepT", 1])
+    for force in ("0", "1"):
+        monkeypatch.setenv("B200_FORCE_GENERAL_SETUP", force)
+        A = hb.ParCsr.laplacian(handle, 22, 19, 17)
+        amg = hb.Amg(handle)
+        amg.setup(A)
+        assert amg.num_levels == nlev(d)
+        for l in range(nlev(d)):
+            i, j, a = amg.level_A(l).download()
+            ri, rj, ra, _ = refio.csr(d, "A", l)
+            assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), (force, l)
+            if l < nlev(d) - 1:
+                i, j, a = amg.level_P(l).download()
+                pi, pj, pa, _ = refio.csr(d, "P", l)
+                assert np.array_equal(i, pi) and np.array_equal(j, pj) and np.array_equal(a, pa), (force, "P", l)
+        amg.destroy(); A.destroy()
