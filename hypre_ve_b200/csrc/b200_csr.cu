@@ -17,14 +17,22 @@
 
 namespace {
 
-constexpr int NT = 256;          // threads per CTA
-constexpr int CAP = 4096;        // shared-memory product slots per CTA (32 KB)
-constexpr int MAX_TILE = 2048;   // tile (nnz per CTA) upper bound; CAP - MAX_TILE bounds the longest row
+constexpr int NT = B200_SPMV_NT;              // threads per CTA
+constexpr int CAP = 4096;                     // shared-memory product slots per CTA (32 KB)
+constexpr int MAX_TILE = B200_SPMV_MAX_TILE;  // tile (nnz per CTA) upper bound; CAP - MAX_TILE bounds the longest row
 
-__global__ void plan_kernel(const int *__restrict__ A_i, int nrows, int tile, int nblk, int *blk_row) {
+__global__ void max_row_kernel(int n, const int *__restrict__ A_i, int *__restrict__ out_max) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int len = i < n ? A_i[i + 1] - A_i[i] : 0;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_down_sync(0xffffffffu, len, off));
+  if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out_max, len);
+}
+
+__global__ void plan_kernel(const int *__restrict__ A_i, int nrows, int tile, int nblk, int *blk_row, int *blk_ent) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblk) return;
-  if (b == nblk) { blk_row[b] = nrows; return; }
+  if (b == nblk) { blk_row[b] = nrows; blk_ent[b] = A_i[nrows]; return; }
   long long target = (long long)b * tile;
   int lo = 0, hi = nrows;          // first r in [0,nrows] with A_i[r] >= target
   while (lo < hi) {
@@ -32,6 +40,12 @@ __global__ void plan_kernel(const int *__restrict__ A_i, int nrows, int tile, in
     if ((long long)A_i[mid] >= target) hi = mid; else lo = mid + 1;
   }
   blk_row[b] = lo;
+  blk_ent[b] = A_i[lo];
+}
+
+__global__ void meta_kernel(int nblk, const int *__restrict__ blk_row, const int *__restrict__ blk_ent, int4 *__restrict__ meta) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nblk) meta[b] = make_int4(blk_row[b], blk_row[b + 1], blk_ent[b], blk_ent[b + 1]);
 }
 
 struct Epi {
@@ -123,10 +137,16 @@ __global__ void scale_copy_kernel(int n, double beta, const double *__restrict__
 
 }  // namespace
 
+bool b200_spmv_pipe_ok(b200_csr A);
+int b200_csr_spmv_pipe(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha, double beta,
+                       const double *b, const double *d);
+
 int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha,
                       double beta, const double *b, const double *d) {
   if (A->nrows == 0) return 0;
   if (!A->blk_row) B200_TRY(b200_csr_build_plan(h, A));
+  static const bool force_v1 = [] { const char *e = getenv("B200_SPMV_TWO_PHASE"); return e && e[0] == '1'; }();
+  if (!force_v1 && b200_spmv_pipe_ok(A)) return b200_csr_spmv_pipe(h, A, x, y, mode, alpha, beta, b, d);
   Epi e{mode, alpha, beta, b, d};
   switch (A->group) {
     case 1:  return launch_stream<1>(h, A, x, y, e);
@@ -150,16 +170,36 @@ int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data,
 
 int b200_csr_build_plan(b200_handle h, b200_csr A) {
   if (A->blk_row) { B200_TRY(b200_dfree(h, A->blk_row)); A->blk_row = nullptr; }
+  if (A->blk_ent) { B200_TRY(b200_dfree(h, A->blk_ent)); A->blk_ent = nullptr; }
+  if (A->blk_meta) { B200_TRY(b200_dfree(h, A->blk_meta)); A->blk_meta = nullptr; }
   double avg = A->nrows ? (double)A->nnz / A->nrows : 0.0;
   int G = avg <= 10 ? 1 : avg <= 20 ? 2 : avg <= 40 ? 4 : avg <= 80 ? 8 : avg <= 160 ? 16 : 32;
   int tile = (int)(avg * (NT / G) * 0.97);
   if (tile > MAX_TILE) tile = MAX_TILE;
-  if (tile < 256) tile = 256;
+  if (tile < 128) tile = 128;
   A->group = G;
+  A->tile = tile;
   A->nblk = A->nnz > 0 ? (int)(((long long)A->nnz + tile - 1) / tile) : 1;
   B200_TRY(b200_dalloc<int>(h, &A->blk_row, (size_t)A->nblk + 1));
-  plan_kernel<<<b200_grid((size_t)A->nblk + 1, 256), 256, 0, h->stream>>>(A->i, A->nrows, tile, A->nblk, A->blk_row);
+  B200_TRY(b200_dalloc<int>(h, &A->blk_ent, (size_t)A->nblk + 1));
+  plan_kernel<<<b200_grid((size_t)A->nblk + 1, 256), 256, 0, h->stream>>>(A->i, A->nrows, tile, A->nblk, A->blk_row,
+                                                                          A->blk_ent);
   B200_LAUNCH_CHECK();
+  B200_TRY(b200_dalloc<int>(h, &A->blk_meta, (size_t)4 * A->nblk));
+  meta_kernel<<<b200_grid((size_t)A->nblk, 256), 256, 0, h->stream>>>(A->nblk, A->blk_row, A->blk_ent,
+                                                                      reinterpret_cast<int4 *>(A->blk_meta));
+  B200_LAUNCH_CHECK();
+  A->max_row = 0;
+  if (A->nrows) {
+    int *d_max = nullptr;
+    B200_TRY(b200_dalloc<int>(h, &d_max, 1));
+    B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
+    max_row_kernel<<<b200_grid(A->nrows, 256), 256, 0, h->stream>>>(A->nrows, A->i, d_max);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(&A->max_row, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, d_max));
+  }
   return 0;
 }
 
@@ -203,6 +243,8 @@ extern "C" int b200_csr_destroy(b200_handle h, b200_csr A) {
     B200_TRY(b200_dfree(h, A->a));
   }
   B200_TRY(b200_dfree(h, A->blk_row));
+  B200_TRY(b200_dfree(h, A->blk_ent));
+  B200_TRY(b200_dfree(h, A->blk_meta));
   delete A;
   return 0;
 }

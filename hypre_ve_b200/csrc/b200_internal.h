@@ -10,6 +10,9 @@
 #include "../../include/hypre_b200.h"
 
 #define B200_NUM_SM_FALLBACK 148
+// streaming SpMV geometry shared by the row-block plan and both kernels
+#define B200_SPMV_NT 128          // threads per CTA
+#define B200_SPMV_MAX_TILE 1024   // upper bound on the entries of one tile
 
 struct b200_pool_s;   // slab sub-allocator (b200_runtime.cu)
 
@@ -36,9 +39,12 @@ struct b200_csr_s {
   bool owns = true;
   // streaming-SpMV plan: block b owns rows [blk_row[b], blk_row[b+1])
   int *blk_row = nullptr;
+  int *blk_ent = nullptr; // first entry of each tile: i[blk_row[b]]  [nblk+1]
+  int *blk_meta = nullptr; // int4 per tile {row0,row1,ent0,ent1} for the pipelined kernel [4*nblk]
   int  nblk = 0;
   int  group = 1;         // threads cooperating on one row in the reduce phase
   int  max_row = 0;
+  int  tile = 0;          // entries per tile the plan was cut with
 };
 
 struct b200_halo_s;   // multi-rank halo plan (b200_parcsr.cu)
