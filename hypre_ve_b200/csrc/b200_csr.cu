@@ -29,6 +29,43 @@ __global__ void max_row_kernel(int n, const int *__restrict__ A_i, int *__restri
   if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out_max, len);
 }
 
+// Gather-cost model for choosing G (lanes per row): for a sample of 32-row windows, count the
+// distinct 128-byte lines of x one warp-wide gather would touch under each candidate G -- that is
+// the number of L1 wavefronts the load costs, and L1 wavefronts are what bound the SpMV once the
+// matrix stream is staged by bulk copies.  Banded stencils come out cheapest at G = 1 (lanes own
+// consecutive rows: their p-th columns are adjacent), irregular coarse operators at G = 16/32.
+__global__ void gather_cost_kernel(int nrows, const int *__restrict__ A_i, const int *__restrict__ A_j, int nwin,
+                                   int stride, unsigned long long *__restrict__ cost /* [6][2] */) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= nwin) return;
+  const int rbase = (int)(((long long)w * stride) * 32);
+  for (int gi = 0; gi < 6; gi++) {
+    const int G = 1 << gi, rows_per = 32 / G;
+    unsigned long long wf = 0, ent = 0;
+    for (int rb = 0; rb < G; rb++) {               // the 32 rows are covered by G passes of 32/G rows
+      const int row = rbase + rb * rows_per + lane / G;
+      const int ln = lane % G;
+      int s0 = 0, s1 = 0;
+      if (row < nrows) { s0 = A_i[row]; s1 = A_i[row + 1]; }
+      int maxlen = s1 - s0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xffffffffu, maxlen, off));
+      for (int p0 = 0; p0 < maxlen; p0 += G) {
+        const int e = s0 + p0 + ln;
+        const bool valid = e < s1;
+        const int line = valid ? (A_j[e] >> 4) : (-1 - lane);
+        const unsigned m = __match_any_sync(0xffffffffu, line);
+        const unsigned lead = __ballot_sync(0xffffffffu, valid && (__ffs(m) - 1 == lane));
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        wf += __popc(lead);
+        ent += __popc(vm);
+      }
+    }
+    if (lane == 0) { atomicAdd(&cost[2 * gi], wf); atomicAdd(&cost[2 * gi + 1], ent); }
+  }
+}
+
 __global__ void plan_kernel(const int *__restrict__ A_i, int nrows, int tile, int nblk, int *blk_row, int *blk_ent) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > nblk) return;
@@ -173,10 +210,46 @@ int b200_csr_build_plan(b200_handle h, b200_csr A) {
   if (A->blk_ent) { B200_TRY(b200_dfree(h, A->blk_ent)); A->blk_ent = nullptr; }
   if (A->blk_meta) { B200_TRY(b200_dfree(h, A->blk_meta)); A->blk_meta = nullptr; }
   double avg = A->nrows ? (double)A->nnz / A->nrows : 0.0;
-  int G = avg <= 10 ? 1 : avg <= 20 ? 2 : avg <= 40 ? 4 : avg <= 80 ? 8 : avg <= 160 ? 16 : 32;
-  int tile = (int)(avg * (NT / G) * 0.97);
+  int G = 1;
+  if (A->nnz > 0 && A->nrows >= 64) {
+    // pick the lanes-per-row that minimises gather wavefronts per entry on a sample of the matrix
+    const int windows = A->nrows / 32;
+    const int nwin = windows < 2048 ? windows : 2048;
+    const int stride = windows / nwin;
+    unsigned long long *d_cost = nullptr, h_cost[12];
+    B200_TRY(b200_dalloc<unsigned long long>(h, &d_cost, 12));
+    B200_CUDA(cudaMemsetAsync(d_cost, 0, sizeof(h_cost), h->stream));
+    gather_cost_kernel<<<b200_grid((size_t)nwin * 32, 128), 128, 0, h->stream>>>(A->nrows, A->i, A->j, nwin, stride, d_cost);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(h_cost), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, d_cost));
+    // lanes-per-row must keep the CTA busy: a tile of MAX_TILE entries holds MAX_TILE/avg rows, so fewer
+    // than avg*NT/MAX_TILE lanes per row would leave threads idle
+    int gmin = 1;
+    while (gmin < 32 && gmin * MAX_TILE < avg * NT) gmin <<= 1;
+    double best = 1e300;
+    static const bool dbg2 = [] { const char *e = getenv("B200_DEBUG_PLAN"); return e && e[0] == '1'; }();
+    for (int gi = 0; gi < 6; gi++) {
+      const int g = 1 << gi;
+      if (g < gmin) continue;
+      if (g > gmin && g > 2 * avg) break;          // more lanes than a row has entries: mostly idle
+      const double c = (double)h_cost[2 * gi] / (double)(h_cost[2 * gi + 1] ? h_cost[2 * gi + 1] : 1);
+      if (dbg2) fprintf(stderr, "[b200 plan]   G=%d wavefronts/entry=%.3f\n", g, c);
+      if (c < best * 0.85) { best = c; G = g; }    // widen only for a clear (15%) saving in L1 wavefronts
+    }
+    if (G < gmin) G = gmin;
+  }
+  // tile: a whole number of row passes (NT/G rows each), close to MAX_TILE entries
+  double per_pass = avg * (NT / G);
+  int passes = per_pass > 0 ? (int)(MAX_TILE / per_pass) : 1;
+  if (passes < 1) passes = 1;
+  if (passes * (NT / G) > 160) passes = 160 / (NT / G) > 0 ? 160 / (NT / G) : 1;   // row pointers staged per tile
+  int tile = (int)(per_pass * passes * 0.97);
   if (tile > MAX_TILE) tile = MAX_TILE;
   if (tile < 128) tile = 128;
+  static const bool dbg = [] { const char *e = getenv("B200_DEBUG_PLAN"); return e && e[0] == '1'; }();
+  if (dbg) fprintf(stderr, "[b200 plan] rows=%d nnz=%d avg=%.1f G=%d passes=%d tile=%d\n", A->nrows, A->nnz, avg, G, passes, tile);
   A->group = G;
   A->tile = tile;
   A->nblk = A->nnz > 0 ? (int)(((long long)A->nnz + tile - 1) / tile) : 1;

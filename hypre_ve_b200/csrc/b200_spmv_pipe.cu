@@ -121,21 +121,11 @@ spmv_pipe_kernel(const int *__restrict__ A_i, const int *__restrict__ A_j, const
       else { bf = epi.b[rfirst]; df = epi.d[rfirst]; xf = x[rfirst]; }
     }
     mbar_wait(&full[stage], parity);
-    const int len = e1 - a0;
-#pragma unroll 2
-    for (int q = 4 * tid; q < len; q += 4 * NT) {
-      const int4 c = *reinterpret_cast<const int4 *>(pc + q);
-      double2 v0 = *reinterpret_cast<double2 *>(pv + q);
-      double2 v1 = *reinterpret_cast<double2 *>(pv + q + 2);
-      const int g = a0 + q;
-      v0.x = (g     >= e0 && g     < e1) ? v0.x * __ldg(x + c.x) : 0.0;
-      v0.y = (g + 1 >= e0 && g + 1 < e1) ? v0.y * __ldg(x + c.y) : 0.0;
-      v1.x = (g + 2 >= e0 && g + 2 < e1) ? v1.x * __ldg(x + c.z) : 0.0;
-      v1.y = (g + 3 >= e0 && g + 3 < e1) ? v1.y * __ldg(x + c.w) : 0.0;
-      *reinterpret_cast<double2 *>(pv + q) = v0;
-      *reinterpret_cast<double2 *>(pv + q + 2) = v1;
-    }
-    __syncthreads();
+    // Rows are consumed straight out of the staged (col,val) stream: G lanes per row multiply-add in
+    // registers, so products never make a round trip through shared memory (the L1 data pipe was the
+    // limiter: profiles/README.md r1_c).  With G = 1 consecutive lanes own consecutive rows, which makes
+    // the x gathers of a banded stencil fully coalesced (lane l reads x[col_p(row0 + l)]), and the row
+    // sum is taken in storage order like the reference's loop (csr_matvec.c:210-216).
     for (int base = r0; base < r1; base += NT / G) {
       const int r = base + sub;
       double s = 0.0;
@@ -143,7 +133,22 @@ spmv_pipe_kernel(const int *__restrict__ A_i, const int *__restrict__ A_j, const
         int s0, s1;
         if (rp_smem) { s0 = rp[r - ra]; s1 = rp[r - ra + 1]; } else { s0 = A_i[r]; s1 = A_i[r + 1]; }
         s0 -= a0; s1 -= a0;
-        for (int p = s0 + lane; p < s1; p += G) s += pv[p];
+        int p = s0 + lane;
+        for (; p + 3 * G < s1; p += 4 * G) {          // four gathers in flight per lane
+          const int c0 = pc[p], c1 = pc[p + G], c2 = pc[p + 2 * G], c3 = pc[p + 3 * G];
+          const double v0 = pv[p], v1 = pv[p + G], v2 = pv[p + 2 * G], v3 = pv[p + 3 * G];
+          const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2), x3 = __ldg(x + c3);
+          s += v0 * x0; s += v1 * x1; s += v2 * x2; s += v3 * x3;
+        }
+        if (p < s1) {                                  // tail of up to three entries, also issued together
+          const bool k1 = p + G < s1, k2 = p + 2 * G < s1;
+          const int c0 = pc[p], c1 = k1 ? pc[p + G] : c0, c2 = k2 ? pc[p + 2 * G] : c0;
+          const double v0 = pv[p], v1 = k1 ? pv[p + G] : 0.0, v2 = k2 ? pv[p + 2 * G] : 0.0;
+          const double x0 = __ldg(x + c0), x1 = __ldg(x + c1), x2 = __ldg(x + c2);
+          s += v0 * x0;
+          if (k1) s += v1 * x1;
+          if (k2) s += v2 * x2;
+        }
       }
       if (G > 1) {
 #pragma unroll
