@@ -78,6 +78,28 @@ SIGNATURES = {
     "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
     "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
     "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
+    "b200_comm_create_single": (_i, [C.POINTER(_vp)]),
+    "b200_comm_group_create": (_i, [_i, C.POINTER(_vp)]),
+    "b200_comm_group_destroy": (_i, [_vp]),
+    "b200_comm_create_threads": (_i, [_vp, _i, C.POINTER(_vp)]),
+    "b200_comm_nccl_unique_id": (_i, [C.c_char_p]),
+    "b200_comm_create_nccl": (_i, [_vp, _i, _i, C.c_char_p, C.POINTER(_vp)]),
+    "b200_comm_destroy": (_i, [_vp, _vp]),
+    "b200_comm_rank": (_i, [_vp]),
+    "b200_comm_size": (_i, [_vp]),
+    "b200_dist_generate_laplacian": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_dist_matrix_destroy": (_i, [_vp, _vp]),
+    "b200_dist_matrix_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
+    "b200_dist_matrix_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "b200_dist_matvec": (_i, [_vp, _vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_dist_amg_setup": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_dist_amg_destroy": (_i, [_vp, _vp]),
+    "b200_dist_amg_num_levels": (_i, [_vp]),
+    "b200_dist_amg_level_A": (_vp, [_vp, _i]),
+    "b200_dist_amg_level_P": (_vp, [_vp, _i]),
+    "b200_dist_amg_level_cf": (_i, [_vp, _vp, _i, _vp]),
+    "b200_dist_amg_setup_ms": (_i, [_vp, _dp]),
+    "b200_dist_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
 }
 
 
@@ -408,3 +430,154 @@ class Handle:
         if self.p:
             _chk(_lib.b200_finalize(self.p))
             self.p = None
+
+
+class Comm:
+    """Communicator: one rank per GPU (NCCL) or N host threads on one GPU (test backend)."""
+
+    def __init__(self, handle, p):
+        self.h, self.p = handle, p
+
+    @classmethod
+    def single(cls, handle):
+        p = _vp()
+        _chk(_lib.b200_comm_create_single(C.byref(p)))
+        return cls(handle, p)
+
+    @classmethod
+    def threads(cls, handle, group, rank):
+        p = _vp()
+        _chk(_lib.b200_comm_create_threads(group, rank, C.byref(p)))
+        return cls(handle, p)
+
+    @classmethod
+    def nccl(cls, handle, nranks, rank, unique_id):
+        p = _vp()
+        _chk(_lib.b200_comm_create_nccl(handle.p, nranks, rank, unique_id, C.byref(p)))
+        return cls(handle, p)
+
+    @staticmethod
+    def nccl_unique_id():
+        load_library()
+        buf = C.create_string_buffer(128)
+        _chk(_lib.b200_comm_nccl_unique_id(buf))
+        return buf.raw
+
+    @staticmethod
+    def group_create(nranks):
+        load_library()
+        g = _vp()
+        _chk(_lib.b200_comm_group_create(nranks, C.byref(g)))
+        return g
+
+    @property
+    def rank(self):
+        return _lib.b200_comm_rank(self.p)
+
+    @property
+    def size(self):
+        return _lib.b200_comm_size(self.p)
+
+    def destroy(self):
+        if self.p:
+            _chk(_lib.b200_comm_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class DistMatrix:
+    """Row-partitioned operator (ParCSR + CommPkg of the reference) of one rank."""
+
+    def __init__(self, handle, comm, p, owned=True):
+        self.h, self.c, self.p, self.owned = handle, comm, p, owned
+
+    @classmethod
+    def laplacian(cls, handle, comm, nx, ny, nz, P, Q, R, stencil=7, c=(1.0, 1.0, 1.0)):
+        v = (C.c_double * 4)()
+        if stencil == 7:
+            v[1], v[2], v[3] = -c[0], -c[1], -c[2]
+            v[0] = (2.0 * c[0] if nx > 1 else 0.0) + (2.0 * c[1] if ny > 1 else 0.0) + (2.0 * c[2] if nz > 1 else 0.0)
+        else:
+            v[0] = 26.0
+            if nx == 1 or ny == 1 or nz == 1:
+                v[0] = 8.0
+            if nx * ny == 1 or nx * nz == 1 or ny * nz == 1:
+                v[0] = 2.0
+            v[1] = -1.0
+        out = _vp()
+        _chk(_lib.b200_dist_generate_laplacian(handle.p, comm.p, nx, ny, nz, P, Q, R, stencil, v, C.byref(out)))
+        return cls(handle, comm, out)
+
+    @property
+    def info(self):
+        v = [_i() for _ in range(7)]
+        _chk(_lib.b200_dist_matrix_info(self.p, *[C.byref(x) for x in v]))
+        k = ["local_rows", "first_row", "global_rows", "local_nnz", "n_ghost", "first_col", "global_cols"]
+        return dict(zip(k, [x.value for x in v]))
+
+    def download(self):
+        inf = self.info
+        i = np.empty(inf["local_rows"] + 1, np.int32)
+        j = np.empty(inf["local_nnz"], np.int32)
+        a = np.empty(inf["local_nnz"], np.float64)
+        _chk(_lib.b200_dist_matrix_download(self.h.p, self.p, _np_ptr(i), _np_ptr(j), _np_ptr(a)))
+        return i, j, a
+
+    def vector(self, fill=0.0):
+        """device vector with room for the ghost tail"""
+        inf = self.info
+        d = self.h.zeros(inf["local_rows"] + inf["n_ghost"] + 8)
+        d.n_owned = inf["local_rows"]
+        if fill != 0.0:
+            _chk(_lib.b200_vec_fill(self.h.p, d.n_owned, fill, d.ptr))
+        return d
+
+    def matvec(self, alpha, x, beta, b, y):
+        _chk(_lib.b200_dist_matvec(self.h.p, self.c.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def destroy(self):
+        if self.owned and self.p:
+            _chk(_lib.b200_dist_matrix_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class DistAmg:
+    def __init__(self, handle, comm, params, A):
+        self.h, self.c = handle, comm
+        p = _vp()
+        _chk(_lib.b200_dist_amg_setup(handle.p, comm.p, params.p, A.p, C.byref(p)))
+        self.p = p
+
+    @property
+    def num_levels(self):
+        return _lib.b200_dist_amg_num_levels(self.p)
+
+    def level_A(self, l):
+        return DistMatrix(self.h, self.c, _vp(_lib.b200_dist_amg_level_A(self.p, l)), owned=False)
+
+    def level_P(self, l):
+        return DistMatrix(self.h, self.c, _vp(_lib.b200_dist_amg_level_P(self.p, l)), owned=False)
+
+    def level_cf(self, l):
+        n = self.level_A(l).info["local_rows"]
+        cf = np.empty(n, np.int32)
+        _chk(_lib.b200_dist_amg_level_cf(self.h.p, self.p, l, _np_ptr(cf)))
+        return cf
+
+    @property
+    def setup_ms(self):
+        ms = _d()
+        _chk(_lib.b200_dist_amg_setup_ms(self.p, C.byref(ms)))
+        return ms.value
+
+    def destroy(self):
+        if self.p:
+            _chk(_lib.b200_dist_amg_destroy(self.h.p, self.p))
+            self.p = None
+
+
+def dist_pcg(handle, comm, A, amg, b, x, tol=1e-8, max_iter=100):
+    its, rel = _i(), _d()
+    norms = np.zeros(max_iter + 2, np.float64)
+    _chk(_lib.b200_dist_pcg_solve(handle.p, comm.p, A.p, amg.p if amg is not None else None, b.ptr, x.ptr, tol, max_iter,
+                                  C.byref(its), C.byref(rel), _np_ptr(norms)))
+    return its.value, rel.value, norms[: its.value + 1]

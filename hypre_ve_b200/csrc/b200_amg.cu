@@ -194,6 +194,9 @@ extern "C" int b200_amg_set_real(b200_amg amg, const char *name, double value) {
   return 0;
 }
 
+int b200_amg_get_int(b200_amg a, const char *name) { return a->ip.count(name) ? a->ip[name] : 0; }
+double b200_amg_get_real(b200_amg a, const char *name) { return a->rp.count(name) ? a->rp[name] : 0.0; }
+
 extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   if (!amg || !Apar) B200_FAIL("amg_setup: null argument");
   if (Apar->offd->ncols > 0) B200_FAIL("amg_setup: multi-rank setup not built yet (offd block must be empty)");

@@ -1,0 +1,42 @@
+// b200_comm.h -- internal interface of the communication layer (b200_comm.cu) and the
+// halo plan (b200_dist.cu).  See include/hypre_b200.h for the exported C-ABI.
+#pragma once
+#include "b200_internal.h"
+#include <vector>
+
+struct b200_xfer {
+  int peer;
+  void *ptr;       // device pointer
+  size_t bytes;
+  int tag;         // ordinal among the messages exchanged with `peer` in this call (0 = first)
+};
+
+int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> &sends, const std::vector<b200_xfer> &recvs);
+int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all);
+int b200_comm_allreduce_sum(b200_handle h, b200_comm c, double *vals, int k);
+int b200_comm_allreduce_sum_ll(b200_handle h, b200_comm c, long long *vals, int k);
+
+// Halo plan = hypre_ParCSRCommPkg (parcsr_mv/par_csr_communication.h:54-82) for one ghost set:
+// ghosts are the sorted global ids this rank reads but does not own; each ghost block is
+// contiguous per owner (owners own contiguous id ranges), so receives land in place.
+struct b200_halo_s {
+  int n_owned = 0;                       // ids owned by this rank: [first, first + n_owned)
+  int first = 0;
+  int ng = 0;                            // number of ghosts
+  int *d_ghost_gid = nullptr;            // device, sorted [ng]
+  std::vector<int> recv_cnt, recv_off;   // per peer, into the ghost array
+  std::vector<int> send_cnt, send_off;   // per peer, into d_send_idx
+  int n_send = 0;
+  int *d_send_idx = nullptr;             // device, local indices to pack [n_send]
+  void *d_send_buf = nullptr;            // device staging, 8 bytes per send entry
+};
+
+// halo operations (b200_dist.cu)
+int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, int *d_ghost_gid_sorted, int ng,
+                    b200_halo_s **plan_out);      // takes ownership of d_ghost_gid_sorted
+void b200_halo_free(b200_handle h, b200_halo_s *p);
+int b200_halo_forward_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *d_owned, int *d_ghost_out);
+int b200_halo_forward_f64(b200_handle h, b200_comm c, b200_halo_s *p, const double *d_owned, double *d_ghost_out);
+int b200_halo_reverse_add_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *d_ghost_in, int *d_owned_inout);
+// reference rule of par_coarsen.c:2509-2526: a ghost copy that was cleared clears the owner's tentative mark
+int b200_halo_reverse_clear_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *d_ghost_in, int *d_owned_inout);

@@ -20,6 +20,9 @@ namespace {
 constexpr int NT = B200_SPMV_NT;              // threads per CTA
 constexpr int CAP = 4096;                     // shared-memory product slots per CTA (32 KB)
 constexpr int MAX_TILE = B200_SPMV_MAX_TILE;  // tile (nnz per CTA) upper bound; CAP - MAX_TILE bounds the longest row
+}
+constexpr int MAX_TILE_DEFAULT = B200_SPMV_MAX_TILE;
+namespace {
 
 __global__ void max_row_kernel(int n, const int *__restrict__ A_i, int *__restrict__ out_max) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,6 +213,8 @@ int b200_csr_build_plan(b200_handle h, b200_csr A) {
   if (A->blk_ent) { B200_TRY(b200_dfree(h, A->blk_ent)); A->blk_ent = nullptr; }
   if (A->blk_meta) { B200_TRY(b200_dfree(h, A->blk_meta)); A->blk_meta = nullptr; }
   double avg = A->nrows ? (double)A->nnz / A->nrows : 0.0;
+  static const int tile_env = [] { const char *e = getenv("B200_SPMV_TILE"); return e ? atoi(e) : 0; }();
+  const int MAX_TILE = tile_env > 0 ? tile_env : ::MAX_TILE_DEFAULT;
   int G = 1;
   if (A->nnz > 0 && A->nrows >= 64) {
     // pick the lanes-per-row that minimises gather wavefronts per entry on a sample of the matrix

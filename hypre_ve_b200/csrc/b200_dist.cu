@@ -1,0 +1,1083 @@
+// b200_dist.cu -- row-partitioned (multi-GPU) ParCSR: halo plans, ghost-row fetches, distributed
+// setup (PMIS / ext+i / Galerkin product), V-cycle and PCG.
+//
+// Reference: hypre_ParCSRMatrix + hypre_ParCSRCommPkg (parcsr_mv/par_csr_matrix.h:27-95,
+// par_csr_communication.h:54-82), hypre_ParCSRMatrixMatvecOutOfPlace (par_csr_matvec.c:22-359),
+// hypre_ParCSRMatrixExtractBExt (par_csr_matop.c:1655), hypre_exchange_interp_data
+// (parcsr_ls/aux_interp.c:552-660), hypre_ParCSRMatrixRAPKTHost multi-rank branch
+// (par_csr_triplemat.c:606-871), hypre_BoomerAMGCoarseParms (par_coarse_parms.c:56-133).
+//
+// Design (B200-first, see include/hypre_b200.h "multi-GPU"): every rank keeps its rows as ONE CSR.
+// During setup the column ids are GLOBAL; ghost rows needed by a per-row algorithm are fetched from
+// their owners with their entry order intact, so the single-GPU row kernels run unchanged and the
+// hierarchy is bit-identical for any number of GPUs.  For the solve phase columns are localized to
+// [owned | ghosts sorted by global id] and a SpMV is: pack -> grouped ncclSend/ncclRecv straight into
+// the ghost tail of x -> one streaming kernel.
+#include "b200_internal.h"
+#include "b200_comm.h"
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+#include <algorithm>
+#include <cmath>
+#include <map>
+
+int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha,
+                      double beta, const double *b, const double *d);
+int b200_pmis_dist(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int *d_cf_ext);
+int b200_extpi_interp_ex(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, int n, const int *d_f2c_in, int ncoarse_in,
+                         double trunc_factor, int max_elmts, b200_csr *out);
+int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out);
+int b200_vec_dot_dev(b200_handle h, int n, const double *x, const double *y, double *d_out);
+int b200_generate_stencil_global(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q, int r,
+                                 int stencil, const double *vals, b200_csr *out, int *first_row);
+int b200_box_first_row(int nx, int ny, int nz, int P, int Q, int R, int p, int q, int r);
+
+struct b200_amg_s;   // parameter maps live in b200_amg.cu
+int b200_amg_get_int(b200_amg a, const char *name);
+double b200_amg_get_real(b200_amg a, const char *name);
+
+// legacy diag/offd ParCSR hooks (b200_parcsr.cu): the multi-rank path is the b200_dist_* API
+int b200_halo_exchange(b200_handle, b200_parcsr, const double *) { B200_FAIL("use the b200_dist_* API for multi-rank operators"); }
+void b200_halo_destroy(b200_handle, b200_halo_s *) {}
+
+struct b200_dist_matrix_s {
+  int n = 0;                    // local rows
+  int first_row = 0, global_rows = 0;
+  int first_col = 0, n_owned_cols = 0, global_cols = 0;
+  std::vector<int> row_starts, col_starts;   // ownership of rows / columns, size nranks+1
+  b200_csr G = nullptr;         // local rows, GLOBAL column ids (setup form)
+  b200_csr L = nullptr;         // local rows, localized columns [owned | ghosts] (solve form)
+  b200_halo_s *halo = nullptr;  // ghosts of L
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void pack_kernel(int n, const int *__restrict__ idx, const T *__restrict__ src, T *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[idx[k]];
+}
+__global__ void unpack_add_kernel(int n, const int *__restrict__ idx, const int *__restrict__ buf, int *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && buf[k]) atomicAdd(&dst[idx[k]], buf[k]);
+}
+__global__ void unpack_clear_kernel(int n, const int *__restrict__ idx, const int *__restrict__ buf, int *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && buf[k] == 0 && dst[idx[k]] > 0) dst[idx[k]] = 0;     // par_coarsen.c:2516-2519
+}
+__global__ void sub_kernel(int n, int *x, int v) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) x[k] -= v;
+}
+__global__ void rowlen_kernel(int n, const int *__restrict__ idx, const int *__restrict__ A_i, int *__restrict__ len) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n) return;
+  if (k == n) { len[n] = 0; return; }
+  len[k] = A_i[idx[k] + 1] - A_i[idx[k]];
+}
+__global__ void pack_rows_kernel(int n, const int *__restrict__ idx, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                 const double *__restrict__ A_a, const int *__restrict__ off, int *__restrict__ bj,
+                                 double *__restrict__ ba) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int r = idx[k], s = A_i[r], len = A_i[r + 1] - s, d = off[k];
+  for (int t = 0; t < len; t++) { bj[d + t] = A_j[s + t]; if (ba) ba[d + t] = A_a[s + t]; }
+}
+// ghost candidates: columns outside the owned range
+__global__ void flag_ghost_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, int *__restrict__ flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > nnz) return;
+  if (k == nnz) { flag[nnz] = 0; return; }
+  const int c = j[k];
+  flag[k] = (c < first || c >= first + n_owned) ? 1 : 0;
+}
+__global__ void scatter_ghost_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, const int *__restrict__ pos,
+                                     int *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int c = j[k];
+  if (c < first || c >= first + n_owned) out[pos[k]] = c;
+}
+// global -> extended local: owned -> c - first ; ghost -> n_owned + rank in the sorted ghost list
+__global__ void localize_kernel(int nnz, const int *__restrict__ jg, int first, int n_owned, int ng,
+                                const int *__restrict__ ghost, int *__restrict__ jl) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int c = jg[k];
+  if (c >= first && c < first + n_owned) { jl[k] = c - first; return; }
+  int lo = 0, hi = ng - 1;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (ghost[mid] < c) lo = mid + 1; else hi = mid; }
+  jl[k] = n_owned + lo;
+}
+// extended local -> global
+__global__ void globalize_kernel(int nnz, const int *__restrict__ jl, int first, int n_owned, const int *__restrict__ ghost,
+                                 int *__restrict__ jg) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int c = jl[k];
+  jg[k] = c < n_owned ? first + c : ghost[c - n_owned];
+}
+__global__ void owner_kernel(int nnz, const int *__restrict__ jg, int nranks, const int *__restrict__ starts, int *__restrict__ owner) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int c = jg[k];
+  int lo = 0, hi = nranks - 1;                        // last r with starts[r] <= c
+  while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (starts[mid] <= c) lo = mid; else hi = mid - 1; }
+  owner[k] = lo;
+}
+__global__ void expand_rows_g_kernel(int nrows, const int *__restrict__ A_i, int first_row, int *__restrict__ rows) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nrows) return;
+  for (int k = A_i[r]; k < A_i[r + 1]; k++) rows[k] = first_row + r;
+}
+__global__ void iota_kernel2(int n, int *x) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = i;
+}
+template <class T>
+__global__ void gather_kernel(int n, const int *__restrict__ perm, const T *__restrict__ src, T *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[perm[k]];
+}
+__global__ void hist_kernel(int n, const int *__restrict__ key, int *__restrict__ cnt) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) atomicAdd(&cnt[key[k]], 1);
+}
+__global__ void cflag2_kernel(int n, const int *__restrict__ cf, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = cf[i] >= 0 ? 1 : 0;
+  if (i == n) flag[n] = 0;
+}
+__global__ void f2c_global_kernel(int n, const int *__restrict__ cf, int coarse_first, int *__restrict__ f2c) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) f2c[i] = cf[i] >= 0 ? coarse_first + f2c[i] : -1;
+}
+__global__ void fix_cf2_kernel(int n, int *cf) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && cf[i] == -3) cf[i] = -1;
+}
+__global__ void concat_rowptr_kernel(int n1, const int *__restrict__ i1, int n2, const int *__restrict__ i2, int *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= n1) out[k] = i1[k];
+  if (k >= 1 && k <= n2) out[n1 + k] = i1[n1] + i2[k];
+}
+__global__ void jacobi_zero_kernel2(size_t n, double w, const double *__restrict__ f, const double *__restrict__ l1, double *__restrict__ u) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) u[i] = 0.0 + w * f[i] / l1[i];
+}
+__global__ void dense_rows_kernel(int n, int ncols, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                  const double *__restrict__ A_a, double *__restrict__ M) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < ncols; k++) M[(size_t)i * ncols + k] = 0.0;
+  for (int jj = A_i[i]; jj < A_i[i + 1]; jj++) M[(size_t)i * ncols + A_j[jj]] = A_a[jj];
+}
+__global__ void gselim_kernel2(int n, const double *__restrict__ A_mat, double *__restrict__ A, const double *__restrict__ f,
+                               double *__restrict__ x) {   // sstruct_ls/gselim.h on a scratch copy
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  for (int i = 0; i < n * n; i++) A[i] = A_mat[i];
+  for (int i = 0; i < n; i++) x[i] = f[i];
+  if (n == 1) { if (A[0] != 0.0) x[0] = x[0] / A[0]; return; }
+  for (int k = 0; k < n - 1; k++) {
+    if (A[k * n + k] != 0.0) {
+      double divA = 1.0 / A[k * n + k];
+      for (int j = k + 1; j < n; j++) {
+        if (A[j * n + k] != 0.0) {
+          double factor = A[j * n + k] * divA;
+          for (int m = k + 1; m < n; m++) A[j * n + m] -= factor * A[k * n + m];
+          x[j] -= factor * x[k];
+        }
+      }
+    }
+  }
+  for (int k = n - 1; k > 0; --k) {
+    if (A[k * n + k] != 0.0) {
+      x[k] /= A[k * n + k];
+      for (int j = 0; j < k; j++) if (A[j * n + k] != 0.0) x[j] -= x[k] * A[j * n + k];
+    }
+  }
+  if (A[0] != 0.0) x[0] /= A[0];
+}
+__global__ void pcg_alpha_kernel2(double *sc) { sc[4] = sc[0] / sc[1]; sc[2] = sc[0]; }
+__global__ void pcg_update_xr_kernel2(size_t n, const double *__restrict__ sc, const double *__restrict__ p,
+                                      const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
+  const double alpha = sc[4];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) { x[i] += alpha * p[i]; r[i] += -alpha * s[i]; }
+}
+__global__ void pcg_beta_kernel2(double *sc) { sc[5] = sc[0] / sc[2]; }
+__global__ void pcg_update_p_kernel2(size_t n, const double *__restrict__ sc, const double *__restrict__ s, double *__restrict__ p) {
+  const double beta = sc[5];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = beta * p[i] + 1.0 * s[i];
+}
+
+inline int vgrid(b200_handle h, size_t n) {
+  size_t g = (n + 255) / 256, cap = (size_t)h->num_sm * 8;
+  return (int)(g < cap ? (g ? g : 1) : cap);
+}
+
+int sort_unique(b200_handle h, int *d_keys, int n, int **out, int *n_out) {
+  *out = nullptr; *n_out = 0;
+  if (n == 0) return 0;
+  int *sorted = nullptr, *uniq = nullptr, *d_num = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &sorted, n));
+  B200_TRY(b200_dalloc<int>(h, &uniq, n));
+  B200_TRY(b200_dalloc<int>(h, &d_num, 1));
+  size_t tb = 0, tb2 = 0;
+  B200_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tb, d_keys, sorted, n, 0, 32, h->stream));
+  B200_CUDA(cub::DeviceSelect::Unique(nullptr, tb2, sorted, uniq, d_num, n, h->stream));
+  char *tmp = nullptr;
+  B200_TRY(b200_dalloc<char>(h, &tmp, tb > tb2 ? tb : tb2));
+  B200_CUDA(cub::DeviceRadixSort::SortKeys(tmp, tb, d_keys, sorted, n, 0, 32, h->stream));
+  B200_CUDA(cub::DeviceSelect::Unique(tmp, tb2, sorted, uniq, d_num, n, h->stream));
+  g_b200_launches += 2;
+  int num = 0;
+  B200_CUDA(cudaMemcpyAsync(&num, d_num, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  int *res = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &res, num));
+  B200_CUDA(cudaMemcpyAsync(res, uniq, sizeof(int) * (size_t)num, cudaMemcpyDeviceToDevice, h->stream));
+  B200_TRY(b200_dfree(h, sorted)); B200_TRY(b200_dfree(h, uniq)); B200_TRY(b200_dfree(h, d_num)); B200_TRY(b200_dfree(h, tmp));
+  *out = res; *n_out = num;
+  return 0;
+}
+
+// sorted unique list of the column ids of G that fall outside [first, first + n_owned)
+int ghost_columns(b200_handle h, const int *d_j, int nnz, int first, int n_owned, int **ghost, int *ng) {
+  *ghost = nullptr; *ng = 0;
+  if (nnz == 0) return 0;
+  int *pos = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &pos, (size_t)nnz + 1));
+  flag_ghost_kernel<<<b200_grid((size_t)nnz + 1, 256), 256, 0, h->stream>>>(nnz, d_j, first, n_owned, pos);
+  B200_LAUNCH_CHECK();
+  B200_TRY(b200_exclusive_scan_inplace(h, pos, (size_t)nnz + 1));
+  int m = 0;
+  B200_CUDA(cudaMemcpyAsync(&m, pos + nnz, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (m) {
+    int *cand = nullptr;
+    B200_TRY(b200_dalloc<int>(h, &cand, m));
+    scatter_ghost_kernel<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, d_j, first, n_owned, pos, cand);
+    B200_LAUNCH_CHECK();
+    B200_TRY(sort_unique(h, cand, m, ghost, ng));
+    B200_TRY(b200_dfree(h, cand));
+  }
+  B200_TRY(b200_dfree(h, pos));
+  return 0;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// halo plan
+// ------------------------------------------------------------------------------------------------
+int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, int *d_ghost, int ng, b200_halo_s **out) {
+  const int R = b200_comm_size(c), me = b200_comm_rank(c);
+  b200_halo_s *p = new b200_halo_s();
+  p->first = starts[me]; p->n_owned = starts[me + 1] - starts[me];
+  p->ng = ng; p->d_ghost_gid = d_ghost;
+  p->recv_cnt.assign(R, 0); p->recv_off.assign(R + 1, 0); p->send_cnt.assign(R, 0); p->send_off.assign(R + 1, 0);
+  std::vector<int> hg(ng);
+  if (ng) {
+    B200_CUDA(cudaMemcpyAsync(hg.data(), d_ghost, sizeof(int) * (size_t)ng, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  for (int r = 0; r < R; r++) {
+    auto lo = std::lower_bound(hg.begin(), hg.end(), starts[r]), hi = std::lower_bound(hg.begin(), hg.end(), starts[r + 1]);
+    p->recv_cnt[r] = (int)(hi - lo);
+    p->recv_off[r] = (int)(lo - hg.begin());
+  }
+  p->recv_off[R] = ng;
+  if (p->recv_cnt[me]) { delete p; B200_FAIL("halo: an owned id was listed as a ghost"); }
+  std::vector<int> all((size_t)R * R);
+  B200_TRY(b200_comm_allgather_host(h, c, p->recv_cnt.data(), sizeof(int) * R, all.data()));
+  for (int r = 0; r < R; r++) { p->send_cnt[r] = all[(size_t)r * R + me]; p->send_off[r + 1] = p->send_off[r] + p->send_cnt[r]; }
+  p->n_send = p->send_off[R];
+  B200_TRY(b200_dalloc<int>(h, &p->d_send_idx, p->n_send));
+  char *buf = nullptr;
+  B200_TRY(b200_dalloc<char>(h, &buf, (size_t)8 * (p->n_send > ng ? p->n_send : ng) + 8));
+  p->d_send_buf = buf;
+  // requests: I send the ghost ids I need to their owners; they become the owners' send lists
+  std::vector<b200_xfer> sends, recvs;
+  for (int r = 0; r < R; r++) {
+    if (p->recv_cnt[r]) sends.push_back({r, d_ghost + p->recv_off[r], sizeof(int) * (size_t)p->recv_cnt[r], 0});
+    if (p->send_cnt[r]) recvs.push_back({r, p->d_send_idx + p->send_off[r], sizeof(int) * (size_t)p->send_cnt[r], 0});
+  }
+  B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+  if (p->n_send) {
+    sub_kernel<<<b200_grid(p->n_send, 256), 256, 0, h->stream>>>(p->n_send, p->d_send_idx, p->first);
+    B200_LAUNCH_CHECK();
+  }
+  *out = p;
+  return 0;
+}
+void b200_halo_free(b200_handle h, b200_halo_s *p) {
+  if (!p) return;
+  b200_dfree(h, p->d_ghost_gid); b200_dfree(h, p->d_send_idx); b200_dfree(h, p->d_send_buf);
+  delete p;
+}
+
+template <class T>
+static int halo_forward(b200_handle h, b200_comm c, b200_halo_s *p, const T *owned, T *ghost_out) {
+  const int R = b200_comm_size(c);
+  T *buf = reinterpret_cast<T *>(p->d_send_buf);
+  if (p->n_send) {
+    pack_kernel<T><<<b200_grid(p->n_send, 256), 256, 0, h->stream>>>(p->n_send, p->d_send_idx, owned, buf);
+    B200_LAUNCH_CHECK();
+  }
+  std::vector<b200_xfer> sends, recvs;
+  for (int r = 0; r < R; r++) {
+    if (p->send_cnt[r]) sends.push_back({r, buf + p->send_off[r], sizeof(T) * (size_t)p->send_cnt[r], 0});
+    if (p->recv_cnt[r]) recvs.push_back({r, ghost_out + p->recv_off[r], sizeof(T) * (size_t)p->recv_cnt[r], 0});
+  }
+  return b200_comm_exchange(h, c, sends, recvs);
+}
+int b200_halo_forward_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *o, int *g) { return halo_forward<int>(h, c, p, o, g); }
+int b200_halo_forward_f64(b200_handle h, b200_comm c, b200_halo_s *p, const double *o, double *g) { return halo_forward<double>(h, c, p, o, g); }
+
+static int halo_reverse_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *ghost_in, int *owned, int op) {
+  const int R = b200_comm_size(c);
+  int *buf = reinterpret_cast<int *>(p->d_send_buf);
+  std::vector<b200_xfer> sends, recvs;
+  for (int r = 0; r < R; r++) {
+    if (p->recv_cnt[r]) sends.push_back({r, const_cast<int *>(ghost_in) + p->recv_off[r], sizeof(int) * (size_t)p->recv_cnt[r], 0});
+    if (p->send_cnt[r]) recvs.push_back({r, buf + p->send_off[r], sizeof(int) * (size_t)p->send_cnt[r], 0});
+  }
+  B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+  if (p->n_send) {
+    if (op == 0) unpack_add_kernel<<<b200_grid(p->n_send, 256), 256, 0, h->stream>>>(p->n_send, p->d_send_idx, buf, owned);
+    else unpack_clear_kernel<<<b200_grid(p->n_send, 256), 256, 0, h->stream>>>(p->n_send, p->d_send_idx, buf, owned);
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
+}
+int b200_halo_reverse_add_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *g, int *o) { return halo_reverse_i32(h, c, p, g, o, 0); }
+int b200_halo_reverse_clear_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *g, int *o) { return halo_reverse_i32(h, c, p, g, o, 1); }
+
+// Fetch the rows of M (owned rows, any column ids) that correspond to the plan's ghosts, in ghost
+// order, entry order preserved.  hypre_ParCSRMatrixExtractBExt (par_csr_matop.c:1655).
+static int fetch_rows(b200_handle h, b200_comm c, b200_halo_s *p, b200_csr M, b200_csr *out) {
+  const int R = b200_comm_size(c);
+  const bool with_data = M->a != nullptr;
+  // owner side: lengths and packed entries of the requested rows
+  int *slen = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &slen, (size_t)p->n_send + 1));
+  rowlen_kernel<<<b200_grid((size_t)p->n_send + 1, 256), 256, 0, h->stream>>>(p->n_send, p->d_send_idx, M->i, slen);
+  B200_LAUNCH_CHECK();
+  // receiver side: ghost row lengths
+  b200_csr E = nullptr;
+  int *glen = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &glen, (size_t)p->ng + 1));
+  B200_CUDA(cudaMemsetAsync(glen + p->ng, 0, sizeof(int), h->stream));
+  {
+    std::vector<b200_xfer> sends, recvs;
+    for (int r = 0; r < R; r++) {
+      if (p->send_cnt[r]) sends.push_back({r, slen + p->send_off[r], sizeof(int) * (size_t)p->send_cnt[r], 0});
+      if (p->recv_cnt[r]) recvs.push_back({r, glen + p->recv_off[r], sizeof(int) * (size_t)p->recv_cnt[r], 0});
+    }
+    B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+  }
+  B200_TRY(b200_exclusive_scan_inplace(h, slen, (size_t)p->n_send + 1));
+  B200_TRY(b200_exclusive_scan_inplace(h, glen, (size_t)p->ng + 1));
+  std::vector<int> hs(p->n_send + 1), hg(p->ng + 1);
+  B200_CUDA(cudaMemcpyAsync(hs.data(), slen, sizeof(int) * ((size_t)p->n_send + 1), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(hg.data(), glen, sizeof(int) * ((size_t)p->ng + 1), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  const int send_nnz = hs[p->n_send], recv_nnz = hg[p->ng];
+  int *bj = nullptr;
+  double *ba = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &bj, send_nnz));
+  if (with_data) B200_TRY(b200_dalloc<double>(h, &ba, send_nnz));
+  if (p->n_send) {
+    pack_rows_kernel<<<b200_grid(p->n_send, 128), 128, 0, h->stream>>>(p->n_send, p->d_send_idx, M->i, M->j, M->a, slen, bj, ba);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_csr_alloc(h, p->ng, M->ncols, recv_nnz, with_data, &E));
+  B200_CUDA(cudaMemcpyAsync(E->i, glen, sizeof(int) * ((size_t)p->ng + 1), cudaMemcpyDeviceToDevice, h->stream));
+  {
+    std::vector<b200_xfer> sends, recvs;
+    for (int r = 0; r < R; r++) {
+      const int sn = hs[p->send_off[r + 1]] - hs[p->send_off[r]], so = hs[p->send_off[r]];
+      const int rn = hg[p->recv_off[r + 1]] - hg[p->recv_off[r]], ro = hg[p->recv_off[r]];
+      if (sn) sends.push_back({r, bj + so, sizeof(int) * (size_t)sn, 0});
+      if (rn) recvs.push_back({r, E->j + ro, sizeof(int) * (size_t)rn, 0});
+    }
+    B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+    if (with_data) {
+      sends.clear(); recvs.clear();
+      for (int r = 0; r < R; r++) {
+        const int sn = hs[p->send_off[r + 1]] - hs[p->send_off[r]], so = hs[p->send_off[r]];
+        const int rn = hg[p->recv_off[r + 1]] - hg[p->recv_off[r]], ro = hg[p->recv_off[r]];
+        if (sn) sends.push_back({r, ba + so, sizeof(double) * (size_t)sn, 0});
+        if (rn) recvs.push_back({r, E->a + ro, sizeof(double) * (size_t)rn, 0});
+      }
+      B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+    }
+  }
+  B200_TRY(b200_dfree(h, slen)); B200_TRY(b200_dfree(h, glen)); B200_TRY(b200_dfree(h, bj)); B200_TRY(b200_dfree(h, ba));
+  *out = E;
+  return 0;
+}
+
+// stack two CSR blocks (rows of `top` then rows of `bot`)
+static int stack_rows(b200_handle h, b200_csr top, b200_csr bot, b200_csr *out) {
+  const bool with_data = top->a != nullptr;
+  b200_csr S = nullptr;
+  B200_TRY(b200_csr_alloc(h, top->nrows + bot->nrows, top->ncols, top->nnz + bot->nnz, with_data, &S));
+  const int m = std::max(top->nrows, bot->nrows) + 1;
+  concat_rowptr_kernel<<<b200_grid(m, 256), 256, 0, h->stream>>>(top->nrows, top->i, bot->nrows, bot->i, S->i);
+  B200_LAUNCH_CHECK();
+  if (top->nnz) B200_CUDA(cudaMemcpyAsync(S->j, top->j, sizeof(int) * (size_t)top->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  if (bot->nnz) B200_CUDA(cudaMemcpyAsync(S->j + top->nnz, bot->j, sizeof(int) * (size_t)bot->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  if (with_data) {
+    if (top->nnz) B200_CUDA(cudaMemcpyAsync(S->a, top->a, sizeof(double) * (size_t)top->nnz, cudaMemcpyDeviceToDevice, h->stream));
+    if (bot->nnz) B200_CUDA(cudaMemcpyAsync(S->a + top->nnz, bot->a, sizeof(double) * (size_t)bot->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  *out = S;
+  return 0;
+}
+
+// E has one row per first-ring ghost (sorted by gid); returns a CSR with `nslots` rows where row
+// pos[k] - n_owned holds E's row k and every other row is empty.  pos is increasing, so the entry
+// arrays are copied unchanged.
+namespace {
+__global__ void spread_len_kernel(int ng, const int *__restrict__ E_i, const int *__restrict__ pos, int n_owned, int *__restrict__ len) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ng) len[pos[k] - n_owned] = E_i[k + 1] - E_i[k];
+}
+}  // namespace
+static int spread_rows(b200_handle h, b200_csr E, const int *d_pos, int n_owned, int nslots, b200_csr *out) {
+  b200_csr Q = nullptr;
+  B200_TRY(b200_csr_alloc(h, nslots, E->ncols, E->nnz, E->a != nullptr, &Q));
+  B200_CUDA(cudaMemsetAsync(Q->i, 0, sizeof(int) * ((size_t)nslots + 1), h->stream));
+  if (E->nrows) {
+    spread_len_kernel<<<b200_grid(E->nrows, 256), 256, 0, h->stream>>>(E->nrows, E->i, d_pos, n_owned, Q->i);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_exclusive_scan_inplace(h, Q->i, (size_t)nslots + 1));
+  if (E->nnz) {
+    B200_CUDA(cudaMemcpyAsync(Q->j, E->j, sizeof(int) * (size_t)E->nnz, cudaMemcpyDeviceToDevice, h->stream));
+    if (E->a) B200_CUDA(cudaMemcpyAsync(Q->a, E->a, sizeof(double) * (size_t)E->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  *out = Q;
+  return 0;
+}
+
+// copy of M with its column ids mapped global -> [owned | ghost] for the given plan
+static int localize_copy(b200_handle h, b200_csr M, b200_halo_s *p, int first, int n_owned, bool build_plan, b200_csr *out) {
+  b200_csr L = nullptr;
+  B200_TRY(b200_csr_alloc(h, M->nrows, n_owned + p->ng, M->nnz, M->a != nullptr, &L));
+  B200_CUDA(cudaMemcpyAsync(L->i, M->i, sizeof(int) * ((size_t)M->nrows + 1), cudaMemcpyDeviceToDevice, h->stream));
+  if (M->nnz) {
+    localize_kernel<<<b200_grid(M->nnz, 256), 256, 0, h->stream>>>(M->nnz, M->j, first, n_owned, p->ng, p->d_ghost_gid, L->j);
+    B200_LAUNCH_CHECK();
+    if (M->a) B200_CUDA(cudaMemcpyAsync(L->a, M->a, sizeof(double) * (size_t)M->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (build_plan && L->a) B200_TRY(b200_csr_build_plan(h, L));
+  *out = L;
+  return 0;
+}
+
+// builds M->L and M->halo from M->G
+static int dist_localize(b200_handle h, b200_comm c, b200_dist_matrix M) {
+  int *ghost = nullptr, ng = 0;
+  B200_TRY(ghost_columns(h, M->G->j, M->G->nnz, M->first_col, M->n_owned_cols, &ghost, &ng));
+  if (!ghost) B200_TRY(b200_dalloc<int>(h, &ghost, 1));
+  B200_TRY(b200_halo_build(h, c, M->col_starts, ghost, ng, &M->halo));
+  B200_TRY(localize_copy(h, M->G, M->halo, M->first_col, M->n_owned_cols, true, &M->L));
+  return 0;
+}
+
+static int gather_starts(b200_handle h, b200_comm c, int n_local, std::vector<int> *starts) {
+  const int R = b200_comm_size(c);
+  std::vector<int> all(R);
+  B200_TRY(b200_comm_allgather_host(h, c, &n_local, sizeof(int), all.data()));
+  starts->assign(R + 1, 0);
+  for (int r = 0; r < R; r++) (*starts)[r + 1] = (*starts)[r] + all[r];
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// public: generator, info, download, matvec
+// ------------------------------------------------------------------------------------------------
+extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                                            int stencil, const double *values, b200_dist_matrix *out) {
+  const int nr = b200_comm_size(c), me = b200_comm_rank(c);
+  if (P * Q * R != nr) B200_FAIL("process grid P*Q*R must equal the number of ranks");
+  if (stencil != 7 && stencil != 27) B200_FAIL("stencil must be 7 or 27");
+  const int p = me % P, q = ((me - p) / P) % Q, r = (me - p - P * q) / (P * Q);      // ij.c:7785-7787
+  b200_dist_matrix M = new b200_dist_matrix_s();
+  B200_TRY(b200_generate_stencil_global(h, nx, ny, nz, P, Q, R, p, q, r, stencil, values, &M->G, &M->first_row));
+  M->n = M->G->nrows;
+  M->global_rows = M->global_cols = nx * ny * nz;
+  M->row_starts.assign(nr + 1, 0);
+  for (int k = 0; k < nr; k++) {
+    const int pk = k % P, qk = ((k - pk) / P) % Q, rk = (k - pk - P * qk) / (P * Q);
+    M->row_starts[k] = b200_box_first_row(nx, ny, nz, P, Q, R, pk, qk, rk);
+  }
+  M->row_starts[nr] = nx * ny * nz;
+  M->col_starts = M->row_starts;
+  M->first_col = M->first_row; M->n_owned_cols = M->n;
+  if (M->row_starts[me] != M->first_row || M->row_starts[me + 1] - M->row_starts[me] != M->n) B200_FAIL("partition mismatch");
+  B200_TRY(dist_localize(h, c, M));
+  *out = M;
+  return 0;
+}
+
+extern "C" int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix M) {
+  if (!M) return 0;
+  B200_TRY(b200_csr_destroy(h, M->G));
+  B200_TRY(b200_csr_destroy(h, M->L));
+  b200_halo_free(h, M->halo);
+  delete M;
+  return 0;
+}
+extern "C" int b200_dist_matrix_info(b200_dist_matrix M, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
+                                     int *n_ghost, int *first_col, int *global_cols) {
+  if (!M) B200_FAIL("null matrix");
+  if (local_rows) *local_rows = M->n;
+  if (first_row) *first_row = M->first_row;
+  if (global_rows) *global_rows = M->global_rows;
+  if (local_nnz) *local_nnz = M->G ? M->G->nnz : (M->L ? M->L->nnz : 0);
+  if (n_ghost) *n_ghost = M->halo ? M->halo->ng : 0;
+  if (first_col) *first_col = M->first_col;
+  if (global_cols) *global_cols = M->global_cols;
+  return 0;
+}
+extern "C" int b200_dist_matrix_download(b200_handle h, b200_dist_matrix M, int *h_i, int *h_j, double *h_a) {
+  if (!M) B200_FAIL("null matrix");
+  if (M->G) return b200_csr_download(h, M->G, h_i, h_j, h_a);
+  // setup form already released: rebuild global ids from the localized form
+  int *jg = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &jg, M->L->nnz));
+  if (M->L->nnz) {
+    globalize_kernel<<<b200_grid(M->L->nnz, 256), 256, 0, h->stream>>>(M->L->nnz, M->L->j, M->first_col, M->n_owned_cols,
+                                                                      M->halo->d_ghost_gid, jg);
+    B200_LAUNCH_CHECK();
+  }
+  if (h_i) B200_CUDA(cudaMemcpyAsync(h_i, M->L->i, sizeof(int) * ((size_t)M->n + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (h_j && M->L->nnz) B200_CUDA(cudaMemcpyAsync(h_j, jg, sizeof(int) * (size_t)M->L->nnz, cudaMemcpyDeviceToHost, h->stream));
+  if (h_a && M->L->nnz) B200_CUDA(cudaMemcpyAsync(h_a, M->L->a, sizeof(double) * (size_t)M->L->nnz, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  B200_TRY(b200_dfree(h, jg));
+  return 0;
+}
+
+// halo of x (job 1) straight into the ghost tail, then ONE kernel over [owned | ghost]
+static int dist_spmv(b200_handle h, b200_comm c, b200_dist_matrix M, double *x, double *y, int mode, double alpha, double beta,
+                     const double *b, const double *d) {
+  if (M->halo->ng || M->halo->n_send) B200_TRY(b200_halo_forward_f64(h, c, M->halo, x, x + M->n_owned_cols));
+  return b200_csr_spmv_epi(h, M->L, x, y, mode, alpha, beta, b, d);
+}
+extern "C" int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_dist_matrix M, double *d_x, double beta,
+                                const double *d_b, double *d_y) {
+  if (!M || !M->L) B200_FAIL("dist_matvec: matrix not localized");
+  return dist_spmv(h, c, M, d_x, d_y, 0, alpha, beta, d_b, nullptr);
+}
+
+// ------------------------------------------------------------------------------------------------
+// distributed hierarchy
+// ------------------------------------------------------------------------------------------------
+struct dist_level {
+  b200_dist_matrix A = nullptr;      // level 0 borrowed
+  b200_dist_matrix P = nullptr;      // rows: fine (this level), cols: coarse
+  b200_dist_matrix R = nullptr;      // rows: coarse, cols: fine (P^T)
+  int *cf = nullptr;                 // [n]
+  double *l1 = nullptr;
+  double *F = nullptr, *U = nullptr, *T = nullptr;   // capacity n + max ghosts
+  int n = 0, cap = 0;
+};
+struct b200_dist_amg_s {
+  std::vector<dist_level> lv;
+  double *Vtemp = nullptr;
+  int vtemp_cap = 0;
+  double *ge_A = nullptr, *ge_f = nullptr;   // dense coarsest matrix (n x n) + scratch + gathered rhs
+  int ge_n = 0;
+  std::vector<int> ge_starts;
+  bool coarse_ge = false;
+  double relax_wt = 1.0;
+  double setup_ms = 0;
+};
+
+// distributed transpose of P (global coarse cols) -> R rows = local coarse, cols = global fine ids,
+// entries of a row ordered by ascending fine row (csr_matop.c:740-767 order, partition independent)
+static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const std::vector<int> &coarse_starts, b200_csr *out) {
+  const int R = b200_comm_size(c), me = b200_comm_rank(c);
+  const int nnz = P->G->nnz, n = P->n;
+  const int nc = coarse_starts[me + 1] - coarse_starts[me], cfirst = coarse_starts[me];
+  // owner of every entry's column; stable sort by owner keeps the (row, entry) order inside a bucket
+  int *owner = nullptr, *rows = nullptr, *idx = nullptr, *owner_s = nullptr, *perm = nullptr, *d_starts = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &owner, nnz)); B200_TRY(b200_dalloc<int>(h, &rows, nnz)); B200_TRY(b200_dalloc<int>(h, &idx, nnz));
+  B200_TRY(b200_dalloc<int>(h, &owner_s, nnz)); B200_TRY(b200_dalloc<int>(h, &perm, nnz));
+  B200_TRY(b200_dalloc<int>(h, &d_starts, R + 1));
+  B200_CUDA(cudaMemcpyAsync(d_starts, coarse_starts.data(), sizeof(int) * (R + 1), cudaMemcpyHostToDevice, h->stream));
+  int *cntr = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &cntr, R + 1));
+  B200_CUDA(cudaMemsetAsync(cntr, 0, sizeof(int) * (R + 1), h->stream));
+  if (nnz) {
+    owner_kernel<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, P->G->j, R, d_starts, owner);
+    B200_LAUNCH_CHECK();
+    expand_rows_g_kernel<<<b200_grid(n, 128), 128, 0, h->stream>>>(n, P->G->i, P->first_row, rows);
+    B200_LAUNCH_CHECK();
+    iota_kernel2<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, idx);
+    B200_LAUNCH_CHECK();
+    hist_kernel<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, owner, cntr);
+    B200_LAUNCH_CHECK();
+    int bits = 1;
+    while ((1 << bits) < R) bits++;
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, owner, owner_s, idx, perm, nnz, 0, bits, h->stream));
+    char *tmp = nullptr;
+    B200_TRY(b200_dalloc<char>(h, &tmp, tb));
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, owner, owner_s, idx, perm, nnz, 0, bits, h->stream));
+    ++g_b200_launches;
+    B200_TRY(b200_dfree(h, tmp));
+  }
+  std::vector<int> scnt(R + 1, 0);
+  B200_CUDA(cudaMemcpyAsync(scnt.data(), cntr, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  // bucketed triplets (fine row, coarse col, value)
+  int *s_row = nullptr, *s_col = nullptr;
+  double *s_val = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &s_row, nnz)); B200_TRY(b200_dalloc<int>(h, &s_col, nnz)); B200_TRY(b200_dalloc<double>(h, &s_val, nnz));
+  if (nnz) {
+    gather_kernel<int><<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, perm, rows, s_row);
+    gather_kernel<int><<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, perm, P->G->j, s_col);
+    gather_kernel<double><<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, perm, P->G->a, s_val);
+    g_b200_launches += 3;
+  }
+  std::vector<int> all((size_t)R * R), rcnt(R), soff(R + 1, 0), roff(R + 1, 0);
+  B200_TRY(b200_comm_allgather_host(h, c, scnt.data(), sizeof(int) * R, all.data()));
+  for (int r = 0; r < R; r++) { rcnt[r] = all[(size_t)r * R + me]; soff[r + 1] = soff[r] + scnt[r]; roff[r + 1] = roff[r] + rcnt[r]; }
+  const int m = roff[R];
+  int *r_row = nullptr, *r_col = nullptr;
+  double *r_val = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &r_row, m)); B200_TRY(b200_dalloc<int>(h, &r_col, m)); B200_TRY(b200_dalloc<double>(h, &r_val, m));
+  for (int pass = 0; pass < 3; pass++) {
+    std::vector<b200_xfer> sends, recvs;
+    for (int r = 0; r < R; r++) {
+      const size_t es = pass == 2 ? sizeof(double) : sizeof(int);
+      char *sp = pass == 0 ? (char *)(s_row + soff[r]) : pass == 1 ? (char *)(s_col + soff[r]) : (char *)(s_val + soff[r]);
+      char *rp = pass == 0 ? (char *)(r_row + roff[r]) : pass == 1 ? (char *)(r_col + roff[r]) : (char *)(r_val + roff[r]);
+      if (scnt[r]) sends.push_back({r, sp, es * (size_t)scnt[r], 0});
+      if (rcnt[r]) recvs.push_back({r, rp, es * (size_t)rcnt[r], 0});
+    }
+    B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+  }
+  // received triplets are ordered by ascending fine row (rank blocks ascend); stable sort by local coarse column
+  b200_csr T = nullptr;
+  B200_TRY(b200_csr_alloc(h, nc, P->global_rows, m, true, &T));
+  B200_CUDA(cudaMemsetAsync(T->i, 0, sizeof(int) * ((size_t)nc + 1), h->stream));
+  if (m) {
+    sub_kernel<<<b200_grid(m, 256), 256, 0, h->stream>>>(m, r_col, cfirst);
+    B200_LAUNCH_CHECK();
+    hist_kernel<<<b200_grid(m, 256), 256, 0, h->stream>>>(m, r_col, T->i);
+    B200_LAUNCH_CHECK();
+    B200_TRY(b200_exclusive_scan_inplace(h, T->i, (size_t)nc + 1));
+    int *idx2 = nullptr, *keys2 = nullptr, *perm2 = nullptr;
+    B200_TRY(b200_dalloc<int>(h, &idx2, m)); B200_TRY(b200_dalloc<int>(h, &keys2, m)); B200_TRY(b200_dalloc<int>(h, &perm2, m));
+    iota_kernel2<<<b200_grid(m, 256), 256, 0, h->stream>>>(m, idx2);
+    B200_LAUNCH_CHECK();
+    int bits = 1;
+    while ((1LL << bits) < (long long)nc) bits++;
+    size_t tb = 0;
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, r_col, keys2, idx2, perm2, m, 0, bits, h->stream));
+    char *tmp = nullptr;
+    B200_TRY(b200_dalloc<char>(h, &tmp, tb));
+    B200_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tb, r_col, keys2, idx2, perm2, m, 0, bits, h->stream));
+    ++g_b200_launches;
+    gather_kernel<int><<<b200_grid(m, 256), 256, 0, h->stream>>>(m, perm2, r_row, T->j);
+    gather_kernel<double><<<b200_grid(m, 256), 256, 0, h->stream>>>(m, perm2, r_val, T->a);
+    g_b200_launches += 2;
+    B200_TRY(b200_dfree(h, tmp)); B200_TRY(b200_dfree(h, idx2)); B200_TRY(b200_dfree(h, keys2)); B200_TRY(b200_dfree(h, perm2));
+  }
+  for (void *q : {(void *)owner, (void *)rows, (void *)idx, (void *)owner_s, (void *)perm, (void *)d_starts, (void *)cntr, (void *)s_row,
+                  (void *)s_col, (void *)s_val, (void *)r_row, (void *)r_col, (void *)r_val})
+    B200_TRY(b200_dfree(h, q));
+  *out = T;
+  return 0;
+}
+
+static b200_dist_matrix new_dist(int n, int first_row, int global_rows, const std::vector<int> &row_starts, int first_col,
+                                 int n_owned_cols, int global_cols, const std::vector<int> &col_starts, b200_csr G) {
+  b200_dist_matrix M = new b200_dist_matrix_s();
+  M->n = n; M->first_row = first_row; M->global_rows = global_rows; M->row_starts = row_starts;
+  M->first_col = first_col; M->n_owned_cols = n_owned_cols; M->global_cols = global_cols; M->col_starts = col_starts;
+  M->G = G;
+  return M;
+}
+
+extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b200_dist_matrix A0, b200_dist_amg *out) {
+  if (!prm || !A0) B200_FAIL("dist_amg_setup: null argument");
+  if (b200_amg_get_int(prm, "CoarsenType") != 8 && b200_amg_get_int(prm, "CoarsenType") != 9)
+    B200_FAIL("only PMIS (CoarsenType 8; measures are drawn as for 9 = partition independent) is implemented");
+  if (b200_amg_get_int(prm, "InterpType") != 6 || b200_amg_get_int(prm, "RelaxType") != 18 ||
+      b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") != 0 ||
+      b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
+      !(b200_amg_get_int(prm, "ModuleRAP2") == 1 && b200_amg_get_int(prm, "RAP2") == 0))
+    B200_FAIL("unsupported BoomerAMG configuration on the B200 path (see b200_amg_setup)");
+  const int R = b200_comm_size(c), me = b200_comm_rank(c);
+  const double theta = b200_amg_get_real(prm, "StrongThreshold"), mrs = b200_amg_get_real(prm, "MaxRowSum");
+  const double trunc = b200_amg_get_real(prm, "TruncFactor");
+  const int pmax = b200_amg_get_int(prm, "PMaxElmts"), max_levels = b200_amg_get_int(prm, "MaxLevels");
+  const int max_coarse = b200_amg_get_int(prm, "MaxCoarseSize"), seed = b200_amg_get_int(prm, "Seed");
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->stream);
+  b200_dist_amg amg = new b200_dist_amg_s();
+  amg->relax_wt = b200_amg_get_real(prm, "RelaxWt");
+  dist_level L0;
+  L0.A = A0; L0.n = A0->n;
+  amg->lv.push_back(L0);
+  int level = 0;
+  bool not_finished = max_levels > 1;
+  while (not_finished) {
+    dist_level &L = amg->lv[level];
+    b200_dist_matrix A = L.A;
+    const int n = A->n, ng = A->halo->ng;
+    const long long fine_size = A->global_rows;
+    // --- strength + PMIS on the localized operator (par_amg_setup.c:1035,:1114) -----------------
+    b200_csr S = nullptr;
+    B200_TRY(b200_strength(h, A->L, theta, mrs, &S));
+    int *cf = nullptr;                              // [n + ng]
+    B200_TRY(b200_dalloc<int>(h, &cf, (size_t)n + ng + 1));
+    B200_TRY(b200_pmis_dist(h, c, S, A->halo, seed, A->first_row, cf));
+    // --- coarse numbering (par_coarse_parms.c:83-122) ---------------------------------------------
+    int *f2c = nullptr;                             // [n + ng]: global coarse id or -1
+    B200_TRY(b200_dalloc<int>(h, &f2c, (size_t)n + ng + 1));
+    cflag2_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, cf, f2c);
+    B200_LAUNCH_CHECK();
+    B200_TRY(b200_exclusive_scan_inplace(h, f2c, (size_t)n + 1));
+    int nc = 0;
+    B200_CUDA(cudaMemcpyAsync(&nc, f2c + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<int> cstarts;
+    B200_TRY(gather_starts(h, c, nc, &cstarts));
+    const long long coarse_size = cstarts[R];
+    if (coarse_size == 0 || coarse_size == fine_size) {       // par_amg_setup.c:1487-1525
+      B200_TRY(b200_csr_destroy(h, S)); B200_TRY(b200_dfree(h, cf)); B200_TRY(b200_dfree(h, f2c));
+      break;
+    }
+    if (n) {
+      f2c_global_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, cf, cstarts[me], f2c);
+      B200_LAUNCH_CHECK();
+    }
+    B200_TRY(b200_halo_forward_i32(h, c, A->halo, f2c, f2c + n));
+    // --- ext+i interpolation (par_lr_interp.c:1040-1925 with hypre_exchange_interp_data) ---------
+    // rows of A and S for the ghost nodes, then the second ring of ghost ids they mention
+    b200_csr Sg = nullptr;                          // S with global column ids (to serve fetches)
+    B200_TRY(b200_csr_alloc(h, n, A->global_cols, S->nnz, false, &Sg));
+    B200_CUDA(cudaMemcpyAsync(Sg->i, S->i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+    if (S->nnz) {
+      globalize_kernel<<<b200_grid(S->nnz, 256), 256, 0, h->stream>>>(S->nnz, S->j, A->first_col, A->n_owned_cols,
+                                                                    A->halo->d_ghost_gid, Sg->j);
+      B200_LAUNCH_CHECK();
+    }
+    b200_csr Aext = nullptr, Sext = nullptr;
+    B200_TRY(fetch_rows(h, c, A->halo, A->G, &Aext));
+    B200_TRY(fetch_rows(h, c, A->halo, Sg, &Sext));
+    B200_TRY(b200_csr_destroy(h, Sg));
+    // second ring: ids in the fetched rows that are neither owned nor first-ring ghosts.  Build the
+    // sorted union U = ghosts1 + ring2 and a plan for it; extended index space = [owned | U].
+    int *ring = nullptr, nring = 0;
+    {
+      int *cand = nullptr;
+      const int tot = Aext->nnz + A->halo->ng;
+      B200_TRY(b200_dalloc<int>(h, &cand, tot));
+      if (Aext->nnz) B200_CUDA(cudaMemcpyAsync(cand, Aext->j, sizeof(int) * (size_t)Aext->nnz, cudaMemcpyDeviceToDevice, h->stream));
+      if (A->halo->ng)
+        B200_CUDA(cudaMemcpyAsync(cand + Aext->nnz, A->halo->d_ghost_gid, sizeof(int) * (size_t)A->halo->ng, cudaMemcpyDeviceToDevice, h->stream));
+      B200_TRY(ghost_columns(h, cand, tot, A->first_col, A->n_owned_cols, &ring, &nring));
+      B200_TRY(b200_dfree(h, cand));
+      if (!ring) B200_TRY(b200_dalloc<int>(h, &ring, 1));
+    }
+    b200_halo_s *plan2 = nullptr;
+    B200_TRY(b200_halo_build(h, c, A->col_starts, ring, nring, &plan2));
+    // Extended operators: rows [owned | U], columns [owned | U].  The row kernels address neighbour
+    // ROWS by column id, so every id of U needs a row slot; only the first ring has entries (second-ring
+    // rows are never dereferenced: the kernels visit rows of strong neighbours of owned rows only).
+    // ghosts1 and U are both sorted by global id and ghosts1 is a subset of U, so the fetched entries
+    // are already in U order: only the row pointer has to be spread out.
+    int *pos = nullptr;                              // position (in [owned | U]) of every first-ring ghost
+    B200_TRY(b200_dalloc<int>(h, &pos, (size_t)ng + 1));
+    if (ng) {
+      localize_kernel<<<b200_grid(ng, 256), 256, 0, h->stream>>>(ng, A->halo->d_ghost_gid, A->first_col, A->n_owned_cols, nring,
+                                                               plan2->d_ghost_gid, pos);
+      B200_LAUNCH_CHECK();
+    }
+    b200_csr AextU = nullptr, SextU = nullptr, Abig_g = nullptr, Sbig_g = nullptr, Abig2 = nullptr, Sbig2 = nullptr;
+    B200_TRY(spread_rows(h, Aext, pos, A->n_owned_cols, nring, &AextU));
+    B200_TRY(spread_rows(h, Sext, pos, A->n_owned_cols, nring, &SextU));
+    B200_TRY(b200_dfree(h, pos));
+    B200_TRY(b200_csr_destroy(h, Aext)); B200_TRY(b200_csr_destroy(h, Sext));
+    B200_TRY(stack_rows(h, A->G, AextU, &Abig_g));
+    {
+      b200_csr Sg2 = nullptr;                       // local S rows in global ids
+      B200_TRY(b200_csr_alloc(h, n, A->global_cols, S->nnz, false, &Sg2));
+      B200_CUDA(cudaMemcpyAsync(Sg2->i, S->i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+      if (S->nnz) {
+        globalize_kernel<<<b200_grid(S->nnz, 256), 256, 0, h->stream>>>(S->nnz, S->j, A->first_col, A->n_owned_cols,
+                                                                      A->halo->d_ghost_gid, Sg2->j);
+        B200_LAUNCH_CHECK();
+      }
+      B200_TRY(stack_rows(h, Sg2, SextU, &Sbig_g));
+      B200_TRY(b200_csr_destroy(h, Sg2));
+    }
+    B200_TRY(b200_csr_destroy(h, AextU)); B200_TRY(b200_csr_destroy(h, SextU));
+    B200_TRY(localize_copy(h, Abig_g, plan2, A->first_col, A->n_owned_cols, false, &Abig2));
+    B200_TRY(localize_copy(h, Sbig_g, plan2, A->first_col, A->n_owned_cols, false, &Sbig2));
+    B200_TRY(b200_csr_destroy(h, Abig_g)); B200_TRY(b200_csr_destroy(h, Sbig_g));
+    // cf / f2c over [owned | U]
+    int *cf_big = nullptr, *f2c_big = nullptr;
+    B200_TRY(b200_dalloc<int>(h, &cf_big, (size_t)n + nring + 1));
+    B200_TRY(b200_dalloc<int>(h, &f2c_big, (size_t)n + nring + 1));
+    B200_CUDA(cudaMemcpyAsync(cf_big, cf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    B200_CUDA(cudaMemcpyAsync(f2c_big, f2c, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    B200_TRY(b200_halo_forward_i32(h, c, plan2, cf_big, cf_big + n));
+    B200_TRY(b200_halo_forward_i32(h, c, plan2, f2c_big, f2c_big + n));
+    b200_csr Pg = nullptr;
+    B200_TRY(b200_extpi_interp_ex(h, Abig2, Sbig2, cf_big, n, f2c_big, (int)coarse_size, trunc, pmax, &Pg));
+    B200_TRY(b200_csr_destroy(h, Abig2)); B200_TRY(b200_csr_destroy(h, Sbig2));
+    B200_TRY(b200_dfree(h, cf_big)); B200_TRY(b200_dfree(h, f2c_big));
+    b200_halo_free(h, plan2);
+    B200_TRY(b200_csr_destroy(h, S));
+    if (n) {
+      fix_cf2_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, cf);     // par_lr_interp.c:1888-1894
+      B200_LAUNCH_CHECK();
+    }
+    L.cf = cf;
+    B200_TRY(b200_dfree(h, f2c));
+    L.P = new_dist(n, A->first_row, A->global_rows, A->row_starts, cstarts[me], nc, (int)coarse_size, cstarts, Pg);
+    // --- Galerkin product (par_csr_triplemat.c:606-871): Q = A*P with ghost rows of P, C = P^T * Q ---
+    b200_csr Rg = nullptr;
+    B200_TRY(dist_transpose(h, c, L.P, cstarts, &Rg));
+    L.R = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_row, n, A->global_rows, A->row_starts, Rg);
+    b200_csr Pext = nullptr, Pbig = nullptr, Qg = nullptr;
+    B200_TRY(fetch_rows(h, c, A->halo, Pg, &Pext));             // hypre_ParCSRMatrixExtractBExt(P, A)
+    B200_TRY(stack_rows(h, Pg, Pext, &Pbig));
+    B200_TRY(b200_csr_destroy(h, Pext));
+    B200_TRY(b200_csr_multiply_ex(h, A->L, Pbig, 0, 0, (int)coarse_size, &Qg));
+    B200_TRY(b200_csr_destroy(h, Pbig));
+    B200_TRY(dist_localize(h, c, L.R));                         // ghosts of R = remote fine rows
+    b200_csr Qext = nullptr, Qbig = nullptr, AHg = nullptr;
+    B200_TRY(fetch_rows(h, c, L.R->halo, Qg, &Qext));
+    B200_TRY(stack_rows(h, Qg, Qext, &Qbig));
+    B200_TRY(b200_csr_destroy(h, Qext)); B200_TRY(b200_csr_destroy(h, Qg));
+    B200_TRY(b200_csr_multiply_ex(h, L.R->L, Qbig, 1, cstarts[me], (int)coarse_size, &AHg));
+    B200_TRY(b200_csr_destroy(h, Qbig));
+    dist_level Ln;
+    Ln.A = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, cstarts[me], nc, (int)coarse_size, cstarts, AHg);
+    B200_TRY(dist_localize(h, c, Ln.A));
+    Ln.n = nc;
+    B200_TRY(dist_localize(h, c, L.P));
+    amg->lv.push_back(Ln);
+    ++level;
+    if (level == max_levels - 1 || coarse_size <= max_coarse) not_finished = false;
+    if (not_finished && (double)coarse_size >= 0.75 * (double)fine_size)
+      B200_FAIL("coarsening stalled (coarse >= 0.75 fine): the reference switches to CLJP here, which is out of scope");
+  }
+  const int nl = (int)amg->lv.size();
+  // vectors: capacity = owned + the largest ghost set any operator reads them with
+  for (int l = 0; l < nl; l++) {
+    dist_level &L = amg->lv[l];
+    int cap = L.n + L.A->halo->ng;
+    if (L.R) cap = std::max(cap, L.n + L.R->halo->ng);                 // R reads fine vectors (Vtemp)
+    if (l > 0) cap = std::max(cap, L.n + amg->lv[l - 1].P->halo->ng);   // P of the finer level reads this level's U
+    L.cap = cap + 8;
+    B200_TRY(b200_dalloc<double>(h, &L.F, L.cap)); B200_TRY(b200_dalloc<double>(h, &L.U, L.cap)); B200_TRY(b200_dalloc<double>(h, &L.T, L.cap));
+    B200_CUDA(cudaMemsetAsync(L.F, 0, sizeof(double) * L.cap, h->stream));
+    B200_CUDA(cudaMemsetAsync(L.U, 0, sizeof(double) * L.cap, h->stream));
+    B200_CUDA(cudaMemsetAsync(L.T, 0, sizeof(double) * L.cap, h->stream));
+    B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
+    B200_TRY(b200_l1_norms(h, L.A->L, 1, L.l1));     // offd entries are part of the merged row (ams.c:651-657)
+    amg->vtemp_cap = std::max(amg->vtemp_cap, L.cap);
+    // setup-form copies are no longer needed below level 0 (level 0's belongs to the caller)
+  }
+  B200_TRY(b200_dalloc<double>(h, &amg->Vtemp, amg->vtemp_cap));
+  B200_CUDA(cudaMemsetAsync(amg->Vtemp, 0, sizeof(double) * amg->vtemp_cap, h->stream));
+  // coarsest level: gather the dense matrix on every rank (par_gauss_elim.c:78-118)
+  {
+    dist_level &Lc = amg->lv[nl - 1];
+    const int ncg = Lc.A->global_rows;
+    amg->coarse_ge = ncg <= max_coarse && ncg > 0;
+    if (amg->coarse_ge) {
+      amg->ge_n = ncg;
+      amg->ge_starts = Lc.A->row_starts;
+      double *loc = nullptr;
+      B200_TRY(b200_dalloc<double>(h, &loc, (size_t)Lc.n * ncg + 1));
+      B200_TRY(b200_dalloc<double>(h, &amg->ge_A, (size_t)2 * ncg * ncg + 1));
+      B200_TRY(b200_dalloc<double>(h, &amg->ge_f, (size_t)2 * ncg + 1));
+      if (Lc.n) {
+        dense_rows_kernel<<<b200_grid(Lc.n, 64), 64, 0, h->stream>>>(Lc.n, ncg, Lc.A->G->i, Lc.A->G->j, Lc.A->G->a, loc);
+        B200_LAUNCH_CHECK();
+      }
+      std::vector<b200_xfer> sends, recvs;
+      for (int r = 0; r < R; r++) {
+        const int rn = amg->ge_starts[r + 1] - amg->ge_starts[r];
+        if (Lc.n) sends.push_back({r, loc, sizeof(double) * (size_t)Lc.n * ncg, 0});
+        if (rn) recvs.push_back({r, amg->ge_A + (size_t)amg->ge_starts[r] * ncg, sizeof(double) * (size_t)rn * ncg, 0});
+      }
+      B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      B200_TRY(b200_dfree(h, loc));
+    }
+  }
+  cudaEventRecord(e1, h->stream);
+  cudaEventSynchronize(e1);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  amg->setup_ms = ms;
+  *out = amg;
+  return 0;
+}
+
+extern "C" int b200_dist_amg_destroy(b200_handle h, b200_dist_amg amg) {
+  if (!amg) return 0;
+  for (size_t l = 0; l < amg->lv.size(); l++) {
+    dist_level &L = amg->lv[l];
+    if (l > 0) B200_TRY(b200_dist_matrix_destroy(h, L.A));
+    B200_TRY(b200_dist_matrix_destroy(h, L.P));
+    B200_TRY(b200_dist_matrix_destroy(h, L.R));
+    B200_TRY(b200_dfree(h, L.cf)); B200_TRY(b200_dfree(h, L.l1));
+    B200_TRY(b200_dfree(h, L.F)); B200_TRY(b200_dfree(h, L.U)); B200_TRY(b200_dfree(h, L.T));
+  }
+  B200_TRY(b200_dfree(h, amg->Vtemp)); B200_TRY(b200_dfree(h, amg->ge_A)); B200_TRY(b200_dfree(h, amg->ge_f));
+  delete amg;
+  return 0;
+}
+extern "C" int b200_dist_amg_num_levels(b200_dist_amg amg) { return amg ? (int)amg->lv.size() : 0; }
+extern "C" b200_dist_matrix b200_dist_amg_level_A(b200_dist_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].A : nullptr; }
+extern "C" b200_dist_matrix b200_dist_amg_level_P(b200_dist_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].P : nullptr; }
+extern "C" int b200_dist_amg_level_cf(b200_handle h, b200_dist_amg amg, int l, int *h_cf) {
+  if (!amg || l < 0 || l >= (int)amg->lv.size() || !amg->lv[l].cf) B200_FAIL("no CF marker on this level");
+  B200_CUDA(cudaMemcpyAsync(h_cf, amg->lv[l].cf, sizeof(int) * (size_t)amg->lv[l].n, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+extern "C" int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms) { if (!amg) B200_FAIL("null"); *ms = amg->setup_ms; return 0; }
+
+// one V(1,1) cycle across ranks (par_cycle.c:255-622); u is zero on entry (PCG clears it)
+static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const double *f, double *u /* capacity >= lv[0].cap */) {
+  const int nl = (int)amg->lv.size();
+  const double w = amg->relax_wt;
+  const int me = b200_comm_rank(c), R = b200_comm_size(c);
+  auto coarse_solve = [&](dist_level &L, const double *F, double *U) -> int {
+    if (amg->coarse_ge) {
+      const int ncg = amg->ge_n;
+      std::vector<b200_xfer> sends, recvs;               // Allgatherv of f (par_gauss_elim.c:264)
+      for (int r = 0; r < R; r++) {
+        const int rn = amg->ge_starts[r + 1] - amg->ge_starts[r];
+        if (L.n) sends.push_back({r, const_cast<double *>(F), sizeof(double) * (size_t)L.n, 0});
+        if (rn) recvs.push_back({r, amg->ge_f + amg->ge_starts[r], sizeof(double) * (size_t)rn, 0});
+      }
+      B200_TRY(b200_comm_exchange(h, c, sends, recvs));
+      gselim_kernel2<<<1, 32, 0, h->stream>>>(ncg, amg->ge_A, amg->ge_A + (size_t)ncg * ncg, amg->ge_f, amg->ge_f + ncg);
+      B200_LAUNCH_CHECK();
+      if (L.n) B200_CUDA(cudaMemcpyAsync(U, amg->ge_f + ncg + amg->ge_starts[me], sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));
+      return 0;
+    }
+    if (L.n) {
+      jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F, L.l1, U);
+      B200_LAUNCH_CHECK();
+    }
+    return 0;
+  };
+  if (nl == 1) return coarse_solve(amg->lv[0], f, u);
+  std::vector<const double *> F(nl);
+  std::vector<double *> U(nl);
+  F[0] = f;
+  for (int l = 1; l < nl; l++) F[l] = amg->lv[l].F;
+  for (int l = 0; l < nl - 1; l++) {
+    dist_level &L = amg->lv[l];
+    dist_level &Lc = amg->lv[l + 1];
+    double *ucur = (l == 0) ? L.T : L.U;
+    if (L.n) {
+      jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, ucur);
+      B200_LAUNCH_CHECK();
+    }
+    U[l] = ucur;
+    B200_TRY(dist_spmv(h, c, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));        // Vtemp = F - A U
+    B200_TRY(dist_spmv(h, c, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr));      // F_{l+1} = R Vtemp
+  }
+  {
+    dist_level &L = amg->lv[nl - 1];
+    B200_TRY(coarse_solve(L, L.F, L.U));
+    U[nl - 1] = L.U;
+  }
+  for (int l = nl - 2; l >= 0; l--) {
+    dist_level &L = amg->lv[l];
+    B200_TRY(dist_spmv(h, c, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));           // U_l += P U_{l+1}
+    double *dst = (l == 0) ? u : L.T;
+    B200_TRY(dist_spmv(h, c, L.A, U[l], dst, 1, w, 0.0, F[l], L.l1));                      // l1-Jacobi post-sweep
+    if (l > 0) { std::swap(L.U, L.T); U[l] = L.U; }
+  }
+  return 0;
+}
+
+static int dist_dot(b200_handle h, b200_comm c, int n, const double *x, const double *y, double *result) {
+  double v = 0;
+  B200_TRY(b200_vec_dot(h, n, x, y, &v));
+  B200_TRY(b200_comm_allreduce_sum(h, c, &v, 1));      // hypre_ParVectorInnerProd (par_vector.c:481-501)
+  *result = v;
+  return 0;
+}
+
+extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const double *d_b,
+                                   double *d_x, double tol, int max_iter, int *iters_out, double *final_rel_res, double *h_norms) {
+  if (!A || !A->L) B200_FAIL("dist_pcg: matrix not localized");
+  const int n = A->n;
+  int cap = n + A->halo->ng + 8;
+  if (amg) cap = std::max(cap, amg->lv[0].cap);
+  double *p = nullptr, *s = nullptr, *r = nullptr, *xx = nullptr, *sc = nullptr;
+  B200_TRY(b200_dalloc<double>(h, &p, cap)); B200_TRY(b200_dalloc<double>(h, &s, cap)); B200_TRY(b200_dalloc<double>(h, &r, cap));
+  B200_TRY(b200_dalloc<double>(h, &xx, cap)); B200_TRY(b200_dalloc<double>(h, &sc, 8));
+  B200_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cap, h->stream));
+  B200_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * cap, h->stream));
+  B200_CUDA(cudaMemcpyAsync(xx, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+  auto precond = [&](const double *rhs, double *out) -> int {
+    if (amg) return dist_cycle(h, c, amg, rhs, out);
+    return b200_vec_copy(h, n, rhs, out);
+  };
+  int rc = 0, i = 0;
+  double bi_prod = 0, i_prod = 0, eps = tol * tol, gamma = 0, gamma_old = 0;
+  do {
+    if ((rc = dist_dot(h, c, n, d_b, d_b, &bi_prod))) break;
+    if (!(bi_prod > 0.0)) { rc = b200_vec_copy(h, n, d_b, d_x); if (h_norms) h_norms[0] = 0.0; break; }
+    if ((rc = dist_spmv(h, c, A, xx, r, 0, -1.0, 1.0, d_b, nullptr))) break;       // r = b - A x
+    if ((rc = precond(r, p))) break;
+    if ((rc = dist_dot(h, c, n, r, p, &gamma))) break;
+    if (h_norms) { double t = 0; if ((rc = dist_dot(h, c, n, r, r, &t))) break; h_norms[0] = std::sqrt(t); }
+    while ((i + 1) <= max_iter) {
+      i++;
+      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr))) break;   // s = A p
+      double sdotp = 0;
+      if ((rc = dist_dot(h, c, n, s, p, &sdotp))) break;
+      if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }
+      const double alpha = gamma / sdotp;
+      gamma_old = gamma;
+      if ((rc = b200_vec_axpy(h, n, alpha, p, xx))) break;
+      if ((rc = b200_vec_axpy(h, n, -alpha, s, r))) break;
+      if ((rc = precond(r, s))) break;
+      if ((rc = dist_dot(h, c, n, r, s, &gamma))) break;
+      if ((rc = dist_dot(h, c, n, r, r, &i_prod))) break;
+      if (h_norms) h_norms[i] = std::sqrt(i_prod);
+      if (i_prod / bi_prod < eps) break;
+      if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
+      const double beta = gamma / gamma_old;
+      if ((rc = b200_vec_scale(h, n, beta, p))) break;
+      if ((rc = b200_vec_axpy(h, n, 1.0, s, p))) break;
+    }
+  } while (0);
+  if (!rc) {
+    cudaMemcpyAsync(d_x, xx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream);
+    if (iters_out) *iters_out = i;
+    if (final_rel_res) *final_rel_res = bi_prod > 0.0 ? std::sqrt(i_prod / bi_prod) : 0.0;
+  }
+  b200_dfree(h, p); b200_dfree(h, s); b200_dfree(h, r); b200_dfree(h, xx); b200_dfree(h, sc);
+  return rc;
+}

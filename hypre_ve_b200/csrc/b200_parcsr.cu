@@ -113,6 +113,29 @@ __global__ void gen_kernel(Grid g, double v0, double v1, double v2, double v3, i
   if (!FILL) { diag_i[row] = cd; offd_i[row] = co; }
 }
 
+// merged form for the multi-rank path: local rows, GLOBAL column ids, reference entry order
+template <int STENCIL, bool FILL>
+__global__ void gen_global_kernel(Grid g, double v0, double v1, double v2, double v3, int *A_i, int *A_j, double *A_a) {
+  const int nxl = g.x1 - g.x0, nyl = g.y1 - g.y0, nzl = g.z1 - g.z0;
+  const long long nloc = (long long)nxl * nyl * nzl;
+  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= nloc) return;
+  const int lx = (int)(row % nxl), ly = (int)((row / nxl) % nyl), lz = (int)(row / ((long long)nxl * nyl));
+  const int ix = g.x0 + lx, iy = g.y0 + ly, iz = g.z0 + lz;
+  int cnt = 0;
+  const int pos = FILL ? A_i[row] : 0;
+  const double vals[4] = {v0, v1, v2, v3};
+  for (int k = 0; k < STENCIL; k++) {
+    int dx, dy, dz, vi;
+    stencil_offset<STENCIL>(k, &dx, &dy, &dz, &vi);
+    const int jx = ix + dx, jy = iy + dy, jz = iz + dz;
+    if (jx < 0 || jx >= g.nx || jy < 0 || jy >= g.ny || jz < 0 || jz >= g.nz) continue;
+    if (FILL) { A_j[pos + cnt] = global_index(g, jx, jy, jz); A_a[pos + cnt] = vals[vi]; }
+    cnt++;
+  }
+  if (!FILL) A_i[row] = cnt;
+}
+
 __global__ void lookup_kernel(int n, const int *__restrict__ gj, int ncols, const int *__restrict__ col_map,
                               int *__restrict__ j) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +186,53 @@ int b200_compress_offd(b200_handle h, int nnz, const int *d_gj, int *d_j, int *n
   B200_TRY(b200_dfree(h, d_num)); B200_TRY(b200_dfree(h, tmp));
   *ncols_out = num; *col_map_out = col_map;
   return 0;
+}
+
+int b200_box_first_row(int nx, int ny, int nz, int P, int Q, int R, int p, int q, int r) {
+  int x0, x1, y0, y1, z0, z1;
+  part_range(nx, P, p, &x0, &x1); part_range(ny, Q, q, &y0, &y1); part_range(nz, R, r, &z0, &z1);
+  (void)x1; (void)R;
+  return (int)((long long)z0 * nx * ny + ((long long)y0 * nx + (long long)x0 * (y1 - y0)) * (z1 - z0));   // par_laplace.c:78
+}
+
+template <int STENCIL>
+static int generate_global(b200_handle h, Grid g, const double *vals, b200_csr *out) {
+  const int nxl = g.x1 - g.x0, nyl = g.y1 - g.y0, nzl = g.z1 - g.z0;
+  const int nloc = nxl * nyl * nzl;
+  int *ai = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &ai, (size_t)nloc + 1));
+  B200_CUDA(cudaMemsetAsync(ai + nloc, 0, sizeof(int), h->stream));
+  const double v0 = vals[0], v1 = vals[1], v2 = STENCIL == 7 ? vals[2] : 0.0, v3 = STENCIL == 7 ? vals[3] : 0.0;
+  if (nloc) {
+    gen_global_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, ai, nullptr, nullptr);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_exclusive_scan_inplace(h, ai, (size_t)nloc + 1));
+  int nnz = 0;
+  B200_CUDA(cudaMemcpyAsync(&nnz, ai + nloc, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  b200_csr A = nullptr;
+  B200_TRY(b200_csr_alloc(h, nloc, g.nx * g.ny * g.nz, nnz, true, &A));
+  B200_CUDA(cudaMemcpyAsync(A->i, ai, sizeof(int) * ((size_t)nloc + 1), cudaMemcpyDeviceToDevice, h->stream));
+  if (nloc) {
+    gen_global_kernel<STENCIL, true><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, A->i, A->j, A->a);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_dfree(h, ai));
+  *out = A;
+  return 0;
+}
+
+int b200_generate_stencil_global(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q, int r,
+                                 int stencil, const double *vals, b200_csr *out, int *first_row) {
+  if (nx < 1 || ny < 1 || nz < 1 || P < 1 || Q < 1 || R < 1) B200_FAIL("bad grid");
+  if ((long long)nx * ny * nz > 2147483647LL) B200_FAIL("global size exceeds int32 (HYPRE_BigInt=int)");
+  Grid g{nx, ny, nz, P, Q, R, p, q, r, 0, 0, 0, 0, 0, 0};
+  part_range(nx, P, p, &g.x0, &g.x1);
+  part_range(ny, Q, q, &g.y0, &g.y1);
+  part_range(nz, R, r, &g.z0, &g.z1);
+  *first_row = b200_box_first_row(nx, ny, nz, P, Q, R, p, q, r);
+  return stencil == 7 ? generate_global<7>(h, g, vals, out) : generate_global<27>(h, g, vals, out);
 }
 
 template <int STENCIL>

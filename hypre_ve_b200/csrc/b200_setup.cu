@@ -15,6 +15,7 @@
 // HBM scratch replacing the reference's dense per-thread marker arrays; rows are processed in
 // chunks so the scratch stays bounded.
 #include "b200_internal.h"
+#include "b200_comm.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -498,7 +499,7 @@ __global__ void spgemm_ub_kernel(int n, const int *__restrict__ A_i, const int *
   cap[i] = cap_for((int)ub);
 }
 __global__ void spgemm_count_kernel(int r0, int r1, const int *__restrict__ A_i, const int *__restrict__ A_j,
-                                    const int *__restrict__ B_i, const int *__restrict__ B_j, int allsquare,
+                                    const int *__restrict__ B_i, const int *__restrict__ B_j, int allsquare, int diag_base,
                                     const long long *__restrict__ scan, long long base, int *__restrict__ keys,
                                     int *__restrict__ vals, int *__restrict__ cnt) {
   int ic = r0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,7 +509,7 @@ __global__ void spgemm_count_kernel(int r0, int r1, const int *__restrict__ A_i,
   if (cap == 0) { cnt[ic - r0] = 0; return; }
   Tab t{keys + off, vals + off, (unsigned)(cap - 1)};
   int n = 0;
-  if (allsquare) { tab_insert(t, ic, n); n++; }      // diagonal first (:384-388, :442-448)
+  if (allsquare) { tab_insert(t, diag_base + ic, n); n++; }      // diagonal first (:384-388, :442-448)
   for (int ia = A_i[ic]; ia < A_i[ic + 1]; ia++) {
     int ja = A_j[ia];
     for (int ib = B_i[ja]; ib < B_i[ja + 1]; ib++) {
@@ -647,6 +648,83 @@ int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int
   return 0;
 }
 
+namespace {
+__global__ void pmis_ghost_measure_kernel(int ng, const int *__restrict__ cf_ghost, double *__restrict__ m_ghost) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < ng && cf_ghost[i] != 0) m_ghost[i] = 0;          // par_coarsen.c:2654-2662
+}
+}  // namespace
+
+// Row-partitioned PMIS (par_coarsen.c:2031-2738 with num_procs > 1).  S has n local rows and columns in
+// the extended local space [owned | ghosts of `halo`]; measures use the GLOBAL row index for the random
+// draw (seq_rand, par_indepset.c:44-55), so the result does not depend on the partition.
+int b200_pmis_dist(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int *d_cf_ext) {
+  const int n = S->nrows, ng = halo ? halo->ng : 0, ne = n + ng;
+  int *colcnt = nullptr, *ingraph = nullptr, *d_count = nullptr, *cf2 = nullptr;
+  double *measure = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &colcnt, ne));
+  B200_TRY(b200_dalloc<int>(h, &ingraph, n));
+  B200_TRY(b200_dalloc<int>(h, &cf2, n));
+  B200_TRY(b200_dalloc<int>(h, &d_count, 1));
+  B200_TRY(b200_dalloc<double>(h, &measure, ne));
+  B200_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * (size_t)(ne ? ne : 1), h->stream));
+  if (S->nnz) {
+    colcount_kernel<<<b200_grid(S->nnz, 256), 256, 0, h->stream>>>(S->nnz, S->j, colcnt);
+    B200_LAUNCH_CHECK();
+  }
+  if (halo) B200_TRY(b200_halo_reverse_add_i32(h, c, halo, colcnt + n, colcnt));     // :2187-2228 (job 2)
+  if (n) {
+    pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf_ext);
+    B200_LAUNCH_CHECK();
+  }
+  if (halo) {
+    B200_TRY(b200_halo_forward_f64(h, c, halo, measure, measure + n));               // :2357-2372 (job 1)
+    B200_TRY(b200_halo_forward_i32(h, c, halo, d_cf_ext, d_cf_ext + n));
+  }
+  int iter = 0;
+  while (true) {
+    B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
+    if (n) {
+      pmis_graph_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf_ext, ingraph, d_count);
+      B200_LAUNCH_CHECK();
+    }
+    int count = 0;
+    B200_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    long long total = count;
+    B200_TRY(b200_comm_allreduce_sum_ll(h, c, &total, 1));                           // :2399
+    if (total == 0) break;
+    if (ne) {
+      pmis_mark_kernel<<<b200_grid(ne, 256), 256, 0, h->stream>>>(ne, measure, d_cf_ext);   // local and ghost nodes (:2430-2449)
+      B200_LAUNCH_CHECK();
+    }
+    if (n) {
+      pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf_ext);
+      B200_LAUNCH_CHECK();
+    }
+    if (halo) {
+      B200_TRY(b200_halo_reverse_clear_i32(h, c, halo, d_cf_ext + n, d_cf_ext));     // job 12 + :2509-2526
+      B200_TRY(b200_halo_forward_i32(h, c, halo, d_cf_ext, d_cf_ext + n));           // job 11 (:2530)
+    }
+    if (n) {
+      pmis_setcf_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, ingraph, measure, d_cf_ext, cf2);
+      B200_LAUNCH_CHECK();
+      B200_CUDA(cudaMemcpyAsync(d_cf_ext, cf2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    if (halo) {
+      B200_TRY(b200_halo_forward_i32(h, c, halo, d_cf_ext, d_cf_ext + n));           // :2603-2617
+      if (ng) {
+        pmis_ghost_measure_kernel<<<b200_grid(ng, 256), 256, 0, h->stream>>>(ng, d_cf_ext + n, measure + n);
+        B200_LAUNCH_CHECK();
+      }
+    }
+    if (++iter > 1000) B200_FAIL("PMIS did not terminate");
+  }
+  B200_TRY(b200_dfree(h, colcnt)); B200_TRY(b200_dfree(h, ingraph)); B200_TRY(b200_dfree(h, cf2));
+  B200_TRY(b200_dfree(h, d_count)); B200_TRY(b200_dfree(h, measure));
+  return 0;
+}
+
 extern "C" int b200_pmis(b200_handle h, b200_csr S, int seed, int *d_cf) {
   if (!S) B200_FAIL("pmis: null S");
   return b200_pmis_rows(h, S, seed, 0, d_cf, nullptr);
@@ -665,25 +743,36 @@ int b200_coarse_map(b200_handle h, int n, const int *d_cf, int **f2c_out, int *n
   return 0;
 }
 
-int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor, int max_elmts,
+int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, int n, const int *d_f2c, int ncoarse,
+                           double trunc_factor, int max_elmts, b200_csr *out, int *done);
+int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C,
                            b200_csr *out, int *done);
-int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, b200_csr *out, int *done);
 static bool force_general() {
   const char *e = getenv("B200_FORCE_GENERAL_SETUP");   // test hook: exercise the HBM-scratch kernels
   return e && e[0] == '1';
 }
 
+int b200_extpi_interp_ex(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, int n, const int *d_f2c_in, int ncoarse_in,
+                         double trunc_factor, int max_elmts, b200_csr *out);
+
 extern "C" int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor,
                                  int max_elmts, b200_csr *out) {
   if (!A || !A->a || !S) B200_FAIL("interp: bad arguments");
+  return b200_extpi_interp_ex(h, A, S, d_cf, A->nrows, nullptr, 0, trunc_factor, max_elmts, out);
+}
+
+// General form used by the multi-rank path: A and S may carry extra (ghost) rows after the first n,
+// cf / f2c are indexed in the same extended space, and f2c holds the (global) coarse column ids.
+int b200_extpi_interp_ex(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, int n, const int *d_f2c_in, int ncoarse_in,
+                         double trunc_factor, int max_elmts, b200_csr *out) {
   if (!force_general()) {
     int done = 0;
-    B200_TRY(b200_extpi_interp_warp(h, A, S, d_cf, trunc_factor, max_elmts, out, &done));
+    B200_TRY(b200_extpi_interp_warp(h, A, S, d_cf, n, d_f2c_in, ncoarse_in, trunc_factor, max_elmts, out, &done));
     if (done) return 0;
   }
-  const int n = A->nrows;
-  int *f2c = nullptr, ncoarse = 0;
-  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
+  int *f2c = nullptr, ncoarse = ncoarse_in;
+  if (d_f2c_in) f2c = const_cast<int *>(d_f2c_in);
+  else B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
   int *cap = nullptr;
   B200_TRY(b200_dalloc<int>(h, &cap, (size_t)n + 1));
   extpi_ub_kernel<<<b200_grid((size_t)n + 1, TB), TB, 0, h->stream>>>(n, S->i, S->j, d_cf, cap);
@@ -738,7 +827,8 @@ extern "C" int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const in
     B200_TRY(b200_dfree(h, ck.Pf_i)); B200_TRY(b200_dfree(h, ck.Pf_j)); B200_TRY(b200_dfree(h, ck.Pf_a));
   }
   B200_TRY(b200_dfree(h, keys)); B200_TRY(b200_dfree(h, vals));
-  B200_TRY(b200_dfree(h, plan.scan)); B200_TRY(b200_dfree(h, P_cnt)); B200_TRY(b200_dfree(h, f2c));
+  B200_TRY(b200_dfree(h, plan.scan)); B200_TRY(b200_dfree(h, P_cnt));
+  if (!d_f2c_in) B200_TRY(b200_dfree(h, f2c));
   B200_TRY(b200_csr_build_plan(h, P));
   *out = P;
   return 0;
@@ -781,19 +871,27 @@ extern "C" int b200_csr_transpose(b200_handle h, b200_csr A, b200_csr *out) {
   return 0;
 }
 
+int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out);
+
 extern "C" int b200_csr_multiply(b200_handle h, b200_csr A, b200_csr B, b200_csr *out) {
   if (!A || !B || !A->a || !B->a) B200_FAIL("multiply: matrices with values required");
   if (A->ncols != B->nrows) B200_FAIL("multiply: incompatible matrix dimensions");   // csr_matop.c:334-338
+  return b200_csr_multiply_ex(h, A, B, (A->nrows == B->ncols) ? 1 : 0, 0, B->ncols, out);
+}
+
+// General form used by the multi-rank path: A's column ids index the rows of B (B may hold ghost
+// rows), B's column ids may be global, `allsquare` and the diagonal's column id (diag_base + row)
+// are given by the caller.
+int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out) {
   if (!force_general()) {
     int done = 0;
-    B200_TRY(b200_csr_multiply_warp(h, A, B, out, &done));
+    B200_TRY(b200_csr_multiply_warp(h, A, B, allsquare, diag_base, ncols_C, out, &done));
     if (done) return 0;
   }
   const int n = A->nrows;
-  const int allsquare = (A->nrows == B->ncols) ? 1 : 0;
   int *cap = nullptr;
   B200_TRY(b200_dalloc<int>(h, &cap, (size_t)n + 1));
-  spgemm_ub_kernel<<<b200_grid((size_t)n + 1, TB), TB, 0, h->stream>>>(n, A->i, A->j, B->i, allsquare, B->ncols, cap);
+  spgemm_ub_kernel<<<b200_grid((size_t)n + 1, TB), TB, 0, h->stream>>>(n, A->i, A->j, B->i, allsquare, ncols_C, cap);
   B200_LAUNCH_CHECK();
   ChunkPlan plan;
   B200_TRY(plan_chunks(h, n, cap, &plan));
@@ -814,7 +912,7 @@ extern "C" int b200_csr_multiply(b200_handle h, b200_csr A, b200_csr B, b200_csr
     Chunk ck{r0, r1, nullptr, nullptr, nullptr};
     B200_TRY(b200_dalloc<int>(h, &ck.Ci, (size_t)nr + 1));
     B200_CUDA(cudaMemsetAsync(ck.Ci + nr, 0, sizeof(int), h->stream));
-    spgemm_count_kernel<<<b200_grid(nr, TB), TB, 0, h->stream>>>(r0, r1, A->i, A->j, B->i, B->j, allsquare, plan.scan,
+    spgemm_count_kernel<<<b200_grid(nr, TB), TB, 0, h->stream>>>(r0, r1, A->i, A->j, B->i, B->j, allsquare, diag_base, plan.scan,
                                                                  plan.base[c], keys, vals, ck.Ci);
     B200_LAUNCH_CHECK();
     B200_CUDA(cudaMemcpyAsync(C_cnt + r0, ck.Ci, sizeof(int) * (size_t)nr, cudaMemcpyDeviceToDevice, h->stream));
@@ -834,7 +932,7 @@ extern "C" int b200_csr_multiply(b200_handle h, b200_csr A, b200_csr B, b200_csr
   B200_CUDA(cudaMemcpyAsync(&nnz, C_cnt + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   b200_csr Cm = nullptr;
-  B200_TRY(b200_csr_alloc(h, n, B->ncols, nnz, true, &Cm));
+  B200_TRY(b200_csr_alloc(h, n, ncols_C, nnz, true, &Cm));
   B200_CUDA(cudaMemcpyAsync(Cm->i, C_cnt, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
   for (auto &ck : chunks) {
     const int nr = ck.r1 - ck.r0;

@@ -289,7 +289,7 @@ template <int CAP, int GB, bool NUMERIC>
 __global__ void __launch_bounds__(32 * WPB)
 spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
                    const int *__restrict__ B_i, const int *__restrict__ B_j, const double *__restrict__ B_a,
-                   int allsquare, const int *__restrict__ rows, int *__restrict__ cnt,
+                   int allsquare, int diag_base, const int *__restrict__ rows, int *__restrict__ cnt,
                    const int *__restrict__ C_i, int *__restrict__ C_j, double *__restrict__ C_a,
                    int *__restrict__ overflow) {
   constexpr int LIMIT = CAP / 2;
@@ -314,8 +314,8 @@ spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A
     bool over = false;
     if (allsquare) {                                // diagonal first (:384-388, :442-448)
       if (lane == 0) {
-        bool nw; int slot = wt_insert<CAP>(keys, ic, &nw);
-        if (NUMERIC) { vals[slot] = 0; cols[0] = ic; acc[0] = 0.0; }
+        bool nw; int slot = wt_insert<CAP>(keys, diag_base + ic, &nw);
+        if (NUMERIC) { vals[slot] = 0; cols[0] = diag_base + ic; acc[0] = 0.0; }
       }
       count = 1;
       __syncwarp();
@@ -472,19 +472,19 @@ int build_row_list(b200_handle h, int n, const int *cnt, int lo, int hi, int **l
 int b200_coarse_map(b200_handle h, int n, const int *d_cf, int **f2c_out, int *ncoarse);
 
 // returns 0 and *done = 1 when the warp path produced P; *done = 0 -> caller must use the general path
-int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, double trunc_factor, int max_elmts,
-                           b200_csr *out, int *done) {
+int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf, int n, const int *d_f2c_in, int ncoarse_in,
+                           double trunc_factor, int max_elmts, b200_csr *out, int *done) {
   *done = 0;
   if (max_elmts <= 0) return 0;                       // unbounded rows: general path
-  const int n = A->nrows;
   if (n == 0) return 0;
   // stencil-sized rows: the dependent-load chain per row is short and thread-per-row keeps 32x more
   // rows in flight than a warp per row -> the general kernels win there (profiles/README.md r1_b)
-  if ((double)A->nnz / n <= 10.0) return 0;
+  if ((double)A->nnz / (A->nrows ? A->nrows : 1) <= 10.0) return 0;
   int *d_flag = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
-  int *f2c = nullptr, ncoarse = 0;
-  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
+  int *f2c = nullptr, ncoarse = ncoarse_in;
+  if (d_f2c_in) f2c = const_cast<int *>(d_f2c_in);
+  else B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &ncoarse));
   int *sj = nullptr, *cnt = nullptr;
   double *sa = nullptr;
   B200_TRY(b200_dalloc<int>(h, &sj, (size_t)n * max_elmts));
@@ -518,7 +518,8 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   }
   if (flag) {                                         // some row outgrew even the large shared table
     B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa)); B200_TRY(b200_dfree(h, cnt));
-    B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, d_flag));
+    if (!d_f2c_in) B200_TRY(b200_dfree(h, f2c));
+    B200_TRY(b200_dfree(h, d_flag));
     return 0;
   }
   B200_TRY(b200_exclusive_scan_inplace(h, cnt, (size_t)n + 1));
@@ -531,7 +532,8 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   strided_to_csr_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, max_elmts, P->i, sj, sa, P->j, P->a);
   B200_LAUNCH_CHECK();
   B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa)); B200_TRY(b200_dfree(h, cnt));
-  B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, d_flag));
+  if (!d_f2c_in) B200_TRY(b200_dfree(h, f2c));
+  B200_TRY(b200_dfree(h, d_flag));
   B200_TRY(b200_csr_build_plan(h, P));
   *out = P;
   *done = 1;
@@ -539,7 +541,7 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
 }
 
 template <int GB>
-static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare, b200_csr *out, int *done) {
+static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out, int *done) {
   const int n = A->nrows;
   int *cnt = nullptr, *d_flag = nullptr;
   B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
@@ -555,7 +557,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
       constexpr int CAP = 256;
       const size_t bytes = (size_t)WPB * sizeof(int) * CAP;
       spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, n, 16), 32 * WPB, bytes, h->stream>>>(
-          n, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, nullptr, cnt, nullptr, nullptr, nullptr, d_flag);
+          n, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, nullptr, cnt, nullptr, nullptr, nullptr, d_flag);
       B200_LAUNCH_CHECK();
     } else {
       constexpr int CAP = 2048;
@@ -564,7 +566,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
       B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
       if (m > 0) {
         spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, m, 6), 32 * WPB, bytes, h->stream>>>(
-            m, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, rows, cnt, nullptr, nullptr, nullptr, d_flag);
+            m, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, rows, cnt, nullptr, nullptr, nullptr, d_flag);
         B200_LAUNCH_CHECK();
       }
       B200_TRY(b200_dfree(h, rows));
@@ -581,7 +583,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
   B200_CUDA(cudaMemcpyAsync(&nnz, C_i + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   b200_csr C = nullptr;
-  B200_TRY(b200_csr_alloc(h, n, B->ncols, nnz, true, &C));
+  B200_TRY(b200_csr_alloc(h, n, ncols_C, nnz, true, &C));
   B200_CUDA(cudaMemcpyAsync(C->i, C_i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
   B200_TRY(b200_dfree(h, C_i));
   // numeric: one launch per size class (order-preserving row lists), each with the smallest table that holds the row
@@ -594,7 +596,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
     if (m > 0) {                                                                                                  \
       B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, true>, bytes));                                               \
       spgemm_warp_kernel<CAP, GB, true><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                    \
-          m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, rows, cnt, C->i, C->j, C->a, d_flag);                 \
+          m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, diag_base, rows, cnt, C->i, C->j, C->a, d_flag);                 \
       B200_LAUNCH_CHECK();                                                                                        \
     }                                                                                                             \
     B200_TRY(b200_dfree(h, rows));                                                                                \
@@ -610,11 +612,11 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
   return 0;
 }
 
-int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, b200_csr *out, int *done) {
+int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C,
+                           b200_csr *out, int *done) {
   *done = 0;
   const int n = A->nrows;
   if (n == 0) return 0;
-  const int allsquare = (A->nrows == B->ncols) ? 1 : 0;
   int *d_max = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_max, 1));
   B200_CUDA(cudaMemsetAsync(d_max, 0, sizeof(int), h->stream));
@@ -626,8 +628,8 @@ int b200_csr_multiply_warp(b200_handle h, b200_csr A, b200_csr B, b200_csr *out,
   B200_CUDA(cudaMemcpyAsync(&maxlen, d_max, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   B200_TRY(b200_dfree(h, d_max));
-  if (maxlen <= 4) return spgemm_warp_run<4>(h, A, B, allsquare, out, done);
-  if (maxlen <= 8) return spgemm_warp_run<8>(h, A, B, allsquare, out, done);
-  if (maxlen <= 16) return spgemm_warp_run<16>(h, A, B, allsquare, out, done);
-  return spgemm_warp_run<32>(h, A, B, allsquare, out, done);
+  if (maxlen <= 4) return spgemm_warp_run<4>(h, A, B, allsquare, diag_base, ncols_C, out, done);
+  if (maxlen <= 8) return spgemm_warp_run<8>(h, A, B, allsquare, diag_base, ncols_C, out, done);
+  if (maxlen <= 16) return spgemm_warp_run<16>(h, A, B, allsquare, diag_base, ncols_C, out, done);
+  return spgemm_warp_run<32>(h, A, B, allsquare, diag_base, ncols_C, out, done);
 }

@@ -26,6 +26,10 @@ typedef struct b200_handle_s *b200_handle;
 typedef struct b200_csr_s    *b200_csr;     /* device CSR block            (seq_mv/csr_matrix.h:25-56)   */
 typedef struct b200_parcsr_s *b200_parcsr;  /* row-partitioned ParCSR      (parcsr_mv/par_csr_matrix.h:27-95) */
 typedef struct b200_amg_s    *b200_amg;     /* BoomerAMG hierarchy + parms (parcsr_ls/par_amg.h:18-271)  */
+typedef struct b200_comm_s   *b200_comm;    /* communicator: one rank per GPU (MPI_Comm of the reference)  */
+typedef struct b200_comm_group_s *b200_comm_group;   /* in-process rank group (test backend)             */
+typedef struct b200_dist_matrix_s *b200_dist_matrix; /* row-partitioned operator + halo plan (ParCSR + CommPkg) */
+typedef struct b200_dist_amg_s *b200_dist_amg;       /* row-partitioned BoomerAMG hierarchy                */
 
 /* ---- runtime (utilities/hypre_general.c:128 HYPRE_Init, hypre_memory.c) -------------------- */
 int         b200_init(int device, b200_handle *h);
@@ -137,6 +141,48 @@ int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
  * receives ||r_k||_2 for k=0..iters (needs max_iter+1 doubles). */
 int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x,
                    double tol, int max_iter, int *iters, double *final_rel_res, double *h_norms);
+
+/* ---- multi-GPU: row-partitioned ParCSR over NVLink ---------------------------------
+ * One process per GPU.  Rows are partitioned contiguously like hypre's ParCSR layout
+ * (par_csr_matrix.h:27-95); each rank stores its rows as ONE CSR whose columns are the owned
+ * range followed by the ghost columns (sorted by global id), so a SpMV is a halo exchange
+ * (hypre_ParCSRCommHandleCreate job 1, par_csr_communication.c:307-580) + one kernel over
+ * [x_owned | x_ghost].  Setup runs the same per-row algorithms as the single-GPU path on rows
+ * fetched from their owners, in the global row's entry order, with PMIS measures drawn from the
+ * global row index (the reference's partition-independent `-pmis1`, par_indepset.c:44-55): the
+ * hierarchy is therefore bit-identical for every number of GPUs.                                    */
+int b200_comm_create_single(b200_comm *c);
+int b200_comm_group_create(int nranks, b200_comm_group *g);     /* N ranks = N host threads, one GPU   */
+int b200_comm_group_destroy(b200_comm_group g);
+int b200_comm_create_threads(b200_comm_group g, int rank, b200_comm *c);
+int b200_comm_nccl_unique_id(char *id128);                       /* rank 0, then broadcast by the host  */
+int b200_comm_create_nccl(b200_handle h, int nranks, int rank, const char *id128, b200_comm *c);
+int b200_comm_destroy(b200_handle h, b200_comm c);
+int b200_comm_rank(b200_comm c);
+int b200_comm_size(b200_comm c);
+
+/* GenerateLaplacian / GenerateLaplacian27pt on a P x Q x R process grid, rank -> (p,q,r) as ij.c:7785-7787 */
+int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                                 int stencil, const double *values, b200_dist_matrix *A);
+int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix A);
+int b200_dist_matrix_info(b200_dist_matrix A, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
+                          int *n_ghost, int *first_col, int *global_cols);
+/* local rows with GLOBAL column ids, entry order preserved (for parity tests) */
+int b200_dist_matrix_download(b200_handle h, b200_dist_matrix A, int *h_i, int *h_j_global, double *h_a);
+/* y = alpha*A*x + beta*b; d_x must have room for local_rows + n_ghost doubles (ghosts are received in place) */
+int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_dist_matrix A, double *d_x, double beta,
+                     const double *d_b, double *d_y);
+/* hypre_BoomerAMGSetup across ranks; parameters are taken from a b200_amg object */
+int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg params, b200_dist_matrix A, b200_dist_amg *amg);
+int b200_dist_amg_destroy(b200_handle h, b200_dist_amg amg);
+int b200_dist_amg_num_levels(b200_dist_amg amg);
+b200_dist_matrix b200_dist_amg_level_A(b200_dist_amg amg, int level);
+b200_dist_matrix b200_dist_amg_level_P(b200_dist_amg amg, int level);
+int b200_dist_amg_level_cf(b200_handle h, b200_dist_amg amg, int level, int *h_cf);
+int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms);
+/* hypre_PCGSolve across ranks (dot products = deterministic rank-ordered sums) */
+int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const double *d_b,
+                        double *d_x, double tol, int max_iter, int *iters, double *final_rel_res, double *h_norms);
 
 #ifdef __cplusplus
 }
