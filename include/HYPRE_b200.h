@@ -1,0 +1,146 @@
+/* HYPRE_b200.h -- the reference's public C API for the hot path, served by libhypre_b200.so.
+ *
+ * Same names, argument meaning and error behaviour as hypre 2.20 (HYPRE_Int return = the global
+ * accumulated error flag, utilities/hypre_error.h:19-20; HYPRE_ERROR_GENERIC 1, MEMORY 2, ARG 4,
+ * CONV 256).  Types follow the reference configuration of this build: HYPRE_Int = HYPRE_BigInt =
+ * int, HYPRE_Real = HYPRE_Complex = double, MPI_Comm = int (sequential stubs, mpistubs.h:138).
+ * A driver written against hypre's HYPRE.h / HYPRE_IJ_mv.h / HYPRE_parcsr_ls.h / HYPRE_krylov.h
+ * for the ex5 / `ij -solver 1` call sequence compiles and links against this header + library
+ * unchanged (examples/ij_b200.c is such a driver).
+ *
+ * Reference declarations: IJ_mv/HYPRE_IJ_mv.h:68-460, parcsr_ls/HYPRE_parcsr_ls.h (BoomerAMG
+ * :75-1500, ParCSRPCG :2160-2230), krylov/HYPRE_krylov.h:75-200, utilities/HYPRE_utilities.h. */
+#ifndef HYPRE_B200_API_H
+#define HYPRE_B200_API_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int HYPRE_Int;
+typedef int HYPRE_BigInt;
+typedef double HYPRE_Real;
+typedef double HYPRE_Complex;
+#ifndef HYPRE_B200_HAVE_MPI_COMM
+typedef int MPI_Comm;
+#define hypre_MPI_COMM_WORLD 0
+#define MPI_COMM_WORLD 0
+#endif
+#define HYPRE_PARCSR 5555
+#define HYPRE_ERROR_GENERIC 1
+#define HYPRE_ERROR_MEMORY 2
+#define HYPRE_ERROR_ARG 4
+#define HYPRE_ERROR_CONV 256
+
+struct hypre_IJMatrix_struct;      typedef struct hypre_IJMatrix_struct *HYPRE_IJMatrix;
+struct hypre_IJVector_struct;      typedef struct hypre_IJVector_struct *HYPRE_IJVector;
+struct hypre_ParCSRMatrix_struct;  typedef struct hypre_ParCSRMatrix_struct *HYPRE_ParCSRMatrix;
+struct hypre_ParVector_struct;     typedef struct hypre_ParVector_struct *HYPRE_ParVector;
+struct hypre_Solver_struct;        typedef struct hypre_Solver_struct *HYPRE_Solver;
+typedef struct hypre_Matrix_struct *HYPRE_Matrix;
+typedef struct hypre_Vector_struct *HYPRE_Vector;
+typedef HYPRE_Int (*HYPRE_PtrToSolverFcn)(HYPRE_Solver, HYPRE_Matrix, HYPRE_Vector, HYPRE_Vector);
+typedef HYPRE_Int (*HYPRE_PtrToParSolverFcn)(HYPRE_Solver, HYPRE_ParCSRMatrix, HYPRE_ParVector, HYPRE_ParVector);
+
+/* utilities/hypre_general.c:128,:197 ; utilities/hypre_error.c */
+HYPRE_Int HYPRE_Init(void);
+HYPRE_Int HYPRE_Finalize(void);
+HYPRE_Int HYPRE_GetError(void);
+HYPRE_Int HYPRE_ClearAllErrors(void);
+HYPRE_Int HYPRE_CheckError(HYPRE_Int ierr, HYPRE_Int code);
+
+/* IJ_mv/HYPRE_IJMatrix.c:23,:282,:418,:800,:1042 */
+HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm comm, HYPRE_BigInt ilower, HYPRE_BigInt iupper, HYPRE_BigInt jlower,
+                               HYPRE_BigInt jupper, HYPRE_IJMatrix *matrix);
+HYPRE_Int HYPRE_IJMatrixDestroy(HYPRE_IJMatrix matrix);
+HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix matrix, HYPRE_Int type);
+HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix matrix);
+HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix matrix, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows,
+                                  const HYPRE_BigInt *cols, const HYPRE_Complex *values);
+HYPRE_Int HYPRE_IJMatrixAddToValues(HYPRE_IJMatrix matrix, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows,
+                                    const HYPRE_BigInt *cols, const HYPRE_Complex *values);
+HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix);
+HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix matrix, void **object);
+HYPRE_Int HYPRE_IJVectorCreate(MPI_Comm comm, HYPRE_BigInt jlower, HYPRE_BigInt jupper, HYPRE_IJVector *vector);
+HYPRE_Int HYPRE_IJVectorDestroy(HYPRE_IJVector vector);
+HYPRE_Int HYPRE_IJVectorSetObjectType(HYPRE_IJVector vector, HYPRE_Int type);
+HYPRE_Int HYPRE_IJVectorInitialize(HYPRE_IJVector vector);
+HYPRE_Int HYPRE_IJVectorSetValues(HYPRE_IJVector vector, HYPRE_Int nvalues, const HYPRE_BigInt *indices, const HYPRE_Complex *values);
+HYPRE_Int HYPRE_IJVectorGetValues(HYPRE_IJVector vector, HYPRE_Int nvalues, const HYPRE_BigInt *indices, HYPRE_Complex *values);
+HYPRE_Int HYPRE_IJVectorAssemble(HYPRE_IJVector vector);
+HYPRE_Int HYPRE_IJVectorGetObject(HYPRE_IJVector vector, void **object);
+
+/* parcsr_ls/par_laplace.c:15, par_laplace_27pt.c:15 (problem generators used by ij.c:7808,:9084) */
+HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,
+                                     HYPRE_Int R, HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value);
+HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,
+                                         HYPRE_Int R, HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value);
+HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix matrix);
+HYPRE_Int HYPRE_ParCSRMatrixGetDims(HYPRE_ParCSRMatrix matrix, HYPRE_BigInt *M, HYPRE_BigInt *N);
+/* parcsr_mv/HYPRE_parcsr_matrix.c: y = alpha*A*x + beta*y */
+HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y);
+HYPRE_Int HYPRE_ParVectorCreate(MPI_Comm comm, HYPRE_BigInt global_size, HYPRE_BigInt *partitioning, HYPRE_ParVector *vector);
+HYPRE_Int HYPRE_ParVectorInitialize(HYPRE_ParVector vector);
+HYPRE_Int HYPRE_ParVectorSetConstantValues(HYPRE_ParVector vector, HYPRE_Complex value);
+HYPRE_Int HYPRE_ParVectorDestroy(HYPRE_ParVector vector);
+HYPRE_Int HYPRE_ParVectorInnerProd(HYPRE_ParVector x, HYPRE_ParVector y, HYPRE_Real *prod);
+/* copies the local part of the vector to a host buffer (reference users read hypre_VectorData directly) */
+HYPRE_Int HYPRE_b200_ParVectorGetHostValues(HYPRE_ParVector vector, HYPRE_Complex *host_out);
+
+/* parcsr_ls/HYPRE_parcsr_amg.c:15,:32,:42,:58 + setters (:235 StrongThreshold ... :1914 KeepTranspose) */
+HYPRE_Int HYPRE_BoomerAMGCreate(HYPRE_Solver *solver);
+HYPRE_Int HYPRE_BoomerAMGDestroy(HYPRE_Solver solver);
+HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver solver, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x);
+HYPRE_Int HYPRE_BoomerAMGSolve(HYPRE_Solver solver, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x);
+HYPRE_Int HYPRE_BoomerAMGSetCoarsenType(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetInterpType(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetPMaxElmts(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetTruncFactor(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetStrongThreshold(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetMaxRowSum(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetRelaxType(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetRelaxOrder(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetRelaxWt(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetOuterWt(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetNumSweeps(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetCycleType(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetMaxLevels(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetMaxCoarseSize(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetMinCoarseSize(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetMaxIter(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetTol(HYPRE_Solver solver, HYPRE_Real v);
+HYPRE_Int HYPRE_BoomerAMGSetAggNumLevels(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetNumFunctions(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetRAP2(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetModuleRAP2(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetKeepTranspose(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetPrintLevel(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetLogging(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGSetDebugFlag(HYPRE_Solver solver, HYPRE_Int v);
+HYPRE_Int HYPRE_BoomerAMGGetNumIterations(HYPRE_Solver solver, HYPRE_Int *num_iterations);
+
+/* parcsr_ls/HYPRE_parcsr_pcg.c:14-75, krylov/HYPRE_pcg.c:29,:45,:260,:326,:348 */
+HYPRE_Int HYPRE_ParCSRPCGCreate(MPI_Comm comm, HYPRE_Solver *solver);
+HYPRE_Int HYPRE_ParCSRPCGDestroy(HYPRE_Solver solver);
+HYPRE_Int HYPRE_ParCSRPCGSetup(HYPRE_Solver solver, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x);
+HYPRE_Int HYPRE_ParCSRPCGSolve(HYPRE_Solver solver, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x);
+HYPRE_Int HYPRE_PCGSetup(HYPRE_Solver solver, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x);
+HYPRE_Int HYPRE_PCGSolve(HYPRE_Solver solver, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x);
+HYPRE_Int HYPRE_PCGSetTol(HYPRE_Solver solver, HYPRE_Real tol);
+HYPRE_Int HYPRE_PCGSetAbsoluteTol(HYPRE_Solver solver, HYPRE_Real a_tol);
+HYPRE_Int HYPRE_PCGSetMaxIter(HYPRE_Solver solver, HYPRE_Int max_iter);
+HYPRE_Int HYPRE_PCGSetTwoNorm(HYPRE_Solver solver, HYPRE_Int two_norm);
+HYPRE_Int HYPRE_PCGSetRelChange(HYPRE_Solver solver, HYPRE_Int rel_change);
+HYPRE_Int HYPRE_PCGSetRecomputeResidual(HYPRE_Solver solver, HYPRE_Int recompute_residual);
+HYPRE_Int HYPRE_PCGSetPrintLevel(HYPRE_Solver solver, HYPRE_Int level);
+HYPRE_Int HYPRE_PCGSetLogging(HYPRE_Solver solver, HYPRE_Int level);
+HYPRE_Int HYPRE_PCGSetPrecond(HYPRE_Solver solver, HYPRE_PtrToSolverFcn precond, HYPRE_PtrToSolverFcn precond_setup,
+                              HYPRE_Solver precond_solver);
+HYPRE_Int HYPRE_PCGGetNumIterations(HYPRE_Solver solver, HYPRE_Int *num_iterations);
+HYPRE_Int HYPRE_PCGGetFinalRelativeResidualNorm(HYPRE_Solver solver, HYPRE_Real *norm);
+/* device times of the last Setup / Solve in seconds (the reference prints wall clock via hypre_PrintTiming) */
+HYPRE_Int HYPRE_b200_PCGGetTimes(HYPRE_Solver solver, HYPRE_Real *setup_s, HYPRE_Real *solve_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
