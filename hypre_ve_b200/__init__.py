@@ -66,6 +66,7 @@ SIGNATURES = {
     "b200_amg_set_real": (_i, [_vp, C.c_char_p, _d]),
     "b200_amg_setup": (_i, [_vp, _vp, _vp]),
     "b200_amg_solve": (_i, [_vp, _vp, _vp, _vp]),
+    "b200_amg_solve_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _ip, _dp]),
     "b200_amg_num_levels": (_i, [_vp]),
     "b200_amg_level_A": (_vp, [_vp, _i]),
     "b200_amg_level_P": (_vp, [_vp, _i]),
@@ -78,6 +79,8 @@ SIGNATURES = {
     "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
     "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
     "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
+    "b200_pcg_solve_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp]),
+    "b200_parcsr_diag_scale": (_i, [_vp, _vp, _vp, _vp]),
     "b200_comm_create_single": (_i, [C.POINTER(_vp)]),
     "b200_comm_group_create": (_i, [_i, C.POINTER(_vp)]),
     "b200_comm_group_destroy": (_i, [_vp]),

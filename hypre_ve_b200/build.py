@@ -61,5 +61,22 @@ def build(verbose=False, force=False):
     return LIB
 
 
+def build_examples():
+    """gcc-compile the plain-C client of the HYPRE_* API (examples/ij_b200.c) against the library."""
+    root = os.path.abspath(os.path.join(HERE, ".."))
+    src = os.path.join(root, "examples", "ij_b200.c")
+    exe = os.path.join(root, "examples", "ij_b200")
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return exe
+    cmd = ["gcc", "-O2", "-Wall", "-I" + os.path.join(root, "include"), src, "-o", exe, "-L" + HERE, "-lhypre_b200",
+           "-Wl,-rpath,$ORIGIN/../hypre_ve_b200", "-lm"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode:
+        print(p.stdout)
+        raise RuntimeError("gcc failed on examples/ij_b200.c")
+    return exe
+
+
 if __name__ == "__main__":
     print(build(verbose="-v" in sys.argv, force="-f" in sys.argv))
+    print(build_examples())

@@ -45,7 +45,7 @@ struct b200_amg_s {
     ip = {{"CoarsenType", 8}, {"InterpType", 6}, {"PMaxElmts", 4}, {"RelaxType", 18}, {"MaxLevels", 25},
           {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"NumSweeps", 1}, {"AggNumLevels", 0}, {"ModuleRAP2", 1},
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
-          {"NumFunctions", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
+          {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
           {"OuterWt", 1.0}, {"Tol", 0.0}};
   }
@@ -401,19 +401,76 @@ static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bo
   return 0;
 }
 
+__global__ void diag_scale_kernel(size_t n, const int *__restrict__ A_i, const double *__restrict__ A_a,
+                                  const double *__restrict__ y, double *__restrict__ x) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) x[i] = y[i] / A_a[A_i[i]];     // HYPRE_parcsr_pcg.c:239-255 (diagonal is stored first)
+}
+
+// HYPRE_ParCSRDiagScale (parcsr_ls/HYPRE_parcsr_pcg.c:228-258): x = y ./ diag(A)
+extern "C" int b200_parcsr_diag_scale(b200_handle h, b200_parcsr A, const double *d_y, double *d_x) {
+  if (!A) B200_FAIL("diag_scale: null matrix");
+  const int n = A->diag->nrows;
+  diag_scale_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, A->diag->i, A->diag->a, d_y, d_x);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// hypre_BoomerAMGSolve (par_amg_solve.c:21-380): V-cycles until ||f - A u|| / ||f|| < Tol (converge_type 0)
+// or MaxIter cycles.  MaxIter 1 / Tol 0 is the preconditioner configuration (one cycle, no norms).
+extern "C" int b200_amg_solve_ex(b200_handle h, b200_amg amg, b200_parcsr A, const double *d_f, double *d_u,
+                                 int *num_iterations, double *final_rel_res) {
+  if (!amg || !amg->is_setup) B200_FAIL("amg_solve: setup has not been called");
+  const int max_iter = amg->ip["MaxIter"], min_iter = amg->ip["MinIter"];
+  const double tol = amg->rp["Tol"];
+  const int n = amg->lv[0].n;
+  double resid_nrm = 1.0, rhs_norm = 0.0, relative_resid = 1.0, t = 0.0;
+  b200_csr A0 = A ? A->diag : amg->lv[0].A;
+  if (tol > 0.) {                                                                  // :143-214
+    B200_TRY(b200_csr_spmv_epi(h, A0, d_u, amg->Vtemp, 0, -1.0, 1.0, d_f, nullptr));
+    B200_TRY(b200_vec_dot(h, n, amg->Vtemp, amg->Vtemp, &t));
+    resid_nrm = std::sqrt(t);
+    if (resid_nrm != 0. && !(resid_nrm / resid_nrm == resid_nrm / resid_nrm))
+      B200_FAIL("hypre_BoomerAMGSolve: INFs and/or NaNs detected in input");
+    B200_TRY(b200_vec_dot(h, n, d_f, d_f, &t));
+    rhs_norm = std::sqrt(t);
+    relative_resid = rhs_norm ? resid_nrm / rhs_norm : resid_nrm;
+  }
+  int cycle_count = 0;
+  while ((relative_resid >= tol || cycle_count < min_iter) && cycle_count < max_iter) {   // :236
+    B200_TRY(amg_cycle(h, amg, d_f, d_u, false));
+    if (tol > 0.) {
+      B200_TRY(b200_csr_spmv_epi(h, A0, d_u, amg->Vtemp, 0, -1.0, 1.0, d_f, nullptr));
+      B200_TRY(b200_vec_dot(h, n, amg->Vtemp, amg->Vtemp, &t));
+      resid_nrm = std::sqrt(t);
+      relative_resid = rhs_norm ? resid_nrm / rhs_norm : resid_nrm;
+    }
+    ++cycle_count;
+  }
+  if (num_iterations) *num_iterations = cycle_count;
+  if (final_rel_res) *final_rel_res = relative_resid;
+  if (cycle_count == max_iter && tol > 0.) return 256;       // HYPRE_ERROR_CONV (:307-311); the solution is still valid
+  return 0;
+}
+
 extern "C" int b200_amg_solve(b200_handle h, b200_amg amg, const double *d_f, double *d_u) {
   if (!amg || !amg->is_setup) B200_FAIL("amg_solve: setup has not been called");
   if (amg->ip["MaxIter"] != 1 || amg->rp["Tol"] != 0.0)
-    B200_FAIL("amg_solve: only the preconditioner configuration MaxIter 1 / Tol 0 is implemented");
+    B200_FAIL("amg_solve: preconditioner entry point needs MaxIter 1 / Tol 0 (use b200_amg_solve_ex as a solver)");
   return amg_cycle(h, amg, d_f, d_u, false);
 }
 
-// hypre_PCGSolve (krylov/pcg.c:271-757), two_norm = 1, rel_change = 0, default stop criteria.
-extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x, double tol,
-                              int max_iter, int *iters_out, double *final_rel_res, double *h_norms) {
-  if (!A) B200_FAIL("pcg: null matrix");
-  if (A->offd->ncols > 0) B200_FAIL("pcg: multi-rank solve not built yet");
+// hypre_PCGSolve (krylov/pcg.c:271-757).  Supported: two_norm 0/1, tol, a_tol, max_iter; preconditioner =
+// BoomerAMG (amg != NULL), diagonal scaling (precond 2) or none.  rel_change / recompute_residual /
+// stop_crit / cf_tol / rtol are rejected (ij.c passes 0 for all of them).
+extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, const b200_pcg_params *prm, const double *d_b,
+                                 double *d_x, int *iters_out, double *final_rel_res, double *h_norms) {
+  if (!A || !prm) B200_FAIL("pcg: null argument");
+  if (A->offd->ncols > 0) B200_FAIL("pcg: this entry point is single-rank; use b200_dist_pcg_solve");
   if (amg && !amg->is_setup) B200_FAIL("pcg: preconditioner has not been set up");
+  if (prm->rel_change || prm->recompute_residual) B200_FAIL("pcg: rel_change / recompute_residual are not implemented");
+  const double tol = prm->tol, a_tol = prm->a_tol;
+  const int max_iter = prm->max_iter, two_norm = prm->two_norm;
   const int n = A->diag->nrows;
   double *p = nullptr, *s = nullptr, *r = nullptr, *sc = nullptr;
   B200_TRY(b200_dalloc<double>(h, &p, n));
@@ -423,25 +480,36 @@ extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const 
   double *hs = h->h_pinned;
   auto precond = [&](const double *rhs, double *out) -> int {
     if (amg) return amg_cycle(h, amg, rhs, out, true);    // ClearVector + precond (pcg.c:434-435,:568-569)
-    return b200_vec_copy(h, n, rhs, out);                 // identity preconditioner
+    if (prm->precond == 2) return b200_parcsr_diag_scale(h, A, rhs, out);
+    return b200_vec_copy(h, n, rhs, out);                 // identity preconditioner (hypre_ParKrylovIdentity)
   };
   int rc = 0, i = 0;
   double bi_prod = 0, i_prod = 0, eps = 0;
   do {
-    if ((rc = b200_vec_dot(h, n, d_b, d_b, &bi_prod))) break;             // :347
-    eps = tol * tol;                                                        // :383, a_tol = 0
+    if (two_norm) {
+      if ((rc = b200_vec_dot(h, n, d_b, d_b, &bi_prod))) break;             // :347
+    } else {
+      if ((rc = precond(d_b, p))) break;                                    // :351-354  <C*b, b>
+      if ((rc = b200_vec_dot(h, n, p, d_b, &bi_prod))) break;
+    }
+    if (bi_prod != 0. && !(bi_prod / bi_prod == bi_prod / bi_prod)) {       // :359-381
+      rc = b200_set_error(__FILE__, __LINE__, "hypre_PCGSolve: INFs and/or NaNs detected in input"); break;
+    }
+    eps = tol * tol;                                                        // :383
     if (!(bi_prod > 0.0)) {                                                 // :403-416  b == 0 -> x = b
       if ((rc = b200_vec_copy(h, n, d_b, d_x))) break;
       if (h_norms) h_norms[0] = 0.0;
       break;
     }
+    eps = std::fmax(tol * tol, a_tol * a_tol / bi_prod);                    // :393-400 default criterion
     // r = b - A x (:428-430)
     if ((rc = b200_parcsr_matvec(h, -1.0, A, d_x, 1.0, d_b, r))) break;
     if ((rc = precond(r, p))) break;                                        // p = C r
     if ((rc = b200_vec_dot_dev(h, n, r, p, sc + 0))) break;                 // gamma = <r,p> (:438)
     if (h_norms) {
       double i_prod_0 = 0;
-      if ((rc = b200_vec_dot(h, n, r, r, &i_prod_0))) break;                // :466
+      if (two_norm) { if ((rc = b200_vec_dot(h, n, r, r, &i_prod_0))) break; }   // :466
+      else { if ((rc = b200_vec_dot(h, n, r, p, &i_prod_0))) break; }
       h_norms[0] = std::sqrt(i_prod_0);
     }
     while ((i + 1) <= max_iter) {                                           // :498
@@ -454,11 +522,11 @@ extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const 
       ++g_b200_launches;
       if ((rc = precond(r, s))) break;                                      // s = C r (:568-569)
       if ((rc = b200_vec_dot_dev(h, n, r, s, sc + 0))) break;               // gamma = <r,s> (:572)
-      if ((rc = b200_vec_dot_dev(h, n, r, r, sc + 3))) break;               // i_prod = <r,r> (:590)
+      if (two_norm) { if ((rc = b200_vec_dot_dev(h, n, r, r, sc + 3))) break; }   // i_prod = <r,r> (:590)
       cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
       if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = b200_set_error(__FILE__, __LINE__, "pcg sync failed"); break; }
       const double gamma = hs[0], sdotp = hs[1];
-      i_prod = hs[3];
+      i_prod = two_norm ? hs[3] : gamma;                                    // :589-592
       if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }   // :516-521
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;                                    // converged (:634, :672-676)
@@ -475,4 +543,12 @@ extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const 
   }
   b200_dfree(h, p); b200_dfree(h, s); b200_dfree(h, r); b200_dfree(h, sc);
   return rc;
+}
+
+extern "C" int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x, double tol,
+                              int max_iter, int *iters_out, double *final_rel_res, double *h_norms) {
+  b200_pcg_params prm;
+  prm.tol = tol; prm.a_tol = 0.0; prm.max_iter = max_iter; prm.two_norm = 1;            // ij.c:3892-3897
+  prm.rel_change = 0; prm.recompute_residual = 0; prm.precond = amg ? 1 : 0;
+  return b200_pcg_solve_ex(h, A, amg, &prm, d_b, d_x, iters_out, final_rel_res, h_norms);
 }

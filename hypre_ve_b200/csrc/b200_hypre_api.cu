@@ -1,0 +1,855 @@
+// b200_hypre_api.cu -- the reference's public C API (boundary B1 of SURVEY.md 8b) for the hot path,
+// implemented on top of the b200_* C-ABI.  Host code only: every numerical step is a b200_* call into
+// the CUDA kernels of this library, there is no CPU arithmetic path.
+//
+// Declarations: include/HYPRE_b200.h (each group cites the reference file it mirrors).
+// Behaviour kept from the reference:
+//   * every function returns the global accumulated error flag (utilities/hypre_error.c:17-40);
+//     argument errors set HYPRE_ERROR_ARG | arg<<3 (hypre_error.h:32);
+//   * handles are opaque pointers; HYPRE_PCGSetPrecond takes two function pointers + a solver
+//     (krylov/HYPRE_pcg.c:260) and HYPRE_PCGSetup calls precond_setup(precond_solver, A, b, x)
+//     (krylov/pcg.c:214-262);
+//   * IJ matrices assembled through the auxiliary-row path keep the diagonal first and the other
+//     entries in insertion order (IJ_mv/IJMatrix_parcsr.c:2925-2952); SetValues overwrites an
+//     existing column, AddToValues accumulates (:697-1213, :1215-1745);
+//   * BoomerAMG setters only store; what the B200 path cannot do is rejected at Setup with
+//     HYPRE_ERROR_GENERIC and a message on stderr (the reference would run it on the CPU).
+// Single rank per process here (MPI_Comm is the sequential-stub int); the row-partitioned
+// multi-GPU path is reached through b200_dist_* (INTEGRATION.md shows the MPI-build binding).
+#include "b200_internal.h"
+#include "../../include/HYPRE_b200.h"
+#include <cmath>
+#include <map>
+#include <string>
+#include <utility>
+#include <vector>
+
+int b200_amg_get_int(b200_amg a, const char *name);
+
+namespace {
+
+HYPRE_Int g_error_flag = 0;             // hypre__global_error (utilities/hypre_error.c:17)
+b200_handle g_handle = nullptr;
+
+HYPRE_Int err(HYPRE_Int code) { g_error_flag |= code; return g_error_flag; }
+HYPRE_Int err_arg(int k) { return err(HYPRE_ERROR_ARG | (k << 3)); }
+HYPRE_Int err_b200(const char *where) {
+  fprintf(stderr, "hypre_b200: %s: %s\n", where, b200_last_error());
+  return err(HYPRE_ERROR_GENERIC);
+}
+b200_handle handle() {
+  if (!g_handle) {
+    const char *dev = getenv("HYPRE_B200_DEVICE");
+    if (b200_init(dev ? atoi(dev) : 0, &g_handle)) {
+      fprintf(stderr, "hypre_b200: no usable CUDA device: %s\n", b200_last_error());
+      g_handle = nullptr;
+      err(HYPRE_ERROR_GENERIC);
+    }
+  }
+  return g_handle;
+}
+#define NEED_HANDLE() b200_handle h = handle(); if (!h) return g_error_flag
+#define CALL(expr, where) do { if ((expr)) return err_b200(where); } while (0)
+
+enum SolverKind { KIND_AMG = 0x414d47, KIND_PCG = 0x504347 };
+
+}  // namespace
+
+struct hypre_ParCSRMatrix_struct {
+  b200_parcsr A = nullptr;
+  int global_rows = 0, global_cols = 0;
+  long long nnz = 0;
+  bool owned = true;
+};
+struct hypre_ParVector_struct {
+  double *d = nullptr;
+  int n = 0;
+  bool initialized = false;
+};
+struct hypre_IJMatrix_struct {
+  int ilower = 0, iupper = -1, jlower = 0, jupper = -1;
+  int object_type = -1;
+  bool initialized = false, assembled = false;
+  std::vector<std::vector<std::pair<int, double>>> rows;      // auxiliary rows, insertion order
+  hypre_ParCSRMatrix_struct *object = nullptr;
+};
+struct hypre_IJVector_struct {
+  int jlower = 0, jupper = -1;
+  int object_type = -1;
+  bool initialized = false, dirty = false;
+  std::vector<double> host;
+  hypre_ParVector_struct *object = nullptr;
+};
+struct hypre_Solver_struct {
+  int kind = 0;
+  // BoomerAMG
+  b200_amg amg = nullptr;
+  std::map<std::string, double> stored;        // every setter's last value (inert ones included)
+  int num_iterations = 0;
+  double rel_res = 0.0;
+  // PCG (krylov/pcg.h:190-230 defaults from hypre_PCGCreate, pcg.c:60-104)
+  double tol = 1e-6, a_tol = 0.0;
+  int max_iter = 1000, two_norm = 0, rel_change = 0, recompute_residual = 0, print_level = 0, logging = 0;
+  HYPRE_PtrToSolverFcn precond = nullptr, precond_setup = nullptr;
+  HYPRE_Solver precond_solver = nullptr;
+  std::vector<double> norms;
+  double setup_s = 0.0, solve_s = 0.0;
+};
+
+namespace {
+
+bool is_amg(HYPRE_Solver s) { return s && s->kind == KIND_AMG; }
+bool is_pcg(HYPRE_Solver s) { return s && s->kind == KIND_PCG; }
+
+struct Neutral { const char *name; double value; const char *what; };
+// parameters that switch on something outside the B200 path: only the neutral value is accepted
+const Neutral kNeutral[] = {
+    {"PostInterpType", 0, "Jacobi interpolation"},     {"SmoothNumLevels", 0, "complex smoothers (Schwarz/Pilut/ParaSails/Euclid)"},
+    {"Additive", -1, "additive cycles"},               {"MultAdditive", -1, "mult-additive cycles"},
+    {"Simple", -1, "simple additive cycles"},          {"Nodal", 0, "nodal systems coarsening"},
+    {"FCycle", 0, "F-cycles"},                         {"NonGalerkinTol", 0, "non-Galerkin coarse operators"},
+    {"NumCPoints", 0, "user C-points"},                {"NumFPoints", 0, "user F-points"},
+    {"NumIsolatedFPoints", 0, "isolated F-points"},    {"NumInterpVectors", 0, "interpolation vectors (GSMG/RBM)"},
+    {"GSMG", 0, "GSMG"},                               {"CoarsenCutFactor", 0, "coarsening cut factor"},
+    {"Redundant", 0, "redundant coarse solves"},       {"SeqThreshold", 0, "sequential coarse AMG"},
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- utilities ------------------------------------------------------------------------------
+HYPRE_Int HYPRE_Init(void) { handle(); return g_error_flag; }
+HYPRE_Int HYPRE_Finalize(void) {
+  if (g_handle) { b200_finalize(g_handle); g_handle = nullptr; }
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_GetError(void) { return g_error_flag; }
+HYPRE_Int HYPRE_ClearAllErrors(void) { g_error_flag = 0; return 0; }
+HYPRE_Int HYPRE_ClearError(HYPRE_Int code) { g_error_flag &= ~code; return g_error_flag; }
+HYPRE_Int HYPRE_CheckError(HYPRE_Int ierr, HYPRE_Int code) { return ierr & code; }
+HYPRE_Int HYPRE_GetErrorArg(void) { return (g_error_flag >> 3) & 31; }
+void HYPRE_DescribeError(HYPRE_Int ierr, char *msg) {         // utilities/hypre_error.c:55-80
+  if (ierr == 0) sprintf(msg, "[No error] ");
+  if (ierr & HYPRE_ERROR_GENERIC) sprintf(msg, "[Generic error] ");
+  if (ierr & HYPRE_ERROR_MEMORY) sprintf(msg, "[Memory error] ");
+  if (ierr & HYPRE_ERROR_ARG) sprintf(msg, "[Error in argument %d] ", (ierr >> 3) & 31);
+  if (ierr & HYPRE_ERROR_CONV) sprintf(msg, "[Method did not converge] ");
+}
+
+// ---- IJ matrix ------------------------------------------------------------------------------
+HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm, HYPRE_BigInt ilower, HYPRE_BigInt iupper, HYPRE_BigInt jlower, HYPRE_BigInt jupper,
+                               HYPRE_IJMatrix *matrix) {
+  if (ilower > iupper + 1 || ilower < 0) return err_arg(2);          // HYPRE_IJMatrix.c:57-73
+  if (iupper < -1) return err_arg(3);
+  if (jlower > jupper + 1 || jlower < 0) return err_arg(4);
+  if (jupper < -1) return err_arg(5);
+  if (!matrix) return err_arg(6);
+  hypre_IJMatrix_struct *m = new hypre_IJMatrix_struct();
+  m->ilower = ilower; m->iupper = iupper; m->jlower = jlower; m->jupper = jupper;
+  *matrix = m;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix A);
+HYPRE_Int HYPRE_IJMatrixDestroy(HYPRE_IJMatrix m) {
+  if (!m) return err_arg(1);
+  if (m->object) HYPRE_ParCSRMatrixDestroy(m->object);
+  delete m;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix m, HYPRE_Int type) {
+  if (!m) return err_arg(1);
+  m->object_type = type;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix m) {
+  if (!m) return err_arg(1);
+  if (m->object_type != HYPRE_PARCSR) return err_arg(1);             // HYPRE_IJMatrix.c:303-311
+  m->rows.assign((size_t)(m->iupper - m->ilower + 1), {});
+  m->initialized = true;
+  m->assembled = false;
+  return g_error_flag;
+}
+static HYPRE_Int ij_set(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows, const HYPRE_BigInt *cols,
+                        const HYPRE_Complex *values, bool add) {
+  if (!m) return err_arg(1);
+  if (nrows == 0) return g_error_flag;
+  if (nrows < 0) return err_arg(2);
+  if (!ncols) return err_arg(3);
+  if (!rows) return err_arg(4);
+  if (!cols) return err_arg(5);
+  if (!values) return err_arg(6);
+  if (!m->initialized) return err_arg(1);
+  size_t at = 0;
+  for (int r = 0; r < nrows; r++) {
+    const int row = rows[r], n = ncols[r];
+    if (row < m->ilower || row > m->iupper) {
+      // the reference stashes off-processor rows for the owner (IJMatrix_parcsr.c:1395-1450); with one
+      // rank per process there is no owner to send them to
+      fprintf(stderr, "hypre_b200: IJMatrix row %d is outside the local range [%d, %d]\n", row, m->ilower, m->iupper);
+      at += n;
+      err(HYPRE_ERROR_GENERIC);
+      continue;
+    }
+    auto &R = m->rows[(size_t)(row - m->ilower)];
+    for (int k = 0; k < n; k++, at++) {
+      const int c = cols[at];
+      if (c < m->jlower || c > m->jupper) { err(HYPRE_ERROR_GENERIC); continue; }
+      bool found = false;
+      for (auto &e : R)
+        if (e.first == c) { e.second = add ? e.second + values[at] : values[at]; found = true; break; }
+      if (!found) R.emplace_back(c, values[at]);
+    }
+  }
+  m->assembled = false;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows,
+                                  const HYPRE_BigInt *cols, const HYPRE_Complex *values) {
+  return ij_set(m, nrows, ncols, rows, cols, values, false);
+}
+HYPRE_Int HYPRE_IJMatrixAddToValues(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows,
+                                    const HYPRE_BigInt *cols, const HYPRE_Complex *values) {
+  return ij_set(m, nrows, ncols, rows, cols, values, true);
+}
+HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix m) {
+  if (!m) return err_arg(1);
+  if (!m->initialized) return err_arg(1);
+  NEED_HANDLE();
+  const int n = (int)m->rows.size(), ncols = m->jupper - m->jlower + 1;
+  const bool square = (m->ilower == m->jlower && m->iupper == m->jupper);
+  std::vector<int> I((size_t)n + 1, 0), J;
+  std::vector<double> V;
+  size_t nnz = 0;
+  for (auto &R : m->rows) nnz += R.size();
+  J.reserve(nnz); V.reserve(nnz);
+  for (int i = 0; i < n; i++) {
+    const auto &R = m->rows[i];
+    int dpos = -1;
+    if (square)
+      for (size_t k = 0; k < R.size(); k++)
+        if (R[k].first - m->jlower == i) { dpos = (int)k; break; }
+    if (dpos >= 0) { J.push_back(i); V.push_back(R[dpos].second); }                 // diagonal first (:2933-2937)
+    for (size_t k = 0; k < R.size(); k++)
+      if ((int)k != dpos) { J.push_back(R[k].first - m->jlower); V.push_back(R[k].second); }
+    I[i + 1] = (int)J.size();
+  }
+  if (m->object) { HYPRE_ParCSRMatrixDestroy(m->object); m->object = nullptr; }
+  hypre_ParCSRMatrix_struct *P = new hypre_ParCSRMatrix_struct();
+  if (J.empty()) { J.push_back(0); V.push_back(0.0); }
+  if (b200_parcsr_create_from_host(h, n, ncols, (int)nnz, I.data(), J.data(), V.data(), &P->A)) {
+    delete P;
+    return err_b200("HYPRE_IJMatrixAssemble");
+  }
+  P->global_rows = n; P->global_cols = ncols; P->nnz = (long long)nnz;
+  m->object = P;
+  m->assembled = true;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix m, void **object) {
+  if (!m) return err_arg(1);
+  *object = m->object;
+  return g_error_flag;
+}
+
+// ---- IJ vector ------------------------------------------------------------------------------
+HYPRE_Int HYPRE_IJVectorCreate(MPI_Comm, HYPRE_BigInt jlower, HYPRE_BigInt jupper, HYPRE_IJVector *vector) {
+  if (jlower > jupper + 1 || jlower < 0) return err_arg(2);          // HYPRE_IJVector.c:45-57
+  if (jupper < -1) return err_arg(3);
+  hypre_IJVector_struct *v = new hypre_IJVector_struct();
+  v->jlower = jlower; v->jupper = jupper;
+  *vector = v;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorDestroy(HYPRE_ParVector v);
+HYPRE_Int HYPRE_IJVectorDestroy(HYPRE_IJVector v) {
+  if (!v) return err_arg(1);
+  if (v->object) HYPRE_ParVectorDestroy(v->object);
+  delete v;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorSetObjectType(HYPRE_IJVector v, HYPRE_Int type) {
+  if (!v) return err_arg(1);
+  v->object_type = type;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorInitialize(HYPRE_IJVector v) {
+  if (!v) return err_arg(1);
+  if (v->object_type != HYPRE_PARCSR) return err_arg(1);
+  NEED_HANDLE();
+  const int n = v->jupper - v->jlower + 1;
+  v->host.assign((size_t)n, 0.0);
+  if (!v->object) {
+    v->object = new hypre_ParVector_struct();
+    v->object->n = n;
+    CALL(b200_malloc(h, (void **)&v->object->d, sizeof(double) * (size_t)(n > 0 ? n : 1)), "HYPRE_IJVectorInitialize");
+    v->object->initialized = true;
+  }
+  CALL(b200_vec_fill(h, n, 0.0, v->object->d), "HYPRE_IJVectorInitialize");
+  v->initialized = true;
+  v->dirty = false;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorSetValues(HYPRE_IJVector v, HYPRE_Int nvalues, const HYPRE_BigInt *indices, const HYPRE_Complex *values) {
+  if (!v) return err_arg(1);
+  if (nvalues == 0) return g_error_flag;
+  if (nvalues < 0) return err_arg(2);
+  if (!values) return err_arg(4);
+  if (!v->initialized) return err_arg(1);
+  for (int k = 0; k < nvalues; k++) {
+    const int g = indices ? indices[k] : v->jlower + k;               // NULL indices = contiguous from jlower (IJVector_parcsr.c:374-390)
+    if (g < v->jlower || g > v->jupper) continue;                     // off-rank entries are dropped on one rank
+    v->host[(size_t)(g - v->jlower)] = values[k];
+  }
+  v->dirty = true;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorAddToValues(HYPRE_IJVector v, HYPRE_Int nvalues, const HYPRE_BigInt *indices, const HYPRE_Complex *values) {
+  if (!v) return err_arg(1);
+  if (nvalues == 0) return g_error_flag;
+  if (nvalues < 0) return err_arg(2);
+  if (!values) return err_arg(4);
+  if (!v->initialized) return err_arg(1);
+  for (int k = 0; k < nvalues; k++) {
+    const int g = indices ? indices[k] : v->jlower + k;
+    if (g < v->jlower || g > v->jupper) continue;
+    v->host[(size_t)(g - v->jlower)] += values[k];
+  }
+  v->dirty = true;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorAssemble(HYPRE_IJVector v) {
+  if (!v) return err_arg(1);
+  if (!v->initialized) return err_arg(1);
+  NEED_HANDLE();
+  if (v->dirty && !v->host.empty())
+    CALL(b200_memcpy_h2d(h, v->object->d, v->host.data(), sizeof(double) * v->host.size()), "HYPRE_IJVectorAssemble");
+  v->dirty = false;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorGetValues(HYPRE_IJVector v, HYPRE_Int nvalues, const HYPRE_BigInt *indices, HYPRE_Complex *values) {
+  if (!v) return err_arg(1);
+  if (nvalues == 0) return g_error_flag;
+  if (nvalues < 0) return err_arg(2);
+  if (!values) return err_arg(4);
+  if (!v->initialized || !v->object) return err_arg(1);
+  NEED_HANDLE();
+  if (!v->host.empty())       // the device copy is the truth (solvers write it); refresh the host mirror
+    CALL(b200_memcpy_d2h(h, v->host.data(), v->object->d, sizeof(double) * v->host.size()), "HYPRE_IJVectorGetValues");
+  for (int k = 0; k < nvalues; k++) {
+    const int g = indices ? indices[k] : v->jlower + k;
+    if (g < v->jlower || g > v->jupper) return err_arg(3);           // IJVector_parcsr.c:583-590
+    values[k] = v->host[(size_t)(g - v->jlower)];
+  }
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorGetObject(HYPRE_IJVector v, void **object) {
+  if (!v) return err_arg(1);
+  *object = v->object;
+  return g_error_flag;
+}
+
+// ---- ParCSR matrix / vector -----------------------------------------------------------------
+static HYPRE_ParCSRMatrix wrap_generated(b200_parcsr A, long long gr) {
+  hypre_ParCSRMatrix_struct *P = new hypre_ParCSRMatrix_struct();
+  P->A = A;
+  int nr = 0, nd = 0, no = 0, nco = 0;
+  b200_parcsr_local_rows(A, &nr, &nd, &no, &nco);
+  P->global_rows = P->global_cols = (int)gr;
+  P->nnz = (long long)nd + no;
+  return P;
+}
+HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int R,
+                                     HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value) {
+  b200_handle h = handle();
+  if (!h) return nullptr;
+  if (P * Q * R != 1) {
+    fprintf(stderr, "hypre_b200: GenerateLaplacian through the HYPRE API is single-rank; use b200_dist_generate_laplacian\n");
+    err(HYPRE_ERROR_GENERIC);
+    return nullptr;
+  }
+  b200_parcsr A = nullptr;
+  if (b200_generate_laplacian(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateLaplacian"); return nullptr; }
+  return wrap_generated(A, (long long)nx * ny * nz);
+}
+HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,
+                                         HYPRE_Int R, HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value) {
+  b200_handle h = handle();
+  if (!h) return nullptr;
+  if (P * Q * R != 1) {
+    fprintf(stderr, "hypre_b200: GenerateLaplacian27pt through the HYPRE API is single-rank; use b200_dist_generate_laplacian\n");
+    err(HYPRE_ERROR_GENERIC);
+    return nullptr;
+  }
+  b200_parcsr A = nullptr;
+  if (b200_generate_laplacian27(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateLaplacian27pt"); return nullptr; }
+  return wrap_generated(A, (long long)nx * ny * nz);
+}
+HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix A) {
+  if (!A) return err_arg(1);
+  NEED_HANDLE();
+  if (A->owned && A->A) b200_parcsr_destroy(h, A->A);
+  delete A;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRMatrixGetDims(HYPRE_ParCSRMatrix A, HYPRE_BigInt *M, HYPRE_BigInt *N) {
+  if (!A) return err_arg(1);
+  *M = A->global_rows; *N = A->global_cols;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRMatrixGetLocalRange(HYPRE_ParCSRMatrix A, HYPRE_BigInt *row_start, HYPRE_BigInt *row_end,
+                                          HYPRE_BigInt *col_start, HYPRE_BigInt *col_end) {
+  if (!A) return err_arg(1);
+  *row_start = 0; *row_end = A->global_rows - 1; *col_start = 0; *col_end = A->global_cols - 1;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_ParCSRMatrixGetNumNonzeros(HYPRE_ParCSRMatrix A, long long *nnz) {
+  if (!A) return err_arg(1);
+  *nnz = A->nnz;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y) {
+  if (!A) return err_arg(2);
+  if (!x) return err_arg(3);
+  if (!y) return err_arg(5);
+  NEED_HANDLE();
+  if (x == y) { fprintf(stderr, "hypre_b200: Matvec needs x != y\n"); return err(HYPRE_ERROR_GENERIC); }   // par_csr_matvec.c:68-76
+  if (x->n != A->global_cols || y->n != A->global_rows) return err(HYPRE_ERROR_GENERIC);                   // size check :85-98
+  CALL(b200_parcsr_matvec(h, alpha, A->A, x->d, beta, y->d, y->d), "HYPRE_ParCSRMatrixMatvec");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorCreate(MPI_Comm, HYPRE_BigInt global_size, HYPRE_BigInt *, HYPRE_ParVector *vector) {
+  if (global_size < 0) return err_arg(2);
+  hypre_ParVector_struct *v = new hypre_ParVector_struct();
+  v->n = global_size;
+  *vector = v;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorInitialize(HYPRE_ParVector v) {
+  if (!v) return err_arg(1);
+  NEED_HANDLE();
+  if (!v->d) {
+    CALL(b200_malloc(h, (void **)&v->d, sizeof(double) * (size_t)(v->n > 0 ? v->n : 1)), "HYPRE_ParVectorInitialize");
+    CALL(b200_vec_fill(h, v->n, 0.0, v->d), "HYPRE_ParVectorInitialize");
+  }
+  v->initialized = true;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorSetConstantValues(HYPRE_ParVector v, HYPRE_Complex value) {
+  if (!v || !v->d) return err_arg(1);
+  NEED_HANDLE();
+  CALL(b200_vec_fill(h, v->n, value, v->d), "HYPRE_ParVectorSetConstantValues");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorDestroy(HYPRE_ParVector v) {
+  if (!v) return err_arg(1);
+  NEED_HANDLE();
+  if (v->d) b200_free(h, v->d);
+  delete v;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorInnerProd(HYPRE_ParVector x, HYPRE_ParVector y, HYPRE_Real *prod) {
+  if (!x || !x->d) return err_arg(1);
+  if (!y || !y->d) return err_arg(2);
+  NEED_HANDLE();
+  CALL(b200_vec_dot(h, x->n, x->d, y->d, prod), "HYPRE_ParVectorInnerProd");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorCopy(HYPRE_ParVector x, HYPRE_ParVector y) {
+  if (!x || !x->d) return err_arg(1);
+  if (!y || !y->d) return err_arg(2);
+  NEED_HANDLE();
+  CALL(b200_vec_copy(h, x->n, x->d, y->d), "HYPRE_ParVectorCopy");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorScale(HYPRE_Complex value, HYPRE_ParVector x) {
+  if (!x || !x->d) return err_arg(2);
+  NEED_HANDLE();
+  CALL(b200_vec_scale(h, x->n, value, x->d), "HYPRE_ParVectorScale");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParVectorAxpy(HYPRE_Complex alpha, HYPRE_ParVector x, HYPRE_ParVector y) {
+  if (!x || !x->d) return err_arg(2);
+  if (!y || !y->d) return err_arg(3);
+  NEED_HANDLE();
+  CALL(b200_vec_axpy(h, x->n, alpha, x->d, y->d), "HYPRE_ParVectorAxpy");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_ParVectorGetHostValues(HYPRE_ParVector v, HYPRE_Complex *host_out) {
+  if (!v || !v->d) return err_arg(1);
+  NEED_HANDLE();
+  CALL(b200_memcpy_d2h(h, host_out, v->d, sizeof(double) * (size_t)v->n), "HYPRE_b200_ParVectorGetHostValues");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_ParVectorSetHostValues(HYPRE_ParVector v, const HYPRE_Complex *host_in) {
+  if (!v || !v->d) return err_arg(1);
+  NEED_HANDLE();
+  CALL(b200_memcpy_h2d(h, v->d, host_in, sizeof(double) * (size_t)v->n), "HYPRE_b200_ParVectorSetHostValues");
+  return g_error_flag;
+}
+
+// ---- BoomerAMG ------------------------------------------------------------------------------
+HYPRE_Int HYPRE_BoomerAMGCreate(HYPRE_Solver *solver) {
+  if (!solver) return err_arg(1);
+  hypre_Solver_struct *s = new hypre_Solver_struct();
+  s->kind = KIND_AMG;
+  b200_amg_create(&s->amg);
+  // library defaults of hypre_BoomerAMGCreate (par_amg.c:139-230) where they differ from b200_amg's
+  // ij-driver defaults: coarsen 10 (HMIS), relax 13/14 hybrid GS, mod_rap2 0, tol 1e-7, max_iter 20
+  s->stored = {{"CoarsenType", 10}, {"InterpType", 6}, {"PMaxElmts", 4}, {"RelaxType", -1}, {"ModuleRAP2", 0}, {"RAP2", 0},
+               {"KeepTranspose", 0}, {"Tol", 1e-7}, {"MaxIter", 20}, {"MinIter", 0}, {"RelaxOrder", 0}, {"NumSweeps", 1},
+               {"CycleType", 1}, {"MaxLevels", 25}, {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"AggNumLevels", 0},
+               {"NumFunctions", 1}, {"StrongThreshold", 0.25}, {"MaxRowSum", 0.9}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
+               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}};
+  for (const Neutral &nv : kNeutral) s->stored[nv.name] = nv.value;
+  *solver = s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGDestroy(HYPRE_Solver s) {
+  if (!is_amg(s)) return err_arg(1);
+  NEED_HANDLE();
+  b200_amg_destroy(h, s->amg);
+  delete s;
+  return g_error_flag;
+}
+
+#define AMG_SETTER(Name, Type, Check)                                                 \
+  HYPRE_Int HYPRE_BoomerAMGSet##Name(HYPRE_Solver s, Type v) {                        \
+    if (!is_amg(s)) return err_arg(1);                                                \
+    if (!(Check)) return err_arg(2);                                                  \
+    s->stored[#Name] = (double)v;                                                     \
+    return g_error_flag;                                                              \
+  }
+// argument checks as in par_amg.c (e.g. :1032 max_levels < 1, :1166 strong_threshold range, :1440 tol range)
+AMG_SETTER(CoarsenType, HYPRE_Int, true)
+AMG_SETTER(InterpType, HYPRE_Int, (v >= 0 && v <= 25) || v == 100)
+AMG_SETTER(PMaxElmts, HYPRE_Int, v >= 0)
+AMG_SETTER(TruncFactor, HYPRE_Real, v >= 0 && v < 1.0)
+AMG_SETTER(StrongThreshold, HYPRE_Real, v >= 0 && v <= 1.0)
+AMG_SETTER(MaxRowSum, HYPRE_Real, v > 0 && v <= 1.0)
+AMG_SETTER(RelaxType, HYPRE_Int, v >= 0)
+AMG_SETTER(RelaxOrder, HYPRE_Int, true)
+AMG_SETTER(RelaxWt, HYPRE_Real, true)
+AMG_SETTER(OuterWt, HYPRE_Real, true)
+AMG_SETTER(NumSweeps, HYPRE_Int, v >= 1)
+AMG_SETTER(CycleType, HYPRE_Int, v >= 1 && v <= 2)
+AMG_SETTER(MaxLevels, HYPRE_Int, v >= 1)
+AMG_SETTER(MaxCoarseSize, HYPRE_Int, v >= 1)
+AMG_SETTER(MinCoarseSize, HYPRE_Int, v >= 0)
+AMG_SETTER(MaxIter, HYPRE_Int, v >= 0)
+AMG_SETTER(MinIter, HYPRE_Int, true)
+AMG_SETTER(Tol, HYPRE_Real, v >= 0 && v <= 1.0)
+AMG_SETTER(AggNumLevels, HYPRE_Int, v >= 0)
+AMG_SETTER(NumFunctions, HYPRE_Int, v >= 1)
+AMG_SETTER(RAP2, HYPRE_Int, true)
+AMG_SETTER(ModuleRAP2, HYPRE_Int, true)
+AMG_SETTER(KeepTranspose, HYPRE_Int, true)
+AMG_SETTER(PrintLevel, HYPRE_Int, true)
+AMG_SETTER(Logging, HYPRE_Int, true)
+AMG_SETTER(DebugFlag, HYPRE_Int, true)
+// features outside the B200 path: stored, and rejected at Setup unless left at the neutral value
+AMG_SETTER(PostInterpType, HYPRE_Int, true)
+AMG_SETTER(SmoothNumLevels, HYPRE_Int, true)
+AMG_SETTER(Additive, HYPRE_Int, true)
+AMG_SETTER(MultAdditive, HYPRE_Int, true)
+AMG_SETTER(Simple, HYPRE_Int, true)
+AMG_SETTER(Nodal, HYPRE_Int, true)
+AMG_SETTER(FCycle, HYPRE_Int, true)
+AMG_SETTER(NonGalerkinTol, HYPRE_Real, v >= 0)
+AMG_SETTER(GSMG, HYPRE_Int, true)
+AMG_SETTER(CoarsenCutFactor, HYPRE_Int, true)
+AMG_SETTER(Redundant, HYPRE_Int, true)
+AMG_SETTER(SeqThreshold, HYPRE_Int, true)
+// parameters that are inert unless one of the switches above is on (the reference only stores them too)
+AMG_SETTER(CGCIts, HYPRE_Int, true)
+AMG_SETTER(NumSamples, HYPRE_Int, true)
+AMG_SETTER(MeasureType, HYPRE_Int, true)
+AMG_SETTER(JacobiTruncThreshold, HYPRE_Real, true)
+AMG_SETTER(SCommPkgSwitch, HYPRE_Real, true)
+AMG_SETTER(ISType, HYPRE_Int, true)
+AMG_SETTER(NumCRRelaxSteps, HYPRE_Int, true)
+AMG_SETTER(CRRate, HYPRE_Real, true)
+AMG_SETTER(CRStrongTh, HYPRE_Real, true)
+AMG_SETTER(CRUseCG, HYPRE_Int, true)
+AMG_SETTER(AddRelaxType, HYPRE_Int, true)
+AMG_SETTER(AddRelaxWt, HYPRE_Real, true)
+AMG_SETTER(AddLastLvl, HYPRE_Int, true)
+AMG_SETTER(MultAddPMaxElmts, HYPRE_Int, true)
+AMG_SETTER(MultAddTruncFactor, HYPRE_Real, true)
+AMG_SETTER(ChebyOrder, HYPRE_Int, true)
+AMG_SETTER(ChebyFraction, HYPRE_Real, true)
+AMG_SETTER(ChebyEigEst, HYPRE_Int, true)
+AMG_SETTER(ChebyVariant, HYPRE_Int, true)
+AMG_SETTER(ChebyScale, HYPRE_Int, true)
+AMG_SETTER(SmoothType, HYPRE_Int, true)
+AMG_SETTER(SmoothNumSweeps, HYPRE_Int, true)
+AMG_SETTER(AggInterpType, HYPRE_Int, true)
+AMG_SETTER(AggTruncFactor, HYPRE_Real, true)
+AMG_SETTER(AggP12TruncFactor, HYPRE_Real, true)
+AMG_SETTER(AggPMaxElmts, HYPRE_Int, true)
+AMG_SETTER(AggP12MaxElmts, HYPRE_Int, true)
+AMG_SETTER(NumPaths, HYPRE_Int, true)
+AMG_SETTER(NodalDiag, HYPRE_Int, true)
+AMG_SETTER(Variant, HYPRE_Int, true)
+AMG_SETTER(Overlap, HYPRE_Int, true)
+AMG_SETTER(DomainType, HYPRE_Int, true)
+AMG_SETTER(SchwarzUseNonSymm, HYPRE_Int, true)
+AMG_SETTER(SchwarzRlxWeight, HYPRE_Real, true)
+AMG_SETTER(EuLevel, HYPRE_Int, true)
+AMG_SETTER(EuBJ, HYPRE_Int, true)
+AMG_SETTER(EuSparseA, HYPRE_Real, true)
+#undef AMG_SETTER
+
+HYPRE_Int HYPRE_BoomerAMGSetOldDefault(HYPRE_Solver s) {               // HYPRE_parcsr_amg.c:1500-1508
+  if (!is_amg(s)) return err_arg(1);
+  s->stored["CoarsenType"] = 6; s->stored["InterpType"] = 0; s->stored["PMaxElmts"] = 0;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetPrintFileName(HYPRE_Solver s, const char *) { return is_amg(s) ? g_error_flag : err_arg(1); }
+HYPRE_Int HYPRE_BoomerAMGSetCycleRelaxType(HYPRE_Solver s, HYPRE_Int relax_type, HYPRE_Int k) {
+  if (!is_amg(s)) return err_arg(1);
+  if (k < 1 || k > 3) return err_arg(3);                               // par_amg.c:1690-1694
+  if (relax_type < 0) return err_arg(2);
+  s->stored[std::string("CycleRelaxType") + char('0' + k)] = relax_type;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetCycleNumSweeps(HYPRE_Solver s, HYPRE_Int num_sweeps, HYPRE_Int k) {
+  if (!is_amg(s)) return err_arg(1);
+  if (k < 1 || k > 3) return err_arg(3);
+  if (num_sweeps < 0) return err_arg(2);
+  s->stored[std::string("CycleNumSweeps") + char('0' + k)] = num_sweeps;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetLevelRelaxWt(HYPRE_Solver s, HYPRE_Real w, HYPRE_Int level) {
+  if (!is_amg(s)) return err_arg(1);
+  (void)level;
+  s->stored["LevelRelaxWtSet"] = 1; s->stored["LevelRelaxWt"] = w;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetLevelOuterWt(HYPRE_Solver s, HYPRE_Real w, HYPRE_Int level) {
+  if (!is_amg(s)) return err_arg(1);
+  (void)level;
+  s->stored["LevelOuterWtSet"] = 1; s->stored["LevelOuterWt"] = w;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetCPoints(HYPRE_Solver s, HYPRE_Int, HYPRE_Int n, HYPRE_BigInt *) {
+  if (!is_amg(s)) return err_arg(1);
+  s->stored["NumCPoints"] = n;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetFPoints(HYPRE_Solver s, HYPRE_Int n, HYPRE_BigInt *) {
+  if (!is_amg(s)) return err_arg(1);
+  s->stored["NumFPoints"] = n;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetIsolatedFPoints(HYPRE_Solver s, HYPRE_Int n, HYPRE_BigInt *) {
+  if (!is_amg(s)) return err_arg(1);
+  s->stored["NumIsolatedFPoints"] = n;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetDofFunc(HYPRE_Solver s, HYPRE_Int *) { return is_amg(s) ? g_error_flag : err_arg(1); }
+
+HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector, HYPRE_ParVector) {
+  if (!is_amg(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  NEED_HANDLE();
+  auto &st = s->stored;
+  for (const Neutral &nv : kNeutral)
+    if (st[nv.name] != nv.value) {
+      fprintf(stderr, "hypre_b200: BoomerAMGSetup: %s (%s = %g) is not on the B200 path\n", nv.what, nv.name, st[nv.name]);
+      return err(HYPRE_ERROR_GENERIC);
+    }
+  // relax type: SetRelaxType sets all three grid-relax slots, coarse defaults to 9 (par_amg.c:1650-1672);
+  // the cycle-specific setters override the slots
+  int rdown = (int)st["RelaxType"], rup = rdown, rcoarse = 9;
+  if (st["RelaxType"] < 0) { rdown = 13; rup = 14; }                    // library default (par_amg.c:206-209)
+  if (st.count("CycleRelaxType1")) rdown = (int)st["CycleRelaxType1"];
+  if (st.count("CycleRelaxType2")) rup = (int)st["CycleRelaxType2"];
+  if (st.count("CycleRelaxType3")) rcoarse = (int)st["CycleRelaxType3"];
+  if (rcoarse != 9) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: coarsest-grid relax type %d (only 9 = Gaussian elimination)\n", rcoarse); return err(HYPRE_ERROR_GENERIC); }
+  if (st.count("LevelRelaxWtSet") || st.count("LevelOuterWtSet")) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: per-level relaxation weights are not on the B200 path\n"); return err(HYPRE_ERROR_GENERIC); }
+  if (st.count("CycleNumSweeps3") && st["CycleNumSweeps3"] != 1) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: only one coarse sweep\n"); return err(HYPRE_ERROR_GENERIC); }
+  static const char *ints[] = {"CoarsenType", "InterpType", "PMaxElmts", "MaxLevels", "MaxCoarseSize", "MinCoarseSize", "NumSweeps",
+                               "AggNumLevels", "ModuleRAP2", "RAP2", "KeepTranspose", "RelaxOrder", "MaxIter", "MinIter", "CycleType",
+                               "NumFunctions", "PrintLevel"};
+  static const char *reals[] = {"StrongThreshold", "MaxRowSum", "TruncFactor", "RelaxWt", "OuterWt", "Tol"};
+  for (const char *k : ints) CALL(b200_amg_set_int(s->amg, k, (int)st[k]), "HYPRE_BoomerAMGSetup");
+  for (const char *k : reals) CALL(b200_amg_set_real(s->amg, k, st[k]), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "RelaxType", rdown), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "RelaxTypeUp", rup), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_setup(h, s->amg, A->A), "HYPRE_BoomerAMGSetup");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSolve(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_amg(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  if (!b || !b->d) return err_arg(3);
+  if (!x || !x->d) return err_arg(4);
+  NEED_HANDLE();
+  const int rc = b200_amg_solve_ex(h, s->amg, A->A, b->d, x->d, &s->num_iterations, &s->rel_res);
+  if (rc == HYPRE_ERROR_CONV) return err(HYPRE_ERROR_CONV);
+  if (rc) return err_b200("HYPRE_BoomerAMGSolve");
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) {
+  if (!is_amg(s)) return err_arg(1);
+  *n = s->num_iterations;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) {
+  if (!is_amg(s)) return err_arg(1);
+  *r = s->rel_res;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_BoomerAMGGetNumLevels(HYPRE_Solver s, HYPRE_Int *n) {
+  if (!is_amg(s)) return err_arg(1);
+  *n = b200_amg_num_levels(s->amg);
+  return g_error_flag;
+}
+// rows and nonzeros of A_level (the columns of the reference's setup statistics table, par_stats.c:22)
+HYPRE_Int HYPRE_b200_BoomerAMGGetLevelSize(HYPRE_Solver s, HYPRE_Int level, HYPRE_Int *rows, HYPRE_Int *nnz) {
+  if (!is_amg(s)) return err_arg(1);
+  b200_csr A = b200_amg_level_A(s->amg, level);
+  if (!A) return err_arg(2);
+  int nr = 0, nc = 0, nz = 0;
+  b200_csr_dims(A, &nr, &nc, &nz);
+  *rows = nr; *nnz = nz;
+  return g_error_flag;
+}
+
+// ---- diagonal scaling -----------------------------------------------------------------------
+HYPRE_Int HYPRE_ParCSRDiagScaleSetup(HYPRE_Solver, HYPRE_ParCSRMatrix, HYPRE_ParVector, HYPRE_ParVector) { return 0; }
+HYPRE_Int HYPRE_ParCSRDiagScale(HYPRE_Solver, HYPRE_ParCSRMatrix A, HYPRE_ParVector y, HYPRE_ParVector x) {
+  if (!A) return err_arg(2);
+  if (!y || !y->d) return err_arg(3);
+  if (!x || !x->d) return err_arg(4);
+  NEED_HANDLE();
+  CALL(b200_parcsr_diag_scale(h, A->A, y->d, x->d), "HYPRE_ParCSRDiagScale");
+  return g_error_flag;
+}
+
+// ---- PCG --------------------------------------------------------------------------------------
+HYPRE_Int HYPRE_ParCSRPCGCreate(MPI_Comm, HYPRE_Solver *solver) {
+  if (!solver) return err_arg(2);
+  hypre_Solver_struct *s = new hypre_Solver_struct();
+  s->kind = KIND_PCG;
+  *solver = s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRPCGDestroy(HYPRE_Solver s) {
+  if (!is_pcg(s)) return err_arg(1);
+  delete s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_PCGSetTol(HYPRE_Solver s, HYPRE_Real v) { if (!is_pcg(s)) return err_arg(1); s->tol = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetAbsoluteTol(HYPRE_Solver s, HYPRE_Real v) { if (!is_pcg(s)) return err_arg(1); s->a_tol = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetMaxIter(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->max_iter = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetTwoNorm(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->two_norm = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetRelChange(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->rel_change = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetRecomputeResidual(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->recompute_residual = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetPrintLevel(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->print_level = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetLogging(HYPRE_Solver s, HYPRE_Int v) { if (!is_pcg(s)) return err_arg(1); s->logging = v; return g_error_flag; }
+HYPRE_Int HYPRE_PCGSetPrecond(HYPRE_Solver s, HYPRE_PtrToSolverFcn precond, HYPRE_PtrToSolverFcn precond_setup, HYPRE_Solver precond_solver) {
+  if (!is_pcg(s)) return err_arg(1);
+  s->precond = precond; s->precond_setup = precond_setup; s->precond_solver = precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_PCGGetPrecond(HYPRE_Solver s, HYPRE_Solver *precond_data) {
+  if (!is_pcg(s)) return err_arg(1);
+  *precond_data = s->precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_PCGGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { if (!is_pcg(s)) return err_arg(1); *n = s->num_iterations; return g_error_flag; }
+HYPRE_Int HYPRE_PCGGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { if (!is_pcg(s)) return err_arg(1); *r = s->rel_res; return g_error_flag; }
+// ParCSR-typed aliases (parcsr_ls/HYPRE_parcsr_pcg.c:14-220)
+HYPRE_Int HYPRE_ParCSRPCGSetTol(HYPRE_Solver s, HYPRE_Real v) { return HYPRE_PCGSetTol(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetAbsoluteTol(HYPRE_Solver s, HYPRE_Real v) { return HYPRE_PCGSetAbsoluteTol(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetMaxIter(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_PCGSetMaxIter(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetTwoNorm(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_PCGSetTwoNorm(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetRelChange(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_PCGSetRelChange(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetPrintLevel(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_PCGSetPrintLevel(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetLogging(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_PCGSetLogging(s, v); }
+HYPRE_Int HYPRE_ParCSRPCGSetPrecond(HYPRE_Solver s, HYPRE_PtrToParSolverFcn precond, HYPRE_PtrToParSolverFcn precond_setup, HYPRE_Solver ps) {
+  return HYPRE_PCGSetPrecond(s, (HYPRE_PtrToSolverFcn)precond, (HYPRE_PtrToSolverFcn)precond_setup, ps);
+}
+HYPRE_Int HYPRE_ParCSRPCGGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { return HYPRE_PCGGetNumIterations(s, n); }
+HYPRE_Int HYPRE_ParCSRPCGGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { return HYPRE_PCGGetFinalRelativeResidualNorm(s, r); }
+
+HYPRE_Int HYPRE_ParCSRPCGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_pcg(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  NEED_HANDLE();
+  b200_timer_start(h);
+  if (s->precond_setup)                                         // hypre_PCGSetup, pcg.c:250
+    s->precond_setup(s->precond_solver, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+  double ms = 0;
+  b200_timer_stop_ms(h, &ms);
+  s->setup_s = ms * 1e-3;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRPCGSolve(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_pcg(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  if (!b || !b->d) return err_arg(3);
+  if (!x || !x->d) return err_arg(4);
+  NEED_HANDLE();
+  b200_pcg_params prm;
+  prm.tol = s->tol; prm.a_tol = s->a_tol; prm.max_iter = s->max_iter; prm.two_norm = s->two_norm;
+  prm.rel_change = s->rel_change; prm.recompute_residual = s->recompute_residual; prm.precond = 0;
+  b200_amg amg = nullptr;
+  if (s->precond == (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSolve) {
+    if (!is_amg(s->precond_solver)) return err_arg(1);
+    amg = s->precond_solver->amg;
+    // the preconditioner is ONE cycle: the reference driver sets MaxIter 1 / Tol 0 on it (ij.c:3930, :3909)
+    if (b200_amg_get_int(amg, "MaxIter") != 1 || s->precond_solver->stored["Tol"] != 0.0) {
+      fprintf(stderr, "hypre_b200: PCG: the BoomerAMG preconditioner must have MaxIter 1 and Tol 0\n");
+      return err(HYPRE_ERROR_GENERIC);
+    }
+    prm.precond = 1;
+  } else if (s->precond == (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScale) {
+    prm.precond = 2;
+  } else if (s->precond != nullptr) {
+    fprintf(stderr, "hypre_b200: PCG: only HYPRE_BoomerAMGSolve, HYPRE_ParCSRDiagScale or no preconditioner run on the B200 path\n");
+    return err(HYPRE_ERROR_GENERIC);
+  }
+  s->norms.assign((size_t)s->max_iter + 2, 0.0);
+  b200_timer_start(h);
+  const int rc = b200_pcg_solve_ex(h, A->A, amg, &prm, b->d, x->d, &s->num_iterations, &s->rel_res, s->norms.data());
+  double ms = 0;
+  b200_timer_stop_ms(h, &ms);
+  s->solve_s = ms * 1e-3;
+  if (rc) return err_b200("HYPRE_ParCSRPCGSolve");
+  if (s->print_level > 1) {                                    // residual table of pcg.c:472-491, :606-627
+    double b2 = 0;
+    b200_vec_dot(h, b->n, b->d, b->d, &b2);
+    const char *nm = s->two_norm ? "2" : "C";
+    printf("\n\nIters       ||r||_%s     conv.rate  ||r||_%s/||b||_%s\n", nm, nm, nm);
+    printf("-----    ------------   ---------  ------------ \n");
+    for (int i = 1; i <= s->num_iterations; i++)
+      printf("% 5d    %e    %f    %e\n", i, s->norms[i], s->norms[i] / s->norms[i - 1],
+             (s->two_norm && b2 > 0) ? s->norms[i] / std::sqrt(b2) : 0.0);
+    printf("\n\n");
+  }
+  const double eps = std::fmax(s->tol * s->tol, 0.0);
+  if (s->num_iterations >= s->max_iter && s->rel_res * s->rel_res >= eps && eps > 0) err(HYPRE_ERROR_CONV);   // pcg.c:741-745
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_PCGSetup(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRPCGSetup(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+HYPRE_Int HYPRE_PCGSolve(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRPCGSolve(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+HYPRE_Int HYPRE_b200_PCGGetTimes(HYPRE_Solver s, HYPRE_Real *setup_s, HYPRE_Real *solve_s) {
+  if (!is_pcg(s)) return err_arg(1);
+  if (setup_s) *setup_s = s->setup_s;
+  if (solve_s) *solve_s = s->solve_s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_PCGGetResidualNorms(HYPRE_Solver s, HYPRE_Int n, HYPRE_Real *norms) {
+  if (!is_pcg(s)) return err_arg(1);
+  for (int i = 0; i < n && i < (int)s->norms.size(); i++) norms[i] = s->norms[i];
+  return g_error_flag;
+}
+
+}  // extern "C"

@@ -112,6 +112,11 @@ int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr A);
 /* one application of the preconditioner: hypre_BoomerAMGSolve with MaxIter=1, Tol=0
  * (par_amg_solve.c:21) = one hypre_BoomerAMGCycle (par_cycle.c:22-641); u is overwritten */
 int b200_amg_solve(b200_handle h, b200_amg amg, const double *d_f, double *d_u);
+/* BoomerAMG as a solver: cycles until ||f - A u||_2 / ||f||_2 < "Tol" or "MaxIter" cycles
+ * (par_amg_solve.c:21-380, converge_type 0).  Returns 256 (HYPRE_ERROR_CONV) when MaxIter was reached
+ * with Tol > 0, as the reference flags it; u then holds the last iterate. */
+int b200_amg_solve_ex(b200_handle h, b200_amg amg, b200_parcsr A, const double *d_f, double *d_u,
+                      int *num_iterations, double *final_rel_res);
 int b200_amg_num_levels(b200_amg amg);
 /* hierarchy access for parity tests (device objects owned by amg) */
 b200_csr b200_amg_level_A(b200_amg amg, int level);
@@ -141,6 +146,16 @@ int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
  * receives ||r_k||_2 for k=0..iters (needs max_iter+1 doubles). */
 int b200_pcg_solve(b200_handle h, b200_parcsr A, b200_amg amg, const double *d_b, double *d_x,
                    double tol, int max_iter, int *iters, double *final_rel_res, double *h_norms);
+/* the same solver with the hypre_PCGData fields that matter on this path (krylov/pcg.h:190-230):
+ * two_norm 0 = energy norm <C r, r>; precond 0 none, 1 BoomerAMG (amg), 2 HYPRE_ParCSRDiagScale */
+typedef struct {
+  double tol, a_tol;
+  int max_iter, two_norm, rel_change, recompute_residual, precond;
+} b200_pcg_params;
+int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, const b200_pcg_params *params, const double *d_b,
+                      double *d_x, int *iters, double *final_rel_res, double *h_norms);
+/* x = y ./ diag(A)   HYPRE_ParCSRDiagScale (parcsr_ls/HYPRE_parcsr_pcg.c:228-258) */
+int b200_parcsr_diag_scale(b200_handle h, b200_parcsr A, const double *d_y, double *d_x);
 
 /* ---- multi-GPU: row-partitioned ParCSR over NVLink ---------------------------------
  * One process per GPU.  Rows are partitioned contiguously like hypre's ParCSR layout

@@ -97,6 +97,32 @@ def test_library_exports_every_declared_symbol():
     assert set(hb.SIGNATURES) <= declared
 
 
+def test_public_api_header_symbols_are_exported_and_client_links():
+    """include/HYPRE_b200.h (boundary B1): every declared HYPRE_* / Generate* function is exported by the
+    library, and the plain-C client examples/ij_b200.c compiles and links against it with gcc"""
+    import ctypes
+    import hypre_ve_b200 as hb
+    from hypre_ve_b200 import build as b
+    lib = ctypes.CDLL(hb.LIB_PATH)
+    hdr = open(os.path.join(ROOT, "include", "HYPRE_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b((?:HYPRE_|Generate)[A-Za-z0-9_]+)\s*\(", hdr)) - {"HYPRE_Int", "HYPRE_ParCSRMatrix"}
+    assert len(declared) > 150
+    for name in sorted(declared):
+        assert hasattr(lib, name), "symbol %s declared in HYPRE_b200.h but not exported" % name
+    exe = b.build_examples()
+    assert os.access(exe, os.X_OK)
+
+
+def test_public_api_fails_loudly_without_device():
+    import torch
+    from hypre_ve_b200 import build as b
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    p = subprocess.run([b.build_examples(), "-n", "4", "4", "4"], capture_output=True, text=True)
+    assert p.returncode != 0 and "no CPU fallback" in p.stderr
+
+
 def test_no_cpu_fallback_without_device():
     import hypre_ve_b200 as hb
     import torch
