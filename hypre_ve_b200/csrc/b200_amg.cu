@@ -37,6 +37,8 @@ struct b200_amg_s {
   double *ge_A = nullptr;         // dense coarsest matrix (row-major n x n) + work copy + rhs
   int ge_n = 0;
   bool coarse_ge = false;
+  bool gs = false;                // Gauss-Seidel family smoother (relax 3/4/6/8/13/14) instead of l1-Jacobi
+  int relax_down = 18, relax_up = 18;
   double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool is_setup = false;
   b200_amg_s() {
@@ -204,7 +206,16 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   auto &rp = amg->rp;
   if (ip["CoarsenType"] != 8) B200_FAIL("only CoarsenType 8 (PMIS) is implemented on the B200 path");
   if (ip["InterpType"] != 6) B200_FAIL("only InterpType 6 (extended+i) is implemented on the B200 path");
-  if (ip["RelaxType"] != 18) B200_FAIL("only RelaxType 18 (l1-Jacobi) is implemented on the B200 path");
+  // grid_relax_type[1] / [2] (par_amg.c:1650-1672); the coarsest grid is always Gaussian elimination (9)
+  const int rdown = ip["RelaxType"], rup = ip["RelaxTypeUp"] >= 0 ? ip["RelaxTypeUp"] : ip["RelaxType"];
+  auto is_gs = [](int t) { return t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14; };
+  auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
+  if (!((rdown == 18 && rup == 18) || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
+    B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), the l1 hybrid Gauss-Seidel family 8/13/14 and the "
+              "hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
+  if (rdown != 18 && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  amg->gs = rdown != 18;
+  amg->relax_down = rdown; amg->relax_up = rup;
   if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
   if (ip["AggNumLevels"] != 0) B200_FAIL("aggressive coarsening is not implemented on the B200 path");
   if (ip["NumSweeps"] != 1 || ip["CycleType"] != 1) B200_FAIL("only V(1,1) cycles are implemented");
@@ -294,13 +305,16 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     dense_from_csr_kernel<<<b200_grid(Lc.n, 128), 128, 0, h->stream>>>(Lc.n, Lc.A->i, Lc.A->j, Lc.A->a, amg->ge_A);
     B200_LAUNCH_CHECK();
   }
-  // l1 norms, option 1 for relax 18 (:3045-3060)
+  // l1 norms: option 1 for relax 18, option 4 for 8/13/14 (:3018-3060); Gauss-Seidel level schedules
   tm.start();
   for (int l = 0; l < nl; l++) {
     b200_level &L = amg->lv[l];
     if (l < nl - 1 || !amg->coarse_ge) {
-      B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
-      B200_TRY(b200_l1_norms(h, L.A, 1, L.l1));
+      if (!amg->gs || is_l1gs(rdown)) {
+        B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
+        B200_TRY(b200_l1_norms(h, L.A, amg->gs ? 4 : 1, L.l1));
+      }
+      if (amg->gs && !L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, &L.A->gs));
     }
     if (l > 0) {
       B200_TRY(b200_dalloc<double>(h, &L.F, L.n));
@@ -335,7 +349,50 @@ static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const
 // One V(1,1) cycle (par_cycle.c:255-622). u_zero: the caller guarantees u == 0 on entry
 // (PCG clears the vector before every preconditioner application, pcg.c:434,:568), which lets
 // the first sweep on every level skip its SpMV: u + (f - A*0)/l1 == f/l1 exactly.
+// one relaxation sweep of the Gauss-Seidel family, in place (par_relax.c cases 3/4/6/8/13/14, relax_points 0)
+static int gs_relax(b200_handle h, b200_level &L, int type, const double *f, double *u, bool zero) {
+  const bool classic = type == 3 || type == 4 || type == 6;
+  bool z = zero;
+  if (type == 3 || type == 13 || type == 6 || type == 8) {
+    B200_TRY(b200_gs_sweep(h, L.A->gs, L.A, +1, classic, z, f, L.l1, u));
+    z = false;
+  }
+  if (type == 4 || type == 14 || type == 6 || type == 8) B200_TRY(b200_gs_sweep(h, L.A->gs, L.A, -1, classic, z, f, L.l1, u));
+  return 0;
+}
+
+// V(1,1) cycle with in-place Gauss-Seidel smoothing (par_cycle.c:255-622)
+static int amg_cycle_gs(b200_handle h, b200_amg amg, const double *f, double *u, bool u_zero) {
+  const int nl = (int)amg->lv.size();
+  std::vector<const double *> F(nl);
+  std::vector<double *> U(nl);
+  F[0] = f; U[0] = u;
+  for (int l = 1; l < nl; l++) { F[l] = amg->lv[l].F; U[l] = amg->lv[l].U; }
+  for (int l = 0; l < nl - 1; l++) {
+    b200_level &L = amg->lv[l];
+    B200_TRY(gs_relax(h, L, amg->relax_down, F[l], U[l], l > 0 || u_zero));
+    B200_TRY(b200_csr_spmv_epi(h, L.A, U[l], amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));              // :549
+    B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, amg->lv[l + 1].F, 0, 1.0, 0.0, nullptr, nullptr)); // :566
+  }
+  {
+    b200_level &L = amg->lv[nl - 1];
+    if (amg->coarse_ge) {
+      gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, F[nl - 1], U[nl - 1]);
+      B200_LAUNCH_CHECK();
+    } else {
+      B200_TRY(gs_relax(h, L, amg->relax_down, F[nl - 1], U[nl - 1], nl > 1 || u_zero));
+    }
+  }
+  for (int l = nl - 2; l >= 0; l--) {
+    b200_level &L = amg->lv[l];
+    B200_TRY(b200_csr_spmv_epi(h, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));                 // :602
+    B200_TRY(gs_relax(h, L, amg->relax_up, F[l], U[l], false));
+  }
+  return 0;
+}
+
 static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bool u_zero) {
+  if (amg->gs) return amg_cycle_gs(h, amg, f, u, u_zero);
   const int nl = (int)amg->lv.size();
   const double w = amg->rp["RelaxWt"];
   // level 0 buffers: the final post-smoothing sweep must land in the caller's u

@@ -323,6 +323,7 @@ extern "C" int b200_csr_destroy(b200_handle h, b200_csr A) {
   B200_TRY(b200_dfree(h, A->blk_row));
   B200_TRY(b200_dfree(h, A->blk_ent));
   B200_TRY(b200_dfree(h, A->blk_meta));
+  B200_TRY(b200_gs_plan_destroy(h, A->gs));
   delete A;
   return 0;
 }

@@ -31,6 +31,7 @@ struct b200_handle_s {
 // Device CSR block.  Arrays are over-allocated by B200_PAD entries so kernels may issue aligned
 // 128-bit loads that straddle the logical end.
 #define B200_PAD 8
+struct b200_gs_plan_s;   // level schedule of the Gauss-Seidel sweeps (b200_gs.cu)
 struct b200_csr_s {
   int nrows = 0, ncols = 0, nnz = 0;
   int *i = nullptr;       // [nrows+1]
@@ -45,6 +46,7 @@ struct b200_csr_s {
   int  group = 1;         // threads cooperating on one row in the reduce phase
   int  max_row = 0;
   int  tile = 0;          // entries per tile the plan was cut with
+  b200_gs_plan_s *gs = nullptr;   // built on first use by b200_relax_gs / the AMG setup
 };
 
 struct b200_halo_s;   // multi-rank halo plan (b200_parcsr.cu)
@@ -103,4 +105,9 @@ static inline int b200_grid(size_t n, int block) { return (int)((n + block - 1) 
 int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data, b200_csr *A);
 int b200_csr_build_plan(b200_handle h, b200_csr A);
 int b200_exclusive_scan_inplace(b200_handle h, int *d_data, size_t n);   // d_data[n] entries, in place
+int b200_gs_plan_create(b200_handle h, b200_csr A, b200_gs_plan_s **out);
+int b200_gs_plan_destroy(b200_handle h, b200_gs_plan_s *p);
+int b200_gs_plan_levels(b200_gs_plan_s *p);
+int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool classic, bool zero, const double *f,
+                  const double *l1, double *u);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);

@@ -328,14 +328,19 @@ static csr_t multiply(const csr_t *A, const csr_t *B)
 }
 
 /* ---- l1 norms option 1: parcsr_ls/ams.c:648-657,:739-769 + csr_matop.c:1326-1352 ---- */
-static double *l1_norms(const csr_t *A)
+static double *l1_norms(const csr_t *A, int option)
 {
    double *l1 = (double *) xmalloc(sizeof(double) * A->n); int i, j;
    for (i = 0; i < A->n; i++)
    {
       double s = 0.0, d = 0.0;
-      for (j = A->i[i]; j < A->i[i + 1]; j++) s += 1.0 * fabs(A->a[j]);
       for (j = A->i[i]; j < A->i[i + 1]; j++) if (A->j[j] == i) { d = A->a[j]; break; }
+      if (option == 1) { for (j = A->i[i]; j < A->i[i + 1]; j++) s += 1.0 * fabs(A->a[j]); }
+      else
+      {  /* option 4 (ams.c:680-703): |a_ii| + 0.5 * l1(offd) (no offd block on one rank), then Remark 6.2 */
+         s = fabs(d);
+         if (s <= 4.0 / 3.0 * fabs(d)) s = fabs(d);
+      }
       l1[i] = d < 0.0 ? -s : s;
    }
    return l1;
@@ -369,6 +374,7 @@ typedef struct { int nl; csr_t A[MAXLEV], P[MAXLEV], R[MAXLEV], S[MAXLEV]; int *
                  double *F[MAXLEV], *U[MAXLEV], *V; double *ge; int ge_n; } amg_t;
 
 /* ---- setup loop: parcsr_ls/par_amg_setup.c:889-2890 for coarsen 8 / interp 6 / mod_rap2 1 ---- */
+static int g_relax_down = 18, g_relax_up = 18;   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
 static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
 {
    int l = 0, i;
@@ -394,7 +400,7 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    for (i = 0; i < g->nl; i++)
    {
       int n = g->A[i].n;
-      g->l1[i] = l1_norms(&g->A[i]);
+      g->l1[i] = l1_norms(&g->A[i], g_relax_down == 18 ? 1 : 4);      /* par_amg_setup.c:3018-3060 */
       g->F[i] = (double *) xcalloc(n, sizeof(double)); g->U[i] = (double *) xcalloc(n, sizeof(double));
    }
    g->V = (double *) xcalloc(g->A[0].n, sizeof(double));
@@ -406,12 +412,55 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    }
 }
 
-/* l1-Jacobi sweep: parcsr_ls/ams.c:72-92 (v=f; v=-A u + v; u += v/l1) */
-static void relax(amg_t *g, int l, const double *f, double *u)
+/* one row of the hybrid Gauss-Seidel family on one rank / one thread block (par_relax.c):
+ * l1 variants 8/13/14 (:3492-4091, :4340-5124): res = f_i - sum_j a_ij u_j over the WHOLE row in storage
+ * order, u_i += res / l1_i;  classic variants 3/4/6 (:1875-2265, original type 6 kept under `#if 0` at
+ * :2685-2753): the diagonal (stored first) is skipped and u_i = res / a_ii. */
+static void gs_row(const csr_t *A, const double *l1, const double *f, double *u, int i, int classic)
+{
+   int jj;
+   if (classic)
+   {
+      if (A->a[A->i[i]] != 0.0)
+      {
+         double res = f[i];
+         for (jj = A->i[i] + 1; jj < A->i[i + 1]; jj++) res -= A->a[jj] * u[A->j[jj]];
+         u[i] = res / A->a[A->i[i]];
+      }
+   }
+   else if (l1[i] != 0.0)
+   {
+      double res = f[i];
+      for (jj = A->i[i]; jj < A->i[i + 1]; jj++) res -= A->a[jj] * u[A->j[jj]];
+      u[i] += res / l1[i];
+   }
+}
+/* relaxation sweep of type `type`, relax_weight = omega = 1, relax_points = 0, one rank, one thread.
+ * 18: l1-Jacobi, parcsr_ls/ams.c:72-92 (v=f; v=-A u + v; u += v/l1) */
+static void relax(amg_t *g, int l, int type, const double *f, double *u)
 {
    int n = g->A[l].n, i; double *v = g->V;
-   matvec(-1.0, &g->A[l], u, 1.0, f, v);
-   for (i = 0; i < n; i++) u[i] += v[i] / g->l1[l][i];
+   const csr_t *A = &g->A[l]; const double *l1 = g->l1[l];
+   switch (type)
+   {
+      case 18:
+         matvec(-1.0, A, u, 1.0, f, v);
+         for (i = 0; i < n; i++) u[i] += v[i] / l1[i];
+         break;
+      case 13: for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 0); break;
+      case 14: for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 0); break;
+      case 8:
+         for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 0);
+         for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 0);
+         break;
+      case 3:  for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 1); break;
+      case 4:  for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 1); break;
+      case 6:
+         for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 1);
+         for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 1);
+         break;
+      default: fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2);
+   }
 }
 /* V(1,1): parcsr_ls/par_cycle.c:255-622 */
 static void cycle(amg_t *g, const double *f, double *u)
@@ -421,7 +470,7 @@ static void cycle(amg_t *g, const double *f, double *u)
    for (l = 0; l < nl - 1; l++)
    {
       F = l ? g->F[l] : f; U = l ? g->U[l] : u;
-      relax(g, l, F, U);
+      relax(g, l, g_relax_down, F, U);
       matvec(-1.0, &g->A[l], U, 1.0, F, g->V);
       matvec(1.0, &g->R[l], g->V, 0.0, g->V, g->F[l + 1]);
       for (i = 0; i < g->A[l + 1].n; i++) g->U[l + 1][i] = 0.0;
@@ -434,12 +483,12 @@ static void cycle(amg_t *g, const double *f, double *u)
       gselim(T, b, n);
       memcpy(U, b, sizeof(double) * n); free(T); free(b);
    }
-   else relax(g, nl - 1, F, U);
+   else relax(g, nl - 1, g_relax_down, F, U);
    for (l = nl - 2; l >= 0; l--)
    {
       F = l ? g->F[l] : f; U = l ? g->U[l] : u;
       matvec(1.0, &g->P[l], g->U[l + 1], 1.0, U, U);
-      relax(g, l, F, U);
+      relax(g, l, g_relax_up, F, U);
    }
 }
 
@@ -464,7 +513,7 @@ static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts
 
 int main(int argc, char **argv)
 {
-   int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0;
+   int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1;
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    const char *ofile = NULL;
    for (i = 1; i < argc; i++)
@@ -480,7 +529,8 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-matvec")) matvec_reps = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
       else if (!strcmp(argv[i], "-pmis") || !strcmp(argv[i], "-nodump")) { }
-      else if (!strcmp(argv[i], "-rlx") || !strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
+      else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
    double v[4];
@@ -498,6 +548,7 @@ int main(int argc, char **argv)
       printf("amg_oracle: matvec_ms=%.6f reps=%d\n", (now() - t0) / matvec_reps * 1e3, matvec_reps);
       return 0;
    }
+   if (rlx > -1) g_relax_down = g_relax_up = rlx; else { g_relax_down = 13; g_relax_up = 14; }
    amg_t g;
    double t0 = now();
    amg_setup(&g, A, th, mxrs, Pmx, 9);
@@ -540,13 +591,14 @@ int main(int argc, char **argv)
    if (ofile)
    {
       g_out = fopen(ofile, "wb");
-      int hdr[8] = { nx, ny, nz, g.nl, it, pt27, Pmx, 18 };
+      int hdr[8] = { nx, ny, nz, g.nl, it, pt27, Pmx, rlx };
       put("hdr", 0, hdr, 8); put("relres", 1, &relres, 1); put("norms", 1, norms, it + 1); put("x", 1, x, N);
       for (i = 0; i < g.nl; i++)
       {
          char nm[64];
          put_csr("A", i, &g.A[i], 1);
-         if (i < g.nl - 1 || !g.ge) { sprintf(nm, "l1_%d", i); put(nm, 1, g.l1[i], g.A[i].n); }   /* par_amg_setup.c:3045-3060 */
+         if ((i < g.nl - 1 || !g.ge) && (g_relax_down == 18 || g_relax_down == 8 || g_relax_down == 13 || g_relax_down == 14))
+         { sprintf(nm, "l1_%d", i); put(nm, 1, g.l1[i], g.A[i].n); }   /* par_amg_setup.c:3045-3060 */
          if (i < g.nl - 1)
          {
             sprintf(nm, "CF%d", i); put(nm, 0, g.cf[i], g.A[i].n);

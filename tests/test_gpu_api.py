@@ -68,6 +68,24 @@ def test_amg_pcg_through_the_public_api_matches_reference_driver(exe, flags, kno
             assert abs(rel / known[1] - 1) < 1e-6
 
 
+@pytest.mark.parametrize("flags,known", [
+    (["-n", "50", "50", "50", "-solver", "1", "-pmis", "-mod_rap2", "1"], 10),           # library default 13 down / 14 up
+    (["-n", "20", "18", "16", "-solver", "1", "-pmis", "-mod_rap2", "1", "-rlx", "8"], None),
+    (["-27pt", "-n", "16", "16", "16", "-solver", "1", "-pmis", "-mod_rap2", "1"], None),
+    (["-n", "14", "14", "14", "-solver", "0", "-pmis", "-mod_rap2", "1", "-rlx", "14"], None),
+])
+def test_hybrid_gauss_seidel_smoothers_through_the_public_api(exe, flags, known):
+    rc, out = run([exe, "-laplacian"] + flags)
+    assert rc == 0, out
+    key = "BoomerAMG Iterations" if "0" == flags[flags.index("-solver") + 1] else "Iterations"
+    its, rel = result(out, key)
+    if os.path.exists(REF_IJ):
+        rits, rrel = ref_result(flags, key)
+        assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)
+    if known:
+        assert its == known
+
+
 def test_ij_assembled_operator_equals_generated_operator(exe):
     """HYPRE_IJMatrixSetValues/Assemble (diagonal first, insertion order) gives the generator's matrix:
     identical iteration count and residual through the whole setup + solve."""

@@ -1,0 +1,180 @@
+"""GPU parity tests for the hybrid Gauss-Seidel relaxation family (hypre_BoomerAMGRelax types 3/4/6 and
+the l1 variants 8/13/14, par_relax.c) -- one Gauss-Seidel block per rank, i.e. the reference run with
+OMP_NUM_THREADS=1.
+
+Checkers: (1) a sequential numpy/Python restatement of one sweep on small matrices (bit-exact: the GPU
+sweep keeps the per-row entry order and uses no FMA); (2) the reference's own CPU build for whole
+BoomerAMG-PCG solves with types 4, 8, 13, 14 and the library default 13-down/14-up (types 3 and 6 do
+not compile off the vector engine in this fork, SURVEY.md 8c: they are checked against the restatement
+oracle, which is pinned on 4/8/13/14); (3) a size-independent identity of the sweep at 128^3."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import refio
+
+pytestmark = pytest.mark.gpu
+ORACLE = os.path.join(refio.ROOT, "oracle", "_build", "amg_oracle")
+
+
+def seq_sweep(ip, ix, a, f, d, u, order, classic):
+    """the reference loop: res = f_i - sum a_ij u_j in storage order; u_i += res/l1_i | u_i = res/a_ii"""
+    u = u.copy()
+    for i in order:
+        b, e = ip[i], ip[i + 1]
+        if classic:
+            if a[b] != 0.0:
+                res = f[i]
+                for jj in range(b + 1, e):
+                    res -= a[jj] * u[ix[jj]]
+                u[i] = res / a[b]
+        elif d[i] != 0.0:
+            res = f[i]
+            for jj in range(b, e):
+                res -= a[jj] * u[ix[jj]]
+            u[i] += res / d[i]
+    return u
+
+
+def diag_first(M):
+    """CSR arrays with the diagonal entry first in every row (the reference's diag-block layout)"""
+    M = M.tocsr(); M.sort_indices()
+    ip, ix, a = M.indptr.copy(), M.indices.copy(), M.data.copy()
+    for i in range(M.shape[0]):
+        b, e = ip[i], ip[i + 1]
+        k = b + int(np.where(ix[b:e] == i)[0][0])
+        ix[b + 1:k + 1], ix[b] = ix[b:k].copy(), i
+        a[b + 1:k + 1], a[b] = a[b:k].copy(), a[k]
+    return ip.astype(np.int32), ix.astype(np.int32), a
+
+
+def small_matrices():
+    rng = np.random.default_rng(11)
+    out = {}
+    # symmetric pattern, random values, strong diagonal
+    S = sp.random(700, 700, density=0.01, random_state=3, format="csr")
+    S = S + S.T + sp.eye(700) * 5.0
+    out["sym_random"] = diag_first(S)
+    # non-symmetric PATTERN: levels must come from the symmetrised graph
+    N = sp.random(500, 500, density=0.012, random_state=5, format="csr") + sp.eye(500) * 4.0
+    out["nonsym_random"] = diag_first(N)
+    # a chain (worst case: one row per level) and a block of isolated rows
+    C = sp.diags([-1.0, 2.5, -1.0], [-1, 0, 1], shape=(300, 300), format="csr")
+    out["chain"] = diag_first(sp.block_diag([C, sp.eye(40) * 3.0]).tocsr())
+    return out
+
+
+@pytest.mark.parametrize("relax_type", [13, 14, 8, 3, 4, 6])
+@pytest.mark.parametrize("name", ["sym_random", "nonsym_random", "chain", "lap7", "lap27", "coarse_level"])
+def test_single_sweep_is_the_sequential_loop_bit_for_bit(handle, name, relax_type):
+    import hypre_ve_b200 as hb
+    if name in ("lap7", "lap27"):
+        A0 = hb.ParCsr.laplacian(handle, 9, 7, 8) if name == "lap7" else hb.ParCsr.laplacian27(handle, 7, 6, 5)
+        ip, ix, a = A0.diag.download()
+        A0.destroy()
+    elif name == "coarse_level":
+        d, _ = refio.run_ref(["-n", 16, 16, 16, "-pmis", "-rlx", 18, "-mod_rap2", 1])
+        ip, ix, a, _ = refio.csr(d, "A", 1)
+    else:
+        ip, ix, a = small_matrices()[name]
+    n = len(ip) - 1
+    rng = np.random.default_rng(relax_type)
+    f, u0 = rng.standard_normal(n), rng.standard_normal(n)
+    A = hb.Csr.from_host(handle, ip, ix, a)
+    classic = relax_type in (3, 4, 6)
+    l1 = None if classic else handle.l1_norms(A, 4)
+    dl1 = None if classic else l1.numpy()
+    want = u0
+    if relax_type in (3, 13, 6, 8):
+        want = seq_sweep(ip, ix, a, f, dl1, want, range(n), classic)
+    if relax_type in (4, 14, 6, 8):
+        want = seq_sweep(ip, ix, a, f, dl1, want, range(n - 1, -1, -1), classic)
+    df, du = handle.array(f), handle.array(u0)
+    handle.relax_gs(A, relax_type, df, l1, du)
+    got = du.numpy()
+    assert np.array_equal(got, want), float(np.max(np.abs(got - want)))
+    A.destroy()
+
+
+def run_oracle(args):
+    subprocess.run(["make", "-s", "-C", os.path.join(refio.ROOT, "oracle")], check=True)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "o.bin")
+        subprocess.run([ORACLE] + [str(x) for x in args] + ["-o", path], check=True, capture_output=True)
+        return refio.read_dump(path)
+
+
+SOLVES = [
+    (["-n", 24, 20, 18], 13), (["-n", 24, 20, 18], 14), (["-n", 24, 20, 18], 8), (["-n", 24, 20, 18], 4),
+    (["-n", 24, 20, 18], -1), (["-n", 16, 16, 16, "-27pt"], -1), (["-n", 20, 20, 20, "-c", 1, 1, 0.001], -1),
+    (["-n", 40, 40, 40], -1),
+    (["-n", 24, 20, 18], 3), (["-n", 24, 20, 18], 6),
+]
+
+
+@pytest.mark.parametrize("args,rlx", SOLVES)
+def test_amg_pcg_with_gauss_seidel_smoothers(handle, args, rlx):
+    """hierarchy (bit-exact), iteration count (exact) and residual history (1e-10) of BoomerAMG-PCG"""
+    import hypre_ve_b200 as hb
+    flags = args + ["-pmis", "-mod_rap2", 1] + (["-rlx", rlx] if rlx > -1 else [])
+    if rlx in (3, 6) or not refio.have_ref():
+        d = run_oracle(flags)              # relax 3/6: VE-only code in this fork -> restatement oracle
+    else:
+        d, _ = refio.run_ref(flags)
+    nx, ny, nz = args[1:4]
+    A = hb.ParCsr.laplacian27(handle, nx, ny, nz) if "-27pt" in args else \
+        hb.ParCsr.laplacian(handle, nx, ny, nz, c=tuple(args[5:8]) if "-c" in args else (1.0, 1.0, 1.0))
+    amg = hb.Amg(handle)
+    if rlx > -1:
+        amg.set("RelaxType", rlx)
+    else:
+        amg.set("RelaxType", 13); amg.set("RelaxTypeUp", 14)      # library default (par_amg.c:206-209)
+    amg.setup(A)
+    nl = int(d["hdr"][3])
+    assert amg.num_levels == nl
+    for l in range(nl):
+        i, j, a = amg.level_A(l).download()
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), l
+        if l < nl - 1 and ("l1_%d" % l) in d:
+            assert np.array_equal(amg.level_l1(l), d["l1_%d" % l]), l           # option 4 norms
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4]), (its, int(d["hdr"][4]))
+    rn = d["norms"]
+    assert np.max(np.abs(norms - rn)) / rn[0] < 1e-10, np.max(np.abs(norms - rn)) / rn[0]
+    assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+    amg.destroy(); A.destroy()
+
+
+def test_forward_sweep_identity_at_128_cubed(handle):
+    """size-independent property: u' = u + (f - L u' - (D + U) u) / l1 row by row (vectorised check)"""
+    import hypre_ve_b200 as hb
+    nx = 128
+    A0 = hb.ParCsr.laplacian(handle, nx, nx, nx)
+    A = A0.diag
+    ip, ix, a = A.download()
+    n = len(ip) - 1
+    M = sp.csr_matrix((a, ix, ip), shape=(n, n))
+    rng = np.random.default_rng(2)
+    f, u0 = rng.standard_normal(n), rng.standard_normal(n)
+    l1 = handle.l1_norms(A, 4)
+    df, du = handle.array(f), handle.array(u0)
+    handle.relax_gs(A, 13, df, l1, du)
+    u1 = du.numpy()
+    L, DU = sp.tril(M, -1).tocsr(), sp.triu(M, 0).tocsr()
+    want = u0 + (f - L @ u1 - DU @ u0) / l1.numpy()
+    assert np.max(np.abs(u1 - want)) < 1e-12 * max(1.0, np.max(np.abs(want)))
+    # backward sweep on top of it
+    handle.relax_gs(A, 14, df, l1, du)
+    u2 = du.numpy()
+    Us, DL = sp.triu(M, 1).tocsr(), sp.tril(M, 0).tocsr()
+    want2 = u1 + (f - Us @ u2 - DL @ u1) / l1.numpy()
+    assert np.max(np.abs(u2 - want2)) < 1e-12 * max(1.0, np.max(np.abs(want2)))
+    A0.destroy()
