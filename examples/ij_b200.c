@@ -54,7 +54,7 @@ int main(int argc, char **argv) {
   /* driver defaults, test/ij.c:203-330 and :1181-1205 */
   int coarsen_type = 10, interp_type = 6, P_max_elmts = 4, relax_type = -1, relax_order = 0, max_levels = 25;
   int agg_num_levels = 0, rap2 = 0, mod_rap2 = 0, keepTranspose = 1, num_sweeps = 1, max_iter = 1000, mg_max_iter = 100;
-  int coarse_threshold = 9, min_coarse_size = 0, ioutdat = 3, poutdat = 1, two_norm = 1;
+  int coarse_threshold = 9, min_coarse_size = 0, ioutdat = 3, poutdat = 1, two_norm = 1, gs_blocks = 1;
   double strong_threshold = 0.25, max_row_sum = 1.0, trunc_factor = 0.0, tol = 1.e-8, pc_tol = 0., relax_wt = 1., outer_wt = 1.;
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-laplacian")) ;
@@ -83,6 +83,7 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[a], "-mg_max_iter") && a + 1 < argc) mg_max_iter = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-tol") && a + 1 < argc) tol = atof(argv[++a]);
     else if (!strcmp(argv[a], "-iout") && a + 1 < argc) ioutdat = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-gs_blocks") && a + 1 < argc) gs_blocks = atoi(argv[++a]);   /* = OMP_NUM_THREADS of the reference run */
     else { fprintf(stderr, "ij_b200: unknown option %s\n", argv[a]); return 2; }
   }
   if (HYPRE_Init()) { fprintf(stderr, "ij_b200: HYPRE_Init failed (no B200 / CUDA device?)\n"); return 1; }
@@ -162,6 +163,7 @@ int main(int argc, char **argv) {
     HYPRE_BoomerAMGSetRAP2(amg, rap2);
     HYPRE_BoomerAMGSetModuleRAP2(amg, mod_rap2);
     HYPRE_BoomerAMGSetKeepTranspose(amg, keepTranspose);
+    HYPRE_b200_BoomerAMGSetGSBlocks(amg, gs_blocks);
     if (solver_id == 0) {
       HYPRE_BoomerAMGSetTol(amg, tol);
       HYPRE_BoomerAMGSetMaxIter(amg, mg_max_iter);

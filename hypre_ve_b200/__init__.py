@@ -78,7 +78,8 @@ SIGNATURES = {
     "b200_pmis": (_i, [_vp, _vp, _i, _vp]),
     "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
     "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
-    "b200_relax_gs": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
+    "b200_l1_norms_blocks": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200_relax_gs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
     "b200_pcg_solve_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp]),
     "b200_parcsr_diag_scale": (_i, [_vp, _vp, _vp, _vp]),
@@ -416,15 +417,16 @@ class Handle:
         _chk(_lib.b200_extpi_interp(self.p, A.p, S.p, cf.ptr, trunc_factor, max_elmts, C.byref(p)))
         return Csr(self, p)
 
-    def l1_norms(self, A, option=1):
+    def l1_norms(self, A, option=1, blocks=1):
         n = A.dims[0]
         d = self.empty(n)
-        _chk(_lib.b200_l1_norms(self.p, A.p, option, d.ptr))
+        _chk(_lib.b200_l1_norms_blocks(self.p, A.p, option, blocks, d.ptr))
         return d
 
-    def relax_gs(self, A, relax_type, f, l1, u):
-        """hypre_BoomerAMGRelax for the Gauss-Seidel family (3/4/6 classic, 8/13/14 l1), in place on u"""
-        _chk(_lib.b200_relax_gs(self.p, A.p, relax_type, f.ptr, l1.ptr if l1 is not None else None, u.ptr))
+    def relax_gs(self, A, relax_type, f, l1, u, blocks=1):
+        """hypre_BoomerAMGRelax for the Gauss-Seidel family (3/4/6 classic, 8/13/14 l1), in place on u;
+        blocks = Gauss-Seidel blocks (the reference's OpenMP thread count)"""
+        _chk(_lib.b200_relax_gs(self.p, A.p, relax_type, blocks, f.ptr, l1.ptr if l1 is not None else None, u.ptr))
 
     def pcg(self, A, amg, b, x, tol=1e-8, max_iter=100):
         its = _i()

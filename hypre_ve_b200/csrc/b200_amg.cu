@@ -47,7 +47,7 @@ struct b200_amg_s {
     ip = {{"CoarsenType", 8}, {"InterpType", 6}, {"PMaxElmts", 4}, {"RelaxType", 18}, {"MaxLevels", 25},
           {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"NumSweeps", 1}, {"AggNumLevels", 0}, {"ModuleRAP2", 1},
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
-          {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
+          {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
           {"OuterWt", 1.0}, {"Tol", 0.0}};
   }
@@ -214,6 +214,7 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), the l1 hybrid Gauss-Seidel family 8/13/14 and the "
               "hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
   if (rdown != 18 && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  if (ip["GSBlocks"] < 1) B200_FAIL("GSBlocks must be >= 1");
   amg->gs = rdown != 18;
   amg->relax_down = rdown; amg->relax_up = rup;
   if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
@@ -312,9 +313,12 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     if (l < nl - 1 || !amg->coarse_ge) {
       if (!amg->gs || is_l1gs(rdown)) {
         B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
-        B200_TRY(b200_l1_norms(h, L.A, amg->gs ? 4 : 1, L.l1));
+        B200_TRY(b200_l1_norms_blocks(h, L.A, amg->gs ? 4 : 1, amg->gs ? ip["GSBlocks"] : 1, L.l1));
       }
-      if (amg->gs && !L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, &L.A->gs));
+      if (amg->gs) {
+        if (L.A->gs && b200_gs_plan_blocks(L.A->gs) != ip["GSBlocks"]) { B200_TRY(b200_gs_plan_destroy(h, L.A->gs)); L.A->gs = nullptr; }
+        if (!L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, ip["GSBlocks"], &L.A->gs));
+      }
     }
     if (l > 0) {
       B200_TRY(b200_dalloc<double>(h, &L.F, L.n));
@@ -349,16 +353,8 @@ static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const
 // One V(1,1) cycle (par_cycle.c:255-622). u_zero: the caller guarantees u == 0 on entry
 // (PCG clears the vector before every preconditioner application, pcg.c:434,:568), which lets
 // the first sweep on every level skip its SpMV: u + (f - A*0)/l1 == f/l1 exactly.
-// one relaxation sweep of the Gauss-Seidel family, in place (par_relax.c cases 3/4/6/8/13/14, relax_points 0)
 static int gs_relax(b200_handle h, b200_level &L, int type, const double *f, double *u, bool zero) {
-  const bool classic = type == 3 || type == 4 || type == 6;
-  bool z = zero;
-  if (type == 3 || type == 13 || type == 6 || type == 8) {
-    B200_TRY(b200_gs_sweep(h, L.A->gs, L.A, +1, classic, z, f, L.l1, u));
-    z = false;
-  }
-  if (type == 4 || type == 14 || type == 6 || type == 8) B200_TRY(b200_gs_sweep(h, L.A->gs, L.A, -1, classic, z, f, L.l1, u));
-  return 0;
+  return b200_gs_relax(h, L.A->gs, L.A, type, zero, f, L.l1, u);
 }
 
 // V(1,1) cycle with in-place Gauss-Seidel smoothing (par_cycle.c:255-622)

@@ -1,57 +1,80 @@
 // b200_gs.cu -- hybrid Gauss-Seidel relaxation (hypre_BoomerAMGRelax types 3/4/6 and the l1 variants
-// 8/13/14, parcsr_ls/par_relax.c:1875-2265, :3492-4091, :4340-5124) as an exact, level-scheduled sweep.
+// 8/13/14, parcsr_ls/par_relax.c:1875-2265, :3492-4091, :4340-5124) as exact, level-scheduled sweeps.
 //
-// Decomposition (what "hybrid" means, par_relax.c:4400-4412): Gauss-Seidel inside a block of rows,
-// Jacobi (old values) across blocks.  Here ONE block per rank (= the reference with OMP_NUM_THREADS=1,
-// one MPI rank per GPU): inside the rank the sweep is the reference's sequential loop, bit for bit --
-// row i reads the NEW value of every neighbour that precedes it in sweep order and the OLD value of the
-// others, and each row's sum runs over its entries in storage order in one thread.
+// "Hybrid" (par_relax.c:4400-4412): the rows of a rank are cut into T contiguous blocks
+// (size = n/T, the first n%T blocks one row longer); inside a block the sweep is sequential
+// Gauss-Seidel, across blocks (and across ranks) it reads the values from before the sweep.  In the
+// reference T is the OpenMP thread count; here it is the parameter "GSBlocks".  For a given T the
+// result is the reference's, bit for bit: a row reads the NEW value of every in-block neighbour that
+// precedes it in sweep order, the OLD value of everything else, and sums its entries in storage order
+// in one thread (no FMA).
 //
-// How a sequential sweep runs on 148 SMs:
-//   setup  -- level[i] = 1 + max(level[j] : j < i, a_ij != 0 or a_ji != 0), by frontier peeling
-//             (Kahn's algorithm, one small kernel per level; no full pass per level); rows sorted by
-//             (level, row) -> perm; levels are cut into chunks of <= 128 rows.  Levels built on the
-//             symmetrised pattern serve both directions: descending level order is a valid order for the
-//             backward sweep, and a row never reads a neighbour that could already have been rewritten.
-//   sweep  -- ONE kernel: CTAs draw chunk tickets in level order, prefetch their rows (indices, values,
-//             old neighbour values) and only then wait on the completion counter of the previous level
-//             (a soft barrier: ticket order makes it deadlock free without a cooperative launch); new
-//             values are read with ld.global.cg (L2) after the acquire.
-// The sweep is bound by the dependency chain (#levels x one L2 round trip), not by HBM: the 7-pt 256^3
-// grid in lexicographic order has 766 levels.  DESIGN.md section 3 gives the model and measurements.
+// Scheduling.  level[i] = 1 + max(level[j] : j in the block of i, j < i, a_ij != 0 or a_ji != 0),
+// found by frontier peeling (Kahn's algorithm, one small kernel per level).  Levels built on the
+// symmetrised pattern serve both directions: descending level order is valid for the backward sweep.
+//   * block path (blocks of <= 16384 rows): ONE CTA PER GAUSS-SEIDEL BLOCK.  The block's iterate lives in
+//     shared memory, its levels are separated by __syncthreads(), everything outside the block is read
+//     from the pre-sweep copy: no inter-CTA synchronisation at all.  Rows are visited in
+//     (block, level, row) order; the next level's row is prefetched into registers before the barrier.
+//   * global path (any block size, T = 1 included): CTAs draw chunk tickets in level order, prefetch
+//     their rows and then wait on the completion counter of the previous level (a soft barrier that is
+//     deadlock free without a cooperative launch because tickets are handed out in dependency order);
+//     new values are read with ld.global.cg after the acquire.  This path is bound by
+//     (#levels x one L2 round trip): 766 levels for the 7-pt 256^3 grid, thousands on coarse grids.
 #include "b200_internal.h"
 #include <algorithm>
 
 struct b200_gs_plan_s {
-  int n = 0, nlevels = 0, nchunks = 0;
-  int *perm = nullptr;        // [n] rows sorted by (level, row)
-  int *level_off = nullptr;   // [nlevels+1] first position of each level in perm
+  int n = 0, T = 1, size = 0, rest = 0;
+  int nlevels = 0;            // depth of the deepest block
+  bool block_path = false;
+  bool lane_path = false;     // one thread per Gauss-Seidel block: no schedule needed
+  int maxblock = 0;
+  int *perm = nullptr;        // rows sorted by (level,row) [global path] or (block,level,row) [block path]
+  // global path
+  int nchunks = 0;
+  int *level_off = nullptr;   // [nlevels+1]
   int *chunks = nullptr;      // int4 per chunk {pos0, pos1, level, 0}
   int *ctr = nullptr;         // [1 + nlevels] ticket counter, rows finished per level
+  // block path
+  int nseg = 0;
+  int *seg_off = nullptr;     // [nseg+1] first position of every non-empty (block, level) segment
+  int *blk_seg = nullptr;     // [T+1] first segment of every block
+  double *old = nullptr;      // [n] iterate before the sweep (T > 1)
 };
 
 namespace {
 
-constexpr int GS_NT = 128;     // threads per CTA = rows per chunk
-constexpr int GS_PRE = 8;      // row entries prefetched into registers before the wait
+constexpr int GS_NT = 128;     // global path: threads per CTA = rows per chunk
+constexpr int GS_PRE = 8;      // row entries prefetched into registers
+constexpr int GS_BLOCK_CAP = 16384;   // rows of one Gauss-Seidel block that fit the shared-memory iterate (128 KB)
+constexpr int GS_LANE_CAP = 2048;     // blocks up to this many rows are swept by ONE THREAD each
 
-// indeg[i] = number of sweep-order predecessors of row i on the symmetrised pattern; rows with none
-// open level 0.  T_i/T_j = pattern of A^T when A's pattern is not symmetric (else null).
-__global__ void gs_indeg_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const int *__restrict__ T_i,
-                                const int *__restrict__ T_j, int *__restrict__ indeg, int *__restrict__ level,
-                                int *__restrict__ frontier, int *__restrict__ cnt) {
+// block of row i: [ns, ne)   (par_relax.c:4400-4412)
+__device__ __forceinline__ void blk_range(int i, int size, int rest, int &ns, int &ne, int &b) {
+  const int split = rest * (size + 1);
+  if (i < split) { b = i / (size + 1); ns = b * (size + 1); ne = ns + size + 1; }
+  else { b = rest + (i - split) / size; ns = b * size + rest; ne = ns + size; }
+}
+
+__global__ void gs_indeg_kernel(int n, int size, int rest, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                const int *__restrict__ T_i, const int *__restrict__ T_j, int *__restrict__ indeg,
+                                int *__restrict__ level, int *__restrict__ frontier, int *__restrict__ cnt) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  int ns, ne, b;
+  blk_range(i, size, rest, ns, ne, b);
   int d = 0;
-  for (int jj = A_i[i]; jj < A_i[i + 1]; jj++) d += (A_j[jj] < i);
-  if (T_i) for (int jj = T_i[i]; jj < T_i[i + 1]; jj++) d += (T_j[jj] < i);
+  for (int jj = A_i[i]; jj < A_i[i + 1]; jj++) { const int j = A_j[jj]; d += (j < i && j >= ns); }
+  if (T_i) for (int jj = T_i[i]; jj < T_i[i + 1]; jj++) { const int j = T_j[jj]; d += (j < i && j >= ns); }
   indeg[i] = d;
   if (d == 0) { level[i] = 0; frontier[atomicAdd(cnt, 1)] = i; }
 }
-// one peeling round: rows of level r release their successors; cnt is a ring of three counters
-__global__ void gs_peel_kernel(int n, int r, const int *__restrict__ A_i, const int *__restrict__ A_j, const int *__restrict__ T_i,
-                               const int *__restrict__ T_j, int *__restrict__ indeg, int *__restrict__ level,
-                               const int *__restrict__ fin, int *__restrict__ fout, int *__restrict__ cnt, int *__restrict__ nlevels) {
+// one peeling round: rows of level r release their in-block successors; cnt is a ring of three counters
+__global__ void gs_peel_kernel(int n, int size, int rest, int r, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                               const int *__restrict__ T_i, const int *__restrict__ T_j, int *__restrict__ indeg,
+                               int *__restrict__ level, const int *__restrict__ fin, int *__restrict__ fout,
+                               int *__restrict__ cnt, int *__restrict__ nlevels) {
   const int nin = cnt[r % 3];
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     cnt[(r + 2) % 3] = 0;                               // becomes the output counter of the next round
@@ -59,14 +82,16 @@ __global__ void gs_peel_kernel(int n, int r, const int *__restrict__ A_i, const 
   }
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nin; idx += gridDim.x * blockDim.x) {
     const int i = fin[idx];
+    int ns, ne, b;
+    blk_range(i, size, rest, ns, ne, b);
     for (int jj = A_i[i]; jj < A_i[i + 1]; jj++) {
       const int j = A_j[jj];
-      if (j > i && j < n && atomicSub(&indeg[j], 1) == 1) { level[j] = r + 1; fout[atomicAdd(&cnt[(r + 1) % 3], 1)] = j; }
+      if (j > i && j < ne && atomicSub(&indeg[j], 1) == 1) { level[j] = r + 1; fout[atomicAdd(&cnt[(r + 1) % 3], 1)] = j; }
     }
     if (T_i)
       for (int jj = T_i[i]; jj < T_i[i + 1]; jj++) {
         const int j = T_j[jj];
-        if (j > i && j < n && atomicSub(&indeg[j], 1) == 1) { level[j] = r + 1; fout[atomicAdd(&cnt[(r + 1) % 3], 1)] = j; }
+        if (j > i && j < ne && atomicSub(&indeg[j], 1) == 1) { level[j] = r + 1; fout[atomicAdd(&cnt[(r + 1) % 3], 1)] = j; }
       }
   }
 }
@@ -87,6 +112,26 @@ __global__ void gs_unit_rows_kernel(int n, int *__restrict__ L_i) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i <= n) L_i[i] = i;
 }
+__global__ void gs_block_key_kernel(int n, int size, int rest, int D, int *__restrict__ level) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int ns, ne, b;
+  blk_range(i, size, rest, ns, ne, b);
+  level[i] = b * D + level[i];
+}
+__global__ void gs_seg_flag_kernel(int K, const int *__restrict__ key_off, int *__restrict__ flag) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > K) return;
+  flag[k] = (k < K && key_off[k + 1] > key_off[k]) ? 1 : 0;
+}
+__global__ void gs_seg_scatter_kernel(int K, int T, int D, const int *__restrict__ key_off, const int *__restrict__ pos,
+                                      int *__restrict__ seg_off, int *__restrict__ blk_seg) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > K) return;
+  if (k == K) { seg_off[pos[K]] = key_off[K]; blk_seg[T] = pos[K]; return; }
+  if (key_off[k + 1] > key_off[k]) seg_off[pos[k]] = key_off[k];
+  if (k % D == 0) blk_seg[k / D] = pos[k];
+}
 
 __device__ __forceinline__ int ld_volatile(const int *p) {
   int v;
@@ -94,15 +139,16 @@ __device__ __forceinline__ int ld_volatile(const int *p) {
   return v;
 }
 
-// One sweep.  DIR = +1 forward (types 3, 13), -1 backward (4, 14).  CLASSIC: u_i = res / a_ii with the
-// diagonal (stored first) skipped, else u_i += res / l1_i over the whole row.  ZERO: the iterate is
-// known to be 0 on entry (first sweep of a level in a cycle): old values are not read.
+// ---- global path ---------------------------------------------------------------------------------------
+// DIR +1 forward (types 3, 13) / -1 backward (4, 14).  CLASSIC: u_i = res / a_ii, diagonal (stored first)
+// skipped; else u_i += res / l1_i over the whole row.  ZERO: the iterate is 0 on entry.  `old` = pre-sweep
+// copy for out-of-block reads (T > 1), null when T == 1 (then every non-dependency is still unwritten in u).
 template <int DIR, bool CLASSIC, bool ZERO>
 __global__ void __launch_bounds__(GS_NT)
-gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks, const int *__restrict__ level_off,
-                const int *__restrict__ perm, const int *__restrict__ A_i, const int *__restrict__ A_j,
-                const double *__restrict__ A_a, const double *__restrict__ f, const double *__restrict__ l1,
-                double *u, int *ctr) {
+gs_sweep_kernel(int n, int size, int rest, int nchunks, int nlevels, const int4 *__restrict__ chunks,
+                const int *__restrict__ level_off, const int *__restrict__ perm, const int *__restrict__ A_i,
+                const int *__restrict__ A_j, const double *__restrict__ A_a, const double *__restrict__ f,
+                const double *__restrict__ l1, const double *__restrict__ old, double *u, int *ctr) {
   __shared__ int s_ticket;
   int *ticket = ctr, *done = ctr + 1;
   while (true) {
@@ -115,12 +161,13 @@ gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks
     const int p = c.x + (int)threadIdx.x;
     const bool active = p < c.y;
     // ---- prefetch everything that does not depend on the previous level ----------------------------
-    int i = 0, b = 0, e = 0;
+    int i = 0, b = 0, e = 0, ns = 0, ne = 0, bk = 0;
     double fi = 0.0, di = 0.0, ui = 0.0;
     int pj[GS_PRE];
     double pa[GS_PRE], pu[GS_PRE];
     if (active) {
       i = perm[p];
+      blk_range(i, size, rest, ns, ne, bk);
       b = A_i[i]; e = A_i[i + 1];
       fi = f[i];
       di = CLASSIC ? A_a[b] : l1[i];
@@ -131,8 +178,8 @@ gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks
         if (b + k < e) {
           const int j = A_j[b + k];
           pj[k] = j; pa[k] = A_a[b + k];
-          const bool dep = (DIR > 0) ? (j < i) : (j > i && j < n);
-          if (!dep && !ZERO) pu[k] = __ldcg(u + j);      // old value: cannot be rewritten before this row is done
+          const bool dep = (DIR > 0) ? (j < i && j >= ns) : (j > i && j < ne);
+          if (!dep && !ZERO) pu[k] = (old && j < n && (j < ns || j >= ne)) ? old[j] : __ldcg(u + j);
         }
       }
     }
@@ -140,8 +187,8 @@ gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks
     const int wl = c.z - DIR;
     if (threadIdx.x == 0 && wl >= 0 && wl < nlevels) {
       const int target = level_off[wl + 1] - level_off[wl];
-      unsigned ns = 20;
-      while (ld_volatile(done + wl) < target) { __nanosleep(ns); if (ns < 400) ns += ns; }
+      unsigned nsleep = 20;
+      while (ld_volatile(done + wl) < target) { __nanosleep(nsleep); if (nsleep < 400) nsleep += nsleep; }
       __threadfence();
     }
     __syncthreads();
@@ -152,15 +199,17 @@ gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks
       for (int k = 0; k < GS_PRE; k++) {
         if (b + k < e && !(CLASSIC && k == 0)) {
           const int j = pj[k];
-          const bool dep = (DIR > 0) ? (j < i) : (j > i && j < n);
+          const bool dep = (DIR > 0) ? (j < i && j >= ns) : (j > i && j < ne);
           const double uj = dep ? __ldcg(u + j) : pu[k];
           res -= pa[k] * uj;
         }
       }
       for (int jj = b + GS_PRE; jj < e; jj++) {
         const int j = A_j[jj];
-        const bool dep = (DIR > 0) ? (j < i) : (j > i && j < n);
-        const double uj = (dep || !ZERO) ? __ldcg(u + j) : 0.0;
+        const bool dep = (DIR > 0) ? (j < i && j >= ns) : (j > i && j < ne);
+        double uj = 0.0;
+        if (dep) uj = __ldcg(u + j);
+        else if (!ZERO) uj = (old && j < n && (j < ns || j >= ne)) ? old[j] : __ldcg(u + j);
         res -= A_a[jj] * uj;
       }
       u[i] = CLASSIC ? res / di : ui + res / di;
@@ -172,23 +221,170 @@ gs_sweep_kernel(int n, int nchunks, int nlevels, const int4 *__restrict__ chunks
   }
 }
 
+// ---- block path: one CTA per Gauss-Seidel block, iterate in shared memory ----------------------------------
+struct RowRegs {
+  int i, b, e;
+  double fi, di;
+  int pj[GS_PRE];
+  double pa[GS_PRE];
+};
+template <bool CLASSIC>
+__device__ __forceinline__ void gs_load_row(RowRegs &r, int p, const int *__restrict__ perm, const int *__restrict__ A_i,
+                                            const int *__restrict__ A_j, const double *__restrict__ A_a,
+                                            const double *__restrict__ f, const double *__restrict__ l1) {
+  r.i = perm[p];
+  r.b = A_i[r.i]; r.e = A_i[r.i + 1];
+  r.fi = f[r.i];
+  r.di = CLASSIC ? A_a[r.b] : l1[r.i];
+#pragma unroll
+  for (int k = 0; k < GS_PRE; k++) {
+    r.pj[k] = 0; r.pa[k] = 0.0;
+    if (r.b + k < r.e) { r.pj[k] = A_j[r.b + k]; r.pa[k] = A_a[r.b + k]; }
+  }
+}
+template <bool CLASSIC, bool ZERO>
+__device__ __forceinline__ void gs_do_row(const RowRegs &r, int n, int ns, int ne, double *u_s, const double *__restrict__ old,
+                                          const int *__restrict__ A_j, const double *__restrict__ A_a) {
+  if (r.di == 0.0) return;                                 // u_s already holds the old value (0 when ZERO)
+  double res = r.fi;
+#pragma unroll
+  for (int k = 0; k < GS_PRE; k++) {
+    if (r.b + k < r.e && !(CLASSIC && k == 0)) {
+      const int j = r.pj[k];
+      double uj;
+      if (j >= ns && j < ne) uj = u_s[j - ns];
+      else uj = (ZERO && j < n) ? 0.0 : old[j];
+      res -= r.pa[k] * uj;
+    }
+  }
+  for (int jj = r.b + GS_PRE; jj < r.e; jj++) {
+    const int j = A_j[jj];
+    double uj;
+    if (j >= ns && j < ne) uj = u_s[j - ns];
+    else uj = (ZERO && j < n) ? 0.0 : old[j];
+    res -= A_a[jj] * uj;
+  }
+  u_s[r.i - ns] = CLASSIC ? res / r.di : u_s[r.i - ns] + res / r.di;
+}
+// `old`: the iterate before the relaxation call, read for everything outside the block (for T == 1 that is
+// only ghost columns >= n and old == u); `u`: iterate, updated in place block by block.
+template <int DIR, bool CLASSIC, bool ZERO>
+__global__ void gs_block_kernel(int n, int T, int size, int rest, const int *__restrict__ blk_seg, const int *__restrict__ seg_off,
+                                const int *__restrict__ perm, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                const double *__restrict__ A_a, const double *__restrict__ f, const double *__restrict__ l1,
+                                const double *old, double *u) {
+  extern __shared__ double u_s[];
+  const int tid = threadIdx.x, NT = blockDim.x;
+  for (int bk = blockIdx.x; bk < T; bk += gridDim.x) {
+    const int ns = bk < rest ? bk * (size + 1) : bk * size + rest;
+    const int ne = ns + size + (bk < rest ? 1 : 0);
+    const int m = ne - ns;
+    if (m == 0) continue;
+    for (int k = tid; k < m; k += NT) u_s[k] = ZERO ? 0.0 : u[ns + k];   // current iterate (second half of 6/8: post-forward)
+    const int s0 = blk_seg[bk], s1 = blk_seg[bk + 1];
+    int seg = DIR > 0 ? s0 : s1 - 1;
+    RowRegs nxt;
+    nxt.i = 0; nxt.b = 0; nxt.e = 0; nxt.fi = 0.0; nxt.di = 0.0;
+    int o0 = seg_off[seg], o1 = seg_off[seg + 1];
+    if (o0 + tid < o1) gs_load_row<CLASSIC>(nxt, o0 + tid, perm, A_i, A_j, A_a, f, l1);
+    __syncthreads();
+    for (int cnt = s1 - s0; cnt > 0; cnt--) {
+      const RowRegs cur = nxt;
+      const int c0 = o0, c1 = o1;
+      if (cnt > 1) {                                       // prefetch this thread's row of the next level
+        seg += DIR;
+        o0 = seg_off[seg]; o1 = seg_off[seg + 1];
+        if (o0 + tid < o1) gs_load_row<CLASSIC>(nxt, o0 + tid, perm, A_i, A_j, A_a, f, l1);
+      }
+      if (c0 + tid < c1) gs_do_row<CLASSIC, ZERO>(cur, n, ns, ne, u_s, old, A_j, A_a);
+      for (int p = c0 + tid + NT; p < c1; p += NT) {       // levels wider than the CTA
+        RowRegs r;
+        gs_load_row<CLASSIC>(r, p, perm, A_i, A_j, A_a, f, l1);
+        gs_do_row<CLASSIC, ZERO>(r, n, ns, ne, u_s, old, A_j, A_a);
+      }
+      __syncthreads();
+    }
+    for (int k = tid; k < m; k += NT) u[ns + k] = u_s[k];
+    __syncthreads();
+  }
+}
+
+// ---- lane path: one THREAD per Gauss-Seidel block ------------------------------------------------------------
+// With many small blocks the reference's own parallelisation maps one to one: thread b walks the rows of
+// block b in sweep order, reads its own earlier results back from u (program order makes them visible to
+// itself) and everything outside the block from the pre-sweep copy.  No schedule, no barriers; the
+// dependency chain of a block is hidden by the other blocks resident on the SM.
+template <int DIR, bool CLASSIC, bool ZERO>
+__global__ void gs_lane_kernel(int n, int T, int size, int rest, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                               const double *__restrict__ A_a, const double *__restrict__ f, const double *__restrict__ l1,
+                               const double *old, double *u) {
+  const int bk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bk >= T) return;
+  const int ns = bk < rest ? bk * (size + 1) : bk * size + rest;
+  const int ne = ns + size + (bk < rest ? 1 : 0);
+  for (int i = (DIR > 0 ? ns : ne - 1); DIR > 0 ? i < ne : i >= ns; i += DIR) {
+    const int b = A_i[i], e = A_i[i + 1];
+    const double di = CLASSIC ? A_a[b] : l1[i];
+    if (di == 0.0) { if (ZERO) u[i] = 0.0; continue; }
+    double res = f[i];
+    for (int jj = b + (CLASSIC ? 1 : 0); jj < e; jj++) {
+      const int j = A_j[jj];
+      double uj;
+      if (j >= ns && j < ne) {
+        const bool swept = (DIR > 0) ? (j < i) : (j > i);
+        uj = (ZERO && !swept) ? 0.0 : u[j];
+      } else {
+        uj = (ZERO && j < n) ? 0.0 : old[j];
+      }
+      res -= A_a[jj] * uj;
+    }
+    u[i] = CLASSIC ? res / di : (ZERO ? 0.0 : u[i]) + res / di;
+  }
+}
+
 }  // namespace
 
 int b200_gs_plan_destroy(b200_handle h, b200_gs_plan_s *p) {
   if (!p) return 0;
   B200_TRY(b200_dfree(h, p->perm)); B200_TRY(b200_dfree(h, p->level_off));
   B200_TRY(b200_dfree(h, p->chunks)); B200_TRY(b200_dfree(h, p->ctr));
+  B200_TRY(b200_dfree(h, p->seg_off)); B200_TRY(b200_dfree(h, p->blk_seg)); B200_TRY(b200_dfree(h, p->old));
   delete p;
   return 0;
 }
 
-// Level schedule of the n x n leading block of A (columns >= n are ghosts: always old values).
-int b200_gs_plan_create(b200_handle h, b200_csr A, b200_gs_plan_s **out) {
+// sort rows by key (stable in the row index): transpose of the n x nkeys pattern with one entry (i, key[i]) per row
+static int sort_rows_by_key(b200_handle h, int n, int nkeys, int *key, int **perm, int **key_off) {
+  b200_csr_s L;
+  L.nrows = n; L.ncols = nkeys; L.nnz = n; L.owns = false;
+  B200_TRY(b200_dalloc<int>(h, &L.i, (size_t)n + 1));
+  gs_unit_rows_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, L.i);
+  B200_LAUNCH_CHECK();
+  L.j = key;
+  b200_csr Lt = nullptr;
+  B200_TRY(b200_csr_transpose(h, &L, &Lt));
+  B200_TRY(b200_dfree(h, L.i));
+  *perm = Lt->j; *key_off = Lt->i;                         // take ownership of the two arrays
+  Lt->owns = false;
+  B200_TRY(b200_csr_destroy(h, Lt));
+  return 0;
+}
+
+// Level schedule of the n x n leading block of A (columns >= n are ghosts: always old values), T blocks.
+int b200_gs_plan_create(b200_handle h, b200_csr A, int T, b200_gs_plan_s **out) {
   const int n = A->nrows;
+  if (T < 1) B200_FAIL("gs plan: GSBlocks must be >= 1");
   b200_gs_plan_s *P = new b200_gs_plan_s();
-  P->n = n;
+  P->n = n; P->T = T; P->size = n / T; P->rest = n - P->size * T;
+  P->maxblock = P->size + (P->rest ? 1 : 0);
   *out = P;
   if (n == 0) return 0;
+  const char *fg = getenv("B200_GS_FORCE_GLOBAL");      // tests: "1" soft-barrier path, "2" CTA-per-block path
+  if (P->maxblock <= GS_LANE_CAP && !(fg && (fg[0] == '1' || fg[0] == '2'))) {
+    P->lane_path = true;
+    if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, n));
+    return 0;
+  }
   int *d_flag = nullptr, *indeg = nullptr, *level = nullptr, *fr[2] = {nullptr, nullptr}, *cnt = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
   B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
@@ -197,13 +393,13 @@ int b200_gs_plan_create(b200_handle h, b200_csr A, b200_gs_plan_s **out) {
   int nonsym = 0;
   B200_CUDA(cudaMemcpyAsync(&nonsym, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
-  b200_csr T = nullptr;
+  b200_csr Tp = nullptr;
   if (nonsym) {                                          // successors also come from the transposed pattern
     b200_csr_s pat = *A;
-    pat.a = nullptr; pat.owns = false; pat.blk_row = pat.blk_ent = pat.blk_meta = nullptr;
-    B200_TRY(b200_csr_transpose(h, &pat, &T));
+    pat.a = nullptr; pat.owns = false; pat.blk_row = pat.blk_ent = pat.blk_meta = nullptr; pat.gs = nullptr;
+    B200_TRY(b200_csr_transpose(h, &pat, &Tp));
   }
-  const int *T_i = T ? T->i : nullptr, *T_j = T ? T->j : nullptr;
+  const int *T_i = Tp ? Tp->i : nullptr, *T_j = Tp ? Tp->j : nullptr;
   B200_TRY(b200_dalloc<int>(h, &indeg, n));
   B200_TRY(b200_dalloc<int>(h, &level, n));
   B200_TRY(b200_dalloc<int>(h, &fr[0], n));
@@ -212,66 +408,129 @@ int b200_gs_plan_create(b200_handle h, b200_csr A, b200_gs_plan_s **out) {
   const int big = 0x7fffffff;
   B200_CUDA(cudaMemsetAsync(cnt, 0, 3 * sizeof(int), h->stream));
   B200_CUDA(cudaMemcpyAsync(cnt + 3, &big, sizeof(int), cudaMemcpyHostToDevice, h->stream));
-  gs_indeg_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, A->i, A->j, T_i, T_j, indeg, level, fr[0], cnt);
+  gs_indeg_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, P->size, P->rest, A->i, A->j, T_i, T_j, indeg, level, fr[0], cnt);
   B200_LAUNCH_CHECK();
   const int grid = std::min(b200_grid(n, 256), h->num_sm * 4);
   int nlevels = big, r = 0;
   while (nlevels == big) {
     for (int k = 0; k < 128; k++, r++) {
-      gs_peel_kernel<<<grid, 256, 0, h->stream>>>(n, r, A->i, A->j, T_i, T_j, indeg, level, fr[r & 1], fr[(r + 1) & 1], cnt, cnt + 3);
+      gs_peel_kernel<<<grid, 256, 0, h->stream>>>(n, P->size, P->rest, r, A->i, A->j, T_i, T_j, indeg, level, fr[r & 1],
+                                                  fr[(r + 1) & 1], cnt, cnt + 3);
       B200_LAUNCH_CHECK();
     }
     B200_CUDA(cudaMemcpyAsync(&nlevels, cnt + 3, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
   }
   P->nlevels = nlevels;
-  // rows sorted by (level, row): transpose of the n x nlevels pattern with one entry (i, level[i]) per row
-  {
-    b200_csr_s L;
-    L.nrows = n; L.ncols = nlevels; L.nnz = n; L.owns = false;
-    B200_TRY(b200_dalloc<int>(h, &L.i, (size_t)n + 1));
-    gs_unit_rows_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, L.i);
+  const int D = nlevels;
+  P->block_path = P->maxblock <= GS_BLOCK_CAP && (long long)T * D <= (1LL << 26) && !(fg && fg[0] == '1');
+  if (P->block_path) {
+    const int K = T * D;
+    gs_block_key_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, P->size, P->rest, D, level);
     B200_LAUNCH_CHECK();
-    L.j = level;
-    b200_csr Lt = nullptr;
-    B200_TRY(b200_csr_transpose(h, &L, &Lt));
-    B200_TRY(b200_dfree(h, L.i));
-    P->perm = Lt->j; P->level_off = Lt->i;               // take ownership of the two arrays
-    Lt->owns = false;
-    B200_TRY(b200_csr_destroy(h, Lt));
+    int *key_off = nullptr, *pos = nullptr;
+    B200_TRY(sort_rows_by_key(h, n, K, level, &P->perm, &key_off));
+    B200_TRY(b200_dalloc<int>(h, &pos, (size_t)K + 1));
+    gs_seg_flag_kernel<<<b200_grid((size_t)K + 1, 256), 256, 0, h->stream>>>(K, key_off, pos);
+    B200_LAUNCH_CHECK();
+    B200_TRY(b200_exclusive_scan_inplace(h, pos, (size_t)K + 1));
+    B200_CUDA(cudaMemcpyAsync(&P->nseg, pos + K, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dalloc<int>(h, &P->seg_off, (size_t)P->nseg + 1));
+    B200_TRY(b200_dalloc<int>(h, &P->blk_seg, (size_t)T + 1));
+    gs_seg_scatter_kernel<<<b200_grid((size_t)K + 1, 256), 256, 0, h->stream>>>(K, T, D, key_off, pos, P->seg_off, P->blk_seg);
+    B200_LAUNCH_CHECK();
+    B200_TRY(b200_dfree(h, key_off)); B200_TRY(b200_dfree(h, pos));
+  } else {
+    B200_TRY(sort_rows_by_key(h, n, D, level, &P->perm, &P->level_off));
+    std::vector<int> off((size_t)D + 1);
+    B200_CUDA(cudaMemcpyAsync(off.data(), P->level_off, sizeof(int) * off.size(), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (off[D] != n) B200_FAIL("gs plan: level schedule does not cover every row");
+    std::vector<int> ch;
+    for (int l = 0; l < D; l++)
+      for (int p0 = off[l]; p0 < off[l + 1]; p0 += GS_NT) {
+        ch.push_back(p0); ch.push_back(std::min(p0 + GS_NT, off[l + 1])); ch.push_back(l); ch.push_back(0);
+      }
+    P->nchunks = (int)(ch.size() / 4);
+    B200_TRY(b200_dalloc<int>(h, &P->chunks, ch.size()));
+    B200_CUDA(cudaMemcpyAsync(P->chunks, ch.data(), sizeof(int) * ch.size(), cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dalloc<int>(h, &P->ctr, (size_t)D + 1));
   }
-  std::vector<int> off((size_t)nlevels + 1);
-  B200_CUDA(cudaMemcpyAsync(off.data(), P->level_off, sizeof(int) * off.size(), cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA(cudaStreamSynchronize(h->stream));
-  if (off[nlevels] != n) B200_FAIL("gs plan: level schedule does not cover every row (cyclic dependency?)");
-  std::vector<int> ch;
-  for (int l = 0; l < nlevels; l++)
-    for (int p0 = off[l]; p0 < off[l + 1]; p0 += GS_NT) {
-      ch.push_back(p0); ch.push_back(std::min(p0 + GS_NT, off[l + 1])); ch.push_back(l); ch.push_back(0);
-    }
-  P->nchunks = (int)(ch.size() / 4);
-  B200_TRY(b200_dalloc<int>(h, &P->chunks, ch.size()));
-  B200_CUDA(cudaMemcpyAsync(P->chunks, ch.data(), sizeof(int) * ch.size(), cudaMemcpyHostToDevice, h->stream));
-  B200_CUDA(cudaStreamSynchronize(h->stream));
-  B200_TRY(b200_dalloc<int>(h, &P->ctr, (size_t)nlevels + 1));
+  if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, n));
   B200_TRY(b200_dfree(h, d_flag)); B200_TRY(b200_dfree(h, indeg)); B200_TRY(b200_dfree(h, level));
   B200_TRY(b200_dfree(h, fr[0])); B200_TRY(b200_dfree(h, fr[1])); B200_TRY(b200_dfree(h, cnt));
-  if (T) B200_TRY(b200_csr_destroy(h, T));
+  if (Tp) B200_TRY(b200_csr_destroy(h, Tp));
   return 0;
 }
 
 int b200_gs_plan_levels(b200_gs_plan_s *p) { return p ? p->nlevels : 0; }
+int b200_gs_plan_blocks(b200_gs_plan_s *p) { return p ? p->T : 0; }
 
-// dir +1 / -1; classic: types 3/4/6, else the l1 variants (d_l1 required); zero: u == 0 on entry
-int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool classic, bool zero, const double *f,
-                  const double *l1, double *u) {
+// dir +1 / -1; classic: types 3/4/6, else the l1 variants (l1 required); zero: u == 0 on entry.
+// refresh_old: copy the iterate to the pre-sweep buffer first (T > 1).  The reference does this once per
+// relaxation call, so the second half of the symmetric types 6/8 keeps reading the copy made before the
+// forward half (par_relax.c:3548-3640).
+int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool classic, bool zero, bool refresh_old,
+                  const double *f, const double *l1, double *u) {
   if (P->n == 0) return 0;
   if (!classic && !l1) B200_FAIL("gs sweep: l1 norms required for relax types 8/13/14");
+  const double *old = u;
+  if (P->T > 1 && A->ncols > P->n) B200_FAIL("gs sweep: GSBlocks > 1 with ghost columns is not implemented (one block per rank)");
+  if (P->T > 1) {
+    if (refresh_old) {
+      if (zero) B200_CUDA(cudaMemsetAsync(P->old, 0, sizeof(double) * (size_t)P->n, h->stream));
+      else B200_CUDA(cudaMemcpyAsync(P->old, u, sizeof(double) * (size_t)P->n, cudaMemcpyDeviceToDevice, h->stream));
+    }
+    old = P->old;
+  }
+  if (P->lane_path) {
+#define GS_LANE(D, C, Z)                                                                                                   \
+    gs_lane_kernel<D, C, Z><<<b200_grid(P->T, 64), 64, 0, h->stream>>>(P->n, P->T, P->size, P->rest, A->i, A->j, A->a, f,  \
+                                                                        l1, old, u)
+    if (dir > 0) {
+      if (classic) { if (zero) GS_LANE(1, true, true); else GS_LANE(1, true, false); }
+      else         { if (zero) GS_LANE(1, false, true); else GS_LANE(1, false, false); }
+    } else {
+      if (classic) { if (zero) GS_LANE(-1, true, true); else GS_LANE(-1, true, false); }
+      else         { if (zero) GS_LANE(-1, false, true); else GS_LANE(-1, false, false); }
+    }
+#undef GS_LANE
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
+  if (P->block_path) {
+    const int NT = P->maxblock <= 2048 ? 64 : (P->maxblock <= 8192 ? 128 : 256);
+    const size_t smem = sizeof(double) * (size_t)P->maxblock;
+    const int grid = std::min(P->T, h->num_sm * 32);
+    // columns >= n (ghosts) are read from `old` too: with T > 1 the copy holds owned rows only, so ghosts
+    // must stay addressable -> multi-rank callers pass T == 1 per rank or a full-width copy
+#define GS_BLOCK(D, C, Z)                                                                                                  \
+    {                                                                                                                      \
+      if (smem > 48 * 1024)                                                                                                \
+        B200_CUDA(cudaFuncSetAttribute(gs_block_kernel<D, C, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      gs_block_kernel<D, C, Z><<<grid, NT, smem, h->stream>>>(P->n, P->T, P->size, P->rest, P->blk_seg, P->seg_off, P->perm, \
+                                                               A->i, A->j, A->a, f, l1, old, u);                           \
+    }
+    if (dir > 0) {
+      if (classic) { if (zero) GS_BLOCK(1, true, true) else GS_BLOCK(1, true, false) }
+      else         { if (zero) GS_BLOCK(1, false, true) else GS_BLOCK(1, false, false) }
+    } else {
+      if (classic) { if (zero) GS_BLOCK(-1, true, true) else GS_BLOCK(-1, true, false) }
+      else         { if (zero) GS_BLOCK(-1, false, true) else GS_BLOCK(-1, false, false) }
+    }
+#undef GS_BLOCK
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
   B200_CUDA(cudaMemsetAsync(P->ctr, 0, sizeof(int) * ((size_t)P->nlevels + 1), h->stream));
   const int grid = std::min(P->nchunks, h->num_sm * 16);
-#define GS_LAUNCH(D, C, Z)                                                                                               \
-  gs_sweep_kernel<D, C, Z><<<grid, GS_NT, 0, h->stream>>>(P->n, P->nchunks, P->nlevels, (const int4 *)P->chunks,      \
-                                                          P->level_off, P->perm, A->i, A->j, A->a, f, l1, u, P->ctr)
+  const double *oldg = P->T > 1 ? P->old : nullptr;
+#define GS_LAUNCH(D, C, Z)                                                                                                 \
+  gs_sweep_kernel<D, C, Z><<<grid, GS_NT, 0, h->stream>>>(P->n, P->size, P->rest, P->nchunks, P->nlevels,                 \
+                                                          (const int4 *)P->chunks, P->level_off, P->perm, A->i, A->j,     \
+                                                          A->a, f, l1, oldg, u, P->ctr)
   if (dir > 0) {
     if (classic) { if (zero) GS_LAUNCH(1, true, true); else GS_LAUNCH(1, true, false); }
     else         { if (zero) GS_LAUNCH(1, false, true); else GS_LAUNCH(1, false, false); }
@@ -284,18 +543,28 @@ int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool cl
   return 0;
 }
 
+// one relaxation call of the Gauss-Seidel family in place (par_relax.c cases 3/4/6/8/13/14, relax_points 0)
+int b200_gs_relax(b200_handle h, b200_gs_plan_s *P, b200_csr A, int type, bool zero, const double *f, const double *l1, double *u) {
+  const bool classic = type == 3 || type == 4 || type == 6;
+  bool z = zero, first = true;
+  if (type == 3 || type == 13 || type == 6 || type == 8) {
+    B200_TRY(b200_gs_sweep(h, P, A, +1, classic, z, first, f, l1, u));
+    z = false; first = false;
+  }
+  if (type == 4 || type == 14 || type == 6 || type == 8) B200_TRY(b200_gs_sweep(h, P, A, -1, classic, z, first, f, l1, u));
+  return 0;
+}
+
 // hypre_BoomerAMGRelax (par_relax.c:30) for the Gauss-Seidel family on one rank, relax_points 0,
-// relax_weight = omega = 1.  The level schedule is cached on the matrix.
-extern "C" int b200_relax_gs(b200_handle h, b200_csr A, int relax_type, const double *d_f, const double *d_l1, double *d_u) {
+// relax_weight = omega = 1, `blocks` Gauss-Seidel blocks.  The level schedule is cached on the matrix.
+extern "C" int b200_relax_gs(b200_handle h, b200_csr A, int relax_type, int blocks, const double *d_f, const double *d_l1,
+                             double *d_u) {
   if (!A || !A->a) B200_FAIL("relax: matrix with values required");
   if (A->nrows != A->ncols) B200_FAIL("relax: square matrix required");
   const bool classic = relax_type == 3 || relax_type == 4 || relax_type == 6;
   if (!classic && relax_type != 8 && relax_type != 13 && relax_type != 14)
     B200_FAIL("relax: Gauss-Seidel types are 3, 4, 6 (classic) and 8, 13, 14 (l1)");
-  if (!A->gs) B200_TRY(b200_gs_plan_create(h, A, &A->gs));
-  if (relax_type == 3 || relax_type == 13 || relax_type == 6 || relax_type == 8)
-    B200_TRY(b200_gs_sweep(h, A->gs, A, +1, classic, false, d_f, d_l1, d_u));
-  if (relax_type == 4 || relax_type == 14 || relax_type == 6 || relax_type == 8)
-    B200_TRY(b200_gs_sweep(h, A->gs, A, -1, classic, false, d_f, d_l1, d_u));
-  return 0;
+  if (A->gs && b200_gs_plan_blocks(A->gs) != blocks) { B200_TRY(b200_gs_plan_destroy(h, A->gs)); A->gs = nullptr; }
+  if (!A->gs) B200_TRY(b200_gs_plan_create(h, A, blocks, &A->gs));
+  return b200_gs_relax(h, A->gs, A, relax_type, false, d_f, d_l1, d_u);
 }

@@ -500,7 +500,7 @@ HYPRE_Int HYPRE_BoomerAMGCreate(HYPRE_Solver *solver) {
                {"KeepTranspose", 0}, {"Tol", 1e-7}, {"MaxIter", 20}, {"MinIter", 0}, {"RelaxOrder", 0}, {"NumSweeps", 1},
                {"CycleType", 1}, {"MaxLevels", 25}, {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"AggNumLevels", 0},
                {"NumFunctions", 1}, {"StrongThreshold", 0.25}, {"MaxRowSum", 0.9}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
-               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}};
+               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}, {"GSBlocks", 1}};
   for (const Neutral &nv : kNeutral) s->stored[nv.name] = nv.value;
   *solver = s;
   return g_error_flag;
@@ -600,6 +600,14 @@ AMG_SETTER(EuBJ, HYPRE_Int, true)
 AMG_SETTER(EuSparseA, HYPRE_Real, true)
 #undef AMG_SETTER
 
+// number of Gauss-Seidel blocks per rank for the hybrid smoothers 3/4/6/8/13/14: what the OpenMP thread
+// count is to the reference (par_relax.c:4400-4412, hypre_NumThreads()); default 1
+HYPRE_Int HYPRE_b200_BoomerAMGSetGSBlocks(HYPRE_Solver s, HYPRE_Int blocks) {
+  if (!is_amg(s)) return err_arg(1);
+  if (blocks < 1) return err_arg(2);
+  s->stored["GSBlocks"] = blocks;
+  return g_error_flag;
+}
 HYPRE_Int HYPRE_BoomerAMGSetOldDefault(HYPRE_Solver s) {               // HYPRE_parcsr_amg.c:1500-1508
   if (!is_amg(s)) return err_arg(1);
   s->stored["CoarsenType"] = 6; s->stored["InterpType"] = 0; s->stored["PMaxElmts"] = 0;
@@ -671,7 +679,7 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   if (st.count("CycleNumSweeps3") && st["CycleNumSweeps3"] != 1) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: only one coarse sweep\n"); return err(HYPRE_ERROR_GENERIC); }
   static const char *ints[] = {"CoarsenType", "InterpType", "PMaxElmts", "MaxLevels", "MaxCoarseSize", "MinCoarseSize", "NumSweeps",
                                "AggNumLevels", "ModuleRAP2", "RAP2", "KeepTranspose", "RelaxOrder", "MaxIter", "MinIter", "CycleType",
-                               "NumFunctions", "PrintLevel"};
+                               "NumFunctions", "PrintLevel", "GSBlocks"};
   static const char *reals[] = {"StrongThreshold", "MaxRowSum", "TruncFactor", "RelaxWt", "OuterWt", "Tol"};
   for (const char *k : ints) CALL(b200_amg_set_int(s->amg, k, (int)st[k]), "HYPRE_BoomerAMGSetup");
   for (const char *k : reals) CALL(b200_amg_set_real(s->amg, k, st[k]), "HYPRE_BoomerAMGSetup");

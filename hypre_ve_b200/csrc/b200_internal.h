@@ -105,9 +105,9 @@ static inline int b200_grid(size_t n, int block) { return (int)((n + block - 1) 
 int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data, b200_csr *A);
 int b200_csr_build_plan(b200_handle h, b200_csr A);
 int b200_exclusive_scan_inplace(b200_handle h, int *d_data, size_t n);   // d_data[n] entries, in place
-int b200_gs_plan_create(b200_handle h, b200_csr A, b200_gs_plan_s **out);
+int b200_gs_plan_create(b200_handle h, b200_csr A, int blocks, b200_gs_plan_s **out);
 int b200_gs_plan_destroy(b200_handle h, b200_gs_plan_s *p);
 int b200_gs_plan_levels(b200_gs_plan_s *p);
-int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool classic, bool zero, const double *f,
-                  const double *l1, double *u);
+int b200_gs_plan_blocks(b200_gs_plan_s *p);
+int b200_gs_relax(b200_handle h, b200_gs_plan_s *P, b200_csr A, int type, bool zero, const double *f, const double *l1, double *u);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);

@@ -548,20 +548,29 @@ __global__ void spgemm_fill_kernel(int r0, int r1, const int *__restrict__ A_i, 
 // ==========================================================================================
 // l1 norms (ams.c:571-790), single-rank (offd empty)
 // ==========================================================================================
-__global__ void l1_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j,
+// hypre_ParCSRComputeL1Norms (ams.c:571-760) / ...L1NormsThreads (ams.c:3398-3650) on one rank.  (size, rest)
+// describe the reference's thread blocks (= Gauss-Seidel blocks); one block: size = n, rest = 0.
+__global__ void l1_kernel(int n, int size, int rest, const int *__restrict__ A_i, const int *__restrict__ A_j,
                           const double *__restrict__ A_a, int option, double *__restrict__ l1) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double v = 0.0, diag = 0.0;
-  for (int j = A_i[i]; j < A_i[i + 1]; j++)
-    if (A_j[j] == i) { diag = A_a[j]; break; }      // hypre_CSRMatrixExtractDiagonalHost
+  double v = 0.0;
   if (option == 1) {
     for (int j = A_i[i]; j < A_i[i + 1]; j++) v += 1.0 * fabs(A_a[j]);   // ComputeRowSum type 1, scal 1.0
-  } else {                                          // option 4: |a_ii| (+ 0.5*offd, none here), Remark 6.2
-    v = fabs(diag);
-    if (v <= 4.0 / 3.0 * fabs(diag)) v = fabs(diag);
+  } else {                                          // option 4: |a_ii| + 0.5 * off-block entries, Remark 6.2
+    const int split = rest * (size + 1);
+    int ns, ne;
+    if (i < split) { ns = (i / (size + 1)) * (size + 1); ne = ns + size + 1; }
+    else { ns = (rest + (i - split) / size) * size + rest; ne = ns + size; }
+    double diag = 0.0;
+    for (int j = A_i[i]; j < A_i[i + 1]; j++) {
+      const int ii = A_j[j];
+      if (ii == i) { diag = fabs(A_a[j]); v += fabs(A_a[j]); }
+      else if (ii < ns || ii >= ne) v += 0.5 * fabs(A_a[j]);
+    }
+    if (v <= 4.0 / 3.0 * diag) v = diag;
   }
-  if (diag < 0.0) v = -v;
+  if (A_i[i] < A_i[i + 1] && A_a[A_i[i]] < 0.0) v = -v;   // negative diagonal (stored first), ams.c:727-735
   l1[i] = v;
 }
 
@@ -953,11 +962,17 @@ int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, i
   return 0;
 }
 
-extern "C" int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1) {
+extern "C" int b200_l1_norms_blocks(b200_handle h, b200_csr A, int option, int blocks, double *d_l1) {
   if (!A || !A->a) B200_FAIL("l1 norms: matrix with values required");
   if (option != 1 && option != 4) B200_FAIL("l1 norms: only options 1 and 4 are supported");
+  if (blocks < 1) B200_FAIL("l1 norms: blocks must be >= 1");
   if (A->nrows == 0) return 0;
-  l1_kernel<<<b200_grid(A->nrows, TB), TB, 0, h->stream>>>(A->nrows, A->i, A->j, A->a, option, d_l1);
+  const int size = A->nrows / blocks, rest = A->nrows - size * blocks;
+  l1_kernel<<<b200_grid(A->nrows, TB), TB, 0, h->stream>>>(A->nrows, size, rest, A->i, A->j, A->a, option, d_l1);
   B200_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1) {
+  return b200_l1_norms_blocks(h, A, option, 1, d_l1);
 }

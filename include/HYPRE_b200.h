@@ -180,6 +180,9 @@ HYPRE_Int HYPRE_BoomerAMGSetSchwarzRlxWeight(HYPRE_Solver solver, HYPRE_Real v);
 HYPRE_Int HYPRE_BoomerAMGSetEuLevel(HYPRE_Solver solver, HYPRE_Int v);
 HYPRE_Int HYPRE_BoomerAMGSetEuBJ(HYPRE_Solver solver, HYPRE_Int v);
 HYPRE_Int HYPRE_BoomerAMGSetEuSparseA(HYPRE_Solver solver, HYPRE_Real v);
+/* Gauss-Seidel blocks per rank for relax types 3/4/6/8/13/14 = the reference's OpenMP thread count
+ * (par_relax.c:4400-4412); default 1 = sequential Gauss-Seidel inside the rank */
+HYPRE_Int HYPRE_b200_BoomerAMGSetGSBlocks(HYPRE_Solver solver, HYPRE_Int blocks);
 HYPRE_Int HYPRE_BoomerAMGSetOldDefault(HYPRE_Solver solver);
 HYPRE_Int HYPRE_BoomerAMGSetPrintFileName(HYPRE_Solver solver, const char *print_file_name);
 HYPRE_Int HYPRE_BoomerAMGSetCycleRelaxType(HYPRE_Solver solver, HYPRE_Int relax_type, HYPRE_Int k);

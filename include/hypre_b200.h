@@ -104,7 +104,7 @@ int b200_amg_destroy(b200_handle h, b200_amg amg);       /* HYPRE_BoomerAMGDestr
 /* integer / real parameters by the reference setter's name without the HYPRE_BoomerAMGSet prefix:
  * "CoarsenType","InterpType","PMaxElmts","RelaxType","MaxLevels","MaxCoarseSize","NumSweeps",
  * "AggNumLevels","ModuleRAP2","KeepTranspose","RelaxOrder","MaxIter","MinIter","RelaxTypeUp" (up-cycle
- * smoother when it differs from "RelaxType", e.g. 13 down / 14 up) / "StrongThreshold",
+ * smoother when it differs from "RelaxType", e.g. 13 down / 14 up), "GSBlocks" (Gauss-Seidel blocks per rank) / "StrongThreshold",
  * "MaxRowSum","TruncFactor","RelaxWt","Tol".  Unsupported values are rejected at setup. */
 int b200_amg_set_int(b200_amg amg, const char *name, int value);
 int b200_amg_set_real(b200_amg amg, const char *name, double value);
@@ -140,12 +140,18 @@ int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf,
                       double trunc_factor, int max_elmts, b200_csr *P);
 /* hypre_ParCSRComputeL1Norms (ams.c:571-760), options 1 and 4 */
 int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
+/* the same with the reference's thread blocks (hypre_ParCSRComputeL1NormsThreads, ams.c:3398-3650): option 4
+ * adds half of every entry that lies outside the Gauss-Seidel block of its row */
+int b200_l1_norms_blocks(b200_handle h, b200_csr A, int option, int blocks, double *d_l1);
 
 /* hypre_BoomerAMGRelax (par_relax.c:30-5264) for the hybrid Gauss-Seidel family on one rank, relax_points 0,
  * relax_weight = omega = 1: types 3 / 4 / 6 (forward / backward / symmetric, u_i = res / a_ii) and the l1
- * variants 13 / 14 / 8 (u_i += res / l1_i, d_l1 from b200_l1_norms option 4).  One Gauss-Seidel block per
- * rank = the reference with OMP_NUM_THREADS=1; the sweep is the sequential loop's result bit for bit. */
-int b200_relax_gs(b200_handle h, b200_csr A, int relax_type, const double *d_f, const double *d_l1, double *d_u);
+ * variants 13 / 14 / 8 (u_i += res / l1_i, d_l1 from b200_l1_norms option 4).  `blocks` = number of
+ * Gauss-Seidel blocks the rows are cut into (the reference's OpenMP thread count, par_relax.c:4400-4412):
+ * sequential inside a block, pre-sweep values across blocks.  For a given block count the result is the
+ * reference loop's bit for bit.  (AMG parameter: "GSBlocks".) */
+int b200_relax_gs(b200_handle h, b200_csr A, int relax_type, int blocks, const double *d_f, const double *d_l1,
+                  double *d_u);
 
 /* ---- PCG (krylov/pcg.c:271-757 via HYPRE_ParCSRPCGSolve) ------------------------------------- */
 /* Solves A x = b with BoomerAMG-preconditioned CG (amg may be NULL: unpreconditioned).

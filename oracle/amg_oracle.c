@@ -328,24 +328,37 @@ static csr_t multiply(const csr_t *A, const csr_t *B)
 }
 
 /* ---- l1 norms option 1: parcsr_ls/ams.c:648-657,:739-769 + csr_matop.c:1326-1352 ---- */
+static int g_gs_blocks = 1;   /* the reference's num_threads = hypre_NumThreads() */
+/* hypre_ParCSRComputeL1Norms (ams.c:571-760), which hands over to ...L1NormsThreads (ams.c:3398-3650) when
+ * num_threads > 1: option 1 = sum |a_ij|; option 4 = |a_ii| + 0.5 * sum of |a_ij| over the entries OUTSIDE
+ * the thread block [ns, ne) of row i (plus the offd block: none on one rank), truncated by Remark 6.2 */
 static double *l1_norms(const csr_t *A, int option)
 {
-   double *l1 = (double *) xmalloc(sizeof(double) * A->n); int i, j;
-   for (i = 0; i < A->n; i++)
+   double *l1 = (double *) xmalloc(sizeof(double) * A->n); int i, j, k, T = g_gs_blocks, n = A->n;
+   for (k = 0; k < T; k++)
    {
-      double s = 0.0, d = 0.0;
-      for (j = A->i[i]; j < A->i[i + 1]; j++) if (A->j[j] == i) { d = A->a[j]; break; }
-      if (option == 1) { for (j = A->i[i]; j < A->i[i + 1]; j++) s += 1.0 * fabs(A->a[j]); }
-      else
-      {  /* option 4 (ams.c:680-703): |a_ii| + 0.5 * l1(offd) (no offd block on one rank), then Remark 6.2 */
-         s = fabs(d);
-         if (s <= 4.0 / 3.0 * fabs(d)) s = fabs(d);
+      int size = n / T, rest = n - size * T, ns, ne;
+      if (k < rest) { ns = k * size + k; ne = (k + 1) * size + k + 1; }
+      else { ns = k * size + rest; ne = (k + 1) * size + rest; }
+      for (i = ns; i < ne; i++)
+      {
+         double s = 0.0, d = 0.0;
+         if (option == 1) { for (j = A->i[i]; j < A->i[i + 1]; j++) s += fabs(A->a[j]); }
+         else
+         {
+            for (j = A->i[i]; j < A->i[i + 1]; j++)
+            {
+               int ii = A->j[j];
+               if (ii == i) { d = fabs(A->a[j]); s += fabs(A->a[j]); }
+               else if (ii < ns || ii >= ne) s += 0.5 * fabs(A->a[j]);
+            }
+            if (s <= 4.0 / 3.0 * d) s = d;
+         }
+         l1[i] = (A->a[A->i[i]] < 0) ? -s : s;
       }
-      l1[i] = d < 0.0 ? -s : s;
    }
    return l1;
 }
-
 /* ---- sstruct_ls/gselim.h ---- */
 static void gselim(double *A, double *x, int n)
 {
@@ -412,55 +425,59 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    }
 }
 
-/* one row of the hybrid Gauss-Seidel family on one rank / one thread block (par_relax.c):
+/* one row of the hybrid Gauss-Seidel family (par_relax.c), thread block [ns, ne): in-block neighbours are
+ * read from u (new where already swept), everything else from tmp (the iterate before the sweep).
  * l1 variants 8/13/14 (:3492-4091, :4340-5124): res = f_i - sum_j a_ij u_j over the WHOLE row in storage
  * order, u_i += res / l1_i;  classic variants 3/4/6 (:1875-2265, original type 6 kept under `#if 0` at
  * :2685-2753): the diagonal (stored first) is skipped and u_i = res / a_ii. */
-static void gs_row(const csr_t *A, const double *l1, const double *f, double *u, int i, int classic)
+static void gs_row(const csr_t *A, const double *l1, const double *f, double *u, const double *tmp, int ns, int ne,
+                   int i, int classic)
 {
-   int jj;
+   int jj, ii;
    if (classic)
    {
       if (A->a[A->i[i]] != 0.0)
       {
          double res = f[i];
-         for (jj = A->i[i] + 1; jj < A->i[i + 1]; jj++) res -= A->a[jj] * u[A->j[jj]];
+         for (jj = A->i[i] + 1; jj < A->i[i + 1]; jj++)
+         { ii = A->j[jj]; res -= A->a[jj] * ((ii >= ns && ii < ne) ? u[ii] : tmp[ii]); }
          u[i] = res / A->a[A->i[i]];
       }
    }
    else if (l1[i] != 0.0)
    {
       double res = f[i];
-      for (jj = A->i[i]; jj < A->i[i + 1]; jj++) res -= A->a[jj] * u[A->j[jj]];
+      for (jj = A->i[i]; jj < A->i[i + 1]; jj++)
+      { ii = A->j[jj]; res -= A->a[jj] * ((ii >= ns && ii < ne) ? u[ii] : tmp[ii]); }
       u[i] += res / l1[i];
    }
 }
-/* relaxation sweep of type `type`, relax_weight = omega = 1, relax_points = 0, one rank, one thread.
- * 18: l1-Jacobi, parcsr_ls/ams.c:72-92 (v=f; v=-A u + v; u += v/l1) */
+/* relaxation sweep of type `type`, relax_weight = omega = 1, relax_points = 0, one rank, g_gs_blocks thread
+ * blocks (par_relax.c:4400-4412).  18: l1-Jacobi, parcsr_ls/ams.c:72-92 (v=f; v=-A u + v; u += v/l1) */
 static void relax(amg_t *g, int l, int type, const double *f, double *u)
 {
-   int n = g->A[l].n, i; double *v = g->V;
+   int n = g->A[l].n, i, j, T = g_gs_blocks; double *v = g->V;
    const csr_t *A = &g->A[l]; const double *l1 = g->l1[l];
-   switch (type)
+   if (type == 18)
    {
-      case 18:
-         matvec(-1.0, A, u, 1.0, f, v);
-         for (i = 0; i < n; i++) u[i] += v[i] / l1[i];
-         break;
-      case 13: for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 0); break;
-      case 14: for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 0); break;
-      case 8:
-         for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 0);
-         for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 0);
-         break;
-      case 3:  for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 1); break;
-      case 4:  for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 1); break;
-      case 6:
-         for (i = 0; i < n; i++) gs_row(A, l1, f, u, i, 1);
-         for (i = n - 1; i > -1; i--) gs_row(A, l1, f, u, i, 1);
-         break;
-      default: fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2);
+      matvec(-1.0, A, u, 1.0, f, v);
+      for (i = 0; i < n; i++) u[i] += v[i] / l1[i];
+      return;
    }
+   int classic = (type == 3 || type == 4 || type == 6);
+   int fwd = (type == 3 || type == 13 || type == 6 || type == 8), bwd = (type == 4 || type == 14 || type == 6 || type == 8);
+   if (!fwd && !bwd) { fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2); }
+   double *tmp = (double *) xmalloc(sizeof(double) * n);
+   memcpy(tmp, u, sizeof(double) * n);
+   for (j = 0; j < T; j++)
+   {
+      int size = n / T, rest = n - size * T, ns, ne;
+      if (j < rest) { ns = j * size + j; ne = (j + 1) * size + j + 1; }
+      else { ns = j * size + rest; ne = (j + 1) * size + rest; }
+      if (fwd) for (i = ns; i < ne; i++) gs_row(A, l1, f, u, tmp, ns, ne, i, classic);
+      if (bwd) for (i = ne - 1; i > ns - 1; i--) gs_row(A, l1, f, u, tmp, ns, ne, i, classic);
+   }
+   free(tmp);
 }
 /* V(1,1): parcsr_ls/par_cycle.c:255-622 */
 static void cycle(amg_t *g, const double *f, double *u)
@@ -530,6 +547,7 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
       else if (!strcmp(argv[i], "-pmis") || !strcmp(argv[i], "-nodump")) { }
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-gs_blocks")) g_gs_blocks = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }

@@ -34,8 +34,8 @@ def result(out, key="Iterations"):
     return its, rel
 
 
-def ref_result(flags, key="Iterations"):
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+def ref_result(flags, key="Iterations", threads=1):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
     rc, out = run([REF_IJ, "-laplacian"] + flags, env)
     assert rc == 0, out
     return result(out, key)
@@ -84,6 +84,17 @@ def test_hybrid_gauss_seidel_smoothers_through_the_public_api(exe, flags, known)
         assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)
     if known:
         assert its == known
+
+
+def test_gauss_seidel_blocks_equal_reference_thread_count(exe):
+    """-gs_blocks T on our side == OMP_NUM_THREADS=T on the reference's"""
+    flags = ["-n", "30", "30", "30", "-solver", "1", "-pmis", "-mod_rap2", "1"]
+    rc, out = run([exe, "-laplacian"] + flags + ["-gs_blocks", "24"])
+    assert rc == 0, out
+    its, rel = result(out)
+    if os.path.exists(REF_IJ):
+        rits, rrel = ref_result(flags, threads=24)
+        assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)
 
 
 def test_ij_assembled_operator_equals_generated_operator(exe):

@@ -21,23 +21,60 @@ pytestmark = pytest.mark.gpu
 ORACLE = os.path.join(refio.ROOT, "oracle", "_build", "amg_oracle")
 
 
-def seq_sweep(ip, ix, a, f, d, u, order, classic):
-    """the reference loop: res = f_i - sum a_ij u_j in storage order; u_i += res/l1_i | u_i = res/a_ii"""
-    u = u.copy()
-    for i in order:
-        b, e = ip[i], ip[i + 1]
-        if classic:
-            if a[b] != 0.0:
-                res = f[i]
-                for jj in range(b + 1, e):
-                    res -= a[jj] * u[ix[jj]]
-                u[i] = res / a[b]
-        elif d[i] != 0.0:
-            res = f[i]
-            for jj in range(b, e):
-                res -= a[jj] * u[ix[jj]]
-            u[i] += res / d[i]
+def blocks_of(n, T):
+    """the reference's thread blocks (par_relax.c:4400-4412)"""
+    size, out = n // T, []
+    if size == 0:
+        return [(j, j + 1) for j in range(n)]
+    rest = n - size * T
+    for j in range(T):
+        ns = j * size + j if j < rest else j * size + rest
+        out.append((ns, ns + size + (1 if j < rest else 0)))
+    return out
+
+
+def seq_relax(ip, ix, a, f, d, u0, fwd, bwd, classic, T):
+    """the reference loop per thread block: res = f_i - sum a_ij (u_j in block | tmp_j outside) in storage
+    order; u_i += res/l1_i | u_i = res/a_ii.  tmp is copied ONCE per call (also for the symmetric types)."""
+    u, tmp = u0.copy(), u0.copy()
+    for ns, ne in blocks_of(len(ip) - 1, T):
+        orders = ([range(ns, ne)] if fwd else []) + ([range(ne - 1, ns - 1, -1)] if bwd else [])
+        for order in orders:
+            for i in order:
+                b, e = ip[i], ip[i + 1]
+                if classic:
+                    if a[b] != 0.0:
+                        res = f[i]
+                        for jj in range(b + 1, e):
+                            j = ix[jj]
+                            res -= a[jj] * (u[j] if ns <= j < ne else tmp[j])
+                        u[i] = res / a[b]
+                elif d[i] != 0.0:
+                    res = f[i]
+                    for jj in range(b, e):
+                        j = ix[jj]
+                        res -= a[jj] * (u[j] if ns <= j < ne else tmp[j])
+                    u[i] += res / d[i]
     return u
+
+
+def l1_opt4(ip, ix, a, T):
+    """hypre_ParCSRComputeL1NormsThreads option 4 (ams.c:3560-3625)"""
+    n = len(ip) - 1
+    out = np.zeros(n)
+    for ns, ne in blocks_of(n, T):
+        for i in range(ns, ne):
+            s = d = 0.0
+            for jj in range(ip[i], ip[i + 1]):
+                j = ix[jj]
+                if j == i:
+                    d = abs(a[jj]); s += abs(a[jj])
+                elif j < ns or j >= ne:
+                    s += 0.5 * abs(a[jj])
+            if s <= 4.0 / 3.0 * d:
+                s = d
+            out[i] = -s if a[ip[i]] < 0 else s
+    return out
 
 
 def diag_first(M):
@@ -68,10 +105,15 @@ def small_matrices():
     return out
 
 
+@pytest.mark.parametrize("path,T", [("auto", 1), ("global", 1), ("block", 1), ("block", 3), ("block", 40), ("global", 7),
+                                    ("auto", 3), ("auto", 40), ("auto", 100000)])
 @pytest.mark.parametrize("relax_type", [13, 14, 8, 3, 4, 6])
 @pytest.mark.parametrize("name", ["sym_random", "nonsym_random", "chain", "lap7", "lap27", "coarse_level"])
-def test_single_sweep_is_the_sequential_loop_bit_for_bit(handle, name, relax_type):
+def test_single_sweep_is_the_sequential_loop_bit_for_bit(handle, monkeypatch, name, relax_type, path, T):
+    """all three schedulers (global soft barriers / one CTA per Gauss-Seidel block / one thread per block),
+    1 .. n blocks"""
     import hypre_ve_b200 as hb
+    monkeypatch.setenv("B200_GS_FORCE_GLOBAL", {"global": "1", "block": "2", "auto": "0"}[path])
     if name in ("lap7", "lap27"):
         A0 = hb.ParCsr.laplacian(handle, 9, 7, 8) if name == "lap7" else hb.ParCsr.laplacian27(handle, 7, 6, 5)
         ip, ix, a = A0.diag.download()
@@ -86,15 +128,13 @@ def test_single_sweep_is_the_sequential_loop_bit_for_bit(handle, name, relax_typ
     f, u0 = rng.standard_normal(n), rng.standard_normal(n)
     A = hb.Csr.from_host(handle, ip, ix, a)
     classic = relax_type in (3, 4, 6)
-    l1 = None if classic else handle.l1_norms(A, 4)
+    l1 = None if classic else handle.l1_norms(A, 4, T)
     dl1 = None if classic else l1.numpy()
-    want = u0
-    if relax_type in (3, 13, 6, 8):
-        want = seq_sweep(ip, ix, a, f, dl1, want, range(n), classic)
-    if relax_type in (4, 14, 6, 8):
-        want = seq_sweep(ip, ix, a, f, dl1, want, range(n - 1, -1, -1), classic)
+    if not classic:
+        assert np.array_equal(dl1, l1_opt4(ip, ix, a, T))
+    want = seq_relax(ip, ix, a, f, dl1, u0, relax_type in (3, 13, 6, 8), relax_type in (4, 14, 6, 8), classic, T)
     df, du = handle.array(f), handle.array(u0)
-    handle.relax_gs(A, relax_type, df, l1, du)
+    handle.relax_gs(A, relax_type, df, l1, du, T)
     got = du.numpy()
     assert np.array_equal(got, want), float(np.max(np.abs(got - want)))
     A.destroy()
@@ -109,26 +149,30 @@ def run_oracle(args):
 
 
 SOLVES = [
-    (["-n", 24, 20, 18], 13), (["-n", 24, 20, 18], 14), (["-n", 24, 20, 18], 8), (["-n", 24, 20, 18], 4),
-    (["-n", 24, 20, 18], -1), (["-n", 16, 16, 16, "-27pt"], -1), (["-n", 20, 20, 20, "-c", 1, 1, 0.001], -1),
-    (["-n", 40, 40, 40], -1),
-    (["-n", 24, 20, 18], 3), (["-n", 24, 20, 18], 6),
+    (["-n", 24, 20, 18], 13, 1), (["-n", 24, 20, 18], 14, 1), (["-n", 24, 20, 18], 8, 1), (["-n", 24, 20, 18], 4, 1),
+    (["-n", 24, 20, 18], -1, 1), (["-n", 16, 16, 16, "-27pt"], -1, 1), (["-n", 20, 20, 20, "-c", 1, 1, 0.001], -1, 1),
+    (["-n", 40, 40, 40], -1, 1),
+    (["-n", 24, 20, 18], 3, 1), (["-n", 24, 20, 18], 6, 1),
+    # T Gauss-Seidel blocks = the reference with OMP_NUM_THREADS = T
+    (["-n", 24, 20, 18], -1, 4), (["-n", 24, 20, 18], 8, 16), (["-n", 30, 30, 30], -1, 64), (["-n", 16, 16, 16, "-27pt"], -1, 48),
+    (["-n", 24, 20, 18], 6, 5),
 ]
 
 
-@pytest.mark.parametrize("args,rlx", SOLVES)
-def test_amg_pcg_with_gauss_seidel_smoothers(handle, args, rlx):
+@pytest.mark.parametrize("args,rlx,T", SOLVES)
+def test_amg_pcg_with_gauss_seidel_smoothers(handle, args, rlx, T):
     """hierarchy (bit-exact), iteration count (exact) and residual history (1e-10) of BoomerAMG-PCG"""
     import hypre_ve_b200 as hb
     flags = args + ["-pmis", "-mod_rap2", 1] + (["-rlx", rlx] if rlx > -1 else [])
     if rlx in (3, 6) or not refio.have_ref():
-        d = run_oracle(flags)              # relax 3/6: VE-only code in this fork -> restatement oracle
+        d = run_oracle(flags + ["-gs_blocks", T])   # relax 3/6: VE-only code in this fork -> restatement oracle
     else:
-        d, _ = refio.run_ref(flags)
+        d, _ = refio.run_ref(flags, threads=T)
     nx, ny, nz = args[1:4]
     A = hb.ParCsr.laplacian27(handle, nx, ny, nz) if "-27pt" in args else \
         hb.ParCsr.laplacian(handle, nx, ny, nz, c=tuple(args[5:8]) if "-c" in args else (1.0, 1.0, 1.0))
     amg = hb.Amg(handle)
+    amg.set("GSBlocks", T)
     if rlx > -1:
         amg.set("RelaxType", rlx)
     else:
