@@ -86,6 +86,11 @@ __device__ void qsort2_abs_smem(int *v, double *w, int left, int right) {
 // ext+i interpolation + truncation, one warp per fine row, output rows of <= pmax entries
 // written with stride pmax (par_lr_interp.c:1301-1416, :1523-1803; par_csr_matrix.c:2768-3020)
 // ------------------------------------------------------------------------------------------
+// Latency structure: everything that depends only on the entries of row i (neighbour ids, their CF
+// markers, row extents, diagonal signs, hash lookups) is fetched by the 32 lanes at once, one lane per
+// entry, and handed to the sequential outer loop by shuffles; the first 32-entry chunk of the NEXT strong
+// F neighbour's row is already in flight (software pipeline) while the current one is folded in.  The
+// arithmetic and its order are unchanged.
 template <int CAP>
 __global__ void __launch_bounds__(32 * WPB)
 extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
@@ -97,9 +102,9 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
   extern __shared__ unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // per-warp layout: ra[LIMIT] doubles | keys[CAP] | vals[CAP] | rj[LIMIT]
-  unsigned char *base = smem_raw + (size_t)warp * (sizeof(double) * LIMIT + sizeof(int) * (2 * CAP + LIMIT));
-  double *ra = reinterpret_cast<double *>(base);
-  int *keys = reinterpret_cast<int *>(base + sizeof(double) * LIMIT);
+  unsigned char *base_p = smem_raw + (size_t)warp * (sizeof(double) * LIMIT + sizeof(int) * (2 * CAP + LIMIT));
+  double *ra = reinterpret_cast<double *>(base_p);
+  int *keys = reinterpret_cast<int *>(base_p + sizeof(double) * LIMIT);
   int *vals = keys + CAP;
   int *rj = vals + CAP;
   const unsigned ltmask = (1u << lane) - 1u;
@@ -118,47 +123,87 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
     int count = 0, used = 0;
     bool over = false;
     // ---- discovery of C-hat_i in the reference's order -----------------------------------
-    for (int jj = S_i[i]; jj < S_i[i + 1] && !over; jj++) {
-      const int i1 = S_j[jj];
-      const int c1 = cf[i1];
-      if (c1 >= 0) {
-        if (used + 1 > LIMIT) { over = true; break; }
-        int isn = 0;
-        if (lane == 0) {
-          bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
-          if (nw) { vals[slot] = count; rj[count] = f2c[i1]; ra[count] = 0.0; isn = 1; }
+    const int sb = S_i[i], se = S_i[i + 1];
+    for (int base = sb; base < se && !over; base += 32) {
+      const int nv = min(32, se - base);
+      int i1_l = -1, c1_l = 0, b1_l = 0, e1_l = 0;
+      if (lane < nv) {
+        i1_l = S_j[base + lane];
+        c1_l = cf[i1_l];
+        if (c1_l < 0 && c1_l != -3) { b1_l = S_i[i1_l]; e1_l = S_i[i1_l + 1]; }
+      }
+      const unsigned fmask = __ballot_sync(FULL, lane < nv && c1_l < 0 && c1_l != -3);
+      // two-stage pipeline over the strong F neighbours: stage A holds k1 = S_j[..] of neighbour tA,
+      // stage B holds k1 and cf[k1] of neighbour tB (the next one to be consumed)
+      int tB = fmask ? __ffs(fmask) - 1 : -1, tA = -1, kA = -1, kB = -1, cB = -1;
+      if (tB >= 0) {
+        const int bb = __shfl_sync(FULL, b1_l, tB), ee = __shfl_sync(FULL, e1_l, tB);
+        if (bb + lane < ee) kB = S_j[bb + lane];
+        const unsigned m = (tB >= 31) ? 0u : (fmask & ~((2u << tB) - 1u));
+        tA = m ? __ffs(m) - 1 : -1;
+        if (tA >= 0) {
+          const int b2 = __shfl_sync(FULL, b1_l, tA), e2 = __shfl_sync(FULL, e1_l, tA);
+          if (b2 + lane < e2) kA = S_j[b2 + lane];
         }
-        isn = __shfl_sync(FULL, isn, 0);
-        count += isn; used += isn;
-        __syncwarp();
-      } else if (c1 != -3) {
-        if (used + 1 > LIMIT) { over = true; break; }
-        int isn = 0;
-        if (lane == 0) {
-          bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
-          if (nw) { vals[slot] = STRONG_F; isn = 1; }
-        }
-        isn = __shfl_sync(FULL, isn, 0);
-        used += isn;
-        __syncwarp();
-        const int e1 = S_i[i1 + 1];
-        for (int kk0 = S_i[i1]; kk0 < e1; kk0 += 32) {
-          if (used + min(32, e1 - kk0) > LIMIT) { over = true; break; }
-          const int kk = kk0 + lane;
-          int k1 = -1;
-          bool want = false;
-          if (kk < e1) { k1 = S_j[kk]; want = cf[k1] >= 0; }
-          bool nw = false;
-          int slot = 0;
-          if (want) slot = wt_insert<CAP>(keys, k1, &nw);
-          const unsigned newmask = __ballot_sync(FULL, nw);
-          if (nw) {
-            const int pos = count + __popc(newmask & ltmask);
-            vals[slot] = pos; rj[pos] = f2c[k1]; ra[pos] = 0.0;
+        if (kB >= 0) cB = cf[kB];
+      }
+      for (int t = 0; t < nv && !over; t++) {
+        const int i1 = __shfl_sync(FULL, i1_l, t);
+        const int c1 = __shfl_sync(FULL, c1_l, t);
+        if (c1 >= 0) {
+          if (used + 1 > LIMIT) { over = true; break; }
+          int isn = 0;
+          if (lane == 0) {
+            bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
+            if (nw) { vals[slot] = count; rj[count] = f2c[i1]; ra[count] = 0.0; isn = 1; }
           }
-          const int nn = __popc(newmask);
-          count += nn; used += nn;
+          isn = __shfl_sync(FULL, isn, 0);
+          count += isn; used += isn;
           __syncwarp();
+        } else if (c1 != -3) {
+          const int b1 = __shfl_sync(FULL, b1_l, t), e1 = __shfl_sync(FULL, e1_l, t);
+          const int cur_k = kB, cur_c = cB;                 // first chunk of this neighbour (t == tB)
+          // advance the pipeline before touching the hash table: B <- A, A <- following neighbour
+          tB = tA; kB = kA; cB = -1; tA = -1; kA = -1;
+          if (tB >= 0) {
+            if (kB >= 0) cB = cf[kB];
+            const unsigned m = (tB >= 31) ? 0u : (fmask & ~((2u << tB) - 1u));
+            tA = m ? __ffs(m) - 1 : -1;
+            if (tA >= 0) {
+              const int b2 = __shfl_sync(FULL, b1_l, tA), e2 = __shfl_sync(FULL, e1_l, tA);
+              if (b2 + lane < e2) kA = S_j[b2 + lane];
+            }
+          }
+          if (used + 1 > LIMIT) { over = true; break; }
+          int isn = 0;
+          if (lane == 0) {
+            bool nw; int slot = wt_insert<CAP>(keys, i1, &nw);
+            if (nw) { vals[slot] = STRONG_F; isn = 1; }
+          }
+          isn = __shfl_sync(FULL, isn, 0);
+          used += isn;
+          __syncwarp();
+          for (int kk0 = b1; kk0 < e1; kk0 += 32) {
+            if (used + min(32, e1 - kk0) > LIMIT) { over = true; break; }
+            int k1 = -1;
+            bool want = false;
+            if (kk0 == b1) { k1 = cur_k; want = (k1 >= 0) && (cur_c >= 0); }
+            else {
+              const int kk = kk0 + lane;
+              if (kk < e1) { k1 = S_j[kk]; want = cf[k1] >= 0; }
+            }
+            bool nw = false;
+            int slot = 0;
+            if (want) slot = wt_insert<CAP>(keys, k1, &nw);
+            const unsigned newmask = __ballot_sync(FULL, nw);
+            if (nw) {
+              const int pos = count + __popc(newmask & ltmask);
+              vals[slot] = pos; rj[pos] = f2c[k1]; ra[pos] = 0.0;
+            }
+            const int nn = __popc(newmask);
+            count += nn; used += nn;
+            __syncwarp();
+          }
         }
       }
     }
@@ -171,59 +216,98 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
     // ---- weights, reference accumulation order ---------------------------------------------
     double diagonal = A_a[A_i[i]];
     const int eA = A_i[i + 1];
-    for (int jj = A_i[i] + 1; jj < eA; jj++) {
-      const int i1 = A_j[jj];
-      const double aij = A_a[jj];
-      const int m1 = wt_find<CAP>(keys, vals, i1);
-      if (m1 >= 0) {
-        if (lane == 0) ra[m1] += aij;
-      } else if (m1 == STRONG_F) {
-        const int b1 = A_i[i1] + 1, e1 = A_i[i1 + 1];
-        const int sgn = (A_a[A_i[i1]] < 0) ? -1 : 1;
-        double sum = 0.0;
-        for (int k0 = b1; k0 < e1; k0 += 32) {
-          const int k = k0 + lane;
-          double contrib = 0.0;
-          if (k < e1) {
-            const double a = A_a[k];
-            if ((sgn * a) < 0) {
-              const int i2 = A_j[k];
-              if (i2 == i || wt_find<CAP>(keys, vals, i2) >= 0) contrib = a;
+    for (int base = A_i[i] + 1; base < eA; base += 32) {
+      const int nv = min(32, eA - base);
+      int i1_l = -1, m1_l = NOTFOUND, cf1_l = 0, b1_l = 0, e1_l = 0, sg_l = 1;
+      double aij_l = 0.0;
+      if (lane < nv) {
+        i1_l = A_j[base + lane];
+        aij_l = A_a[base + lane];
+        m1_l = wt_find<CAP>(keys, vals, i1_l);
+        if (m1_l == STRONG_F) {
+          const int r0 = A_i[i1_l];
+          b1_l = r0 + 1; e1_l = A_i[i1_l + 1];
+          sg_l = (A_a[r0] < 0) ? -1 : 1;
+        } else if (m1_l == NOTFOUND) {
+          cf1_l = cf[i1_l];
+        }
+      }
+      const unsigned fmask = __ballot_sync(FULL, lane < nv && m1_l == STRONG_F);
+      // prefetch the first chunk of the first strong F neighbour's row
+      int tP = fmask ? __ffs(fmask) - 1 : -1, pI = -1;
+      double pA = 0.0;
+      if (tP >= 0) {
+        const int bb = __shfl_sync(FULL, b1_l, tP), ee = __shfl_sync(FULL, e1_l, tP);
+        if (bb + lane < ee) { pI = A_j[bb + lane]; pA = A_a[bb + lane]; }
+      }
+      for (int t = 0; t < nv; t++) {
+        const int m1 = __shfl_sync(FULL, m1_l, t);
+        const double aij = __shfl_sync(FULL, aij_l, t);
+        if (m1 >= 0) {
+          if (lane == 0) ra[m1] += aij;
+        } else if (m1 == STRONG_F) {
+          const int b1 = __shfl_sync(FULL, b1_l, t), e1 = __shfl_sync(FULL, e1_l, t);
+          const int sgn = __shfl_sync(FULL, sg_l, t);
+          const int cI = pI;
+          const double cA = pA;
+          {                                                   // next neighbour's first chunk goes in flight now
+            const unsigned m = (t >= 31) ? 0u : (fmask & ~((2u << t) - 1u));
+            tP = m ? __ffs(m) - 1 : -1;
+            pI = -1; pA = 0.0;
+            if (tP >= 0) {
+              const int bb = __shfl_sync(FULL, b1_l, tP), ee = __shfl_sync(FULL, e1_l, tP);
+              if (bb + lane < ee) { pI = A_j[bb + lane]; pA = A_a[bb + lane]; }
             }
           }
-          const unsigned any = __ballot_sync(FULL, contrib != 0.0);
-          if (any) {
-#pragma unroll
-            for (int l = 0; l < 32; l++) sum += __shfl_sync(FULL, contrib, l);   // lane order == entry order
-          }
-        }
-        if (sum != 0) {
-          const double distribute = aij / sum;
+          double sum = 0.0;
+          int q0 = NOTFOUND;
           for (int k0 = b1; k0 < e1; k0 += 32) {
             const int k = k0 + lane;
+            double contrib = 0.0, a = 0.0;
+            int i2 = -1;
+            const bool have = k < e1;
+            if (k0 == b1) { i2 = cI; a = cA; }
+            else if (have) { a = A_a[k]; i2 = A_j[k]; }
             int q = NOTFOUND;
-            double a = 0.0;
-            if (k < e1) {
-              a = A_a[k];
-              if ((sgn * a) < 0) {
-                const int i2 = A_j[k];
-                q = (i2 == i) ? SELF : wt_find<CAP>(keys, vals, i2);
+            if (have && (sgn * a) < 0) {
+              q = (i2 == i) ? SELF : wt_find<CAP>(keys, vals, i2);
+              if (q == SELF || q >= 0) contrib = a;
+            }
+            if (k0 == b1) q0 = q;
+            // lane order == entry order; lanes with contrib == 0 would add an exact 0.0, so only the
+            // contributing lanes are visited
+            for (unsigned any = __ballot_sync(FULL, contrib != 0.0); any; any &= any - 1)
+              sum += __shfl_sync(FULL, contrib, __ffs(any) - 1);
+          }
+          if (sum != 0) {
+            const double distribute = aij / sum;
+            for (int k0 = b1; k0 < e1; k0 += 32) {
+              const int k = k0 + lane;
+              int q = NOTFOUND;
+              double a = 0.0;
+              if (k0 == b1) { q = q0; a = cA; }
+              else if (k < e1) {
+                a = A_a[k];
+                if ((sgn * a) < 0) {
+                  const int i2 = A_j[k];
+                  q = (i2 == i) ? SELF : wt_find<CAP>(keys, vals, i2);
+                }
+              }
+              if (q >= 0) ra[q] += distribute * a;            // distinct q across the lanes of one row
+              const unsigned selfmask = __ballot_sync(FULL, q == SELF);
+              if (selfmask) {
+                const double d = __shfl_sync(FULL, distribute * a, __ffs(selfmask) - 1);
+                diagonal += d;
               }
             }
-            if (q >= 0) ra[q] += distribute * a;            // distinct q across the lanes of one row
-            const unsigned selfmask = __ballot_sync(FULL, q == SELF);
-            if (selfmask) {
-              const double d = __shfl_sync(FULL, distribute * a, __ffs(selfmask) - 1);
-              diagonal += d;
-            }
+          } else {
+            diagonal += aij;
           }
-        } else {
+        } else if (__shfl_sync(FULL, cf1_l, t) != -3) {
           diagonal += aij;
         }
-      } else if (cf[i1] != -3) {
-        diagonal += aij;
+        __syncwarp();
       }
-      __syncwarp();
     }
     if (diagonal) {
       for (int p = lane; p < count; p += 32) ra[p] /= -diagonal;
@@ -321,50 +405,90 @@ spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A
       __syncwarp();
     }
     const int eA = A_i[ic + 1];
-    for (int ia0 = A_i[ic]; ia0 < eA && !over; ia0 += APS) {
-      const int ia = ia0 + grp_id;
-      int ja = -1, bB = 0, eB = 0;
-      double a = 0.0;
-      if (ia < eA) { ja = A_j[ia]; bB = B_i[ja]; eB = B_i[ja + 1]; if (NUMERIC) a = A_a[ia]; }
-      // GB == 32: one A entry per step, B row walked in chunks of 32 (order preserved: chunks are sequential)
-      int maxlen = eB - bB;
-      if (GB == 32) maxlen = __shfl_sync(FULL, maxlen, 0);
-      const int nchunk = (GB == 32) ? (maxlen + 31) / 32 : 1;
-      for (int ch = 0; ch < nchunk; ch++) {
-        const int ib = bB + ch * GB + sub;
+    // one step: up to 32 (entry of B, product) pairs, in the reference's (ia, ib) order across the lanes
+    auto fold = [&](bool valid, int jb, double prod) {
+      const unsigned vm = __ballot_sync(FULL, valid);
+      if (vm == 0) return;
+      if (!NUMERIC && count + __popc(vm) > LIMIT) { over = true; return; }   // numeric tables are sized from the symbolic count
+      unsigned grp = 0;
+      if (valid) grp = __match_any_sync(vm, jb);
+      const int leader = valid ? (__ffs(grp) - 1) : lane;
+      const bool is_leader = valid && leader == lane;
+      bool nw = false;
+      int slot = 0;
+      if (is_leader) slot = wt_insert<CAP>(keys, jb, &nw);
+      const unsigned newmask = __ballot_sync(FULL, nw);
+      if (NUMERIC) {
+        if (nw) {
+          const int pos = count + __popc(newmask & ltmask);
+          vals[slot] = pos; cols[pos] = jb; acc[pos] = 0.0;      // 0 + a*b == a*b: same as the first-touch store
+        }
+        slot = __shfl_sync(FULL, slot, leader);
+        __syncwarp();
+        const int rank = __popc(grp & ltmask);
+        int maxrank = valid ? __popc(grp) : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) maxrank = max(maxrank, __shfl_xor_sync(FULL, maxrank, off));
+        for (int r = 0; r < maxrank; r++) {
+          if (valid && rank == r) acc[vals[slot]] += prod;
+          __syncwarp();
+        }
+      }
+      count += __popc(newmask);
+      __syncwarp();
+    };
+    if (GB == 32) {
+      // rows of B longer than 16 entries: one A entry per step.  The 32 lanes fetch (ja, a, row extent of B)
+      // for 32 entries of A at once; the first chunk of the NEXT entry's B row is in flight while the
+      // current one is folded into the table.
+      for (int base = A_i[ic]; base < eA && !over; base += 32) {
+        const int nv = min(32, eA - base);
+        int bB_l = 0, eB_l = 0;
+        double a_l = 0.0;
+        if (lane < nv) {
+          const int ja = A_j[base + lane];
+          bB_l = B_i[ja]; eB_l = B_i[ja + 1];
+          if (NUMERIC) a_l = A_a[base + lane];
+        }
+        int pJ = -1;
+        double pB = 0.0;
+        {
+          const int bb = __shfl_sync(FULL, bB_l, 0), ee = __shfl_sync(FULL, eB_l, 0);
+          if (bb + lane < ee) { pJ = B_j[bb + lane]; if (NUMERIC) pB = B_a[bb + lane]; }
+        }
+        for (int t = 0; t < nv && !over; t++) {
+          const int bB = __shfl_sync(FULL, bB_l, t), eB = __shfl_sync(FULL, eB_l, t);
+          const double a = __shfl_sync(FULL, a_l, t);
+          const int cJ = pJ;
+          const double cB = pB;
+          pJ = -1; pB = 0.0;
+          if (t + 1 < nv) {
+            const int bb = __shfl_sync(FULL, bB_l, t + 1), ee = __shfl_sync(FULL, eB_l, t + 1);
+            if (bb + lane < ee) { pJ = B_j[bb + lane]; if (NUMERIC) pB = B_a[bb + lane]; }
+          }
+          for (int c0 = bB; c0 < eB && !over; c0 += 32) {
+            const int ib = c0 + lane;
+            const bool valid = ib < eB;
+            int jb = -1;
+            double prod = 0.0;
+            if (c0 == bB) { jb = cJ; if (NUMERIC) prod = a * cB; }
+            else if (valid) { jb = B_j[ib]; if (NUMERIC) prod = a * B_a[ib]; }
+            fold(valid, jb, prod);
+          }
+        }
+      }
+    } else {
+      for (int ia0 = A_i[ic]; ia0 < eA && !over; ia0 += APS) {
+        const int ia = ia0 + grp_id;
+        int bB = 0, eB = 0;
+        double a = 0.0;
+        if (ia < eA) { const int ja = A_j[ia]; bB = B_i[ja]; eB = B_i[ja + 1]; if (NUMERIC) a = A_a[ia]; }
+        const int ib = bB + sub;                          // every row of B has at most GB entries
         const bool valid = ib < eB;
-        const unsigned vm = __ballot_sync(FULL, valid);
-        if (vm == 0) continue;
-        if (!NUMERIC && count + __popc(vm) > LIMIT) { over = true; break; }   // numeric tables are sized from the symbolic count
         int jb = -1;
         double prod = 0.0;
         if (valid) { jb = B_j[ib]; if (NUMERIC) prod = a * B_a[ib]; }
-        unsigned grp = 0;
-        if (valid) grp = __match_any_sync(vm, jb);
-        const int leader = valid ? (__ffs(grp) - 1) : lane;
-        const bool is_leader = valid && leader == lane;
-        bool nw = false;
-        int slot = 0;
-        if (is_leader) slot = wt_insert<CAP>(keys, jb, &nw);
-        const unsigned newmask = __ballot_sync(FULL, nw);
-        if (NUMERIC) {
-          if (nw) {
-            const int pos = count + __popc(newmask & ltmask);
-            vals[slot] = pos; cols[pos] = jb; acc[pos] = 0.0;      // 0 + a*b == a*b: same as the first-touch store
-          }
-          slot = __shfl_sync(FULL, slot, leader);
-          __syncwarp();
-          const int rank = __popc(grp & ltmask);
-          int maxrank = valid ? __popc(grp) : 0;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) maxrank = max(maxrank, __shfl_xor_sync(FULL, maxrank, off));
-          for (int r = 0; r < maxrank; r++) {
-            if (valid && rank == r) acc[vals[slot]] += prod;
-            __syncwarp();
-          }
-        }
-        count += __popc(newmask);
-        __syncwarp();
+        fold(valid, jb, prod);
       }
     }
     if (over) {
