@@ -97,6 +97,7 @@ SIGNATURES = {
     "b200_dist_matrix_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "b200_dist_matrix_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_dist_matvec": (_i, [_vp, _vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_dist_relax_gs": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp]),
     "b200_dist_amg_setup": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_dist_amg_destroy": (_i, [_vp, _vp]),
     "b200_dist_amg_num_levels": (_i, [_vp]),
@@ -543,6 +544,10 @@ class DistMatrix:
 
     def matvec(self, alpha, x, beta, b, y):
         _chk(_lib.b200_dist_matvec(self.h.p, self.c.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def relax_gs(self, relax_type, blocks, f, u):
+        """hypre_BoomerAMGRelax 8/13/14 across ranks: halo of u, then Gauss-Seidel inside each block"""
+        _chk(_lib.b200_dist_relax_gs(self.h.p, self.c.p, self.p, relax_type, blocks, f.ptr, u.ptr))
 
     def destroy(self):
         if self.owned and self.p:

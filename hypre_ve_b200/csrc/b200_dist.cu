@@ -579,6 +579,25 @@ extern "C" int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_d
   return dist_spmv(h, c, M, d_x, d_y, 0, alpha, beta, d_b, nullptr);
 }
 
+// hypre_BoomerAMGRelax types 8/13/14 across ranks (par_relax.c:4340-5124): halo of u (job 1), then Gauss-Seidel
+// inside each of the rank's `blocks` blocks; everything outside a block -- other blocks, other ranks --
+// enters with its pre-sweep value.  l1 norms: option 4 (ams.c:3560-3625), computed here.
+extern "C" int b200_dist_relax_gs(b200_handle h, b200_comm c, b200_dist_matrix M, int relax_type, int blocks, const double *d_f,
+                                  double *d_u) {
+  if (!M || !M->L) B200_FAIL("dist_relax_gs: matrix not localized");
+  if (relax_type != 8 && relax_type != 13 && relax_type != 14) B200_FAIL("dist_relax_gs: relax types 8, 13, 14");
+  b200_csr A = M->L;
+  if (A->gs && b200_gs_plan_blocks(A->gs) != blocks) { B200_TRY(b200_gs_plan_destroy(h, A->gs)); A->gs = nullptr; }
+  if (!A->gs) B200_TRY(b200_gs_plan_create(h, A, blocks, &A->gs));
+  double *l1 = nullptr;
+  B200_TRY(b200_dalloc<double>(h, &l1, M->n));
+  B200_TRY(b200_l1_norms_blocks(h, A, 4, blocks, l1));
+  if (M->halo->ng || M->halo->n_send) B200_TRY(b200_halo_forward_f64(h, c, M->halo, d_u, d_u + M->n_owned_cols));
+  B200_TRY(b200_gs_relax(h, A->gs, A, relax_type, false, d_f, l1, d_u));
+  B200_TRY(b200_dfree(h, l1));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // distributed hierarchy
 // ------------------------------------------------------------------------------------------------
@@ -600,6 +619,8 @@ struct b200_dist_amg_s {
   std::vector<int> ge_starts;
   bool coarse_ge = false;
   double relax_wt = 1.0;
+  bool gs = false;                   // l1 hybrid Gauss-Seidel (8/13/14): Gauss-Seidel inside the rank's blocks,
+  int relax_down = 18, relax_up = 18, gs_blocks = 1;   // pre-sweep values across blocks and ranks (par_relax.c:4352-4372)
   double setup_ms = 0;
 };
 
@@ -715,7 +736,13 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   if (!prm || !A0) B200_FAIL("dist_amg_setup: null argument");
   if (b200_amg_get_int(prm, "CoarsenType") != 8 && b200_amg_get_int(prm, "CoarsenType") != 9)
     B200_FAIL("only PMIS (CoarsenType 8; measures are drawn as for 9 = partition independent) is implemented");
-  if (b200_amg_get_int(prm, "InterpType") != 6 || b200_amg_get_int(prm, "RelaxType") != 18 ||
+  const int rdown = b200_amg_get_int(prm, "RelaxType");
+  const int rup = b200_amg_get_int(prm, "RelaxTypeUp") >= 0 ? b200_amg_get_int(prm, "RelaxTypeUp") : rdown;
+  auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
+  if (!((rdown == 18 && rup == 18) || (is_l1gs(rdown) && is_l1gs(rup))))
+    B200_FAIL("multi-GPU RelaxType: 18 (l1-Jacobi) or the l1 hybrid Gauss-Seidel family 8/13/14");
+  if (rdown != 18 && b200_amg_get_real(prm, "RelaxWt") != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  if (b200_amg_get_int(prm, "InterpType") != 6 ||
       b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") != 0 ||
       b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
       !(b200_amg_get_int(prm, "ModuleRAP2") == 1 && b200_amg_get_int(prm, "RAP2") == 0))
@@ -730,6 +757,8 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   cudaEventRecord(e0, h->stream);
   b200_dist_amg amg = new b200_dist_amg_s();
   amg->relax_wt = b200_amg_get_real(prm, "RelaxWt");
+  amg->gs = rdown != 18; amg->relax_down = rdown; amg->relax_up = rup;
+  amg->gs_blocks = b200_amg_get_int(prm, "GSBlocks");
   dist_level L0;
   L0.A = A0; L0.n = A0->n;
   amg->lv.push_back(L0);
@@ -893,7 +922,13 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_CUDA(cudaMemsetAsync(L.U, 0, sizeof(double) * L.cap, h->stream));
     B200_CUDA(cudaMemsetAsync(L.T, 0, sizeof(double) * L.cap, h->stream));
     B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
-    B200_TRY(b200_l1_norms(h, L.A->L, 1, L.l1));     // offd entries are part of the merged row (ams.c:651-657)
+    // offd entries are part of the merged row (ams.c:651-657); option 4 counts them -- and the entries
+    // outside the Gauss-Seidel block of the row -- with weight 1/2 (ams.c:3560-3625)
+    B200_TRY(b200_l1_norms_blocks(h, L.A->L, amg->gs ? 4 : 1, amg->gs ? amg->gs_blocks : 1, L.l1));
+    if (amg->gs && (l < nl - 1 || L.A->global_rows > max_coarse)) {
+      if (L.A->L->gs && b200_gs_plan_blocks(L.A->L->gs) != amg->gs_blocks) { B200_TRY(b200_gs_plan_destroy(h, L.A->L->gs)); L.A->L->gs = nullptr; }
+      if (!L.A->L->gs) B200_TRY(b200_gs_plan_create(h, L.A->L, amg->gs_blocks, &L.A->L->gs));
+    }
     amg->vtemp_cap = std::max(amg->vtemp_cap, L.cap);
     // setup-form copies are no longer needed below level 0 (level 0's belongs to the caller)
   }
@@ -981,6 +1016,10 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
       if (L.n) B200_CUDA(cudaMemcpyAsync(U, amg->ge_f + ncg + amg->ge_starts[me], sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));
       return 0;
     }
+    if (amg->gs) {
+      if (L.A->L->gs) return b200_gs_relax(h, L.A->L->gs, L.A->L, amg->relax_down, true, F, L.l1, U);
+      return 0;
+    }
     if (L.n) {
       jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F, L.l1, U);
       B200_LAUNCH_CHECK();
@@ -991,6 +1030,29 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
   std::vector<const double *> F(nl);
   std::vector<double *> U(nl);
   F[0] = f;
+  if (amg->gs) {
+    // in-place hybrid Gauss-Seidel smoothing: halo of u (old values for everything off rank), then the sweep
+    auto relax = [&](dist_level &L, int type, const double *Fl, double *Ul, bool zero) -> int {
+      b200_dist_matrix M = L.A;
+      if (!zero && (M->halo->ng || M->halo->n_send)) B200_TRY(b200_halo_forward_f64(h, c, M->halo, Ul, Ul + M->n_owned_cols));
+      return b200_gs_relax(h, M->L->gs, M->L, type, zero, Fl, L.l1, Ul);
+    };
+    U[0] = u;
+    for (int l = 1; l < nl; l++) { F[l] = amg->lv[l].F; U[l] = amg->lv[l].U; }
+    for (int l = 0; l < nl - 1; l++) {
+      dist_level &L = amg->lv[l];
+      B200_TRY(relax(L, amg->relax_down, F[l], U[l], true));                                   // iterate is 0 on entry
+      B200_TRY(dist_spmv(h, c, L.A, U[l], amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
+      B200_TRY(dist_spmv(h, c, L.R, amg->Vtemp, amg->lv[l + 1].F, 0, 1.0, 0.0, nullptr, nullptr));
+    }
+    B200_TRY(coarse_solve(amg->lv[nl - 1], F[nl - 1], U[nl - 1]));
+    for (int l = nl - 2; l >= 0; l--) {
+      dist_level &L = amg->lv[l];
+      B200_TRY(dist_spmv(h, c, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));
+      B200_TRY(relax(L, amg->relax_up, F[l], U[l], false));
+    }
+    return 0;
+  }
   for (int l = 1; l < nl; l++) F[l] = amg->lv[l].F;
   for (int l = 0; l < nl - 1; l++) {
     dist_level &L = amg->lv[l];

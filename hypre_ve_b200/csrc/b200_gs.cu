@@ -253,7 +253,7 @@ __device__ __forceinline__ void gs_do_row(const RowRegs &r, int n, int ns, int n
       const int j = r.pj[k];
       double uj;
       if (j >= ns && j < ne) uj = u_s[j - ns];
-      else uj = (ZERO && j < n) ? 0.0 : old[j];
+      else uj = ZERO ? 0.0 : old[j];
       res -= r.pa[k] * uj;
     }
   }
@@ -261,7 +261,7 @@ __device__ __forceinline__ void gs_do_row(const RowRegs &r, int n, int ns, int n
     const int j = A_j[jj];
     double uj;
     if (j >= ns && j < ne) uj = u_s[j - ns];
-    else uj = (ZERO && j < n) ? 0.0 : old[j];
+    else uj = ZERO ? 0.0 : old[j];
     res -= A_a[jj] * uj;
   }
   u_s[r.i - ns] = CLASSIC ? res / r.di : u_s[r.i - ns] + res / r.di;
@@ -334,7 +334,7 @@ __global__ void gs_lane_kernel(int n, int T, int size, int rest, const int *__re
         const bool swept = (DIR > 0) ? (j < i) : (j > i);
         uj = (ZERO && !swept) ? 0.0 : u[j];
       } else {
-        uj = (ZERO && j < n) ? 0.0 : old[j];
+        uj = ZERO ? 0.0 : old[j];
       }
       res -= A_a[jj] * uj;
     }
@@ -382,7 +382,7 @@ int b200_gs_plan_create(b200_handle h, b200_csr A, int T, b200_gs_plan_s **out) 
   const char *fg = getenv("B200_GS_FORCE_GLOBAL");      // tests: "1" soft-barrier path, "2" CTA-per-block path
   if (P->maxblock <= GS_LANE_CAP && !(fg && (fg[0] == '1' || fg[0] == '2'))) {
     P->lane_path = true;
-    if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, n));
+    if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, (size_t)std::max(A->ncols, n)));
     return 0;
   }
   int *d_flag = nullptr, *indeg = nullptr, *level = nullptr, *fr[2] = {nullptr, nullptr}, *cnt = nullptr;
@@ -458,7 +458,7 @@ int b200_gs_plan_create(b200_handle h, b200_csr A, int T, b200_gs_plan_s **out) 
     B200_CUDA(cudaStreamSynchronize(h->stream));
     B200_TRY(b200_dalloc<int>(h, &P->ctr, (size_t)D + 1));
   }
-  if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, n));
+  if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, (size_t)std::max(A->ncols, n)));
   B200_TRY(b200_dfree(h, d_flag)); B200_TRY(b200_dfree(h, indeg)); B200_TRY(b200_dfree(h, level));
   B200_TRY(b200_dfree(h, fr[0])); B200_TRY(b200_dfree(h, fr[1])); B200_TRY(b200_dfree(h, cnt));
   if (Tp) B200_TRY(b200_csr_destroy(h, Tp));
@@ -477,11 +477,11 @@ int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool cl
   if (P->n == 0) return 0;
   if (!classic && !l1) B200_FAIL("gs sweep: l1 norms required for relax types 8/13/14");
   const double *old = u;
-  if (P->T > 1 && A->ncols > P->n) B200_FAIL("gs sweep: GSBlocks > 1 with ghost columns is not implemented (one block per rank)");
-  if (P->T > 1) {
+  if (P->T > 1) {                                        // pre-sweep copy of [owned | ghost]
+    const size_t w = (size_t)std::max(A->ncols, P->n);
     if (refresh_old) {
-      if (zero) B200_CUDA(cudaMemsetAsync(P->old, 0, sizeof(double) * (size_t)P->n, h->stream));
-      else B200_CUDA(cudaMemcpyAsync(P->old, u, sizeof(double) * (size_t)P->n, cudaMemcpyDeviceToDevice, h->stream));
+      if (zero) B200_CUDA(cudaMemsetAsync(P->old, 0, sizeof(double) * w, h->stream));
+      else B200_CUDA(cudaMemcpyAsync(P->old, u, sizeof(double) * w, cudaMemcpyDeviceToDevice, h->stream));
     }
     old = P->old;
   }

@@ -200,6 +200,11 @@ int b200_dist_matrix_download(b200_handle h, b200_dist_matrix A, int *h_i, int *
 /* y = alpha*A*x + beta*b; d_x must have room for local_rows + n_ghost doubles (ghosts are received in place) */
 int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_dist_matrix A, double *d_x, double beta,
                      const double *d_b, double *d_y);
+/* hypre_BoomerAMGRelax types 8 / 13 / 14 across ranks (par_relax.c:4340-5124): halo of u, then Gauss-Seidel
+ * inside each of the rank's `blocks` blocks with option-4 l1 norms (ams.c:3560-3625); d_u has room for
+ * local_rows + n_ghost doubles */
+int b200_dist_relax_gs(b200_handle h, b200_comm c, b200_dist_matrix A, int relax_type, int blocks, const double *d_f,
+                       double *d_u);
 /* hypre_BoomerAMGSetup across ranks; parameters are taken from a b200_amg object */
 int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg params, b200_dist_matrix A, b200_dist_amg *amg);
 int b200_dist_amg_destroy(b200_handle h, b200_dist_amg amg);

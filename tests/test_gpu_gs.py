@@ -33,11 +33,11 @@ def blocks_of(n, T):
     return out
 
 
-def seq_relax(ip, ix, a, f, d, u0, fwd, bwd, classic, T):
+def seq_relax(ip, ix, a, f, d, u0, fwd, bwd, classic, T, blocks=None):
     """the reference loop per thread block: res = f_i - sum a_ij (u_j in block | tmp_j outside) in storage
     order; u_i += res/l1_i | u_i = res/a_ii.  tmp is copied ONCE per call (also for the symmetric types)."""
     u, tmp = u0.copy(), u0.copy()
-    for ns, ne in blocks_of(len(ip) - 1, T):
+    for ns, ne in (blocks if blocks is not None else blocks_of(len(ip) - 1, T)):
         orders = ([range(ns, ne)] if fwd else []) + ([range(ne - 1, ns - 1, -1)] if bwd else [])
         for order in orders:
             for i in order:
@@ -58,11 +58,11 @@ def seq_relax(ip, ix, a, f, d, u0, fwd, bwd, classic, T):
     return u
 
 
-def l1_opt4(ip, ix, a, T):
+def l1_opt4(ip, ix, a, T, blocks=None):
     """hypre_ParCSRComputeL1NormsThreads option 4 (ams.c:3560-3625)"""
     n = len(ip) - 1
     out = np.zeros(n)
-    for ns, ne in blocks_of(n, T):
+    for ns, ne in (blocks if blocks is not None else blocks_of(n, T)):
         for i in range(ns, ne):
             s = d = 0.0
             for jj in range(ip[i], ip[i + 1]):
