@@ -111,15 +111,20 @@ def reference_arm(a):
         s, v, its = run_reference(n1, threads)
         t_set += s
         t_sol += v
-    scale = (N1 / n1) ** 3                    # AMG-PCG work is linear in the number of unknowns
+    # AMG-PCG work is linear in the number of unknowns; the N-GPU arm is weak-scaled (256^3 unknowns per GPU),
+    # so the same job on the host is N x 256^3 unknowns
+    scale = (N1 / n1) ** 3 * max(1, a.gpus)
     per_step = (t_set + t_sol) / a.steps * scale
-    sample = ("full workload (256^3) per step" if n1 == N1 else
-              "128^3 sample per step, seconds scaled by 8 (= unknown ratio) to the 256^3 workload")
+    sample = "%d^3 run per step on all host threads, seconds scaled by %g (= unknown ratio) to the %d x 256^3 workload" % (
+        n1, scale, max(1, a.gpus))
+    if n1 == N1 and a.gpus <= 1:
+        sample = "full workload (256^3) per step"
     line = {
         "impl": "reference", "metric": "boomeramg_pcg_setup_plus_solve_seconds", "value": per_step, "unit": "s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "impl": "reference hypre 2.20 (SX-Aurora fork) CPU path, OpenMP, sequential MPI stubs"},
+        "config": {"workload": WORKLOAD if a.gpus <= 1 else WORKLOAD.replace("256^3", "%d x 256^3 (weak-scaled)" % a.gpus),
+                   "impl": "reference hypre 2.20 (SX-Aurora fork) CPU path, OpenMP, sequential MPI stubs"},
         "setup_s": t_set / a.steps * scale, "solve_s": t_sol / a.steps * scale, "iterations": its,
         "cpu_baseline": {"value": per_step, "unit": "s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": per_step, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

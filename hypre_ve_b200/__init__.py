@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200_csr_dims": (_i, [_vp, _ip, _ip, _ip]),
     "b200_csr_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_csr_matvec": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_csr_matvecT": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_csr_sorted_copy": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200_csr_transpose": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200_csr_multiply": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_vec_fill": (_i, [_vp, _i, _d, _vp]),
@@ -217,6 +219,14 @@ class Csr:
 
     def matvec(self, alpha, x, beta, b, y):
         _chk(_lib.b200_csr_matvec(self.h.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def matvecT(self, alpha, x, beta, b, y):
+        _chk(_lib.b200_csr_matvecT(self.h.p, alpha, self.p, x.ptr, beta, b.ptr if b is not None else None, y.ptr))
+
+    def sorted_copy(self):
+        p = _vp()
+        _chk(_lib.b200_csr_sorted_copy(self.h.p, self.p, C.byref(p)))
+        return Csr(self.h, p)
 
     def transpose(self):
         p = _vp()

@@ -20,6 +20,7 @@ int b200_vec_dot_dev(b200_handle h, int n, const double *x, const double *y, dou
 
 struct b200_level {
   b200_csr A = nullptr;     // owned except level 0 (borrowed from the caller's ParCSR diag block)
+  b200_csr As = nullptr;    // solve-phase operator: A itself on level 0, a column-sorted copy on the coarse levels
   b200_csr P = nullptr;     // interpolation to this level from the next coarser one
   b200_csr R = nullptr;     // P^T
   b200_csr S = nullptr;     // kept only when KeepS
@@ -162,6 +163,7 @@ extern "C" int b200_amg_create(b200_amg *out) {
 static int free_levels(b200_handle h, b200_amg amg) {
   for (size_t l = 0; l < amg->lv.size(); l++) {
     b200_level &L = amg->lv[l];
+    if (L.As && L.As != L.A) B200_TRY(b200_csr_destroy(h, L.As));
     if (l > 0) B200_TRY(b200_csr_destroy(h, L.A));
     B200_TRY(b200_csr_destroy(h, L.P));
     B200_TRY(b200_csr_destroy(h, L.R));
@@ -308,8 +310,15 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   }
   // l1 norms: option 1 for relax 18, option 4 for 8/13/14 (:3018-3060); Gauss-Seidel level schedules
   tm.start();
+  static const bool no_sort = [] { const char *e = getenv("B200_NO_SORTED_COPY"); return e && e[0] == '1'; }();
   for (int l = 0; l < nl; l++) {
     b200_level &L = amg->lv[l];
+    L.As = L.A;
+    if (l > 0 && l < nl - 1 && !no_sort && (double)L.A->nnz > 12.0 * L.n) B200_TRY(b200_csr_sorted_copy(h, L.A, &L.As));
+    // streaming-SpMV plans for exactly the operators the cycle applies (setup products build none)
+    if (!L.As->blk_row) B200_TRY(b200_csr_build_plan(h, L.As));
+    if (L.P && !L.P->blk_row) B200_TRY(b200_csr_build_plan(h, L.P));
+    if (L.R && !L.R->blk_row) B200_TRY(b200_csr_build_plan(h, L.R));
     if (l < nl - 1 || !amg->coarse_ge) {
       if (!amg->gs || is_l1gs(rdown)) {
         B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
@@ -347,7 +356,7 @@ extern "C" int b200_amg_setup_times(b200_amg amg, double *t) {
 
 // One l1-Jacobi sweep u_out = u_in + w (f - A u_in) / l1   (ams.c:72-92, fused into one pass over A)
 static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const double *u_in, double *u_out) {
-  return b200_csr_spmv_epi(h, L.A, u_in, u_out, 1, w, 0.0, f, L.l1);
+  return b200_csr_spmv_epi(h, L.As, u_in, u_out, 1, w, 0.0, f, L.l1);
 }
 
 // One V(1,1) cycle (par_cycle.c:255-622). u_zero: the caller guarantees u == 0 on entry
@@ -367,7 +376,7 @@ static int amg_cycle_gs(b200_handle h, b200_amg amg, const double *f, double *u,
   for (int l = 0; l < nl - 1; l++) {
     b200_level &L = amg->lv[l];
     B200_TRY(gs_relax(h, L, amg->relax_down, F[l], U[l], l > 0 || u_zero));
-    B200_TRY(b200_csr_spmv_epi(h, L.A, U[l], amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));              // :549
+    B200_TRY(b200_csr_spmv_epi(h, L.As, U[l], amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));             // :549
     B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, amg->lv[l + 1].F, 0, 1.0, 0.0, nullptr, nullptr)); // :566
   }
   {
@@ -427,7 +436,7 @@ static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bo
     }
     U[l] = ucur;
     // Vtemp = F - A U (par_cycle.c:549) ; F_{l+1} = R Vtemp (:566)
-    B200_TRY(b200_csr_spmv_epi(h, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
+    B200_TRY(b200_csr_spmv_epi(h, L.As, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
     B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr));
   }
   // coarsest level

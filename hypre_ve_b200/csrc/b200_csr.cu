@@ -14,6 +14,7 @@
 //     writes y (axpby), the l1-Jacobi update, or the residual.
 //   HBM sees every matrix byte exactly once, fully coalesced, independent of row length.
 #include "b200_internal.h"
+#include <algorithm>
 
 namespace {
 
@@ -324,6 +325,7 @@ extern "C" int b200_csr_destroy(b200_handle h, b200_csr A) {
   B200_TRY(b200_dfree(h, A->blk_ent));
   B200_TRY(b200_dfree(h, A->blk_meta));
   B200_TRY(b200_gs_plan_destroy(h, A->gs));
+  if (A->T) B200_TRY(b200_csr_destroy(h, A->T));
   delete A;
   return 0;
 }
@@ -356,4 +358,63 @@ extern "C" int b200_csr_matvec(b200_handle h, double alpha, b200_csr A, const do
     return 0;
   }
   return b200_csr_spmv_epi(h, A, d_x, d_y, 0, alpha, beta, d_b, nullptr);
+}
+
+// y = alpha*A^T*x + beta*b.  hypre_CSRMatrixMatvecT (seq_mv/csr_matvec.c:424-668) scatters row by row; here
+// the transpose is formed once (stable counting-sort order = ascending source row, the order in which the
+// sequential scatter adds to y_j) and cached on the matrix, as hypre_ParCSRMatrixMatvecT does with
+// diagT / offdT when they exist (par_csr_matvec.c:553-597); the product is then the streaming SpMV.
+extern "C" int b200_csr_matvecT(b200_handle h, double alpha, b200_csr A, const double *d_x, double beta,
+                                const double *d_b, double *d_y) {
+  if (!A || !A->a) B200_FAIL("matvecT needs a matrix with values");
+  if (d_x == d_y) B200_FAIL("matvecT: x must not alias y");
+  if (!A->T) B200_TRY(b200_csr_transpose(h, A, &A->T));
+  return b200_csr_matvec(h, alpha, A->T, d_x, beta, d_b, d_y);
+}
+
+// ---- solve-phase copy with the entries of every row sorted by column --------------------------------------
+// The coarse Galerkin operators keep the reference's first-touch entry order (the next level's setup depends
+// on it, and the parity tests compare it).  For the solve phase that order is poison for the x gather: the
+// lanes working on neighbouring entries hit unrelated 128-byte lines and the L1 data pipe saturates at ~45 %
+// of the HBM roofline (profiles/r1_c: l1tex lsu wavefronts 92 %).  Sorting each row by column makes
+// neighbouring lanes read neighbouring x.  One warp per row, rank sort in shared memory.
+namespace {
+constexpr int SORT_CAP = 2048;     // longest row sorted; longer rows are copied as they are
+__global__ void __launch_bounds__(128)
+row_sort_copy_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                     int *__restrict__ S_j, double *__restrict__ S_a) {
+  __shared__ int keys[4][SORT_CAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = blockIdx.x * 4 + warp; r < n; r += gridDim.x * 4) {
+    const int b = A_i[r], len = A_i[r + 1] - b;
+    if (len > SORT_CAP) {
+      for (int k = lane; k < len; k += 32) { S_j[b + k] = A_j[b + k]; S_a[b + k] = A_a[b + k]; }
+      continue;
+    }
+    for (int k = lane; k < len; k += 32) keys[warp][k] = A_j[b + k];
+    __syncwarp();
+    for (int k = lane; k < len; k += 32) {
+      const int key = keys[warp][k];
+      int rank = 0;
+      for (int t = 0; t < len; t++) rank += (keys[warp][t] < key) || (keys[warp][t] == key && t < k);
+      S_j[b + rank] = key;
+      S_a[b + rank] = A_a[b + k];
+    }
+    __syncwarp();
+  }
+}
+}  // namespace
+
+extern "C" int b200_csr_sorted_copy(b200_handle h, b200_csr A, b200_csr *out) {
+  if (!A || !A->a) B200_FAIL("sorted copy: matrix with values required");
+  b200_csr S = nullptr;
+  B200_TRY(b200_csr_alloc(h, A->nrows, A->ncols, A->nnz, true, &S));
+  B200_CUDA(cudaMemcpyAsync(S->i, A->i, sizeof(int) * ((size_t)A->nrows + 1), cudaMemcpyDeviceToDevice, h->stream));
+  if (A->nrows) {
+    const int grid = std::min(b200_grid(A->nrows, 4), h->num_sm * 16);
+    row_sort_copy_kernel<<<grid, 128, 0, h->stream>>>(A->nrows, A->i, A->j, A->a, S->j, S->a);
+    B200_LAUNCH_CHECK();
+  }
+  *out = S;
+  return 0;
 }

@@ -29,6 +29,11 @@ struct b200_gs_plan_s {
   int nlevels = 0;            // depth of the deepest block
   bool block_path = false;
   bool lane_path = false;     // one thread per Gauss-Seidel block: no schedule needed
+  // lane path, sliced-ELL copy of A (slice = the 32 rows the lanes of a warp visit in the same step)
+  int maxm = 0;               // rows of the longest block
+  int *slice_ptr = nullptr;   // [nwarps * maxm + 1] first padded entry of every slice
+  int *sell_j = nullptr;      // column ids, -1 = padding
+  double *sell_a = nullptr;
   int maxblock = 0;
   int *perm = nullptr;        // rows sorted by (level,row) [global path] or (block,level,row) [block path]
   // global path
@@ -309,6 +314,80 @@ __global__ void gs_block_kernel(int n, int T, int size, int rest, const int *__r
   }
 }
 
+// ---- sliced-ELL copy for the lane path ---------------------------------------------------------------------
+// Warp w owns blocks 32w .. 32w+31 (lane l -> block 32w + l); in step k every lane visits row ns_l + k.
+// Slice (w, k) stores those 32 rows column-major: entry e of lane l at slice_ptr[w*maxm + k] + 32*e + l,
+// padded with column -1 to the longest of the 32 rows, so a warp's loads are fully coalesced.
+__device__ __forceinline__ void lane_block(int bk, int T, int size, int rest, int &ns, int &m) {
+  if (bk >= T) { ns = 0; m = 0; return; }
+  ns = bk < rest ? bk * (size + 1) : bk * size + rest;
+  m = size + (bk < rest ? 1 : 0);
+}
+__global__ void gs_sell_width_kernel(int nwarps, int maxm, int T, int size, int rest, const int *__restrict__ A_i,
+                                     int *__restrict__ width) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nwarps * maxm) { return; }
+  const int w = s / maxm, k = s % maxm;
+  int ns, m, len = 0;
+  lane_block(32 * w + lane, T, size, rest, ns, m);
+  if (k < m) len = A_i[ns + k + 1] - A_i[ns + k];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_xor_sync(0xffffffffu, len, off));
+  if (lane == 0) width[s] = 32 * len;
+  if (s == 0 && lane == 0) width[nwarps * maxm] = 0;
+}
+__global__ void gs_sell_fill_kernel(int nwarps, int maxm, int T, int size, int rest, const int *__restrict__ A_i,
+                                    const int *__restrict__ A_j, const double *__restrict__ A_a,
+                                    const int *__restrict__ slice_ptr, int *__restrict__ sj, double *__restrict__ sa) {
+  const int s = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (s >= nwarps * maxm) return;
+  const int w = s / maxm, k = s % maxm;
+  int ns, m;
+  lane_block(32 * w + lane, T, size, rest, ns, m);
+  const int base = slice_ptr[s], W = (slice_ptr[s + 1] - base) >> 5;
+  int b = 0, len = 0;
+  if (k < m) { b = A_i[ns + k]; len = A_i[ns + k + 1] - b; }
+  for (int e = 0; e < W; e++) {
+    sj[base + 32 * e + lane] = e < len ? A_j[b + e] : -1;
+    sa[base + 32 * e + lane] = e < len ? A_a[b + e] : 0.0;
+  }
+}
+// the sweep over the sliced copy: same arithmetic, same order as gs_lane_kernel
+template <int DIR, bool CLASSIC, bool ZERO>
+__global__ void gs_sell_kernel(int n, int T, int size, int rest, int maxm, const int *__restrict__ slice_ptr,
+                               const int *__restrict__ sj, const double *__restrict__ sa, const double *__restrict__ f,
+                               const double *__restrict__ l1, const double *old, double *u) {
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  int ns, m;
+  lane_block(32 * w + lane, T, size, rest, ns, m);
+  if (32 * w >= T) return;
+  const int ne = ns + m;
+  const int *sp = slice_ptr + (size_t)w * maxm;
+  for (int t = 0; t < m; t++) {
+    const int k = DIR > 0 ? t : m - 1 - t;
+    const int i = ns + k;
+    const int base = sp[k], W = (sp[k + 1] - base) >> 5;
+    const int *cj = sj + base + lane;
+    const double *ca = sa + base + lane;
+    const double di = CLASSIC ? ca[0] : l1[i];
+    if (di == 0.0) { if (ZERO) u[i] = 0.0; continue; }
+    double res = f[i];
+    for (int e = CLASSIC ? 1 : 0; e < W; e++) {
+      const int j = cj[32 * e];
+      if (j < 0) break;                                     // padding: the row is over
+      double uj;
+      if (j >= ns && j < ne) {
+        const bool swept = (DIR > 0) ? (j < i) : (j > i);
+        uj = (ZERO && !swept) ? 0.0 : u[j];
+      } else {
+        uj = ZERO ? 0.0 : old[j];
+      }
+      res -= ca[32 * e] * uj;
+    }
+    u[i] = CLASSIC ? res / di : (ZERO ? 0.0 : u[i]) + res / di;
+  }
+}
+
 // ---- lane path: one THREAD per Gauss-Seidel block ------------------------------------------------------------
 // With many small blocks the reference's own parallelisation maps one to one: thread b walks the rows of
 // block b in sweep order, reads its own earlier results back from u (program order makes them visible to
@@ -349,6 +428,7 @@ int b200_gs_plan_destroy(b200_handle h, b200_gs_plan_s *p) {
   B200_TRY(b200_dfree(h, p->perm)); B200_TRY(b200_dfree(h, p->level_off));
   B200_TRY(b200_dfree(h, p->chunks)); B200_TRY(b200_dfree(h, p->ctr));
   B200_TRY(b200_dfree(h, p->seg_off)); B200_TRY(b200_dfree(h, p->blk_seg)); B200_TRY(b200_dfree(h, p->old));
+  B200_TRY(b200_dfree(h, p->slice_ptr)); B200_TRY(b200_dfree(h, p->sell_j)); B200_TRY(b200_dfree(h, p->sell_a));
   delete p;
   return 0;
 }
@@ -383,6 +463,32 @@ int b200_gs_plan_create(b200_handle h, b200_csr A, int T, b200_gs_plan_s **out) 
   if (P->maxblock <= GS_LANE_CAP && !(fg && (fg[0] == '1' || fg[0] == '2'))) {
     P->lane_path = true;
     if (T > 1) B200_TRY(b200_dalloc<double>(h, &P->old, (size_t)std::max(A->ncols, n)));
+    const char *se = getenv("B200_GS_SELL");              // "0": plain CSR walk (tests compare both)
+    // measured at 256^3 (profiles/r1_e_gs_*.txt): the sliced copy wins for short blocks (<= 128 rows: many lanes,
+    // the CSR walk thrashes L1), the plain CSR walk for longer ones; "1" forces the sliced copy
+    if (T >= 32 && !(se && se[0] == '0') && (P->maxblock <= 128 || (se && se[0] == '1'))) {
+      const int nwarps = (T + 31) / 32, maxm = P->maxblock;
+      const long long nsl = (long long)nwarps * maxm;
+      if (nsl < (1LL << 30)) {
+        P->maxm = maxm;
+        B200_TRY(b200_dalloc<int>(h, &P->slice_ptr, (size_t)nsl + 1));
+        gs_sell_width_kernel<<<b200_grid((size_t)nsl, 8), 256, 0, h->stream>>>(nwarps, maxm, T, P->size, P->rest, A->i, P->slice_ptr);
+        B200_LAUNCH_CHECK();
+        B200_TRY(b200_exclusive_scan_inplace(h, P->slice_ptr, (size_t)nsl + 1));
+        int total = 0;
+        B200_CUDA(cudaMemcpyAsync(&total, P->slice_ptr + nsl, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        B200_CUDA(cudaStreamSynchronize(h->stream));
+        if (total < 0 || (double)total > 1.6 * (double)A->nnz + 1024.0) {        // padding too expensive: keep the CSR walk
+          B200_TRY(b200_dfree(h, P->slice_ptr)); P->slice_ptr = nullptr; P->maxm = 0;
+        } else {
+          B200_TRY(b200_dalloc<int>(h, &P->sell_j, (size_t)total + 32));
+          B200_TRY(b200_dalloc<double>(h, &P->sell_a, (size_t)total + 32));
+          gs_sell_fill_kernel<<<b200_grid((size_t)nsl, 8), 256, 0, h->stream>>>(nwarps, maxm, T, P->size, P->rest, A->i, A->j, A->a,
+                                                                                P->slice_ptr, P->sell_j, P->sell_a);
+          B200_LAUNCH_CHECK();
+        }
+      }
+    }
     return 0;
   }
   int *d_flag = nullptr, *indeg = nullptr, *level = nullptr, *fr[2] = {nullptr, nullptr}, *cnt = nullptr;
@@ -484,6 +590,22 @@ int b200_gs_sweep(b200_handle h, b200_gs_plan_s *P, b200_csr A, int dir, bool cl
       else B200_CUDA(cudaMemcpyAsync(P->old, u, sizeof(double) * w, cudaMemcpyDeviceToDevice, h->stream));
     }
     old = P->old;
+  }
+  if (P->lane_path && P->sell_j) {
+    const int nwarps = (P->T + 31) / 32;
+#define GS_SELL(D, C, Z)                                                                                                   \
+    gs_sell_kernel<D, C, Z><<<b200_grid(nwarps, 2), 64, 0, h->stream>>>(P->n, P->T, P->size, P->rest, P->maxm, P->slice_ptr, \
+                                                                         P->sell_j, P->sell_a, f, l1, old, u)
+    if (dir > 0) {
+      if (classic) { if (zero) GS_SELL(1, true, true); else GS_SELL(1, true, false); }
+      else         { if (zero) GS_SELL(1, false, true); else GS_SELL(1, false, false); }
+    } else {
+      if (classic) { if (zero) GS_SELL(-1, true, true); else GS_SELL(-1, true, false); }
+      else         { if (zero) GS_SELL(-1, false, true); else GS_SELL(-1, false, false); }
+    }
+#undef GS_SELL
+    B200_LAUNCH_CHECK();
+    return 0;
   }
   if (P->lane_path) {
 #define GS_LANE(D, C, Z)                                                                                                   \

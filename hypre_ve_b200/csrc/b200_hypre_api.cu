@@ -418,6 +418,16 @@ HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HY
   CALL(b200_parcsr_matvec(h, alpha, A->A, x->d, beta, y->d, y->d), "HYPRE_ParCSRMatrixMatvec");
   return g_error_flag;
 }
+HYPRE_Int HYPRE_ParCSRMatrixMatvecT(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y) {
+  if (!A) return err_arg(2);
+  if (!x) return err_arg(3);
+  if (!y) return err_arg(5);
+  NEED_HANDLE();
+  if (x == y) { fprintf(stderr, "hypre_b200: MatvecT needs x != y\n"); return err(HYPRE_ERROR_GENERIC); }
+  if (x->n != A->global_rows || y->n != A->global_cols) return err(HYPRE_ERROR_GENERIC);      // par_csr_matvec.c:420-440
+  CALL(b200_csr_matvecT(h, alpha, b200_parcsr_diag(A->A), x->d, beta, y->d, y->d), "HYPRE_ParCSRMatrixMatvecT");
+  return g_error_flag;
+}
 HYPRE_Int HYPRE_ParVectorCreate(MPI_Comm, HYPRE_BigInt global_size, HYPRE_BigInt *, HYPRE_ParVector *vector) {
   if (global_size < 0) return err_arg(2);
   hypre_ParVector_struct *v = new hypre_ParVector_struct();

@@ -47,6 +47,7 @@ struct b200_csr_s {
   int  max_row = 0;
   int  tile = 0;          // entries per tile the plan was cut with
   b200_gs_plan_s *gs = nullptr;   // built on first use by b200_relax_gs / the AMG setup
+  b200_csr_s *T = nullptr;        // explicit transpose, built on first b200_csr_matvecT (diagT/offdT of the reference)
 };
 
 struct b200_halo_s;   // multi-rank halo plan (b200_parcsr.cu)

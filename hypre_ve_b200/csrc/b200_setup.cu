@@ -838,7 +838,6 @@ int b200_extpi_interp_ex(b200_handle h, b200_csr A, b200_csr S, const int *d_cf,
   B200_TRY(b200_dfree(h, keys)); B200_TRY(b200_dfree(h, vals));
   B200_TRY(b200_dfree(h, plan.scan)); B200_TRY(b200_dfree(h, P_cnt));
   if (!d_f2c_in) B200_TRY(b200_dfree(h, f2c));
-  B200_TRY(b200_csr_build_plan(h, P));
   *out = P;
   return 0;
 }
@@ -875,7 +874,6 @@ extern "C" int b200_csr_transpose(b200_handle h, b200_csr A, b200_csr *out) {
     B200_TRY(b200_dfree(h, rows)); B200_TRY(b200_dfree(h, idx)); B200_TRY(b200_dfree(h, keys_out));
     B200_TRY(b200_dfree(h, perm)); B200_TRY(b200_dfree(h, tmp));
   }
-  if (T->a) B200_TRY(b200_csr_build_plan(h, T));
   *out = T;
   return 0;
 }
@@ -957,7 +955,6 @@ int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, i
   }
   B200_TRY(b200_dfree(h, keys)); B200_TRY(b200_dfree(h, vals));
   B200_TRY(b200_dfree(h, plan.scan)); B200_TRY(b200_dfree(h, C_cnt));
-  B200_TRY(b200_csr_build_plan(h, Cm));
   *out = Cm;
   return 0;
 }

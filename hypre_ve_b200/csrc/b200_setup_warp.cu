@@ -658,7 +658,6 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa)); B200_TRY(b200_dfree(h, cnt));
   if (!d_f2c_in) B200_TRY(b200_dfree(h, f2c));
   B200_TRY(b200_dfree(h, d_flag));
-  B200_TRY(b200_csr_build_plan(h, P));
   *out = P;
   *done = 1;
   return 0;
@@ -730,7 +729,6 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
   B200_SPGEMM_NUMERIC(2048, 256, 1)      // 257..1024 (the symbolic pass guarantees <= 1024)
 #undef B200_SPGEMM_NUMERIC
   B200_TRY(b200_dfree(h, cnt)); B200_TRY(b200_dfree(h, d_flag));
-  B200_TRY(b200_csr_build_plan(h, C));
   *out = C;
   *done = 1;
   return 0;

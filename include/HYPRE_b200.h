@@ -85,6 +85,8 @@ HYPRE_Int HYPRE_ParCSRMatrixGetLocalRange(HYPRE_ParCSRMatrix matrix, HYPRE_BigIn
 HYPRE_Int HYPRE_b200_ParCSRMatrixGetNumNonzeros(HYPRE_ParCSRMatrix matrix, long long *nnz);
 /* parcsr_mv/HYPRE_parcsr_matrix.c: y = alpha*A*x + beta*y */
 HYPRE_Int HYPRE_ParCSRMatrixMatvec(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y);
+/* y = alpha*A^T*x + beta*y (parcsr_mv/HYPRE_parcsr_matrix.c, par_csr_matvec.c:369-711) */
+HYPRE_Int HYPRE_ParCSRMatrixMatvecT(HYPRE_Complex alpha, HYPRE_ParCSRMatrix A, HYPRE_ParVector x, HYPRE_Complex beta, HYPRE_ParVector y);
 HYPRE_Int HYPRE_ParVectorCreate(MPI_Comm comm, HYPRE_BigInt global_size, HYPRE_BigInt *partitioning, HYPRE_ParVector *vector);
 HYPRE_Int HYPRE_ParVectorInitialize(HYPRE_ParVector vector);
 HYPRE_Int HYPRE_ParVectorSetConstantValues(HYPRE_ParVector vector, HYPRE_Complex value);

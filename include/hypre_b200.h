@@ -62,6 +62,14 @@ int b200_csr_download(b200_handle h, b200_csr A, int *h_i, int *h_j, double *h_a
  * device seam hypre_CSRMatrixMatvecDevice (seq_mv/csr_matvec_device.c:56-120). b may equal y. */
 int b200_csr_matvec(b200_handle h, double alpha, b200_csr A, const double *d_x,
                     double beta, const double *d_b, double *d_y);
+/* y = alpha*A^T*x + beta*b.   hypre_CSRMatrixMatvecT (seq_mv/csr_matvec.c:424-668), device seam
+ * hypre_CSRMatrixMatvecDevice(trans = 1).  The explicit transpose is built on first use and cached on A
+ * (the reference's diagT / offdT, par_csr_matvec.c:553-597). */
+int b200_csr_matvecT(b200_handle h, double alpha, b200_csr A, const double *d_x,
+                     double beta, const double *d_b, double *d_y);
+/* copy of A with the entries of every row sorted by column (hypre_CSRMatrixReorder's job for all columns):
+ * the solve phase applies the coarse Galerkin operators from such a copy, see DESIGN.md section 3 */
+int b200_csr_sorted_copy(b200_handle h, b200_csr A, b200_csr *S);
 /* AT = A^T with rows ordered by source row (stable counting sort semantics).
  * hypre_CSRMatrixTransposeHost (seq_mv/csr_matop.c:578-779) */
 int b200_csr_transpose(b200_handle h, b200_csr A, b200_csr *AT);

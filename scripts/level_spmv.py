@@ -13,7 +13,8 @@ tot_ms = 0
 for l in range(amg.num_levels):
     if only >= 0 and l != only:
         continue
-    for name, M in (("A", amg.level_A(l)), ("P", amg.level_P(l) if l < amg.num_levels - 1 else None)):
+    for name, M in (("A", amg.level_A(l)), ("Asorted", amg.level_A(l).sorted_copy() if l > 0 else None),
+                    ("P", amg.level_P(l) if l < amg.num_levels - 1 else None)):
         if M is None or not M.p:
             continue
         n, m, nnz = M.dims

@@ -106,14 +106,15 @@ def small_matrices():
 
 
 @pytest.mark.parametrize("path,T", [("auto", 1), ("global", 1), ("block", 1), ("block", 3), ("block", 40), ("global", 7),
-                                    ("auto", 3), ("auto", 40), ("auto", 100000)])
+                                    ("auto", 3), ("auto", 40), ("auto", 100000), ("csr", 40), ("csr", 100)])
 @pytest.mark.parametrize("relax_type", [13, 14, 8, 3, 4, 6])
 @pytest.mark.parametrize("name", ["sym_random", "nonsym_random", "chain", "lap7", "lap27", "coarse_level"])
 def test_single_sweep_is_the_sequential_loop_bit_for_bit(handle, monkeypatch, name, relax_type, path, T):
     """all three schedulers (global soft barriers / one CTA per Gauss-Seidel block / one thread per block),
     1 .. n blocks"""
     import hypre_ve_b200 as hb
-    monkeypatch.setenv("B200_GS_FORCE_GLOBAL", {"global": "1", "block": "2", "auto": "0"}[path])
+    monkeypatch.setenv("B200_GS_FORCE_GLOBAL", {"global": "1", "block": "2", "auto": "0", "csr": "0"}[path])
+    monkeypatch.setenv("B200_GS_SELL", "0" if path == "csr" else "1")    # thread-per-block over CSR / forced sliced ELL
     if name in ("lap7", "lap27"):
         A0 = hb.ParCsr.laplacian(handle, 9, 7, 8) if name == "lap7" else hb.ParCsr.laplacian27(handle, 7, 6, 5)
         ip, ix, a = A0.diag.download()

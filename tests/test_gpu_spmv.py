@@ -140,3 +140,25 @@ def test_spmv_full_size_linearity(handle):
     A.matvec(1.0, dxz, 0.0, None, y3)
     np.testing.assert_allclose(y3.numpy(), y1.numpy() + 2.0 * y2.numpy(), rtol=0, atol=1e-12)
     A.destroy()
+
+
+def test_matvecT_matches_sequential_scatter(handle):
+    """y = alpha A^T x + beta b (hypre_CSRMatrixMatvecT, csr_matvec.c:424-668) against the reference's
+    row-by-row scatter loop (1e-14: the SpMV kernel may split a row's sum over several lanes)"""
+    import scipy.sparse as sp
+    import hypre_ve_b200 as hb
+    rng = np.random.default_rng(4)
+    M = sp.random(900, 400, density=0.02, random_state=9, format="csr")
+    M.sort_indices()
+    x, b = rng.standard_normal(900), rng.standard_normal(400)
+    A = hb.Csr.from_host(handle, M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data)
+    dx, db, dy = handle.array(x), handle.array(b), handle.zeros(400)
+    A.matvecT(1.0, dx, 0.0, None, dy)
+    want = np.zeros(400)
+    for i in range(900):                               # csr_matvec.c:560-575 (one thread)
+        for jj in range(M.indptr[i], M.indptr[i + 1]):
+            want[M.indices[jj]] += M.data[jj] * x[i]
+    np.testing.assert_allclose(dy.numpy(), want, rtol=1e-14, atol=1e-14)
+    A.matvecT(-2.0, dx, 0.5, db, dy)
+    np.testing.assert_allclose(dy.numpy(), -2.0 * (M.T @ x) + 0.5 * b, rtol=1e-13, atol=1e-13)
+    A.destroy()
