@@ -1,0 +1,140 @@
+"""Full-size runs (BASELINE.json configs) on the GPU, checked against known answers recorded from the
+reference's own CPU build and through size-independent properties.
+
+Known answers were produced in the build container with
+    OMP_NUM_THREADS=8 oracle/_ref/ref_dump -n 256 256 256 -pmis -rlx 18 -mod_rap2 1 -keepT 1 -nodump
+    OMP_NUM_THREADS=8 oracle/_ref/ref_dump -n 128 128 128 -27pt -pmis -rlx 18 -mod_rap2 1 -keepT 1 -nodump
+    OMP_NUM_THREADS=8 oracle/_ref/ref_dump -n 128 128 128 -pmis -mod_rap2 1 -keepT 1 -nodump      (13/14 smoother, 8 blocks)
+(the 256^3 reference run takes 45 s on 8 cores; it is not repeated inside the test suite)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+CONFIG2 = dict(levels=[(16777216, 117047296), (5155128, 150640470), (700599, 48767931), (72913, 6595345), (8313, 750027),
+                       (978, 73488), (184, 10710), (32, 786), (6, 36)], its=24, rel=5.618903e-09)
+LAP27_128 = dict(levels=[(2097152, 55742968), (170851, 10198213), (20115, 1706045), (2385, 191827), (310, 18324), (58, 2500),
+                         (13, 163), (3, 9)], its=18, rel=2.951425e-09)
+
+
+def solve(handle, A, **params):
+    import hypre_ve_b200 as hb
+    amg = hb.Amg(handle, **params)
+    amg.setup(A)
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    sizes = [tuple(amg.level_A(l).dims[i] for i in (0, 2)) for l in range(amg.num_levels)]
+    return amg, b, x, its, rel, norms, sizes
+
+
+def test_config2_256_cubed_matches_reference_known_answer(handle):
+    """ij 3D 7-pt 256^3, PMIS + ext+i(Pmx 4) + l1-Jacobi: level table (rows, nnz of every A_l), iteration count
+    and final residual of the reference; plus properties that do not need the reference at this size"""
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian(handle, 256, 256, 256)
+    amg, b, x, its, rel, norms, sizes = solve(handle, A)
+    assert sizes == CONFIG2["levels"]
+    assert its == CONFIG2["its"]
+    assert abs(rel / CONFIG2["rel"] - 1) < 1e-6
+    assert norms[0] == 4096.0 and np.all(np.diff(norms[1:]) < 0)     # ||b|| = sqrt(256^3); 2-norm decreases after the first step
+    # true residual of the returned x: ||b - A x|| / ||b|| equals the recurrence residual PCG reports
+    n = A.local[0]
+    r = handle.zeros(n)
+    A.matvec(-1.0, x, 1.0, b, r)
+    true_rel = np.sqrt(handle.dot(r, r) / handle.dot(b, b))
+    assert abs(true_rel / rel - 1) < 1e-4
+    # Galerkin property on the finest level, without the reference: (A_1 e_c) == P^T (A_0 (P e_c)) for a random e_c
+    P = amg.level_P(0)
+    A1 = amg.level_A(1)
+    nc = A1.dims[0]
+    rng = np.random.default_rng(0)
+    ec = handle.array(rng.standard_normal(nc))
+    pe, ape, lhs, rhs = handle.zeros(n), handle.zeros(n), handle.zeros(nc), handle.zeros(nc)
+    P.matvec(1.0, ec, 0.0, None, pe)
+    A.diag.matvec(1.0, pe, 0.0, None, ape)
+    P.matvecT(1.0, ape, 0.0, None, rhs)
+    A1.matvec(1.0, ec, 0.0, None, lhs)
+    a, c = lhs.numpy(), rhs.numpy()
+    assert np.max(np.abs(a - c)) <= 1e-12 * np.max(np.abs(c))
+    # interpolation reproduces constants on interior rows (row sums of P are 1 where the row of A sums to 0)
+    one_c, p1 = handle.zeros(nc), handle.zeros(n)
+    handle.fill(one_c, 1.0)
+    P.matvec(1.0, one_c, 0.0, None, p1)
+    p1 = p1.numpy().reshape(256, 256, 256)
+    assert np.max(np.abs(p1[1:-1, 1:-1, 1:-1] - 1.0)) < 1e-13
+    amg.destroy(); A.destroy()
+
+
+def test_27pt_128_cubed_matches_reference_known_answer(handle):
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian27(handle, 128, 128, 128)
+    amg, b, x, its, rel, norms, sizes = solve(handle, A)
+    assert sizes == LAP27_128["levels"]
+    assert its == LAP27_128["its"] and abs(rel / LAP27_128["rel"] - 1) < 1e-6
+    amg.destroy(); A.destroy()
+
+
+def test_default_smoother_128_cubed_with_8_blocks_matches_reference(handle):
+    """library default 13-down / 14-up hybrid Gauss-Seidel, 8 blocks = the reference on 8 OpenMP threads"""
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian(handle, 128, 128, 128)
+    amg, b, x, its, rel, norms, sizes = solve(handle, A, RelaxType=13, RelaxTypeUp=14, GSBlocks=8)
+    assert its == 13 and abs(rel / 5.362439e-09 - 1) < 1e-5
+    amg.destroy(); A.destroy()
+
+
+def test_spmv_256_cubed_linearity_and_symmetry(handle):
+    """size-independent SpMV properties at the bench size: linearity, symmetry <Ax,y> == <x,Ay>, and the exact
+    row sums of the 7-pt operator (6 minus the number of neighbours)"""
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian(handle, 256, 256, 256)
+    n = A.local[0]
+    rng = np.random.default_rng(1)
+    x, y = handle.array(rng.standard_normal(n)), handle.array(rng.standard_normal(n))
+    ax, ay, axy, s = handle.zeros(n), handle.zeros(n), handle.zeros(n), handle.zeros(n)
+    A.matvec(1.0, x, 0.0, None, ax)
+    A.matvec(1.0, y, 0.0, None, ay)
+    assert abs(handle.dot(ax, y) - handle.dot(x, ay)) <= 1e-10 * abs(handle.dot(ax, y))
+    handle.copy(x, s); handle.axpy(2.5, y, s)                # s = x + 2.5 y
+    A.matvec(1.0, s, 0.0, None, axy)
+    handle.axpy(-1.0, ax, axy); handle.axpy(-2.5, ay, axy)
+    assert np.sqrt(handle.dot(axy, axy)) <= 1e-12 * np.sqrt(handle.dot(ax, ax))
+    one, a1 = handle.zeros(n), handle.zeros(n)
+    handle.fill(one, 1.0)
+    A.matvec(1.0, one, 0.0, None, a1)
+    g = a1.numpy().reshape(256, 256, 256)
+    idx = np.arange(256)
+    nb = sum(((idx > 0).astype(int) + (idx < 255).astype(int)).reshape(sh) for sh in ((256, 1, 1), (1, 256, 1), (1, 1, 256)))
+    assert np.array_equal(g, 6.0 - nb)
+    A.destroy()
+
+
+def test_degenerate_inputs(handle):
+    """edge cases the reference handles: tiny grids that never coarsen, 1-D chains, a zero right-hand side, and the
+    singular 1 x 1 x 1 operator (A = [0]: the reference flags "Zero sdotp value in PCG", pcg.c:516-521)"""
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian(handle, 1, 1, 1)
+    amg = hb.Amg(handle)
+    amg.setup(A)
+    b1 = handle.zeros(1); handle.fill(b1, 1.0)
+    with pytest.raises(hb.B200Error, match="Zero sdotp"):
+        handle.pcg(A, amg, b1, handle.zeros(1), tol=1e-8, max_iter=10)
+    amg.destroy(); A.destroy()
+    for dims in ((1, 1, 2), (1, 1, 7), (40, 1, 1), (3, 3, 1)):
+        A = hb.ParCsr.laplacian(handle, *dims)
+        amg = hb.Amg(handle)
+        amg.setup(A)
+        n = A.local[0]
+        b = handle.zeros(n); handle.fill(b, 1.0)
+        x = handle.zeros(n)
+        its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+        ip, ix, a = A.diag.download()
+        M = sp.csr_matrix((a, ix, ip), shape=(n, n))
+        assert np.linalg.norm(M @ x.numpy() - 1.0) <= 1e-7 * np.sqrt(n), dims
+        z = handle.zeros(n)
+        its0, rel0, _ = handle.pcg(A, amg, z, x, tol=1e-8, max_iter=100)      # b == 0 -> x = b (pcg.c:403-416)
+        assert its0 == 0 and np.all(x.numpy() == 0.0)
+        amg.destroy(); A.destroy()
