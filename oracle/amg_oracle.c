@@ -137,7 +137,11 @@ static double hrand(void)
 
 /* ---- PMIS: parcsr_ls/par_coarsen.c:2159-2700, CF_init 0, one rank; measures from
  *      par_indepset.c:44-59 (seed 2747, one draw per row in row order) ---- */
-static int *pmis(const csr_t *S)
+static int *pmis_init(const csr_t *S, int cf_init);
+static int *pmis(const csr_t *S) { return pmis_init(S, 0); }
+/* cf_init 3 (second PMIS of aggressive coarsening, par_amg_setup.c:1253): isolated rows become C points
+ * (:2322-2326) and the first sweep skips the independent-set selection (`if (!CF_init || iter)`, :2420) */
+static int *pmis_init(const csr_t *S, int cf_init)
 {
    int n = S->n, i, k, jS;
    double *m = (double *) xcalloc(n, sizeof(double));
@@ -148,11 +152,14 @@ static int *pmis(const csr_t *S)
    for (i = 0; i < n; i++)
    {
       cf[i] = 0;
-      if (S->i[i + 1] - S->i[i] == 0) { cf[i] = -3; m[i] = 0; } else graph[gsize++] = i;
+      if (S->i[i + 1] - S->i[i] == 0) { cf[i] = (cf_init == 3) ? 1 : -3; m[i] = 0; } else graph[gsize++] = i;
    }
+   int iter = 0;
    while (gsize > 0)
    {
       int ig;
+      if (!cf_init || iter)
+      {
       for (ig = 0; ig < gsize; ig++) { i = graph[ig]; if (m[i] > 1) cf[i] = 1; }
       for (ig = 0; ig < gsize; ig++)
       {
@@ -164,6 +171,8 @@ static int *pmis(const csr_t *S)
                if (m[j] > 1) { if (m[i] > m[j]) cf[j] = 0; else if (m[j] > m[i]) cf[i] = 0; }
             }
       }
+      }
+      iter++;
       for (ig = 0; ig < gsize; ig++)
       {
          i = graph[ig];
@@ -387,6 +396,147 @@ typedef struct { int nl; csr_t A[MAXLEV], P[MAXLEV], R[MAXLEV], S[MAXLEV]; int *
                  double *F[MAXLEV], *U[MAXLEV], *V; double *ge; int ge_n; } amg_t;
 
 /* ---- setup loop: parcsr_ls/par_amg_setup.c:889-2890 for coarsen 8 / interp 6 / mod_rap2 1 ---- */
+/* ---- aggressive coarsening (par_amg_setup.c:1239-1256, :1590-1605), one rank ------------------------------ */
+/* hypre_BoomerAMGCreate2ndSHost, num_paths 1 (par_strength.c:2326-2400 count, :2620-2700 fill): row ic of S2
+ * (coarse point i1) lists, in first-touch order, the C points among the strong neighbours i2 of i1 and among
+ * the strong neighbours of every such i2 (C or F), except ic itself */
+static csr_t create2ndS(const csr_t *S, const int *cf, int *nc_out)
+{
+   int n = S->n, i, ic, jj1, jj2, nc = 0, nnz = 0, pass;
+   int *f2c = (int *) xmalloc(sizeof(int) * n), *c2f = (int *) xmalloc(sizeof(int) * n);
+   for (i = 0; i < n; i++) { f2c[i] = -1; if (cf[i] > 0) { f2c[i] = nc; c2f[nc++] = i; } }
+   int *mark = (int *) xmalloc(sizeof(int) * (nc ? nc : 1));
+   csr_t C; memset(&C, 0, sizeof C);
+   for (pass = 0; pass < 2; pass++)
+   {
+      if (pass) { C = csr_new(nc, nc, nnz, 0); }
+      for (i = 0; i < nc; i++) mark[i] = -1;
+      nnz = 0;
+      for (ic = 0; ic < nc; ic++)
+      {
+         int i1 = c2f[ic], row0 = nnz;
+         if (pass) C.i[ic] = nnz;
+         for (jj1 = S->i[i1]; jj1 < S->i[i1 + 1]; jj1++)
+         {
+            int i2 = S->j[jj1];
+            if (cf[i2] > 0)
+            {
+               int idx = f2c[i2];
+               if (mark[idx] < row0) { mark[idx] = nnz; if (pass) C.j[nnz] = idx; nnz++; }
+            }
+            for (jj2 = S->i[i2]; jj2 < S->i[i2 + 1]; jj2++)
+            {
+               int i3 = S->j[jj2];
+               if (cf[i3] > 0)
+               {
+                  int idx = f2c[i3];
+                  if (idx != ic && mark[idx] < row0) { mark[idx] = nnz; if (pass) C.j[nnz] = idx; nnz++; }
+               }
+            }
+         }
+      }
+      if (pass) C.i[nc] = nnz;
+   }
+   free(f2c); free(c2f); free(mark);
+   *nc_out = nc;
+   return C;
+}
+/* hypre_BoomerAMGBuildMultipass (par_multi_interp.c:16-2061), one rank, weight_option 0, no truncation.
+ * pass 0 = C points (identity rows); pass 1 = F points with a strong C neighbour: the strong C entries of the
+ * row of A in A's order, scaled by alfa = -sum_N / (sum_C * a_ii) (:1600-1660); pass p >= 2 = points with a strong
+ * neighbour of pass p-1: sum over those neighbours j (A's order) of a_ij * (row j of P), columns in first-touch
+ * order, sum_C / sum_N accumulated product by product, same scaling (:1770-1860). At most 9 passes (:102). */
+static csr_t multipass(const csr_t *A, const csr_t *S, int *cf, int *ncoarse_out)
+{
+   int n = A->n, i, j, k, nc = 0, pass, npass, remaining = 0;
+   int *f2c = (int *) xmalloc(sizeof(int) * n), *assigned = (int *) xmalloc(sizeof(int) * n);
+   for (i = 0; i < n; i++)
+   {
+      f2c[i] = -1; assigned[i] = -1;
+      if (cf[i] == 1) { f2c[i] = nc++; assigned[i] = 0; } else if (cf[i] == -1) remaining++;
+   }
+   /* pass numbers (:404-510) */
+   for (i = 0; i < n; i++) if (cf[i] == -1)
+      for (j = S->i[i]; j < S->i[i + 1]; j++) if (cf[S->j[j]] == 1) { assigned[i] = 1; }
+   for (i = 0; i < n; i++) if (assigned[i] == 1) remaining--;
+   pass = 2;
+   while (remaining && pass < 10)
+   {
+      for (i = 0; i < n; i++) if (cf[i] == -1 && assigned[i] == -1)
+         for (j = S->i[i]; j < S->i[i + 1]; j++) if (assigned[S->j[j]] == pass - 1) { assigned[i] = pass; break; }
+      for (i = 0; i < n; i++) if (assigned[i] == pass) remaining--;
+      pass++;
+   }
+   npass = pass;
+   /* rows are built pass by pass into per-row buffers */
+   int **rj = (int **) xcalloc(n, sizeof(int *)); double **ra = (double **) xcalloc(n, sizeof(double *));
+   int *rl = (int *) xcalloc(n, sizeof(int));
+   int *marker = (int *) xmalloc(sizeof(int) * n), *pos = (int *) xmalloc(sizeof(int) * (nc ? nc : 1)), *pm = (int *) xmalloc(sizeof(int) * (nc ? nc : 1));
+   for (i = 0; i < n; i++) marker[i] = -1;
+   for (i = 0; i < nc; i++) pm[i] = -1;
+   double alfa = 1.0;
+   for (i = 0; i < n; i++) if (cf[i] == 1)
+   { rj[i] = (int *) xmalloc(sizeof(int)); ra[i] = (double *) xmalloc(sizeof(double)); rj[i][0] = f2c[i]; ra[i][0] = 1.0; rl[i] = 1; }
+   for (i = 0; i < n; i++) if (assigned[i] == 1)
+   {
+      int len = 0; double sum_C = 0, sum_N = 0;
+      for (j = S->i[i]; j < S->i[i + 1]; j++) if (cf[S->j[j]] == 1) { marker[S->j[j]] = i; len++; }
+      rj[i] = (int *) xmalloc(sizeof(int) * (len ? len : 1)); ra[i] = (double *) xmalloc(sizeof(double) * (len ? len : 1));
+      len = 0;
+      for (j = A->i[i] + 1; j < A->i[i + 1]; j++)
+      {
+         int j1 = A->j[j];
+         if (cf[j1] != -3) sum_N += A->a[j];
+         if (marker[j1] == i) { ra[i][len] = A->a[j]; rj[i][len++] = f2c[j1]; sum_C += A->a[j]; }
+      }
+      rl[i] = len;
+      double diagonal = A->a[A->i[i]];
+      if (sum_C * diagonal != 0) alfa = -sum_N / (sum_C * diagonal);
+      for (j = 0; j < len; j++) ra[i][j] *= alfa;
+   }
+   for (pass = 2; pass < npass; pass++)
+      for (i = 0; i < n; i++) if (assigned[i] == pass)
+      {
+         int len = 0, cap = 0; double sum_C = 0, sum_N = 0;
+         for (j = S->i[i]; j < S->i[i + 1]; j++) if (assigned[S->j[j]] == pass - 1) { marker[S->j[j]] = i; cap += rl[S->j[j]]; }
+         rj[i] = (int *) xmalloc(sizeof(int) * (cap ? cap : 1)); ra[i] = (double *) xmalloc(sizeof(double) * (cap ? cap : 1));
+         for (j = A->i[i] + 1; j < A->i[i + 1]; j++)
+         {
+            int j1 = A->j[j];
+            if (marker[j1] == i)
+               for (k = 0; k < rl[j1]; k++)
+               {
+                  int k1 = rj[j1][k];
+                  if (pm[k1] != i) { pm[k1] = i; pos[k1] = len; rj[i][len] = k1; ra[i][len] = 0; len++; }
+                  alfa = A->a[j] * ra[j1][k];
+                  ra[i][pos[k1]] += alfa;
+                  sum_C += alfa; sum_N += alfa;
+               }
+            else if (cf[j1] != -3) sum_N += A->a[j];
+         }
+         rl[i] = len;
+         double diagonal = A->a[A->i[i]];
+         if (sum_C * diagonal != 0) alfa = -sum_N / (sum_C * diagonal);
+         for (j = 0; j < len; j++) ra[i][j] *= alfa;
+      }
+   int nnz = 0;
+   for (i = 0; i < n; i++) nnz += rl[i];
+   csr_t P = csr_new(n, nc, nnz, 1);
+   nnz = 0;
+   for (i = 0; i < n; i++)
+   {
+      P.i[i] = nnz;
+      for (j = 0; j < rl[i]; j++) { P.j[nnz] = rj[i][j]; P.a[nnz++] = ra[i][j]; }
+      free(rj[i]); free(ra[i]);
+   }
+   P.i[n] = nnz;
+   for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;               /* :2030-2036 */
+   free(rj); free(ra); free(rl); free(marker); free(pos); free(pm); free(f2c); free(assigned);
+   *ncoarse_out = nc;
+   return P;
+}
+
+static int g_agg_nl = 0;
 static int g_relax_down = 18, g_relax_up = 18;   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
 static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
 {
@@ -397,9 +547,18 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    {
       csr_t S = strength(&g->A[l], theta, mrs);
       int *cf = pmis(&S), n = g->A[l].n, nc = 0;
+      if (l < g_agg_nl)
+      {  /* second coarsening on the distance-two graph of the C points, then CorrectCFMarker (par_strength.c:2957-2974) */
+         int nc1 = 0, cnt = 0;
+         csr_t S2 = create2ndS(&S, cf, &nc1);
+         int *cfn = pmis_init(&S2, 3);
+         for (i = 0; i < n; i++) if (cf[i] > 0) { if (cf[i] == 1) cf[i] = cfn[cnt++]; else { cf[i] = 1; cnt++; } }
+         csr_free(&S2); free(cfn);
+      }
       for (i = 0; i < n; i++) if (cf[i] == 1) nc++;
       if (nc == 0 || nc == n) { csr_free(&S); free(cf); break; }
-      g->P[l] = extpi(&g->A[l], &S, cf, pmax, &nc);
+      if (l < g_agg_nl) g->P[l] = multipass(&g->A[l], &S, cf, &nc);
+      else g->P[l] = extpi(&g->A[l], &S, cf, pmax, &nc);
       for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;            /* par_lr_interp.c:1888-1894 */
       g->cf[l] = cf; g->S[l] = S;
       g->R[l] = transpose(&g->P[l]);                                  /* par_csr_triplemat.c:874-876 */
@@ -548,6 +707,7 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-pmis") || !strcmp(argv[i], "-nodump")) { }
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-gs_blocks")) g_gs_blocks = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-agg_nl")) g_agg_nl = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
