@@ -79,6 +79,9 @@ SIGNATURES = {
     "b200_strength": (_i, [_vp, _vp, _d, _d, C.POINTER(_vp)]),
     "b200_pmis": (_i, [_vp, _vp, _i, _vp]),
     "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
+    "b200_create_2nd_s": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_agg_coarsen": (_i, [_vp, _vp, _i, _vp]),
+    "b200_multipass_interp": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
     "b200_l1_norms_blocks": (_i, [_vp, _vp, _i, _i, _vp]),
     "b200_relax_gs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
@@ -426,6 +429,20 @@ class Handle:
     def extpi_interp(self, A, S, cf, trunc_factor=0.0, max_elmts=4):
         p = _vp()
         _chk(_lib.b200_extpi_interp(self.p, A.p, S.p, cf.ptr, trunc_factor, max_elmts, C.byref(p)))
+        return Csr(self, p)
+
+    def create_2nd_s(self, S, cf):
+        p = _vp()
+        _chk(_lib.b200_create_2nd_s(self.p, S.p, cf.ptr, C.byref(p)))
+        return Csr(self, p)
+
+    def agg_coarsen(self, S, cf, seed=2747):
+        """second PMIS on the distance-two graph + CorrectCFMarker; cf is updated in place"""
+        _chk(_lib.b200_agg_coarsen(self.p, S.p, seed, cf.ptr))
+
+    def multipass_interp(self, A, S, cf):
+        p = _vp()
+        _chk(_lib.b200_multipass_interp(self.p, A.p, S.p, cf.ptr, C.byref(p)))
         return Csr(self, p)
 
     def l1_norms(self, A, option=1, blocks=1):

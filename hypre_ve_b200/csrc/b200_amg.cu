@@ -17,6 +17,8 @@ int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int
                       double beta, const double *b, const double *d);
 int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int *d_cf, int *iterations);
 int b200_vec_dot_dev(b200_handle h, int n, const double *x, const double *y, double *d_out);
+extern "C" int b200_agg_coarsen(b200_handle h, b200_csr S, int seed, int *d_cf);
+extern "C" int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int *d_cf, b200_csr *P);
 
 struct b200_level {
   b200_csr A = nullptr;     // owned except level 0 (borrowed from the caller's ParCSR diag block)
@@ -220,7 +222,9 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   amg->gs = rdown != 18;
   amg->relax_down = rdown; amg->relax_up = rup;
   if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
-  if (ip["AggNumLevels"] != 0) B200_FAIL("aggressive coarsening is not implemented on the B200 path");
+  if (ip["AggNumLevels"] < 0) B200_FAIL("AggNumLevels must be >= 0");
+  // aggressive levels: second PMIS on the distance-two graph + multipass interpolation (agg_interp_type 4, the
+  // reference default; agg_trunc_factor = agg_P_max_elmts = 0, num_paths 1), par_amg_setup.c:1239-1256, :1590-1605
   if (ip["NumSweeps"] != 1 || ip["CycleType"] != 1) B200_FAIL("only V(1,1) cycles are implemented");
   if (ip["NumFunctions"] != 1) B200_FAIL("only scalar problems (NumFunctions 1)");
   if (!(ip["ModuleRAP2"] == 1 && ip["RAP2"] == 0))
@@ -253,6 +257,8 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     B200_TRY(b200_dalloc<int>(h, &cf, fine_size));
     tm.start();
     B200_TRY(b200_pmis_rows(h, S, seed, 0, cf, nullptr));  // :1114
+    const bool aggressive = level < ip["AggNumLevels"];
+    if (aggressive) B200_TRY(b200_agg_coarsen(h, S, seed, cf));   // :1239-1256 + CorrectCFMarker :1592
     amg->times[1] += tm.stop();
     B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
     count_c_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf, d_count);
@@ -267,7 +273,8 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     }
     tm.start();
     b200_csr P = nullptr;
-    B200_TRY(b200_extpi_interp(h, L.A, S, cf, trunc, pmax, &P));   // :1989
+    if (aggressive) B200_TRY(b200_multipass_interp(h, L.A, S, cf, &P));   // :1601
+    else B200_TRY(b200_extpi_interp(h, L.A, S, cf, trunc, pmax, &P));     // :1989
     amg->times[2] += tm.stop();
     fix_cf_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf);
     B200_LAUNCH_CHECK();

@@ -182,14 +182,14 @@ __global__ void colcount_kernel(int nnz, const int *__restrict__ S_j, int *__res
   if (k < nnz) atomicAdd(&cnt[S_j[k]], 1);
 }
 __global__ void pmis_init_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ colcnt, int seed,
-                                 long long first_row, double *__restrict__ measure, int *__restrict__ cf) {
+                                 long long first_row, double *__restrict__ measure, int *__restrict__ cf, int cf_init = 0) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   // measure = #influences + hypre_Rand()   (par_indepset.c:56-59: i-th local row takes the (i+1)-th draw)
   int s = lcg_at(seed, (unsigned long long)(first_row + i + 1));
   double m = (double)colcnt[i] + ((double)s / 2147483647.0);
-  if (S_i[i + 1] - S_i[i] == 0) {   // isolated point: SF_PT, measure 0  (par_coarsen.c:2316-2328, CF_init 0)
-    cf[i] = -3;
+  if (S_i[i + 1] - S_i[i] == 0) {   // isolated point: SF_PT, measure 0; C_PT when CF_init is 3 (par_coarsen.c:2316-2328)
+    cf[i] = (cf_init == 3) ? 1 : -3;
     m = 0.0;
   } else {
     cf[i] = 0;
@@ -615,7 +615,15 @@ extern "C" int b200_strength(b200_handle h, b200_csr A, double theta, double max
   return 0;
 }
 
+int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row, int cf_init, int *d_cf, int *iterations);
 int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int *d_cf, int *iterations) {
+  return b200_pmis_rows_init(h, S, seed, first_row, 0, d_cf, iterations);
+}
+// cf_init 0: hypre_BoomerAMGCoarsenPMIS(S, A, 0, ...); cf_init 3: the second coarsening of aggressive coarsening
+// (par_amg_setup.c:1253): isolated rows become C points and the first sweep does not pick an independent set
+// (`if (!CF_init || iter)`, par_coarsen.c:2420)
+int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row, int cf_init, int *d_cf, int *iterations) {
+  if (cf_init != 0 && cf_init != 3) B200_FAIL("pmis: CF_init 0 or 3");
   const int n = S->nrows;
   if (iterations) *iterations = 0;
   if (n == 0) return 0;
@@ -631,7 +639,7 @@ int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int
     colcount_kernel<<<b200_grid(S->nnz, 256), 256, 0, h->stream>>>(S->nnz, S->j, colcnt);
     B200_LAUNCH_CHECK();
   }
-  pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf);
+  pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf, cf_init);
   B200_LAUNCH_CHECK();
   int iter = 0;
   while (true) {
@@ -642,10 +650,12 @@ int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int
     B200_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
     if (count == 0) break;                          // :2399-2407
-    pmis_mark_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, measure, d_cf);
-    B200_LAUNCH_CHECK();
-    pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf);
-    B200_LAUNCH_CHECK();
+    if (!cf_init || iter) {
+      pmis_mark_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, measure, d_cf);
+      B200_LAUNCH_CHECK();
+      pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf);
+      B200_LAUNCH_CHECK();
+    }
     pmis_setcf_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, ingraph, measure, d_cf, cf2);
     B200_LAUNCH_CHECK();
     B200_CUDA(cudaMemcpyAsync(d_cf, cf2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));

@@ -146,6 +146,16 @@ int b200_pmis(b200_handle h, b200_csr S, int seed, int *d_cf);
  * hypre_BoomerAMGInterpTruncation (par_interp.c:2718 -> par_csr_matrix.c:2671-3060) */
 int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf,
                       double trunc_factor, int max_elmts, b200_csr *P);
+/* aggressive coarsening (par_amg_setup.c:1239-1256, :1590-1605; AMG parameter "AggNumLevels"):
+ * hypre_BoomerAMGCreate2ndS, num_paths 1 (par_strength.c:1729-2918): S2 = distance-two strength graph on the C points
+ * of d_cf, pattern only, first-touch column order */
+int b200_create_2nd_s(b200_handle h, b200_csr S, const int *d_cf, b200_csr *S2);
+/* second coarsening: PMIS on S2 with CF_init 3 (par_coarsen.c:2322-2326, :2420) + hypre_BoomerAMGCorrectCFMarker
+ * (par_strength.c:2957-2974); d_cf in: marker of the first PMIS, out: corrected marker */
+int b200_agg_coarsen(b200_handle h, b200_csr S, int seed, int *d_cf);
+/* hypre_BoomerAMGBuildMultipass (par_multi_interp.c:16-2061), weight_option 0, no truncation; SF points (-3) in d_cf
+ * are folded into F on return as the reference does */
+int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int *d_cf, b200_csr *P);
 /* hypre_ParCSRComputeL1Norms (ams.c:571-760), options 1 and 4 */
 int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
 /* the same with the reference's thread blocks (hypre_ParCSRComputeL1NormsThreads, ams.c:3398-3650): option 4
