@@ -134,27 +134,23 @@ def reference_arm(a):
     return 0
 
 
-GRIDS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
-
-
 def main_dist(a, rank, world, local_rank):
     """N > 1: row-partitioned BoomerAMG-PCG, 256^3 unknowns per GPU (weak scaling)."""
     import torch
     import torch.distributed as dist
     import hypre_ve_b200 as hb
+    from hypre_ve_b200 import launch
 
-    if world not in GRIDS:
-        raise SystemExit("supported GPU counts: 1, 2, 4, 8")
-    P, Q, R = GRIDS[world]
+    try:
+        P, Q, R = launch.process_grid(world)
+    except ValueError as e:
+        raise SystemExit(str(e))
     n1 = a.n
     nx, ny, nz = n1 * P, n1 * Q, n1 * R
     h = hb.Handle(local_rank)
     # NCCL communicator of the library: rank 0 creates the id, torch.distributed broadcasts it
-    idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
-    if rank == 0:
-        idt.copy_(torch.frombuffer(bytearray(hb.Comm.nccl_unique_id()), dtype=torch.uint8))
-    dist.broadcast(idt, 0)
-    comm = hb.Comm.nccl(h, world, rank, bytes(idt.cpu().numpy().tobytes()))
+    uid = launch.broadcast_bytes(hb.Comm.nccl_unique_id() if rank == 0 else b"", 0, 128, "cuda")
+    comm = hb.Comm.nccl(h, world, rank, uid)
 
     def barrier():
         dist.barrier()
@@ -219,12 +215,9 @@ def main_dist(a, rank, world, local_rank):
     spmv_ms = h.timer_stop_ms() / reps
     sampler.stop_flag = True
     sampler.join()
-    per = torch.tensor([t_set / a.steps, t_sol / a.steps, e2e_ms / a.steps, spmv_ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(per, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([float(n), float(nnz)], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    set_s, sol_s, e2e_s, spmv_ms = per[0].item() / 1e3, per[1].item() / 1e3, per[2].item() / 1e3, per[3].item()
-    gn, gnnz = tot[0].item(), tot[1].item()
+    per = launch.reduce_over_ranks([t_set / a.steps, t_sol / a.steps, e2e_ms / a.steps, spmv_ms], "max", "cuda")
+    gn, gnnz = launch.reduce_over_ranks([float(n), float(nnz)], "sum", "cuda")
+    set_s, sol_s, e2e_s, spmv_ms = per[0] / 1e3, per[1] / 1e3, per[2] / 1e3, per[3]
     spmv_bytes = 12.0 * gnnz + 4.0 * (gn + world) + 16.0 * gn
     peak, peak_src = peaks()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9

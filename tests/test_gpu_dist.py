@@ -242,3 +242,20 @@ def test_dist_amg_pcg_with_hybrid_gauss_seidel(handle, nranks, grid, dims, T):
     else:
         assert abs(res[0]["its"] - its) <= 3, (res[0]["its"], its)
     amg.destroy(); A.destroy()
+
+
+def test_launch_helper_agrees_with_the_library_partition():
+    """hypre_ve_b200.launch (host arithmetic, covered on CPU by tests/test_launch_gloo.py) describes the same
+    row partition the library generates"""
+    import hypre_ve_b200 as hb
+    from hypre_ve_b200 import launch
+    dims, grid, nranks = (13, 12, 9), (2, 2, 1), 4
+
+    def fn(r, h, c):
+        A = hb.DistMatrix.laplacian(h, c, *dims, *grid, 7)
+        inf = A.info
+        return inf["local_rows"], inf["first_row"]
+    res = run_ranks(nranks, fn)
+    for r, (rows, first) in enumerate(res):
+        box, f0 = launch.local_box(r, dims, grid)
+        assert rows == box[0] * box[1] * box[2] and first == f0
