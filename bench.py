@@ -258,6 +258,8 @@ def main():
     if a.impl == "reference":
         return reference_arm(a)
 
+    # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import hypre_ve_b200 as hb
