@@ -36,8 +36,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N1 = 256                       # config 2 grid edge
-REF_ARGS = ["-pmis", "-rlx", "18", "-mod_rap2", "1", "-keepT", "1", "-nodump"]
-WORKLOAD = "ij 3D 7-pt Laplacian 256^3 BoomerAMG-PCG, PMIS + ext+i(Pmx 4) interp + l1-Jacobi, tol 1e-8"
+# N = 1: the driver's own flags for config 2, `ij -n 256 256 256 -solver 1 -pmis -rlx 18` (Galerkin product in the library's
+# default fused order, ModuleRAP2 0: 22 iterations).  N > 1: the row-partitioned path implements the modularized product
+# (-mod_rap2 1), so both arms use it there.
+REF_ARGS = ["-pmis", "-rlx", "18", "-keepT", "1", "-nodump"]
+REF_ARGS_DIST = ["-pmis", "-rlx", "18", "-mod_rap2", "1", "-keepT", "1", "-nodump"]
+WORKLOAD = ("ij 3D 7-pt Laplacian 256^3 BoomerAMG-PCG, PMIS + ext+i(Pmx 4) interp + l1-Jacobi, tol 1e-8 "
+            "(ij -n 256 256 256 -solver 1 -pmis -rlx 18)")
 
 
 def peaks():
@@ -82,13 +87,13 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(n1, threads):
+def run_reference(n1, threads, dist_flags=False):
     """One setup+solve of the reference CPU build; returns (setup_s, solve_s, iterations)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
     if not os.path.exists(exe):
         raise RuntimeError("oracle/_ref/ref_dump missing: run __graft_entry__.build() where /root/reference exists")
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false")
-    out = subprocess.run([exe, "-n", str(n1), str(n1), str(n1)] + REF_ARGS, env=env, capture_output=True, text=True,
+    out = subprocess.run([exe, "-n", str(n1), str(n1), str(n1)] + (REF_ARGS_DIST if dist_flags else REF_ARGS), env=env, capture_output=True, text=True,
                          check=True).stdout
     m = re.search(r"iterations=(\d+) relres=(\S+) setup_s=(\S+) solve_s=(\S+)", out)
     return float(m.group(3)), float(m.group(4)), int(m.group(1))
@@ -100,15 +105,16 @@ def reference_arm(a):
         return 0
     threads = host_threads()
     # bounded sample: probe with 128^3, then use the full 256^3 workload only if K+W steps fit ~4 minutes
-    s0, v0, _ = run_reference(128, threads)
+    df = a.gpus > 1
+    s0, v0, _ = run_reference(128, threads, df)
     est_full = 8.5 * (s0 + v0)
     n1 = N1 if est_full * (a.steps + a.warmup) < 240 else 128
     for _ in range(a.warmup):
-        run_reference(n1, threads)
+        run_reference(n1, threads, df)
     t_set = t_sol = 0.0
     its = 0
     for _ in range(a.steps):
-        s, v, its = run_reference(n1, threads)
+        s, v, its = run_reference(n1, threads, df)
         t_set += s
         t_sol += v
     # AMG-PCG work is linear in the number of unknowns; the N-GPU arm is weak-scaled (256^3 unknowns per GPU),
@@ -294,7 +300,7 @@ def main():
     d2h = hx.nbytes
 
     def step_resident():
-        amg = hb.Amg(h)
+        amg = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
         h.timer_start()
         amg.setup(A)
         s_ms = h.timer_stop_ms()
@@ -311,7 +317,7 @@ def main():
         A2 = hb.ParCsr.from_host(h, hi, hj, ha)
         b2 = h.array(hb_)
         x2 = h.zeros(n)
-        amg = hb.Amg(h)
+        amg = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
         amg.setup(A2)
         its, rel, _ = h.pcg(A2, amg, b2, x2, tol=1e-8, max_iter=100)
         hb._chk(hb._lib.b200_memcpy_d2h(h.p, hb._np_ptr(hx), x2.ptr, hx.nbytes))

@@ -227,8 +227,9 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   // reference default; agg_trunc_factor = agg_P_max_elmts = 0, num_paths 1), par_amg_setup.c:1239-1256, :1590-1605
   if (ip["NumSweeps"] != 1 || ip["CycleType"] != 1) B200_FAIL("only V(1,1) cycles are implemented");
   if (ip["NumFunctions"] != 1) B200_FAIL("only scalar problems (NumFunctions 1)");
-  if (!(ip["ModuleRAP2"] == 1 && ip["RAP2"] == 0))
-    B200_FAIL("only the modularized Galerkin product (ModuleRAP2 1, RAP2 0: hypre_ParCSRMatrixRAPKT) is implemented");
+  if (ip["RAP2"] != 0 || (ip["ModuleRAP2"] != 0 && ip["ModuleRAP2"] != 1))
+    B200_FAIL("Galerkin product: ModuleRAP2 1 (hypre_ParCSRMatrixRAPKT, R(AP)) or ModuleRAP2 0 (the fused "
+              "hypre_BoomerAMGBuildCoarseOperatorKT order, (RA)P) with RAP2 0");
   B200_TRY(free_levels(h, amg));
   for (double &t : amg->times) t = 0;
   PhaseTimer tm(h), total(h);
@@ -281,16 +282,23 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     L.cf = cf;
     L.P = P;
     if (keepS) L.S = S; else B200_TRY(b200_csr_destroy(h, S));
-    // Galerkin product, hypre_ParCSRMatrixRAPKTHost single-rank branch (par_csr_triplemat.c:872-888):
-    //   Q = A*P ; RT = P^T ; C = RT*Q
+    // Galerkin product.  ModuleRAP2 1: hypre_ParCSRMatrixRAPKTHost single-rank branch (par_csr_triplemat.c:872-888):
+    //   Q = A*P ; RT = P^T ; C = RT*Q.   ModuleRAP2 0 (library default): hypre_BoomerAMGBuildCoarseOperatorKT forms
+    //   row ic of R*A first (par_rap.c:1640-1700) and multiplies it by P with the diagonal entry created first
+    //   (:1546-1553, :1790-1857), i.e. the same two Gustavson products associated the other way: C = (RT*A)*P
     tm.start();
     b200_csr R = nullptr;
     B200_TRY(b200_csr_transpose(h, P, &R));
     amg->times[4] += tm.stop();
     tm.start();
     b200_csr Q = nullptr, AH = nullptr;
-    B200_TRY(b200_csr_multiply(h, L.A, P, &Q));
-    B200_TRY(b200_csr_multiply(h, R, Q, &AH));
+    if (ip["ModuleRAP2"] == 1) {
+      B200_TRY(b200_csr_multiply(h, L.A, P, &Q));
+      B200_TRY(b200_csr_multiply(h, R, Q, &AH));
+    } else {
+      B200_TRY(b200_csr_multiply(h, R, L.A, &Q));
+      B200_TRY(b200_csr_multiply(h, Q, P, &AH));
+    }
     B200_TRY(b200_csr_destroy(h, Q));
     amg->times[5] += tm.stop();
     L.R = R;

@@ -536,7 +536,7 @@ static csr_t multipass(const csr_t *A, const csr_t *S, int *cf, int *ncoarse_out
    return P;
 }
 
-static int g_agg_nl = 0;
+static int g_agg_nl = 0, g_mod_rap2 = 0;
 static int g_relax_down = 18, g_relax_up = 18;   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
 static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
 {
@@ -562,9 +562,19 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
       for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;            /* par_lr_interp.c:1888-1894 */
       g->cf[l] = cf; g->S[l] = S;
       g->R[l] = transpose(&g->P[l]);                                  /* par_csr_triplemat.c:874-876 */
-      csr_t Q = multiply(&g->A[l], &g->P[l]);
-      g->A[l + 1] = multiply(&g->R[l], &Q);
-      csr_free(&Q);
+      if (g_mod_rap2)
+      {  /* hypre_ParCSRMatrixRAPKT: R (A P), par_csr_triplemat.c:872-888 */
+         csr_t Q = multiply(&g->A[l], &g->P[l]);
+         g->A[l + 1] = multiply(&g->R[l], &Q);
+         csr_free(&Q);
+      }
+      else
+      {  /* hypre_BoomerAMGBuildCoarseOperatorKT (the library default): row ic of R A is formed first
+            (par_rap.c:1640-1700), then multiplied by P with the diagonal entry created first (:1546-1553, :1790-1857) */
+         csr_t Q = multiply(&g->R[l], &g->A[l]);
+         g->A[l + 1] = multiply(&Q, &g->P[l]);
+         csr_free(&Q);
+      }
       l++;
       if (l == MAXLEV - 1 || nc <= max_coarse) break;
    }
@@ -708,7 +718,8 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-gs_blocks")) g_gs_blocks = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-agg_nl")) g_agg_nl = atoi(argv[++i]);
-      else if (!strcmp(argv[i], "-mod_rap2") || !strcmp(argv[i], "-keepT")) { ++i; }
+      else if (!strcmp(argv[i], "-mod_rap2")) g_mod_rap2 = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-keepT")) { ++i; }
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
    double v[4];

@@ -216,7 +216,7 @@ def test_vcycle_matches_reference_preconditioner(handle):
 def test_unsupported_configurations_fail_loudly(handle):
     import hypre_ve_b200 as hb
     A = hb.ParCsr.laplacian(handle, 8, 8, 8)
-    for k, v in [("CoarsenType", 10), ("InterpType", 0), ("RelaxType", 16), ("AggNumLevels", -1), ("ModuleRAP2", 0)]:
+    for k, v in [("CoarsenType", 10), ("InterpType", 0), ("RelaxType", 16), ("AggNumLevels", -1), ("RAP2", 1)]:
         amg = hb.Amg(handle)
         amg.set(k, v)
         with pytest.raises(hb.B200Error):
@@ -245,3 +245,29 @@ def test_general_hbm_scratch_path_is_identical(handle, monkeypatch):
                 pi, pj, pa, _ = refio.csr(d, "P", l)
                 assert np.array_equal(i, pi) and np.array_equal(j, pj) and np.array_equal(a, pa), (force, "P", l)
         amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("args", [["-n", 24, 20, 18], ["-n", 16, 16, 16, "-27pt"], ["-n", 20, 20, 20, "-c", 1, 1, 0.001],
+                                  ["-n", 30, 30, 30, "-agg_nl", 1]])
+def test_default_fused_galerkin_product_order(handle, args):
+    """ModuleRAP2 0 = hypre_BoomerAMGBuildCoarseOperatorKT, the reference's default: (R A) P.  Hierarchy bit-exact,
+    same iteration count as the reference run WITHOUT -mod_rap2 1"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-pmis", "-rlx", 18])
+    nx, ny, nz = args[1:4]
+    A = hb.ParCsr.laplacian27(handle, nx, ny, nz) if "-27pt" in args else \
+        hb.ParCsr.laplacian(handle, nx, ny, nz, c=tuple(args[5:8]) if "-c" in args else (1.0, 1.0, 1.0))
+    amg = hb.Amg(handle, ModuleRAP2=0, AggNumLevels=(1 if "-agg_nl" in args else 0))
+    amg.setup(A)
+    assert amg.num_levels == nlev(d)
+    for l in range(nlev(d)):
+        i, j, a = amg.level_A(l).download()
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), l
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4])
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    amg.destroy(); A.destroy()

@@ -133,6 +133,17 @@ def test_diagonal_scaled_pcg_matches_reference_driver(exe):
     assert its == rits and abs(rel / rrel - 1) < 1e-6
 
 
+def test_driver_default_galerkin_product(exe):
+    """no -mod_rap2 flag: the driver default (fused hypre_BoomerAMGBuildCoarseOperatorKT order)"""
+    flags = ["-n", "50", "50", "50", "-solver", "1", "-pmis", "-rlx", "18"]
+    rc, out = run([exe, "-laplacian"] + flags)
+    assert rc == 0, out
+    its, rel = result(out)
+    assert its == 15 and abs(rel / 4.192356e-09 - 1) < 1e-6          # SURVEY.md 8c known answer
+    if os.path.exists(REF_IJ):
+        assert (its, ) == ref_result(flags)[:1]
+
+
 def test_out_of_scope_configuration_is_rejected_loudly(exe):
     """HMIS coarsening (the driver default) is not on the B200 path: Setup must fail, not fall back"""
     rc, out = run([exe, "-laplacian", "-n", "8", "8", "8", "-solver", "1", "-rlx", "18", "-mod_rap2", "1"])

@@ -14,6 +14,10 @@ pytestmark = pytest.mark.gpu
 
 CONFIG2 = dict(levels=[(16777216, 117047296), (5155128, 150640470), (700599, 48767931), (72913, 6595345), (8313, 750027),
                        (978, 73488), (184, 10710), (32, 786), (6, 36)], its=24, rel=5.618903e-09)
+# the driver's own default (no -mod_rap2): SURVEY.md section 6 / 8c table for config 2
+#     OMP_NUM_THREADS=8 ij -laplacian -n 256 256 256 -solver 1 -pmis -rlx 18     -> 22 its, 9.472469e-09
+CONFIG2_DEFAULT = dict(levels=[(16777216, 117047296), (5155128, 150640470), (700599, 48767907), (72905, 6594273), (8290, 748618),
+                               (1003, 77151), (185, 12217), (37, 1131), (8, 64)], its=22, rel=9.472469e-09)
 LAP27_128 = dict(levels=[(2097152, 55742968), (170851, 10198213), (20115, 1706045), (2385, 191827), (310, 18324), (58, 2500),
                          (13, 163), (3, 9)], its=18, rel=2.951425e-09)
 
@@ -65,6 +69,17 @@ def test_config2_256_cubed_matches_reference_known_answer(handle):
     P.matvec(1.0, one_c, 0.0, None, p1)
     p1 = p1.numpy().reshape(256, 256, 256)
     assert np.max(np.abs(p1[1:-1, 1:-1, 1:-1] - 1.0)) < 1e-13
+    amg.destroy(); A.destroy()
+
+
+def test_config2_with_the_driver_default_galerkin_product(handle):
+    """`ij -n 256 256 256 -solver 1 -pmis -rlx 18` as the driver runs it (fused (R A) P product): the survey's table"""
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.laplacian(handle, 256, 256, 256)
+    amg, b, x, its, rel, norms, sizes = solve(handle, A, ModuleRAP2=0)
+    assert sizes == CONFIG2_DEFAULT["levels"]
+    assert its == CONFIG2_DEFAULT["its"] and abs(rel / CONFIG2_DEFAULT["rel"] - 1) < 1e-6
+    assert abs(norms[1] / 5.263800e+04 - 1) < 1e-6 and abs(norms[2] / 3.108875e+04 - 1) < 1e-6     # first residuals, SURVEY 8c
     amg.destroy(); A.destroy()
 
 
