@@ -36,13 +36,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N1 = 256                       # config 2 grid edge
-# N = 1: the driver's own flags for config 2, `ij -n 256 256 256 -solver 1 -pmis -rlx 18` (Galerkin product in the library's
-# default fused order, ModuleRAP2 0: 22 iterations).  N > 1: the row-partitioned path implements the modularized product
-# (-mod_rap2 1), so both arms use it there.
+# the driver's own flags for config 2, `ij -n 256 256 256 -solver 1 -pmis -rlx 18`: Galerkin product in the library's
+# default fused order (ModuleRAP2 0; 22 iterations at 256^3), on one GPU and across ranks alike
 REF_ARGS = ["-pmis", "-rlx", "18", "-keepT", "1", "-nodump"]
-REF_ARGS_DIST = ["-pmis", "-rlx", "18", "-mod_rap2", "1", "-keepT", "1", "-nodump"]
+REF_ARGS_DIST = REF_ARGS
 WORKLOAD = ("ij 3D 7-pt Laplacian 256^3 BoomerAMG-PCG, PMIS + ext+i(Pmx 4) interp + l1-Jacobi, tol 1e-8 "
             "(ij -n 256 256 256 -solver 1 -pmis -rlx 18)")
+
+
+def spmv_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if absent)"""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "spmv_traffic.json")))["traffic_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def peaks():
@@ -167,7 +174,7 @@ def main_dist(a, rank, world, local_rank):
     n, nnz = inf["local_rows"], inf["local_nnz"]
     b = A.vector(1.0)
     x = A.vector(0.0)
-    prm = hb.Amg(h)
+    prm = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
 
     def step():
         amg = hb.DistAmg(h, comm, prm, A)
@@ -382,7 +389,7 @@ def main():
         "spmv_gbs": achieved, "spmv_ms": spmv_ms,
         "roofline": {"bound": "hbm", "kernel": "spmv_pipe_kernel<1,2> (y = A0*x, 256^3 7-pt)", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                     "algorithmic_bytes_per_launch": spmv_bytes, "traffic": None},
+                     "algorithmic_bytes_per_launch": spmv_bytes, "traffic": spmv_traffic()},
         "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),

@@ -745,13 +745,14 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   if (b200_amg_get_int(prm, "InterpType") != 6 ||
       b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") != 0 ||
       b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
-      !(b200_amg_get_int(prm, "ModuleRAP2") == 1 && b200_amg_get_int(prm, "RAP2") == 0))
+      b200_amg_get_int(prm, "RAP2") != 0 || (b200_amg_get_int(prm, "ModuleRAP2") != 0 && b200_amg_get_int(prm, "ModuleRAP2") != 1))
     B200_FAIL("unsupported BoomerAMG configuration on the B200 path (see b200_amg_setup)");
   const int R = b200_comm_size(c), me = b200_comm_rank(c);
   const double theta = b200_amg_get_real(prm, "StrongThreshold"), mrs = b200_amg_get_real(prm, "MaxRowSum");
   const double trunc = b200_amg_get_real(prm, "TruncFactor");
   const int pmax = b200_amg_get_int(prm, "PMaxElmts"), max_levels = b200_amg_get_int(prm, "MaxLevels");
   const int max_coarse = b200_amg_get_int(prm, "MaxCoarseSize"), seed = b200_amg_get_int(prm, "Seed");
+  const int mod_rap2 = b200_amg_get_int(prm, "ModuleRAP2");
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
@@ -885,19 +886,43 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     b200_csr Rg = nullptr;
     B200_TRY(dist_transpose(h, c, L.P, cstarts, &Rg));
     L.R = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_row, n, A->global_rows, A->row_starts, Rg);
-    b200_csr Pext = nullptr, Pbig = nullptr, Qg = nullptr;
-    B200_TRY(fetch_rows(h, c, A->halo, Pg, &Pext));             // hypre_ParCSRMatrixExtractBExt(P, A)
-    B200_TRY(stack_rows(h, Pg, Pext, &Pbig));
-    B200_TRY(b200_csr_destroy(h, Pext));
-    B200_TRY(b200_csr_multiply_ex(h, A->L, Pbig, 0, 0, (int)coarse_size, &Qg));
-    B200_TRY(b200_csr_destroy(h, Pbig));
-    B200_TRY(dist_localize(h, c, L.R));                         // ghosts of R = remote fine rows
-    b200_csr Qext = nullptr, Qbig = nullptr, AHg = nullptr;
-    B200_TRY(fetch_rows(h, c, L.R->halo, Qg, &Qext));
-    B200_TRY(stack_rows(h, Qg, Qext, &Qbig));
-    B200_TRY(b200_csr_destroy(h, Qext)); B200_TRY(b200_csr_destroy(h, Qg));
-    B200_TRY(b200_csr_multiply_ex(h, L.R->L, Qbig, 1, cstarts[me], (int)coarse_size, &AHg));
-    B200_TRY(b200_csr_destroy(h, Qbig));
+    b200_csr AHg = nullptr;
+    if (mod_rap2) {
+      // hypre_ParCSRMatrixRAPKT: Q = A*P with ghost rows of P, C = P^T * Q
+      b200_csr Pext = nullptr, Pbig = nullptr, Qg = nullptr;
+      B200_TRY(fetch_rows(h, c, A->halo, Pg, &Pext));             // hypre_ParCSRMatrixExtractBExt(P, A)
+      B200_TRY(stack_rows(h, Pg, Pext, &Pbig));
+      B200_TRY(b200_csr_destroy(h, Pext));
+      B200_TRY(b200_csr_multiply_ex(h, A->L, Pbig, 0, 0, (int)coarse_size, &Qg));
+      B200_TRY(b200_csr_destroy(h, Pbig));
+      B200_TRY(dist_localize(h, c, L.R));                         // ghosts of R = remote fine rows
+      b200_csr Qext = nullptr, Qbig = nullptr;
+      B200_TRY(fetch_rows(h, c, L.R->halo, Qg, &Qext));
+      B200_TRY(stack_rows(h, Qg, Qext, &Qbig));
+      B200_TRY(b200_csr_destroy(h, Qext)); B200_TRY(b200_csr_destroy(h, Qg));
+      B200_TRY(b200_csr_multiply_ex(h, L.R->L, Qbig, 1, cstarts[me], (int)coarse_size, &AHg));
+      B200_TRY(b200_csr_destroy(h, Qbig));
+    } else {
+      // the library default, hypre_BoomerAMGBuildCoarseOperatorKT (par_rap.c): row ic of R*A first, then times P with
+      // the diagonal entry created first -- (R*A)*P, rows of A and P fetched from their owners in global entry order
+      B200_TRY(dist_localize(h, c, L.R));
+      b200_csr Aext = nullptr, Abig = nullptr, RAg = nullptr;
+      B200_TRY(fetch_rows(h, c, L.R->halo, A->G, &Aext));
+      B200_TRY(stack_rows(h, A->G, Aext, &Abig));
+      B200_TRY(b200_csr_destroy(h, Aext));
+      B200_TRY(b200_csr_multiply_ex(h, L.R->L, Abig, 0, 0, A->global_cols, &RAg));
+      B200_TRY(b200_csr_destroy(h, Abig));
+      b200_dist_matrix RAd = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_col, A->n_owned_cols, A->global_cols,
+                                      A->col_starts, RAg);
+      B200_TRY(dist_localize(h, c, RAd));
+      b200_csr Pext = nullptr, Pbig = nullptr;
+      B200_TRY(fetch_rows(h, c, RAd->halo, Pg, &Pext));
+      B200_TRY(stack_rows(h, Pg, Pext, &Pbig));
+      B200_TRY(b200_csr_destroy(h, Pext));
+      B200_TRY(b200_csr_multiply_ex(h, RAd->L, Pbig, 1, cstarts[me], (int)coarse_size, &AHg));
+      B200_TRY(b200_csr_destroy(h, Pbig));
+      B200_TRY(b200_dist_matrix_destroy(h, RAd));
+    }
     dist_level Ln;
     Ln.A = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, cstarts[me], nc, (int)coarse_size, cstarts, AHg);
     B200_TRY(dist_localize(h, c, Ln.A));

@@ -55,14 +55,14 @@ def gather(parts):
     return (np.concatenate(I).astype(np.int32), np.concatenate([p[2] for p in parts]), np.concatenate([p[3] for p in parts]))
 
 
-def dist_case(nranks, grid, dims, stencil=7, solve=True):
+def dist_case(nranks, grid, dims, stencil=7, solve=True, **params):
     import hypre_ve_b200 as hb
     nx, ny, nz = dims
     P, Q, R = grid
 
     def fn(r, h, c):
         A = hb.DistMatrix.laplacian(h, c, nx, ny, nz, P, Q, R, stencil)
-        prm = hb.Amg(h)
+        prm = hb.Amg(h, **params)
         amg = hb.DistAmg(h, c, prm, A)
         lv = []
         for l in range(amg.num_levels):
@@ -83,10 +83,10 @@ def dist_case(nranks, grid, dims, stencil=7, solve=True):
     return run_ranks(nranks, fn)
 
 
-def single_gpu_on(handle, i, j, a):
+def single_gpu_on(handle, i, j, a, **params):
     import hypre_ve_b200 as hb
     A = hb.ParCsr.from_host(handle, i, j, a)
-    amg = hb.Amg(handle)
+    amg = hb.Amg(handle, **params)
     amg.setup(A)
     lv = []
     for l in range(amg.num_levels):
@@ -113,11 +113,23 @@ def single_gpu_on(handle, i, j, a):
     (4, (1, 2, 2), (9, 10, 11), 27),
 ])
 def test_nrank_hierarchy_equals_single_gpu(handle, nranks, grid, dims, stencil):
-    res = dist_case(nranks, grid, dims, stencil)
+    check_against_single_gpu(handle, nranks, grid, dims, stencil)
+
+
+@pytest.mark.parametrize("nranks,grid,dims,stencil", [
+    (2, (1, 1, 2), (12, 11, 10), 7), (4, (2, 2, 1), (13, 12, 9), 7), (8, (2, 2, 2), (14, 13, 12), 7), (3, (3, 1, 1), (10, 9, 8), 27),
+])
+def test_nrank_fused_galerkin_order_equals_single_gpu(handle, nranks, grid, dims, stencil):
+    """ModuleRAP2 0, the reference default (R A) P, across ranks"""
+    check_against_single_gpu(handle, nranks, grid, dims, stencil, ModuleRAP2=0)
+
+
+def check_against_single_gpu(handle, nranks, grid, dims, stencil, **params):
+    res = dist_case(nranks, grid, dims, stencil, **params)
     nl = len(res[0]["levels"])
     assert all(len(r["levels"]) == nl for r in res)
     gi, gj, ga = gather([r["levels"][0]["A"] for r in res])
-    ref = single_gpu_on(handle, gi, gj, ga)
+    ref = single_gpu_on(handle, gi, gj, ga, **params)
     assert len(ref["levels"]) == nl
     for l in range(nl):
         i, j, a = gather([r["levels"][l]["A"] for r in res])
