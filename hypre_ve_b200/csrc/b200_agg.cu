@@ -70,19 +70,19 @@ __global__ void m_fill_kernel(int n, const int *__restrict__ cf, const int *__re
     if (cf[i3] > 0) { M_j[d] = f2c[i3]; M_a[d++] = 1.0; }
   }
 }
-__global__ void offdiag_count_kernel(int n, const int *__restrict__ C_i, const int *__restrict__ C_j, int *__restrict__ cnt) {
+__global__ void offdiag_count_kernel(int n, int first, const int *__restrict__ C_i, const int *__restrict__ C_j, int *__restrict__ cnt) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r > n) return;
   int c = 0;
-  if (r < n) for (int jj = C_i[r]; jj < C_i[r + 1]; jj++) c += C_j[jj] != r;
+  if (r < n) for (int jj = C_i[r]; jj < C_i[r + 1]; jj++) c += C_j[jj] != first + r;
   cnt[r] = c;
 }
-__global__ void offdiag_fill_kernel(int n, const int *__restrict__ C_i, const int *__restrict__ C_j, const int *__restrict__ O_i,
-                                    int *__restrict__ O_j) {
+__global__ void offdiag_fill_kernel(int n, int first, const int *__restrict__ C_i, const int *__restrict__ C_j,
+                                    const int *__restrict__ O_i, int *__restrict__ O_j) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   int d = O_i[r];
-  for (int jj = C_i[r]; jj < C_i[r + 1]; jj++) if (C_j[jj] != r) O_j[d++] = C_j[jj];
+  for (int jj = C_i[r]; jj < C_i[r + 1]; jj++) if (C_j[jj] != first + r) O_j[d++] = C_j[jj];
 }
 // hypre_BoomerAMGCorrectCFMarker: C points of the first coarsening take the marker of the second one
 __global__ void correct_cf_kernel(int n, const int *__restrict__ f2c, const int *__restrict__ cfn, int *__restrict__ cf) {
@@ -236,95 +236,125 @@ int csr_from_counts(b200_handle h, int n, int ncols, int *cnt, bool with_data, b
 
 }  // namespace
 
-// hypre_BoomerAMGCreate2ndS, num_paths 1: S2 on the C points of cf (pattern only, no diagonal)
-extern "C" int b200_create_2nd_s(b200_handle h, b200_csr S, const int *d_cf, b200_csr *out) {
-  if (!S) B200_FAIL("create2ndS: null S");
-  const int n = S->nrows;
-  int *f2c = nullptr, nc = 0, *c2f = nullptr, *cnt = nullptr;
-  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &nc));
+// hypre_BoomerAMGCreate2ndS, num_paths 1.  General form shared with the multi-rank path:
+//   S      rows [owned | ghost nodes ...] with localized columns (rows beyond the first ring may be empty),
+//   cf/f2c indexed like the columns of S; f2c = coarse id of a C point in the numbering of the output columns
+//          (global ids across ranks), first_coarse = id of this rank's first C point, ncoarse = number of columns.
+// Output: one row per OWNED C point, column ids from f2c, pattern only, no diagonal.
+int b200_create_2nd_s_ex(b200_handle h, b200_csr S, int n_owned, const int *d_cf, const int *d_f2c, int first_coarse,
+                         int ncoarse, b200_csr *out) {
+  const int next = S->nrows;
+  int nc = 0, *c2f = nullptr, *cnt = nullptr, *lf2c = nullptr;
+  // local numbering of the owned C points (rank among the owned rows)
+  B200_TRY(b200_coarse_map(h, n_owned, d_cf, &lf2c, &nc));
   B200_TRY(b200_dalloc<int>(h, &c2f, (size_t)nc + 1));
-  if (n) { c2f_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, d_cf, f2c, c2f); B200_LAUNCH_CHECK(); }
+  if (n_owned) { c2f_kernel<<<b200_grid(n_owned, TBA), TBA, 0, h->stream>>>(n_owned, d_cf, lf2c, c2f); B200_LAUNCH_CHECK(); }
   b200_csr Sc = nullptr, M = nullptr, C = nullptr, S2 = nullptr;
-  B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)std::max(n, nc) + 1));
+  B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)std::max(next, nc) + 1));
   sc_count_kernel<<<b200_grid((size_t)nc + 1, TBA), TBA, 0, h->stream>>>(nc, c2f, S->i, cnt);
   B200_LAUNCH_CHECK();
-  B200_TRY(csr_from_counts(h, nc, n, cnt, true, &Sc));
+  B200_TRY(csr_from_counts(h, nc, next, cnt, true, &Sc));
   if (nc) { sc_fill_kernel<<<b200_grid(nc, TBA), TBA, 0, h->stream>>>(nc, c2f, S->i, S->j, Sc->i, Sc->j, Sc->a); B200_LAUNCH_CHECK(); }
-  m_count_kernel<<<b200_grid((size_t)n + 1, TBA), TBA, 0, h->stream>>>(n, d_cf, S->i, S->j, cnt);
+  m_count_kernel<<<b200_grid((size_t)next + 1, TBA), TBA, 0, h->stream>>>(next, d_cf, S->i, S->j, cnt);
   B200_LAUNCH_CHECK();
-  B200_TRY(csr_from_counts(h, n, nc, cnt, true, &M));
-  if (n) { m_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, d_cf, f2c, S->i, S->j, M->i, M->j, M->a); B200_LAUNCH_CHECK(); }
-  B200_TRY(b200_csr_multiply_ex(h, Sc, M, 0, 0, nc, &C));
-  offdiag_count_kernel<<<b200_grid((size_t)nc + 1, TBA), TBA, 0, h->stream>>>(nc, C->i, C->j, cnt);
+  B200_TRY(csr_from_counts(h, next, ncoarse, cnt, true, &M));
+  if (next) { m_fill_kernel<<<b200_grid(next, TBA), TBA, 0, h->stream>>>(next, d_cf, d_f2c, S->i, S->j, M->i, M->j, M->a); B200_LAUNCH_CHECK(); }
+  B200_TRY(b200_csr_multiply_ex(h, Sc, M, 0, 0, ncoarse, &C));
+  offdiag_count_kernel<<<b200_grid((size_t)nc + 1, TBA), TBA, 0, h->stream>>>(nc, first_coarse, C->i, C->j, cnt);
   B200_LAUNCH_CHECK();
-  B200_TRY(csr_from_counts(h, nc, nc, cnt, false, &S2));
-  if (nc) { offdiag_fill_kernel<<<b200_grid(nc, TBA), TBA, 0, h->stream>>>(nc, C->i, C->j, S2->i, S2->j); B200_LAUNCH_CHECK(); }
+  B200_TRY(csr_from_counts(h, nc, ncoarse, cnt, false, &S2));
+  if (nc) { offdiag_fill_kernel<<<b200_grid(nc, TBA), TBA, 0, h->stream>>>(nc, first_coarse, C->i, C->j, S2->i, S2->j); B200_LAUNCH_CHECK(); }
   B200_TRY(b200_csr_destroy(h, Sc)); B200_TRY(b200_csr_destroy(h, M)); B200_TRY(b200_csr_destroy(h, C));
-  B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, c2f)); B200_TRY(b200_dfree(h, cnt));
+  B200_TRY(b200_dfree(h, lf2c)); B200_TRY(b200_dfree(h, c2f)); B200_TRY(b200_dfree(h, cnt));
   *out = S2;
+  return 0;
+}
+extern "C" int b200_create_2nd_s(b200_handle h, b200_csr S, const int *d_cf, b200_csr *out) {
+  if (!S) B200_FAIL("create2ndS: null S");
+  int *f2c = nullptr, nc = 0;
+  B200_TRY(b200_coarse_map(h, S->nrows, d_cf, &f2c, &nc));
+  B200_TRY(b200_create_2nd_s_ex(h, S, S->nrows, d_cf, f2c, 0, nc, out));
+  B200_TRY(b200_dfree(h, f2c));
+  return 0;
+}
+
+// hypre_BoomerAMGCorrectCFMarker on the owned rows: cfn is indexed by the local rank of the C point
+int b200_correct_cf(b200_handle h, int n_owned, const int *d_cfn, int *d_cf) {
+  int *f2c = nullptr, nc = 0;
+  B200_TRY(b200_coarse_map(h, n_owned, d_cf, &f2c, &nc));
+  if (n_owned) { correct_cf_kernel<<<b200_grid(n_owned, TBA), TBA, 0, h->stream>>>(n_owned, f2c, d_cfn, d_cf); B200_LAUNCH_CHECK(); }
+  B200_TRY(b200_dfree(h, f2c));
   return 0;
 }
 
 // second stage of aggressive coarsening (par_amg_setup.c:1239-1256 + :1592): PMIS on S2 with CF_init 3, then
 // hypre_BoomerAMGCorrectCFMarker.  d_cf: in = first PMIS marker, out = corrected marker
 extern "C" int b200_agg_coarsen(b200_handle h, b200_csr S, int seed, int *d_cf) {
-  const int n = S->nrows;
   b200_csr S2 = nullptr;
   B200_TRY(b200_create_2nd_s(h, S, d_cf, &S2));
-  int *cfn = nullptr, *f2c = nullptr, nc = 0;
+  int *cfn = nullptr;
   B200_TRY(b200_dalloc<int>(h, &cfn, (size_t)S2->nrows + 1));
   B200_TRY(b200_pmis_rows_init(h, S2, seed, 0, 3, cfn, nullptr));
-  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &nc));
-  if (n) { correct_cf_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, f2c, cfn, d_cf); B200_LAUNCH_CHECK(); }
+  B200_TRY(b200_correct_cf(h, S->nrows, cfn, d_cf));
   B200_TRY(b200_csr_destroy(h, S2));
-  B200_TRY(b200_dfree(h, cfn)); B200_TRY(b200_dfree(h, f2c));
+  B200_TRY(b200_dfree(h, cfn));
   return 0;
 }
 
-// hypre_BoomerAMGBuildMultipass, one rank, weight_option 0, trunc_factor 0, P_max_elmts 0.
-// d_cf: {1, -1, -3}; SF points (-3) are folded into F on return, as the reference does.
-extern "C" int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int *d_cf, b200_csr *out) {
-  if (!A || !A->a || !S) B200_FAIL("multipass: bad arguments");
-  const int n = A->nrows;
-  int *f2c = nullptr, nc = 0, *assigned = nullptr, *assigned2 = nullptr, *d_rem = nullptr, *cnt = nullptr;
-  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &nc));
-  B200_TRY(b200_dalloc<int>(h, &assigned, (size_t)n + 1));
-  B200_TRY(b200_dalloc<int>(h, &assigned2, (size_t)n + 1));
+// hypre_BoomerAMGBuildMultipass, weight_option 0, trunc_factor 0, P_max_elmts 0.  General form shared with the
+// multi-rank path: A and S hold the n owned rows with localized columns [owned | ghost]; d_cf, d_f2c (coarse ids in
+// the numbering of P's columns) and the pass numbers are indexed like those columns; the hooks refresh ghost tails,
+// sum over ranks and append the ghost nodes' rows of a pass (all no-ops on one rank).
+int b200_multipass_ex(b200_handle h, b200_csr A, b200_csr S, int n, int n_ext, int *d_cf, const int *d_f2c, int ncoarse,
+                      const b200_agg_hooks *hooks, b200_csr *out) {
+  int *assigned = nullptr, *assigned2 = nullptr, *d_rem = nullptr, *cnt = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &assigned, (size_t)n_ext + 1));
+  B200_TRY(b200_dalloc<int>(h, &assigned2, (size_t)n_ext + 1));
   B200_TRY(b200_dalloc<int>(h, &d_rem, 1));
   B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
-  if (n) { assign_init_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, d_cf, assigned); B200_LAUNCH_CHECK(); }
+  if (n_ext) { assign_init_kernel<<<b200_grid(n_ext, TBA), TBA, 0, h->stream>>>(n_ext, d_cf, assigned); B200_LAUNCH_CHECK(); }
   int npass = 1, remaining = 1;
-  for (int p = 1; p < MAX_PASSES && remaining && n; p++) {            // pass 1, then `while (remaining && pass < 10)`
+  for (int p = 1; p < MAX_PASSES && remaining; p++) {                 // pass 1, then `while (remaining && pass < 10)`
     B200_CUDA(cudaMemsetAsync(d_rem, 0, sizeof(int), h->stream));
-    assign_pass_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, d_cf, S->i, S->j, assigned, assigned2, d_rem);
-    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(assigned2, assigned, sizeof(int) * (size_t)n_ext, cudaMemcpyDeviceToDevice, h->stream));
+    if (n) {
+      assign_pass_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, d_cf, S->i, S->j, assigned, assigned2, d_rem);
+      B200_LAUNCH_CHECK();
+    }
     std::swap(assigned, assigned2);
+    if (hooks && hooks->sync_int) B200_TRY(hooks->sync_int(assigned));
     B200_CUDA(cudaMemcpyAsync(&remaining, d_rem, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (hooks && hooks->sum_int) B200_TRY(hooks->sum_int(&remaining));
     npass = p + 1;
   }
-  // the reference always runs pass 1 and only then tests `remaining`; a pass that assigns nothing is harmless here
   b200_csr rows[MAX_PASSES] = {nullptr};
   for (int p = 1; p < npass; p++) {
     nbr_count_kernel<<<b200_grid((size_t)n + 1, TBA), TBA, 0, h->stream>>>(n, p, S->i, S->j, assigned, cnt);
     B200_LAUNCH_CHECK();
     if (p == 1) {
-      B200_TRY(csr_from_counts(h, n, nc, cnt, true, &rows[1]));
+      B200_TRY(csr_from_counts(h, n, ncoarse, cnt, true, &rows[1]));
       if (n) {
-        pass1_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, assigned,
+        pass1_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, d_f2c, assigned,
                                                                     rows[1]->i, rows[1]->j, rows[1]->a);
         B200_LAUNCH_CHECK();
       }
     } else {
-      b200_csr Ap = nullptr;
-      B200_TRY(csr_from_counts(h, n, n, cnt, true, &Ap));
-      ap_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, A->i, A->j, A->a, S->i, S->j, assigned, Ap->i, Ap->j, Ap->a);
-      B200_LAUNCH_CHECK();
-      B200_TRY(b200_csr_multiply_ex(h, Ap, rows[p - 1], 0, 0, nc, &rows[p]));
+      b200_csr Ap = nullptr, B = rows[p - 1];
+      if (hooks && hooks->with_ghost_rows) B200_TRY(hooks->with_ghost_rows(rows[p - 1], &B));   // [owned rows ; ghost nodes' rows]
+      B200_TRY(csr_from_counts(h, n, n_ext, cnt, true, &Ap));
+      if (n) {
+        ap_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, A->i, A->j, A->a, S->i, S->j, assigned, Ap->i, Ap->j, Ap->a);
+        B200_LAUNCH_CHECK();
+      }
+      B200_TRY(b200_csr_multiply_ex(h, Ap, B, 0, 0, ncoarse, &rows[p]));
       B200_TRY(b200_csr_destroy(h, Ap));
-      passp_scale_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, A->i, A->j, A->a, S->i, S->j, d_cf, assigned,
-                                                                   rows[p - 1]->i, rows[p - 1]->a, rows[p]->i, rows[p]->a);
-      B200_LAUNCH_CHECK();
+      if (n) {
+        passp_scale_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, p, A->i, A->j, A->a, S->i, S->j, d_cf, assigned, B->i, B->a,
+                                                                     rows[p]->i, rows[p]->a);
+        B200_LAUNCH_CHECK();
+      }
+      if (B != rows[p - 1]) B200_TRY(b200_csr_destroy(h, B));
     }
   }
   PassRows R;
@@ -334,16 +364,27 @@ extern "C" int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int 
   merge_count_kernel<<<b200_grid((size_t)n + 1, TBA), TBA, 0, h->stream>>>(n, assigned, R, cnt);
   B200_LAUNCH_CHECK();
   b200_csr P = nullptr;
-  B200_TRY(csr_from_counts(h, n, nc, cnt, true, &P));
+  B200_TRY(csr_from_counts(h, n, ncoarse, cnt, true, &P));
   if (n) {
-    merge_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, assigned, f2c, R, P->i, P->j, P->a);
+    merge_fill_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, assigned, d_f2c, R, P->i, P->j, P->a);
     B200_LAUNCH_CHECK();
     sf_to_f_kernel<<<b200_grid(n, TBA), TBA, 0, h->stream>>>(n, d_cf);
     B200_LAUNCH_CHECK();
   }
   for (int p = 1; p < MAX_PASSES; p++) if (rows[p]) B200_TRY(b200_csr_destroy(h, rows[p]));
-  B200_TRY(b200_dfree(h, f2c)); B200_TRY(b200_dfree(h, assigned)); B200_TRY(b200_dfree(h, assigned2));
+  B200_TRY(b200_dfree(h, assigned)); B200_TRY(b200_dfree(h, assigned2));
   B200_TRY(b200_dfree(h, d_rem)); B200_TRY(b200_dfree(h, cnt));
   *out = P;
+  return 0;
+}
+
+// one rank.  d_cf: {1, -1, -3}; SF points (-3) are folded into F on return, as the reference does.
+extern "C" int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int *d_cf, b200_csr *out) {
+  if (!A || !A->a || !S) B200_FAIL("multipass: bad arguments");
+  const int n = A->nrows;
+  int *f2c = nullptr, nc = 0;
+  B200_TRY(b200_coarse_map(h, n, d_cf, &f2c, &nc));
+  B200_TRY(b200_multipass_ex(h, A, S, n, n, d_cf, f2c, nc, nullptr, out));
+  B200_TRY(b200_dfree(h, f2c));
   return 0;
 }

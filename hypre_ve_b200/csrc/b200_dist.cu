@@ -34,6 +34,8 @@ int b200_box_first_row(int nx, int ny, int nz, int P, int Q, int R, int p, int q
 
 struct b200_amg_s;   // parameter maps live in b200_amg.cu
 int b200_amg_get_int(b200_amg a, const char *name);
+int b200_pmis_dist_init(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int cf_init,
+                        int *d_cf_ext);
 double b200_amg_get_real(b200_amg a, const char *name);
 
 // legacy diag/offd ParCSR hooks (b200_parcsr.cu): the multi-rank path is the b200_dist_* API
@@ -743,7 +745,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_FAIL("multi-GPU RelaxType: 18 (l1-Jacobi) or the l1 hybrid Gauss-Seidel family 8/13/14");
   if (rdown != 18 && b200_amg_get_real(prm, "RelaxWt") != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (b200_amg_get_int(prm, "InterpType") != 6 ||
-      b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") != 0 ||
+      b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") < 0 ||
       b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
       b200_amg_get_int(prm, "RAP2") != 0 || (b200_amg_get_int(prm, "ModuleRAP2") != 0 && b200_amg_get_int(prm, "ModuleRAP2") != 1))
     B200_FAIL("unsupported BoomerAMG configuration on the B200 path (see b200_amg_setup)");
@@ -752,7 +754,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   const double trunc = b200_amg_get_real(prm, "TruncFactor");
   const int pmax = b200_amg_get_int(prm, "PMaxElmts"), max_levels = b200_amg_get_int(prm, "MaxLevels");
   const int max_coarse = b200_amg_get_int(prm, "MaxCoarseSize"), seed = b200_amg_get_int(prm, "Seed");
-  const int mod_rap2 = b200_amg_get_int(prm, "ModuleRAP2");
+  const int mod_rap2 = b200_amg_get_int(prm, "ModuleRAP2"), agg_nl = b200_amg_get_int(prm, "AggNumLevels");
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
@@ -776,28 +778,31 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     int *cf = nullptr;                              // [n + ng]
     B200_TRY(b200_dalloc<int>(h, &cf, (size_t)n + ng + 1));
     B200_TRY(b200_pmis_dist(h, c, S, A->halo, seed, A->first_row, cf));
-    // --- coarse numbering (par_coarse_parms.c:83-122) ---------------------------------------------
-    int *f2c = nullptr;                             // [n + ng]: global coarse id or -1
-    B200_TRY(b200_dalloc<int>(h, &f2c, (size_t)n + ng + 1));
-    cflag2_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, cf, f2c);
-    B200_LAUNCH_CHECK();
-    B200_TRY(b200_exclusive_scan_inplace(h, f2c, (size_t)n + 1));
-    int nc = 0;
-    B200_CUDA(cudaMemcpyAsync(&nc, f2c + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA(cudaStreamSynchronize(h->stream));
-    std::vector<int> cstarts;
-    B200_TRY(gather_starts(h, c, nc, &cstarts));
-    const long long coarse_size = cstarts[R];
-    if (coarse_size == 0 || coarse_size == fine_size) {       // par_amg_setup.c:1487-1525
-      B200_TRY(b200_csr_destroy(h, S)); B200_TRY(b200_dfree(h, cf)); B200_TRY(b200_dfree(h, f2c));
-      break;
-    }
-    if (n) {
-      f2c_global_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, cf, cstarts[me], f2c);
+    const bool aggressive = level < agg_nl;
+    // --- coarse numbering (par_coarse_parms.c:83-122): global coarse ids over [owned | ghost], -1 for F points ----
+    auto number_coarse = [&](const int *cfv, int **f2c_out, int *nc_out, std::vector<int> *starts) -> int {
+      int *f = nullptr;
+      B200_TRY(b200_dalloc<int>(h, &f, (size_t)n + ng + 1));
+      cflag2_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, cfv, f);
       B200_LAUNCH_CHECK();
-    }
-    B200_TRY(b200_halo_forward_i32(h, c, A->halo, f2c, f2c + n));
-    // --- ext+i interpolation (par_lr_interp.c:1040-1925 with hypre_exchange_interp_data) ---------
+      B200_TRY(b200_exclusive_scan_inplace(h, f, (size_t)n + 1));
+      B200_CUDA(cudaMemcpyAsync(nc_out, f + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      B200_TRY(gather_starts(h, c, *nc_out, starts));
+      if (n) {
+        f2c_global_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, cfv, (*starts)[me], f);
+        B200_LAUNCH_CHECK();
+      }
+      B200_TRY(b200_halo_forward_i32(h, c, A->halo, f, f + n));
+      *f2c_out = f;
+      return 0;
+    };
+    // --- extended operators over [owned | U] (hypre_exchange_interp_data, aux_interp.c:552-660): needed by the
+    //     ext+i weights and by the distance-two strength graph of aggressive coarsening -------------------------
+    b200_csr Abig2 = nullptr, Sbig2 = nullptr;
+    b200_halo_s *plan2 = nullptr;
+    int nring = 0;
+    auto build_extended = [&]() -> int {
     // rows of A and S for the ghost nodes, then the second ring of ghost ids they mention
     b200_csr Sg = nullptr;                          // S with global column ids (to serve fetches)
     B200_TRY(b200_csr_alloc(h, n, A->global_cols, S->nnz, false, &Sg));
@@ -813,7 +818,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_TRY(b200_csr_destroy(h, Sg));
     // second ring: ids in the fetched rows that are neither owned nor first-ring ghosts.  Build the
     // sorted union U = ghosts1 + ring2 and a plan for it; extended index space = [owned | U].
-    int *ring = nullptr, nring = 0;
+    int *ring = nullptr;
     {
       int *cand = nullptr;
       const int tot = Aext->nnz + A->halo->ng;
@@ -825,7 +830,6 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_dfree(h, cand));
       if (!ring) B200_TRY(b200_dalloc<int>(h, &ring, 1));
     }
-    b200_halo_s *plan2 = nullptr;
     B200_TRY(b200_halo_build(h, c, A->col_starts, ring, nring, &plan2));
     // Extended operators: rows [owned | U], columns [owned | U].  The row kernels address neighbour
     // ROWS by column id, so every id of U needs a row slot; only the first ring has entries (second-ring
@@ -839,7 +843,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
                                                                plan2->d_ghost_gid, pos);
       B200_LAUNCH_CHECK();
     }
-    b200_csr AextU = nullptr, SextU = nullptr, Abig_g = nullptr, Sbig_g = nullptr, Abig2 = nullptr, Sbig2 = nullptr;
+    b200_csr AextU = nullptr, SextU = nullptr, Abig_g = nullptr, Sbig_g = nullptr;
     B200_TRY(spread_rows(h, Aext, pos, A->n_owned_cols, nring, &AextU));
     B200_TRY(spread_rows(h, Sext, pos, A->n_owned_cols, nring, &SextU));
     B200_TRY(b200_dfree(h, pos));
@@ -861,18 +865,81 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_TRY(localize_copy(h, Abig_g, plan2, A->first_col, A->n_owned_cols, false, &Abig2));
     B200_TRY(localize_copy(h, Sbig_g, plan2, A->first_col, A->n_owned_cols, false, &Sbig2));
     B200_TRY(b200_csr_destroy(h, Abig_g)); B200_TRY(b200_csr_destroy(h, Sbig_g));
-    // cf / f2c over [owned | U]
-    int *cf_big = nullptr, *f2c_big = nullptr;
-    B200_TRY(b200_dalloc<int>(h, &cf_big, (size_t)n + nring + 1));
-    B200_TRY(b200_dalloc<int>(h, &f2c_big, (size_t)n + nring + 1));
-    B200_CUDA(cudaMemcpyAsync(cf_big, cf, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
-    B200_CUDA(cudaMemcpyAsync(f2c_big, f2c, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
-    B200_TRY(b200_halo_forward_i32(h, c, plan2, cf_big, cf_big + n));
-    B200_TRY(b200_halo_forward_i32(h, c, plan2, f2c_big, f2c_big + n));
+      return 0;
+    };
+    auto extend_markers = [&](const int *cfv, const int *f2cv, int **cf_big_out, int **f2c_big_out) -> int {
+      int *cf_big = nullptr, *f2c_big = nullptr;                 // cf / f2c over [owned | U]
+      B200_TRY(b200_dalloc<int>(h, &cf_big, (size_t)n + nring + 1));
+      B200_TRY(b200_dalloc<int>(h, &f2c_big, (size_t)n + nring + 1));
+      B200_CUDA(cudaMemcpyAsync(cf_big, cfv, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      B200_CUDA(cudaMemcpyAsync(f2c_big, f2cv, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      B200_TRY(b200_halo_forward_i32(h, c, plan2, cf_big, cf_big + n));
+      B200_TRY(b200_halo_forward_i32(h, c, plan2, f2c_big, f2c_big + n));
+      *cf_big_out = cf_big; *f2c_big_out = f2c_big;
+      return 0;
+    };
+    B200_TRY(build_extended());
+    if (aggressive) {
+      // second coarsening on the distance-two strength graph of the C points (par_amg_setup.c:1239-1256), then
+      // hypre_BoomerAMGCorrectCFMarker (:1592).  S2's columns carry the global ids of the FIRST coarse numbering.
+      int *f2c1 = nullptr, nc1 = 0;
+      std::vector<int> cs1;
+      B200_TRY(number_coarse(cf, &f2c1, &nc1, &cs1));
+      if (cs1[R] > 0) {
+        int *cfb = nullptr, *f2cb = nullptr;
+        B200_TRY(extend_markers(cf, f2c1, &cfb, &f2cb));
+        b200_csr S2g = nullptr;
+        B200_TRY(b200_create_2nd_s_ex(h, Sbig2, n, cfb, f2cb, cs1[me], cs1[R], &S2g));
+        B200_TRY(b200_dfree(h, cfb)); B200_TRY(b200_dfree(h, f2cb));
+        b200_dist_matrix S2d = new_dist(nc1, cs1[me], cs1[R], cs1, cs1[me], nc1, cs1[R], cs1, S2g);
+        B200_TRY(dist_localize(h, c, S2d));
+        int *cfn = nullptr;
+        B200_TRY(b200_dalloc<int>(h, &cfn, (size_t)nc1 + S2d->halo->ng + 1));
+        B200_TRY(b200_pmis_dist_init(h, c, S2d->L, S2d->halo, seed, cs1[me], 3, cfn));
+        B200_TRY(b200_correct_cf(h, n, cfn, cf));
+        B200_TRY(b200_halo_forward_i32(h, c, A->halo, cf, cf + n));
+        B200_TRY(b200_dfree(h, cfn));
+        B200_TRY(b200_dist_matrix_destroy(h, S2d));
+      }
+      B200_TRY(b200_dfree(h, f2c1));
+    }
+    int *f2c = nullptr, nc = 0;                     // [n + ng]: global coarse id or -1
+    std::vector<int> cstarts;
+    B200_TRY(number_coarse(cf, &f2c, &nc, &cstarts));
+    const long long coarse_size = cstarts[R];
+    if (coarse_size == 0 || coarse_size == fine_size) {       // par_amg_setup.c:1487-1525
+      B200_TRY(b200_csr_destroy(h, S)); B200_TRY(b200_dfree(h, cf)); B200_TRY(b200_dfree(h, f2c));
+      B200_TRY(b200_csr_destroy(h, Abig2)); B200_TRY(b200_csr_destroy(h, Sbig2));
+      b200_halo_free(h, plan2);
+      break;
+    }
     b200_csr Pg = nullptr;
-    B200_TRY(b200_extpi_interp_ex(h, Abig2, Sbig2, cf_big, n, f2c_big, (int)coarse_size, trunc, pmax, &Pg));
+    if (aggressive) {
+      // hypre_BoomerAMGBuildMultipass (:1601): pass numbers, pass rows and their ghost copies move over the halo of A
+      b200_agg_hooks hooks;
+      hooks.sync_int = [&](int *v) -> int { return b200_halo_forward_i32(h, c, A->halo, v, v + n); };
+      hooks.sum_int = [&](int *v) -> int {
+        long long t = *v;
+        B200_TRY(b200_comm_allreduce_sum_ll(h, c, &t, 1));
+        *v = t > 0x7fffffffLL ? 0x7fffffff : (int)t;
+        return 0;
+      };
+      hooks.with_ghost_rows = [&](b200_csr rows, b200_csr *big) -> int {
+        b200_csr ext = nullptr;
+        B200_TRY(fetch_rows(h, c, A->halo, rows, &ext));
+        B200_TRY(stack_rows(h, rows, ext, big));
+        B200_TRY(b200_csr_destroy(h, ext));
+        return 0;
+      };
+      B200_TRY(b200_multipass_ex(h, A->L, S, n, n + ng, cf, f2c, (int)coarse_size, &hooks, &Pg));
+    } else {
+      // --- ext+i interpolation (par_lr_interp.c:1040-1925 with hypre_exchange_interp_data) ---------
+      int *cf_big = nullptr, *f2c_big = nullptr;
+      B200_TRY(extend_markers(cf, f2c, &cf_big, &f2c_big));
+      B200_TRY(b200_extpi_interp_ex(h, Abig2, Sbig2, cf_big, n, f2c_big, (int)coarse_size, trunc, pmax, &Pg));
+      B200_TRY(b200_dfree(h, cf_big)); B200_TRY(b200_dfree(h, f2c_big));
+    }
     B200_TRY(b200_csr_destroy(h, Abig2)); B200_TRY(b200_csr_destroy(h, Sbig2));
-    B200_TRY(b200_dfree(h, cf_big)); B200_TRY(b200_dfree(h, f2c_big));
     b200_halo_free(h, plan2);
     B200_TRY(b200_csr_destroy(h, S));
     if (n) {

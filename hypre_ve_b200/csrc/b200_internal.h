@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/hypre_b200.h"
@@ -111,4 +112,15 @@ int b200_gs_plan_destroy(b200_handle h, b200_gs_plan_s *p);
 int b200_gs_plan_levels(b200_gs_plan_s *p);
 int b200_gs_plan_blocks(b200_gs_plan_s *p);
 int b200_gs_relax(b200_handle h, b200_gs_plan_s *P, b200_csr A, int type, bool zero, const double *f, const double *l1, double *u);
+// aggressive coarsening building blocks shared by the single-rank and the row-partitioned setup (b200_agg.cu)
+struct b200_agg_hooks {
+  std::function<int(int *)> sync_int;                        // refresh the ghost tail of an int array indexed like A's columns
+  std::function<int(int *)> sum_int;                         // sum one host int over the ranks, in place
+  std::function<int(b200_csr, b200_csr *)> with_ghost_rows;  // [rows of the owned nodes ; rows of the ghost nodes]
+};
+int b200_create_2nd_s_ex(b200_handle h, b200_csr S, int n_owned, const int *d_cf, const int *d_f2c, int first_coarse,
+                         int ncoarse, b200_csr *out);
+int b200_correct_cf(b200_handle h, int n_owned, const int *d_cfn, int *d_cf);
+int b200_multipass_ex(b200_handle h, b200_csr A, b200_csr S, int n, int n_ext, int *d_cf, const int *d_f2c, int ncoarse,
+                      const b200_agg_hooks *hooks, b200_csr *out);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);

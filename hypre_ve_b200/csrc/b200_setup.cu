@@ -677,7 +677,15 @@ __global__ void pmis_ghost_measure_kernel(int ng, const int *__restrict__ cf_gho
 // Row-partitioned PMIS (par_coarsen.c:2031-2738 with num_procs > 1).  S has n local rows and columns in
 // the extended local space [owned | ghosts of `halo`]; measures use the GLOBAL row index for the random
 // draw (seq_rand, par_indepset.c:44-55), so the result does not depend on the partition.
+int b200_pmis_dist_init(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int cf_init,
+                        int *d_cf_ext);
 int b200_pmis_dist(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int *d_cf_ext) {
+  return b200_pmis_dist_init(h, c, S, halo, seed, first_row, 0, d_cf_ext);
+}
+// cf_init 3: see b200_pmis_rows_init
+int b200_pmis_dist_init(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int cf_init,
+                        int *d_cf_ext) {
+  if (cf_init != 0 && cf_init != 3) B200_FAIL("pmis: CF_init 0 or 3");
   const int n = S->nrows, ng = halo ? halo->ng : 0, ne = n + ng;
   int *colcnt = nullptr, *ingraph = nullptr, *d_count = nullptr, *cf2 = nullptr;
   double *measure = nullptr;
@@ -693,7 +701,7 @@ int b200_pmis_dist(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, in
   }
   if (halo) B200_TRY(b200_halo_reverse_add_i32(h, c, halo, colcnt + n, colcnt));     // :2187-2228 (job 2)
   if (n) {
-    pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf_ext);
+    pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf_ext, cf_init);
     B200_LAUNCH_CHECK();
   }
   if (halo) {
@@ -713,17 +721,19 @@ int b200_pmis_dist(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, in
     long long total = count;
     B200_TRY(b200_comm_allreduce_sum_ll(h, c, &total, 1));                           // :2399
     if (total == 0) break;
-    if (ne) {
-      pmis_mark_kernel<<<b200_grid(ne, 256), 256, 0, h->stream>>>(ne, measure, d_cf_ext);   // local and ghost nodes (:2430-2449)
-      B200_LAUNCH_CHECK();
-    }
-    if (n) {
-      pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf_ext);
-      B200_LAUNCH_CHECK();
-    }
-    if (halo) {
-      B200_TRY(b200_halo_reverse_clear_i32(h, c, halo, d_cf_ext + n, d_cf_ext));     // job 12 + :2509-2526
-      B200_TRY(b200_halo_forward_i32(h, c, halo, d_cf_ext, d_cf_ext + n));           // job 11 (:2530)
+    if (!cf_init || iter) {                                                          // :2420
+      if (ne) {
+        pmis_mark_kernel<<<b200_grid(ne, 256), 256, 0, h->stream>>>(ne, measure, d_cf_ext);   // local and ghost nodes (:2430-2449)
+        B200_LAUNCH_CHECK();
+      }
+      if (n) {
+        pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf_ext);
+        B200_LAUNCH_CHECK();
+      }
+      if (halo) {
+        B200_TRY(b200_halo_reverse_clear_i32(h, c, halo, d_cf_ext + n, d_cf_ext));     // job 12 + :2509-2526
+        B200_TRY(b200_halo_forward_i32(h, c, halo, d_cf_ext, d_cf_ext + n));           // job 11 (:2530)
+      }
     }
     if (n) {
       pmis_setcf_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, ingraph, measure, d_cf_ext, cf2);

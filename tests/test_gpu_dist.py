@@ -124,6 +124,17 @@ def test_nrank_fused_galerkin_order_equals_single_gpu(handle, nranks, grid, dims
     check_against_single_gpu(handle, nranks, grid, dims, stencil, ModuleRAP2=0)
 
 
+@pytest.mark.parametrize("nranks,grid,dims,stencil,agg", [
+    (2, (1, 1, 2), (12, 11, 10), 7, 1), (3, (1, 3, 1), (14, 15, 9), 7, 1), (4, (2, 2, 1), (16, 14, 12), 7, 2),
+    (8, (2, 2, 2), (16, 16, 16), 7, 1), (2, (2, 1, 1), (10, 9, 8), 27, 1),
+])
+def test_nrank_aggressive_coarsening_equals_single_gpu(handle, nranks, grid, dims, stencil, agg):
+    """-agg_nl L across ranks: distance-two strength graph from fetched S rows, second PMIS over the halo of S2,
+    multipass interpolation with pass numbers and pass rows exchanged over the halo of A"""
+    check_against_single_gpu(handle, nranks, grid, dims, stencil, AggNumLevels=agg)
+    check_against_single_gpu(handle, nranks, grid, dims, stencil, AggNumLevels=agg, ModuleRAP2=0)
+
+
 def check_against_single_gpu(handle, nranks, grid, dims, stencil, **params):
     res = dist_case(nranks, grid, dims, stencil, **params)
     nl = len(res[0]["levels"])
