@@ -214,12 +214,13 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   const int rdown = ip["RelaxType"], rup = ip["RelaxTypeUp"] >= 0 ? ip["RelaxTypeUp"] : ip["RelaxType"];
   auto is_gs = [](int t) { return t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14; };
   auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
-  if (!((rdown == 18 && rup == 18) || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
-    B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), the l1 hybrid Gauss-Seidel family 8/13/14 and the "
-              "hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
-  if (rdown != 18 && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  auto is_jac = [](int t) { return t == 18 || t == 7; };
+  if (!((is_jac(rdown) && rup == rdown) || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
+    B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), 7 (weighted Jacobi), the l1 hybrid Gauss-Seidel family "
+              "8/13/14 and the hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
+  if (!is_jac(rdown) && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (ip["GSBlocks"] < 1) B200_FAIL("GSBlocks must be >= 1");
-  amg->gs = rdown != 18;
+  amg->gs = !is_jac(rdown);
   amg->relax_down = rdown; amg->relax_up = rup;
   if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
   if (ip["AggNumLevels"] < 0) B200_FAIL("AggNumLevels must be >= 0");
@@ -334,11 +335,13 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     if (!L.As->blk_row) B200_TRY(b200_csr_build_plan(h, L.As));
     if (L.P && !L.P->blk_row) B200_TRY(b200_csr_build_plan(h, L.P));
     if (L.R && !L.R->blk_row) B200_TRY(b200_csr_build_plan(h, L.R));
-    if (l < nl - 1 || !amg->coarse_ge) {
-      if (!amg->gs || is_l1gs(rdown)) {
+    if (l < nl - 1 || !amg->coarse_ge || rdown == 7) {
+      if (!amg->gs || is_l1gs(rdown)) {                // option 1: relax 18, 4: relax 8/13/14, 5 (= the diagonal): relax 7
         B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
-        B200_TRY(b200_l1_norms_blocks(h, L.A, amg->gs ? 4 : 1, amg->gs ? ip["GSBlocks"] : 1, L.l1));
+        B200_TRY(b200_l1_norms_blocks(h, L.A, amg->gs ? 4 : (rdown == 7 ? 5 : 1), amg->gs ? ip["GSBlocks"] : 1, L.l1));
       }
+    }
+    if (l < nl - 1 || !amg->coarse_ge) {
       if (amg->gs) {
         if (L.A->gs && b200_gs_plan_blocks(L.A->gs) != ip["GSBlocks"]) { B200_TRY(b200_gs_plan_destroy(h, L.A->gs)); L.A->gs = nullptr; }
         if (!L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, ip["GSBlocks"], &L.A->gs));

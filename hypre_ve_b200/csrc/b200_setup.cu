@@ -555,6 +555,12 @@ __global__ void l1_kernel(int n, int size, int rest, const int *__restrict__ A_i
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double v = 0.0;
+  if (option == 5) {                                // relax 7: a_ii itself, 1 where it is zero, no sign handling (ams.c:704-725)
+    for (int j = A_i[i]; j < A_i[i + 1]; j++)
+      if (A_j[j] == i) { v = A_a[j]; break; }
+    l1[i] = (v == 0.0) ? 1.0 : v;
+    return;
+  }
   if (option == 1) {
     for (int j = A_i[i]; j < A_i[i + 1]; j++) v += 1.0 * fabs(A_a[j]);   // ComputeRowSum type 1, scal 1.0
   } else {                                          // option 4: |a_ii| + 0.5 * off-block entries, Remark 6.2
@@ -981,7 +987,7 @@ int b200_csr_multiply_ex(b200_handle h, b200_csr A, b200_csr B, int allsquare, i
 
 extern "C" int b200_l1_norms_blocks(b200_handle h, b200_csr A, int option, int blocks, double *d_l1) {
   if (!A || !A->a) B200_FAIL("l1 norms: matrix with values required");
-  if (option != 1 && option != 4) B200_FAIL("l1 norms: only options 1 and 4 are supported");
+  if (option != 1 && option != 4 && option != 5) B200_FAIL("l1 norms: options 1, 4 and 5 are supported");
   if (blocks < 1) B200_FAIL("l1 norms: blocks must be >= 1");
   if (A->nrows == 0) return 0;
   const int size = A->nrows / blocks, rest = A->nrows - size * blocks;

@@ -353,6 +353,12 @@ static double *l1_norms(const csr_t *A, int option)
       {
          double s = 0.0, d = 0.0;
          if (option == 1) { for (j = A->i[i]; j < A->i[i + 1]; j++) s += fabs(A->a[j]); }
+         else if (option == 5)
+         {  /* relax 7: the diagonal itself, 1 where it is zero; no sign handling (ams.c:704-725) */
+            for (j = A->i[i]; j < A->i[i + 1]; j++) if (A->j[j] == i) { s = A->a[j]; break; }
+            l1[i] = (s == 0.0) ? 1.0 : s;
+            continue;
+         }
          else
          {
             for (j = A->i[i]; j < A->i[i + 1]; j++)
@@ -582,7 +588,7 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    for (i = 0; i < g->nl; i++)
    {
       int n = g->A[i].n;
-      g->l1[i] = l1_norms(&g->A[i], g_relax_down == 18 ? 1 : 4);      /* par_amg_setup.c:3018-3060 */
+      g->l1[i] = l1_norms(&g->A[i], g_relax_down == 18 ? 1 : (g_relax_down == 7 ? 5 : 4));      /* par_amg_setup.c:3018-3100 */
       g->F[i] = (double *) xcalloc(n, sizeof(double)); g->U[i] = (double *) xcalloc(n, sizeof(double));
    }
    g->V = (double *) xcalloc(g->A[0].n, sizeof(double));
@@ -627,8 +633,8 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
 {
    int n = g->A[l].n, i, j, T = g_gs_blocks; double *v = g->V;
    const csr_t *A = &g->A[l]; const double *l1 = g->l1[l];
-   if (type == 18)
-   {
+   if (type == 18 || type == 7)
+   {  /* 7: Jacobi through the matvec, Vtemp = w f - w A u, u += Vtemp / a_ii (par_relax.c:3463-3490), w = 1 */
       matvec(-1.0, A, u, 1.0, f, v);
       for (i = 0; i < n; i++) u[i] += v[i] / l1[i];
       return;
@@ -786,7 +792,7 @@ int main(int argc, char **argv)
       {
          char nm[64];
          put_csr("A", i, &g.A[i], 1);
-         if ((i < g.nl - 1 || !g.ge) && (g_relax_down == 18 || g_relax_down == 8 || g_relax_down == 13 || g_relax_down == 14))
+         if ((i < g.nl - 1 || !g.ge || g_relax_down == 7) && (g_relax_down == 18 || g_relax_down == 8 || g_relax_down == 13 || g_relax_down == 14 || g_relax_down == 7))
          { sprintf(nm, "l1_%d", i); put(nm, 1, g.l1[i], g.A[i].n); }   /* par_amg_setup.c:3045-3060 */
          if (i < g.nl - 1)
          {

@@ -271,3 +271,24 @@ def test_default_fused_galerkin_product_order(handle, args):
     assert its == int(d["hdr"][4])
     assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
     amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("args,w", [(["-n", 24, 20, 18], 1.0), (["-n", 14, 14, 14, "-27pt"], 1.0)])
+def test_weighted_jacobi_relax_7(handle, args, w):
+    """relax 7: Jacobi through the matvec with the diagonal as "l1 norm" (par_relax.c:3463-3490, option 5 norms)"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-pmis", "-rlx", 7, "-mod_rap2", 1])
+    nx, ny, nz = args[1:4]
+    A = hb.ParCsr.laplacian27(handle, nx, ny, nz) if "-27pt" in args else hb.ParCsr.laplacian(handle, nx, ny, nz)
+    amg = hb.Amg(handle, RelaxType=7)
+    amg.setup(A)
+    assert amg.num_levels == nlev(d)
+    for l in range(nlev(d) - 1):
+        assert np.array_equal(amg.level_l1(l), d["l1_%d" % l]), l           # option 5: the diagonal
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4])
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    amg.destroy(); A.destroy()
