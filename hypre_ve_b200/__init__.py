@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200_csr_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_csr_matvec": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
     "b200_csr_matvecT": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
+    "b200_csr_row_stats": (_i, [_vp, _vp, _ip, _ip, _dp, _dp, _dp, _dp]),
     "b200_csr_sorted_copy": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200_csr_transpose": (_i, [_vp, _vp, C.POINTER(_vp)]),
     "b200_csr_multiply": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),

@@ -418,3 +418,75 @@ extern "C" int b200_csr_sorted_copy(b200_handle h, b200_csr A, b200_csr *out) {
   *out = S;
   return 0;
 }
+
+// ---- per-matrix statistics of hypre_BoomerAMGSetupStats (parcsr_ls/par_stats.c:575-606 for A_l, :866-925 for P_l) ----
+// entries per row (min, max), row sums (min, max; each row summed in storage order like the reference) and, for
+// interpolation matrices, min weight / max weight over the entries != 1.  One thread per row, block reduction, the
+// handful of per-block partials is finished on the host.
+namespace {
+struct RowStats { int min_e, max_e; double min_rs, max_rs, min_w, max_w; };
+__global__ void __launch_bounds__(256)
+row_stats_kernel(int n, const int *__restrict__ A_i, const double *__restrict__ A_a, RowStats *__restrict__ part) {
+  __shared__ RowStats sh[256];
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  RowStats s;
+  s.min_e = 0x7fffffff; s.max_e = 0; s.min_rs = 1e300; s.max_rs = -1e300; s.min_w = 1e300; s.max_w = 0.0;
+  if (r < n) {
+    const int b = A_i[r], e = A_i[r + 1];
+    double sum = 0.0;
+    for (int k = b; k < e; k++) {
+      const double v = A_a[k];
+      sum += v;
+      s.min_w = v < s.min_w ? v : s.min_w;
+      if (v != 1.0) s.max_w = v > s.max_w ? v : s.max_w;
+    }
+    s.min_e = s.max_e = e - b;
+    s.min_rs = s.max_rs = sum;
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (threadIdx.x < off) {
+      RowStats &a = sh[threadIdx.x];
+      const RowStats &c = sh[threadIdx.x + off];
+      a.min_e = min(a.min_e, c.min_e); a.max_e = max(a.max_e, c.max_e);
+      a.min_rs = fmin(a.min_rs, c.min_rs); a.max_rs = fmax(a.max_rs, c.max_rs);
+      a.min_w = fmin(a.min_w, c.min_w); a.max_w = fmax(a.max_w, c.max_w);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[blockIdx.x] = sh[0];
+}
+}  // namespace
+
+extern "C" int b200_csr_row_stats(b200_handle h, b200_csr A, int *min_entries, int *max_entries, double *min_rowsum,
+                                  double *max_rowsum, double *min_weight, double *max_weight) {
+  if (!A || !A->a) B200_FAIL("row stats: matrix with values required");
+  int mn = 0, mx = 0;
+  double rs0 = 0.0, rs1 = 0.0, w0 = 1.0, w1 = 0.0;                    // the reference's values for an empty matrix
+  if (A->nrows > 0) {
+    const int nb = b200_grid(A->nrows, 256);
+    RowStats *d = nullptr;
+    B200_TRY(b200_dalloc<RowStats>(h, &d, nb));
+    row_stats_kernel<<<nb, 256, 0, h->stream>>>(A->nrows, A->i, A->a, d);
+    B200_LAUNCH_CHECK();
+    std::vector<RowStats> p(nb);
+    B200_CUDA(cudaMemcpyAsync(p.data(), d, sizeof(RowStats) * nb, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, d));
+    mn = p[0].min_e; mx = p[0].max_e; rs0 = p[0].min_rs; rs1 = p[0].max_rs; w0 = p[0].min_w; w1 = p[0].max_w;
+    for (int k = 1; k < nb; k++) {
+      mn = std::min(mn, p[k].min_e); mx = std::max(mx, p[k].max_e);
+      rs0 = std::min(rs0, p[k].min_rs); rs1 = std::max(rs1, p[k].max_rs);
+      w0 = std::min(w0, p[k].min_w); w1 = std::max(w1, p[k].max_w);
+    }
+    if (A->nnz == 0) w0 = 1.0;
+  }
+  if (min_entries) *min_entries = mn;
+  if (max_entries) *max_entries = mx;
+  if (min_rowsum) *min_rowsum = rs0;
+  if (max_rowsum) *max_rowsum = rs1;
+  if (min_weight) *min_weight = w0;
+  if (max_weight) *max_weight = w1;
+  return 0;
+}

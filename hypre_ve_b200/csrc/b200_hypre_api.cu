@@ -18,6 +18,7 @@
 // multi-GPU path is reached through b200_dist_* (INTEGRATION.md shows the MPI-build binding).
 #include "b200_internal.h"
 #include "../../include/HYPRE_b200.h"
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <string>
@@ -113,6 +114,75 @@ const Neutral kNeutral[] = {
     {"GSMG", 0, "GSMG"},                               {"CoarsenCutFactor", 0, "coarsening cut factor"},
     {"Redundant", 0, "redundant coarse solves"},       {"SeqThreshold", 0, "sequential coarse AMG"},
 };
+
+int ndigits(long long number) {            // utilities/hypre_printf.c:115
+  int d = 0;
+  while (number) { number /= 10; d++; }
+  return d;
+}
+// the two tables and the complexity lines of hypre_BoomerAMGSetupStats (parcsr_ls/par_stats.c:22-1060), one rank
+int setup_stats(b200_handle h, HYPRE_Solver s) {
+  b200_amg amg = s->amg;
+  auto &st = s->stored;
+  const int nl = b200_amg_num_levels(amg);
+  std::vector<long long> rows(nl), nnz(nl);
+  for (int l = 0; l < nl; l++) {
+    int nr = 0, nc = 0, nz = 0;
+    b200_csr_dims(b200_amg_level_A(amg, l), &nr, &nc, &nz);
+    rows[l] = nr; nnz[l] = nz;
+  }
+  printf("\n\n Num MPI tasks = 1\n\n Num OpenMP threads = 1\n\n\nBoomerAMG SETUP PARAMETERS:\n\n");
+  printf(" Max levels = %d\n Num levels = %d\n\n", (int)st["MaxLevels"], nl);
+  printf(" Strength Threshold = %f\n", st["StrongThreshold"]);
+  printf(" Interpolation Truncation Factor = %f\n", st["TruncFactor"]);
+  printf(" Maximum Row Sum Threshold for Dependency Weakening = %f\n\n", st["MaxRowSum"]);
+  printf(" Coarsening Type = PMIS \n");
+  const int agg = (int)st["AggNumLevels"];
+  if (agg > 0) printf("\n No. of levels of aggressive coarsening: %d\n\n Interpolation on agg. levels= multipass interpolation\n", agg);
+  printf(" measures are determined locally\n\n\n No global partition option chosen.\n\n");
+  printf(" Interpolation = extended+i interpolation\n");
+  printf("\nOperator Matrix Information:\n\n");
+  int nd[4];
+  nd[0] = std::max(7, ndigits(rows[0])); nd[1] = std::max(8, ndigits(nnz[0])); nd[2] = 4;
+  for (int l = 0; l < nl; l++) nd[2] = std::max(ndigits(rows[l] ? nnz[l] / rows[l] : 0), nd[2]);
+  nd[2] += 2; nd[3] = nd[0] + nd[1] + nd[2];
+  printf("%*s", nd[0] + 13, "nonzero"); printf("%*s", nd[1] + 15, "entries/row"); printf("%18s\n", "row sums");
+  printf("%s %*s ", "lev", nd[0], "rows"); printf("%*s", nd[1], "entries");
+  printf("%7s %5s %4s", "sparse", "min", "max"); printf("%*s %8s %11s\n", nd[2] + 2, "avg", "min", "max");
+  for (int i = 0; i < 49 + nd[3]; i++) printf("=");
+  printf("\n");
+  double num_mem = 0, num_coeffs = 0, num_vars = 0;
+  for (int l = 0; l < nl; l++) {
+    int mn = 0, mx = 0;
+    double r0 = 0, r1 = 0;
+    CALL(b200_csr_row_stats(h, b200_amg_level_A(amg, l), &mn, &mx, &r0, &r1, nullptr, nullptr), "setup stats");
+    const double sparse = (double)nnz[l] / ((double)rows[l] * (double)rows[l]);
+    printf("%3d %*lld %*.0f  %0.3f  %4d %4d", l, nd[0], rows[l], nd[1], (double)nnz[l], sparse, mn, mx);
+    printf("  %*.1f  %10.3e  %10.3e\n", nd[2], (double)nnz[l] / (double)rows[l], r0, r1);
+    num_mem += (double)nnz[l]; num_coeffs += (double)nnz[l]; num_vars += (double)rows[l];
+  }
+  nd[0] = 5;                                                       // par_stats.c:698-709
+  if (nl > 1) nd[0] = std::max(ndigits(rows[0]), nd[0]);
+  printf("\n\nInterpolation Matrix Information:\n");
+  printf("%*s ", 2 * nd[0] + 21, "entries/row"); printf("%10s %10s %19s\n", "min", "max", "row sums");
+  printf("lev %*s x %-*s min  max  avgW", nd[0], "rows", nd[0], "cols"); printf("%11s %11s %9s %11s\n", "weight", "weight", "min", "max");
+  for (int i = 0; i < 70 + 2 * nd[0]; i++) printf("=");
+  printf("\n");
+  for (int l = 0; l + 1 < nl; l++) {
+    b200_csr P = b200_amg_level_P(amg, l);
+    int nr = 0, nc = 0, nz = 0, mn = 0, mx = 0;
+    double r0 = 0, r1 = 0, w0 = 0, w1 = 0;
+    b200_csr_dims(P, &nr, &nc, &nz);
+    CALL(b200_csr_row_stats(h, P, &mn, &mx, &r0, &r1, &w0, &w1), "setup stats");
+    printf("%3d %*d x %-*d %3d  %3d", l, nd[0], nr, nd[0], nc, mn, mx);
+    printf("  %4.1f  %10.3e  %10.3e  %10.3e  %10.3e\n", (double)(nz - nc) / (double)(nr - nc), w0, w1, r0, r1);
+    num_mem += (double)nz;
+  }
+  printf("\n\n     Complexity:    grid = %f\n", num_vars / (double)rows[0]);
+  printf("                operator = %f\n", num_coeffs / (double)nnz[0]);
+  printf("                memory = %f\n\n", num_mem / (double)nnz[0]);
+  return 0;
+}
 
 }  // namespace
 
@@ -696,6 +766,8 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   CALL(b200_amg_set_int(s->amg, "RelaxType", rdown), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxTypeUp", rup), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_setup(h, s->amg, A->A), "HYPRE_BoomerAMGSetup");
+  const int pl = (int)st["PrintLevel"];
+  if (pl == 1 || pl == 3) setup_stats(h, s);
   return g_error_flag;
 }
 HYPRE_Int HYPRE_BoomerAMGSolve(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {

@@ -67,6 +67,10 @@ int b200_csr_matvec(b200_handle h, double alpha, b200_csr A, const double *d_x,
  * (the reference's diagT / offdT, par_csr_matvec.c:553-597). */
 int b200_csr_matvecT(b200_handle h, double alpha, b200_csr A, const double *d_x,
                      double beta, const double *d_b, double *d_y);
+/* the per-matrix numbers of hypre_BoomerAMGSetupStats (parcsr_ls/par_stats.c:575-606, :866-925): entries per row,
+ * row sums (each row summed in storage order), and min weight / max weight over the entries != 1 (for P) */
+int b200_csr_row_stats(b200_handle h, b200_csr A, int *min_entries, int *max_entries, double *min_rowsum,
+                       double *max_rowsum, double *min_weight, double *max_weight);
 /* copy of A with the entries of every row sorted by column (hypre_CSRMatrixReorder's job for all columns):
  * the solve phase applies the coarse Galerkin operators from such a copy, see DESIGN.md section 3 */
 int b200_csr_sorted_copy(b200_handle h, b200_csr A, b200_csr *S);

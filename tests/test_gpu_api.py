@@ -133,6 +133,30 @@ def test_diagonal_scaled_pcg_matches_reference_driver(exe):
     assert its == rits and abs(rel / rrel - 1) < 1e-6
 
 
+def _stats_block(out):
+    """the setup statistics the reference prints at print_level 1: both tables and the complexity lines"""
+    a = out.index("Operator Matrix Information:")
+    b = out.index("memory = ", a)
+    b = out.index("\n", b)
+    return [l.rstrip() for l in out[a:b].splitlines()]
+
+
+@pytest.mark.parametrize("flags", [["-n", "12", "12", "12"], ["-n", "30", "28", "26"], ["-27pt", "-n", "14", "14", "14"],
+                                   ["-n", "20", "20", "20", "-agg_nl", "1"], ["-n", "16", "16", "16", "-c", "1", "1", "0.001"]])
+def test_setup_statistics_tables_equal_the_reference_drivers(exe, flags):
+    """hypre_BoomerAMGSetupStats (par_stats.c): "Operator Matrix Information", "Interpolation Matrix Information" and
+    the complexities printed by our Setup are the reference driver's lines, character for character"""
+    if not os.path.exists(REF_IJ):
+        pytest.skip("reference driver not built")
+    f = flags + ["-solver", "1", "-pmis", "-rlx", "18"]
+    rc, out = run([exe, "-laplacian"] + f)
+    assert rc == 0, out
+    rc2, ref = run([REF_IJ, "-laplacian"] + f, dict(os.environ, OMP_NUM_THREADS="1"))
+    assert rc2 == 0
+    mine, theirs = _stats_block(out), _stats_block(ref)
+    assert mine == theirs, "\n".join(mine) + "\n-----\n" + "\n".join(theirs)
+
+
 def test_driver_default_galerkin_product(exe):
     """no -mod_rap2 flag: the driver default (fused hypre_BoomerAMGBuildCoarseOperatorKT order)"""
     flags = ["-n", "50", "50", "50", "-solver", "1", "-pmis", "-rlx", "18"]
