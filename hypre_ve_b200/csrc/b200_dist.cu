@@ -741,9 +741,10 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   const int rdown = b200_amg_get_int(prm, "RelaxType");
   const int rup = b200_amg_get_int(prm, "RelaxTypeUp") >= 0 ? b200_amg_get_int(prm, "RelaxTypeUp") : rdown;
   auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
-  if (!((rdown == 18 && rup == 18) || (is_l1gs(rdown) && is_l1gs(rup))))
-    B200_FAIL("multi-GPU RelaxType: 18 (l1-Jacobi) or the l1 hybrid Gauss-Seidel family 8/13/14");
-  if (rdown != 18 && b200_amg_get_real(prm, "RelaxWt") != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  const bool jac = (rdown == 18 || rdown == 7) && rup == rdown;
+  if (!(jac || (is_l1gs(rdown) && is_l1gs(rup))))
+    B200_FAIL("multi-GPU RelaxType: 18 (l1-Jacobi), 7 (Jacobi) or the l1 hybrid Gauss-Seidel family 8/13/14");
+  if (!jac && b200_amg_get_real(prm, "RelaxWt") != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (b200_amg_get_int(prm, "InterpType") != 6 ||
       b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") < 0 ||
       b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
@@ -760,7 +761,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   cudaEventRecord(e0, h->stream);
   b200_dist_amg amg = new b200_dist_amg_s();
   amg->relax_wt = b200_amg_get_real(prm, "RelaxWt");
-  amg->gs = rdown != 18; amg->relax_down = rdown; amg->relax_up = rup;
+  amg->gs = !jac; amg->relax_down = rdown; amg->relax_up = rup;
   amg->gs_blocks = b200_amg_get_int(prm, "GSBlocks");
   dist_level L0;
   L0.A = A0; L0.n = A0->n;
@@ -1016,7 +1017,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
     // offd entries are part of the merged row (ams.c:651-657); option 4 counts them -- and the entries
     // outside the Gauss-Seidel block of the row -- with weight 1/2 (ams.c:3560-3625)
-    B200_TRY(b200_l1_norms_blocks(h, L.A->L, amg->gs ? 4 : 1, amg->gs ? amg->gs_blocks : 1, L.l1));
+    B200_TRY(b200_l1_norms_blocks(h, L.A->L, amg->gs ? 4 : (amg->relax_down == 7 ? 5 : 1), amg->gs ? amg->gs_blocks : 1, L.l1));
     if (amg->gs && (l < nl - 1 || L.A->global_rows > max_coarse)) {
       if (L.A->L->gs && b200_gs_plan_blocks(L.A->L->gs) != amg->gs_blocks) { B200_TRY(b200_gs_plan_destroy(h, L.A->L->gs)); L.A->L->gs = nullptr; }
       if (!L.A->L->gs) B200_TRY(b200_gs_plan_create(h, L.A->L, amg->gs_blocks, &L.A->L->gs));

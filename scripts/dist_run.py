@@ -16,6 +16,8 @@ ap.add_argument("--edge-per-gpu", type=int, default=0)
 ap.add_argument("--relax", type=int, default=18)
 ap.add_argument("--gs-blocks", type=int, default=1)
 ap.add_argument("--spmv-sweep", action="store_true")
+ap.add_argument("--agg-nl", type=int, default=0)
+ap.add_argument("--aniso", type=float, default=1.0, help="cz of -c 1 1 cz (config 4: 0.001)")
 ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -63,7 +65,7 @@ else:
     e = a.edge_per_gpu or 256
     dims = (e * P, e * Q, e * R)
 out["global_dims"] = list(dims)
-A = hb.DistMatrix.laplacian(h, comm, *dims, P, Q, R, a.stencil)
+A = hb.DistMatrix.laplacian(h, comm, *dims, P, Q, R, a.stencil, c=(1.0, 1.0, a.aniso))
 inf = A.info
 n, nnz = inf["local_rows"], inf["local_nnz"]
 if a.spmv_sweep:
@@ -78,7 +80,8 @@ if a.spmv_sweep:
     byts = 12.0 * gnnz + 20.0 * gn
     out.update(spmv_ms=ms, spmv_gbs=byts / ms / 1e6, algorithmic_gb=byts / 1e9)
 else:
-    prm = hb.Amg(h, RelaxType=a.relax, RelaxTypeUp=(14 if a.relax == 13 else a.relax), GSBlocks=a.gs_blocks)
+    prm = hb.Amg(h, RelaxType=a.relax, RelaxTypeUp=(14 if a.relax == 13 else a.relax), GSBlocks=a.gs_blocks, AggNumLevels=a.agg_nl,
+                 ModuleRAP2=0)
     b, x = A.vector(1.0), A.vector(0.0)
     res = []
     for k in range(a.steps + 1):
@@ -93,7 +96,7 @@ else:
         amg.destroy()
         if k:
             res.append((allmax(s_ms), allmax(v_ms)))
-    out.update(relax=a.relax, gs_blocks_per_gpu=a.gs_blocks, levels=nl, iterations=its, final_rel_res=rel,
+    out.update(agg_nl=a.agg_nl, c=[1.0, 1.0, a.aniso], relax=a.relax, gs_blocks_per_gpu=a.gs_blocks, levels=nl, iterations=its, final_rel_res=rel,
                setup_s=sum(r[0] for r in res) / len(res) / 1e3, solve_s=sum(r[1] for r in res) / len(res) / 1e3)
 if rank == 0:
     print(json.dumps(out))
