@@ -52,6 +52,27 @@ def spmv_traffic():
         return None
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line.  Native libraries print there too (NCCL's version banner, for one),
+    so file descriptor 1 is pointed at stderr for the whole run and the JSON line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -143,7 +164,7 @@ def reference_arm(a):
         "e2e": {"value": per_step, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -253,7 +274,7 @@ def main_dist(a, rank, world, local_rank):
         "clocks": sampler.summary(),
     }
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     A.destroy()
     dist.destroy_process_group()
     return 0
@@ -268,11 +289,10 @@ def main():
     ap.add_argument("--edge", dest="n", type=int, default=N1, help="grid edge per GPU (default: config 2, 256)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
+    claim_stdout()
     if a.impl == "reference":
         return reference_arm(a)
 
-    # stdout carries exactly one JSON line: NCCL's own log lines (version banner, NCCL_DEBUG output) go to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     import hypre_ve_b200 as hb
@@ -405,7 +425,7 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "s", "cores": host_threads(), "kind": "reference",
                                     "sample": "unavailable: %s" % e}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     A.destroy()
     h.close()
     if world > 1:
