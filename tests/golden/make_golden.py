@@ -14,9 +14,22 @@ CASES = {
     "lap27_10_pmis_rlx18_modrap.bin": ["-n", "10", "10", "10", "-27pt"],
     "aniso_12_pmis_rlx18_modrap.bin": ["-n", "12", "12", "12", "-c", "1", "1", "0.001"],
 }
+# features added after the first fixtures: full flag lists, (threads = Gauss-Seidel blocks)
+MORE = {
+    "lap7_11_pmis_rlx18_defaultrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "18"], 1),          # fused (R A) P, the driver default
+    "lap7_12x11x9_agg1_modrap.bin": (["-n", "12", "11", "9", "-pmis", "-rlx", "18", "-mod_rap2", "1", "-agg_nl", "1"], 1),
+    "aniso_11_agg2_defaultrap.bin": (["-n", "11", "11", "11", "-c", "1", "1", "0.001", "-pmis", "-rlx", "18", "-agg_nl", "2"], 1),
+    "lap7_11_gs1314_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-mod_rap2", "1"], 1),               # library default 13 down / 14 up
+    "lap7_11_gs8_blocks4_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "8", "-mod_rap2", "1"], 4),
+    "lap27_8_rlx7_modrap.bin": (["-n", "8", "8", "8", "-27pt", "-pmis", "-rlx", "7", "-mod_rap2", "1"], 1),
+}
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="1")
     for name, args in CASES.items():
         out = subprocess.run([REF] + args + COMMON + ["-o", os.path.join(HERE, name)], env=env, check=True,
                              capture_output=True, text=True).stdout
+        print(name, out.splitlines()[1])
+    for name, (args, threads) in MORE.items():
+        out = subprocess.run([REF] + args + ["-keepT", "1", "-o", os.path.join(HERE, name)], check=True, capture_output=True,
+                             text=True, env=dict(os.environ, OMP_NUM_THREADS=str(threads))).stdout
         print(name, out.splitlines()[1])
