@@ -20,7 +20,6 @@ namespace {
 
 constexpr int NT = B200_SPMV_NT;              // threads per CTA
 constexpr int CAP = 4096;                     // shared-memory product slots per CTA (32 KB)
-constexpr int MAX_TILE = B200_SPMV_MAX_TILE;  // tile (nnz per CTA) upper bound; CAP - MAX_TILE bounds the longest row
 }
 constexpr int MAX_TILE_DEFAULT = B200_SPMV_MAX_TILE;
 namespace {

@@ -203,20 +203,6 @@ __global__ void gselim_kernel2(int n, const double *__restrict__ A_mat, double *
   }
   if (A[0] != 0.0) x[0] /= A[0];
 }
-__global__ void pcg_alpha_kernel2(double *sc) { sc[4] = sc[0] / sc[1]; sc[2] = sc[0]; }
-__global__ void pcg_update_xr_kernel2(size_t n, const double *__restrict__ sc, const double *__restrict__ p,
-                                      const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
-  const double alpha = sc[4];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) { x[i] += alpha * p[i]; r[i] += -alpha * s[i]; }
-}
-__global__ void pcg_beta_kernel2(double *sc) { sc[5] = sc[0] / sc[2]; }
-__global__ void pcg_update_p_kernel2(size_t n, const double *__restrict__ sc, const double *__restrict__ s, double *__restrict__ p) {
-  const double beta = sc[5];
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = beta * p[i] + 1.0 * s[i];
-}
-
 inline int vgrid(b200_handle h, size_t n) {
   size_t g = (n + 255) / 256, cap = (size_t)h->num_sm * 8;
   return (int)(g < cap ? (g ? g : 1) : cap);

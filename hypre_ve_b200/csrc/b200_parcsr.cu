@@ -148,10 +148,6 @@ __global__ void lookup_kernel(int n, const int *__restrict__ gj, int ncols, cons
   j[k] = lo;
 }
 
-__global__ void axpby_inplace_kernel(int n, double alpha, const double *__restrict__ t, double *__restrict__ y) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] += alpha * t[i];
-}
 
 }  // namespace
 

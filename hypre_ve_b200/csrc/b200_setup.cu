@@ -480,10 +480,6 @@ __global__ void transpose_fill_kernel(int nnz, const int *__restrict__ perm, con
   T_j[k] = rows[src];
   if (T_a) T_a[k] = A_a[src];
 }
-__global__ void zero_int_kernel(size_t n, int *x, int v) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) x[i] = v;
-}
 
 // ==========================================================================================
 // SpGEMM C = A*B (csr_matop.c:295-473)

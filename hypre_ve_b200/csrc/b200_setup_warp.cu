@@ -513,21 +513,6 @@ __global__ void max_rowlen_kernel(int n, const int *__restrict__ A_i, int *__res
   for (int off = 16; off > 0; off >>= 1) len = max(len, __shfl_down_sync(FULL, len, off));
   if ((threadIdx.x & 31) == 0 && len > 0) atomicMax(out_max, len);
 }
-__global__ void extpi_max_ub_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ S_j,
-                                    const int *__restrict__ cf, int *__restrict__ out_max) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  int ub = 0;
-  if (i < n && cf[i] < 0 && cf[i] != -3) {
-    for (int jj = S_i[i]; jj < S_i[i + 1]; jj++) {
-      int i1 = S_j[jj];
-      ub += 1;
-      if (cf[i1] < 0 && cf[i1] != -3) ub += S_i[i1 + 1] - S_i[i1];
-    }
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) ub = max(ub, __shfl_down_sync(FULL, ub, off));
-  if ((threadIdx.x & 31) == 0 && ub > 0) atomicMax(out_max, ub);
-}
 __global__ void fill_int_kernel(size_t n, int v, int *x) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
   for (; i < n; i += stride) x[i] = v;

@@ -103,7 +103,7 @@ spmv_pipe_kernel(const int *__restrict__ A_i, const int *__restrict__ A_j, const
   for (int k = 0; k < ntiles; k++) {
     const int stage = k % NSTAGE;
     const unsigned parity = (unsigned)((k / NSTAGE) & 1);
-    const int r0 = m.x, r1 = m.y, e0 = m.z, e1 = m.w;
+    const int r0 = m.x, r1 = m.y, e0 = m.z;
     const int a0 = e0 & ~3, ra = r0 & ~3;
     // prefetches for later: next tile's metadata (all threads) and the refill tile's metadata (thread 0)
     int4 m_next = m, m_refill = m;
