@@ -28,6 +28,7 @@ struct b200_level {
   b200_csr S = nullptr;     // kept only when KeepS
   int *cf = nullptr;        // CF marker {1,-1}
   double *l1 = nullptr;     // l1 norms
+  b200_cheby_s *cheby = nullptr;   // Chebyshev smoother data (relax 16)
   double *F = nullptr, *U = nullptr, *T = nullptr;   // rhs, iterate, ping-pong iterate (levels >= 1; T also level 0)
   int n = 0;
 };
@@ -50,9 +51,10 @@ struct b200_amg_s {
     ip = {{"CoarsenType", 8}, {"InterpType", 6}, {"PMaxElmts", 4}, {"RelaxType", 18}, {"MaxLevels", 25},
           {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"NumSweeps", 1}, {"AggNumLevels", 0}, {"ModuleRAP2", 1},
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
-          {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
+          {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"ChebyOrder", 2}, {"ChebyEigEst", 10},
+          {"ChebyVariant", 0}, {"ChebyScale", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
-          {"OuterWt", 1.0}, {"Tol", 0.0}};
+          {"OuterWt", 1.0}, {"Tol", 0.0}, {"ChebyFraction", 0.3}};
   }
 };
 
@@ -171,6 +173,7 @@ static int free_levels(b200_handle h, b200_amg amg) {
     B200_TRY(b200_csr_destroy(h, L.R));
     B200_TRY(b200_csr_destroy(h, L.S));
     B200_TRY(b200_dfree(h, L.cf)); B200_TRY(b200_dfree(h, L.l1));
+    B200_TRY(b200_cheby_destroy(h, L.cheby));
     B200_TRY(b200_dfree(h, L.F)); B200_TRY(b200_dfree(h, L.U)); B200_TRY(b200_dfree(h, L.T));
   }
   amg->lv.clear();
@@ -215,12 +218,13 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   auto is_gs = [](int t) { return t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14; };
   auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
   auto is_jac = [](int t) { return t == 18 || t == 7; };
-  if (!((is_jac(rdown) && rup == rdown) || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
-    B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), 7 (weighted Jacobi), the l1 hybrid Gauss-Seidel family "
-              "8/13/14 and the hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
-  if (!is_jac(rdown) && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  const bool cheby = rdown == 16 && rup == 16;
+  if (!((is_jac(rdown) && rup == rdown) || cheby || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
+    B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), 7 (weighted Jacobi), 16 (Chebyshev), the l1 hybrid "
+              "Gauss-Seidel family 8/13/14 and the hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
+  if (!is_jac(rdown) && !cheby && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (ip["GSBlocks"] < 1) B200_FAIL("GSBlocks must be >= 1");
-  amg->gs = !is_jac(rdown);
+  amg->gs = !is_jac(rdown);                  // in-place smoothers (Gauss-Seidel family, Chebyshev) use amg_cycle_gs
   amg->relax_down = rdown; amg->relax_up = rup;
   if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
   if (ip["AggNumLevels"] < 0) B200_FAIL("AggNumLevels must be >= 0");
@@ -341,7 +345,10 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
         B200_TRY(b200_l1_norms_blocks(h, L.A, amg->gs ? 4 : (rdown == 7 ? 5 : 1), amg->gs ? ip["GSBlocks"] : 1, L.l1));
       }
     }
-    if (l < nl - 1 || !amg->coarse_ge) {
+    if (cheby && (l < nl - 1 || !amg->coarse_ge))           // par_amg_setup.c:3137-3160
+      B200_TRY(b200_cheby_setup(h, L.A, ip["ChebyEigEst"], ip["ChebyOrder"], rp["ChebyFraction"], ip["ChebyVariant"],
+                                ip["ChebyScale"], &L.cheby));
+    if ((l < nl - 1 || !amg->coarse_ge) && !cheby) {
       if (amg->gs) {
         if (L.A->gs && b200_gs_plan_blocks(L.A->gs) != ip["GSBlocks"]) { B200_TRY(b200_gs_plan_destroy(h, L.A->gs)); L.A->gs = nullptr; }
         if (!L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, ip["GSBlocks"], &L.A->gs));
@@ -380,7 +387,9 @@ static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const
 // One V(1,1) cycle (par_cycle.c:255-622). u_zero: the caller guarantees u == 0 on entry
 // (PCG clears the vector before every preconditioner application, pcg.c:434,:568), which lets
 // the first sweep on every level skip its SpMV: u + (f - A*0)/l1 == f/l1 exactly.
+// one in-place relaxation call: Gauss-Seidel family or Chebyshev
 static int gs_relax(b200_handle h, b200_level &L, int type, const double *f, double *u, bool zero) {
+  if (type == 16) return b200_cheby_solve(h, L.cheby, L.As, zero, f, u);      // par_cycle.c:440-452
   return b200_gs_relax(h, L.A->gs, L.A, type, zero, f, L.l1, u);
 }
 

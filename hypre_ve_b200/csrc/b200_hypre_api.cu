@@ -580,7 +580,8 @@ HYPRE_Int HYPRE_BoomerAMGCreate(HYPRE_Solver *solver) {
                {"KeepTranspose", 0}, {"Tol", 1e-7}, {"MaxIter", 20}, {"MinIter", 0}, {"RelaxOrder", 0}, {"NumSweeps", 1},
                {"CycleType", 1}, {"MaxLevels", 25}, {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"AggNumLevels", 0},
                {"NumFunctions", 1}, {"StrongThreshold", 0.25}, {"MaxRowSum", 0.9}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
-               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}, {"GSBlocks", 1}};
+               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}, {"GSBlocks", 1},
+               {"ChebyOrder", 2}, {"ChebyEigEst", 10}, {"ChebyVariant", 0}, {"ChebyScale", 1}, {"ChebyFraction", 0.3}};   // par_amg.c:215-220
   for (const Neutral &nv : kNeutral) s->stored[nv.name] = nv.value;
   *solver = s;
   return g_error_flag;
@@ -759,8 +760,8 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   if (st.count("CycleNumSweeps3") && st["CycleNumSweeps3"] != 1) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: only one coarse sweep\n"); return err(HYPRE_ERROR_GENERIC); }
   static const char *ints[] = {"CoarsenType", "InterpType", "PMaxElmts", "MaxLevels", "MaxCoarseSize", "MinCoarseSize", "NumSweeps",
                                "AggNumLevels", "ModuleRAP2", "RAP2", "KeepTranspose", "RelaxOrder", "MaxIter", "MinIter", "CycleType",
-                               "NumFunctions", "PrintLevel", "GSBlocks"};
-  static const char *reals[] = {"StrongThreshold", "MaxRowSum", "TruncFactor", "RelaxWt", "OuterWt", "Tol"};
+                               "NumFunctions", "PrintLevel", "GSBlocks", "ChebyOrder", "ChebyEigEst", "ChebyVariant", "ChebyScale"};
+  static const char *reals[] = {"StrongThreshold", "MaxRowSum", "TruncFactor", "RelaxWt", "OuterWt", "Tol", "ChebyFraction"};
   for (const char *k : ints) CALL(b200_amg_set_int(s->amg, k, (int)st[k]), "HYPRE_BoomerAMGSetup");
   for (const char *k : reals) CALL(b200_amg_set_real(s->amg, k, st[k]), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxType", rdown), "HYPRE_BoomerAMGSetup");

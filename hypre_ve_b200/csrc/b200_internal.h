@@ -123,4 +123,10 @@ int b200_create_2nd_s_ex(b200_handle h, b200_csr S, int n_owned, const int *d_cf
 int b200_correct_cf(b200_handle h, int n_owned, const int *d_cfn, int *d_cf);
 int b200_multipass_ex(b200_handle h, b200_csr A, b200_csr S, int n, int n_ext, int *d_cf, const int *d_f2c, int ncoarse,
                       const b200_agg_hooks *hooks, b200_csr *out);
+// Chebyshev smoother, relax 16 (b200_cheby.cu)
+struct b200_cheby_s;
+int b200_cheby_setup(b200_handle h, b200_csr A, int eig_est, int order, double fraction, int variant, int scale,
+                     b200_cheby_s **out);
+int b200_cheby_solve(b200_handle h, b200_cheby_s *C, b200_csr As, bool zero, const double *f, double *u);
+int b200_cheby_destroy(b200_handle h, b200_cheby_s *c);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);

@@ -399,7 +399,8 @@ static void gselim(double *A, double *x, int n)
 
 #define MAXLEV 25
 typedef struct { int nl; csr_t A[MAXLEV], P[MAXLEV], R[MAXLEV], S[MAXLEV]; int *cf[MAXLEV]; double *l1[MAXLEV];
-                 double *F[MAXLEV], *U[MAXLEV], *V; double *ge; int ge_n; } amg_t;
+                 double *F[MAXLEV], *U[MAXLEV], *V; double *ge; int ge_n;
+                 double *cheby_ds[MAXLEV], cheby_coefs[MAXLEV][5], max_eig[MAXLEV], min_eig[MAXLEV]; } amg_t;
 
 /* ---- setup loop: parcsr_ls/par_amg_setup.c:889-2890 for coarsen 8 / interp 6 / mod_rap2 1 ---- */
 /* ---- aggressive coarsening (par_amg_setup.c:1239-1256, :1590-1605), one rank ------------------------------ */
@@ -543,6 +544,160 @@ static csr_t multipass(const csr_t *A, const csr_t *S, int *cf, int *ncoarse_out
 }
 
 static int g_agg_nl = 0, g_mod_rap2 = 0;
+
+/* ---- Chebyshev smoother (relax 16): parcsr_ls/par_cheby.c + hypre_ParCSRMaxEigEstimateCG (par_relax_more.c:115-330) ---- */
+/* eigenvalues of the symmetric tridiagonal matrix (d[0..n-1]; e[i] couples i-1 and i), ascending, by the implicit QL
+ * iteration.  The reference calls the EISPACK routine tql1 (hypre_LINPACKcgtql1); any backward-stable method returns
+ * the same values to a few ulp, which is all the Chebyshev coefficients need. */
+static void tridiag_eigenvalues(int n, double *d, double *e)
+{
+   int l, m, i, iter;
+   for (i = 1; i < n; i++) e[i - 1] = e[i];
+   if (n > 0) e[n - 1] = 0.0;
+   for (l = 0; l < n; l++)
+   {
+      iter = 0;
+      do
+      {
+         for (m = l; m < n - 1; m++)
+         {
+            double dd = fabs(d[m]) + fabs(d[m + 1]);
+            if (fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+         }
+         if (m != l)
+         {
+            if (iter++ == 60) break;
+            double g = (d[l + 1] - d[l]) / (2.0 * e[l]), r = sqrt(g * g + 1.0);
+            g = d[m] - d[l] + e[l] / (g + (g >= 0 ? fabs(r) : -fabs(r)));
+            double sn = 1.0, c = 1.0, p = 0.0;
+            for (i = m - 1; i >= l; i--)
+            {
+               double f = sn * e[i], b = c * e[i];
+               r = sqrt(f * f + g * g);
+               e[i + 1] = r;
+               if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; break; }
+               sn = f / r; c = g / r;
+               g = d[i + 1] - p;
+               r = (d[i] - g) * sn + 2.0 * c * b;
+               p = sn * r;
+               d[i + 1] = g + p;
+               g = c * r - b;
+            }
+            if (r == 0.0 && i >= l) continue;
+            d[l] -= p; e[l] = g; e[m] = 0.0;
+         }
+      } while (m != l);
+   }
+   for (i = 1; i < n; i++) { double v = d[i]; int k = i - 1; while (k >= 0 && d[k] > v) { d[k + 1] = d[k]; k--; } d[k + 1] = v; }
+}
+static int g_cheby_order = 2, g_cheby_eig_est = 10, g_cheby_variant = 0, g_cheby_scale = 1;
+static double g_cheby_fraction = 0.3;
+static void cheby_setup(amg_t *g, int l)
+{
+   const csr_t *A = &g->A[l];
+   int n = A->n, i, j, max_iter = g_cheby_eig_est;
+   if (n < max_iter) max_iter = n;
+   double *r = (double *) xmalloc(sizeof(double) * n), *p = (double *) xcalloc(n, sizeof(double)), *sv = (double *) xcalloc(n, sizeof(double));
+   double *ds = (double *) xmalloc(sizeof(double) * n), *u = (double *) xcalloc(n, sizeof(double));
+   double *td = (double *) xcalloc(max_iter + 1, sizeof(double)), *to = (double *) xcalloc(max_iter + 1, sizeof(double));
+   g_seed = 1;                                                   /* hypre_ParVectorSetRandomValues(r, 1), vector.c:286-300 */
+   for (i = 0; i < n; i++) r[i] = 2.0 * hrand() - 1.0;
+   for (i = 0; i < n; i++) ds[i] = g_cheby_scale ? 1 / sqrt(A->a[A->i[i]]) : 1.0;
+   double gamma = dot(n, r, p), gamma_old, beta = 1.0;
+   i = 0;
+   while (i < max_iter)
+   {
+      memcpy(sv, r, sizeof(double) * n);
+      gamma_old = gamma;
+      gamma = dot(n, r, sv);
+      if (i == 0) { beta = 1.0; memcpy(p, sv, sizeof(double) * n); }
+      else { beta = gamma / gamma_old; for (j = 0; j < n; j++) p[j] = sv[j] + beta * p[j]; }
+      if (g_cheby_scale)
+      {
+         for (j = 0; j < n; j++) u[j] = ds[j] * p[j];
+         matvec(1.0, A, u, 0.0, u, sv);
+         for (j = 0; j < n; j++) sv[j] = ds[j] * sv[j];
+      }
+      else matvec(1.0, A, p, 0.0, p, sv);
+      double sdotp = dot(n, sv, p), alpha = gamma / sdotp, alphainv = 1.0 / alpha;
+      td[i + 1] = alphainv; td[i] *= beta; td[i] += alphainv;
+      to[i + 1] = alphainv; to[i] *= sqrt(beta);
+      for (j = 0; j < n; j++) r[j] += -alpha * sv[j];
+      i++;
+   }
+   tridiag_eigenvalues(i, td, to);
+   double max_eig = td[i - 1], min_eig = td[0];
+   g->max_eig[l] = max_eig; g->min_eig[l] = min_eig;
+   /* hypre_ParCSRRelax_Cheby_Setup (par_cheby.c:41-187) */
+   int order = g_cheby_order; if (order > 4) order = 4; if (order < 1) order = 1;
+   int co = order - 1;
+   double ub = max_eig * 1.1, lb = (ub - min_eig) * g_cheby_fraction + min_eig, theta = (ub + lb) / 2, delta = (ub - lb) / 2, den;
+   double *c = g->cheby_coefs[l];
+   if (g_cheby_variant == 1)
+   {
+      switch (co)
+      {
+         case 0: c[0] = 1.0 / theta; break;
+         case 1: den = (theta * theta + delta * theta); c[0] = (delta + 2 * theta) / den; c[1] = -1.0 / den; break;
+         case 2: den = 2 * delta * theta * theta - delta * delta * theta - pow(delta, 3) + 2 * pow(theta, 3);
+                 c[0] = (4 * delta * theta - pow(delta, 2) + 6 * pow(theta, 2)) / den; c[1] = -(2 * delta + 6 * theta) / den; c[2] = 2 / den; break;
+         case 3: den = -(4 * delta * pow(theta, 3) - 3 * pow(delta, 2) * pow(theta, 2) - 3 * pow(delta, 3) * theta + 4 * pow(theta, 4));
+                 c[0] = (6 * pow(delta, 2) * theta - 12 * delta * pow(theta, 2) + 3 * pow(delta, 3) - 16 * pow(theta, 3)) / den;
+                 c[1] = (12 * delta * theta - 3 * pow(delta, 2) + 24 * pow(theta, 2)) / den; c[2] = -(4 * delta + 16 * theta) / den; c[3] = 4 / den; break;
+      }
+   }
+   else
+   {
+      switch (co)
+      {
+         case 0: c[0] = 1.0 / theta; break;
+         case 1: den = delta * delta - 2 * theta * theta; c[0] = -4 * theta / den; c[1] = 2 / den; break;
+         case 2: den = 3 * (delta * delta) * theta - 4 * (theta * theta * theta);
+                 c[0] = (3 * delta * delta - 12 * theta * theta) / den; c[1] = 12 * theta / den; c[2] = -4 / den; break;
+         case 3: den = pow(delta, 4) - 8 * delta * delta * theta * theta + 8 * pow(theta, 4);
+                 c[0] = (32 * pow(theta, 3) - 16 * delta * delta * theta) / den; c[1] = (8 * delta * delta - 48 * theta * theta) / den;
+                 c[2] = 32 * theta / den; c[3] = -8 / den; break;
+      }
+   }
+   g->cheby_ds[l] = ds;
+   free(r); free(p); free(sv); free(u); free(td); free(to);
+}
+/* hypre_ParCSRRelax_Cheby_Solve (par_cheby.c:190-345) */
+static void cheby_solve(amg_t *g, int l, const double *f, double *u)
+{
+   const csr_t *A = &g->A[l];
+   int n = A->n, i, j, order = g_cheby_order; if (order > 4) order = 4; if (order < 1) order = 1;
+   int co = order - 1;
+   const double *c = g->cheby_coefs[l], *ds = g->cheby_ds[l];
+   double *orig = (double *) xmalloc(sizeof(double) * n), *r = (double *) xmalloc(sizeof(double) * n);
+   double *v = (double *) xmalloc(sizeof(double) * n), *tmp = (double *) xmalloc(sizeof(double) * n);
+   if (!g_cheby_scale)
+   {
+      memcpy(r, f, sizeof(double) * n);
+      matvec(-1.0, A, u, 1.0, r, r);
+      for (i = 0; i < n; i++) { orig[i] = u[i]; u[i] = r[i] * c[co]; }
+      for (i = co - 1; i >= 0; i--)
+      {
+         matvec(1.0, A, u, 0.0, u, v);
+         for (j = 0; j < n; j++) u[j] = c[i] * r[j] + v[j];
+      }
+      for (i = 0; i < n; i++) u[i] = orig[i] + u[i];
+   }
+   else
+   {
+      matvec(-1.0, A, u, 0.0, u, tmp);
+      for (j = 0; j < n; j++) r[j] = ds[j] * (f[j] + tmp[j]);
+      for (j = 0; j < n; j++) { orig[j] = u[j]; u[j] = r[j] * c[co]; }
+      for (i = co - 1; i >= 0; i--)
+      {
+         for (j = 0; j < n; j++) tmp[j] = ds[j] * u[j];
+         matvec(1.0, A, tmp, 0.0, tmp, v);
+         for (j = 0; j < n; j++) u[j] = c[i] * r[j] + ds[j] * v[j];
+      }
+      for (j = 0; j < n; j++) u[j] = orig[j] + ds[j] * u[j];
+   }
+   free(orig); free(r); free(v); free(tmp);
+}
 static int g_relax_down = 18, g_relax_up = 18;   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
 static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
 {
@@ -590,6 +745,7 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
       int n = g->A[i].n;
       g->l1[i] = l1_norms(&g->A[i], g_relax_down == 18 ? 1 : (g_relax_down == 7 ? 5 : 4));      /* par_amg_setup.c:3018-3100 */
       g->F[i] = (double *) xcalloc(n, sizeof(double)); g->U[i] = (double *) xcalloc(n, sizeof(double));
+      if (g_relax_down == 16 && (i < g->nl - 1 || g->A[i].n > max_coarse)) cheby_setup(g, i);      /* par_amg_setup.c:3137-3160 */
    }
    g->V = (double *) xcalloc(g->A[0].n, sizeof(double));
    csr_t *Ac = &g->A[g->nl - 1];
@@ -639,6 +795,7 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
       for (i = 0; i < n; i++) u[i] += v[i] / l1[i];
       return;
    }
+   if (type == 16) { cheby_solve(g, l, f, u); return; }
    int classic = (type == 3 || type == 4 || type == 6);
    int fwd = (type == 3 || type == 13 || type == 6 || type == 8), bwd = (type == 4 || type == 14 || type == 6 || type == 8);
    if (!fwd && !bwd) { fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2); }

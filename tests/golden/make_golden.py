@@ -21,6 +21,7 @@ MORE = {
     "aniso_11_agg2_defaultrap.bin": (["-n", "11", "11", "11", "-c", "1", "1", "0.001", "-pmis", "-rlx", "18", "-agg_nl", "2"], 1),
     "lap7_11_gs1314_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-mod_rap2", "1"], 1),               # library default 13 down / 14 up
     "lap7_11_gs8_blocks4_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "8", "-mod_rap2", "1"], 4),
+    "lap7_11_cheby16_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "16", "-mod_rap2", "1"], 1),
     "lap27_8_rlx7_modrap.bin": (["-n", "8", "8", "8", "-27pt", "-pmis", "-rlx", "7", "-mod_rap2", "1"], 1),
 }
 if __name__ == "__main__":

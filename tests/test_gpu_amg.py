@@ -216,7 +216,7 @@ def test_vcycle_matches_reference_preconditioner(handle):
 def test_unsupported_configurations_fail_loudly(handle):
     import hypre_ve_b200 as hb
     A = hb.ParCsr.laplacian(handle, 8, 8, 8)
-    for k, v in [("CoarsenType", 10), ("InterpType", 0), ("RelaxType", 16), ("AggNumLevels", -1), ("RAP2", 1)]:
+    for k, v in [("CoarsenType", 10), ("InterpType", 0), ("RelaxType", 15), ("AggNumLevels", -1), ("RAP2", 1)]:
         amg = hb.Amg(handle)
         amg.set(k, v)
         with pytest.raises(hb.B200Error):
@@ -291,4 +291,27 @@ def test_weighted_jacobi_relax_7(handle, args, w):
     its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
     assert its == int(d["hdr"][4])
     assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("args", [["-n", 24, 20, 18], ["-n", 14, 14, 14, "-27pt"], ["-n", 20, 20, 20, "-c", 1, 1, 0.001],
+                                  ["-n", 40, 40, 40]])
+def test_chebyshev_smoother_relax_16(handle, args):
+    """relax 16 (par_cheby.c): CG-Lanczos spectrum estimate from the reference's random vector, order-2 polynomial;
+    iteration counts equal the reference's, residual history to 1e-10"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-pmis", "-rlx", 16, "-mod_rap2", 1])
+    nx, ny, nz = args[1:4]
+    A = hb.ParCsr.laplacian27(handle, nx, ny, nz) if "-27pt" in args else \
+        hb.ParCsr.laplacian(handle, nx, ny, nz, c=tuple(args[5:8]) if "-c" in args else (1.0, 1.0, 1.0))
+    amg = hb.Amg(handle, RelaxType=16)
+    amg.setup(A)
+    assert amg.num_levels == nlev(d)
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4]), (its, int(d["hdr"][4]))
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
     amg.destroy(); A.destroy()

@@ -55,6 +55,9 @@ GOLDEN_MORE = {
     "lap7_11_gs1314_modrap.bin": (["-n", 11, 11, 11, "-pmis", "-mod_rap2", 1], True),
     "lap7_11_gs8_blocks4_modrap.bin": (["-n", 11, 11, 11, "-pmis", "-rlx", 8, "-mod_rap2", 1, "-gs_blocks", 4], False),
     "lap27_8_rlx7_modrap.bin": (["-n", 8, 8, 8, "-27pt", "-pmis", "-rlx", 7, "-mod_rap2", 1], True),
+    # Chebyshev: the extreme Lanczos eigenvalues come from a different (equally stable) tridiagonal solver than the
+    # reference's EISPACK tql1 -> last-bit differences in the coefficients, hierarchy exact
+    "lap7_11_cheby16_modrap.bin": (["-n", 11, 11, 11, "-pmis", "-rlx", 16, "-mod_rap2", 1], False),
 }
 
 
