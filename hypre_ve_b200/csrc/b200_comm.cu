@@ -197,6 +197,34 @@ int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_
   return 0;
 }
 
+// k device-resident partial sums -> global sums on the host, added in rank order.  Over NCCL the partials go
+// device-to-device into the all-gather and come back with ONE copy + synchronisation (no host round trip first).
+int b200_comm_allreduce_sum_dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *h_out) {
+  if (k < 1 || (size_t)k * c->nranks > 64) B200_FAIL("allreduce_sum_dev: at most 64 values over all ranks");
+  if (c->nranks == 1 || c->backend != 1) {
+    B200_CUDA(cudaMemcpyAsync(h->h_pinned, d_vals, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    for (int j = 0; j < k; j++) h_out[j] = h->h_pinned[j];
+    return b200_comm_allreduce_sum(h, c, h_out, k);
+  }
+  const size_t need = sizeof(double) * (size_t)k * c->nranks;
+  if (c->stage_bytes < need) {
+    if (c->d_stage) B200_TRY(b200_dfree(h, c->d_stage));
+    char *p = nullptr;
+    B200_TRY(b200_dalloc<char>(h, &p, 4096));
+    c->d_stage = p; c->stage_bytes = 4096;
+  }
+  B200_NCCL(g_nccl.AllGather(d_vals, c->d_stage, sizeof(double) * k, ncclInt8, c->nccl, h->stream));
+  B200_CUDA(cudaMemcpyAsync(h->h_pinned, c->d_stage, need, cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  for (int j = 0; j < k; j++) {
+    double s = 0.0;
+    for (int r = 0; r < c->nranks; r++) s += h->h_pinned[(size_t)r * k + j];
+    h_out[j] = s;
+  }
+  return 0;
+}
+
 // deterministic global sums: gather the per-rank partials and add them in rank order
 int b200_comm_allreduce_sum(b200_handle h, b200_comm c, double *vals, int k) {
   if (c->nranks == 1) return 0;

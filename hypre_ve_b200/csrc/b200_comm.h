@@ -14,6 +14,7 @@ struct b200_xfer {
 int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> &sends, const std::vector<b200_xfer> &recvs);
 int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all);
 int b200_comm_allreduce_sum(b200_handle h, b200_comm c, double *vals, int k);
+int b200_comm_allreduce_sum_dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *h_out);
 int b200_comm_allreduce_sum_ll(b200_handle h, b200_comm c, long long *vals, int k);
 
 // Halo plan = hypre_ParCSRCommPkg (parcsr_mv/par_csr_communication.h:54-82) for one ghost set:

@@ -14,6 +14,7 @@
 // [owned | ghosts sorted by global id] and a SpMV is: pack -> grouped ncclSend/ncclRecv straight into
 // the ghost tail of x -> one streaming kernel.
 #include "b200_internal.h"
+#include <chrono>
 #include "b200_comm.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -147,6 +148,25 @@ __global__ void gather_kernel(int n, const int *__restrict__ perm, const T *__re
 __global__ void hist_kernel(int n, const int *__restrict__ key, int *__restrict__ cnt) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) atomicAdd(&cnt[key[k]], 1);
+}
+// histogram over a handful of bins (the owner rank of every entry): equal keys of a warp are counted with one
+// shared-memory atomic, a CTA adds its bins to the result once -- millions of entries on two or three counters
+// would serialise in L2 otherwise
+__global__ void hist_few_bins_kernel(int n, const int *__restrict__ key, int nbins, int *__restrict__ cnt) {
+  extern __shared__ int bins[];
+  for (int b = threadIdx.x; b < nbins; b += blockDim.x) bins[b] = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * blockDim.x;
+  for (int base = blockIdx.x * blockDim.x + (threadIdx.x & ~31); base < n; base += stride) {
+    const int k = base + lane;
+    const int v = k < n ? key[k] : -1;
+    const unsigned same = __match_any_sync(0xffffffffu, v);
+    if (v >= 0 && lane == __ffs(same) - 1) atomicAdd(&bins[v], __popc(same));
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+    if (bins[b]) atomicAdd(&cnt[b], bins[b]);
 }
 __global__ void cflag2_kernel(int n, const int *__restrict__ cf, int *__restrict__ flag) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -634,8 +654,11 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
     B200_LAUNCH_CHECK();
     iota_kernel2<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, idx);
     B200_LAUNCH_CHECK();
-    hist_kernel<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, owner, cntr);
-    B200_LAUNCH_CHECK();
+    {
+      const int want = b200_grid(nnz, 256), cap = h->num_sm * 8;
+      hist_few_bins_kernel<<<want < cap ? want : cap, 256, sizeof(int) * (R + 1), h->stream>>>(nnz, owner, R + 1, cntr);
+      B200_LAUNCH_CHECK();
+    }
     int bits = 1;
     while ((1 << bits) < R) bits++;
     size_t tb = 0;
@@ -745,6 +768,19 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->stream);
+  // B200_TRACE=1: wall-clock (stream-synchronised) time of every setup phase, per level, on stderr
+  const bool trace = getenv("B200_TRACE") != nullptr;
+  auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlast = 0;
+  int tlevel = 0;
+  auto mark = [&](const char *what) {
+    if (!trace) return;
+    cudaStreamSynchronize(h->stream);
+    const double t = tnow();
+    if (what) fprintf(stderr, "[b200 trace] rank %d level %d %-18s %8.3f ms\n", b200_comm_rank(c), tlevel, what, t - tlast);
+    tlast = t;
+  };
+  mark(nullptr);
   b200_dist_amg amg = new b200_dist_amg_s();
   amg->relax_wt = b200_amg_get_real(prm, "RelaxWt");
   amg->gs = !jac; amg->relax_down = rdown; amg->relax_up = rup;
@@ -759,12 +795,15 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     b200_dist_matrix A = L.A;
     const int n = A->n, ng = A->halo->ng;
     const long long fine_size = A->global_rows;
+    tlevel = level;
     // --- strength + PMIS on the localized operator (par_amg_setup.c:1035,:1114) -----------------
     b200_csr S = nullptr;
     B200_TRY(b200_strength(h, A->L, theta, mrs, &S));
+    mark("strength");
     int *cf = nullptr;                              // [n + ng]
     B200_TRY(b200_dalloc<int>(h, &cf, (size_t)n + ng + 1));
     B200_TRY(b200_pmis_dist(h, c, S, A->halo, seed, A->first_row, cf));
+    mark("pmis");
     const bool aggressive = level < agg_nl;
     // --- coarse numbering (par_coarse_parms.c:83-122): global coarse ids over [owned | ghost], -1 for F points ----
     auto number_coarse = [&](const int *cfv, int **f2c_out, int *nc_out, std::vector<int> *starts) -> int {
@@ -866,6 +905,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       return 0;
     };
     B200_TRY(build_extended());
+    mark("extended A,S");
     if (aggressive) {
       // second coarsening on the distance-two strength graph of the C points (par_amg_setup.c:1239-1256), then
       // hypre_BoomerAMGCorrectCFMarker (:1592).  S2's columns carry the global ids of the FIRST coarse numbering.
@@ -893,6 +933,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     int *f2c = nullptr, nc = 0;                     // [n + ng]: global coarse id or -1
     std::vector<int> cstarts;
     B200_TRY(number_coarse(cf, &f2c, &nc, &cstarts));
+    mark(aggressive ? "2nd pass + numbering" : "coarse numbering");
     const long long coarse_size = cstarts[R];
     if (coarse_size == 0 || coarse_size == fine_size) {       // par_amg_setup.c:1487-1525
       B200_TRY(b200_csr_destroy(h, S)); B200_TRY(b200_dfree(h, cf)); B200_TRY(b200_dfree(h, f2c));
@@ -926,6 +967,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_extpi_interp_ex(h, Abig2, Sbig2, cf_big, n, f2c_big, (int)coarse_size, trunc, pmax, &Pg));
       B200_TRY(b200_dfree(h, cf_big)); B200_TRY(b200_dfree(h, f2c_big));
     }
+    mark("interpolation");
     B200_TRY(b200_csr_destroy(h, Abig2)); B200_TRY(b200_csr_destroy(h, Sbig2));
     b200_halo_free(h, plan2);
     B200_TRY(b200_csr_destroy(h, S));
@@ -939,6 +981,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     // --- Galerkin product (par_csr_triplemat.c:606-871): Q = A*P with ghost rows of P, C = P^T * Q ---
     b200_csr Rg = nullptr;
     B200_TRY(dist_transpose(h, c, L.P, cstarts, &Rg));
+    mark("transpose");
     L.R = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_row, n, A->global_rows, A->row_starts, Rg);
     b200_csr AHg = nullptr;
     if (mod_rap2) {
@@ -964,7 +1007,9 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(fetch_rows(h, c, L.R->halo, A->G, &Aext));
       B200_TRY(stack_rows(h, A->G, Aext, &Abig));
       B200_TRY(b200_csr_destroy(h, Aext));
+      mark("RA: fetch+stack");
       B200_TRY(b200_csr_multiply_ex(h, L.R->L, Abig, 0, 0, A->global_cols, &RAg));
+      mark("RA: multiply");
       B200_TRY(b200_csr_destroy(h, Abig));
       b200_dist_matrix RAd = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_col, A->n_owned_cols, A->global_cols,
                                       A->col_starts, RAg);
@@ -973,7 +1018,9 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(fetch_rows(h, c, RAd->halo, Pg, &Pext));
       B200_TRY(stack_rows(h, Pg, Pext, &Pbig));
       B200_TRY(b200_csr_destroy(h, Pext));
+      mark("(RA)P: localize+fetch");
       B200_TRY(b200_csr_multiply_ex(h, RAd->L, Pbig, 1, cstarts[me], (int)coarse_size, &AHg));
+      mark("(RA)P: multiply");
       B200_TRY(b200_csr_destroy(h, Pbig));
       B200_TRY(b200_dist_matrix_destroy(h, RAd));
     }
@@ -982,6 +1029,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     B200_TRY(dist_localize(h, c, Ln.A));
     Ln.n = nc;
     B200_TRY(dist_localize(h, c, L.P));
+    mark("localize A_H, P");
     amg->lv.push_back(Ln);
     ++level;
     if (level == max_levels - 1 || coarse_size <= max_coarse) not_finished = false;
@@ -1011,6 +1059,8 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     amg->vtemp_cap = std::max(amg->vtemp_cap, L.cap);
     // setup-form copies are no longer needed below level 0 (level 0's belongs to the caller)
   }
+  tlevel = nl;
+  mark("vectors + l1 norms");
   B200_TRY(b200_dalloc<double>(h, &amg->Vtemp, amg->vtemp_cap));
   B200_CUDA(cudaMemsetAsync(amg->Vtemp, 0, sizeof(double) * amg->vtemp_cap, h->stream));
   // coarsest level: gather the dense matrix on every rank (par_gauss_elim.c:78-118)
@@ -1040,6 +1090,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_dfree(h, loc));
     }
   }
+  mark("coarse gather");
   cudaEventRecord(e1, h->stream);
   cudaEventSynchronize(e1);
   float ms = 0;
@@ -1160,11 +1211,19 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
   return 0;
 }
 
-static int dist_dot(b200_handle h, b200_comm c, int n, const double *x, const double *y, double *result) {
-  double v = 0;
-  B200_TRY(b200_vec_dot(h, n, x, y, &v));
-  B200_TRY(b200_comm_allreduce_sum(h, c, &v, 1));      // hypre_ParVectorInnerProd (par_vector.c:481-501)
-  *result = v;
+// hypre_ParVectorInnerProd (par_vector.c:481-501): local partial on the device, one all-gather, ranks added in order
+static int dist_dot(b200_handle h, b200_comm c, int n, const double *x, const double *y, double *d_scratch, double *result) {
+  B200_TRY(b200_vec_dot_dev(h, n, x, y, d_scratch));
+  return b200_comm_allreduce_sum_dev(h, c, d_scratch, 1, result);
+}
+// <x1,y1> and <x2,y2> with ONE exchange (the two inner products PCG needs at the same point of an iteration)
+static int dist_dot2(b200_handle h, b200_comm c, int n, const double *x1, const double *y1, const double *x2, const double *y2,
+                     double *d_scratch, double *r1, double *r2) {
+  B200_TRY(b200_vec_dot_dev(h, n, x1, y1, d_scratch));
+  B200_TRY(b200_vec_dot_dev(h, n, x2, y2, d_scratch + 1));
+  double out[2] = {0, 0};
+  B200_TRY(b200_comm_allreduce_sum_dev(h, c, d_scratch, 2, out));
+  *r1 = out[0]; *r2 = out[1];
   return 0;
 }
 
@@ -1187,25 +1246,24 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
   int rc = 0, i = 0;
   double bi_prod = 0, i_prod = 0, eps = tol * tol, gamma = 0, gamma_old = 0;
   do {
-    if ((rc = dist_dot(h, c, n, d_b, d_b, &bi_prod))) break;
+    if ((rc = dist_dot(h, c, n, d_b, d_b, sc, &bi_prod))) break;
     if (!(bi_prod > 0.0)) { rc = b200_vec_copy(h, n, d_b, d_x); if (h_norms) h_norms[0] = 0.0; break; }
     if ((rc = dist_spmv(h, c, A, xx, r, 0, -1.0, 1.0, d_b, nullptr))) break;       // r = b - A x
     if ((rc = precond(r, p))) break;
-    if ((rc = dist_dot(h, c, n, r, p, &gamma))) break;
-    if (h_norms) { double t = 0; if ((rc = dist_dot(h, c, n, r, r, &t))) break; h_norms[0] = std::sqrt(t); }
+    if (h_norms) { double t = 0; if ((rc = dist_dot2(h, c, n, r, p, r, r, sc, &gamma, &t))) break; h_norms[0] = std::sqrt(t); }
+    else if ((rc = dist_dot(h, c, n, r, p, sc, &gamma))) break;
     while ((i + 1) <= max_iter) {
       i++;
       if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr))) break;   // s = A p
       double sdotp = 0;
-      if ((rc = dist_dot(h, c, n, s, p, &sdotp))) break;
+      if ((rc = dist_dot(h, c, n, s, p, sc, &sdotp))) break;
       if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }
       const double alpha = gamma / sdotp;
       gamma_old = gamma;
       if ((rc = b200_vec_axpy(h, n, alpha, p, xx))) break;
       if ((rc = b200_vec_axpy(h, n, -alpha, s, r))) break;
       if ((rc = precond(r, s))) break;
-      if ((rc = dist_dot(h, c, n, r, s, &gamma))) break;
-      if ((rc = dist_dot(h, c, n, r, r, &i_prod))) break;
+      if ((rc = dist_dot2(h, c, n, r, s, r, r, sc, &gamma, &i_prod))) break;
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;
       if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
