@@ -55,6 +55,7 @@ int main(int argc, char **argv) {
   int coarsen_type = 10, interp_type = 6, P_max_elmts = 4, relax_type = -1, relax_order = 0, max_levels = 25;
   int agg_num_levels = 0, rap2 = 0, mod_rap2 = 0, keepTranspose = 1, num_sweeps = 1, max_iter = 1000, mg_max_iter = 100;
   int coarse_threshold = 9, min_coarse_size = 0, ioutdat = 3, poutdat = 1, two_norm = 1, gs_blocks = 1;
+  int cycle_type = 1, fcycle = 0, ns_coarse = 1, ns_down = -1, ns_up = -1;                        /* ij.c:167, :205-206 */
   double strong_threshold = 0.25, max_row_sum = 1.0, trunc_factor = 0.0, tol = 1.e-8, pc_tol = 0., relax_wt = 1., outer_wt = 1.;
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-laplacian")) ;
@@ -78,6 +79,11 @@ int main(int argc, char **argv) {
     else if (!strcmp(argv[a], "-mod_rap2") && a + 1 < argc) mod_rap2 = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-keepT") && a + 1 < argc) keepTranspose = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-ns") && a + 1 < argc) num_sweeps = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-ns_coarse") && a + 1 < argc) ns_coarse = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-ns_down") && a + 1 < argc) ns_down = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-ns_up") && a + 1 < argc) ns_up = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-mu") && a + 1 < argc) cycle_type = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-fmg")) fcycle = 1;
     else if (!strcmp(argv[a], "-mxl") && a + 1 < argc) max_levels = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-max_iter") && a + 1 < argc) max_iter = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-mg_max_iter") && a + 1 < argc) mg_max_iter = atoi(argv[++a]);
@@ -150,8 +156,14 @@ int main(int argc, char **argv) {
     HYPRE_BoomerAMGSetTruncFactor(amg, trunc_factor);
     HYPRE_BoomerAMGSetPMaxElmts(amg, P_max_elmts);
     HYPRE_BoomerAMGSetPrintLevel(amg, solver_id == 0 ? ioutdat : poutdat);
-    HYPRE_BoomerAMGSetCycleType(amg, 1);
+    HYPRE_BoomerAMGSetCycleType(amg, cycle_type);
+    HYPRE_BoomerAMGSetFCycle(amg, fcycle);
     HYPRE_BoomerAMGSetNumSweeps(amg, num_sweeps);
+    HYPRE_BoomerAMGSetCycleNumSweeps(amg, ns_coarse, 3);
+    if (solver_id == 0) {                                                  /* ij.c:3494-3502: only the AMG solver takes these */
+      if (ns_down > -1) HYPRE_BoomerAMGSetCycleNumSweeps(amg, ns_down, 1);
+      if (ns_up > -1) HYPRE_BoomerAMGSetCycleNumSweeps(amg, ns_up, 2);
+    }
     if (relax_type > -1) HYPRE_BoomerAMGSetRelaxType(amg, relax_type);
     HYPRE_BoomerAMGSetRelaxOrder(amg, relax_order);
     HYPRE_BoomerAMGSetRelaxWt(amg, relax_wt);

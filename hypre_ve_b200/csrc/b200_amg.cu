@@ -43,6 +43,9 @@ struct b200_amg_s {
   bool coarse_ge = false;
   bool gs = false;                // Gauss-Seidel family smoother (relax 3/4/6/8/13/14) instead of l1-Jacobi
   int relax_down = 18, relax_up = 18;
+  int ns[4] = {1, 1, 1, 1};       // num_grid_sweeps[1..3]: down, up, coarsest (par_amg.c:1934-2030)
+  int cycle_type = 1, fcycle = 0; // 1 = V, 2 = W (par_cycle.c:199-210); F-cycle flag
+  bool general_cycle = false;     // anything other than V(1,1) with one coarse sweep
   double times[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   bool is_setup = false;
   b200_amg_s() {
@@ -52,7 +55,8 @@ struct b200_amg_s {
           {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"NumSweeps", 1}, {"AggNumLevels", 0}, {"ModuleRAP2", 1},
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
           {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"ChebyOrder", 2}, {"ChebyEigEst", 10},
-          {"ChebyVariant", 0}, {"ChebyScale", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747}};
+          {"ChebyVariant", 0}, {"ChebyScale", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747},
+          {"NumSweepsDown", -1}, {"NumSweepsUp", -1}, {"NumSweepsCoarse", 1}, {"FCycle", 0}};
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
           {"OuterWt", 1.0}, {"Tol", 0.0}, {"ChebyFraction", 0.3}};
   }
@@ -230,7 +234,14 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   if (ip["AggNumLevels"] < 0) B200_FAIL("AggNumLevels must be >= 0");
   // aggressive levels: second PMIS on the distance-two graph + multipass interpolation (agg_interp_type 4, the
   // reference default; agg_trunc_factor = agg_P_max_elmts = 0, num_paths 1), par_amg_setup.c:1239-1256, :1590-1605
-  if (ip["NumSweeps"] != 1 || ip["CycleType"] != 1) B200_FAIL("only V(1,1) cycles are implemented");
+  if (ip["NumSweeps"] < 1) B200_FAIL("NumSweeps must be >= 1");                      // par_amg.c:1947-1951
+  if (ip["CycleType"] < 1) B200_FAIL("CycleType must be >= 1 (1 = V, 2 = W)");
+  amg->ns[1] = ip["NumSweepsDown"] >= 0 ? ip["NumSweepsDown"] : ip["NumSweeps"];
+  amg->ns[2] = ip["NumSweepsUp"] >= 0 ? ip["NumSweepsUp"] : ip["NumSweeps"];
+  amg->ns[3] = ip["NumSweepsCoarse"];
+  if (amg->ns[3] < 0) B200_FAIL("NumSweepsCoarse must be >= 0");
+  amg->cycle_type = ip["CycleType"]; amg->fcycle = ip["FCycle"] ? 1 : 0;
+  amg->general_cycle = amg->ns[1] != 1 || amg->ns[2] != 1 || amg->ns[3] != 1 || amg->cycle_type != 1 || amg->fcycle;
   if (ip["NumFunctions"] != 1) B200_FAIL("only scalar problems (NumFunctions 1)");
   if (ip["RAP2"] != 0 || (ip["ModuleRAP2"] != 0 && ip["ModuleRAP2"] != 1))
     B200_FAIL("Galerkin product: ModuleRAP2 1 (hypre_ParCSRMatrixRAPKT, R(AP)) or ModuleRAP2 0 (the fused "
@@ -423,7 +434,68 @@ static int amg_cycle_gs(b200_handle h, b200_amg amg, const double *f, double *u,
   return 0;
 }
 
+// Any other cycle shape: the reference's level-counter state machine (par_cycle.c:180-622) -- lev_counter[k] visits
+// per level (cycle_type: 1 = V, 2 = W; F-cycle flag), num_grid_sweeps[cycle_param] sweeps per visit (1 down, 2 up,
+// 3 coarsest).  Jacobi sweeps are out of place (ping-pong between U and T), the other smoothers in place.
+static int amg_cycle_general(b200_handle h, b200_amg amg, const double *f, double *u, bool u_zero) {
+  const int nl = (int)amg->lv.size();
+  const double w = amg->rp["RelaxWt"];
+  std::vector<const double *> F(nl);
+  std::vector<double *> U(nl), alt(nl);
+  std::vector<char> zero(nl, 0);
+  std::vector<int> lev_counter(nl);
+  F[0] = f; U[0] = u; alt[0] = amg->lv[0].T; zero[0] = u_zero;
+  for (int l = 1; l < nl; l++) { F[l] = amg->lv[l].F; U[l] = amg->lv[l].U; alt[l] = amg->lv[l].T; }
+  lev_counter[0] = 1;
+  for (int k = 1; k < nl; k++) lev_counter[k] = amg->fcycle ? 1 : amg->cycle_type;
+  int fcycle_lev = nl - 2, level = 0, cycle_param = 1;
+  while (true) {
+    b200_level &L = amg->lv[level];
+    const int num_sweep = amg->ns[cycle_param];
+    const int type = cycle_param == 2 ? amg->relax_up : amg->relax_down;
+    for (int j = 0; j < num_sweep; j++) {
+      if (level == nl - 1 && amg->coarse_ge) {                       // grid_relax_type[3] = 9
+        gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, F[level], U[level]);
+        B200_LAUNCH_CHECK();
+      } else if (amg->gs) {
+        B200_TRY(gs_relax(h, L, type, F[level], U[level], zero[level] != 0));
+      } else if (zero[level]) {
+        jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[level], L.l1, U[level]);
+        B200_LAUNCH_CHECK();
+      } else {
+        B200_TRY(jacobi(h, L, w, F[level], U[level], alt[level]));
+        std::swap(U[level], alt[level]);
+      }
+      zero[level] = 0;
+    }
+    if (zero[level]) {                                               // no sweep was asked for: the iterate is the zero vector
+      B200_CUDA(cudaMemsetAsync(U[level], 0, sizeof(double) * (size_t)L.n, h->stream));
+      zero[level] = 0;
+    }
+    --lev_counter[level];
+    if (lev_counter[level] >= 0 && level != nl - 1) {                // :534-591 residual, restriction, coarse iterate = 0
+      B200_TRY(b200_csr_spmv_epi(h, L.As, U[level], amg->Vtemp, 0, -1.0, 1.0, F[level], nullptr));
+      B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, amg->lv[level + 1].F, 0, 1.0, 0.0, nullptr, nullptr));
+      ++level;
+      zero[level] = 1;
+      lev_counter[level] = std::max(lev_counter[level], amg->cycle_type);
+      cycle_param = (level == nl - 1) ? 3 : 1;
+    } else if (level != 0) {                                         // :592-625 interpolation
+      B200_TRY(b200_csr_spmv_epi(h, amg->lv[level - 1].P, U[level], U[level - 1], 0, 1.0, 1.0, U[level - 1], nullptr));
+      --level;
+      cycle_param = 2;
+      if (amg->fcycle && fcycle_lev == level) { lev_counter[level] = std::max(lev_counter[level], 1); fcycle_lev--; }
+    } else {
+      break;
+    }
+  }
+  for (int l = 1; l < nl; l++) { amg->lv[l].U = U[l]; amg->lv[l].T = alt[l]; }
+  if (U[0] != u) B200_TRY(b200_vec_copy(h, amg->lv[0].n, U[0], u));
+  return 0;
+}
+
 static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bool u_zero) {
+  if (amg->general_cycle && amg->lv.size() > 1) return amg_cycle_general(h, amg, f, u, u_zero);
   if (amg->gs) return amg_cycle_gs(h, amg, f, u, u_zero);
   const int nl = (int)amg->lv.size();
   const double w = amg->rp["RelaxWt"];

@@ -756,7 +756,9 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   if (!jac && b200_amg_get_real(prm, "RelaxWt") != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (b200_amg_get_int(prm, "InterpType") != 6 ||
       b200_amg_get_int(prm, "RelaxOrder") != 0 || b200_amg_get_int(prm, "AggNumLevels") < 0 ||
-      b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 ||
+      b200_amg_get_int(prm, "NumSweeps") != 1 || b200_amg_get_int(prm, "CycleType") != 1 || b200_amg_get_int(prm, "FCycle") != 0 ||
+      (b200_amg_get_int(prm, "NumSweepsDown") != -1 && b200_amg_get_int(prm, "NumSweepsDown") != 1) ||
+      (b200_amg_get_int(prm, "NumSweepsUp") != -1 && b200_amg_get_int(prm, "NumSweepsUp") != 1) || b200_amg_get_int(prm, "NumSweepsCoarse") != 1 ||
       b200_amg_get_int(prm, "RAP2") != 0 || (b200_amg_get_int(prm, "ModuleRAP2") != 0 && b200_amg_get_int(prm, "ModuleRAP2") != 1))
     B200_FAIL("unsupported BoomerAMG configuration on the B200 path (see b200_amg_setup)");
   const int R = b200_comm_size(c), me = b200_comm_rank(c);

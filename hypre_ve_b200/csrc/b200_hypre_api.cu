@@ -108,7 +108,7 @@ const Neutral kNeutral[] = {
     {"PostInterpType", 0, "Jacobi interpolation"},     {"SmoothNumLevels", 0, "complex smoothers (Schwarz/Pilut/ParaSails/Euclid)"},
     {"Additive", -1, "additive cycles"},               {"MultAdditive", -1, "mult-additive cycles"},
     {"Simple", -1, "simple additive cycles"},          {"Nodal", 0, "nodal systems coarsening"},
-    {"FCycle", 0, "F-cycles"},                         {"NonGalerkinTol", 0, "non-Galerkin coarse operators"},
+    {"NonGalerkinTol", 0, "non-Galerkin coarse operators"},
     {"NumCPoints", 0, "user C-points"},                {"NumFPoints", 0, "user F-points"},
     {"NumIsolatedFPoints", 0, "isolated F-points"},    {"NumInterpVectors", 0, "interpolation vectors (GSMG/RBM)"},
     {"GSMG", 0, "GSMG"},                               {"CoarsenCutFactor", 0, "coarsening cut factor"},
@@ -580,7 +580,7 @@ HYPRE_Int HYPRE_BoomerAMGCreate(HYPRE_Solver *solver) {
                {"KeepTranspose", 0}, {"Tol", 1e-7}, {"MaxIter", 20}, {"MinIter", 0}, {"RelaxOrder", 0}, {"NumSweeps", 1},
                {"CycleType", 1}, {"MaxLevels", 25}, {"MaxCoarseSize", 9}, {"MinCoarseSize", 0}, {"AggNumLevels", 0},
                {"NumFunctions", 1}, {"StrongThreshold", 0.25}, {"MaxRowSum", 0.9}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
-               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}, {"GSBlocks", 1},
+               {"OuterWt", 1.0}, {"PrintLevel", 0}, {"Logging", 0}, {"GSBlocks", 1}, {"FCycle", 0},
                {"ChebyOrder", 2}, {"ChebyEigEst", 10}, {"ChebyVariant", 0}, {"ChebyScale", 1}, {"ChebyFraction", 0.3}};   // par_amg.c:215-220
   for (const Neutral &nv : kNeutral) s->stored[nv.name] = nv.value;
   *solver = s;
@@ -612,7 +612,13 @@ AMG_SETTER(RelaxType, HYPRE_Int, v >= 0)
 AMG_SETTER(RelaxOrder, HYPRE_Int, true)
 AMG_SETTER(RelaxWt, HYPRE_Real, true)
 AMG_SETTER(OuterWt, HYPRE_Real, true)
-AMG_SETTER(NumSweeps, HYPRE_Int, v >= 1)
+HYPRE_Int HYPRE_BoomerAMGSetNumSweeps(HYPRE_Solver s, HYPRE_Int v) {          // par_amg.c:1934-1962: down = up = v, coarse = 1
+  if (!is_amg(s)) return err_arg(1);
+  if (v < 1) return err_arg(2);
+  s->stored["NumSweeps"] = v;
+  for (char k = '1'; k <= '3'; k++) s->stored.erase(std::string("CycleNumSweeps") + k);
+  return g_error_flag;
+}
 AMG_SETTER(CycleType, HYPRE_Int, v >= 1 && v <= 2)
 AMG_SETTER(MaxLevels, HYPRE_Int, v >= 1)
 AMG_SETTER(MaxCoarseSize, HYPRE_Int, v >= 1)
@@ -757,7 +763,6 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   if (st.count("CycleRelaxType3")) rcoarse = (int)st["CycleRelaxType3"];
   if (rcoarse != 9) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: coarsest-grid relax type %d (only 9 = Gaussian elimination)\n", rcoarse); return err(HYPRE_ERROR_GENERIC); }
   if (st.count("LevelRelaxWtSet") || st.count("LevelOuterWtSet")) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: per-level relaxation weights are not on the B200 path\n"); return err(HYPRE_ERROR_GENERIC); }
-  if (st.count("CycleNumSweeps3") && st["CycleNumSweeps3"] != 1) { fprintf(stderr, "hypre_b200: BoomerAMGSetup: only one coarse sweep\n"); return err(HYPRE_ERROR_GENERIC); }
   static const char *ints[] = {"CoarsenType", "InterpType", "PMaxElmts", "MaxLevels", "MaxCoarseSize", "MinCoarseSize", "NumSweeps",
                                "AggNumLevels", "ModuleRAP2", "RAP2", "KeepTranspose", "RelaxOrder", "MaxIter", "MinIter", "CycleType",
                                "NumFunctions", "PrintLevel", "GSBlocks", "ChebyOrder", "ChebyEigEst", "ChebyVariant", "ChebyScale"};
@@ -766,6 +771,10 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   for (const char *k : reals) CALL(b200_amg_set_real(s->amg, k, st[k]), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxType", rdown), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxTypeUp", rup), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "NumSweepsDown", st.count("CycleNumSweeps1") ? (int)st["CycleNumSweeps1"] : -1), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "NumSweepsUp", st.count("CycleNumSweeps2") ? (int)st["CycleNumSweeps2"] : -1), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "NumSweepsCoarse", st.count("CycleNumSweeps3") ? (int)st["CycleNumSweeps3"] : 1), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "FCycle", (int)st["FCycle"]), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_setup(h, s->amg, A->A), "HYPRE_BoomerAMGSetup");
   const int pl = (int)st["PrintLevel"];
   if (pl == 1 || pl == 3) setup_stats(h, s);

@@ -118,7 +118,9 @@ int b200_amg_destroy(b200_handle h, b200_amg amg);       /* HYPRE_BoomerAMGDestr
  * "AggNumLevels","ModuleRAP2","KeepTranspose","RelaxOrder","MaxIter","MinIter","RelaxTypeUp" (up-cycle
  * smoother when it differs from "RelaxType", e.g. 13 down / 14 up), "GSBlocks" (Gauss-Seidel blocks per rank),
  * "ChebyOrder" (1-4, default 2), "ChebyEigEst" (CG steps, default 10), "ChebyVariant" (0), "ChebyScale" (1)
- * for RelaxType 16 (par_cheby.c:41-345; real parameter "ChebyFraction", default 0.3) / "StrongThreshold",
+ * for RelaxType 16 (par_cheby.c:41-345; real parameter "ChebyFraction", default 0.3), "CycleType" (1 = V, 2 = W),
+ * "FCycle", "NumSweeps" (down = up), "NumSweepsDown" / "NumSweepsUp" (-1 = follow NumSweeps), "NumSweepsCoarse"
+ * (num_grid_sweeps[1..3], par_amg.c:1934-2030; cycle control par_cycle.c:180-622) / "StrongThreshold",
  * "MaxRowSum","TruncFactor","RelaxWt","Tol".  Unsupported values are rejected at setup. */
 int b200_amg_set_int(b200_amg amg, const char *name, int value);
 int b200_amg_set_real(b200_amg amg, const char *name, double value);

@@ -811,34 +811,52 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
    }
    free(tmp);
 }
-/* V(1,1): parcsr_ls/par_cycle.c:255-622 */
+/* One multigrid cycle, parcsr_ls/par_cycle.c:180-622: the level-counter state machine (V: cycle_type 1, W: 2, F-cycle flag),
+ * num_grid_sweeps[1..3] sweeps on the way down / up / on the coarsest grid (par_amg.c:1934-1962, :1990-2030). */
+static int g_ns[4] = { 1, 1, 1, 1 }, g_cycle_type = 1, g_fcycle = 0;
 static void cycle(amg_t *g, const double *f, double *u)
 {
-   int l, i, nl = g->nl;
-   const double *F; double *U;
-   for (l = 0; l < nl - 1; l++)
+   int i, j, k, nl = g->nl, level = 0, cycle_param = 1, not_finished = 1, fcycle_lev = nl - 2;
+   int *lev_counter = (int *) xmalloc(sizeof(int) * nl);
+   lev_counter[0] = 1;
+   for (k = 1; k < nl; k++) lev_counter[k] = g_fcycle ? 1 : g_cycle_type;
+   while (not_finished)
    {
-      F = l ? g->F[l] : f; U = l ? g->U[l] : u;
-      relax(g, l, g_relax_down, F, U);
-      matvec(-1.0, &g->A[l], U, 1.0, F, g->V);
-      matvec(1.0, &g->R[l], g->V, 0.0, g->V, g->F[l + 1]);
-      for (i = 0; i < g->A[l + 1].n; i++) g->U[l + 1][i] = 0.0;
+      const double *F = level ? g->F[level] : f; double *U = level ? g->U[level] : u;
+      int num_sweep = (nl > 1) ? g_ns[cycle_param] : 1;
+      int type = (cycle_param == 2) ? g_relax_up : g_relax_down;
+      for (j = 0; j < num_sweep; j++)
+      {
+         if (level == nl - 1 && g->ge)
+         {  /* grid_relax_type[3] = 9 (par_gauss_elim.c) */
+            int n = g->ge_n; double *T = (double *) xmalloc(sizeof(double) * n * n), *b = (double *) xmalloc(sizeof(double) * n);
+            memcpy(T, g->ge, sizeof(double) * n * n); memcpy(b, F, sizeof(double) * n);
+            gselim(T, b, n);
+            memcpy(U, b, sizeof(double) * n); free(T); free(b);
+         }
+         else relax(g, level, type, F, U);
+      }
+      --lev_counter[level];
+      if (lev_counter[level] >= 0 && level != nl - 1)
+      {  /* :534-591 */
+         for (i = 0; i < g->A[level + 1].n; i++) g->U[level + 1][i] = 0.0;
+         matvec(-1.0, &g->A[level], U, 1.0, F, g->V);
+         matvec(1.0, &g->R[level], g->V, 0.0, g->V, g->F[level + 1]);
+         ++level;
+         if (lev_counter[level] < g_cycle_type) lev_counter[level] = g_cycle_type;
+         cycle_param = (level == nl - 1) ? 3 : 1;
+      }
+      else if (level != 0)
+      {  /* :592-625 */
+         double *Uf = (level - 1) ? g->U[level - 1] : u;
+         matvec(1.0, &g->P[level - 1], g->U[level], 1.0, Uf, Uf);
+         --level;
+         cycle_param = 2;
+         if (g_fcycle && fcycle_lev == level) { if (lev_counter[level] < 1) lev_counter[level] = 1; fcycle_lev--; }
+      }
+      else not_finished = 0;
    }
-   F = (nl > 1) ? g->F[nl - 1] : f; U = (nl > 1) ? g->U[nl - 1] : u;
-   if (g->ge)
-   {
-      int n = g->ge_n; double *T = (double *) xmalloc(sizeof(double) * n * n), *b = (double *) xmalloc(sizeof(double) * n);
-      memcpy(T, g->ge, sizeof(double) * n * n); memcpy(b, F, sizeof(double) * n);
-      gselim(T, b, n);
-      memcpy(U, b, sizeof(double) * n); free(T); free(b);
-   }
-   else relax(g, nl - 1, g_relax_down, F, U);
-   for (l = nl - 2; l >= 0; l--)
-   {
-      F = l ? g->F[l] : f; U = l ? g->U[l] : u;
-      matvec(1.0, &g->P[l], g->U[l + 1], 1.0, U, U);
-      relax(g, l, g_relax_up, F, U);
-   }
+   free(lev_counter);
 }
 
 /* ---- output in ref_dump.c's record format ---- */
@@ -883,6 +901,12 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-agg_nl")) g_agg_nl = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-mod_rap2")) g_mod_rap2 = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-keepT")) { ++i; }
+      else if (!strcmp(argv[i], "-ns")) { g_ns[1] = g_ns[2] = atoi(argv[++i]); }          /* ij.c:881-885 -> SetNumSweeps */
+      else if (!strcmp(argv[i], "-ns_down")) g_ns[1] = atoi(argv[++i]);                  /* ij.c:891-900 -> SetCycleNumSweeps */
+      else if (!strcmp(argv[i], "-ns_up")) g_ns[2] = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-ns_coarse")) g_ns[3] = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-mu")) g_cycle_type = atoi(argv[++i]);                  /* ij.c:1490 */
+      else if (!strcmp(argv[i], "-fmg")) g_fcycle = 1;                                   /* ij.c:1495-1499 */
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
    double v[4];

@@ -63,6 +63,7 @@ int main(int argc, char **argv)
 {
    int nx = 10, ny = 10, nz = 10, pt27 = 0, pmis = 0, rlx = -1, Pmx = 4, agg_nl = 0;
    int mod_rap2 = 0, keepT = 0, interp_type = 6, nodump = 0, matvec = 0, max_iter = 100;
+   int ns = 1, ns_coarse = 1, mu = 1, fmg = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    const char *ofile = NULL;
    int i;
@@ -84,6 +85,10 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-max_iter")) max_iter = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-matvec")) matvec = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-nodump")) nodump = 1;
+      else if (!strcmp(argv[i], "-ns")) ns = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-ns_coarse")) ns_coarse = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-mu")) mu = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-fmg")) fmg = 1;
       else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
@@ -160,8 +165,9 @@ int main(int argc, char **argv)
    HYPRE_BoomerAMGSetPMaxElmts(amg, Pmx);
    HYPRE_BoomerAMGSetPrintLevel(amg, 0);
    HYPRE_BoomerAMGSetMaxIter(amg, 1);
-   HYPRE_BoomerAMGSetCycleType(amg, 1);
-   HYPRE_BoomerAMGSetNumSweeps(amg, 1);
+   HYPRE_BoomerAMGSetCycleType(amg, mu);
+   HYPRE_BoomerAMGSetFCycle(amg, fmg);
+   HYPRE_BoomerAMGSetNumSweeps(amg, ns);
    if (rlx > -1) HYPRE_BoomerAMGSetRelaxType(amg, rlx);
    HYPRE_BoomerAMGSetRelaxOrder(amg, 0);
    HYPRE_BoomerAMGSetRelaxWt(amg, 1.0);
@@ -171,7 +177,7 @@ int main(int argc, char **argv)
    HYPRE_BoomerAMGSetNumFunctions(amg, 1);
    HYPRE_BoomerAMGSetAggNumLevels(amg, agg_nl);
    HYPRE_BoomerAMGSetAggInterpType(amg, 4);
-   HYPRE_BoomerAMGSetCycleNumSweeps(amg, 1, 3);
+   HYPRE_BoomerAMGSetCycleNumSweeps(amg, ns_coarse, 3);
    HYPRE_BoomerAMGSetRAP2(amg, 0);
    HYPRE_BoomerAMGSetModuleRAP2(amg, mod_rap2);
    HYPRE_BoomerAMGSetKeepTranspose(amg, keepT);

@@ -3,6 +3,7 @@
 OMP_NUM_THREADS=1).  Run in the container that has /root/reference after
 `python oracle/build_ref.py`.  Each .bin is a ref_dump stream (see tests/refio.py)."""
 import os
+import sys
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -23,14 +24,21 @@ MORE = {
     "lap7_11_gs8_blocks4_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "8", "-mod_rap2", "1"], 4),
     "lap7_11_cheby16_modrap.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "16", "-mod_rap2", "1"], 1),
     "lap27_8_rlx7_modrap.bin": (["-n", "8", "8", "8", "-27pt", "-pmis", "-rlx", "7", "-mod_rap2", "1"], 1),
+    "lap7_11_w22_rlx18.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "18", "-mu", "2", "-ns", "2"], 1),            # W(2,2) cycle
+    "lap7_11_fmg_gs1314_coarse2.bin": (["-n", "11", "11", "11", "-pmis", "-fmg", "-ns_coarse", "2"], 1),              # F-cycle, GS
 }
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="1")
     for name, args in CASES.items():
+        if sys.argv[1:] and name not in sys.argv[1:]:
+            continue
         out = subprocess.run([REF] + args + COMMON + ["-o", os.path.join(HERE, name)], env=env, check=True,
                              capture_output=True, text=True).stdout
         print(name, out.splitlines()[1])
+    only = sys.argv[1:]                  # optional: regenerate just the named fixtures
     for name, (args, threads) in MORE.items():
+        if only and name not in only:
+            continue
         out = subprocess.run([REF] + args + ["-keepT", "1", "-o", os.path.join(HERE, name)], check=True, capture_output=True,
                              text=True, env=dict(os.environ, OMP_NUM_THREADS=str(threads))).stdout
         print(name, out.splitlines()[1])

@@ -315,3 +315,32 @@ def test_chebyshev_smoother_relax_16(handle, args):
     assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
     assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
     amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("extra,params", [
+    (["-ns", 2], dict(NumSweeps=2)),
+    (["-mu", 2], dict(CycleType=2)),
+    (["-mu", 2, "-ns", 2], dict(CycleType=2, NumSweeps=2)),
+    (["-fmg"], dict(FCycle=1)),
+    (["-ns_coarse", 2, "-ns", 3], dict(NumSweeps=3, NumSweepsCoarse=2)),
+])
+@pytest.mark.parametrize("rlx", [18, -1, 16])
+def test_cycle_shapes(handle, extra, params, rlx):
+    """W / F cycles and several sweeps per visit: the reference's level-counter state machine (par_cycle.c:180-622);
+    residual history of AMG-PCG against the reference CPU build"""
+    import hypre_ve_b200 as hb
+    args = ["-n", 21, 19, 17, "-pmis"] + (["-rlx", rlx] if rlx > -1 else []) + extra
+    d, _ = refio.run_ref(args)
+    A = hb.ParCsr.laplacian(handle, 21, 19, 17)
+    kw = dict(RelaxType=rlx, ModuleRAP2=0) if rlx > -1 else dict(RelaxType=13, RelaxTypeUp=14, ModuleRAP2=0)
+    amg = hb.Amg(handle, **kw, **params)
+    amg.setup(A)
+    assert amg.num_levels == nlev(d)
+    n = A.local[0]
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4]), (its, int(d["hdr"][4]))
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+    amg.destroy(); A.destroy()

@@ -86,6 +86,30 @@ def test_hybrid_gauss_seidel_smoothers_through_the_public_api(exe, flags, known)
         assert its == known
 
 
+@pytest.mark.parametrize("flags", [
+    ["-n", "20", "20", "20", "-solver", "1", "-pmis", "-rlx", "18", "-ns", "2"],                     # V(2,2)
+    ["-n", "20", "20", "20", "-solver", "1", "-pmis", "-rlx", "18", "-mu", "2"],                     # W(1,1)
+    ["-n", "22", "18", "20", "-solver", "1", "-pmis", "-rlx", "18", "-mu", "2", "-ns", "2", "-mod_rap2", "1"],
+    ["-n", "20", "20", "20", "-solver", "1", "-pmis", "-rlx", "18", "-fmg"],                         # F-cycle
+    ["-n", "20", "20", "20", "-solver", "1", "-pmis", "-mu", "2", "-ns", "2"],                       # W(2,2), 13 down / 14 up
+    ["-n", "18", "18", "18", "-solver", "1", "-pmis", "-rlx", "16", "-mu", "2", "-ns", "2"],         # Chebyshev
+    ["-n", "20", "20", "20", "-solver", "1", "-pmis", "-rlx", "18", "-ns_coarse", "3", "-ns", "2"],
+    ["-27pt", "-n", "12", "12", "12", "-solver", "1", "-pmis", "-rlx", "7", "-mu", "2", "-agg_nl", "1"],
+    ["-n", "16", "16", "16", "-solver", "0", "-pmis", "-rlx", "18", "-ns_down", "2", "-ns_up", "1"],  # V(2,1), AMG as the solver
+    ["-n", "16", "16", "16", "-solver", "0", "-pmis", "-rlx", "18", "-ns_down", "0", "-ns_up", "3"],  # V(0,3)
+    ["-n", "16", "16", "16", "-solver", "0", "-pmis", "-mu", "2", "-ns_down", "1", "-ns_up", "2"],
+])
+def test_cycle_shapes_match_reference_driver(exe, flags):
+    """-ns / -ns_down / -ns_up / -ns_coarse (num_grid_sweeps), -mu (cycle type), -fmg (F-cycle): par_cycle.c:180-622"""
+    rc, out = run([exe, "-laplacian"] + flags)
+    assert rc == 0, out
+    key = "BoomerAMG Iterations" if "0" == flags[flags.index("-solver") + 1] else "Iterations"
+    its, rel = result(out, key)
+    assert os.path.exists(REF_IJ)
+    rits, rrel = ref_result(flags, key)
+    assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)
+
+
 def test_gauss_seidel_blocks_equal_reference_thread_count(exe):
     """-gs_blocks T on our side == OMP_NUM_THREADS=T on the reference's"""
     flags = ["-n", "30", "30", "30", "-solver", "1", "-pmis", "-mod_rap2", "1"]

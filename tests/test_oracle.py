@@ -58,6 +58,9 @@ GOLDEN_MORE = {
     # Chebyshev: the extreme Lanczos eigenvalues come from a different (equally stable) tridiagonal solver than the
     # reference's EISPACK tql1 -> last-bit differences in the coefficients, hierarchy exact
     "lap7_11_cheby16_modrap.bin": (["-n", 11, 11, 11, "-pmis", "-rlx", 16, "-mod_rap2", 1], False),
+    # other cycle shapes (par_cycle.c level counters): W(2,2) with l1-Jacobi, F-cycle with 13/14 and two coarse sweeps
+    "lap7_11_w22_rlx18.bin": (["-n", 11, 11, 11, "-pmis", "-rlx", 18, "-mu", 2, "-ns", 2], True),
+    "lap7_11_fmg_gs1314_coarse2.bin": (["-n", 11, 11, 11, "-pmis", "-fmg", "-ns_coarse", 2], True),
 }
 
 
