@@ -859,6 +859,29 @@ static void cycle(amg_t *g, const double *f, double *u)
    free(lev_counter);
 }
 
+
+/* -perturb SEED: a non-Laplacian SPD test operator on the stencil's pattern -- symmetric pseudo-random off-diagonal
+ * magnitudes in [0.05, 1.5] (weak and strong connections), one in sixteen with a POSITIVE sign, strictly dominant
+ * diagonal.  The same function lives in oracle/ref_dump.c and oracle/amg_oracle.c (test infrastructure). */
+static void perturb_operator(int n, const int *I, const int *J, double *a, unsigned seed)
+{
+   int i, k;
+   for (i = 0; i < n; i++)
+   {
+      double sum = 0.0;
+      for (k = I[i] + 1; k < I[i + 1]; k++)
+      {
+         unsigned lo = (unsigned) (i < J[k] ? i : J[k]), hi = (unsigned) (i < J[k] ? J[k] : i);
+         unsigned h = (lo * 73856093u) ^ (hi * 19349663u) ^ (seed * 83492791u);
+         h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+         double f = 0.05 + 1.45 * (double) (h & 0xffffu) / 65535.0;
+         a[k] = (((h >> 16) & 15u) == 0u) ? 0.25 * f : -f;
+         sum += fabs(a[k]);
+      }
+      a[I[i]] = sum + 0.05;
+   }
+}
+
 /* ---- output in ref_dump.c's record format ---- */
 static FILE *g_out;
 static void put(const char *name, int dtype, const void *p, size_t n)
@@ -880,7 +903,7 @@ static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts
 
 int main(int argc, char **argv)
 {
-   int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1;
+   int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1, perturb = 0;
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    const char *ofile = NULL;
    for (i = 1; i < argc; i++)
@@ -906,6 +929,7 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-ns_up")) g_ns[2] = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-ns_coarse")) g_ns[3] = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-mu")) g_cycle_type = atoi(argv[++i]);                  /* ij.c:1490 */
+      else if (!strcmp(argv[i], "-perturb")) perturb = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-fmg")) g_fcycle = 1;                                   /* ij.c:1495-1499 */
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
@@ -914,6 +938,7 @@ int main(int argc, char **argv)
    else { v[1] = -cx; v[2] = -cy; v[3] = -cz; v[0] = 0.; if (nx > 1) v[0] += 2.0 * cx; if (ny > 1) v[0] += 2.0 * cy; if (nz > 1) v[0] += 2.0 * cz; }
    csr_t A = gen_laplace(nx, ny, nz, pt27, v);
    int N = A.n;
+   if (perturb) perturb_operator(N, A.i, A.j, A.a, (unsigned) perturb);
    double *b = (double *) xmalloc(sizeof(double) * N), *x = (double *) xcalloc(N, sizeof(double));
    for (i = 0; i < N; i++) b[i] = 1.0;
    if (matvec_reps > 0)

@@ -16,7 +16,7 @@
  * Flags follow ij.c's spelling: -n nx ny nz, -27pt, -c cx cy cz, -pmis, -rlx T,
  * -Pmx K, -agg_nl L, -mod_rap2 B, -keepT B, -th theta, -tol t, -interptype I,
  * -mxrs r (max_row_sum), -o FILE, -matvec K (time K SpMVs, ij -solver -1 analogue),
- * -nodump (timing only).
+ * -nodump (timing only), -ns / -ns_coarse / -mu / -fmg (cycle shape), -perturb SEED (non-Laplacian values, see below).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -53,6 +53,28 @@ static void put_csr(const char *pre, int l, hypre_CSRMatrix *M, int with_data)
    sprintf(nm, "%s%d.j", pre, l);    put(nm, 0, hypre_CSRMatrixJ(M), nnz);
    if (with_data) { sprintf(nm, "%s%d.a", pre, l); put(nm, 1, hypre_CSRMatrixData(M), nnz); }
 }
+
+/* -perturb SEED: a non-Laplacian SPD test operator on the stencil's pattern -- symmetric pseudo-random off-diagonal
+ * magnitudes in [0.05, 1.5] (weak and strong connections), one in sixteen with a POSITIVE sign, strictly dominant
+ * diagonal.  The same function lives in oracle/ref_dump.c and oracle/amg_oracle.c (test infrastructure). */
+static void perturb_operator(int n, const int *I, const int *J, double *a, unsigned seed)
+{
+   int i, k;
+   for (i = 0; i < n; i++)
+   {
+      double sum = 0.0;
+      for (k = I[i] + 1; k < I[i + 1]; k++)
+      {
+         unsigned lo = (unsigned) (i < J[k] ? i : J[k]), hi = (unsigned) (i < J[k] ? J[k] : i);
+         unsigned h = (lo * 73856093u) ^ (hi * 19349663u) ^ (seed * 83492791u);
+         h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15;
+         double f = 0.05 + 1.45 * (double) (h & 0xffffu) / 65535.0;
+         a[k] = (((h >> 16) & 15u) == 0u) ? 0.25 * f : -f;
+         sum += fabs(a[k]);
+      }
+      a[I[i]] = sum + 0.05;
+   }
+}
 static double now(void)
 {
    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -63,7 +85,7 @@ int main(int argc, char **argv)
 {
    int nx = 10, ny = 10, nz = 10, pt27 = 0, pmis = 0, rlx = -1, Pmx = 4, agg_nl = 0;
    int mod_rap2 = 0, keepT = 0, interp_type = 6, nodump = 0, matvec = 0, max_iter = 100;
-   int ns = 1, ns_coarse = 1, mu = 1, fmg = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
+   int ns = 1, ns_coarse = 1, mu = 1, fmg = 0, perturb = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    const char *ofile = NULL;
    int i;
@@ -89,6 +111,7 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-ns_coarse")) ns_coarse = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-mu")) mu = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-fmg")) fmg = 1;
+      else if (!strcmp(argv[i], "-perturb")) perturb = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
@@ -120,6 +143,9 @@ int main(int argc, char **argv)
    double t_gen = now() - t0;
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
    int N = hypre_CSRMatrixNumRows(hypre_ParCSRMatrixDiag(pA));
+   if (perturb)                                   /* one rank: the whole operator is the diag block, diagonal entry first */
+      perturb_operator(N, hypre_CSRMatrixI(hypre_ParCSRMatrixDiag(pA)), hypre_CSRMatrixJ(hypre_ParCSRMatrixDiag(pA)),
+                       hypre_CSRMatrixData(hypre_ParCSRMatrixDiag(pA)), (unsigned) perturb);
    HYPRE_BigInt *row_starts = hypre_ParCSRMatrixRowStarts(pA);
 
    hypre_ParVector *b = hypre_ParVectorCreate(hypre_MPI_COMM_WORLD, N, row_starts);

@@ -26,6 +26,8 @@ MORE = {
     "lap27_8_rlx7_modrap.bin": (["-n", "8", "8", "8", "-27pt", "-pmis", "-rlx", "7", "-mod_rap2", "1"], 1),
     "lap7_11_w22_rlx18.bin": (["-n", "11", "11", "11", "-pmis", "-rlx", "18", "-mu", "2", "-ns", "2"], 1),            # W(2,2) cycle
     "lap7_11_fmg_gs1314_coarse2.bin": (["-n", "11", "11", "11", "-pmis", "-fmg", "-ns_coarse", "2"], 1),              # F-cycle, GS
+    "perturbed7_11_rlx18.bin": (["-n", "11", "11", "11", "-perturb", "1", "-pmis", "-rlx", "18"], 1),                 # non-Laplacian SPD
+    "perturbed27_8_agg1_gs.bin": (["-n", "8", "8", "8", "-27pt", "-perturb", "7", "-pmis", "-agg_nl", "1"], 1),
 }
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="1")

@@ -344,3 +344,45 @@ def test_cycle_shapes(handle, extra, params, rlx):
     assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
     assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
     amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("args,params", [
+    (["-n", 22, 19, 17, "-perturb", 1, "-rlx", 18], dict(ModuleRAP2=0)),
+    (["-n", 22, 19, 17, "-perturb", 2, "-rlx", 18, "-mod_rap2", 1], dict(ModuleRAP2=1)),
+    (["-n", 13, 12, 11, "-27pt", "-perturb", 7, "-rlx", 18], dict(ModuleRAP2=0)),
+    (["-n", 20, 20, 20, "-perturb", 11, "-rlx", 18, "-th", 0.5, "-Pmx", 6], dict(ModuleRAP2=0, StrongThreshold=0.5, PMaxElmts=6)),
+    (["-n", 18, 18, 18, "-perturb", 5, "-rlx", 18, "-agg_nl", 1], dict(ModuleRAP2=0, AggNumLevels=1)),
+    (["-n", 18, 16, 14, "-perturb", 3], dict(ModuleRAP2=0, RelaxType=13, RelaxTypeUp=14)),
+    (["-n", 12, 12, 12, "-27pt", "-perturb", 9, "-rlx", 16], dict(ModuleRAP2=0, RelaxType=16)),
+    (["-n", 40, 36, 30, "-perturb", 4, "-rlx", 18], dict(ModuleRAP2=0)),
+])
+def test_non_laplacian_operator_hierarchy_and_pcg(handle, args, params):
+    """An SPD operator that is NOT a Laplacian (ref_dump -perturb: random symmetric magnitudes spanning weak and
+    strong connections, 1/16 positive off-diagonals) uploaded from host CSR: every level bit-identical to the
+    reference CPU build, residual history to 1e-10.  Exercises the sign filters and weak-connection branches of
+    strength / ext+i / multipass that the stencil operators never reach."""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-pmis", "-keepT", 1])
+    i0, j0, a0, _ = refio.csr(d, "A", 0)
+    assert (a0[i0[:-1]] > 0).all() and (a0 > 0).sum() > i0.size - 1          # positive diagonal AND positive off-diagonals
+    A = hb.ParCsr.from_host(handle, i0, j0, a0)
+    amg = hb.Amg(handle, **params)
+    amg.setup(A)
+    assert amg.num_levels == nlev(d)
+    for l in range(nlev(d)):
+        i, j, a = amg.level_A(l).download()
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), ("A", l)
+        if l < nlev(d) - 1:
+            assert np.array_equal(amg.level_CF(l), d["CF%d" % l]), ("CF", l)
+            i, j, a = amg.level_P(l).download()
+            pi, pj, pa, _ = refio.csr(d, "P", l)
+            assert np.array_equal(i, pi) and np.array_equal(j, pj) and np.array_equal(a, pa), ("P", l)
+    n = i0.size - 1
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    assert its == int(d["hdr"][4]), (its, int(d["hdr"][4]))
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    assert np.max(np.abs(x.numpy() - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+    amg.destroy(); A.destroy()

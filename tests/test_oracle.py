@@ -61,6 +61,9 @@ GOLDEN_MORE = {
     # other cycle shapes (par_cycle.c level counters): W(2,2) with l1-Jacobi, F-cycle with 13/14 and two coarse sweeps
     "lap7_11_w22_rlx18.bin": (["-n", 11, 11, 11, "-pmis", "-rlx", 18, "-mu", 2, "-ns", 2], True),
     "lap7_11_fmg_gs1314_coarse2.bin": (["-n", 11, 11, 11, "-pmis", "-fmg", "-ns_coarse", 2], True),
+    # non-Laplacian SPD operators (ref_dump -perturb): mixed-sign, weak and strong off-diagonals
+    "perturbed7_11_rlx18.bin": (["-n", 11, 11, 11, "-perturb", 1, "-pmis", "-rlx", 18], True),
+    "perturbed27_8_agg1_gs.bin": (["-n", 8, 8, 8, "-27pt", "-perturb", 7, "-pmis", "-agg_nl", 1], True),
 }
 
 
