@@ -369,13 +369,17 @@ __global__ void strided_to_csr_kernel(int n, int stride, const int *__restrict__
 // Products of one step that hit the same column are found with __match_any_sync and applied in
 // lane order; new columns take their first-touch positions from a ballot prefix.
 // ------------------------------------------------------------------------------------------
-template <int CAP, int GB, bool NUMERIC>
+// MODE 0: symbolic (row counts only);  MODE 1: numeric into an exactly sized CSR (counts known);
+// MODE 2: ONE pass -- numeric into a scratch row of upper-bound length, count written afterwards; a row that
+//         outgrows the table stays PENDING for the next, larger-table pass.
+template <int CAP, int GB, int MODE>
 __global__ void __launch_bounds__(32 * WPB)
 spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
                    const int *__restrict__ B_i, const int *__restrict__ B_j, const double *__restrict__ B_a,
                    int allsquare, int diag_base, const int *__restrict__ rows, int *__restrict__ cnt,
                    const int *__restrict__ C_i, int *__restrict__ C_j, double *__restrict__ C_a,
-                   int *__restrict__ overflow) {
+                   int *__restrict__ overflow, int skip_ub = 0) {
+  constexpr bool NUMERIC = MODE != 0;
   constexpr int LIMIT = CAP / 2;
   constexpr int APS = 32 / GB;                      // A entries per step
   extern __shared__ unsigned char smem_raw[];
@@ -391,7 +395,11 @@ spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A
   const int sub = lane % GB, grp_id = lane / GB;
   for (int idx = blockIdx.x * WPB + warp; idx < n; idx += nwarps) {
     const int ic = rows ? rows[idx] : idx;          // rows of one size class / rows still pending
-    if (!NUMERIC && cnt[ic] != PENDING) continue;
+    if (MODE != 1 && cnt[ic] != PENDING) continue;
+    if (MODE == 2 && skip_ub > 0 && C_i[ic + 1] - C_i[ic] > skip_ub) {   // almost surely too long for this table: next pass
+      if (lane == 0) atomicExch(overflow, 1);
+      continue;
+    }
     for (int s = lane; s < CAP; s += 32) keys[s] = -1;
     __syncwarp();
     int count = 0;
@@ -409,7 +417,7 @@ spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A
     auto fold = [&](bool valid, int jb, double prod) {
       const unsigned vm = __ballot_sync(FULL, valid);
       if (vm == 0) return;
-      if (!NUMERIC && count + __popc(vm) > LIMIT) { over = true; return; }   // numeric tables are sized from the symbolic count
+      if (MODE != 1 && count + __popc(vm) > LIMIT) { over = true; return; }   // MODE 1 tables are sized from the symbolic count
       unsigned grp = 0;
       if (valid) grp = __match_any_sync(vm, jb);
       const int leader = valid ? (__ffs(grp) - 1) : lane;
@@ -496,13 +504,35 @@ spgemm_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A
       __syncwarp();
       continue;
     }
-    if (!NUMERIC) {
+    if (MODE == 0) {
       if (lane == 0) cnt[ic] = count;
     } else {
-      const int start = C_i[ic];
+      const int start = C_i[ic];                    // MODE 2: offset of the row's upper-bound slot in the scratch
       for (int p = lane; p < count; p += 32) { C_j[start + p] = cols[p]; C_a[start + p] = acc[p]; }
+      if (MODE == 2 && lane == 0) cnt[ic] = count;
     }
     __syncwarp();
+  }
+}
+
+// upper bound of the length of row ic of A*B: the products it forms (+1 for the diagonal slot), at most `cap`
+__global__ void spgemm_row_bound_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                        const int *__restrict__ B_i, int allsquare, int cap, int *__restrict__ ub) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { ub[n] = 0; return; }
+  long long s = allsquare ? 1 : 0;
+  for (int k = A_i[i]; k < A_i[i + 1]; k++) { const int ja = A_j[k]; s += B_i[ja + 1] - B_i[ja]; }
+  ub[i] = (int)(s < cap ? s : cap);
+}
+// scratch rows (upper-bound offsets) -> CSR rows, one warp per row
+__global__ void spgemm_compact_kernel(int n, const int *__restrict__ off, const int *__restrict__ sj, const double *__restrict__ sa,
+                                      const int *__restrict__ C_i, int *__restrict__ C_j, double *__restrict__ C_a) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  for (int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < n; r += nwarps) {
+    const int src = off[r], dst = C_i[r], len = C_i[r + 1] - dst;
+    for (int p = lane; p < len; p += 32) { C_j[dst + p] = sj[src + p]; C_a[dst + p] = sa[src + p]; }
   }
 }
 
@@ -648,8 +678,84 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   return 0;
 }
 
+// One-pass product: every row is formed once, in shared memory, and parked in a scratch slot of its upper-bound
+// length; the exact CSR is compacted afterwards.  Saves the whole symbolic pass (a second walk over A and B with the
+// same hashing) for one extra copy of C.  *done = 0 -> the caller uses the two-pass path.
+template <int GB>
+static int spgemm_fused_run(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out, int *done) {
+  *done = 0;
+  const int n = A->nrows;
+  int *off = nullptr, *cnt = nullptr, *d_flag = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &off, (size_t)n + 1));
+  spgemm_row_bound_kernel<<<b200_grid((size_t)n + 1, 256), 256, 0, h->stream>>>(n, A->i, A->j, B->i, allsquare, 1024, off);
+  B200_LAUNCH_CHECK();
+  long long total = 0;
+  B200_TRY(b200_reduce_sum_int(h, off, (size_t)n, &total));
+  if (total >= 0x7fffffffLL || total > 12LL * ((long long)A->nnz + B->nnz) + 64LL * n) {   // scratch would dwarf the operands
+    B200_TRY(b200_dfree(h, off));
+    return 0;
+  }
+  B200_TRY(b200_exclusive_scan_inplace(h, off, (size_t)n + 1));
+  int *sj = nullptr;
+  double *sa = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &sj, (size_t)total + 1));
+  B200_TRY(b200_dalloc<double>(h, &sa, (size_t)total + 1));
+  B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
+  B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
+  fill_int_kernel<<<fill_grid(h, n), 256, 0, h->stream>>>((size_t)n, PENDING, cnt);
+  B200_LAUNCH_CHECK();
+  B200_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), h->stream));
+  int flag = 1;
+  for (int pass = 0; pass < 4 && flag; pass++) {
+    B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+    int *rows = nullptr, m = n;
+    if (pass > 0) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
+#define B200_SPGEMM_FUSED(CAPV, BPS)                                                                              \
+    {                                                                                                             \
+      constexpr int CAP = CAPV;                                                                                   \
+      const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));        \
+      B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, 2>, bytes));                                                  \
+      spgemm_warp_kernel<CAP, GB, 2><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                       \
+          m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, diag_base, rows, cnt, off, sj, sa, d_flag,            \
+          pass == 0 ? 512 : 0);                                                                                   \
+    }
+    if (m > 0) {
+      if (pass == 0) B200_SPGEMM_FUSED(256, 15)           // rows of <= 128 entries
+      else if (pass == 1) B200_SPGEMM_FUSED(512, 7)       // <= 256
+      else if (pass == 2) B200_SPGEMM_FUSED(1024, 3)      // <= 512
+      else B200_SPGEMM_FUSED(2048, 1)                     // <= 1024
+      B200_LAUNCH_CHECK();
+    }
+#undef B200_SPGEMM_FUSED
+    B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, rows));
+  }
+  if (!flag) {
+    B200_TRY(b200_exclusive_scan_inplace(h, cnt, (size_t)n + 1));
+    int nnz = 0;
+    B200_CUDA(cudaMemcpyAsync(&nnz, cnt + n, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    b200_csr C = nullptr;
+    B200_TRY(b200_csr_alloc(h, n, ncols_C, nnz, true, &C));
+    B200_CUDA(cudaMemcpyAsync(C->i, cnt, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
+    spgemm_compact_kernel<<<warp_grid(h, n, 16), 32 * WPB, 0, h->stream>>>(n, off, sj, sa, C->i, C->j, C->a);
+    B200_LAUNCH_CHECK();
+    *out = C;
+    *done = 1;
+  }
+  B200_TRY(b200_dfree(h, off)); B200_TRY(b200_dfree(h, cnt)); B200_TRY(b200_dfree(h, d_flag));
+  B200_TRY(b200_dfree(h, sj)); B200_TRY(b200_dfree(h, sa));
+  return 0;
+}
+
 template <int GB>
 static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare, int diag_base, int ncols_C, b200_csr *out, int *done) {
+  static const bool two_pass = [] { const char *e = getenv("B200_SPGEMM_TWO_PASS"); return e && e[0] == '1'; }();
+  if (!two_pass && A->a && B->a) {
+    B200_TRY(spgemm_fused_run<GB>(h, A, B, allsquare, diag_base, ncols_C, out, done));
+    if (*done) return 0;
+  }
   const int n = A->nrows;
   int *cnt = nullptr, *d_flag = nullptr;
   B200_TRY(b200_dalloc<int>(h, &cnt, (size_t)n + 1));
@@ -664,7 +770,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
     if (pass == 0) {
       constexpr int CAP = 256;
       const size_t bytes = (size_t)WPB * sizeof(int) * CAP;
-      spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, n, 16), 32 * WPB, bytes, h->stream>>>(
+      spgemm_warp_kernel<CAP, GB, 0><<<warp_grid(h, n, 16), 32 * WPB, bytes, h->stream>>>(
           n, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, nullptr, cnt, nullptr, nullptr, nullptr, d_flag);
       B200_LAUNCH_CHECK();
     } else {
@@ -673,7 +779,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
       int *rows = nullptr, m = 0;
       B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
       if (m > 0) {
-        spgemm_warp_kernel<CAP, GB, false><<<warp_grid(h, m, 6), 32 * WPB, bytes, h->stream>>>(
+        spgemm_warp_kernel<CAP, GB, 0><<<warp_grid(h, m, 6), 32 * WPB, bytes, h->stream>>>(
             m, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, rows, cnt, nullptr, nullptr, nullptr, d_flag);
         B200_LAUNCH_CHECK();
       }
@@ -702,8 +808,8 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
     int *rows = nullptr, m = 0;                                                                                   \
     B200_TRY(build_row_list(h, n, cnt, LO, CAP / 2, &rows, &m));                                                  \
     if (m > 0) {                                                                                                  \
-      B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, true>, bytes));                                               \
-      spgemm_warp_kernel<CAP, GB, true><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                    \
+      B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, 1>, bytes));                                               \
+      spgemm_warp_kernel<CAP, GB, 1><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                    \
           m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, diag_base, rows, cnt, C->i, C->j, C->a, d_flag);                 \
       B200_LAUNCH_CHECK();                                                                                        \
     }                                                                                                             \
