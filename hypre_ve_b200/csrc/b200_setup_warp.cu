@@ -353,6 +353,120 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// ext+i interpolation + truncation for STENCIL-SIZED rows (the finest level): one thread per fine row, the
+// reference's own sequential loops (par_lr_interp.c:1301-1416, :1523-1803) on thread-private arrays -- C-hat_i
+// (first-touch order) and the strong F neighbours are short lists searched linearly, so no hash table, no HBM
+// scratch and no separate truncation pass.  A row that outgrows the lists raises `overflow` and the caller
+// falls back to the general kernels.
+// ------------------------------------------------------------------------------------------
+template <int CH, int SF>
+__global__ void __launch_bounds__(128)
+extpi_thread_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                    const int *__restrict__ S_i, const int *__restrict__ S_j, const int *__restrict__ cf,
+                    const int *__restrict__ f2c, double trunc_tol, int pmax, int *__restrict__ out_j,
+                    double *__restrict__ out_a, int *__restrict__ out_cnt, int *__restrict__ overflow) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cf[i];
+  if (c >= 0) { out_j[(size_t)i * pmax] = f2c[i]; out_a[(size_t)i * pmax] = 1.0; out_cnt[i] = 1; return; }
+  if (c == -3) { out_cnt[i] = 0; return; }
+  int key[CH], sf[SF];
+  double val[CH];
+  int nkey = 0, nsf = 0;
+  bool over = false;
+  auto find = [&](int k) { for (int p = 0; p < nkey; p++) if (key[p] == k) return p; return -1; };
+  auto touch = [&](int k) {
+    if (find(k) >= 0) return;
+    if (nkey == CH) { over = true; return; }
+    key[nkey++] = k;
+  };
+  for (int jj = S_i[i]; jj < S_i[i + 1] && !over; jj++) {
+    const int i1 = S_j[jj];
+    const int c1 = cf[i1];
+    if (c1 >= 0) touch(i1);
+    else if (c1 != -3) {
+      if (nsf == SF) { over = true; break; }
+      sf[nsf++] = i1;
+      for (int kk = S_i[i1]; kk < S_i[i1 + 1] && !over; kk++) {
+        const int k1 = S_j[kk];
+        if (cf[k1] >= 0) touch(k1);
+      }
+    }
+  }
+  if (over) { atomicExch(overflow, 1); out_cnt[i] = 0; return; }
+  if (nkey == 0) { out_cnt[i] = 0; return; }
+  for (int p = 0; p < nkey; p++) val[p] = 0.0;
+  double diagonal = A_a[A_i[i]];
+  for (int jj = A_i[i] + 1; jj < A_i[i + 1]; jj++) {
+    const int i1 = A_j[jj];
+    const double aij = A_a[jj];
+    const int m1 = find(i1);
+    if (m1 >= 0) { val[m1] += aij; continue; }
+    bool strong_f = false;
+    for (int q = 0; q < nsf; q++) strong_f |= (sf[q] == i1);
+    if (strong_f) {
+      const int b1 = A_i[i1], e1 = A_i[i1 + 1];
+      const int sgn = (A_a[b1] < 0) ? -1 : 1;
+      double sum = 0.0;
+      for (int k = b1 + 1; k < e1; k++) {
+        const double a = A_a[k];
+        if ((sgn * a) < 0) { const int i2 = A_j[k]; if (i2 == i || find(i2) >= 0) sum += a; }
+      }
+      if (sum != 0) {
+        const double distribute = aij / sum;
+        for (int k = b1 + 1; k < e1; k++) {
+          const double a = A_a[k];
+          if ((sgn * a) < 0) {
+            const int i2 = A_j[k];
+            const int m2 = find(i2);
+            if (m2 >= 0) val[m2] += distribute * a;
+            if (i2 == i) diagonal += distribute * a;
+          }
+        }
+      } else {
+        diagonal += aij;
+      }
+    } else if (cf[i1] != -3) {
+      diagonal += aij;
+    }
+  }
+  if (diagonal) for (int p = 0; p < nkey; p++) val[p] /= -diagonal;
+  for (int p = 0; p < nkey; p++) key[p] = f2c[key[p]];
+  // truncation (par_csr_matrix.c:2768-3020)
+  int len = nkey;
+  if (trunc_tol > 0) {
+    double row_nrm = 0;
+    for (int j = 0; j < len; j++) row_nrm = (row_nrm < fabs(val[j])) ? fabs(val[j]) : row_nrm;
+    const double drop = trunc_tol * row_nrm;
+    double row_sum = 0, scale = 0;
+    int keep = 0;
+    for (int j = 0; j < len; j++) {
+      row_sum += val[j];
+      if (!(fabs(val[j]) < drop)) { scale += val[j]; val[keep] = val[j]; key[keep] = key[j]; keep++; }
+    }
+    len = keep;
+    if (scale != 0. && scale != row_sum) {
+      scale = row_sum / scale;
+      for (int j = 0; j < len; j++) val[j] *= scale;
+    }
+  }
+  if (len > pmax) {
+    double row_sum = 0;
+    for (int j = 0; j < len; j++) row_sum += val[j];
+    qsort2_abs_smem(key, val, 0, len - 1);
+    double scale = 0;
+    for (int j = 0; j < pmax; j++) scale += val[j];
+    len = pmax;
+    if (scale != 0. && scale != row_sum) {
+      scale = row_sum / scale;
+      for (int j = 0; j < len; j++) val[j] *= scale;
+    }
+  }
+  out_cnt[i] = len;
+  for (int p = 0; p < len; p++) { out_j[(size_t)i * pmax + p] = key[p]; out_a[(size_t)i * pmax + p] = val[p]; }
+}
+
 __global__ void strided_to_csr_kernel(int n, int stride, const int *__restrict__ P_i, const int *__restrict__ sj,
                                       const double *__restrict__ sa, int *__restrict__ P_j, double *__restrict__ P_a) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,9 +730,10 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   *done = 0;
   if (max_elmts <= 0) return 0;                       // unbounded rows: general path
   if (n == 0) return 0;
-  // stencil-sized rows: the dependent-load chain per row is short and thread-per-row keeps 32x more
-  // rows in flight than a warp per row -> the general kernels win there (profiles/README.md r1_b)
-  if ((double)A->nnz / (A->nrows ? A->nrows : 1) <= 10.0) return 0;
+  // stencil-sized rows (the finest level): one thread per row on private lists (extpi_thread_kernel)
+  const bool stencil_rows = (double)A->nnz / (A->nrows ? A->nrows : 1) <= 10.0;
+  static const bool no_thread_rows = [] { const char *e = getenv("B200_EXTPI_NO_THREAD_ROWS"); return e && e[0] == '1'; }();
+  if (stencil_rows && no_thread_rows) return 0;
   int *d_flag = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_flag, 1));
   int *f2c = nullptr, ncoarse = ncoarse_in;
@@ -633,7 +748,16 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   B200_LAUNCH_CHECK();
   B200_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), h->stream));
   int flag = 1;
-  for (int pass = 0; pass < 2 && flag; pass++) {
+  if (stencil_rows) {
+    // the dependent-load chain per row is short and thread-per-row keeps 32x more rows in flight than a warp per row
+    B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
+    extpi_thread_kernel<32, 16><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
+                                                                        max_elmts, sj, sa, cnt, d_flag);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  for (int pass = 0; pass < 2 && flag && !stencil_rows; pass++) {
     B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
     int *rows = nullptr, m = n;
     if (pass == 1) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
