@@ -394,7 +394,7 @@ extpi_thread_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ 
       }
     }
   }
-  if (over) { atomicExch(overflow, 1); out_cnt[i] = 0; return; }
+  if (over) { atomicExch(overflow, 1); return; }          // stays PENDING: the warp-per-row passes take it
   if (nkey == 0) { out_cnt[i] = 0; return; }
   for (int p = 0; p < nkey; p++) val[p] = 0.0;
   double diagonal = A_a[A_i[i]];
@@ -731,7 +731,9 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   if (max_elmts <= 0) return 0;                       // unbounded rows: general path
   if (n == 0) return 0;
   // stencil-sized rows (the finest level): one thread per row on private lists (extpi_thread_kernel)
-  const bool stencil_rows = (double)A->nnz / (A->nrows ? A->nrows : 1) <= 10.0;
+  static const double thread_avg = [] { const char *e = getenv("B200_EXTPI_THREAD_AVG"); return e ? atof(e) : 10.0; }();
+  const double avg_row = (double)A->nnz / (A->nrows ? A->nrows : 1);
+  const bool stencil_rows = avg_row <= thread_avg;
   static const bool no_thread_rows = [] { const char *e = getenv("B200_EXTPI_NO_THREAD_ROWS"); return e && e[0] == '1'; }();
   if (stencil_rows && no_thread_rows) return 0;
   int *d_flag = nullptr;
@@ -751,16 +753,21 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   if (stencil_rows) {
     // the dependent-load chain per row is short and thread-per-row keeps 32x more rows in flight than a warp per row
     B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
-    extpi_thread_kernel<32, 16><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
-                                                                        max_elmts, sj, sa, cnt, d_flag);
+    if (avg_row <= 10.0)
+      extpi_thread_kernel<32, 16><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
+                                                                          max_elmts, sj, sa, cnt, d_flag);
+    else
+      extpi_thread_kernel<64, 32><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
+                                                                          max_elmts, sj, sa, cnt, d_flag);
     B200_LAUNCH_CHECK();
     B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
   }
-  for (int pass = 0; pass < 2 && flag && !stencil_rows; pass++) {
+  // rows still PENDING (all of them on the coarse levels; the few the private lists could not hold otherwise)
+  for (int pass = 0; pass < 2 && flag; pass++) {
     B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
     int *rows = nullptr, m = n;
-    if (pass == 1) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
+    if (pass == 1 || stencil_rows) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
 #define B200_EXTPI_LAUNCH(CAPV, BPS)                                                                              \
     {                                                                                                             \
       constexpr int CAP = CAPV;                                                                                   \
