@@ -1,9 +1,9 @@
 /* ij_b200.c -- a plain-C client of the reference's public API, linked against libhypre_b200.so.
  *
  * It walks the same call sequence as the reference driver test/ij.c does for
- *     ij -laplacian [-27pt] -n nx ny nz [-c cx cy cz] -solver {0,1,2,-1} ...
+ *     ij -laplacian [-27pt] | -difconv [-a ax ay az] [-atype t]  -n nx ny nz [-c cx cy cz] -solver {0,1,2,3,4,9,10,-1} ...
  * (problem: ij.c:7785-7830 / :9084; rhs b = 1, x0 = 0: :2318-2340; AMG-PCG: :3884-4043, :4270-4330;
- * AMG alone: :3390-3560; matvec loop: :3206-3243) using only HYPRE_* calls, so it shows that host C
+ * AMG alone: :3390-3560; AMG-GMRES: :5298-5480; AMG-BiCGSTAB: :6364-6500; matvec loop: :3206-3243) using only HYPRE_* calls, so it shows that host C
  * written against hypre's API runs on the B200 path by relinking.  It prints the result lines in the
  * driver's format ("Iterations = ", "Final Relative Residual Norm = ") so the tests can diff it
  * against the reference's own `ij` run with the same flags.
@@ -48,9 +48,38 @@ static HYPRE_ParCSRMatrix build_by_ij(int nx, int ny, int nz, const double *cv, 
   return (HYPRE_ParCSRMatrix)obj;
 }
 
+/* the seven values of the convection-diffusion stencil -cx Dxx - cy Dyy - cz Dzz + ax Dx + ay Dy + az Dz, as
+ * BuildParDifConv computes them (ij.c:8266-8409): centre, x-, y-, z-, x+, y+, z+ */
+static int sign_double(double a) { return (0.0 < a) - (0.0 > a); }
+static void difconv_values(int nx, int ny, int nz, double cx, double cy, double cz, double ax, double ay, double az, int atype,
+                           double *v) {
+  const int n[3] = {nx, ny, nz};
+  const double c[3] = {cx, cy, cz}, a[3] = {ax, ay, az};
+  v[0] = 0.;
+  for (int d = 0; d < 3; d++) {
+    const double hin = 1. / (double)(n[d] + 1);
+    if (atype == 0 || atype == 1 || atype == 3) {
+      const int back = atype == 1 || (atype == 3 && sign_double(c[d]) * sign_double(a[d]) == 1);
+      if (back) {                                         /* backward differences for the convection term */
+        v[1 + d] = -c[d] / (hin * hin) - a[d] / hin;
+        v[4 + d] = -c[d] / (hin * hin);
+        if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) + 1. * a[d] / hin;
+      } else {                                            /* forward differences */
+        v[1 + d] = -c[d] / (hin * hin);
+        v[4 + d] = -c[d] / (hin * hin) + a[d] / hin;
+        if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) - 1. * a[d] / hin;
+      }
+    } else {                                              /* centred differences */
+      v[1 + d] = -c[d] / (hin * hin) - a[d] / (2. * hin);
+      v[4 + d] = -c[d] / (hin * hin) + a[d] / (2. * hin);
+      if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin);
+    }
+  }
+}
+
 int main(int argc, char **argv) {
-  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0;
-  double cx = 1., cy = 1., cz = 1.;
+  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0, difconv = 0, atype = 0, k_dim = 5;
+  double cx = 1., cy = 1., cz = 1., ax = 1., ay = 1., az = 1.;
   /* driver defaults, test/ij.c:203-330 and :1181-1205 */
   int coarsen_type = 10, interp_type = 6, P_max_elmts = 4, relax_type = -1, relax_order = 0, max_levels = 25;
   int agg_num_levels = 0, rap2 = 0, mod_rap2 = 0, keepTranspose = 1, num_sweeps = 1, max_iter = 1000, mg_max_iter = 100;
@@ -60,6 +89,10 @@ int main(int argc, char **argv) {
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-laplacian")) ;
     else if (!strcmp(argv[a], "-27pt")) stencil27 = 1;
+    else if (!strcmp(argv[a], "-difconv")) difconv = 1;
+    else if (!strcmp(argv[a], "-a") && a + 3 < argc) { ax = atof(argv[a + 1]); ay = atof(argv[a + 2]); az = atof(argv[a + 3]); a += 3; }
+    else if (!strcmp(argv[a], "-atype") && a + 1 < argc) atype = atoi(argv[++a]);
+    else if (!strcmp(argv[a], "-k") && a + 1 < argc) k_dim = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-ijbuild")) ijbuild = 1;
     else if (!strcmp(argv[a], "-n") && a + 3 < argc) { nx = atoi(argv[a + 1]); ny = atoi(argv[a + 2]); nz = atoi(argv[a + 3]); a += 3; }
     else if (!strcmp(argv[a], "-c") && a + 3 < argc) { cx = atof(argv[a + 1]); cy = atof(argv[a + 2]); cz = atof(argv[a + 3]); a += 3; }
@@ -95,7 +128,7 @@ int main(int argc, char **argv) {
   if (HYPRE_Init()) { fprintf(stderr, "ij_b200: HYPRE_Init failed (no B200 / CUDA device?)\n"); return 1; }
 
   /* operator */
-  double values[4];
+  double values[7];
   HYPRE_ParCSRMatrix A;
   HYPRE_IJMatrix ij_A = NULL;
   if (stencil27) {
@@ -103,6 +136,9 @@ int main(int argc, char **argv) {
     if (nx == 1 || ny == 1 || nz == 1) values[0] = 8.0;
     if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
     A = GenerateLaplacian27pt(MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+  } else if (difconv) {
+    difconv_values(nx, ny, nz, cx, cy, cz, ax, ay, az, atype, values);  /* ij.c:8266-8409 */
+    A = GenerateDifConv(MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
   } else {
     values[1] = -cx; values[2] = -cy; values[3] = -cz;                   /* ij.c:7789-7806 */
     values[0] = 0.;
@@ -115,7 +151,8 @@ int main(int argc, char **argv) {
   if (!A) { fprintf(stderr, "ij_b200: could not build the operator\n"); return 1; }
   HYPRE_BigInt M, N;
   HYPRE_ParCSRMatrixGetDims(A, &M, &N);
-  printf("  Laplacian%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", stencil27 ? " 27pt" : "", nx, ny, nz, M);
+  printf("  %s%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", difconv && !stencil27 ? "Convection-Diffusion" : "Laplacian",
+         stencil27 ? " 27pt" : "", nx, ny, nz, M);
 
   /* rhs = 1, x0 = 0 (the driver's default build_rhs_type 2 / build_x0_type) */
   HYPRE_IJVector ij_b, ij_x;
@@ -145,7 +182,7 @@ int main(int argc, char **argv) {
     double xx = 0;
     HYPRE_ParVectorInnerProd(x, x, &xx);
     printf("Matvec x 100 done, <Ab, Ab> = %.15e\n", xx);
-  } else if (solver_id == 0 || solver_id == 1) {
+  } else if (solver_id == 0 || solver_id == 1 || solver_id == 3 || solver_id == 9) {
     HYPRE_Solver amg, pcg = NULL;
     HYPRE_BoomerAMGCreate(&amg);
     HYPRE_BoomerAMGSetInterpType(amg, interp_type);
@@ -185,6 +222,49 @@ int main(int argc, char **argv) {
       HYPRE_BoomerAMGGetNumIterations(amg, &num_iterations);
       HYPRE_BoomerAMGGetFinalRelativeResidualNorm(amg, &final_res_norm);
       printf("\nBoomerAMG Iterations = %d\n", num_iterations);
+    } else if (solver_id == 3) {                                            /* ij.c:5298-5480 */
+      HYPRE_ParCSRGMRESCreate(MPI_COMM_WORLD, &pcg);
+      HYPRE_GMRESSetKDim(pcg, k_dim);
+      HYPRE_GMRESSetMaxIter(pcg, max_iter);
+      HYPRE_GMRESSetTol(pcg, tol);
+      HYPRE_GMRESSetAbsoluteTol(pcg, 0.);
+      HYPRE_GMRESSetLogging(pcg, 1);
+      HYPRE_GMRESSetPrintLevel(pcg, ioutdat);
+      HYPRE_GMRESSetRelChange(pcg, 0);
+      printf("Solver: AMG-GMRES\n");
+      HYPRE_BoomerAMGSetTol(amg, pc_tol);
+      HYPRE_BoomerAMGSetMaxIter(amg, 1);
+      HYPRE_GMRESSetMaxIter(pcg, mg_max_iter);
+      HYPRE_GMRESSetPrecond(pcg, (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSolve, (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSetup, amg);
+      HYPRE_Solver got = NULL;
+      HYPRE_GMRESGetPrecond(pcg, &got);
+      if (got != amg) { printf("HYPRE_GMRESGetPrecond got bad precond\n"); return -1; }
+      HYPRE_GMRESSetup(pcg, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+      HYPRE_GMRESSolve(pcg, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+      HYPRE_GMRESGetNumIterations(pcg, &num_iterations);
+      HYPRE_GMRESGetFinalRelativeResidualNorm(pcg, &final_res_norm);
+      double ts = 0, tv = 0;
+      HYPRE_b200_KrylovGetTimes(pcg, &ts, &tv);
+      printf("GMRES Setup: device time = %f seconds\nGMRES Solve: device time = %f seconds\n", ts, tv);
+      printf("\nGMRES Iterations = %d\n", num_iterations);
+      HYPRE_ParCSRGMRESDestroy(pcg);
+    } else if (solver_id == 9) {                                            /* ij.c:6364-6500 */
+      HYPRE_ParCSRBiCGSTABCreate(MPI_COMM_WORLD, &pcg);
+      HYPRE_BiCGSTABSetMaxIter(pcg, max_iter);
+      HYPRE_BiCGSTABSetTol(pcg, tol);
+      HYPRE_BiCGSTABSetAbsoluteTol(pcg, 0.);
+      HYPRE_BiCGSTABSetLogging(pcg, ioutdat);
+      HYPRE_BiCGSTABSetPrintLevel(pcg, ioutdat);
+      printf("Solver: AMG-BiCGSTAB\n");
+      HYPRE_BoomerAMGSetTol(amg, pc_tol);
+      HYPRE_BoomerAMGSetMaxIter(amg, 1);
+      HYPRE_BiCGSTABSetPrecond(pcg, (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSolve, (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSetup, amg);
+      HYPRE_BiCGSTABSetup(pcg, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+      HYPRE_BiCGSTABSolve(pcg, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+      HYPRE_BiCGSTABGetNumIterations(pcg, &num_iterations);
+      HYPRE_BiCGSTABGetFinalRelativeResidualNorm(pcg, &final_res_norm);
+      printf("\nBiCGSTAB Iterations = %d\n", num_iterations);
+      HYPRE_ParCSRBiCGSTABDestroy(pcg);
     } else {
       HYPRE_ParCSRPCGCreate(MPI_COMM_WORLD, &pcg);
       HYPRE_PCGSetMaxIter(pcg, max_iter);
@@ -236,8 +316,42 @@ int main(int argc, char **argv) {
     HYPRE_PCGGetFinalRelativeResidualNorm(pcg, &final_res_norm);
     printf("\nIterations = %d\nFinal Relative Residual Norm = %e\n", num_iterations, final_res_norm);
     HYPRE_ParCSRPCGDestroy(pcg);
+  } else if (solver_id == 4) {                                             /* ij.c:5481-5491 */
+    HYPRE_Solver gm;
+    HYPRE_ParCSRGMRESCreate(MPI_COMM_WORLD, &gm);
+    HYPRE_GMRESSetKDim(gm, k_dim);
+    HYPRE_GMRESSetMaxIter(gm, max_iter);
+    HYPRE_GMRESSetTol(gm, tol);
+    HYPRE_GMRESSetAbsoluteTol(gm, 0.);
+    HYPRE_GMRESSetLogging(gm, 1);
+    HYPRE_GMRESSetPrintLevel(gm, ioutdat);
+    HYPRE_GMRESSetRelChange(gm, 0);
+    printf("Solver: DS-GMRES\n");
+    HYPRE_GMRESSetPrecond(gm, (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScale, (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScaleSetup, NULL);
+    HYPRE_GMRESSetup(gm, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+    HYPRE_GMRESSolve(gm, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+    HYPRE_GMRESGetNumIterations(gm, &num_iterations);
+    HYPRE_GMRESGetFinalRelativeResidualNorm(gm, &final_res_norm);
+    printf("\nGMRES Iterations = %d\nFinal Relative Residual Norm = %e\n", num_iterations, final_res_norm);
+    HYPRE_ParCSRGMRESDestroy(gm);
+  } else if (solver_id == 10) {                                            /* ij.c:6481-6491 */
+    HYPRE_Solver bi;
+    HYPRE_ParCSRBiCGSTABCreate(MPI_COMM_WORLD, &bi);
+    HYPRE_BiCGSTABSetMaxIter(bi, max_iter);
+    HYPRE_BiCGSTABSetTol(bi, tol);
+    HYPRE_BiCGSTABSetAbsoluteTol(bi, 0.);
+    HYPRE_BiCGSTABSetLogging(bi, ioutdat);
+    HYPRE_BiCGSTABSetPrintLevel(bi, ioutdat);
+    printf("Solver: DS-BiCGSTAB\n");
+    HYPRE_BiCGSTABSetPrecond(bi, (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScale, (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScaleSetup, NULL);
+    HYPRE_BiCGSTABSetup(bi, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+    HYPRE_BiCGSTABSolve(bi, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+    HYPRE_BiCGSTABGetNumIterations(bi, &num_iterations);
+    HYPRE_BiCGSTABGetFinalRelativeResidualNorm(bi, &final_res_norm);
+    printf("\nBiCGSTAB Iterations = %d\nFinal Relative Residual Norm = %e\n", num_iterations, final_res_norm);
+    HYPRE_ParCSRBiCGSTABDestroy(bi);
   } else {
-    fprintf(stderr, "ij_b200: solver %d is not on the B200 path (0 AMG, 1 AMG-PCG, 2 DS-PCG, -1 matvec)\n", solver_id);
+    fprintf(stderr, "ij_b200: solver %d is not on the B200 path (0 AMG, 1 AMG-PCG, 2 DS-PCG, 3 AMG-GMRES, 4 DS-GMRES, 9 AMG-BiCGSTAB, 10 DS-BiCGSTAB, -1 matvec)\n", solver_id);
     return 2;
   }
   /* read a few solution values back through the IJ interface, as examples/ex5.c does */

@@ -57,6 +57,7 @@ SIGNATURES = {
     "b200_vec_dot": (_i, [_vp, _i, _vp, _vp, _dp]),
     "b200_generate_laplacian": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_laplacian27": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_generate_difconv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_parcsr_create_from_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_parcsr_destroy": (_i, [_vp, _vp]),
     "b200_parcsr_local_rows": (_i, [_vp, _ip, _ip, _ip, _ip]),
@@ -89,6 +90,8 @@ SIGNATURES = {
     "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
     "b200_pcg_solve_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp]),
     "b200_parcsr_diag_scale": (_i, [_vp, _vp, _vp, _vp]),
+    "b200_gmres_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp, _ip]),
+    "b200_bicgstab_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp, _ip]),
     "b200_comm_create_single": (_i, [C.POINTER(_vp)]),
     "b200_comm_group_create": (_i, [_i, C.POINTER(_vp)]),
     "b200_comm_group_destroy": (_i, [_vp]),
@@ -99,6 +102,7 @@ SIGNATURES = {
     "b200_comm_rank": (_i, [_vp]),
     "b200_comm_size": (_i, [_vp]),
     "b200_dist_generate_laplacian": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_dist_generate_difconv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_dist_matrix_destroy": (_i, [_vp, _vp]),
     "b200_dist_matrix_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "b200_dist_matrix_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -248,6 +252,44 @@ class Csr:
             self.p = None
 
 
+class _GmresParams(C.Structure):      # b200_gmres_params (include/hypre_b200.h)
+    _fields_ = [("tol", _d), ("a_tol", _d), ("cf_tol", _d), ("max_iter", _i), ("min_iter", _i), ("k_dim", _i),
+                ("rel_change", _i), ("skip_real_r_check", _i), ("precond", _i)]
+
+
+class _BicgstabParams(C.Structure):   # b200_bicgstab_params
+    _fields_ = [("tol", _d), ("a_tol", _d), ("cf_tol", _d), ("max_iter", _i), ("min_iter", _i), ("stop_crit", _i),
+                ("precond", _i)]
+
+
+def difconv_values(nx, ny, nz, c=(1.0, 1.0, 1.0), a=(1.0, 1.0, 1.0), atype=0):
+    """The seven stencil values of -cx Dxx - cy Dyy - cz Dzz + ax Dx + ay Dy + az Dz as the reference driver
+    computes them (src/test/ij.c:8266-8409, BuildParDifConv): centre, x-, y-, z-, x+, y+, z+.
+    atype 0 forward, 1 backward, 3 upwind, anything else centred differences for the convection term."""
+    v = [0.0] * 7
+    for d, n in enumerate((nx, ny, nz)):
+        hin = 1.0 / float(n + 1)
+        sign = lambda t: (0.0 < t) - (0.0 > t)
+        if atype in (0, 1, 3):
+            back = atype == 1 or (atype == 3 and sign(c[d]) * sign(a[d]) == 1)
+            if back:
+                v[1 + d] = -c[d] / (hin * hin) - a[d] / hin
+                v[4 + d] = -c[d] / (hin * hin)
+                if n > 1:
+                    v[0] += 2.0 * c[d] / (hin * hin) + 1.0 * a[d] / hin
+            else:
+                v[1 + d] = -c[d] / (hin * hin)
+                v[4 + d] = -c[d] / (hin * hin) + a[d] / hin
+                if n > 1:
+                    v[0] += 2.0 * c[d] / (hin * hin) - 1.0 * a[d] / hin
+        else:
+            v[1 + d] = -c[d] / (hin * hin) - a[d] / (2.0 * hin)
+            v[4 + d] = -c[d] / (hin * hin) + a[d] / (2.0 * hin)
+            if n > 1:
+                v[0] += 2.0 * c[d] / (hin * hin)
+    return v
+
+
 class ParCsr:
     def __init__(self, handle, p):
         self.h, self.p = handle, p
@@ -274,6 +316,14 @@ class ParCsr:
         v[1] = -1.0
         out = _vp()
         _chk(_lib.b200_generate_laplacian27(handle.p, nx, ny, nz, P, Q, R, p, q, r, v, C.byref(out)))
+        return cls(handle, out)
+
+    @classmethod
+    def difconv(cls, handle, nx, ny, nz, c=(1.0, 1.0, 1.0), a=(1.0, 1.0, 1.0), atype=0, P=1, Q=1, R=1, p=0, q=0, r=0):
+        """`ij -difconv -n nx ny nz -c .. -a .. -atype ..`: GenerateDifConv (par_difconv.c:15), nonsymmetric 7-point"""
+        v = (C.c_double * 7)(*difconv_values(nx, ny, nz, c, a, atype))
+        out = _vp()
+        _chk(_lib.b200_generate_difconv(handle.p, nx, ny, nz, P, Q, R, p, q, r, v, C.byref(out)))
         return cls(handle, out)
 
     @classmethod
@@ -465,6 +515,29 @@ class Handle:
                                  C.byref(its), C.byref(rel), _np_ptr(norms)))
         return its.value, rel.value, norms[: its.value + 1]
 
+    def gmres(self, A, amg, b, x, tol=1e-8, max_iter=100, k_dim=5, precond=None, a_tol=0.0, min_iter=0,
+              skip_real_r_check=0):
+        """hypre_GMRESSolve (krylov/gmres.c:226): restarted GMRES(k_dim), right-preconditioned by one BoomerAMG cycle
+        (precond 1, default when amg is given), diagonal scaling (2) or nothing (0).
+        Returns (iterations, final relative residual, norms[0..iterations], converged)."""
+        prm = _GmresParams(tol, a_tol, 0.0, max_iter, min_iter, k_dim, 0, skip_real_r_check,
+                           (1 if amg is not None else 0) if precond is None else precond)
+        its, rel, conv = _i(), _d(), _i()
+        norms = np.zeros(max_iter + 2, np.float64)
+        _chk(_lib.b200_gmres_solve(self.p, A.p, amg.p if amg is not None else None, C.byref(prm), b.ptr, x.ptr,
+                                   C.byref(its), C.byref(rel), _np_ptr(norms), C.byref(conv)))
+        return its.value, rel.value, norms[: its.value + 1], conv.value
+
+    def bicgstab(self, A, amg, b, x, tol=1e-8, max_iter=100, precond=None, a_tol=0.0, min_iter=0):
+        """hypre_BiCGSTABSolve (krylov/bicgstab.c:207); same conventions as gmres()"""
+        prm = _BicgstabParams(tol, a_tol, 0.0, max_iter, min_iter, 0,
+                              (1 if amg is not None else 0) if precond is None else precond)
+        its, rel, conv = _i(), _d(), _i()
+        norms = np.zeros(max_iter + 2, np.float64)
+        _chk(_lib.b200_bicgstab_solve(self.p, A.p, amg.p if amg is not None else None, C.byref(prm), b.ptr, x.ptr,
+                                      C.byref(its), C.byref(rel), _np_ptr(norms), C.byref(conv)))
+        return its.value, rel.value, norms[: its.value + 1], conv.value
+
     def close(self):
         if self.p:
             _chk(_lib.b200_finalize(self.p))
@@ -544,6 +617,14 @@ class DistMatrix:
             v[1] = -1.0
         out = _vp()
         _chk(_lib.b200_dist_generate_laplacian(handle.p, comm.p, nx, ny, nz, P, Q, R, stencil, v, C.byref(out)))
+        return cls(handle, comm, out)
+
+    @classmethod
+    def difconv(cls, handle, comm, nx, ny, nz, P, Q, R, c=(1.0, 1.0, 1.0), a=(1.0, 1.0, 1.0), atype=0):
+        """GenerateDifConv on the P x Q x R process grid (par_difconv.c:15)"""
+        v = (C.c_double * 7)(*difconv_values(nx, ny, nz, c, a, atype))
+        out = _vp()
+        _chk(_lib.b200_dist_generate_difconv(handle.p, comm.p, nx, ny, nz, P, Q, R, v, C.byref(out)))
         return cls(handle, comm, out)
 
     @property

@@ -614,6 +614,12 @@ extern "C" int b200_amg_solve_ex(b200_handle h, b200_amg amg, b200_parcsr A, con
   return 0;
 }
 
+// ClearVector(out); precond(A, rhs, out): one cycle from a zero guess, for the Krylov drivers in b200_krylov.cu
+int b200_amg_precond(b200_handle h, b200_amg amg, const double *d_rhs, double *d_out) {
+  if (!amg || !amg->is_setup) B200_FAIL("krylov: preconditioner has not been set up");
+  return amg_cycle(h, amg, d_rhs, d_out, true);
+}
+
 extern "C" int b200_amg_solve(b200_handle h, b200_amg amg, const double *d_f, double *d_u) {
   if (!amg || !amg->is_setup) B200_FAIL("amg_solve: setup has not been called");
   if (amg->ip["MaxIter"] != 1 || amg->rp["Tol"] != 0.0)

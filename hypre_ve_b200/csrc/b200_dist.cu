@@ -512,11 +512,21 @@ static int gather_starts(b200_handle h, b200_comm c, int n_local, std::vector<in
 // ------------------------------------------------------------------------------------------------
 // public: generator, info, download, matvec
 // ------------------------------------------------------------------------------------------------
-extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
-                                            int stencil, const double *values, b200_dist_matrix *out) {
+// stencil 7: values = centre, x, y, z (GenerateLaplacian); 27: centre, off-centre (GenerateLaplacian27pt);
+// 70: centre, x-, y-, z-, x+, y+, z+ (GenerateDifConv, par_difconv.c:15)
+static int dist_generate(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                         int stencil, const double *user_values, b200_dist_matrix *out) {
   const int nr = b200_comm_size(c), me = b200_comm_rank(c);
   if (P * Q * R != nr) B200_FAIL("process grid P*Q*R must equal the number of ranks");
-  if (stencil != 7 && stencil != 27) B200_FAIL("stencil must be 7 or 27");
+  if (stencil != 7 && stencil != 27 && stencil != 70) B200_FAIL("stencil must be 7 or 27");
+  double values[7] = {0, 0, 0, 0, 0, 0, 0};
+  if (stencil == 7) {
+    for (int k = 0; k < 4; k++) values[k] = user_values[k];
+    for (int k = 1; k < 4; k++) values[k + 3] = user_values[k];
+  } else {
+    for (int k = 0; k < (stencil == 70 ? 7 : 2); k++) values[k] = user_values[k];
+  }
+  if (stencil == 70) stencil = 7;
   const int p = me % P, q = ((me - p) / P) % Q, r = (me - p - P * q) / (P * Q);      // ij.c:7785-7787
   b200_dist_matrix M = new b200_dist_matrix_s();
   B200_TRY(b200_generate_stencil_global(h, nx, ny, nz, P, Q, R, p, q, r, stencil, values, &M->G, &M->first_row));
@@ -534,6 +544,15 @@ extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, 
   B200_TRY(dist_localize(h, c, M));
   *out = M;
   return 0;
+}
+extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                                            int stencil, const double *values, b200_dist_matrix *out) {
+  if (stencil != 7 && stencil != 27) B200_FAIL("stencil must be 7 or 27");
+  return dist_generate(h, c, nx, ny, nz, P, Q, R, stencil, values, out);
+}
+extern "C" int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                                          const double values[7], b200_dist_matrix *out) {
+  return dist_generate(h, c, nx, ny, nz, P, Q, R, 70, values, out);
 }
 
 extern "C" int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix M) {

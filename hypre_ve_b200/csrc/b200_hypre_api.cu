@@ -52,7 +52,7 @@ b200_handle handle() {
 #define NEED_HANDLE() b200_handle h = handle(); if (!h) return g_error_flag
 #define CALL(expr, where) do { if ((expr)) return err_b200(where); } while (0)
 
-enum SolverKind { KIND_AMG = 0x414d47, KIND_PCG = 0x504347 };
+enum SolverKind { KIND_AMG = 0x414d47, KIND_PCG = 0x504347, KIND_GMRES = 0x474d52, KIND_BICGSTAB = 0x424943 };
 
 }  // namespace
 
@@ -95,12 +95,17 @@ struct hypre_Solver_struct {
   HYPRE_Solver precond_solver = nullptr;
   std::vector<double> norms;
   double setup_s = 0.0, solve_s = 0.0;
+  // GMRES / BiCGSTAB (hypre_GMRESCreate gmres.c:60-100, hypre_BiCGSTABCreate bicgstab.c:55-95)
+  int k_dim = 5, min_iter = 0, stop_crit = 0, skip_real_r_check = 0, converged = 0;
+  double cf_tol = 0.0;
 };
 
 namespace {
 
 bool is_amg(HYPRE_Solver s) { return s && s->kind == KIND_AMG; }
 bool is_pcg(HYPRE_Solver s) { return s && s->kind == KIND_PCG; }
+bool is_gmres(HYPRE_Solver s) { return s && s->kind == KIND_GMRES; }
+bool is_bicgstab(HYPRE_Solver s) { return s && s->kind == KIND_BICGSTAB; }
 
 struct Neutral { const char *name; double value; const char *what; };
 // parameters that switch on something outside the B200 path: only the neutral value is accepted
@@ -440,6 +445,19 @@ HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny,
   }
   b200_parcsr A = nullptr;
   if (b200_generate_laplacian(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateLaplacian"); return nullptr; }
+  return wrap_generated(A, (long long)nx * ny * nz);
+}
+HYPRE_ParCSRMatrix GenerateDifConv(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int R,
+                                   HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value) {     // par_difconv.c:15
+  b200_handle h = handle();
+  if (!h) return nullptr;
+  if (P * Q * R != 1) {
+    fprintf(stderr, "hypre_b200: GenerateDifConv through the HYPRE API is single-rank; use b200_dist_generate_difconv\n");
+    err(HYPRE_ERROR_GENERIC);
+    return nullptr;
+  }
+  b200_parcsr A = nullptr;
+  if (b200_generate_difconv(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateDifConv"); return nullptr; }
   return wrap_generated(A, (long long)nx * ny * nz);
 }
 HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,
@@ -948,6 +966,227 @@ HYPRE_Int HYPRE_b200_PCGGetTimes(HYPRE_Solver s, HYPRE_Real *setup_s, HYPRE_Real
 }
 HYPRE_Int HYPRE_b200_PCGGetResidualNorms(HYPRE_Solver s, HYPRE_Int n, HYPRE_Real *norms) {
   if (!is_pcg(s)) return err_arg(1);
+  for (int i = 0; i < n && i < (int)s->norms.size(); i++) norms[i] = s->norms[i];
+  return g_error_flag;
+}
+
+// ---- GMRES (krylov/HYPRE_gmres.c:21-320, parcsr_ls/HYPRE_parcsr_gmres.c:15-230) and BiCGSTAB
+//      (krylov/HYPRE_bicgstab.c:25-210, parcsr_ls/HYPRE_parcsr_bicgstab.c:15-220): ij -solver 3 / -solver 9 ----------
+static HYPRE_Int krylov_create(HYPRE_Solver *solver, int kind) {
+  if (!solver) return err_arg(2);
+  hypre_Solver_struct *s = new hypre_Solver_struct();
+  s->kind = kind;
+  *solver = s;
+  return g_error_flag;
+}
+static HYPRE_Int krylov_setup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!A) return err_arg(2);
+  NEED_HANDLE();
+  b200_timer_start(h);
+  if (s->precond_setup)                                         // hypre_GMRESSetup gmres.c:201, hypre_BiCGSTABSetup bicgstab.c:180
+    s->precond_setup(s->precond_solver, (HYPRE_Matrix)A, (HYPRE_Vector)b, (HYPRE_Vector)x);
+  double ms = 0;
+  b200_timer_stop_ms(h, &ms);
+  s->setup_s = ms * 1e-3;
+  return g_error_flag;
+}
+// which device preconditioner the two function pointers stand for: 0 none, 1 BoomerAMG (one cycle), 2 diagonal scaling
+static int krylov_precond(HYPRE_Solver s, const char *who, b200_amg *amg) {
+  *amg = nullptr;
+  if (s->precond == (HYPRE_PtrToSolverFcn)HYPRE_BoomerAMGSolve) {
+    if (!is_amg(s->precond_solver)) { err_arg(1); return -1; }
+    *amg = s->precond_solver->amg;
+    if (b200_amg_get_int(*amg, "MaxIter") != 1 || s->precond_solver->stored["Tol"] != 0.0) {     // ij.c:5345, :5339
+      fprintf(stderr, "hypre_b200: %s: the BoomerAMG preconditioner must have MaxIter 1 and Tol 0\n", who);
+      err(HYPRE_ERROR_GENERIC);
+      return -1;
+    }
+    return 1;
+  }
+  if (s->precond == (HYPRE_PtrToSolverFcn)HYPRE_ParCSRDiagScale) return 2;
+  if (s->precond != nullptr) {
+    fprintf(stderr, "hypre_b200: %s: only HYPRE_BoomerAMGSolve, HYPRE_ParCSRDiagScale or no preconditioner run on the B200 path\n", who);
+    err(HYPRE_ERROR_GENERIC);
+    return -1;
+  }
+  return 0;
+}
+static void krylov_print_norms(HYPRE_Solver s, b200_handle h, HYPRE_ParVector b) {   // gmres.c:516-526, bicgstab.c:453-461
+  double b2 = 0;
+  b200_vec_dot(h, b->n, b->d, b->d, &b2);
+  const double b_norm = std::sqrt(b2);
+  printf("L2 norm of b: %e\n", b_norm);
+  printf("Initial L2 norm of residual: %e\n", s->norms[0]);
+  printf("=============================================\n\n");
+  printf("Iters     resid.norm     conv.rate  rel.res.norm\n");
+  printf("-----    ------------    ---------- ------------\n");
+  for (int i = 1; i <= s->num_iterations; i++)
+    printf("% 5d    %e    %f   %e\n", i, s->norms[i], s->norms[i] / s->norms[i - 1], b_norm > 0 ? s->norms[i] / b_norm : 0.0);
+  printf("\n\n");
+}
+
+HYPRE_Int HYPRE_ParCSRGMRESCreate(MPI_Comm, HYPRE_Solver *solver) { return krylov_create(solver, KIND_GMRES); }
+HYPRE_Int HYPRE_ParCSRGMRESDestroy(HYPRE_Solver s) {
+  if (!is_gmres(s)) return err_arg(1);
+  delete s;
+  return g_error_flag;
+}
+#define GMRES_SET(NAME, TYPE, FIELD) \
+  HYPRE_Int HYPRE_GMRESSet##NAME(HYPRE_Solver s, TYPE v) { if (!is_gmres(s)) return err_arg(1); s->FIELD = v; return g_error_flag; } \
+  HYPRE_Int HYPRE_GMRESGet##NAME(HYPRE_Solver s, TYPE *v) { if (!is_gmres(s)) return err_arg(1); *v = s->FIELD; return g_error_flag; }
+GMRES_SET(KDim, HYPRE_Int, k_dim)
+GMRES_SET(Tol, HYPRE_Real, tol)
+GMRES_SET(AbsoluteTol, HYPRE_Real, a_tol)
+GMRES_SET(ConvergenceFactorTol, HYPRE_Real, cf_tol)
+GMRES_SET(MinIter, HYPRE_Int, min_iter)
+GMRES_SET(MaxIter, HYPRE_Int, max_iter)
+GMRES_SET(StopCrit, HYPRE_Int, stop_crit)
+GMRES_SET(RelChange, HYPRE_Int, rel_change)
+GMRES_SET(SkipRealResidualCheck, HYPRE_Int, skip_real_r_check)
+GMRES_SET(PrintLevel, HYPRE_Int, print_level)
+GMRES_SET(Logging, HYPRE_Int, logging)
+#undef GMRES_SET
+HYPRE_Int HYPRE_GMRESSetPrecond(HYPRE_Solver s, HYPRE_PtrToSolverFcn precond, HYPRE_PtrToSolverFcn precond_setup, HYPRE_Solver precond_solver) {
+  if (!is_gmres(s)) return err_arg(1);
+  s->precond = precond; s->precond_setup = precond_setup; s->precond_solver = precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_GMRESGetPrecond(HYPRE_Solver s, HYPRE_Solver *precond_data) {
+  if (!is_gmres(s)) return err_arg(1);
+  *precond_data = s->precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_GMRESGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { if (!is_gmres(s)) return err_arg(1); *n = s->num_iterations; return g_error_flag; }
+HYPRE_Int HYPRE_GMRESGetConverged(HYPRE_Solver s, HYPRE_Int *c) { if (!is_gmres(s)) return err_arg(1); *c = s->converged; return g_error_flag; }
+HYPRE_Int HYPRE_GMRESGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { if (!is_gmres(s)) return err_arg(1); *r = s->rel_res; return g_error_flag; }
+HYPRE_Int HYPRE_ParCSRGMRESSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_gmres(s)) return err_arg(1);
+  return krylov_setup(s, A, b, x);
+}
+HYPRE_Int HYPRE_ParCSRGMRESSolve(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_gmres(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  if (!b || !b->d) return err_arg(3);
+  if (!x || !x->d) return err_arg(4);
+  NEED_HANDLE();
+  b200_amg amg = nullptr;
+  const int pk = krylov_precond(s, "GMRES", &amg);
+  if (pk < 0) return g_error_flag;
+  b200_gmres_params prm;
+  prm.tol = s->tol; prm.a_tol = s->a_tol; prm.cf_tol = s->cf_tol; prm.max_iter = s->max_iter; prm.min_iter = s->min_iter;
+  prm.k_dim = s->k_dim; prm.rel_change = s->rel_change; prm.skip_real_r_check = s->skip_real_r_check; prm.precond = pk;
+  s->norms.assign((size_t)s->max_iter + 2, 0.0);
+  b200_timer_start(h);
+  const int rc = b200_gmres_solve(h, A->A, amg, &prm, b->d, x->d, &s->num_iterations, &s->rel_res, s->norms.data(), &s->converged);
+  double ms = 0;
+  b200_timer_stop_ms(h, &ms);
+  s->solve_s = ms * 1e-3;
+  if (rc) return err_b200("HYPRE_ParCSRGMRESSolve");
+  if (s->print_level > 1) krylov_print_norms(s, h, b);
+  if (s->num_iterations >= s->max_iter && !s->converged && s->rel_res > s->tol && s->tol > 0) err(HYPRE_ERROR_CONV);   // gmres.c:785-787
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_GMRESSetup(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRGMRESSetup(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+HYPRE_Int HYPRE_GMRESSolve(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRGMRESSolve(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+// ParCSR-typed aliases (parcsr_ls/HYPRE_parcsr_gmres.c:87-220)
+HYPRE_Int HYPRE_ParCSRGMRESSetKDim(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetKDim(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetTol(HYPRE_Solver s, HYPRE_Real v) { return HYPRE_GMRESSetTol(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetAbsoluteTol(HYPRE_Solver s, HYPRE_Real v) { return HYPRE_GMRESSetAbsoluteTol(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetMinIter(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetMinIter(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetMaxIter(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetMaxIter(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetStopCrit(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetStopCrit(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetLogging(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetLogging(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetPrintLevel(HYPRE_Solver s, HYPRE_Int v) { return HYPRE_GMRESSetPrintLevel(s, v); }
+HYPRE_Int HYPRE_ParCSRGMRESSetPrecond(HYPRE_Solver s, HYPRE_PtrToParSolverFcn precond, HYPRE_PtrToParSolverFcn precond_setup, HYPRE_Solver ps) {
+  return HYPRE_GMRESSetPrecond(s, (HYPRE_PtrToSolverFcn)precond, (HYPRE_PtrToSolverFcn)precond_setup, ps);
+}
+HYPRE_Int HYPRE_ParCSRGMRESGetPrecond(HYPRE_Solver s, HYPRE_Solver *p) { return HYPRE_GMRESGetPrecond(s, p); }
+HYPRE_Int HYPRE_ParCSRGMRESGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { return HYPRE_GMRESGetNumIterations(s, n); }
+HYPRE_Int HYPRE_ParCSRGMRESGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { return HYPRE_GMRESGetFinalRelativeResidualNorm(s, r); }
+
+HYPRE_Int HYPRE_ParCSRBiCGSTABCreate(MPI_Comm, HYPRE_Solver *solver) { return krylov_create(solver, KIND_BICGSTAB); }
+HYPRE_Int HYPRE_ParCSRBiCGSTABDestroy(HYPRE_Solver s) {
+  if (!is_bicgstab(s)) return err_arg(1);
+  delete s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BiCGSTABDestroy(HYPRE_Solver s) { return HYPRE_ParCSRBiCGSTABDestroy(s); }
+#define BICG_SET(NAME, TYPE, FIELD) \
+  HYPRE_Int HYPRE_BiCGSTABSet##NAME(HYPRE_Solver s, TYPE v) { if (!is_bicgstab(s)) return err_arg(1); s->FIELD = v; return g_error_flag; } \
+  HYPRE_Int HYPRE_ParCSRBiCGSTABSet##NAME(HYPRE_Solver s, TYPE v) { return HYPRE_BiCGSTABSet##NAME(s, v); }
+BICG_SET(Tol, HYPRE_Real, tol)
+BICG_SET(AbsoluteTol, HYPRE_Real, a_tol)
+BICG_SET(MinIter, HYPRE_Int, min_iter)
+BICG_SET(MaxIter, HYPRE_Int, max_iter)
+BICG_SET(StopCrit, HYPRE_Int, stop_crit)
+BICG_SET(Logging, HYPRE_Int, logging)
+BICG_SET(PrintLevel, HYPRE_Int, print_level)
+#undef BICG_SET
+HYPRE_Int HYPRE_BiCGSTABSetConvergenceFactorTol(HYPRE_Solver s, HYPRE_Real v) { if (!is_bicgstab(s)) return err_arg(1); s->cf_tol = v; return g_error_flag; }
+HYPRE_Int HYPRE_BiCGSTABSetPrecond(HYPRE_Solver s, HYPRE_PtrToSolverFcn precond, HYPRE_PtrToSolverFcn precond_setup, HYPRE_Solver precond_solver) {
+  if (!is_bicgstab(s)) return err_arg(1);
+  s->precond = precond; s->precond_setup = precond_setup; s->precond_solver = precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRBiCGSTABSetPrecond(HYPRE_Solver s, HYPRE_PtrToParSolverFcn precond, HYPRE_PtrToParSolverFcn precond_setup, HYPRE_Solver ps) {
+  return HYPRE_BiCGSTABSetPrecond(s, (HYPRE_PtrToSolverFcn)precond, (HYPRE_PtrToSolverFcn)precond_setup, ps);
+}
+HYPRE_Int HYPRE_BiCGSTABGetPrecond(HYPRE_Solver s, HYPRE_Solver *precond_data) {
+  if (!is_bicgstab(s)) return err_arg(1);
+  *precond_data = s->precond_solver;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_ParCSRBiCGSTABGetPrecond(HYPRE_Solver s, HYPRE_Solver *p) { return HYPRE_BiCGSTABGetPrecond(s, p); }
+HYPRE_Int HYPRE_BiCGSTABGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { if (!is_bicgstab(s)) return err_arg(1); *n = s->num_iterations; return g_error_flag; }
+HYPRE_Int HYPRE_BiCGSTABGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { if (!is_bicgstab(s)) return err_arg(1); *r = s->rel_res; return g_error_flag; }
+HYPRE_Int HYPRE_ParCSRBiCGSTABGetNumIterations(HYPRE_Solver s, HYPRE_Int *n) { return HYPRE_BiCGSTABGetNumIterations(s, n); }
+HYPRE_Int HYPRE_ParCSRBiCGSTABGetFinalRelativeResidualNorm(HYPRE_Solver s, HYPRE_Real *r) { return HYPRE_BiCGSTABGetFinalRelativeResidualNorm(s, r); }
+HYPRE_Int HYPRE_ParCSRBiCGSTABSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_bicgstab(s)) return err_arg(1);
+  return krylov_setup(s, A, b, x);
+}
+HYPRE_Int HYPRE_ParCSRBiCGSTABSolve(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVector b, HYPRE_ParVector x) {
+  if (!is_bicgstab(s)) return err_arg(1);
+  if (!A) return err_arg(2);
+  if (!b || !b->d) return err_arg(3);
+  if (!x || !x->d) return err_arg(4);
+  NEED_HANDLE();
+  b200_amg amg = nullptr;
+  const int pk = krylov_precond(s, "BiCGSTAB", &amg);
+  if (pk < 0) return g_error_flag;
+  b200_bicgstab_params prm;
+  prm.tol = s->tol; prm.a_tol = s->a_tol; prm.cf_tol = s->cf_tol; prm.max_iter = s->max_iter; prm.min_iter = s->min_iter;
+  prm.stop_crit = s->stop_crit; prm.precond = pk;
+  s->norms.assign((size_t)s->max_iter + 2, 0.0);
+  b200_timer_start(h);
+  const int rc = b200_bicgstab_solve(h, A->A, amg, &prm, b->d, x->d, &s->num_iterations, &s->rel_res, s->norms.data(), &s->converged);
+  double ms = 0;
+  b200_timer_stop_ms(h, &ms);
+  s->solve_s = ms * 1e-3;
+  if (rc) return err_b200("HYPRE_ParCSRBiCGSTABSolve");
+  if (s->print_level > 0) krylov_print_norms(s, h, b);
+  if (s->num_iterations >= s->max_iter && !s->converged && s->rel_res > s->tol && s->tol > 0) err(HYPRE_ERROR_CONV);   // bicgstab.c:528
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BiCGSTABSetup(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRBiCGSTABSetup(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+HYPRE_Int HYPRE_BiCGSTABSolve(HYPRE_Solver s, HYPRE_Matrix A, HYPRE_Vector b, HYPRE_Vector x) {
+  return HYPRE_ParCSRBiCGSTABSolve(s, (HYPRE_ParCSRMatrix)A, (HYPRE_ParVector)b, (HYPRE_ParVector)x);
+}
+// times and residual history of the last GMRES / BiCGSTAB solve (same accessors as the PCG ones)
+HYPRE_Int HYPRE_b200_KrylovGetTimes(HYPRE_Solver s, HYPRE_Real *setup_s, HYPRE_Real *solve_s) {
+  if (!is_gmres(s) && !is_bicgstab(s) && !is_pcg(s)) return err_arg(1);
+  if (setup_s) *setup_s = s->setup_s;
+  if (solve_s) *solve_s = s->solve_s;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_b200_KrylovGetResidualNorms(HYPRE_Solver s, HYPRE_Int n, HYPRE_Real *norms) {
+  if (!is_gmres(s) && !is_bicgstab(s) && !is_pcg(s)) return err_arg(1);
   for (int i = 0; i < n && i < (int)s->norms.size(); i++) norms[i] = s->norms[i];
   return g_error_flag;
 }

@@ -130,3 +130,15 @@ int b200_cheby_setup(b200_handle h, b200_csr A, int eig_est, int order, double f
 int b200_cheby_solve(b200_handle h, b200_cheby_s *C, b200_csr As, bool zero, const double *f, double *u);
 int b200_cheby_destroy(b200_handle h, b200_cheby_s *c);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);
+// GMRES / BiCGSTAB written once over these operations (b200_krylov.cu); single GPU there, row-partitioned in b200_dist.cu
+struct b200_krylov_ops {
+  int n = 0, cap = 0;          // owned entries; allocation length of a work vector (n + the ghost tail the operator reads)
+  bool device_mgs = true;      // inner products complete on this device: Gram-Schmidt coefficients never visit the host
+  std::function<int(double, const double *, double, const double *, double *)> matvec;   // y = alpha A x + beta b
+  std::function<int(const double *, double *)> precond;                                  // out = M^{-1} rhs from a zero guess
+  std::function<int(const double *, int, double *)> reduce;      // k device partial sums -> host, summed over the ranks in order
+};
+int b200_gmres_core(b200_handle h, const b200_krylov_ops *ops, const b200_gmres_params *prm, const double *d_b, double *d_x,
+                    int *iters, double *final_rel_res, double *h_norms, int *converged);
+int b200_bicgstab_core(b200_handle h, const b200_krylov_ops *ops, const b200_bicgstab_params *prm, const double *d_b, double *d_x,
+                       int *iters, double *final_rel_res, double *h_norms, int *converged);

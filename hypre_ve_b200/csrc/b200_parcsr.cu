@@ -58,8 +58,7 @@ __device__ inline int global_index(const Grid &g, int ix, int iy, int iz) {
 
 // STENCIL 7: centre, z-, y-, x-, x+, y+, z+ (par_laplace.c:206-300); 27: centre then (dz,dy,dx)
 // lexicographic (par_laplace_27pt.c fill pass).
-template <int STENCIL>
-__device__ inline int stencil_size() { return STENCIL; }
+struct StencilVals { double v[7]; };     // centre, x-, y-, z-, x+, y+, z+ (27-pt: centre, off-centre)
 
 template <int STENCIL>
 __device__ inline void stencil_offset(int k, int *dx, int *dy, int *dz, int *vidx) {
@@ -67,7 +66,7 @@ __device__ inline void stencil_offset(int k, int *dx, int *dy, int *dz, int *vid
     const int ox[7] = {0, 0, 0, -1, 1, 0, 0};
     const int oy[7] = {0, 0, -1, 0, 0, 1, 0};
     const int oz[7] = {0, -1, 0, 0, 0, 0, 1};
-    const int vi[7] = {0, 3, 2, 1, 1, 2, 3};
+    const int vi[7] = {0, 3, 2, 1, 4, 5, 6};      // GenerateDifConv's seven values (par_difconv.c:247-330); the Laplacian passes v[4..6] = v[1..3]
     *dx = ox[k]; *dy = oy[k]; *dz = oz[k]; *vidx = vi[k];
   } else {
     if (k == 0) { *dx = *dy = *dz = 0; *vidx = 0; return; }
@@ -78,7 +77,7 @@ __device__ inline void stencil_offset(int k, int *dx, int *dy, int *dz, int *vid
 }
 
 template <int STENCIL, bool FILL>
-__global__ void gen_kernel(Grid g, double v0, double v1, double v2, double v3, int *diag_i, int *offd_i,
+__global__ void gen_kernel(Grid g, StencilVals sv, int *diag_i, int *offd_i,
                            int *diag_j, double *diag_a, int *offd_gj, double *offd_a) {
   const int nxl = g.x1 - g.x0, nyl = g.y1 - g.y0, nzl = g.z1 - g.z0;
   const long long nloc = (long long)nxl * nyl * nzl;
@@ -89,7 +88,7 @@ __global__ void gen_kernel(Grid g, double v0, double v1, double v2, double v3, i
   int cd = 0, co = 0;
   int pd = 0, po = 0;
   if (FILL) { pd = diag_i[row]; po = offd_i[row]; }
-  const double vals[4] = {v0, v1, v2, v3};
+  const double *vals = sv.v;
   for (int k = 0; k < STENCIL; k++) {
     int dx, dy, dz, vi;
     stencil_offset<STENCIL>(k, &dx, &dy, &dz, &vi);
@@ -115,7 +114,7 @@ __global__ void gen_kernel(Grid g, double v0, double v1, double v2, double v3, i
 
 // merged form for the multi-rank path: local rows, GLOBAL column ids, reference entry order
 template <int STENCIL, bool FILL>
-__global__ void gen_global_kernel(Grid g, double v0, double v1, double v2, double v3, int *A_i, int *A_j, double *A_a) {
+__global__ void gen_global_kernel(Grid g, StencilVals sv, int *A_i, int *A_j, double *A_a) {
   const int nxl = g.x1 - g.x0, nyl = g.y1 - g.y0, nzl = g.z1 - g.z0;
   const long long nloc = (long long)nxl * nyl * nzl;
   long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,7 +123,7 @@ __global__ void gen_global_kernel(Grid g, double v0, double v1, double v2, doubl
   const int ix = g.x0 + lx, iy = g.y0 + ly, iz = g.z0 + lz;
   int cnt = 0;
   const int pos = FILL ? A_i[row] : 0;
-  const double vals[4] = {v0, v1, v2, v3};
+  const double *vals = sv.v;
   for (int k = 0; k < STENCIL; k++) {
     int dx, dy, dz, vi;
     stencil_offset<STENCIL>(k, &dx, &dy, &dz, &vi);
@@ -198,9 +197,10 @@ static int generate_global(b200_handle h, Grid g, const double *vals, b200_csr *
   int *ai = nullptr;
   B200_TRY(b200_dalloc<int>(h, &ai, (size_t)nloc + 1));
   B200_CUDA(cudaMemsetAsync(ai + nloc, 0, sizeof(int), h->stream));
-  const double v0 = vals[0], v1 = vals[1], v2 = STENCIL == 7 ? vals[2] : 0.0, v3 = STENCIL == 7 ? vals[3] : 0.0;
+  StencilVals sv;
+  for (int k = 0; k < 7; k++) sv.v[k] = k < (STENCIL == 7 ? 7 : 2) ? vals[k] : 0.0;
   if (nloc) {
-    gen_global_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, ai, nullptr, nullptr);
+    gen_global_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, ai, nullptr, nullptr);
     B200_LAUNCH_CHECK();
   }
   B200_TRY(b200_exclusive_scan_inplace(h, ai, (size_t)nloc + 1));
@@ -211,7 +211,7 @@ static int generate_global(b200_handle h, Grid g, const double *vals, b200_csr *
   B200_TRY(b200_csr_alloc(h, nloc, g.nx * g.ny * g.nz, nnz, true, &A));
   B200_CUDA(cudaMemcpyAsync(A->i, ai, sizeof(int) * ((size_t)nloc + 1), cudaMemcpyDeviceToDevice, h->stream));
   if (nloc) {
-    gen_global_kernel<STENCIL, true><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, A->i, A->j, A->a);
+    gen_global_kernel<STENCIL, true><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, A->i, A->j, A->a);
     B200_LAUNCH_CHECK();
   }
   B200_TRY(b200_dfree(h, ai));
@@ -249,9 +249,10 @@ static int generate(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, 
   B200_TRY(b200_dalloc<int>(h, &oi, (size_t)nloc + 1));
   B200_CUDA(cudaMemsetAsync(di + nloc, 0, sizeof(int), h->stream));
   B200_CUDA(cudaMemsetAsync(oi + nloc, 0, sizeof(int), h->stream));
-  const double v0 = vals[0], v1 = vals[1], v2 = STENCIL == 7 ? vals[2] : 0.0, v3 = STENCIL == 7 ? vals[3] : 0.0;
+  StencilVals sv;
+  for (int k = 0; k < 7; k++) sv.v[k] = k < (STENCIL == 7 ? 7 : 2) ? vals[k] : 0.0;
   if (nloc) {
-    gen_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, di, oi, nullptr,
+    gen_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, di, oi, nullptr,
                                                                            nullptr, nullptr, nullptr);
     B200_LAUNCH_CHECK();
   }
@@ -272,7 +273,7 @@ static int generate(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, 
   int *ogj = nullptr;
   B200_TRY(b200_dalloc<int>(h, &ogj, (size_t)nnz_o));
   if (nloc) {
-    gen_kernel<STENCIL, true><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, v0, v1, v2, v3, A->diag->i, A->offd->i,
+    gen_kernel<STENCIL, true><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, A->diag->i, A->offd->i,
                                                                           A->diag->j, A->diag->a, ogj, A->offd->a);
     B200_LAUNCH_CHECK();
   }
@@ -295,6 +296,13 @@ static int generate(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, 
 
 extern "C" int b200_generate_laplacian(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q,
                                        int r, const double values[4], b200_parcsr *A) {
+  const double v7[7] = {values[0], values[1], values[2], values[3], values[1], values[2], values[3]};
+  return generate<7>(h, nx, ny, nz, P, Q, R, p, q, r, v7, A);
+}
+// GenerateDifConv (parcsr_ls/par_difconv.c:15-365): the 7-point pattern and entry order of GenerateLaplacian with
+// separate lower (x-,y-,z-) and upper (x+,y+,z+) coefficients -- a nonsymmetric operator.
+extern "C" int b200_generate_difconv(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q,
+                                     int r, const double values[7], b200_parcsr *A) {
   return generate<7>(h, nx, ny, nz, P, Q, R, p, q, r, values, A);
 }
 extern "C" int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q,

@@ -95,6 +95,11 @@ int b200_generate_laplacian(b200_handle h, int nx, int ny, int nz, int P, int Q,
                             int p, int q, int r, const double values[4], b200_parcsr *A);
 int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
                               int p, int q, int r, const double values[2], b200_parcsr *A);
+/* GenerateDifConv (parcsr_ls/par_difconv.c:15-365): same pattern and entry order as the 7-point Laplacian with
+ * seven coefficients values[7] = centre, x-, y-, z-, x+, y+, z+ (ij.c:8270-8420 computes them from -c, -a, -atype);
+ * nonsymmetric unless values[k] == values[k+3]. */
+int b200_generate_difconv(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
+                          int p, int q, int r, const double values[7], b200_parcsr *A);
 
 /* ---- ParCSR (parcsr_mv) -------------------------------------------------------------------- */
 /* single-rank ParCSR from a host CSR (diag block = whole matrix); diagonal entry must be first
@@ -196,6 +201,25 @@ int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, const b200_pcg
 /* x = y ./ diag(A)   HYPRE_ParCSRDiagScale (parcsr_ls/HYPRE_parcsr_pcg.c:228-258) */
 int b200_parcsr_diag_scale(b200_handle h, b200_parcsr A, const double *d_y, double *d_x);
 
+/* ---- GMRES / BiCGSTAB (krylov/gmres.c:226-800, krylov/bicgstab.c:207-530; ij -solver 3 / -solver 9) ----------
+ * The Krylov drivers for nonsymmetric operators (GenerateDifConv) over the same SpMV / BLAS-1 kernels as PCG.
+ * Fields = the hypre_GMRESData / hypre_BiCGSTABData members that matter here (gmres.h:84-111, bicgstab.h);
+ * precond 0 none, 1 BoomerAMG (one cycle from a zero guess, right preconditioning), 2 HYPRE_ParCSRDiagScale.
+ * rel_change and cf_tol > 0 are rejected.  h_norms (may be NULL) receives the residual-norm history norms[0..iters]
+ * (max_iter + 1 doubles); *converged mirrors the `converged` member. */
+typedef struct {
+  double tol, a_tol, cf_tol;
+  int max_iter, min_iter, k_dim, rel_change, skip_real_r_check, precond;
+} b200_gmres_params;
+int b200_gmres_solve(b200_handle h, b200_parcsr A, b200_amg amg, const b200_gmres_params *params, const double *d_b,
+                     double *d_x, int *iters, double *final_rel_res, double *h_norms, int *converged);
+typedef struct {
+  double tol, a_tol, cf_tol;
+  int max_iter, min_iter, stop_crit, precond;
+} b200_bicgstab_params;
+int b200_bicgstab_solve(b200_handle h, b200_parcsr A, b200_amg amg, const b200_bicgstab_params *params, const double *d_b,
+                        double *d_x, int *iters, double *final_rel_res, double *h_norms, int *converged);
+
 /* ---- multi-GPU: row-partitioned ParCSR over NVLink ---------------------------------
  * One process per GPU.  Rows are partitioned contiguously like hypre's ParCSR layout
  * (par_csr_matrix.h:27-95); each rank stores its rows as ONE CSR whose columns are the owned
@@ -218,6 +242,9 @@ int b200_comm_size(b200_comm c);
 /* GenerateLaplacian / GenerateLaplacian27pt on a P x Q x R process grid, rank -> (p,q,r) as ij.c:7785-7787 */
 int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
                                  int stencil, const double *values, b200_dist_matrix *A);
+/* GenerateDifConv on the process grid (par_difconv.c:15): values[7] = centre, x-, y-, z-, x+, y+, z+ */
+int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
+                               const double values[7], b200_dist_matrix *A);
 int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix A);
 int b200_dist_matrix_info(b200_dist_matrix A, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
                           int *n_ghost, int *first_col, int *global_cols);

@@ -34,7 +34,8 @@ static csr_t csr_new(int n, int m, int nnz, int with_data)
 }
 static void csr_free(csr_t *A) { free(A->i); free(A->j); free(A->a); A->i = A->j = NULL; A->a = NULL; }
 
-/* ---- generators: parcsr_ls/par_laplace.c:124-300 (7-pt: centre, z-,y-,x-,x+,y+,z+) and
+/* ---- generators: parcsr_ls/par_laplace.c:124-300 and par_difconv.c:247-330 (7-pt: centre, z-,y-,x-,x+,y+,z+; v = centre,
+ *      x-, y-, z-, x+, y+, z+ -- the Laplacian passes v[4..6] = v[1..3]) and
  *      parcsr_ls/par_laplace_27pt.c fill pass (centre, then (dz,dy,dx) lexicographic), 1 rank ---- */
 static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
 {
@@ -53,7 +54,7 @@ static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
             if (!pt27)
             {
                static const int ox[7] = {0, 0, 0, -1, 1, 0, 0}, oy[7] = {0, 0, -1, 0, 0, 1, 0}, oz[7] = {0, -1, 0, 0, 0, 0, 1};
-               static const int vi[7] = {0, 3, 2, 1, 1, 2, 3};
+               static const int vi[7] = {0, 3, 2, 1, 4, 5, 6};   /* par_difconv.c:247-330: lower and upper coefficients separate */
                dx = ox[k]; dy = oy[k]; dz = oz[k]; val = v[vi[k]];
             }
             else
@@ -860,6 +861,168 @@ static void cycle(amg_t *g, const double *f, double *u)
 }
 
 
+
+/* ---- GMRES(k) with right preconditioning: krylov/gmres.c:226-800 (rel_change 0, cf_tol 0, min_iter 0,
+ *      skip_real_r_check 0); M^{-1} = one cycle from a zero guess.  Returns the iteration count; *rnorm = last r_norm. ---- */
+static void axpy(int n, double a, const double *x, double *y) { int i; for (i = 0; i < n; i++) y[i] += a * x[i]; }   /* vector.c:451-490 */
+static void scal(int n, double a, double *y) { int i; for (i = 0; i < n; i++) y[i] *= a; }                          /* vector.c:394-430 */
+static int gmres(amg_t *g, const csr_t *A, const double *b, double *x, int k_dim, double r_tol, int max_iter, double *norms,
+                 double *rel_out)
+{
+   int n = A->n, i = 0, j, k, iter = 0;
+   double **p = (double **) xmalloc(sizeof(double *) * (k_dim + 1)), **hh = (double **) xmalloc(sizeof(double *) * (k_dim + 1));
+   double *r = (double *) xcalloc(n, sizeof(double)), *w = (double *) xcalloc(n, sizeof(double));
+   double *rs = (double *) xcalloc(k_dim + 1, sizeof(double)), *c = (double *) xcalloc(k_dim, sizeof(double)), *sn = (double *) xcalloc(k_dim, sizeof(double));
+   double epsmac = 1.e-16, t, gamma, r_norm, b_norm, den_norm, epsilon, real_r_norm_old, real_r_norm_new;
+   for (j = 0; j <= k_dim; j++) { p[j] = (double *) xcalloc(n, sizeof(double)); hh[j] = (double *) xcalloc(k_dim, sizeof(double)); }
+   memcpy(p[0], b, sizeof(double) * n);
+   matvec(-1.0, A, x, 1.0, p[0], p[0]);                                   /* :316-319 */
+   b_norm = sqrt(dot(n, b, b)); real_r_norm_old = b_norm;
+   r_norm = sqrt(dot(n, p[0], p[0]));
+   norms[0] = r_norm;
+   den_norm = b_norm > 0.0 ? b_norm : r_norm;                             /* :388-394 */
+   epsilon = r_tol * den_norm;                                            /* :403, a_tol 0 */
+   while (iter < max_iter)
+   {
+      rs[0] = r_norm;
+      if (r_norm == 0.0) break;                                           /* :427-439 */
+      if (r_norm <= epsilon)                                              /* :443-462 */
+      {
+         memcpy(r, b, sizeof(double) * n);
+         matvec(-1.0, A, x, 1.0, r, r);
+         r_norm = sqrt(dot(n, r, r));
+         if (r_norm <= epsilon) break;
+      }
+      t = 1.0 / r_norm;
+      scal(n, t, p[0]);
+      i = 0;
+      while (i < k_dim && iter < max_iter)                                /* :469 restart cycle */
+      {
+         i++; iter++;
+         memset(r, 0, sizeof(double) * n);
+         cycle(g, p[i - 1], r);
+         matvec(1.0, A, r, 0.0, p[i], p[i]);
+         for (j = 0; j < i; j++)                                          /* modified Gram-Schmidt :476-479 */
+         {
+            hh[j][i - 1] = dot(n, p[j], p[i]);
+            axpy(n, -hh[j][i - 1], p[j], p[i]);
+         }
+         t = sqrt(dot(n, p[i], p[i]));
+         hh[i][i - 1] = t;
+         if (t != 0.0) { t = 1.0 / t; scal(n, t, p[i]); }
+         for (j = 1; j < i; j++)                                          /* :488-492 */
+         {
+            t = hh[j - 1][i - 1];
+            hh[j - 1][i - 1] = sn[j - 1] * hh[j][i - 1] + c[j - 1] * t;
+            hh[j][i - 1] = -sn[j - 1] * t + c[j - 1] * hh[j][i - 1];
+         }
+         t = hh[i][i - 1] * hh[i][i - 1];
+         t += hh[i - 1][i - 1] * hh[i - 1][i - 1];
+         gamma = sqrt(t);
+         if (gamma == 0.0) gamma = epsmac;
+         c[i - 1] = hh[i - 1][i - 1] / gamma;
+         sn[i - 1] = hh[i][i - 1] / gamma;
+         rs[i] = -hh[i][i - 1] * rs[i - 1];
+         rs[i] /= gamma;
+         rs[i - 1] = c[i - 1] * rs[i - 1];
+         hh[i - 1][i - 1] = sn[i - 1] * hh[i][i - 1] + c[i - 1] * hh[i - 1][i - 1];
+         r_norm = fabs(rs[i]);
+         norms[iter] = r_norm;
+         if (r_norm <= epsilon) break;                                    /* :541, no relative change */
+      }
+      rs[i - 1] = rs[i - 1] / hh[i - 1][i - 1];                           /* :641-649 triangular solve */
+      for (k = i - 2; k >= 0; k--)
+      {
+         t = 0.0;
+         for (j = k + 1; j < i; j++) t -= hh[k][j] * rs[j];
+         t += rs[k];
+         rs[k] = t / hh[k][k];
+      }
+      memcpy(w, p[i - 1], sizeof(double) * n);                            /* :651-654 */
+      scal(n, rs[i - 1], w);
+      for (j = i - 2; j >= 0; j--) axpy(n, rs[j], p[j], w);
+      memset(r, 0, sizeof(double) * n);
+      cycle(g, w, r);
+      axpy(n, 1.0, r, x);
+      if (r_norm <= epsilon)                                              /* :664-752 check the true residual */
+      {
+         memcpy(r, b, sizeof(double) * n);
+         matvec(-1.0, A, x, 1.0, r, r);
+         real_r_norm_new = r_norm = sqrt(dot(n, r, r));
+         if (r_norm <= epsilon) break;
+         if (real_r_norm_new >= real_r_norm_old) break;
+         memcpy(p[0], r, sizeof(double) * n);
+         i = 0;
+         real_r_norm_old = real_r_norm_new;
+      }
+      for (j = i; j > 0; j--)                                             /* :755-768 residual vector for the restart */
+      {
+         rs[j - 1] = -sn[j - 1] * rs[j];
+         rs[j] = c[j - 1] * rs[j];
+      }
+      if (i) axpy(n, rs[i] - 1.0, p[i], p[i]);
+      for (j = i - 1; j > 0; j--) axpy(n, rs[j], p[j], p[i]);
+      if (i) { axpy(n, rs[0] - 1.0, p[0], p[0]); axpy(n, 1.0, p[i], p[0]); }
+   }
+   *rel_out = b_norm > 0.0 ? r_norm / b_norm : r_norm;                    /* :777-783 */
+   return iter;
+}
+
+/* ---- BiCGSTAB: krylov/bicgstab.c:207-530 (stop_crit 0, a_tol 0, cf_tol 0, min_iter 0) ---- */
+static int bicgstab(amg_t *g, const csr_t *A, const double *b, double *x, double r_tol, int max_iter, double *norms, double *rel_out)
+{
+   int n = A->n, iter = 0;
+   double *r = (double *) xcalloc(n, sizeof(double)), *r0 = (double *) xcalloc(n, sizeof(double)), *s = (double *) xcalloc(n, sizeof(double));
+   double *v = (double *) xcalloc(n, sizeof(double)), *p = (double *) xcalloc(n, sizeof(double)), *q = (double *) xcalloc(n, sizeof(double));
+   double alpha, beta, gamma, epsilon, temp, res, r_norm, b_norm, den_norm, gamma_numer, gamma_denom, epsmac = 2.2250738585072014e-308;
+   memcpy(r0, b, sizeof(double) * n);
+   matvec(-1.0, A, x, 1.0, r0, r0);
+   memcpy(r, r0, sizeof(double) * n);
+   memcpy(p, r0, sizeof(double) * n);
+   b_norm = sqrt(dot(n, b, b));
+   res = dot(n, r0, r0);
+   r_norm = sqrt(res);
+   norms[0] = r_norm;
+   den_norm = b_norm > 0.0 ? b_norm : r_norm;
+   epsilon = r_tol * den_norm;
+   *rel_out = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   if (r_norm == 0.0 || r_norm <= epsilon) return 0;                     /* :396-413 */
+   while (iter < max_iter)
+   {
+      iter++;
+      memset(v, 0, sizeof(double) * n); cycle(g, p, v);
+      matvec(1.0, A, v, 0.0, q, q);
+      temp = dot(n, r0, q);
+      if (fabs(temp) >= epsmac) alpha = res / temp; else { fprintf(stderr, "BiCGSTAB broke down\n"); break; }
+      axpy(n, alpha, v, x);
+      axpy(n, -alpha, q, r);
+      memset(v, 0, sizeof(double) * n); cycle(g, r, v);
+      matvec(1.0, A, v, 0.0, s, s);
+      gamma_numer = dot(n, r, s);
+      gamma_denom = dot(n, s, s);
+      gamma = (gamma_numer == 0.0 && gamma_denom == 0.0) ? 0.0 : gamma_numer / gamma_denom;
+      axpy(n, gamma, v, x);
+      axpy(n, -gamma, s, r);
+      r_norm = sqrt(dot(n, r, r));
+      norms[iter] = r_norm;
+      if (r_norm <= epsilon)                                              /* :464-481 */
+      {
+         memcpy(r, b, sizeof(double) * n);
+         matvec(-1.0, A, x, 1.0, r, r);
+         r_norm = sqrt(dot(n, r, r));
+         if (r_norm <= epsilon) break;
+      }
+      if (fabs(res) >= epsmac) beta = 1.0 / res; else { fprintf(stderr, "BiCGSTAB broke down\n"); break; }
+      res = dot(n, r0, r);
+      beta *= res;
+      axpy(n, -gamma, q, p);
+      if (fabs(gamma) >= epsmac) scal(n, beta * alpha / gamma, p); else { fprintf(stderr, "BiCGSTAB broke down\n"); break; }
+      axpy(n, 1.0, r, p);
+   }
+   *rel_out = b_norm > 0.0 ? r_norm / b_norm : r_norm;
+   return iter;
+}
+
 /* -perturb SEED: a non-Laplacian SPD test operator on the stencil's pattern -- symmetric pseudo-random off-diagonal
  * magnitudes in [0.05, 1.5] (weak and strong connections), one in sixteen with a POSITIVE sign, strictly dominant
  * diagonal.  The same function lives in oracle/ref_dump.c and oracle/amg_oracle.c (test infrastructure). */
@@ -899,18 +1062,60 @@ static void put_csr(const char *pre, int l, const csr_t *M, int with_data)
    sprintf(nm, "%s%d.j", pre, l); put(nm, 0, M->j, M->i[M->n]);
    if (with_data) { sprintf(nm, "%s%d.a", pre, l); put(nm, 1, M->a, M->i[M->n]); }
 }
+
+/* values[7] of the convection-diffusion stencil -cx Dxx - cy Dyy - cz Dzz + ax Dx + ay Dy + az Dz, computed as the
+ * reference driver does (src/test/ij.c:8266-8409, BuildParDifConv; same helper as oracle/ref_dump.c): centre, x-, y-, z-, x+, y+, z+;
+ * atype 0 forward, 1 backward, 3 upwind, else centred differences for the convection term. */
+static int sign_double(double a) { return (0.0 < a) - (0.0 > a); }
+static void difconv_values(int nx, int ny, int nz, const double *c, const double *a, int atype, double *v)
+{
+   int n[3] = { nx, ny, nz }, d;
+   v[0] = 0.;
+   for (d = 0; d < 3; d++)
+   {
+      double hin = 1. / (double) (n[d] + 1);
+      int back = atype == 1 || (atype == 3 && sign_double(c[d]) * sign_double(a[d]) == 1);
+      if (atype == 0 || atype == 1 || atype == 3)
+      {
+         if (back)
+         {
+            v[1 + d] = -c[d] / (hin * hin) - a[d] / hin;
+            v[4 + d] = -c[d] / (hin * hin);
+            if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) + 1. * a[d] / hin;
+         }
+         else
+         {
+            v[1 + d] = -c[d] / (hin * hin);
+            v[4 + d] = -c[d] / (hin * hin) + a[d] / hin;
+            if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) - 1. * a[d] / hin;
+         }
+      }
+      else
+      {
+         v[1 + d] = -c[d] / (hin * hin) - a[d] / (2. * hin);
+         v[4 + d] = -c[d] / (hin * hin) + a[d] / (2. * hin);
+         if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin);
+      }
+   }
+}
 static double now(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 int main(int argc, char **argv)
 {
    int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1, perturb = 0;
-   double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
+   double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0, ax = 1, ay = 1, az = 1;
+   int difconv = 0, atype = 0, solver_id = 1, k_dim = 5;
    const char *ofile = NULL;
    for (i = 1; i < argc; i++)
    {
       if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
       else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
       else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);     /* 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB */
+      else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-difconv")) difconv = 1;
+      else if (!strcmp(argv[i], "-a")) { ax = atof(argv[++i]); ay = atof(argv[++i]); az = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-atype")) atype = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-Pmx")) Pmx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-th")) th = atof(argv[++i]);
       else if (!strcmp(argv[i], "-tol")) tol = atof(argv[++i]);
@@ -933,9 +1138,10 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-fmg")) g_fcycle = 1;                                   /* ij.c:1495-1499 */
       else { fprintf(stderr, "unknown flag %s\n", argv[i]); return 2; }
    }
-   double v[4];
+   double v[7];
    if (pt27) { v[0] = 26.0; if (nx == 1 || ny == 1 || nz == 1) v[0] = 8.0; if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) v[0] = 2.0; v[1] = -1.; }
-   else { v[1] = -cx; v[2] = -cy; v[3] = -cz; v[0] = 0.; if (nx > 1) v[0] += 2.0 * cx; if (ny > 1) v[0] += 2.0 * cy; if (nz > 1) v[0] += 2.0 * cz; }
+   else { v[1] = -cx; v[2] = -cy; v[3] = -cz; v[0] = 0.; if (nx > 1) v[0] += 2.0 * cx; if (ny > 1) v[0] += 2.0 * cy; if (nz > 1) v[0] += 2.0 * cz; v[4] = v[1]; v[5] = v[2]; v[6] = v[3]; }
+   if (difconv && !pt27) { double c[3] = { cx, cy, cz }, a[3] = { ax, ay, az }; difconv_values(nx, ny, nz, c, a, atype, v); }
    csr_t A = gen_laplace(nx, ny, nz, pt27, v);
    int N = A.n;
    if (perturb) perturb_operator(N, A.i, A.j, A.a, (unsigned) perturb);
@@ -959,8 +1165,10 @@ int main(int argc, char **argv)
    double *p = (double *) xcalloc(N, sizeof(double)), *s = (double *) xcalloc(N, sizeof(double)), *r = (double *) xmalloc(sizeof(double) * N);
    double *norms = (double *) xcalloc(max_iter + 2, sizeof(double));
    t0 = now();
-   double bi_prod = dot(N, b, b), eps = tol * tol, i_prod = 0, gamma, gamma_old;
+   double bi_prod = dot(N, b, b), eps = tol * tol, i_prod = 0, gamma, gamma_old, krylov_rel = 0;
    int it = 0;
+   if (solver_id == 3) { it = gmres(&g, &A, b, x, k_dim, tol, max_iter, norms, &krylov_rel); goto solved; }
+   if (solver_id == 9) { it = bicgstab(&g, &A, b, x, tol, max_iter, norms, &krylov_rel); goto solved; }
    memcpy(r, b, sizeof(double) * N);
    matvec(-1.0, &A, x, 1.0, r, r);
    memset(p, 0, sizeof(double) * N); cycle(&g, r, p);
@@ -985,7 +1193,8 @@ int main(int argc, char **argv)
       for (i = 0; i < N; i++) p[i] *= beta;
       for (i = 0; i < N; i++) p[i] += 1.0 * s[i];
    }
-   double t_solve = now() - t0, relres = sqrt(i_prod / bi_prod);
+solved: ;
+   double t_solve = now() - t0, relres = solver_id == 1 ? sqrt(i_prod / bi_prod) : krylov_rel;
    printf("amg_oracle: n=%d %d %d rows=%d nnz=%d\n", nx, ny, nz, N, A.nnz);
    printf("amg_oracle: levels=%d iterations=%d relres=%.6e setup_s=%.4f solve_s=%.4f\n", g.nl, it, relres, t_setup, t_solve);
    for (i = 0; i < g.nl; i++) printf("amg_oracle: level %d rows=%d nnz=%d\n", i, g.A[i].n, g.A[i].i[g.A[i].n]);

@@ -16,7 +16,8 @@
  * Flags follow ij.c's spelling: -n nx ny nz, -27pt, -c cx cy cz, -pmis, -rlx T,
  * -Pmx K, -agg_nl L, -mod_rap2 B, -keepT B, -th theta, -tol t, -interptype I,
  * -mxrs r (max_row_sum), -o FILE, -matvec K (time K SpMVs, ij -solver -1 analogue),
- * -nodump (timing only), -ns / -ns_coarse / -mu / -fmg (cycle shape), -perturb SEED (non-Laplacian values, see below).
+ * -solver 1|3|9 (AMG-PCG, AMG-GMRES with -k K, AMG-BiCGSTAB: ij.c:5298-5330, :6364-6380),
+ * -difconv [-a ax ay az] [-atype T] (GenerateDifConv, nonsymmetric), -nodump (timing only), -ns / -ns_coarse / -mu / -fmg (cycle shape), -perturb SEED (non-Laplacian values, see below).
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -75,6 +76,42 @@ static void perturb_operator(int n, const int *I, const int *J, double *a, unsig
       a[I[i]] = sum + 0.05;
    }
 }
+
+/* values[7] of the convection-diffusion stencil -cx Dxx - cy Dyy - cz Dzz + ax Dx + ay Dy + az Dz, computed as the
+ * reference driver does (src/test/ij.c:8266-8409, BuildParDifConv): centre, x-, y-, z-, x+, y+, z+;
+ * atype 0 forward, 1 backward, 3 upwind, else centred differences for the convection term. */
+static int sign_double(double a) { return (0.0 < a) - (0.0 > a); }
+static void difconv_values(int nx, int ny, int nz, const double *c, const double *a, int atype, double *v)
+{
+   int n[3] = { nx, ny, nz }, d;
+   v[0] = 0.;
+   for (d = 0; d < 3; d++)
+   {
+      double hin = 1. / (double) (n[d] + 1);
+      int back = atype == 1 || (atype == 3 && sign_double(c[d]) * sign_double(a[d]) == 1);
+      if (atype == 0 || atype == 1 || atype == 3)
+      {
+         if (back)
+         {
+            v[1 + d] = -c[d] / (hin * hin) - a[d] / hin;
+            v[4 + d] = -c[d] / (hin * hin);
+            if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) + 1. * a[d] / hin;
+         }
+         else
+         {
+            v[1 + d] = -c[d] / (hin * hin);
+            v[4 + d] = -c[d] / (hin * hin) + a[d] / hin;
+            if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin) - 1. * a[d] / hin;
+         }
+      }
+      else
+      {
+         v[1 + d] = -c[d] / (hin * hin) - a[d] / (2. * hin);
+         v[4 + d] = -c[d] / (hin * hin) + a[d] / (2. * hin);
+         if (n[d] > 1) v[0] += 2.0 * c[d] / (hin * hin);
+      }
+   }
+}
 static double now(void)
 {
    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -87,6 +124,9 @@ int main(int argc, char **argv)
    int mod_rap2 = 0, keepT = 0, interp_type = 6, nodump = 0, matvec = 0, max_iter = 100;
    int ns = 1, ns_coarse = 1, mu = 1, fmg = 0, perturb = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
+   int difconv = 0, atype = 0;                                   /* ij.c: -difconv, -a ax ay az, -atype */
+   int solver_id = 1, k_dim = 5;                                 /* ij.c: -solver 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB; -k */
+   double ax = 1, ay = 1, az = 1;
    const char *ofile = NULL;
    int i;
    for (i = 1; i < argc; i++)
@@ -94,6 +134,11 @@ int main(int argc, char **argv)
       if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
       else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
       else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-difconv")) difconv = 1;
+      else if (!strcmp(argv[i], "-a")) { ax = atof(argv[++i]); ay = atof(argv[++i]); az = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-atype")) atype = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-pmis")) pmis = 1;
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-Pmx")) Pmx = atoi(argv[++i]);
@@ -130,6 +175,12 @@ int main(int argc, char **argv)
       if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
       values[1] = -1.;
       A = (HYPRE_ParCSRMatrix) GenerateLaplacian27pt(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+   }
+   else if (difconv)
+   {
+      HYPRE_Real values[7], c[3] = { cx, cy, cz }, a[3] = { ax, ay, az };
+      difconv_values(nx, ny, nz, c, a, atype, values);
+      A = (HYPRE_ParCSRMatrix) GenerateDifConv(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
    }
    else
    {
@@ -172,7 +223,28 @@ int main(int argc, char **argv)
       return 0;
    }
 
+   if (solver_id != 1 && solver_id != 3 && solver_id != 9) { fprintf(stderr, "-solver must be 1, 3 or 9\n"); return 2; }
    HYPRE_Solver pcg, amg;
+   if (solver_id == 3)
+   {  /* ij.c:5305-5312; print level 1 because gmres.c:513 records norms[iter] only then (it prints nothing else) */
+      HYPRE_ParCSRGMRESCreate(hypre_MPI_COMM_WORLD, &pcg);
+      HYPRE_GMRESSetKDim(pcg, k_dim);
+      HYPRE_GMRESSetTol(pcg, tol);
+      HYPRE_GMRESSetAbsoluteTol(pcg, 0.);
+      HYPRE_GMRESSetLogging(pcg, 1);
+      HYPRE_GMRESSetPrintLevel(pcg, 1);
+      HYPRE_GMRESSetRelChange(pcg, 0);
+   }
+   else if (solver_id == 9)
+   {  /* ij.c:6364-6369 */
+      HYPRE_ParCSRBiCGSTABCreate(hypre_MPI_COMM_WORLD, &pcg);
+      HYPRE_BiCGSTABSetTol(pcg, tol);
+      HYPRE_BiCGSTABSetAbsoluteTol(pcg, 0.);
+      HYPRE_BiCGSTABSetLogging(pcg, 1);
+      HYPRE_BiCGSTABSetPrintLevel(pcg, 0);
+   }
+   else
+   {
    HYPRE_ParCSRPCGCreate(hypre_MPI_COMM_WORLD, &pcg);
    HYPRE_PCGSetMaxIter(pcg, 1000);
    HYPRE_PCGSetTol(pcg, tol);
@@ -180,6 +252,7 @@ int main(int argc, char **argv)
    HYPRE_PCGSetRelChange(pcg, 0);
    HYPRE_PCGSetPrintLevel(pcg, 0);
    HYPRE_PCGSetLogging(pcg, 1);
+   }
 
    HYPRE_BoomerAMGCreate(&amg);
    HYPRE_BoomerAMGSetInterpType(amg, interp_type);
@@ -207,20 +280,57 @@ int main(int argc, char **argv)
    HYPRE_BoomerAMGSetRAP2(amg, 0);
    HYPRE_BoomerAMGSetModuleRAP2(amg, mod_rap2);
    HYPRE_BoomerAMGSetKeepTranspose(amg, keepT);
+   double t_setup, t_solve;
+   HYPRE_Int its; HYPRE_Real relres;
+   const double *norms;
+   if (solver_id == 3)
+   {
+      HYPRE_GMRESSetMaxIter(pcg, max_iter);
+      HYPRE_GMRESSetPrecond(pcg, (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSolve,
+                            (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSetup, amg);
+      t0 = now();
+      HYPRE_GMRESSetup(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+      t_setup = now() - t0;
+      t0 = now();
+      HYPRE_GMRESSolve(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+      t_solve = now() - t0;
+      HYPRE_GMRESGetNumIterations(pcg, &its);
+      HYPRE_GMRESGetFinalRelativeResidualNorm(pcg, &relres);
+      norms = ((hypre_GMRESData *) pcg)->norms;
+   }
+   else if (solver_id == 9)
+   {
+      HYPRE_BiCGSTABSetMaxIter(pcg, max_iter);
+      HYPRE_BiCGSTABSetPrecond(pcg, (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSolve,
+                               (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSetup, amg);
+      t0 = now();
+      HYPRE_BiCGSTABSetup(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+      t_setup = now() - t0;
+      t0 = now();
+      HYPRE_BiCGSTABSolve(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
+      t_solve = now() - t0;
+      HYPRE_BiCGSTABGetNumIterations(pcg, &its);
+      HYPRE_BiCGSTABGetFinalRelativeResidualNorm(pcg, &relres);
+      norms = ((hypre_BiCGSTABData *) pcg)->norms;
+   }
+   else
+   {
    HYPRE_PCGSetMaxIter(pcg, max_iter);
    HYPRE_PCGSetPrecond(pcg, (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSolve,
                        (HYPRE_PtrToSolverFcn) HYPRE_BoomerAMGSetup, amg);
 
    t0 = now();
    HYPRE_PCGSetup(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
-   double t_setup = now() - t0;
+   t_setup = now() - t0;
    t0 = now();
    HYPRE_PCGSolve(pcg, (HYPRE_Matrix) A, (HYPRE_Vector) b, (HYPRE_Vector) x);
-   double t_solve = now() - t0;
+   t_solve = now() - t0;
 
-   HYPRE_Int its; HYPRE_Real relres;
    HYPRE_PCGGetNumIterations(pcg, &its);
    HYPRE_PCGGetFinalRelativeResidualNorm(pcg, &relres);
+   norms = ((hypre_PCGData *) pcg)->norms;      /* residual history (pcg.c:597-600 norms[]) */
+   }
+   HYPRE_ClearAllErrors();       /* a run that stops at max_iter sets HYPRE_ERROR_CONV; the dump is still wanted */
 
    hypre_ParAMGData *ad = (hypre_ParAMGData *) amg;
    int nl = hypre_ParAMGDataNumLevels(ad);
@@ -238,9 +348,7 @@ int main(int argc, char **argv)
       int hdr[8] = { nx, ny, nz, nl, (int) its, pt27, Pmx, rlx };
       put("hdr", 0, hdr, 8);
       put("relres", 1, &relres, 1);
-      /* residual history (pcg.c:597-600 norms[]) */
-      hypre_PCGData *pd = (hypre_PCGData *) pcg;
-      put("norms", 1, pd->norms, its + 1);
+      put("norms", 1, norms, its + 1);
       put("x", 1, hypre_VectorData(hypre_ParVectorLocalVector(x)), N);
       for (i = 0; i < nl; i++)
       {

@@ -28,6 +28,14 @@ MORE = {
     "lap7_11_fmg_gs1314_coarse2.bin": (["-n", "11", "11", "11", "-pmis", "-fmg", "-ns_coarse", "2"], 1),              # F-cycle, GS
     "perturbed7_11_rlx18.bin": (["-n", "11", "11", "11", "-perturb", "1", "-pmis", "-rlx", "18"], 1),                 # non-Laplacian SPD
     "perturbed27_8_agg1_gs.bin": (["-n", "8", "8", "8", "-27pt", "-perturb", "7", "-pmis", "-agg_nl", "1"], 1),
+    # nonsymmetric convection-diffusion (GenerateDifConv) and the Krylov drivers for it: AMG-PCG, AMG-GMRES(5), GMRES(3)
+    # restarted on upwind convection, AMG-BiCGSTAB
+    "difconv_11_pcg_rlx18.bin": (["-n", "11", "11", "11", "-difconv", "-pmis", "-rlx", "18"], 1),
+    "difconv_11_gmres_rlx18.bin": (["-n", "11", "11", "11", "-difconv", "-pmis", "-rlx", "18", "-solver", "3"], 1),
+    "difconv_13x11x9_upwind_gmres3_agg1.bin": (["-n", "13", "11", "9", "-difconv", "-a", "3", "-2", "1", "-atype", "3", "-pmis",
+                                                 "-rlx", "18", "-solver", "3", "-k", "3", "-agg_nl", "1"], 1),
+    "difconv_11_bicgstab_gs.bin": (["-n", "11", "11", "11", "-difconv", "-a", "2", "1", "0", "-atype", "1", "-pmis", "-solver", "9"], 1),
+    "lap7_11_gmres_gs1314.bin": (["-n", "11", "11", "11", "-pmis", "-solver", "3"], 1),
 }
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="1")

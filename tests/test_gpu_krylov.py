@@ -1,0 +1,269 @@
+"""GPU parity tests for the nonsymmetric side of the path:
+GenerateDifConv (parcsr_ls/par_difconv.c) on the device, the BoomerAMG hierarchy of that nonsymmetric operator, and the
+Krylov drivers for it -- restarted GMRES (krylov/gmres.c) and BiCGSTAB (krylov/bicgstab.c) preconditioned by one AMG
+cycle, by diagonal scaling, or not at all.
+
+Checker = the reference's own CPU build (oracle/_ref/ref_dump and the unmodified driver oracle/_ref/ij), run live on
+the same flags, plus the committed golden dumps.  Bars: generator output, CF / P / A_l bit-identical (np.array_equal,
+values included); iteration counts equal; residual histories within 1e-10 relative; solution within 1e-9."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import refio
+
+pytestmark = pytest.mark.gpu
+REF_IJ = os.path.join(refio.ROOT, "oracle", "_ref", "ij")
+
+
+def nlev(d):
+    return int(d["hdr"][3])
+
+
+def difconv_kw(args):
+    """ref_dump / ij flags -> keyword arguments of hb.ParCsr.difconv"""
+    kw = {}
+    if "-a" in args:
+        k = args.index("-a")
+        kw["a"] = tuple(float(v) for v in args[k + 1:k + 4])
+    if "-c" in args:
+        k = args.index("-c")
+        kw["c"] = tuple(float(v) for v in args[k + 1:k + 4])
+    if "-atype" in args:
+        kw["atype"] = int(args[args.index("-atype") + 1])
+    return kw
+
+
+@pytest.mark.parametrize("args", [
+    ["-n", 9, 8, 7],                                                       # forward differences, a = (1,1,1)
+    ["-n", 9, 8, 7, "-a", 3, -2, 1, "-atype", 3],                          # upwind: backward in x and z, forward in y
+    ["-n", 6, 11, 5, "-a", 2, 1, 0, "-atype", 1, "-c", 1, 2, 0.5],         # backward differences, anisotropic diffusion
+    ["-n", 7, 1, 12, "-atype", 2],                                         # centred differences, a 2-D slab (ny = 1)
+    ["-n", 1, 1, 17, "-a", 0, 0, 5],                                       # a line
+    ["-n", 5, 5, 5, "-a", 0, 0, 0],                                        # no convection: symmetric
+])
+def test_difconv_generator_equals_the_reference(handle, args):
+    """b200_generate_difconv: row pointers, columns (entry order centre, z-, y-, x-, x+, y+, z+) and values
+    bit-identical to GenerateDifConv fed with the driver's seven coefficients (ij.c:8266-8409)"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-difconv", "-pmis", "-rlx", 18])
+    ri, rj, ra, _ = refio.csr(d, "A", 0)
+    nx, ny, nz = args[1:4]
+    A = hb.ParCsr.difconv(handle, nx, ny, nz, **difconv_kw(args))
+    i, j, a = A.diag.download()
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra)
+    A.destroy()
+
+
+def check_hierarchy(amg, d):
+    assert amg.num_levels == nlev(d)
+    for l in range(nlev(d)):
+        i, j, a = amg.level_A(l).download()
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), ("A", l)
+        if l < nlev(d) - 1:
+            assert np.array_equal(amg.level_CF(l), d["CF%d" % l]), ("CF", l)
+            i, j, a = amg.level_P(l).download()
+            pi, pj, pa, _ = refio.csr(d, "P", l)
+            assert np.array_equal(i, pi) and np.array_equal(j, pj) and np.array_equal(a, pa), ("P", l)
+
+
+def solve_with(handle, solver, A, amg, n, k_dim=5, max_iter=100):
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    if solver == 1:
+        its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=max_iter)
+    elif solver == 3:
+        its, rel, norms, _ = handle.gmres(A, amg, b, x, tol=1e-8, max_iter=max_iter, k_dim=k_dim)
+    else:
+        its, rel, norms, _ = handle.bicgstab(A, amg, b, x, tol=1e-8, max_iter=max_iter)
+    return its, rel, norms, x.numpy()
+
+
+def check_solve(d, its, rel, norms, x):
+    assert its == int(d["hdr"][4]), (its, int(d["hdr"][4]))
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    # GMRES / BiCGSTAB report the TRUE residual b - A x of the last iterate: its rounding floor (eps * |A| |x| / |b|, about
+    # 1e-14 here) is visible in a 1e-9 number, so the bar is absolute -- far inside the 1e-10 the north star asks for
+    assert abs(rel - d["relres"][0]) <= 1e-12 + 1e-6 * d["relres"][0]
+    assert np.max(np.abs(x - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+
+
+CASES = [
+    # (problem flags, solver id, extra ref flags, Amg parameters, k_dim)
+    (["-n", 16, 14, 12, "-difconv"], 1, ["-rlx", 18], dict(), 5),
+    (["-n", 16, 14, 12, "-difconv"], 3, ["-rlx", 18], dict(), 5),
+    (["-n", 16, 14, 12, "-difconv"], 9, ["-rlx", 18], dict(), 5),
+    (["-n", 18, 17, 13, "-difconv", "-a", 3, -2, 1, "-atype", 3], 3, ["-rlx", 18, "-k", 3], dict(), 3),            # restarts
+    (["-n", 18, 17, 13, "-difconv", "-a", 3, -2, 1, "-atype", 3], 3, ["-rlx", 18, "-agg_nl", 1], dict(AggNumLevels=1), 5),
+    (["-n", 15, 15, 15, "-difconv", "-a", 2, 1, 0, "-atype", 1], 9, [], dict(RelaxType=13, RelaxTypeUp=14), 5),    # l1 hybrid GS
+    (["-n", 15, 15, 15, "-difconv", "-a", 10, 10, 10, "-atype", 2], 3, ["-rlx", 18, "-mod_rap2", 1], dict(ModuleRAP2=1), 5),
+    (["-n", 14, 14, 14, "-difconv", "-c", 1, 1, 0.01, "-a", 0, 5, 0], 3, ["-rlx", 18, "-Pmx", 6, "-th", 0.5],
+     dict(PMaxElmts=6, StrongThreshold=0.5), 5),
+    (["-n", 32, 30, 28, "-difconv"], 3, ["-rlx", 18], dict(), 5),
+    # symmetric operators under the nonsymmetric drivers
+    (["-n", 20, 18, 16], 3, ["-rlx", 18], dict(), 5),
+    (["-n", 20, 18, 16], 9, ["-rlx", 18], dict(), 5),
+    (["-n", 12, 12, 12, "-27pt"], 3, ["-k", 2], dict(RelaxType=13, RelaxTypeUp=14), 2),
+    (["-n", 18, 16, 14, "-perturb", 3], 9, ["-rlx", 18], dict(), 5),
+]
+
+
+@pytest.mark.parametrize("prob,solver,extra,params,k_dim", CASES)
+def test_nonsymmetric_hierarchy_and_krylov_drivers(handle, prob, solver, extra, params, k_dim):
+    """ref_dump -difconv / -solver 3 / -solver 9 against the device path: the hierarchy of the nonsymmetric operator
+    is bit-identical (strength, PMIS, ext+i, both Galerkin orders, aggressive levels use only rows of A and S, never
+    symmetry), GMRES / BiCGSTAB take the reference's iteration count and reproduce its residual history to 1e-10"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(prob + ["-pmis", "-keepT", 1, "-solver", solver] + extra)
+    i0, j0, a0, _ = refio.csr(d, "A", 0)
+    if "-difconv" in prob:
+        nx, ny, nz = prob[1:4]
+        A = hb.ParCsr.difconv(handle, nx, ny, nz, **difconv_kw(prob))
+        if any(float(v) != 0.0 for v in difconv_kw(prob).get("a", (1, 1, 1))):
+            import scipy.sparse as sp
+            M = sp.csr_matrix((a0.copy(), j0.copy(), i0.copy()))          # copies: scipy sorts indices in place
+            assert abs(M - M.T).max() > 1.0 and ((M != 0) != (M.T != 0)).nnz == 0     # structurally symmetric, numerically not
+    else:
+        A = hb.ParCsr.from_host(handle, i0, j0, a0)
+    kw = dict(RelaxType=18, ModuleRAP2=0)
+    kw.update(params)
+    amg = hb.Amg(handle, **kw)
+    amg.setup(A)
+    check_hierarchy(amg, d)
+    its, rel, norms, x = solve_with(handle, solver, A, amg, i0.size - 1, k_dim)
+    check_solve(d, its, rel, norms, x)
+    amg.destroy(); A.destroy()
+
+
+GOLDEN = {
+    "difconv_11_pcg_rlx18.bin": (dict(), 1, dict(RelaxType=18), 5),
+    "difconv_11_gmres_rlx18.bin": (dict(), 3, dict(RelaxType=18), 5),
+    "difconv_13x11x9_upwind_gmres3_agg1.bin": (dict(a=(3, -2, 1), atype=3), 3, dict(RelaxType=18, AggNumLevels=1), 3),
+    "difconv_11_bicgstab_gs.bin": (dict(a=(2, 1, 0), atype=1), 9, dict(RelaxType=13, RelaxTypeUp=14), 5),
+    "lap7_11_gmres_gs1314.bin": (None, 3, dict(RelaxType=13, RelaxTypeUp=14), 5),
+}
+
+
+@pytest.mark.parametrize("name", sorted(GOLDEN))
+def test_committed_golden_dumps_of_the_krylov_drivers(handle, name):
+    """the same statements against tests/golden/ (made by tests/golden/make_golden.py from the reference build)"""
+    import hypre_ve_b200 as hb
+    gen, solver, params, k_dim = GOLDEN[name]
+    d = refio.read_dump(os.path.join(refio.GOLDEN, name))
+    nx, ny, nz = (int(v) for v in d["hdr"][:3])
+    A = hb.ParCsr.laplacian(handle, nx, ny, nz) if gen is None else hb.ParCsr.difconv(handle, nx, ny, nz, **gen)
+    amg = hb.Amg(handle, ModuleRAP2=0, **params)
+    amg.setup(A)
+    check_hierarchy(amg, d)
+    its, rel, norms, x = solve_with(handle, solver, A, amg, nx * ny * nz, k_dim)
+    check_solve(d, its, rel, norms, x)
+    amg.destroy(); A.destroy()
+
+
+def test_gmres_options(handle):
+    """min_iter keeps iterating past convergence; skip_real_r_check reports convergence without the extra residual;
+    a max_iter smaller than needed stops there; rel_change / cf_tol are rejected loudly; precond 0 and 2 run"""
+    import ctypes as C
+    import hypre_ve_b200 as hb
+    A = hb.ParCsr.difconv(handle, 12, 11, 10)
+    amg = hb.Amg(handle, RelaxType=18, ModuleRAP2=0)
+    amg.setup(A)
+    n = 12 * 11 * 10
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its0, rel0, norms0, conv0 = handle.gmres(A, amg, b, x, tol=1e-8)
+    assert conv0 == 1 and rel0 < 1e-8
+    # the true residual of the returned x is what was reported
+    r = handle.zeros(n)
+    A.matvec(-1.0, x, 1.0, b, r)
+    assert abs(np.linalg.norm(r.numpy()) / np.sqrt(n) - rel0) < 1e-12
+    handle.fill(x, 0.0)
+    its1, rel1, _, conv1 = handle.gmres(A, amg, b, x, tol=1e-8, min_iter=its0 + 4)
+    assert its1 >= its0 + 4 and rel1 <= rel0 * 1.0000001 and conv1 == 1
+    handle.fill(x, 0.0)
+    its2, rel2, norms2, conv2 = handle.gmres(A, amg, b, x, tol=1e-8, skip_real_r_check=1)
+    assert its2 == its0 and conv2 == 1 and np.array_equal(norms2, norms0)
+    handle.fill(x, 0.0)
+    its3, rel3, norms3, conv3 = handle.gmres(A, amg, b, x, tol=1e-8, max_iter=3)
+    assert its3 == 3 and conv3 == 0 and rel3 > 1e-8 and np.array_equal(norms3, norms0[:4])
+    for pre in (0, 2):                                    # unpreconditioned / diagonally scaled GMRES(20)
+        handle.fill(x, 0.0)
+        its, rel, norms, conv = handle.gmres(A, None, b, x, tol=1e-8, max_iter=400, k_dim=20, precond=pre)
+        assert conv == 1 and rel < 1e-8 and its > its0
+        A.matvec(-1.0, x, 1.0, b, r)
+        assert np.linalg.norm(r.numpy()) / np.sqrt(n) < 1e-8
+    prm = hb._GmresParams(1e-8, 0.0, 0.0, 100, 0, 5, 1, 0, 1)        # rel_change = 1
+    its, rel, conv = C.c_int(), C.c_double(), C.c_int()
+    assert hb._lib.b200_gmres_solve(handle.p, A.p, amg.p, C.byref(prm), b.ptr, x.ptr, C.byref(its), C.byref(rel), None, C.byref(conv)) != 0
+    prm = hb._GmresParams(1e-8, 0.0, 0.5, 100, 0, 5, 0, 0, 1)        # cf_tol > 0
+    assert hb._lib.b200_gmres_solve(handle.p, A.p, amg.p, C.byref(prm), b.ptr, x.ptr, C.byref(its), C.byref(rel), None, C.byref(conv)) != 0
+    prm = hb._GmresParams(1e-8, 0.0, 0.0, 100, 0, 0, 0, 0, 1)        # k_dim = 0
+    assert hb._lib.b200_gmres_solve(handle.p, A.p, amg.p, C.byref(prm), b.ptr, x.ptr, C.byref(its), C.byref(rel), None, C.byref(conv)) != 0
+    # zero right-hand side: nothing to do, x stays 0 (gmres.c:427-439)
+    handle.fill(b, 0.0); handle.fill(x, 0.0)
+    its, rel, _, _ = handle.gmres(A, amg, b, x, tol=1e-8)
+    assert its == 0 and rel == 0.0 and not x.numpy().any()
+    its, rel, _, _ = handle.bicgstab(A, amg, b, x, tol=1e-8)
+    assert its == 0 and not x.numpy().any()
+    amg.destroy(); A.destroy()
+
+
+def test_full_size_difconv_gmres_properties(handle):
+    """128^3 convection-diffusion (2.1 M rows) under AMG-GMRES: converges, the reported residual is the true one, and
+    the Krylov residual norms decrease monotonically (GMRES minimises the residual over a growing space)"""
+    import hypre_ve_b200 as hb
+    n1 = 128
+    A = hb.ParCsr.difconv(handle, n1, n1, n1)
+    amg = hb.Amg(handle, RelaxType=18, ModuleRAP2=0)
+    amg.setup(A)
+    n = n1 ** 3
+    b = handle.zeros(n); handle.fill(b, 1.0)
+    x = handle.zeros(n)
+    its, rel, norms, conv = handle.gmres(A, amg, b, x, tol=1e-8, max_iter=200)
+    assert conv == 1 and rel < 1e-8 and its < 60
+    restart_free = norms[:6]
+    assert np.all(np.diff(restart_free) < 0)
+    r = handle.zeros(n)
+    A.matvec(-1.0, x, 1.0, b, r)
+    assert abs(np.linalg.norm(r.numpy()) / np.sqrt(n) - rel) < 1e-11
+    amg.destroy(); A.destroy()
+
+
+# ---- the public API / plain-C client against the unmodified reference driver --------------------------------------
+def run(cmd, env=None):
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+    return p.returncode, p.stdout
+
+
+def result(out, key):
+    its = int(re.search(r"^%s = (\d+)" % key, out, re.M).group(1))
+    rel = float(re.search(r"Final (?:\w+ )?Relative Residual Norm = (\S+)", out).group(1))
+    return its, rel
+
+
+@pytest.mark.parametrize("flags,key", [
+    (["-difconv", "-n", "12", "12", "12", "-solver", "3", "-pmis", "-rlx", "18"], "GMRES Iterations"),
+    (["-difconv", "-n", "12", "12", "12", "-solver", "1", "-pmis", "-rlx", "18"], "Iterations"),
+    (["-difconv", "-n", "14", "12", "10", "-a", "3", "-2", "1", "-atype", "3", "-solver", "3", "-pmis", "-k", "3"], "GMRES Iterations"),
+    (["-difconv", "-n", "12", "12", "12", "-solver", "9", "-pmis"], "BiCGSTAB Iterations"),
+    (["-laplacian", "-27pt", "-n", "10", "10", "10", "-solver", "3", "-pmis", "-agg_nl", "1"], "GMRES Iterations"),
+    (["-difconv", "-n", "9", "8", "7", "-solver", "4", "-k", "10"], "GMRES Iterations"),                # DS-GMRES(10), 47 iterations
+    (["-laplacian", "-n", "9", "8", "7", "-solver", "10"], "BiCGSTAB Iterations"),                      # DS-BiCGSTAB
+])
+def test_krylov_drivers_through_the_public_api_match_the_reference_driver(flags, key):
+    """examples/ij_b200.c (HYPRE_ParCSRGMRES* / HYPRE_ParCSRBiCGSTAB* / GenerateDifConv over libhypre_b200.so) against
+    oracle/_ref/ij (the unmodified test/ij.c over the reference CPU library) on the same flags"""
+    from hypre_ve_b200 import build as b
+    exe = b.build_examples()
+    rc, out = run([exe] + flags)
+    assert rc == 0, out
+    its, rel = result(out, key)
+    assert os.path.exists(REF_IJ)
+    rrc, rout = run([REF_IJ] + flags, dict(os.environ, OMP_NUM_THREADS="1"))
+    assert rrc == 0, rout
+    rits, rrel = result(rout, key)
+    assert its == rits and abs(rel - rrel) <= 1e-12 + 1e-5 * rrel, (its, rits, rel, rrel)      # true-residual floor, see check_solve

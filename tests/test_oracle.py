@@ -64,6 +64,14 @@ GOLDEN_MORE = {
     # non-Laplacian SPD operators (ref_dump -perturb): mixed-sign, weak and strong off-diagonals
     "perturbed7_11_rlx18.bin": (["-n", 11, 11, 11, "-perturb", 1, "-pmis", "-rlx", 18], True),
     "perturbed27_8_agg1_gs.bin": (["-n", 8, 8, 8, "-27pt", "-perturb", 7, "-pmis", "-agg_nl", 1], True),
+    # nonsymmetric convection-diffusion (GenerateDifConv, par_difconv.c) under AMG-PCG / AMG-GMRES / AMG-BiCGSTAB
+    # (krylov/gmres.c, bicgstab.c restated in the oracle)
+    "difconv_11_pcg_rlx18.bin": (["-n", 11, 11, 11, "-difconv", "-pmis", "-rlx", 18], True),
+    "difconv_11_gmres_rlx18.bin": (["-n", 11, 11, 11, "-difconv", "-pmis", "-rlx", 18, "-solver", 3], True),
+    "difconv_13x11x9_upwind_gmres3_agg1.bin": (["-n", 13, 11, 9, "-difconv", "-a", 3, -2, 1, "-atype", 3, "-pmis", "-rlx", 18,
+                                                 "-solver", 3, "-k", 3, "-agg_nl", 1], True),
+    "difconv_11_bicgstab_gs.bin": (["-n", 11, 11, 11, "-difconv", "-a", 2, 1, 0, "-atype", 1, "-pmis", "-solver", 9], True),
+    "lap7_11_gmres_gs1314.bin": (["-n", 11, 11, 11, "-pmis", "-solver", 3], True),
 }
 
 
