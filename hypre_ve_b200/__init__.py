@@ -116,6 +116,8 @@ SIGNATURES = {
     "b200_dist_amg_level_cf": (_i, [_vp, _vp, _i, _vp]),
     "b200_dist_amg_setup_ms": (_i, [_vp, _dp]),
     "b200_dist_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
+    "b200_dist_gmres_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp, _ip]),
+    "b200_dist_bicgstab_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp, _ip]),
 }
 
 
@@ -705,3 +707,23 @@ def dist_pcg(handle, comm, A, amg, b, x, tol=1e-8, max_iter=100):
     _chk(_lib.b200_dist_pcg_solve(handle.p, comm.p, A.p, amg.p if amg is not None else None, b.ptr, x.ptr, tol, max_iter,
                                   C.byref(its), C.byref(rel), _np_ptr(norms)))
     return its.value, rel.value, norms[: its.value + 1]
+
+
+def dist_gmres(handle, comm, A, amg, b, x, tol=1e-8, max_iter=100, k_dim=5):
+    """hypre_GMRESSolve across ranks; returns (iterations, final relative residual, norms, converged)"""
+    prm = _GmresParams(tol, 0.0, 0.0, max_iter, 0, k_dim, 0, 0, 1 if amg is not None else 0)
+    its, rel, conv = _i(), _d(), _i()
+    norms = np.zeros(max_iter + 2, np.float64)
+    _chk(_lib.b200_dist_gmres_solve(handle.p, comm.p, A.p, amg.p if amg is not None else None, C.byref(prm), b.ptr, x.ptr,
+                                    C.byref(its), C.byref(rel), _np_ptr(norms), C.byref(conv)))
+    return its.value, rel.value, norms[: its.value + 1], conv.value
+
+
+def dist_bicgstab(handle, comm, A, amg, b, x, tol=1e-8, max_iter=100):
+    """hypre_BiCGSTABSolve across ranks; returns (iterations, final relative residual, norms, converged)"""
+    prm = _BicgstabParams(tol, 0.0, 0.0, max_iter, 0, 0, 1 if amg is not None else 0)
+    its, rel, conv = _i(), _d(), _i()
+    norms = np.zeros(max_iter + 2, np.float64)
+    _chk(_lib.b200_dist_bicgstab_solve(handle.p, comm.p, A.p, amg.p if amg is not None else None, C.byref(prm), b.ptr, x.ptr,
+                                       C.byref(its), C.byref(rel), _np_ptr(norms), C.byref(conv)))
+    return its.value, rel.value, norms[: its.value + 1], conv.value

@@ -1301,3 +1301,46 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
   b200_dfree(h, p); b200_dfree(h, s); b200_dfree(h, r); b200_dfree(h, xx); b200_dfree(h, sc);
   return rc;
 }
+
+// ---- GMRES / BiCGSTAB across ranks: the loops of b200_krylov.cu over the row-partitioned operator ----------------------
+// (hypre_GMRESSolve / hypre_BiCGSTABSolve with the hypre_ParKrylov* callbacks, parcsr_ls/par_krylov_func.c: matvec =
+// halo exchange + one kernel, inner product = local partial + one rank-ordered reduction, preconditioner = the
+// distributed cycle from a zero guess).  Every inner product of the Gram-Schmidt sweep is a reduction over the ranks.
+static int dist_krylov_ops(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, int precond, b200_krylov_ops *ops) {
+  if (!A || !A->L) B200_FAIL("dist krylov: matrix not localized");
+  if (precond != 0 && precond != 1) B200_FAIL("dist krylov: precond must be 0 (none) or 1 (BoomerAMG)");
+  if (precond == 1 && !amg) B200_FAIL("dist krylov: precond 1 needs a set-up BoomerAMG hierarchy");
+  const int n = A->n;
+  int cap = n + A->halo->ng + 8;
+  if (amg) cap = std::max(cap, amg->lv[0].cap);
+  ops->n = n;
+  ops->cap = cap;
+  ops->device_mgs = false;
+  ops->matvec = [h, c, A](double alpha, const double *x, double beta, const double *b, double *y) {
+    return dist_spmv(h, c, A, const_cast<double *>(x), y, 0, alpha, beta, b, nullptr);    // x is a work vector with a ghost tail
+  };
+  ops->precond = [h, c, amg, precond, n](const double *rhs, double *out) {
+    if (precond == 1) return dist_cycle(h, c, amg, rhs, out);
+    return b200_vec_copy(h, n, rhs, out);
+  };
+  ops->reduce = [h, c](const double *d_partials, int k, double *out) {
+    return b200_comm_allreduce_sum_dev(h, c, d_partials, k, out);
+  };
+  return 0;
+}
+extern "C" int b200_dist_gmres_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const b200_gmres_params *prm,
+                                     const double *d_b, double *d_x, int *iters, double *final_rel_res, double *h_norms,
+                                     int *converged) {
+  if (!prm) B200_FAIL("dist_gmres: null argument");
+  b200_krylov_ops ops;
+  B200_TRY(dist_krylov_ops(h, c, A, amg, prm->precond, &ops));
+  return b200_gmres_core(h, &ops, prm, d_b, d_x, iters, final_rel_res, h_norms, converged);
+}
+extern "C" int b200_dist_bicgstab_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg,
+                                        const b200_bicgstab_params *prm, const double *d_b, double *d_x, int *iters,
+                                        double *final_rel_res, double *h_norms, int *converged) {
+  if (!prm) B200_FAIL("dist_bicgstab: null argument");
+  b200_krylov_ops ops;
+  B200_TRY(dist_krylov_ops(h, c, A, amg, prm->precond, &ops));
+  return b200_bicgstab_core(h, &ops, prm, d_b, d_x, iters, final_rel_res, h_norms, converged);
+}

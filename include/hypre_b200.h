@@ -269,6 +269,14 @@ int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms);
 /* hypre_PCGSolve across ranks (dot products = deterministic rank-ordered sums) */
 int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const double *d_b,
                         double *d_x, double tol, int max_iter, int *iters, double *final_rel_res, double *h_norms);
+/* hypre_GMRESSolve / hypre_BiCGSTABSolve across ranks (krylov/gmres.c:226, bicgstab.c:207 over the hypre_ParKrylov*
+ * callbacks of parcsr_ls/par_krylov_func.c): same loops as b200_gmres_solve / b200_bicgstab_solve, every inner product
+ * one rank-ordered reduction; precond 0 none, 1 the distributed BoomerAMG cycle */
+int b200_dist_gmres_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const b200_gmres_params *params,
+                          const double *d_b, double *d_x, int *iters, double *final_rel_res, double *h_norms, int *converged);
+int b200_dist_bicgstab_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg,
+                             const b200_bicgstab_params *params, const double *d_b, double *d_x, int *iters,
+                             double *final_rel_res, double *h_norms, int *converged);
 
 #ifdef __cplusplus
 }

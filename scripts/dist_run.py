@@ -1,5 +1,7 @@
 """Multi-GPU runs of the other BASELINE.json configs (parity-test cases, not bench lines), under torchrun:
   config 3: --stencil 27 --global-edge 256 --relax 13 --gs-blocks T     (strong scaling: 256^3 split over N GPUs)
+  config 4: --global-edge 384 --agg-nl 1 --aniso 0.001                  (anisotropic diffusion, aggressive coarsening), or as written
+            --global-edge 384 --agg-nl 1 --difconv --solver 3          (ij -difconv: nonsymmetric, AMG-GMRES)
   config 5: --stencil 7 --edge-per-gpu 256 --spmv-sweep                 (weak scaling + SpMV bandwidth sweep)
 Prints one JSON line on rank 0."""
 import argparse, json, os, sys
@@ -18,6 +20,10 @@ ap.add_argument("--gs-blocks", type=int, default=1)
 ap.add_argument("--spmv-sweep", action="store_true")
 ap.add_argument("--agg-nl", type=int, default=0)
 ap.add_argument("--aniso", type=float, default=1.0, help="cz of -c 1 1 cz (config 4: 0.001)")
+ap.add_argument("--difconv", action="store_true", help="ij -difconv: GenerateDifConv with -c 1 1 aniso, --conv a a a, --atype")
+ap.add_argument("--conv", type=float, default=1.0)
+ap.add_argument("--atype", type=int, default=0)
+ap.add_argument("--solver", type=int, default=1, help="1 AMG-PCG, 3 AMG-GMRES(5), 9 AMG-BiCGSTAB (ij -solver)")
 ap.add_argument("--steps", type=int, default=2)
 a = ap.parse_args()
 rank, world, lr = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -65,7 +71,11 @@ else:
     e = a.edge_per_gpu or 256
     dims = (e * P, e * Q, e * R)
 out["global_dims"] = list(dims)
-A = hb.DistMatrix.laplacian(h, comm, *dims, P, Q, R, a.stencil, c=(1.0, 1.0, a.aniso))
+if a.difconv:
+    A = hb.DistMatrix.difconv(h, comm, *dims, P, Q, R, c=(1.0, 1.0, a.aniso), a=(a.conv,) * 3, atype=a.atype)
+    out.update(problem="difconv", a=[a.conv] * 3, atype=a.atype)
+else:
+    A = hb.DistMatrix.laplacian(h, comm, *dims, P, Q, R, a.stencil, c=(1.0, 1.0, a.aniso))
 inf = A.info
 n, nnz = inf["local_rows"], inf["local_nnz"]
 if a.spmv_sweep:
@@ -90,13 +100,18 @@ else:
         s_ms = amg.setup_ms
         h.fill(x, 0.0)
         h.timer_start()
-        its, rel, _ = hb.dist_pcg(h, comm, A, amg, b, x, tol=1e-8, max_iter=200)
+        if a.solver == 3:
+            its, rel, _, _ = hb.dist_gmres(h, comm, A, amg, b, x, tol=1e-8, max_iter=200)
+        elif a.solver == 9:
+            its, rel, _, _ = hb.dist_bicgstab(h, comm, A, amg, b, x, tol=1e-8, max_iter=200)
+        else:
+            its, rel, _ = hb.dist_pcg(h, comm, A, amg, b, x, tol=1e-8, max_iter=200)
         v_ms = h.timer_stop_ms()
         nl = amg.num_levels
         amg.destroy()
         if k:
             res.append((allmax(s_ms), allmax(v_ms)))
-    out.update(agg_nl=a.agg_nl, c=[1.0, 1.0, a.aniso], relax=a.relax, gs_blocks_per_gpu=a.gs_blocks, levels=nl, iterations=its, final_rel_res=rel,
+    out.update(solver=a.solver, agg_nl=a.agg_nl, c=[1.0, 1.0, a.aniso], relax=a.relax, gs_blocks_per_gpu=a.gs_blocks, levels=nl, iterations=its, final_rel_res=rel,
                setup_s=sum(r[0] for r in res) / len(res) / 1e3, solve_s=sum(r[1] for r in res) / len(res) / 1e3)
 if rank == 0:
     print(json.dumps(out))

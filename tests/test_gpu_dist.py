@@ -55,7 +55,7 @@ def gather(parts):
     return (np.concatenate(I).astype(np.int32), np.concatenate([p[2] for p in parts]), np.concatenate([p[3] for p in parts]))
 
 
-def dist_case(nranks, grid, dims, stencil=7, solve=True, **params):
+def dist_case(nranks, grid, dims, stencil=7, solve=True, solver=1, **params):
     import hypre_ve_b200 as hb
     nx, ny, nz = dims
     P, Q, R = grid
@@ -80,13 +80,18 @@ def dist_case(nranks, grid, dims, stencil=7, solve=True, **params):
         if solve:
             b = A.vector(1.0)
             x = A.vector(0.0)
-            its, rel, norms = hb.dist_pcg(h, c, A, amg, b, x, tol=1e-8, max_iter=100)
+            if solver == 3:
+                its, rel, norms, _ = hb.dist_gmres(h, c, A, amg, b, x, tol=1e-8, max_iter=100)
+            elif solver == 9:
+                its, rel, norms, _ = hb.dist_bicgstab(h, c, A, amg, b, x, tol=1e-8, max_iter=100)
+            else:
+                its, rel, norms = hb.dist_pcg(h, c, A, amg, b, x, tol=1e-8, max_iter=100)
             res.update(its=its, rel=rel, norms=norms, x=(A.info["first_row"], x.numpy()[:A.info["local_rows"]]))
         return res
     return run_ranks(nranks, fn)
 
 
-def single_gpu_on(handle, i, j, a, **params):
+def single_gpu_on(handle, i, j, a, solver=1, **params):
     import hypre_ve_b200 as hb
     A = hb.ParCsr.from_host(handle, i, j, a)
     amg = hb.Amg(handle, **params)
@@ -101,7 +106,12 @@ def single_gpu_on(handle, i, j, a, **params):
     n = i.size - 1
     b = handle.zeros(n); handle.fill(b, 1.0)
     x = handle.zeros(n)
-    its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
+    if solver == 3:
+        its, rel, norms, _ = handle.gmres(A, amg, b, x, tol=1e-8, max_iter=100)
+    elif solver == 9:
+        its, rel, norms, _ = handle.bicgstab(A, amg, b, x, tol=1e-8, max_iter=100)
+    else:
+        its, rel, norms = handle.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
     out = dict(levels=lv, its=its, rel=rel, norms=norms, x=x.numpy())
     amg.destroy(); A.destroy()
     return out
@@ -152,6 +162,31 @@ def test_nrank_nonsymmetric_operator_equals_single_gpu(handle, nranks, grid, dim
     check_against_single_gpu(handle, nranks, grid, dims, gen, ModuleRAP2=0)
 
 
+@pytest.mark.parametrize("nranks,grid,dims,gen,solver", [
+    (2, (1, 1, 2), (12, 11, 10), dict(), 3),
+    (4, (2, 2, 1), (13, 12, 9), dict(a=(3.0, -2.0, 1.0), atype=3), 3),
+    (8, (2, 2, 2), (14, 13, 12), dict(a=(2.0, 1.0, 0.0), atype=1), 9),
+    (3, (3, 1, 1), (12, 9, 8), 7, 3),
+    (2, (1, 2, 1), (10, 12, 8), dict(), 9),
+])
+def test_nrank_gmres_and_bicgstab_equal_single_gpu(handle, nranks, grid, dims, gen, solver):
+    """b200_dist_gmres_solve / b200_dist_bicgstab_solve: the loops of b200_krylov.cu over the row-partitioned operator and
+    the distributed cycle; iteration count equal to the single-GPU run on the gathered matrix, history to 1e-10"""
+    check_against_single_gpu(handle, nranks, grid, dims, gen, solver=solver)
+
+
+def test_zslab_difconv_gmres_equals_reference_cpu_build():
+    """3 z-slabs, upwind convection-diffusion, AMG-GMRES: hierarchy and iteration count of the reference np=1 run"""
+    dims = (13, 12, 14)
+    d, _ = refio.run_ref(["-n", *dims, "-difconv", "-a", 3, -2, 1, "-atype", 3, "-pmis", "-rlx", 18, "-mod_rap2", 1, "-keepT", 1,
+                          "-solver", 3])
+    res = dist_case(3, (1, 1, 3), dims, dict(a=(3.0, -2.0, 1.0), atype=3), solver=3)
+    assert res[0]["its"] == int(d["hdr"][4])
+    assert np.max(np.abs(res[0]["norms"] - d["norms"])) / d["norms"][0] < 1e-10
+    x = np.concatenate([v for _, v in sorted((r["x"] for r in res), key=lambda t: t[0])])
+    assert np.max(np.abs(x - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+
+
 def test_zslab_difconv_equals_reference_cpu_build():
     """z-slabs keep the lexicographic numbering: the gathered 3-rank convection-diffusion hierarchy is the reference's"""
     dims = (13, 12, 14)
@@ -167,12 +202,12 @@ def test_zslab_difconv_equals_reference_cpu_build():
     assert np.max(np.abs(res[0]["norms"] - d["norms"])) / d["norms"][0] < 1e-10
 
 
-def check_against_single_gpu(handle, nranks, grid, dims, stencil, **params):
-    res = dist_case(nranks, grid, dims, stencil, **params)
+def check_against_single_gpu(handle, nranks, grid, dims, stencil, solver=1, **params):
+    res = dist_case(nranks, grid, dims, stencil, solver=solver, **params)
     nl = len(res[0]["levels"])
     assert all(len(r["levels"]) == nl for r in res)
     gi, gj, ga = gather([r["levels"][0]["A"] for r in res])
-    ref = single_gpu_on(handle, gi, gj, ga, **params)
+    ref = single_gpu_on(handle, gi, gj, ga, solver=solver, **params)
     assert len(ref["levels"]) == nl
     for l in range(nl):
         i, j, a = gather([r["levels"][l]["A"] for r in res])
