@@ -58,6 +58,11 @@ SIGNATURES = {
     "b200_generate_laplacian": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_laplacian27": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_difconv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_ij_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "b200_ij_destroy": (_i, [_vp, _vp]),
+    "b200_ij_set_values": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _ip]),
+    "b200_ij_assemble": (_i, [_vp, _vp, C.POINTER(_vp), _ip]),
+    "b200_ij_num_rejected": (C.c_longlong, [_vp]),
     "b200_parcsr_create_from_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_parcsr_destroy": (_i, [_vp, _vp]),
     "b200_parcsr_local_rows": (_i, [_vp, _ip, _ip, _ip, _ip]),
@@ -359,6 +364,38 @@ class ParCsr:
     def destroy(self):
         if self.p:
             _chk(_lib.b200_parcsr_destroy(self.h.p, self.p))
+            self.p = None
+
+
+class IJAssembler:
+    """HYPRE_IJMatrixSetValues / AddToValues / Assemble on the device (b200_ij_*)"""
+
+    def __init__(self, handle, ilower, iupper, jlower=None, jupper=None):
+        self.h = handle
+        self.p = _vp()
+        _chk(_lib.b200_ij_create(handle.p, ilower, iupper, ilower if jlower is None else jlower,
+                                 iupper if jupper is None else jupper, C.byref(self.p)))
+
+    def set_values(self, ncols, rows, cols, values, add=False):
+        ncols = np.ascontiguousarray(ncols, dtype=np.int32)
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        cols = np.ascontiguousarray(cols, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float64)
+        assert ncols.size == rows.size and cols.size == values.size == int(ncols.sum())
+        rej = _i()
+        _chk(_lib.b200_ij_set_values(self.h.p, self.p, rows.size, _np_ptr(ncols), _np_ptr(rows), _np_ptr(cols), _np_ptr(values),
+                                     1 if add else 0, C.byref(rej)))
+        return rej.value
+
+    def assemble(self):
+        """returns (ParCsr, number of post-assembly records whose element does not exist)"""
+        out, miss = _vp(), _i()
+        _chk(_lib.b200_ij_assemble(self.h.p, self.p, C.byref(out), C.byref(miss)))
+        return ParCsr(self.h, out), miss.value
+
+    def destroy(self):
+        if self.p:
+            _chk(_lib.b200_ij_destroy(self.h.p, self.p))
             self.p = None
 
 

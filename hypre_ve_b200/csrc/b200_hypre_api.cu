@@ -71,7 +71,7 @@ struct hypre_IJMatrix_struct {
   int ilower = 0, iupper = -1, jlower = 0, jupper = -1;
   int object_type = -1;
   bool initialized = false, assembled = false;
-  std::vector<std::vector<std::pair<int, double>>> rows;      // auxiliary rows, insertion order
+  b200_ij ij = nullptr;                                       // device-side assembler (b200_ij.cu): record log + per-row replay
   hypre_ParCSRMatrix_struct *object = nullptr;
 };
 struct hypre_IJVector_struct {
@@ -228,6 +228,7 @@ HYPRE_Int HYPRE_IJMatrixCreate(MPI_Comm, HYPRE_BigInt ilower, HYPRE_BigInt iuppe
 HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix A);
 HYPRE_Int HYPRE_IJMatrixDestroy(HYPRE_IJMatrix m) {
   if (!m) return err_arg(1);
+  if (m->ij) { b200_handle h = handle(); if (h) b200_ij_destroy(h, m->ij); }
   if (m->object) HYPRE_ParCSRMatrixDestroy(m->object);
   delete m;
   return g_error_flag;
@@ -240,11 +241,15 @@ HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix m, HYPRE_Int type) {
 HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix m) {
   if (!m) return err_arg(1);
   if (m->object_type != HYPRE_PARCSR) return err_arg(1);             // HYPRE_IJMatrix.c:303-311
-  m->rows.assign((size_t)(m->iupper - m->ilower + 1), {});
+  NEED_HANDLE();
+  if (m->ij) { b200_ij_destroy(h, m->ij); m->ij = nullptr; }         // a fresh auxiliary matrix (IJMatrix_parcsr.c:178-230)
+  CALL(b200_ij_create(h, m->ilower, m->iupper, m->jlower, m->jupper, &m->ij), "HYPRE_IJMatrixInitialize");
   m->initialized = true;
   m->assembled = false;
   return g_error_flag;
 }
+// SetValues / AddToValues: validate and append to the assembler's record log (pinned chunks streamed to the device);
+// the merge itself happens on the device at Assemble (b200_ij.cu)
 static HYPRE_Int ij_set(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows, const HYPRE_BigInt *cols,
                         const HYPRE_Complex *values, bool add) {
   if (!m) return err_arg(1);
@@ -254,29 +259,17 @@ static HYPRE_Int ij_set(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, con
   if (!rows) return err_arg(4);
   if (!cols) return err_arg(5);
   if (!values) return err_arg(6);
-  if (!m->initialized) return err_arg(1);
-  size_t at = 0;
-  for (int r = 0; r < nrows; r++) {
-    const int row = rows[r], n = ncols[r];
-    if (row < m->ilower || row > m->iupper) {
-      // the reference stashes off-processor rows for the owner (IJMatrix_parcsr.c:1395-1450); with one
-      // rank per process there is no owner to send them to
-      fprintf(stderr, "hypre_b200: IJMatrix row %d is outside the local range [%d, %d]\n", row, m->ilower, m->iupper);
-      at += n;
-      err(HYPRE_ERROR_GENERIC);
-      continue;
-    }
-    auto &R = m->rows[(size_t)(row - m->ilower)];
-    for (int k = 0; k < n; k++, at++) {
-      const int c = cols[at];
-      if (c < m->jlower || c > m->jupper) { err(HYPRE_ERROR_GENERIC); continue; }
-      bool found = false;
-      for (auto &e : R)
-        if (e.first == c) { e.second = add ? e.second + values[at] : values[at]; found = true; break; }
-      if (!found) R.emplace_back(c, values[at]);
-    }
+  if (!m->initialized || !m->ij) return err_arg(1);
+  NEED_HANDLE();
+  int rejected = 0;
+  CALL(b200_ij_set_values(h, m->ij, nrows, ncols, rows, cols, values, add ? 1 : 0, &rejected), "HYPRE_IJMatrixSetValues");
+  if (rejected) {
+    // the reference stashes off-processor rows for the owner (IJMatrix_parcsr.c:1395-1450); with one rank per
+    // process there is no owner to send them to, and columns outside [jlower, jupper] do not exist
+    fprintf(stderr, "hypre_b200: IJMatrix: %d entries outside rows [%d, %d] / columns [%d, %d] were dropped\n", rejected, m->ilower,
+            m->iupper, m->jlower, m->jupper);
+    err(HYPRE_ERROR_GENERIC);
   }
-  m->assembled = false;
   return g_error_flag;
 }
 HYPRE_Int HYPRE_IJMatrixSetValues(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, const HYPRE_BigInt *rows,
@@ -289,35 +282,24 @@ HYPRE_Int HYPRE_IJMatrixAddToValues(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int
 }
 HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix m) {
   if (!m) return err_arg(1);
-  if (!m->initialized) return err_arg(1);
+  if (!m->initialized || !m->ij) return err_arg(1);
   NEED_HANDLE();
-  const int n = (int)m->rows.size(), ncols = m->jupper - m->jlower + 1;
-  const bool square = (m->ilower == m->jlower && m->iupper == m->jupper);
-  std::vector<int> I((size_t)n + 1, 0), J;
-  std::vector<double> V;
-  size_t nnz = 0;
-  for (auto &R : m->rows) nnz += R.size();
-  J.reserve(nnz); V.reserve(nnz);
-  for (int i = 0; i < n; i++) {
-    const auto &R = m->rows[i];
-    int dpos = -1;
-    if (square)
-      for (size_t k = 0; k < R.size(); k++)
-        if (R[k].first - m->jlower == i) { dpos = (int)k; break; }
-    if (dpos >= 0) { J.push_back(i); V.push_back(R[dpos].second); }                 // diagonal first (:2933-2937)
-    for (size_t k = 0; k < R.size(); k++)
-      if ((int)k != dpos) { J.push_back(R[k].first - m->jlower); V.push_back(R[k].second); }
-    I[i + 1] = (int)J.size();
+  const bool first = !m->assembled;
+  b200_parcsr A = nullptr;
+  int missing = 0;
+  if (b200_ij_assemble(h, m->ij, &A, &missing)) return err_b200("HYPRE_IJMatrixAssemble");
+  if (first) {
+    if (m->object) { HYPRE_ParCSRMatrixDestroy(m->object); m->object = nullptr; }     // object of an earlier Initialize cycle
+    hypre_ParCSRMatrix_struct *P = new hypre_ParCSRMatrix_struct();
+    P->A = A;
+    int nr = 0, nd = 0, no = 0, nco = 0;
+    b200_parcsr_local_rows(A, &nr, &nd, &no, &nco);
+    P->global_rows = m->iupper - m->ilower + 1; P->global_cols = m->jupper - m->jlower + 1; P->nnz = (long long)nd + no;
+    m->object = P;
+  } else if (missing) {
+    fprintf(stderr, "hypre_b200: IJMatrix: %d values were set on elements that do not exist in the assembled matrix\n", missing);
+    err(HYPRE_ERROR_GENERIC);                                   // " Error, element %b %b does not exist" (IJMatrix_parcsr.c:836-842)
   }
-  if (m->object) { HYPRE_ParCSRMatrixDestroy(m->object); m->object = nullptr; }
-  hypre_ParCSRMatrix_struct *P = new hypre_ParCSRMatrix_struct();
-  if (J.empty()) { J.push_back(0); V.push_back(0.0); }
-  if (b200_parcsr_create_from_host(h, n, ncols, (int)nnz, I.data(), J.data(), V.data(), &P->A)) {
-    delete P;
-    return err_b200("HYPRE_IJMatrixAssemble");
-  }
-  P->global_rows = n; P->global_cols = ncols; P->nnz = (long long)nnz;
-  m->object = P;
   m->assembled = true;
   return g_error_flag;
 }

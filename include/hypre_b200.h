@@ -101,6 +101,20 @@ int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int 
 int b200_generate_difconv(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
                           int p, int q, int r, const double values[7], b200_parcsr *A);
 
+/* ---- IJ assembly on the device (IJ_mv/IJMatrix_parcsr.c:697-1186 SetValues, :1188 AddToValues, :2774-3080 Assemble) ----
+ * SetValues / AddToValues take HOST arrays (global row / column indices) and only append validated records to a pinned
+ * log that streams to the device; Assemble sorts the log by row (stable), replays every row's insertions on the device
+ * with the reference's rules (an entry is matched only against what its row held before the current (call,row) pair;
+ * unmatched entries are appended; the last entry on the diagonal column moves to the front) and returns the ParCSR
+ * object.  After the first Assemble only existing entries may be set / added; *n_missing counts the others. */
+typedef struct b200_ij_s *b200_ij;
+int b200_ij_create(b200_handle h, int ilower, int iupper, int jlower, int jupper, b200_ij *ij);
+int b200_ij_destroy(b200_handle h, b200_ij ij);
+int b200_ij_set_values(b200_handle h, b200_ij ij, int nrows, const int *ncols, const int *rows, const int *cols,
+                       const double *values, int add, int *n_rejected);
+int b200_ij_assemble(b200_handle h, b200_ij ij, b200_parcsr *A, int *n_missing);
+long long b200_ij_num_rejected(b200_ij ij);
+
 /* ---- ParCSR (parcsr_mv) -------------------------------------------------------------------- */
 /* single-rank ParCSR from a host CSR (diag block = whole matrix); diagonal entry must be first
  * in each row as in the reference's diag block (csr_matrix.h, relied on by relax/strength). */

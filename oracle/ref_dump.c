@@ -16,6 +16,7 @@
  * Flags follow ij.c's spelling: -n nx ny nz, -27pt, -c cx cy cz, -pmis, -rlx T,
  * -Pmx K, -agg_nl L, -mod_rap2 B, -keepT B, -th theta, -tol t, -interptype I,
  * -mxrs r (max_row_sum), -o FILE, -matvec K (time K SpMVs, ij -solver -1 analogue),
+ * -ijbuild MODE [-noamg] (operator re-assembled through the reference's HYPRE_IJMatrix interface),
  * -solver 1|3|9 (AMG-PCG, AMG-GMRES with -k K, AMG-BiCGSTAB: ij.c:5298-5330, :6364-6380),
  * -difconv [-a ax ay az] [-atype T] (GenerateDifConv, nonsymmetric), -nodump (timing only), -ns / -ns_coarse / -mu / -fmg (cycle shape), -perturb SEED (non-Laplacian values, see below).
  */
@@ -31,6 +32,7 @@
 #include "_hypre_parcsr_mv.h"
 #include "_hypre_parcsr_ls.h"
 #include "HYPRE_krylov.h"
+#include "HYPRE_IJ_mv.h"
 
 static FILE *g_out;
 
@@ -112,6 +114,81 @@ static void difconv_values(int nx, int ny, int nz, const double *c, const double
       }
    }
 }
+
+/* -ijbuild MODE: the operator is re-assembled from the generated one through the reference's own HYPRE_IJMatrix
+ * interface by a fixed stream of SetValues / AddToValues calls (mirrored record for record by tests/ijstream.py):
+ *   phase 1  SetValues, two rows per call, rows visited from the last to the first, each row's entries rotated by
+ *            (row mod length), half of every value;
+ *   phase 2  AddToValues, one row per call, first to last, rotated by ((row+1) mod length), the other half;
+ *   MODE 2 only, phase 3 (every row with row mod 7 == 3): one SetValues call holding a far column TWICE and an existing
+ *            column (in-call duplicates stay duplicates, IJMatrix_parcsr.c:941-962), then one AddToValues call that
+ *            lists the same row twice with one more column (the second block finds what the first appended);
+ *   Assemble; then, after assembly, AddToValues(+1) on the diagonal of every third row and SetValues of the second
+ *   stored entry of every fifth row to itself times 1 (existing entries only, :727-905); Assemble again. */
+static HYPRE_ParCSRMatrix ijbuild(HYPRE_ParCSRMatrix G, int mode, HYPRE_IJMatrix *ij_out)
+{
+   hypre_CSRMatrix *D = hypre_ParCSRMatrixDiag((hypre_ParCSRMatrix *) G);
+   int N = hypre_CSRMatrixNumRows(D), *I = hypre_CSRMatrixI(D), *J = hypre_CSRMatrixJ(D), r, k, q;
+   double *a = hypre_CSRMatrixData(D);
+   HYPRE_IJMatrix ij;
+   int rows[2], ncols[2], cols[64];
+   double vals[64];
+   HYPRE_IJMatrixCreate(hypre_MPI_COMM_WORLD, 0, N - 1, 0, N - 1, &ij);
+   HYPRE_IJMatrixSetObjectType(ij, HYPRE_PARCSR);
+   HYPRE_IJMatrixInitialize(ij);
+   for (r = N - 1; r >= 0; r -= 2)                       /* phase 1 */
+   {
+      int nr = 0, at = 0;
+      for (q = 0; q < 2 && r - q >= 0; q++)
+      {
+         int row = r - q, len = I[row + 1] - I[row], rot = row % len;
+         rows[nr] = row; ncols[nr++] = len;
+         for (k = 0; k < len; k++) { int e = I[row] + (k + rot) % len; cols[at] = J[e]; vals[at++] = 0.5 * a[e]; }
+      }
+      HYPRE_IJMatrixSetValues(ij, nr, ncols, rows, cols, vals);
+   }
+   for (r = 0; r < N; r++)                               /* phase 2 */
+   {
+      int len = I[r + 1] - I[r], rot = (r + 1) % len;
+      rows[0] = r; ncols[0] = len;
+      for (k = 0; k < len; k++) { int e = I[r] + (k + rot) % len; cols[k] = J[e]; vals[k] = 0.5 * a[e]; }
+      HYPRE_IJMatrixAddToValues(ij, 1, ncols, rows, cols, vals);
+   }
+   if (mode == 2)
+      for (r = 3; r < N; r += 7)                         /* phase 3 */
+      {
+         int far = (int) (((long long) r * 31 + 17) % N), c2 = (int) (((long long) r * 13 + 5) % N);
+         rows[0] = r; ncols[0] = 3;
+         cols[0] = far; cols[1] = far; cols[2] = J[I[r] + (I[r + 1] - I[r]) / 2];
+         vals[0] = 0.125; vals[1] = 0.25; vals[2] = 9.0;
+         HYPRE_IJMatrixSetValues(ij, 1, ncols, rows, cols, vals);
+         rows[0] = r; rows[1] = r; ncols[0] = 1; ncols[1] = 1;
+         cols[0] = c2; cols[1] = c2; vals[0] = 1.5; vals[1] = 2.5;
+         HYPRE_IJMatrixAddToValues(ij, 2, ncols, rows, cols, vals);
+      }
+   HYPRE_IJMatrixAssemble(ij);
+   {
+      void *obj; hypre_CSRMatrix *E; int *EI, *EJ; double *Ea;
+      HYPRE_IJMatrixGetObject(ij, &obj);
+      E = hypre_ParCSRMatrixDiag((hypre_ParCSRMatrix *) obj);
+      EI = hypre_CSRMatrixI(E); EJ = hypre_CSRMatrixJ(E); Ea = hypre_CSRMatrixData(E);
+      for (r = 0; r < N; r += 3)
+      {
+         rows[0] = r; ncols[0] = 1; cols[0] = r; vals[0] = 1.0;
+         HYPRE_IJMatrixAddToValues(ij, 1, ncols, rows, cols, vals);
+      }
+      for (r = 0; r < N; r += 5)
+         if (EI[r + 1] - EI[r] > 1)
+         {
+            rows[0] = r; ncols[0] = 1; cols[0] = EJ[EI[r] + 1]; vals[0] = Ea[EI[r] + 1] * 1.0;
+            HYPRE_IJMatrixSetValues(ij, 1, ncols, rows, cols, vals);
+         }
+      HYPRE_IJMatrixAssemble(ij);
+      HYPRE_IJMatrixGetObject(ij, &obj);
+      *ij_out = ij;
+      return (HYPRE_ParCSRMatrix) obj;
+   }
+}
 static double now(void)
 {
    struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -125,6 +202,7 @@ int main(int argc, char **argv)
    int ns = 1, ns_coarse = 1, mu = 1, fmg = 0, perturb = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    int difconv = 0, atype = 0;                                   /* ij.c: -difconv, -a ax ay az, -atype */
+   int ij_mode = 0, noamg = 0;                                   /* -ijbuild MODE (see ijbuild above), -noamg: dump A0 only */
    int solver_id = 1, k_dim = 5;                                 /* ij.c: -solver 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB; -k */
    double ax = 1, ay = 1, az = 1;
    const char *ofile = NULL;
@@ -137,6 +215,8 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-difconv")) difconv = 1;
       else if (!strcmp(argv[i], "-a")) { ax = atof(argv[++i]); ay = atof(argv[++i]); az = atof(argv[++i]); }
       else if (!strcmp(argv[i], "-atype")) atype = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-ijbuild")) ij_mode = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-noamg")) noamg = 1;
       else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-pmis")) pmis = 1;
@@ -192,6 +272,8 @@ int main(int argc, char **argv)
       A = (HYPRE_ParCSRMatrix) GenerateLaplacian(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
    }
    double t_gen = now() - t0;
+   HYPRE_IJMatrix ij_A = NULL;
+   if (ij_mode) A = ijbuild(A, ij_mode, &ij_A);      /* (the generated matrix is left to the OS) */
    hypre_ParCSRMatrix *pA = (hypre_ParCSRMatrix *) A;
    int N = hypre_CSRMatrixNumRows(hypre_ParCSRMatrixDiag(pA));
    if (perturb)                                   /* one rank: the whole operator is the diag block, diagonal entry first */
@@ -211,6 +293,15 @@ int main(int argc, char **argv)
    printf("ref_dump: n=%d %d %d rows=%d nnz=%d threads=%d gen=%.3fs\n", nx, ny, nz, N,
           hypre_CSRMatrixI(hypre_ParCSRMatrixDiag(pA))[N], hypre_NumThreads(), t_gen);
 
+   if (noamg)
+   {  /* assembly check only: the operator as the reference's IJ interface built it */
+      int hdr[8] = { nx, ny, nz, 1, 0, pt27, Pmx, rlx };
+      put("hdr", 0, hdr, 8);
+      put_csr("A", 0, hypre_ParCSRMatrixDiag(pA), 1);
+      if (g_out) fclose(g_out);
+      HYPRE_Finalize(); hypre_MPI_Finalize();
+      return 0;
+   }
    if (matvec > 0)
    {  /* ij -solver -1 analogue (ij.c:3206-3243): y = A x repeated */
       hypre_ParVectorSetConstantValues(x, 1.0);

@@ -188,3 +188,22 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h", ".c")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle/" not in txt and "amg_oracle" not in txt and "ref_dump" not in txt, os.path.join(dirpath, f)
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,mode", [(["-n", 6, 5, 4], 1), (["-n", 6, 5, 4], 2), (["-n", 5, 4, 3, "-27pt"], 2), (["-n", 9, 1, 7], 1)])
+def test_ij_call_stream_mirror_matches_the_reference_ij_interface(args, mode):
+    """tests/ijstream.py (the call stream of `ref_dump -ijbuild` and a restatement of the reference's SetValues /
+    AddToValues / Assemble rules) reproduces the matrix the reference's own HYPRE_IJMatrix interface assembles, bit
+    for bit -- so the GPU test may feed the same stream to b200_ij_* and compare with the reference's output"""
+    import ijstream
+    g, _ = refio.run_ref(args + ["-noamg"])
+    I, J, a, _ = refio.csr(g, "A", 0)
+    d, _ = refio.run_ref(args + ["-ijbuild", mode, "-noamg"])
+    ri, rj, ra, _ = refio.csr(d, "A", 0)
+    rows = ijstream.replay(ijstream.calls_before_assembly(I, J, a, mode), I.size - 1)
+    EI, EJ, Ea = ijstream.assemble(rows)
+    assert ijstream.update(EI, EJ, Ea, ijstream.calls_after_assembly(EI, EJ, Ea)) == 0
+    assert np.array_equal(EI, ri) and np.array_equal(EJ, rj) and np.array_equal(Ea, ra)
+    if mode == 2:
+        assert ri[-1] > I[-1] and any(len(set(rj[ri[r]:ri[r + 1]])) < ri[r + 1] - ri[r] for r in range(3, I.size - 1, 7))   # duplicates survive
