@@ -518,13 +518,13 @@ static int dist_generate(b200_handle h, b200_comm c, int nx, int ny, int nz, int
                          int stencil, const double *user_values, b200_dist_matrix *out) {
   const int nr = b200_comm_size(c), me = b200_comm_rank(c);
   if (P * Q * R != nr) B200_FAIL("process grid P*Q*R must equal the number of ranks");
-  if (stencil != 7 && stencil != 27 && stencil != 70) B200_FAIL("stencil must be 7 or 27");
+  if (stencil != 7 && stencil != 27 && stencil != 70 && stencil != 72) B200_FAIL("stencil must be 7 or 27");
   double values[7] = {0, 0, 0, 0, 0, 0, 0};
   if (stencil == 7) {
     for (int k = 0; k < 4; k++) values[k] = user_values[k];
     for (int k = 1; k < 4; k++) values[k + 3] = user_values[k];
   } else {
-    for (int k = 0; k < (stencil == 70 ? 7 : 2); k++) values[k] = user_values[k];
+    for (int k = 0; k < (stencil == 70 ? 7 : stencil == 72 ? 4 : 2); k++) values[k] = user_values[k];
   }
   if (stencil == 70) stencil = 7;
   const int p = me % P, q = ((me - p) / P) % Q, r = (me - p - P * q) / (P * Q);      // ij.c:7785-7787
@@ -549,6 +549,13 @@ extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, 
                                             int stencil, const double *values, b200_dist_matrix *out) {
   if (stencil != 7 && stencil != 27) B200_FAIL("stencil must be 7 or 27");
   return dist_generate(h, c, nx, ny, nz, P, Q, R, stencil, values, out);
+}
+void b200_rotate7pt_values(double alpha, double eps, double *value);      // b200_parcsr.cu
+extern "C" int b200_dist_generate_rotate7pt(b200_handle h, b200_comm c, int nx, int ny, int P, int Q, double alpha, double eps,
+                                            b200_dist_matrix *out) {
+  double v[4];
+  b200_rotate7pt_values(alpha, eps, v);
+  return dist_generate(h, c, nx, ny, 1, P, Q, 1, 72, v, out);                // rank -> (p, q) as ij.c:9190-9191
 }
 extern "C" int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
                                           const double values[7], b200_dist_matrix *out) {

@@ -8,6 +8,7 @@
 // The generators run as one thread per grid point (count -> scan -> fill) and emit exactly the
 // reference's entry order; ghost columns are compressed by sort/unique + binary search instead of
 // the reference's O(num_cols_offd^2) remap loop (par_laplace.c:316-323).
+#include <cmath>
 #include "b200_internal.h"
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_select.cuh>
@@ -60,9 +61,18 @@ __device__ inline int global_index(const Grid &g, int ix, int iy, int iz) {
 // lexicographic (par_laplace_27pt.c fill pass).
 struct StencilVals { double v[7]; };     // centre, x-, y-, z-, x+, y+, z+ (27-pt: centre, off-centre)
 
+// STENCIL 72 = the 2-D rotated-anisotropy 7-point stencil of GenerateRotate7pt (par_rotate_7pt.c:228-350, nz = 1):
+// centre, (-1,-1), (0,-1), (-1,0), (+1,0), (0,+1), (+1,+1) with values v0, v3, v2, v1, v1, v2, v3.
+__host__ __device__ constexpr int stencil_points(int stencil) { return stencil == 72 ? 7 : stencil; }
+__host__ __device__ constexpr int stencil_values(int stencil) { return stencil == 7 ? 7 : stencil == 72 ? 4 : 2; }
 template <int STENCIL>
 __device__ inline void stencil_offset(int k, int *dx, int *dy, int *dz, int *vidx) {
-  if (STENCIL == 7) {
+  if (STENCIL == 72) {
+    const int ox[7] = {0, -1, 0, -1, 1, 0, 1};
+    const int oy[7] = {0, -1, -1, 0, 0, 1, 1};
+    const int vi[7] = {0, 3, 2, 1, 1, 2, 3};
+    *dx = ox[k]; *dy = oy[k]; *dz = 0; *vidx = vi[k];
+  } else if (STENCIL == 7) {
     const int ox[7] = {0, 0, 0, -1, 1, 0, 0};
     const int oy[7] = {0, 0, -1, 0, 0, 1, 0};
     const int oz[7] = {0, -1, 0, 0, 0, 0, 1};
@@ -89,7 +99,7 @@ __global__ void gen_kernel(Grid g, StencilVals sv, int *diag_i, int *offd_i,
   int pd = 0, po = 0;
   if (FILL) { pd = diag_i[row]; po = offd_i[row]; }
   const double *vals = sv.v;
-  for (int k = 0; k < STENCIL; k++) {
+  for (int k = 0; k < stencil_points(STENCIL); k++) {
     int dx, dy, dz, vi;
     stencil_offset<STENCIL>(k, &dx, &dy, &dz, &vi);
     const int jx = ix + dx, jy = iy + dy, jz = iz + dz;
@@ -124,7 +134,7 @@ __global__ void gen_global_kernel(Grid g, StencilVals sv, int *A_i, int *A_j, do
   int cnt = 0;
   const int pos = FILL ? A_i[row] : 0;
   const double *vals = sv.v;
-  for (int k = 0; k < STENCIL; k++) {
+  for (int k = 0; k < stencil_points(STENCIL); k++) {
     int dx, dy, dz, vi;
     stencil_offset<STENCIL>(k, &dx, &dy, &dz, &vi);
     const int jx = ix + dx, jy = iy + dy, jz = iz + dz;
@@ -198,7 +208,7 @@ static int generate_global(b200_handle h, Grid g, const double *vals, b200_csr *
   B200_TRY(b200_dalloc<int>(h, &ai, (size_t)nloc + 1));
   B200_CUDA(cudaMemsetAsync(ai + nloc, 0, sizeof(int), h->stream));
   StencilVals sv;
-  for (int k = 0; k < 7; k++) sv.v[k] = k < (STENCIL == 7 ? 7 : 2) ? vals[k] : 0.0;
+  for (int k = 0; k < 7; k++) sv.v[k] = k < stencil_values(STENCIL) ? vals[k] : 0.0;
   if (nloc) {
     gen_global_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, ai, nullptr, nullptr);
     B200_LAUNCH_CHECK();
@@ -228,6 +238,10 @@ int b200_generate_stencil_global(b200_handle h, int nx, int ny, int nz, int P, i
   part_range(ny, Q, q, &g.y0, &g.y1);
   part_range(nz, R, r, &g.z0, &g.z1);
   *first_row = b200_box_first_row(nx, ny, nz, P, Q, R, p, q, r);
+  if (stencil == 72) {
+    if (nz != 1 || R != 1) B200_FAIL("the rotated 7-point operator is two-dimensional (nz = 1, R = 1)");
+    return generate_global<72>(h, g, vals, out);
+  }
   return stencil == 7 ? generate_global<7>(h, g, vals, out) : generate_global<27>(h, g, vals, out);
 }
 
@@ -250,7 +264,7 @@ static int generate(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, 
   B200_CUDA(cudaMemsetAsync(di + nloc, 0, sizeof(int), h->stream));
   B200_CUDA(cudaMemsetAsync(oi + nloc, 0, sizeof(int), h->stream));
   StencilVals sv;
-  for (int k = 0; k < 7; k++) sv.v[k] = k < (STENCIL == 7 ? 7 : 2) ? vals[k] : 0.0;
+  for (int k = 0; k < 7; k++) sv.v[k] = k < stencil_values(STENCIL) ? vals[k] : 0.0;
   if (nloc) {
     gen_kernel<STENCIL, false><<<b200_grid(nloc, 256), 256, 0, h->stream>>>(g, sv, di, oi, nullptr,
                                                                            nullptr, nullptr, nullptr);
@@ -304,6 +318,25 @@ extern "C" int b200_generate_laplacian(b200_handle h, int nx, int ny, int nz, in
 extern "C" int b200_generate_difconv(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q,
                                      int r, const double values[7], b200_parcsr *A) {
   return generate<7>(h, nx, ny, nz, P, Q, R, p, q, r, values, A);
+}
+// value[4] of GenerateRotate7pt from the rotation angle (degrees) and the anisotropy (par_rotate_7pt.c:62-73)
+void b200_rotate7pt_values(double alpha, double eps, double *value) {
+  const double pi = 4.0 * atan(1.0);
+  const double x = pi * alpha / 180.0;
+  const double s = sin(x), c = cos(x);
+  const double ac = -(c * c + eps * s * s), bc = 2.0 * (1.0 - eps) * s * c, cc = -(s * s + eps * c * c);
+  value[0] = -2 * (2 * ac + bc + 2 * cc);
+  value[1] = 2 * ac + bc;
+  value[2] = bc + 2 * cc;
+  value[3] = -bc;
+}
+// GenerateRotate7pt (parcsr_ls/par_rotate_7pt.c:15-400): -(c^2 + eps s^2) u_xx - 2(1 - eps) s c u_xy - (s^2 + eps c^2) u_yy
+// on an nx x ny grid, P x Q process grid, this rank at (p, q)
+extern "C" int b200_generate_rotate7pt(b200_handle h, int nx, int ny, int P, int Q, int p, int q, double alpha, double eps,
+                                       b200_parcsr *A) {
+  double v[4];
+  b200_rotate7pt_values(alpha, eps, v);
+  return generate<72>(h, nx, ny, 1, P, Q, 1, p, q, 0, v, A);
 }
 extern "C" int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int Q, int R, int p, int q,
                                          int r, const double values[2], b200_parcsr *A) {
