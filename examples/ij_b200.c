@@ -1,7 +1,7 @@
 /* ij_b200.c -- a plain-C client of the reference's public API, linked against libhypre_b200.so.
  *
  * It walks the same call sequence as the reference driver test/ij.c does for
- *     ij -laplacian [-27pt] | -difconv [-a ax ay az] [-atype t]  -n nx ny nz [-c cx cy cz] -solver {0,1,2,3,4,9,10,-1} ...
+ *     ij -laplacian [-27pt] | -difconv [-a ax ay az] [-atype t] | -rotate -alpha A -eps E  -n nx ny nz [-c cx cy cz] -solver {0,1,2,3,4,9,10,-1} ...
  * (problem: ij.c:7785-7830 / :9084; rhs b = 1, x0 = 0: :2318-2340; AMG-PCG: :3884-4043, :4270-4330;
  * AMG alone: :3390-3560; AMG-GMRES: :5298-5480; AMG-BiCGSTAB: :6364-6500; matvec loop: :3206-3243) using only HYPRE_* calls, so it shows that host C
  * written against hypre's API runs on the B200 path by relinking.  It prints the result lines in the
@@ -78,22 +78,27 @@ static void difconv_values(int nx, int ny, int nz, double cx, double cy, double 
 }
 
 int main(int argc, char **argv) {
-  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0, difconv = 0, atype = 0, k_dim = 5;
-  double cx = 1., cy = 1., cz = 1., ax = 1., ay = 1., az = 1.;
+  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0, difconv = 0, atype = 0, k_dim = 5, rotate = 0;
+  double cx = 1., cy = 1., cz = 1., ax = 1., ay = 1., az = 1., alpha = 0., eps = 1.;
   /* driver defaults, test/ij.c:203-330 and :1181-1205 */
   int coarsen_type = 10, interp_type = 6, P_max_elmts = 4, relax_type = -1, relax_order = 0, max_levels = 25;
   int agg_num_levels = 0, rap2 = 0, mod_rap2 = 0, keepTranspose = 1, num_sweeps = 1, max_iter = 1000, mg_max_iter = 100;
   int coarse_threshold = 9, min_coarse_size = 0, ioutdat = 3, poutdat = 1, two_norm = 1, gs_blocks = 1;
   int cycle_type = 1, fcycle = 0, ns_coarse = 1, ns_down = -1, ns_up = -1;                        /* ij.c:167, :205-206 */
   double strong_threshold = 0.25, max_row_sum = 1.0, trunc_factor = 0.0, tol = 1.e-8, pc_tol = 0., relax_wt = 1., outer_wt = 1.;
+  for (int a = 1; a < argc; a++) if (!strcmp(argv[a], "-rotate")) rotate = 1;      /* decides how many numbers -n takes */
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-laplacian")) ;
     else if (!strcmp(argv[a], "-27pt")) stencil27 = 1;
     else if (!strcmp(argv[a], "-difconv")) difconv = 1;
+    else if (!strcmp(argv[a], "-rotate")) rotate = 1;                    /* 2-D: -n nx ny (ij.c:9136-9160) */
+    else if (!strcmp(argv[a], "-alpha") && a + 1 < argc) alpha = atof(argv[++a]);
+    else if (!strcmp(argv[a], "-eps") && a + 1 < argc) eps = atof(argv[++a]);
     else if (!strcmp(argv[a], "-a") && a + 3 < argc) { ax = atof(argv[a + 1]); ay = atof(argv[a + 2]); az = atof(argv[a + 3]); a += 3; }
     else if (!strcmp(argv[a], "-atype") && a + 1 < argc) atype = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-k") && a + 1 < argc) k_dim = atoi(argv[++a]);
     else if (!strcmp(argv[a], "-ijbuild")) ijbuild = 1;
+    else if (!strcmp(argv[a], "-n") && rotate && a + 2 < argc) { nx = atoi(argv[a + 1]); ny = atoi(argv[a + 2]); nz = 1; a += 2; }
     else if (!strcmp(argv[a], "-n") && a + 3 < argc) { nx = atoi(argv[a + 1]); ny = atoi(argv[a + 2]); nz = atoi(argv[a + 3]); a += 3; }
     else if (!strcmp(argv[a], "-c") && a + 3 < argc) { cx = atof(argv[a + 1]); cy = atof(argv[a + 2]); cz = atof(argv[a + 3]); a += 3; }
     else if (!strcmp(argv[a], "-solver") && a + 1 < argc) solver_id = atoi(argv[++a]);
@@ -136,6 +141,8 @@ int main(int argc, char **argv) {
     if (nx == 1 || ny == 1 || nz == 1) values[0] = 8.0;
     if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
     A = GenerateLaplacian27pt(MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+  } else if (rotate) {
+    A = GenerateRotate7pt(MPI_COMM_WORLD, nx, ny, 1, 1, 0, 0, alpha, eps);  /* ij.c:9198 */
   } else if (difconv) {
     difconv_values(nx, ny, nz, cx, cy, cz, ax, ay, az, atype, values);  /* ij.c:8266-8409 */
     A = GenerateDifConv(MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
@@ -151,7 +158,7 @@ int main(int argc, char **argv) {
   if (!A) { fprintf(stderr, "ij_b200: could not build the operator\n"); return 1; }
   HYPRE_BigInt M, N;
   HYPRE_ParCSRMatrixGetDims(A, &M, &N);
-  printf("  %s%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", difconv && !stencil27 ? "Convection-Diffusion" : "Laplacian",
+  printf("  %s%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", rotate ? "Rotate 7pt" : difconv && !stencil27 ? "Convection-Diffusion" : "Laplacian",
          stencil27 ? " 27pt" : "", nx, ny, nz, M);
 
   /* rhs = 1, x0 = 0 (the driver's default build_rhs_type 2 / build_x0_type) */

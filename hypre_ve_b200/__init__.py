@@ -58,6 +58,7 @@ SIGNATURES = {
     "b200_generate_laplacian": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_laplacian27": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_difconv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_generate_rotate7pt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _d, _d, C.POINTER(_vp)]),
     "b200_ij_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
     "b200_ij_destroy": (_i, [_vp, _vp]),
     "b200_ij_set_values": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _ip]),
@@ -108,6 +109,7 @@ SIGNATURES = {
     "b200_comm_size": (_i, [_vp]),
     "b200_dist_generate_laplacian": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_dist_generate_difconv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
+    "b200_dist_generate_rotate7pt": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, C.POINTER(_vp)]),
     "b200_dist_matrix_destroy": (_i, [_vp, _vp]),
     "b200_dist_matrix_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "b200_dist_matrix_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -331,6 +333,13 @@ class ParCsr:
         v = (C.c_double * 7)(*difconv_values(nx, ny, nz, c, a, atype))
         out = _vp()
         _chk(_lib.b200_generate_difconv(handle.p, nx, ny, nz, P, Q, R, p, q, r, v, C.byref(out)))
+        return cls(handle, out)
+
+    @classmethod
+    def rotate7pt(cls, handle, nx, ny, alpha, eps, P=1, Q=1, p=0, q=0):
+        """`ij -rotate -n nx ny -alpha A -eps E`: GenerateRotate7pt (par_rotate_7pt.c:15), 2-D rotated anisotropy"""
+        out = _vp()
+        _chk(_lib.b200_generate_rotate7pt(handle.p, nx, ny, P, Q, p, q, alpha, eps, C.byref(out)))
         return cls(handle, out)
 
     @classmethod
@@ -664,6 +673,13 @@ class DistMatrix:
         v = (C.c_double * 7)(*difconv_values(nx, ny, nz, c, a, atype))
         out = _vp()
         _chk(_lib.b200_dist_generate_difconv(handle.p, comm.p, nx, ny, nz, P, Q, R, v, C.byref(out)))
+        return cls(handle, comm, out)
+
+    @classmethod
+    def rotate7pt(cls, handle, comm, nx, ny, P, Q, alpha, eps):
+        """GenerateRotate7pt on the P x Q process grid (par_rotate_7pt.c:15)"""
+        out = _vp()
+        _chk(_lib.b200_dist_generate_rotate7pt(handle.p, comm.p, nx, ny, P, Q, alpha, eps, C.byref(out)))
         return cls(handle, comm, out)
 
     @property

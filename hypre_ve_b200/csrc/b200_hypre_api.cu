@@ -429,6 +429,19 @@ HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny,
   if (b200_generate_laplacian(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateLaplacian"); return nullptr; }
   return wrap_generated(A, (long long)nx * ny * nz);
 }
+HYPRE_ParCSRMatrix GenerateRotate7pt(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int p, HYPRE_Int q,
+                                     HYPRE_Real alpha, HYPRE_Real eps) {                             // par_rotate_7pt.c:15
+  b200_handle h = handle();
+  if (!h) return nullptr;
+  if (P * Q != 1) {
+    fprintf(stderr, "hypre_b200: GenerateRotate7pt through the HYPRE API is single-rank; use b200_dist_generate_rotate7pt\n");
+    err(HYPRE_ERROR_GENERIC);
+    return nullptr;
+  }
+  b200_parcsr A = nullptr;
+  if (b200_generate_rotate7pt(h, nx, ny, P, Q, p, q, alpha, eps, &A)) { err_b200("GenerateRotate7pt"); return nullptr; }
+  return wrap_generated(A, (long long)nx * ny);
+}
 HYPRE_ParCSRMatrix GenerateDifConv(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int R,
                                    HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value) {     // par_difconv.c:15
   b200_handle h = handle();

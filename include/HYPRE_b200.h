@@ -81,6 +81,9 @@ HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_B
 /* parcsr_ls/par_difconv.c:15: value[7] = centre, x-, y-, z-, x+, y+, z+ (ij.c:8266-8409 computes them from -c, -a, -atype) */
 HYPRE_ParCSRMatrix GenerateDifConv(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,
                                    HYPRE_Int R, HYPRE_Int p, HYPRE_Int q, HYPRE_Int r, HYPRE_Real *value);
+/* parcsr_ls/par_rotate_7pt.c:15: 2-D rotated anisotropic diffusion, alpha in degrees (ij -rotate -alpha .. -eps ..) */
+HYPRE_ParCSRMatrix GenerateRotate7pt(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_Int P, HYPRE_Int Q, HYPRE_Int p, HYPRE_Int q,
+                                     HYPRE_Real alpha, HYPRE_Real eps);
 HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix matrix);
 HYPRE_Int HYPRE_ParCSRMatrixGetDims(HYPRE_ParCSRMatrix matrix, HYPRE_BigInt *M, HYPRE_BigInt *N);
 HYPRE_Int HYPRE_ParCSRMatrixGetLocalRange(HYPRE_ParCSRMatrix matrix, HYPRE_BigInt *row_start, HYPRE_BigInt *row_end,

@@ -100,6 +100,11 @@ int b200_generate_laplacian27(b200_handle h, int nx, int ny, int nz, int P, int 
  * nonsymmetric unless values[k] == values[k+3]. */
 int b200_generate_difconv(b200_handle h, int nx, int ny, int nz, int P, int Q, int R,
                           int p, int q, int r, const double values[7], b200_parcsr *A);
+/* GenerateRotate7pt (parcsr_ls/par_rotate_7pt.c:15-400): the 2-D rotated anisotropic diffusion operator
+ * -(c^2 + eps s^2) u_xx - 2 (1 - eps) s c u_xy - (s^2 + eps c^2) u_yy, c = cos(alpha), s = sin(alpha), alpha in degrees,
+ * 7-point stencil with entry order centre, (-1,-1), (0,-1), (-1,0), (+1,0), (0,+1), (+1,+1); P x Q process grid */
+int b200_generate_rotate7pt(b200_handle h, int nx, int ny, int P, int Q, int p, int q, double alpha, double eps,
+                            b200_parcsr *A);
 
 /* ---- IJ assembly on the device (IJ_mv/IJMatrix_parcsr.c:697-1186 SetValues, :1188 AddToValues, :2774-3080 Assemble) ----
  * SetValues / AddToValues take HOST arrays (global row / column indices) and only append validated records to a pinned
@@ -259,6 +264,9 @@ int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int
 /* GenerateDifConv on the process grid (par_difconv.c:15): values[7] = centre, x-, y-, z-, x+, y+, z+ */
 int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
                                const double values[7], b200_dist_matrix *A);
+/* GenerateRotate7pt on a P x Q process grid, rank -> (p, q) as ij.c:9190-9191 */
+int b200_dist_generate_rotate7pt(b200_handle h, b200_comm c, int nx, int ny, int P, int Q, double alpha, double eps,
+                                 b200_dist_matrix *A);
 int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix A);
 int b200_dist_matrix_info(b200_dist_matrix A, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
                           int *n_ghost, int *first_col, int *global_cols);

@@ -47,11 +47,16 @@ static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
       for (iz = 0; iz < nz; iz++) for (iy = 0; iy < ny; iy++) for (ix = 0; ix < nx; ix++, row++)
       {
          if (pass) A.i[row] = cnt;
-         int ns = pt27 ? 27 : 7;
+         int ns = pt27 == 1 ? 27 : 7;
          for (k = 0; k < ns; k++)
          {
             int dx, dy, dz; double val;
-            if (!pt27)
+            if (pt27 == 2)
+            {  /* GenerateRotate7pt (par_rotate_7pt.c:228-350): centre, (-1,-1), (0,-1), (-1,0), (+1,0), (0,+1), (+1,+1) */
+               static const int rx[7] = {0, -1, 0, -1, 1, 0, 1}, ry[7] = {0, -1, -1, 0, 0, 1, 1}, rv[7] = {0, 3, 2, 1, 1, 2, 3};
+               dx = rx[k]; dy = ry[k]; dz = 0; val = v[rv[k]];
+            }
+            else if (!pt27)
             {
                static const int ox[7] = {0, 0, 0, -1, 1, 0, 0}, oy[7] = {0, 0, -1, 0, 0, 1, 0}, oz[7] = {0, -1, 0, 0, 0, 0, 1};
                static const int vi[7] = {0, 3, 2, 1, 4, 5, 6};   /* par_difconv.c:247-330: lower and upper coefficients separate */
@@ -1104,7 +1109,8 @@ int main(int argc, char **argv)
 {
    int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1, perturb = 0;
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0, ax = 1, ay = 1, az = 1;
-   int difconv = 0, atype = 0, solver_id = 1, k_dim = 5;
+   int difconv = 0, atype = 0, solver_id = 1, k_dim = 5, rotate = 0;
+   double rot_alpha = 0., rot_eps = 1.;
    const char *ofile = NULL;
    for (i = 1; i < argc; i++)
    {
@@ -1113,6 +1119,9 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
       else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);     /* 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB */
       else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-rotate")) rotate = 1;
+      else if (!strcmp(argv[i], "-alpha")) rot_alpha = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-eps")) rot_eps = atof(argv[++i]);
       else if (!strcmp(argv[i], "-difconv")) difconv = 1;
       else if (!strcmp(argv[i], "-a")) { ax = atof(argv[++i]); ay = atof(argv[++i]); az = atof(argv[++i]); }
       else if (!strcmp(argv[i], "-atype")) atype = atoi(argv[++i]);
@@ -1142,7 +1151,14 @@ int main(int argc, char **argv)
    if (pt27) { v[0] = 26.0; if (nx == 1 || ny == 1 || nz == 1) v[0] = 8.0; if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) v[0] = 2.0; v[1] = -1.; }
    else { v[1] = -cx; v[2] = -cy; v[3] = -cz; v[0] = 0.; if (nx > 1) v[0] += 2.0 * cx; if (ny > 1) v[0] += 2.0 * cy; if (nz > 1) v[0] += 2.0 * cz; v[4] = v[1]; v[5] = v[2]; v[6] = v[3]; }
    if (difconv && !pt27) { double c[3] = { cx, cy, cz }, a[3] = { ax, ay, az }; difconv_values(nx, ny, nz, c, a, atype, v); }
-   csr_t A = gen_laplace(nx, ny, nz, pt27, v);
+   if (rotate)
+   {  /* par_rotate_7pt.c:62-73 */
+      double pi = 4.0 * atan(1.0), xr = pi * rot_alpha / 180.0, sn = sin(xr), cs = cos(xr);
+      double ac = -(cs * cs + rot_eps * sn * sn), bc = 2.0 * (1.0 - rot_eps) * sn * cs, cc = -(sn * sn + rot_eps * cs * cs);
+      if (nz != 1) { fprintf(stderr, "-rotate is two-dimensional: -n nx ny 1\n"); return 2; }
+      v[0] = -2 * (2 * ac + bc + 2 * cc); v[1] = 2 * ac + bc; v[2] = bc + 2 * cc; v[3] = -bc;
+   }
+   csr_t A = gen_laplace(nx, ny, nz, rotate ? 2 : pt27, v);
    int N = A.n;
    if (perturb) perturb_operator(N, A.i, A.j, A.a, (unsigned) perturb);
    double *b = (double *) xmalloc(sizeof(double) * N), *x = (double *) xcalloc(N, sizeof(double));

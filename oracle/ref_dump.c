@@ -16,6 +16,7 @@
  * Flags follow ij.c's spelling: -n nx ny nz, -27pt, -c cx cy cz, -pmis, -rlx T,
  * -Pmx K, -agg_nl L, -mod_rap2 B, -keepT B, -th theta, -tol t, -interptype I,
  * -mxrs r (max_row_sum), -o FILE, -matvec K (time K SpMVs, ij -solver -1 analogue),
+ * -rotate -alpha A -eps E (GenerateRotate7pt, 2-D: -n nx ny 1),
  * -ijbuild MODE [-noamg] (operator re-assembled through the reference's HYPRE_IJMatrix interface),
  * -solver 1|3|9 (AMG-PCG, AMG-GMRES with -k K, AMG-BiCGSTAB: ij.c:5298-5330, :6364-6380),
  * -difconv [-a ax ay az] [-atype T] (GenerateDifConv, nonsymmetric), -nodump (timing only), -ns / -ns_coarse / -mu / -fmg (cycle shape), -perturb SEED (non-Laplacian values, see below).
@@ -202,6 +203,7 @@ int main(int argc, char **argv)
    int ns = 1, ns_coarse = 1, mu = 1, fmg = 0, perturb = 0;     /* ij.c: -ns, -ns_coarse, -mu, -fmg */
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0;
    int difconv = 0, atype = 0;                                   /* ij.c: -difconv, -a ax ay az, -atype */
+   int rotate = 0; double alpha = 0., eps = 1.;                  /* ij.c: -rotate -alpha A -eps E (2-D: -n nx ny 1) */
    int ij_mode = 0, noamg = 0;                                   /* -ijbuild MODE (see ijbuild above), -noamg: dump A0 only */
    int solver_id = 1, k_dim = 5;                                 /* ij.c: -solver 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB; -k */
    double ax = 1, ay = 1, az = 1;
@@ -215,6 +217,9 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-difconv")) difconv = 1;
       else if (!strcmp(argv[i], "-a")) { ax = atof(argv[++i]); ay = atof(argv[++i]); az = atof(argv[++i]); }
       else if (!strcmp(argv[i], "-atype")) atype = atoi(argv[++i]);
+      else if (!strcmp(argv[i], "-rotate")) rotate = 1;
+      else if (!strcmp(argv[i], "-alpha")) alpha = atof(argv[++i]);
+      else if (!strcmp(argv[i], "-eps")) eps = atof(argv[++i]);
       else if (!strcmp(argv[i], "-ijbuild")) ij_mode = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-noamg")) noamg = 1;
       else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);
@@ -255,6 +260,11 @@ int main(int argc, char **argv)
       if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
       values[1] = -1.;
       A = (HYPRE_ParCSRMatrix) GenerateLaplacian27pt(hypre_MPI_COMM_WORLD, nx, ny, nz, 1, 1, 1, 0, 0, 0, values);
+   }
+   else if (rotate)
+   {
+      if (nz != 1) { fprintf(stderr, "-rotate is two-dimensional: -n nx ny 1\n"); return 2; }
+      A = (HYPRE_ParCSRMatrix) GenerateRotate7pt(hypre_MPI_COMM_WORLD, nx, ny, 1, 1, 0, 0, alpha, eps);
    }
    else if (difconv)
    {

@@ -36,6 +36,9 @@ MORE = {
                                                  "-rlx", "18", "-solver", "3", "-k", "3", "-agg_nl", "1"], 1),
     "difconv_11_bicgstab_gs.bin": (["-n", "11", "11", "11", "-difconv", "-a", "2", "1", "0", "-atype", "1", "-pmis", "-solver", "9"], 1),
     "lap7_11_gmres_gs1314.bin": (["-n", "11", "11", "11", "-pmis", "-solver", "3"], 1),
+    # 2-D rotated anisotropic diffusion (GenerateRotate7pt): positive off-diagonals, strong diagonal coupling
+    "rotate_24x20_a45_e001_rlx18.bin": (["-n", "24", "20", "1", "-rotate", "-alpha", "45", "-eps", "0.001", "-pmis", "-rlx", "18"], 1),
+    "rotate_20x20_a30_e01_agg1_gs.bin": (["-n", "20", "20", "1", "-rotate", "-alpha", "30", "-eps", "0.01", "-pmis", "-agg_nl", "1"], 1),
 }
 if __name__ == "__main__":
     env = dict(os.environ, OMP_NUM_THREADS="1")

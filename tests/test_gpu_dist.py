@@ -61,7 +61,9 @@ def dist_case(nranks, grid, dims, stencil=7, solve=True, solver=1, **params):
     P, Q, R = grid
 
     def fn(r, h, c):
-        if isinstance(stencil, dict):       # GenerateDifConv with these -c / -a / -atype values (nonsymmetric)
+        if isinstance(stencil, dict) and "alpha" in stencil:     # GenerateRotate7pt, two-dimensional (nz = R = 1)
+            A = hb.DistMatrix.rotate7pt(h, c, nx, ny, P, Q, stencil["alpha"], stencil["eps"])
+        elif isinstance(stencil, dict):       # GenerateDifConv with these -c / -a / -atype values (nonsymmetric)
             A = hb.DistMatrix.difconv(h, c, nx, ny, nz, P, Q, R, **stencil)
         else:
             A = hb.DistMatrix.laplacian(h, c, nx, ny, nz, P, Q, R, stencil)
@@ -173,6 +175,31 @@ def test_nrank_gmres_and_bicgstab_equal_single_gpu(handle, nranks, grid, dims, g
     """b200_dist_gmres_solve / b200_dist_bicgstab_solve: the loops of b200_krylov.cu over the row-partitioned operator and
     the distributed cycle; iteration count equal to the single-GPU run on the gathered matrix, history to 1e-10"""
     check_against_single_gpu(handle, nranks, grid, dims, gen, solver=solver)
+
+
+@pytest.mark.parametrize("nranks,grid,dims,gen", [
+    (2, (2, 1, 1), (14, 12, 1), dict(alpha=45.0, eps=0.001)),
+    (4, (2, 2, 1), (17, 16, 1), dict(alpha=30.0, eps=0.01)),
+    (3, (1, 3, 1), (12, 19, 1), dict(alpha=120.0, eps=0.1)),
+    (6, (3, 2, 1), (20, 18, 1), dict(alpha=60.0, eps=0.05)),
+])
+def test_nrank_rotate7pt_equals_single_gpu(handle, nranks, grid, dims, gen):
+    """GenerateRotate7pt on a P x Q process grid: diagonal neighbours cross box corners (hypre_map2 with p-1, q-1);
+    N-rank hierarchy bit-identical to the single-GPU hierarchy of the gathered matrix"""
+    check_against_single_gpu(handle, nranks, grid, dims, gen, ModuleRAP2=0)
+
+
+def test_yslab_rotate7pt_equals_reference_cpu_build():
+    """(1, N) slabs keep the lexicographic numbering of the 2-D grid: gathered operator and hierarchy = the reference's"""
+    d, _ = refio.run_ref(["-n", 18, 20, 1, "-rotate", "-alpha", 45, "-eps", 0.001, "-pmis", "-rlx", 18, "-keepT", 1])
+    res = dist_case(4, (1, 4, 1), (18, 20, 1), dict(alpha=45.0, eps=0.001), ModuleRAP2=0)
+    nl = int(d["hdr"][3])
+    assert len(res[0]["levels"]) == nl
+    for l in range(nl):
+        i, j, a = gather([r["levels"][l]["A"] for r in res])
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), l
+    assert res[0]["its"] == int(d["hdr"][4])
 
 
 def test_zslab_difconv_gmres_equals_reference_cpu_build():

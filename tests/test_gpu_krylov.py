@@ -267,3 +267,60 @@ def test_krylov_drivers_through_the_public_api_match_the_reference_driver(flags,
     assert rrc == 0, rout
     rits, rrel = result(rout, key)
     assert its == rits and abs(rel - rrel) <= 1e-12 + 1e-5 * rrel, (its, rits, rel, rrel)      # true-residual floor, see check_solve
+
+
+# ---- GenerateRotate7pt (2-D rotated anisotropic diffusion, `ij -rotate`) -------------------------------------------
+ROTATE = [
+    (14, 12, 45.0, 0.001), (20, 17, 30.0, 0.01), (16, 16, 0.0, 1.0), (9, 23, 60.0, 0.1), (1, 12, 10.0, 0.5), (13, 1, 80.0, 0.2),
+    (40, 36, 135.0, 0.001),
+]
+
+
+@pytest.mark.parametrize("nx,ny,alpha,eps", ROTATE)
+def test_rotate7pt_generator_and_hierarchy_equal_the_reference(handle, nx, ny, alpha, eps):
+    """b200_generate_rotate7pt: entry order centre, (-1,-1), (0,-1), (-1,0), (+1,0), (0,+1), (+1,+1) and the four
+    coefficients from (alpha, eps) bit-identical to GenerateRotate7pt; the operator has POSITIVE off-diagonals and a
+    diagonal direction of strong coupling: hierarchy bit-identical, PCG history to 1e-10"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(["-n", nx, ny, 1, "-rotate", "-alpha", alpha, "-eps", eps, "-pmis", "-rlx", 18, "-keepT", 1])
+    ri, rj, ra, _ = refio.csr(d, "A", 0)
+    A = hb.ParCsr.rotate7pt(handle, nx, ny, alpha, eps)
+    i, j, a = A.diag.download()
+    assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra)
+    amg = hb.Amg(handle, RelaxType=18, ModuleRAP2=0)
+    amg.setup(A)
+    check_hierarchy(amg, d)
+    its, rel, norms, x = solve_with(handle, 1, A, amg, nx * ny)
+    assert its == int(d["hdr"][4])
+    assert np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    assert np.max(np.abs(x - d["x"])) / np.max(np.abs(d["x"])) < 1e-9
+    amg.destroy(); A.destroy()
+
+
+@pytest.mark.parametrize("name,nx,ny,alpha,eps,params", [
+    ("rotate_24x20_a45_e001_rlx18.bin", 24, 20, 45.0, 0.001, dict(RelaxType=18)),
+    ("rotate_20x20_a30_e01_agg1_gs.bin", 20, 20, 30.0, 0.01, dict(RelaxType=13, RelaxTypeUp=14, AggNumLevels=1)),
+])
+def test_rotate7pt_committed_goldens(handle, name, nx, ny, alpha, eps, params):
+    import hypre_ve_b200 as hb
+    d = refio.read_dump(os.path.join(refio.GOLDEN, name))
+    A = hb.ParCsr.rotate7pt(handle, nx, ny, alpha, eps)
+    amg = hb.Amg(handle, ModuleRAP2=0, **params)
+    amg.setup(A)
+    check_hierarchy(amg, d)
+    its, rel, norms, x = solve_with(handle, 1, A, amg, nx * ny)
+    assert its == int(d["hdr"][4]) and np.max(np.abs(norms - d["norms"])) / d["norms"][0] < 1e-10
+    amg.destroy(); A.destroy()
+
+
+def test_rotate7pt_through_the_public_api_matches_the_reference_driver():
+    from hypre_ve_b200 import build as b
+    exe = b.build_examples()
+    for flags in (["-rotate", "-n", "24", "20", "-alpha", "45", "-eps", "0.001", "-solver", "1", "-pmis", "-rlx", "18"],
+                  ["-n", "30", "30", "-rotate", "-alpha", "20", "-eps", "0.05", "-solver", "1", "-pmis"]):
+        rc, out = run([exe] + flags)
+        assert rc == 0, out
+        rrc, rout = run([REF_IJ] + flags, dict(os.environ, OMP_NUM_THREADS="1"))
+        assert rrc == 0, rout
+        (its, rel), (rits, rrel) = result(out, "Iterations"), result(rout, "Iterations")
+        assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)

@@ -72,6 +72,9 @@ GOLDEN_MORE = {
                                                  "-solver", 3, "-k", 3, "-agg_nl", 1], True),
     "difconv_11_bicgstab_gs.bin": (["-n", 11, 11, 11, "-difconv", "-a", 2, 1, 0, "-atype", 1, "-pmis", "-solver", 9], True),
     "lap7_11_gmres_gs1314.bin": (["-n", 11, 11, 11, "-pmis", "-solver", 3], True),
+    # GenerateRotate7pt (par_rotate_7pt.c): 2-D rotated anisotropy
+    "rotate_24x20_a45_e001_rlx18.bin": (["-n", 24, 20, 1, "-rotate", "-alpha", 45, "-eps", 0.001, "-pmis", "-rlx", 18], True),
+    "rotate_20x20_a30_e01_agg1_gs.bin": (["-n", 20, 20, 1, "-rotate", "-alpha", 30, "-eps", 0.01, "-pmis", "-agg_nl", 1], True),
 }
 
 
