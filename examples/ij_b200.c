@@ -78,7 +78,8 @@ static void difconv_values(int nx, int ny, int nz, double cx, double cy, double 
 }
 
 int main(int argc, char **argv) {
-  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0, difconv = 0, atype = 0, k_dim = 5, rotate = 0;
+  int nx = 10, ny = 10, nz = 10, solver_id = 1, stencil27 = 0, ijbuild = 0, difconv = 0, atype = 0, k_dim = 5, rotate = 0, print_system = 0;
+  const char *fromfile = NULL;                          /* ij -fromfile NAME: HYPRE_IJMatrixRead(NAME.00000) (ij.c:7504-7540) */
   double cx = 1., cy = 1., cz = 1., ax = 1., ay = 1., az = 1., alpha = 0., eps = 1.;
   /* driver defaults, test/ij.c:203-330 and :1181-1205 */
   int coarsen_type = 10, interp_type = 6, P_max_elmts = 4, relax_type = -1, relax_order = 0, max_levels = 25;
@@ -90,6 +91,8 @@ int main(int argc, char **argv) {
   for (int a = 1; a < argc; a++) {
     if (!strcmp(argv[a], "-laplacian")) ;
     else if (!strcmp(argv[a], "-27pt")) stencil27 = 1;
+    else if (!strcmp(argv[a], "-fromfile") && a + 1 < argc) fromfile = argv[++a];
+    else if (!strcmp(argv[a], "-print")) print_system = 1;               /* ij.c:3169-3188: IJ.out.A, IJ.out.b, IJ.out.x0 */
     else if (!strcmp(argv[a], "-difconv")) difconv = 1;
     else if (!strcmp(argv[a], "-rotate")) rotate = 1;                    /* 2-D: -n nx ny (ij.c:9136-9160) */
     else if (!strcmp(argv[a], "-alpha") && a + 1 < argc) alpha = atof(argv[++a]);
@@ -136,7 +139,12 @@ int main(int argc, char **argv) {
   double values[7];
   HYPRE_ParCSRMatrix A;
   HYPRE_IJMatrix ij_A = NULL;
-  if (stencil27) {
+  if (fromfile) {
+    if (HYPRE_IJMatrixRead(fromfile, MPI_COMM_WORLD, HYPRE_PARCSR, &ij_A)) { fprintf(stderr, "ij_b200: could not read %s.00000\n", fromfile); return 1; }
+    void *o = NULL;
+    HYPRE_IJMatrixGetObject(ij_A, &o);
+    A = (HYPRE_ParCSRMatrix)o;
+  } else if (stencil27) {
     values[0] = 26.0; values[1] = -1.0;                                  /* ij.c:9063-9071 */
     if (nx == 1 || ny == 1 || nz == 1) values[0] = 8.0;
     if (nx * ny == 1 || nx * nz == 1 || ny * nz == 1) values[0] = 2.0;
@@ -158,7 +166,8 @@ int main(int argc, char **argv) {
   if (!A) { fprintf(stderr, "ij_b200: could not build the operator\n"); return 1; }
   HYPRE_BigInt M, N;
   HYPRE_ParCSRMatrixGetDims(A, &M, &N);
-  printf("  %s%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", rotate ? "Rotate 7pt" : difconv && !stencil27 ? "Convection-Diffusion" : "Laplacian",
+  if (fromfile) printf("  FromFile: %s  rows = %d\n", fromfile, M);
+  else printf("  %s%s:   (nx, ny, nz) = (%d, %d, %d)  rows = %d\n", rotate ? "Rotate 7pt" : difconv && !stencil27 ? "Convection-Diffusion" : "Laplacian",
          stencil27 ? " 27pt" : "", nx, ny, nz, M);
 
   /* rhs = 1, x0 = 0 (the driver's default build_rhs_type 2 / build_x0_type) */
@@ -181,6 +190,11 @@ int main(int argc, char **argv) {
   HYPRE_IJVectorGetObject(ij_x, &obj);
   x = (HYPRE_ParVector)obj;
 
+  if (print_system) {
+    if (ij_A) HYPRE_IJMatrixPrint(ij_A, "IJ.out.A"); else hypre_ParCSRMatrixPrintIJ(A, 0, 0, "IJ.out.A");
+    HYPRE_IJVectorPrint(ij_b, "IJ.out.b");
+    HYPRE_IJVectorPrint(ij_x, "IJ.out.x0");
+  }
   int num_iterations = 0;
   double final_res_norm = 0.;
   if (solver_id == -1) {                                                   /* ij.c:3206-3243 */
@@ -361,6 +375,7 @@ int main(int argc, char **argv) {
     fprintf(stderr, "ij_b200: solver %d is not on the B200 path (0 AMG, 1 AMG-PCG, 2 DS-PCG, 3 AMG-GMRES, 4 DS-GMRES, 9 AMG-BiCGSTAB, 10 DS-BiCGSTAB, -1 matvec)\n", solver_id);
     return 2;
   }
+  if (print_system && solver_id >= 0) HYPRE_IJVectorPrint(ij_x, "IJ.out.x");      /* ij.c:7440-7443 */
   /* read a few solution values back through the IJ interface, as examples/ex5.c does */
   if (solver_id >= 0) {
     int idx[2];

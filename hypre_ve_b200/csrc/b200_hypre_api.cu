@@ -406,6 +406,95 @@ HYPRE_Int HYPRE_IJVectorGetObject(HYPRE_IJVector v, void **object) {
   return g_error_flag;
 }
 
+// ---- on-disk IJ format (HYPRE_IJMatrixRead / Print, HYPRE_IJVectorRead / Print; ij -fromfile / -print) -----------
+// matrix file "<name>.00000": "ilower iupper jlower jupper" then one "i j %.14e" line per entry in storage order
+// (IJ_mv/HYPRE_IJMatrix.c:1144-1300); vector file: "jlower jupper" then "j %.14e" lines (HYPRE_IJVector.c:590-710).
+static HYPRE_Int print_csr_ij(b200_handle h, b200_parcsr A, int ilower, int iupper, int jlower, int jupper, const char *filename) {
+  char name[512];
+  snprintf(name, sizeof name, "%s.%05d", filename, 0);
+  FILE *f = fopen(name, "w");
+  if (!f) return err_arg(2);
+  int nr = 0, nd = 0, no = 0, nco = 0;
+  b200_parcsr_local_rows(A, &nr, &nd, &no, &nco);
+  std::vector<int> I((size_t)nr + 1, 0), J((size_t)(nd ? nd : 1));
+  std::vector<double> V((size_t)(nd ? nd : 1));
+  if (b200_csr_download(h, b200_parcsr_diag(A), I.data(), J.data(), V.data())) { fclose(f); return err_b200("HYPRE_IJMatrixPrint"); }
+  fprintf(f, "%d %d %d %d\n", ilower, iupper, jlower, jupper);
+  for (int i = 0; i < nr; i++)
+    for (int k = I[i]; k < I[i + 1]; k++) fprintf(f, "%d %d %.14e\n", ilower + i, jlower + J[k], V[k]);
+  fclose(f);
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJMatrixPrint(HYPRE_IJMatrix m, const char *filename) {
+  if (!m || m->object_type != HYPRE_PARCSR || !m->object) return err_arg(1);
+  if (!filename) return err_arg(2);
+  NEED_HANDLE();
+  return print_csr_ij(h, m->object->A, m->ilower, m->iupper, m->jlower, m->jupper, filename);
+}
+HYPRE_Int HYPRE_IJMatrixRead(const char *filename, MPI_Comm comm, HYPRE_Int type, HYPRE_IJMatrix *matrix_ptr) {
+  if (!filename) return err_arg(1);
+  if (!matrix_ptr) return err_arg(4);
+  char name[512];
+  snprintf(name, sizeof name, "%s.%05d", filename, 0);
+  FILE *f = fopen(name, "r");
+  if (!f) return err_arg(1);
+  int ilower, iupper, jlower, jupper;
+  if (fscanf(f, "%d %d %d %d", &ilower, &iupper, &jlower, &jupper) != 4) { fclose(f); fprintf(stderr, "hypre_b200: Error in IJ matrix input file.\n"); return err(HYPRE_ERROR_GENERIC); }
+  HYPRE_IJMatrix m = nullptr;
+  HYPRE_IJMatrixCreate(comm, ilower, iupper, jlower, jupper, &m);
+  HYPRE_IJMatrixSetObjectType(m, type);
+  if (HYPRE_IJMatrixInitialize(m) || !m->ij) { fclose(f); return g_error_flag; }
+  int II, JJ, ncols = 1, ret;
+  double value;
+  while ((ret = fscanf(f, "%d %d%*[ \t]%le", &II, &JJ, &value)) != EOF) {       // one SetValues per line, as the reference
+    if (ret != 3) { fclose(f); fprintf(stderr, "hypre_b200: Error in IJ matrix input file.\n"); return err(HYPRE_ERROR_GENERIC); }
+    HYPRE_IJMatrixSetValues(m, 1, &ncols, &II, &JJ, &value);                      // (rows outside [ilower, iupper] are rejected there)
+  }
+  fclose(f);
+  HYPRE_IJMatrixAssemble(m);
+  *matrix_ptr = m;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorPrint(HYPRE_IJVector v, const char *filename) {
+  if (!v || !v->initialized || !v->object) return err_arg(1);
+  if (!filename) return err_arg(2);
+  NEED_HANDLE();
+  char name[512];
+  snprintf(name, sizeof name, "%s.%05d", filename, 0);
+  FILE *f = fopen(name, "w");
+  if (!f) return err_arg(2);
+  if (!v->host.empty() && b200_memcpy_d2h(h, v->host.data(), v->object->d, sizeof(double) * v->host.size())) { fclose(f); return err_b200("HYPRE_IJVectorPrint"); }
+  fprintf(f, "%d %d\n", v->jlower, v->jupper);
+  for (int j = v->jlower; j <= v->jupper; j++) fprintf(f, "%d %.14e\n", j, v->host[(size_t)(j - v->jlower)]);
+  fclose(f);
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_IJVectorRead(const char *filename, MPI_Comm comm, HYPRE_Int type, HYPRE_IJVector *vector_ptr) {
+  if (!filename) return err_arg(1);
+  if (!vector_ptr) return err_arg(4);
+  char name[512];
+  snprintf(name, sizeof name, "%s.%05d", filename, 0);
+  FILE *f = fopen(name, "r");
+  if (!f) return err_arg(1);
+  int jlower, jupper;
+  if (fscanf(f, "%d %d", &jlower, &jupper) != 2) { fclose(f); fprintf(stderr, "hypre_b200: Error in IJ vector input file.\n"); return err(HYPRE_ERROR_GENERIC); }
+  HYPRE_IJVector v = nullptr;
+  HYPRE_IJVectorCreate(comm, jlower, jupper, &v);
+  HYPRE_IJVectorSetObjectType(v, type);
+  if (HYPRE_IJVectorInitialize(v)) { fclose(f); return g_error_flag; }
+  int j, ret;
+  double value;
+  while ((ret = fscanf(f, "%d%*[ \t]%le", &j, &value)) != EOF) {
+    if (ret != 2) { fclose(f); fprintf(stderr, "hypre_b200: Error in IJ vector input file.\n"); return err(HYPRE_ERROR_GENERIC); }
+    if (j < jlower || j > jupper) HYPRE_IJVectorAddToValues(v, 1, &j, &value);
+    else HYPRE_IJVectorSetValues(v, 1, &j, &value);
+  }
+  fclose(f);
+  HYPRE_IJVectorAssemble(v);
+  *vector_ptr = v;
+  return g_error_flag;
+}
+
 // ---- ParCSR matrix / vector -----------------------------------------------------------------
 static HYPRE_ParCSRMatrix wrap_generated(b200_parcsr A, long long gr) {
   hypre_ParCSRMatrix_struct *P = new hypre_ParCSRMatrix_struct();
@@ -467,6 +556,13 @@ HYPRE_ParCSRMatrix GenerateLaplacian27pt(MPI_Comm, HYPRE_BigInt nx, HYPRE_BigInt
   b200_parcsr A = nullptr;
   if (b200_generate_laplacian27(h, nx, ny, nz, P, Q, R, p, q, r, value, &A)) { err_b200("GenerateLaplacian27pt"); return nullptr; }
   return wrap_generated(A, (long long)nx * ny * nz);
+}
+// hypre_ParCSRMatrixPrintIJ (parcsr_mv/par_csr_matrix.c:696-830): the same file format from a ParCSR object
+HYPRE_Int hypre_ParCSRMatrixPrintIJ(HYPRE_ParCSRMatrix A, HYPRE_Int base_i, HYPRE_Int base_j, const char *filename) {
+  if (!A || !A->A) return err_arg(1);
+  if (!filename) return err_arg(4);
+  NEED_HANDLE();
+  return print_csr_ij(h, A->A, base_i, base_i + A->global_rows - 1, base_j, base_j + A->global_cols - 1, filename);
 }
 HYPRE_Int HYPRE_ParCSRMatrixDestroy(HYPRE_ParCSRMatrix A) {
   if (!A) return err_arg(1);

@@ -63,6 +63,12 @@ HYPRE_Int HYPRE_IJMatrixAddToValues(HYPRE_IJMatrix matrix, HYPRE_Int nrows, HYPR
                                     const HYPRE_BigInt *cols, const HYPRE_Complex *values);
 HYPRE_Int HYPRE_IJMatrixAssemble(HYPRE_IJMatrix matrix);
 HYPRE_Int HYPRE_IJMatrixGetObject(HYPRE_IJMatrix matrix, void **object);
+/* on-disk IJ format, file "<filename>.00000" (IJ_mv/HYPRE_IJMatrix.c:1144-1300; ij -fromfile / -print): the header
+ * "ilower iupper jlower jupper", then one "i j %.14e" line per entry in storage order */
+HYPRE_Int HYPRE_IJMatrixRead(const char *filename, MPI_Comm comm, HYPRE_Int type, HYPRE_IJMatrix *matrix);
+HYPRE_Int HYPRE_IJMatrixPrint(HYPRE_IJMatrix matrix, const char *filename);
+/* parcsr_mv/par_csr_matrix.c:696: the same format from a ParCSR object (the reference driver calls this internal) */
+HYPRE_Int hypre_ParCSRMatrixPrintIJ(HYPRE_ParCSRMatrix matrix, HYPRE_Int base_i, HYPRE_Int base_j, const char *filename);
 HYPRE_Int HYPRE_IJVectorCreate(MPI_Comm comm, HYPRE_BigInt jlower, HYPRE_BigInt jupper, HYPRE_IJVector *vector);
 HYPRE_Int HYPRE_IJVectorDestroy(HYPRE_IJVector vector);
 HYPRE_Int HYPRE_IJVectorSetObjectType(HYPRE_IJVector vector, HYPRE_Int type);
@@ -72,6 +78,9 @@ HYPRE_Int HYPRE_IJVectorAddToValues(HYPRE_IJVector vector, HYPRE_Int nvalues, co
 HYPRE_Int HYPRE_IJVectorGetValues(HYPRE_IJVector vector, HYPRE_Int nvalues, const HYPRE_BigInt *indices, HYPRE_Complex *values);
 HYPRE_Int HYPRE_IJVectorAssemble(HYPRE_IJVector vector);
 HYPRE_Int HYPRE_IJVectorGetObject(HYPRE_IJVector vector, void **object);
+/* "jlower jupper" then "j %.14e" lines (IJ_mv/HYPRE_IJVector.c:590-710) */
+HYPRE_Int HYPRE_IJVectorRead(const char *filename, MPI_Comm comm, HYPRE_Int type, HYPRE_IJVector *vector);
+HYPRE_Int HYPRE_IJVectorPrint(HYPRE_IJVector vector, const char *filename);
 
 /* parcsr_ls/par_laplace.c:15, par_laplace_27pt.c:15 (problem generators used by ij.c:7808,:9084) */
 HYPRE_ParCSRMatrix GenerateLaplacian(MPI_Comm comm, HYPRE_BigInt nx, HYPRE_BigInt ny, HYPRE_BigInt nz, HYPRE_Int P, HYPRE_Int Q,

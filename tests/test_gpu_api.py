@@ -212,3 +212,36 @@ def test_matvec_loop(exe):
                 tot += (6 - nb) ** 2
     got = float(re.search(r"<Ab, Ab> = (\S+)", out).group(1))
     assert got == tot
+
+
+@pytest.mark.parametrize("flags", [
+    ["-difconv", "-n", "7", "6", "5", "-solver", "1", "-pmis", "-rlx", "18"],
+    ["-laplacian", "-27pt", "-n", "6", "6", "6", "-solver", "1", "-pmis"],
+    ["-rotate", "-n", "12", "11", "-alpha", "30", "-eps", "0.01", "-solver", "1", "-pmis", "-rlx", "18"],
+])
+def test_ij_file_format_print_and_read(exe, tmp_path, flags):
+    """ij -print / -fromfile: HYPRE_IJMatrixPrint / hypre_ParCSRMatrixPrintIJ / HYPRE_IJVectorPrint write the files the
+    reference driver writes (byte-identical for the operator, the right-hand side and the initial guess; the solution
+    to 1e-9), and HYPRE_IJMatrixRead of the REFERENCE's file gives the same solve as the reference reading it"""
+    import numpy as np
+    assert os.path.exists(REF_IJ)
+    mine, ref = tmp_path / "mine", tmp_path / "ref"
+    mine.mkdir(); ref.mkdir()
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p1 = subprocess.run([exe] + flags + ["-print"], cwd=mine, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    p2 = subprocess.run([REF_IJ] + flags + ["-print"], cwd=ref, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    assert p1.returncode == 0 and p2.returncode == 0, p1.stdout + p2.stdout
+    for name in ("IJ.out.A.00000", "IJ.out.b.00000", "IJ.out.x0.00000"):
+        assert (mine / name).read_bytes() == (ref / name).read_bytes(), name
+    xm = np.loadtxt(mine / "IJ.out.x.00000", skiprows=1)
+    xr = np.loadtxt(ref / "IJ.out.x.00000", skiprows=1)
+    assert np.array_equal(xm[:, 0], xr[:, 0]) and np.max(np.abs(xm[:, 1] - xr[:, 1])) < 1e-9 * np.max(np.abs(xr[:, 1]))
+    solver = [f for f in flags if f not in ("-difconv", "-laplacian", "-27pt", "-rotate")]
+    solver = solver[solver.index("-solver"):]
+    q1 = subprocess.run([exe, "-fromfile", str(ref / "IJ.out.A")] + solver, cwd=mine, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    q2 = subprocess.run([REF_IJ, "-fromfile", str(ref / "IJ.out.A")] + solver, cwd=ref, env=env, stdout=subprocess.PIPE,
+                        stderr=subprocess.STDOUT, text=True)
+    assert q1.returncode == 0 and q2.returncode == 0, q1.stdout + q2.stdout
+    (its, rel), (rits, rrel) = result(q1.stdout), result(q2.stdout)
+    assert its == rits and abs(rel / rrel - 1) < 1e-6, (its, rits, rel, rrel)
+    assert result(q1.stdout)[0] == result(p1.stdout)[0]            # 14 printed digits are enough to keep the iteration count
