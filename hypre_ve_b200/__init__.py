@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200_generate_difconv": (_i, [_vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_generate_rotate7pt": (_i, [_vp, _i, _i, _i, _i, _i, _i, _d, _d, C.POINTER(_vp)]),
     "b200_ij_create": (_i, [_vp, _i, _i, _i, _i, C.POINTER(_vp)]),
+    "b200_ij_create_rows": (_i, [_vp, _i, _i, _i, C.POINTER(_vp)]),
     "b200_ij_destroy": (_i, [_vp, _vp]),
     "b200_ij_set_values": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp, _i, _ip]),
     "b200_ij_assemble": (_i, [_vp, _vp, C.POINTER(_vp), _ip]),
@@ -110,6 +111,8 @@ SIGNATURES = {
     "b200_dist_generate_laplacian": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_dist_generate_difconv": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _dp, C.POINTER(_vp)]),
     "b200_dist_generate_rotate7pt": (_i, [_vp, _vp, _i, _i, _i, _i, _d, _d, C.POINTER(_vp)]),
+    "b200_dist_matrix_create_from_host": (_i, [_vp, _vp, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "b200_dist_matrix_create_from_ij": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_dist_matrix_destroy": (_i, [_vp, _vp]),
     "b200_dist_matrix_info": (_i, [_vp, _ip, _ip, _ip, _ip, _ip, _ip, _ip]),
     "b200_dist_matrix_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
@@ -379,11 +382,16 @@ class ParCsr:
 class IJAssembler:
     """HYPRE_IJMatrixSetValues / AddToValues / Assemble on the device (b200_ij_*)"""
 
-    def __init__(self, handle, ilower, iupper, jlower=None, jupper=None):
+    def __init__(self, handle, ilower, iupper, jlower=None, jupper=None, global_cols=None):
+        """global_cols given: the rows [ilower, iupper] of an operator spread over several ranks (global column ids are
+        kept; pass the assembler to DistMatrix.from_ij)"""
         self.h = handle
         self.p = _vp()
-        _chk(_lib.b200_ij_create(handle.p, ilower, iupper, ilower if jlower is None else jlower,
-                                 iupper if jupper is None else jupper, C.byref(self.p)))
+        if global_cols is not None:
+            _chk(_lib.b200_ij_create_rows(handle.p, ilower, iupper, global_cols, C.byref(self.p)))
+        else:
+            _chk(_lib.b200_ij_create(handle.p, ilower, iupper, ilower if jlower is None else jlower,
+                                     iupper if jupper is None else jupper, C.byref(self.p)))
 
     def set_values(self, ncols, rows, cols, values, add=False):
         ncols = np.ascontiguousarray(ncols, dtype=np.int32)
@@ -673,6 +681,24 @@ class DistMatrix:
         v = (C.c_double * 7)(*difconv_values(nx, ny, nz, c, a, atype))
         out = _vp()
         _chk(_lib.b200_dist_generate_difconv(handle.p, comm.p, nx, ny, nz, P, Q, R, v, C.byref(out)))
+        return cls(handle, comm, out)
+
+    @classmethod
+    def from_rows(cls, handle, comm, indptr, indices_global, data):
+        """this rank's contiguous block of rows (global column ids, diagonal first); collective"""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices_global = np.ascontiguousarray(indices_global, dtype=np.int32)
+        data = np.ascontiguousarray(data, dtype=np.float64)
+        out = _vp()
+        _chk(_lib.b200_dist_matrix_create_from_host(handle.p, comm.p, indptr.size - 1, _np_ptr(indptr), _np_ptr(indices_global),
+                                                    _np_ptr(data), C.byref(out)))
+        return cls(handle, comm, out)
+
+    @classmethod
+    def from_ij(cls, handle, comm, assembler):
+        """device-side assembly of this rank's SetValues / AddToValues records, then localization; collective"""
+        out = _vp()
+        _chk(_lib.b200_dist_matrix_create_from_ij(handle.p, comm.p, assembler.p, C.byref(out)))
         return cls(handle, comm, out)
 
     @classmethod

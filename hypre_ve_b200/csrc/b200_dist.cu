@@ -545,6 +545,81 @@ static int dist_generate(b200_handle h, b200_comm c, int nx, int ny, int nz, int
   *out = M;
   return 0;
 }
+// ---- a row-partitioned operator from the caller's own rows -----------------------------------------------------------
+// (what hypre_IJMatrixAssembleParCSR + GenerateDiagAndOffd produce across ranks, IJ_mv/IJMatrix_parcsr.c:2774,
+// parcsr_mv/par_csr_matrix.c:1634: this rank's contiguous block of rows, diagonal entry first, global column ids)
+__global__ void check_rows_kernel(int n, int first_row, int global_cols, const int *__restrict__ A_i, const int *__restrict__ A_j,
+                                  int *__restrict__ bad) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int s = A_i[r], e = A_i[r + 1];
+  if (e > s && A_j[s] != first_row + r) atomicAdd(&bad[0], 1);               // diagonal first (csr_matrix.h invariant)
+  for (int k = s; k < e; k++)
+    if (A_j[k] < 0 || A_j[k] >= global_cols) atomicAdd(&bad[1], 1);
+}
+static int dist_from_global_rows(b200_handle h, b200_comm c, b200_csr G, b200_dist_matrix *out) {
+  const int nr = b200_comm_size(c), me = b200_comm_rank(c);
+  b200_dist_matrix M = new b200_dist_matrix_s();
+  M->G = G;
+  M->n = G->nrows;
+  B200_TRY(gather_starts(h, c, M->n, &M->row_starts));
+  M->first_row = M->row_starts[me];
+  M->global_rows = M->global_cols = M->row_starts[nr];
+  M->col_starts = M->row_starts;
+  M->first_col = M->first_row; M->n_owned_cols = M->n;
+  G->ncols = M->global_cols;
+  int *bad = nullptr, hb[2] = {0, 0};
+  B200_TRY(b200_dalloc<int>(h, &bad, 2));
+  B200_CUDA(cudaMemsetAsync(bad, 0, 2 * sizeof(int), h->stream));
+  if (M->n) {
+    check_rows_kernel<<<b200_grid(M->n, 256), 256, 0, h->stream>>>(M->n, M->first_row, M->global_cols, G->i, G->j, bad);
+    B200_LAUNCH_CHECK();
+  }
+  B200_CUDA(cudaMemcpyAsync(hb, bad, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  B200_TRY(b200_dfree(h, bad));
+  // every rank reaches the collective below even if its own rows are bad: agree on the verdict first
+  int verdict[2] = {hb[0], hb[1]};
+  std::vector<int> all((size_t)2 * nr);
+  B200_TRY(b200_comm_allgather_host(h, c, verdict, 2 * sizeof(int), all.data()));
+  long long bad_diag = 0, bad_col = 0;
+  for (int r = 0; r < nr; r++) { bad_diag += all[2 * r]; bad_col += all[2 * r + 1]; }
+  if (bad_diag) B200_FAIL("dist matrix: a non-empty row does not store its diagonal entry first");
+  if (bad_col) B200_FAIL("dist matrix: column index outside [0, global_rows)");
+  B200_TRY(dist_localize(h, c, M));
+  *out = M;
+  return 0;
+}
+extern "C" int b200_dist_matrix_create_from_host(b200_handle h, b200_comm c, int n_local, const int *h_i, const int *h_j_global,
+                                                 const double *h_a, b200_dist_matrix *out) {
+  if (n_local < 0 || !h_i || !out) B200_FAIL("dist_matrix_create_from_host: bad argument");
+  const int nnz = h_i[n_local];
+  b200_csr G = nullptr;
+  B200_TRY(b200_csr_alloc(h, n_local, 0, nnz, true, &G));
+  B200_CUDA(cudaMemcpyAsync(G->i, h_i, sizeof(int) * ((size_t)n_local + 1), cudaMemcpyHostToDevice, h->stream));
+  if (nnz) {
+    B200_CUDA(cudaMemcpyAsync(G->j, h_j_global, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaMemcpyAsync(G->a, h_a, sizeof(double) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  }
+  B200_CUDA(cudaStreamSynchronize(h->stream));            // the host arrays may be pageable and go out of scope
+  return dist_from_global_rows(h, c, G, out);
+}
+b200_parcsr b200_ij_release_object(b200_ij ij);           // b200_ij.cu
+extern "C" int b200_dist_matrix_create_from_ij(b200_handle h, b200_comm c, b200_ij ij, b200_dist_matrix *out) {
+  if (!ij || !out) B200_FAIL("dist_matrix_create_from_ij: bad argument");
+  b200_parcsr A = nullptr;
+  int missing = 0;
+  B200_TRY(b200_ij_assemble(h, ij, &A, &missing));          // device-side merge of this rank's records (b200_ij.cu)
+  if (missing) B200_FAIL("dist_matrix_create_from_ij: values were set on elements that do not exist");
+  A = b200_ij_release_object(ij);
+  if (!A) B200_FAIL("dist_matrix_create_from_ij: nothing assembled");
+  b200_csr G = A->diag;                                     // rows of this rank, global column ids, diagonal first
+  A->diag = nullptr;
+  B200_TRY(b200_csr_destroy(h, A->offd));
+  delete A;
+  return dist_from_global_rows(h, c, G, out);
+}
+
 extern "C" int b200_dist_generate_laplacian(b200_handle h, b200_comm c, int nx, int ny, int nz, int P, int Q, int R,
                                             int stencil, const double *values, b200_dist_matrix *out) {
   if (stencil != 7 && stencil != 27) B200_FAIL("stencil must be 7 or 27");

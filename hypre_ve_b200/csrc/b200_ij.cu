@@ -19,6 +19,7 @@
 
 struct b200_ij_s {
   int ilower = 0, iupper = -1, jlower = 0, jupper = -1;
+  int diag_shift = 0;          // local row r holds its diagonal in (global) column r + diag_shift
   static constexpr size_t CHUNK = (size_t)1 << 21;      // records per pinned chunk (40 MB)
   int *h_row[2] = {nullptr, nullptr}, *h_col[2] = {nullptr, nullptr}, *h_blk[2] = {nullptr, nullptr};
   double *h_val[2] = {nullptr, nullptr};
@@ -58,7 +59,7 @@ __global__ void gather_kernel(size_t n, const int *__restrict__ perm, const int 
   col_s[i] = col[p]; val_s[i] = val[p]; blk_s[i] = blk[p];
 }
 // replay of the auxiliary-matrix insertion (IJMatrix_parcsr.c:930-1000) for one row, in place on its segment
-__global__ void merge_rows_kernel(int nrows, int jlower, const int *__restrict__ ptr, int *col, double *val, const int *__restrict__ blk,
+__global__ void merge_rows_kernel(int nrows, int diag_shift, const int *__restrict__ ptr, int *col, double *val, const int *__restrict__ blk,
                                   int *__restrict__ cnt, int *__restrict__ dpos) {
   int r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= nrows) return;
@@ -79,7 +80,7 @@ __global__ void merge_rows_kernel(int nrows, int jlower, const int *__restrict__
     if (!found) { col[s + m] = c; val[s + m] = v; m++; }
   }
   for (int q = 0; q < m; q++)
-    if (col[s + q] - jlower == r) dp = q;                 // the LAST entry on the diagonal column (:2974-2977)
+    if (col[s + q] - diag_shift == r) dp = q;               // the LAST entry on the diagonal column (:2974-2977)
   cnt[r] = m;
   dpos[r] = dp;
 }
@@ -166,6 +167,7 @@ extern "C" int b200_ij_create(b200_handle h, int ilower, int iupper, int jlower,
   if (ilower > iupper + 1 || ilower < 0 || jlower > jupper + 1 || jlower < 0) B200_FAIL("ij_create: bad row / column range");
   b200_ij ij = new b200_ij_s();
   ij->ilower = ilower; ij->iupper = iupper; ij->jlower = jlower; ij->jupper = jupper;
+  ij->diag_shift = jlower;                             // one rank: local row r <-> local column r (IJMatrix_parcsr.c:2974)
   for (int c = 0; c < 2; c++) {
     B200_CUDA(cudaHostAlloc((void **)&ij->h_row[c], sizeof(int) * b200_ij_s::CHUNK, cudaHostAllocDefault));
     B200_CUDA(cudaHostAlloc((void **)&ij->h_col[c], sizeof(int) * b200_ij_s::CHUNK, cudaHostAllocDefault));
@@ -175,6 +177,21 @@ extern "C" int b200_ij_create(b200_handle h, int ilower, int iupper, int jlower,
   }
   *out = ij;
   return 0;
+}
+
+// the rows [ilower, iupper] of a square operator spread over several ranks: columns stay GLOBAL (0 .. global_cols-1) in the
+// assembled CSR, which is the form b200_dist_matrix_create_from_ij localizes (diag / offd split + col_map_offd of
+// GenerateDiagAndOffd, par_csr_matrix.c:1634, happen there)
+extern "C" int b200_ij_create_rows(b200_handle h, int ilower, int iupper, int global_cols, b200_ij *out) {
+  B200_TRY(b200_ij_create(h, ilower, iupper, 0, global_cols - 1, out));
+  (*out)->diag_shift = ilower;
+  return 0;
+}
+// hand the assembled object over (b200_dist.cu): the assembler forgets it
+b200_parcsr b200_ij_release_object(b200_ij ij) {
+  b200_parcsr A = ij->A;
+  ij->A = nullptr;
+  return A;
 }
 
 extern "C" int b200_ij_destroy(b200_handle h, b200_ij ij) {
@@ -263,7 +280,7 @@ extern "C" int b200_ij_assemble(b200_handle h, b200_ij ij, b200_parcsr *A_out, i
     B200_TRY(b200_dalloc<int>(h, &dpos, (size_t)nrows + 1));
     B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * ((size_t)nrows + 1), h->stream));
     if (nrows) {
-      merge_rows_kernel<<<b200_grid(nrows, 128), 128, 0, h->stream>>>(nrows, ij->jlower, ptr, col_s, val_s, blk_s, cnt, dpos);
+      merge_rows_kernel<<<b200_grid(nrows, 128), 128, 0, h->stream>>>(nrows, ij->diag_shift, ptr, col_s, val_s, blk_s, cnt, dpos);
       B200_LAUNCH_CHECK();
     }
     B200_TRY(b200_exclusive_scan_inplace(h, cnt, (size_t)nrows + 1));

@@ -119,6 +119,9 @@ int b200_ij_set_values(b200_handle h, b200_ij ij, int nrows, const int *ncols, c
                        const double *values, int add, int *n_rejected);
 int b200_ij_assemble(b200_handle h, b200_ij ij, b200_parcsr *A, int *n_missing);
 long long b200_ij_num_rejected(b200_ij ij);
+/* assembler for the rows [ilower, iupper] of a square operator spread over several ranks: columns stay global
+ * (0 .. global_cols-1); hand it to b200_dist_matrix_create_from_ij */
+int b200_ij_create_rows(b200_handle h, int ilower, int iupper, int global_cols, b200_ij *ij);
 
 /* ---- ParCSR (parcsr_mv) -------------------------------------------------------------------- */
 /* single-rank ParCSR from a host CSR (diag block = whole matrix); diagonal entry must be first
@@ -267,6 +270,13 @@ int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, int ny, int n
 /* GenerateRotate7pt on a P x Q process grid, rank -> (p, q) as ij.c:9190-9191 */
 int b200_dist_generate_rotate7pt(b200_handle h, b200_comm c, int nx, int ny, int P, int Q, double alpha, double eps,
                                  b200_dist_matrix *A);
+/* a row-partitioned operator from the caller's own rows (what hypre_IJMatrixAssembleParCSR + GenerateDiagAndOffd give
+ * across ranks, IJ_mv/IJMatrix_parcsr.c:2774, parcsr_mv/par_csr_matrix.c:1634): rank r owns the next n_local rows after
+ * those of the ranks before it; rows carry GLOBAL column ids and their diagonal entry first.  Collective.
+ * _from_host: host CSR arrays;  _from_ij: the records of a b200_ij_create_rows assembler, merged on the device. */
+int b200_dist_matrix_create_from_host(b200_handle h, b200_comm c, int n_local, const int *h_i, const int *h_j_global,
+                                      const double *h_a, b200_dist_matrix *A);
+int b200_dist_matrix_create_from_ij(b200_handle h, b200_comm c, b200_ij ij, b200_dist_matrix *A);
 int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix A);
 int b200_dist_matrix_info(b200_dist_matrix A, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
                           int *n_ghost, int *first_col, int *global_cols);

@@ -61,7 +61,9 @@ def dist_case(nranks, grid, dims, stencil=7, solve=True, solver=1, **params):
     P, Q, R = grid
 
     def fn(r, h, c):
-        if isinstance(stencil, dict) and "alpha" in stencil:     # GenerateRotate7pt, two-dimensional (nz = R = 1)
+        if callable(stencil):                                    # the caller's own rows: stencil(rank, handle, comm) -> DistMatrix
+            A = stencil(r, h, c)
+        elif isinstance(stencil, dict) and "alpha" in stencil:   # GenerateRotate7pt, two-dimensional (nz = R = 1)
             A = hb.DistMatrix.rotate7pt(h, c, nx, ny, P, Q, stencil["alpha"], stencil["eps"])
         elif isinstance(stencil, dict):       # GenerateDifConv with these -c / -a / -atype values (nonsymmetric)
             A = hb.DistMatrix.difconv(h, c, nx, ny, nz, P, Q, R, **stencil)
@@ -200,6 +202,101 @@ def test_yslab_rotate7pt_equals_reference_cpu_build():
         ri, rj, ra, _ = refio.csr(d, "A", l)
         assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(a, ra), l
     assert res[0]["its"] == int(d["hdr"][4])
+
+
+def uneven_cuts(N, nranks):
+    """contiguous row blocks of different sizes (nothing like a box decomposition)"""
+    w = np.array([1.0 + 0.7 * ((3 * r) % nranks) for r in range(nranks)])
+    cuts = np.concatenate([[0], np.round(np.cumsum(w) / w.sum() * N).astype(int)])
+    cuts[-1] = N
+    assert np.all(np.diff(cuts) > 0)
+    return cuts
+
+
+USER_ROWS = [
+    (["-n", 14, 13, 12, "-perturb", 3, "-rlx", 18], 3, "rows"),
+    (["-n", 14, 13, 12, "-perturb", 3, "-rlx", 18], 3, "ij"),
+    (["-n", 16, 15, 11, "-difconv", "-a", 3, -2, 1, "-atype", 3, "-rlx", 18], 5, "ij"),
+    (["-n", 26, 23, 1, "-rotate", "-alpha", 45, "-eps", 0.001, "-rlx", 18], 4, "rows"),
+    (["-n", 10, 10, 10, "-27pt", "-rlx", 18, "-agg_nl", 1], 2, "ij"),
+]
+
+
+@pytest.mark.parametrize("args,nranks,how", USER_ROWS)
+def test_operator_from_the_callers_rows_equals_reference_cpu_build(handle, args, nranks, how):
+    """b200_dist_matrix_create_from_host / _from_ij: every rank hands in an arbitrary contiguous block of rows of the
+    reference's operator (global column ids) -- as CSR arrays, or as a scrambled SetValues / AddToValues stream merged on
+    the device -- and the N-rank hierarchy, iteration count and residual history are the reference np=1 run's"""
+    import hypre_ve_b200 as hb
+    import ijstream
+    d, _ = refio.run_ref(args + ["-pmis", "-keepT", 1])
+    I, J, a, _ = refio.csr(d, "A", 0)
+    N = I.size - 1
+    cuts = uneven_cuts(N, nranks)
+    agg = int(args[args.index("-agg_nl") + 1]) if "-agg_nl" in args else 0
+
+    def build(r, h, c):
+        r0, r1 = int(cuts[r]), int(cuts[r + 1])
+        Il = (I[r0:r1 + 1] - I[r0]).astype(np.int32)
+        Jl, al = J[I[r0]:I[r1]], a[I[r0]:I[r1]]
+        if how == "rows":
+            return hb.DistMatrix.from_rows(h, c, Il, Jl, al)
+        asm = hb.IJAssembler(h, r0, r1 - 1, global_cols=N)
+        # the -ijbuild mode-1 stream of this block (half the value set, rotated; the other half added, rotated differently),
+        # with row numbers shifted back to global ones
+        for add, rows, ncols, cols, vals in ijstream.calls_before_assembly(Il, Jl, al, 1):
+            assert asm.set_values(ncols, np.asarray(rows) + r0, cols, vals, add=bool(add)) == 0
+        M = hb.DistMatrix.from_ij(h, c, asm)
+        asm.destroy()
+        i2, j2, a2 = M.download()
+        assert np.array_equal(i2, Il) and np.array_equal(a2[i2[:-1]], al[Il[:-1]])            # diagonal first, values restored
+        assert np.array_equal(np.sort(j2), np.sort(Jl))
+        return M
+
+    if how == "ij":      # the assembled entry order differs from the reference's generator order: compare with the single-GPU run
+        res = dist_case(nranks, (nranks, 1, 1), (N, 1, 1), build, ModuleRAP2=0, AggNumLevels=agg)
+        gi, gj, ga = gather([r["levels"][0]["A"] for r in res])
+        ref = single_gpu_on(handle, gi, gj, ga, ModuleRAP2=0, AggNumLevels=agg)
+        nl = len(ref["levels"])
+        assert all(len(r["levels"]) == nl for r in res)
+        for l in range(nl):
+            i, j, v = gather([r["levels"][l]["A"] for r in res])
+            ri, rj, ra = ref["levels"][l]["A"]
+            assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(v, ra), l
+        assert res[0]["its"] == ref["its"] and np.max(np.abs(res[0]["norms"] - ref["norms"])) / ref["norms"][0] < 1e-10
+        return
+    res = dist_case(nranks, (nranks, 1, 1), (N, 1, 1), build, ModuleRAP2=0, AggNumLevels=agg)
+    nl = int(d["hdr"][3])
+    assert all(len(r["levels"]) == nl for r in res)
+    for l in range(nl):
+        i, j, v = gather([r["levels"][l]["A"] for r in res])
+        ri, rj, ra, _ = refio.csr(d, "A", l)
+        assert np.array_equal(i, ri) and np.array_equal(j, rj) and np.array_equal(v, ra), l
+        if l < nl - 1:
+            i, j, v = gather([r["levels"][l]["P"] for r in res])
+            pi, pj, pa, _ = refio.csr(d, "P", l)
+            assert np.array_equal(i, pi) and np.array_equal(j, pj) and np.array_equal(v, pa), ("P", l)
+    assert res[0]["its"] == int(d["hdr"][4])
+    assert np.max(np.abs(res[0]["norms"] - d["norms"])) / d["norms"][0] < 1e-10
+
+
+def test_operator_from_rows_rejects_bad_input():
+    """a row whose diagonal entry is not first, or a column outside the global range, fails on EVERY rank (collective verdict)"""
+    import hypre_ve_b200 as hb
+
+    def fn(r, h, c):
+        I = np.array([0, 2, 4], np.int32)
+        J = np.array([2 * r, 2 * r + 1, 2 * r + 1, 2 * r], np.int32)
+        a = np.array([2.0, -1.0, 2.0, -1.0])
+        if r == 1:
+            J[2], J[3] = J[3], J[2]                          # rank 1: second row stores its off-diagonal first
+        try:
+            hb.DistMatrix.from_rows(h, c, I, J, a)
+            return "built"
+        except hb.B200Error as e:
+            return str(e)
+    out = run_ranks(2, fn)
+    assert all("diagonal entry first" in o for o in out), out
 
 
 def test_zslab_difconv_gmres_equals_reference_cpu_build():
