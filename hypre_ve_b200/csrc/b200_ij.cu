@@ -219,8 +219,8 @@ extern "C" int b200_ij_set_values(b200_handle h, b200_ij ij, int nrows, const in
   for (int r = 0; r < nrows; r++) {
     const int row = rows[r], n = ncols[r];
     if (n < 0) B200_FAIL("ij_set_values: negative ncols");
-    if (row < ij->ilower || row > ij->iupper) { rejected += n ? n : 1; at += (size_t)n; continue; }   // off-processor row: no owner to send it to
-    if (n == 0) continue;                                                                                // "empty row" (:919-922)
+    if (n == 0) continue;                                                                   // "empty row" (:919-922), before the ownership test
+    if (row < ij->ilower || row > ij->iupper) { rejected += n; at += (size_t)n; continue; }   // off-processor row: no owner to send it to
     const int blk = (int)(((ij->block_counter++) & 0x3fffffffu) << 1) | (add ? 1 : 0);
     for (int k = 0; k < n; k++, at++) {
       const int c = cols[at];

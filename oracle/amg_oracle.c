@@ -143,18 +143,36 @@ static double hrand(void)
 
 /* ---- PMIS: parcsr_ls/par_coarsen.c:2159-2700, CF_init 0, one rank; measures from
  *      par_indepset.c:44-59 (seed 2747, one draw per row in row order) ---- */
-static int *pmis_init(const csr_t *S, int cf_init);
-static int *pmis(const csr_t *S) { return pmis_init(S, 0); }
+static int *pmis_init(const csr_t *S, int cf_init, int *cf_in);
+static int *pmis(const csr_t *S) { return pmis_init(S, 0, NULL); }
 /* cf_init 3 (second PMIS of aggressive coarsening, par_amg_setup.c:1253): isolated rows become C points
  * (:2322-2326) and the first sweep skips the independent-set selection (`if (!CF_init || iter)`, :2420) */
-static int *pmis_init(const csr_t *S, int cf_init)
+/* cf_init 1 (HMIS, :2795): cf_in holds the markers of the Ruge-Stueben first pass; its C points are the first
+ * independent set, every F point becomes undecided again and Z points stay F only if nothing depends on them (:2279-2309) */
+static int *pmis_init(const csr_t *S, int cf_init, int *cf_in)
 {
    int n = S->n, i, k, jS;
    double *m = (double *) xcalloc(n, sizeof(double));
-   int *cf = (int *) xcalloc(n, sizeof(int)), *graph = (int *) xmalloc(sizeof(int) * n), gsize = 0;
+   int *cf = cf_in ? cf_in : (int *) xcalloc(n, sizeof(int)), *graph = (int *) xmalloc(sizeof(int) * n), gsize = 0;
    for (k = 0; k < S->nnz; k++) m[S->j[k]] += 1.0;
    g_seed = 2747;
    for (i = 0; i < n; i++) m[i] += hrand();
+   if (cf_init == 1)
+      for (i = 0; i < n; i++)
+      {
+         if (cf[i] != -3)
+         {
+            if (cf[i] == -1) cf[i] = 0;
+            if (cf[i] == -2)
+            {
+               if (m[i] >= 1.0 || S->i[i + 1] - S->i[i] > 0) { cf[i] = 0; graph[gsize++] = i; }
+               else cf[i] = -1;
+            }
+            else graph[gsize++] = i;
+         }
+         else m[i] = 0;
+      }
+   else
    for (i = 0; i < n; i++)
    {
       cf[i] = 0;
@@ -193,6 +211,130 @@ static int *pmis_init(const csr_t *S, int cf_init)
    free(m); free(graph);
    return cf;
 }
+
+static csr_t transpose(const csr_t *A);
+
+/* ---- Ruge-Stueben first pass as HMIS uses it: hypre_BoomerAMGCoarsenRuge with coarsen_type 10 -> 11, f_pnt = Z_PT,
+ *      measure_type 0, no cut factor, one rank (par_coarsen.c:1046-1330).  The reference keeps the undecided points in a
+ *      list of lists ordered by measure (utilities/amg_linklist.c): within one measure the points leave in the order they
+ *      entered, and the next C point is the oldest point of the largest measure.  Same behaviour here with one FIFO per
+ *      measure value, indexed directly. ---- */
+typedef struct { int *head, *tail, *next, *prev, nb, maxm; } buckets_t;
+static void bk_grow(buckets_t *b, int m)
+{
+   if (m < b->nb) return;
+   int nb = 2 * m + 8, k;
+   b->head = (int *) realloc(b->head, sizeof(int) * nb); b->tail = (int *) realloc(b->tail, sizeof(int) * nb);
+   for (k = b->nb; k < nb; k++) b->head[k] = b->tail[k] = -1;
+   b->nb = nb;
+}
+static void bk_enter(buckets_t *b, int m, int i)          /* hypre_enter_on_lists: append to the list of measure m */
+{
+   bk_grow(b, m);
+   b->next[i] = -1; b->prev[i] = b->tail[m];
+   if (b->tail[m] >= 0) b->next[b->tail[m]] = i; else b->head[m] = i;
+   b->tail[m] = i;
+   if (m > b->maxm) b->maxm = m;
+}
+static void bk_remove(buckets_t *b, int m, int i)         /* hypre_remove_point */
+{
+   if (b->prev[i] >= 0) b->next[b->prev[i]] = b->next[i]; else b->head[m] = b->next[i];
+   if (b->next[i] >= 0) b->prev[b->next[i]] = b->prev[i]; else b->tail[m] = b->prev[i];
+   while (b->maxm > 0 && b->head[b->maxm] < 0) b->maxm--;
+}
+/* agg2: the second coarsening of an aggressive level calls it with measure_type + 3 (par_amg_setup.c:1247-1250): isolated
+ * points become special C points (SC_PT) instead of special F points */
+static int *ruge_first_pass(const csr_t *S, int agg2)
+{
+   int n = S->n, i, j, k, num_left = 0;
+   csr_t ST = transpose(S);                                /* :1014-1043, rows of ST ordered by source row */
+   int *cf = (int *) xcalloc(n, sizeof(int)), *meas = (int *) xmalloc(sizeof(int) * n);
+   buckets_t b; memset(&b, 0, sizeof b);
+   b.next = (int *) xmalloc(sizeof(int) * n); b.prev = (int *) xmalloc(sizeof(int) * n);
+   bk_grow(&b, 16);
+   for (i = 0; i < n; i++) meas[i] = ST.i[i + 1] - ST.i[i];                     /* :1056-1059 */
+   for (j = 0; j < n; j++)                                                        /* :1130-1158 (CF_marker starts at 0) */
+   {
+      if (S->i[j + 1] - S->i[j] == 0) { cf[j] = agg2 ? 3 : -3; meas[j] = 0; }
+      else { cf[j] = 0; num_left++; }
+   }
+   for (j = 0; j < n; j++)                                                        /* :1179-1222 */
+   {
+      int measure = meas[j];
+      if (cf[j] == -3 || cf[j] == 3) continue;
+      if (measure > 0) bk_enter(&b, measure, j);
+      else
+      {
+         cf[j] = -2;                                                              /* f_pnt = Z_PT */
+         for (k = S->i[j]; k < S->i[j + 1]; k++)
+         {
+            int nabor = S->j[k];
+            if (cf[nabor] != -3 && cf[nabor] != 3)
+            {
+               if (nabor < j)
+               {
+                  int nm = meas[nabor];
+                  if (nm > 0) bk_remove(&b, nm, nabor);
+                  nm = ++meas[nabor];
+                  bk_enter(&b, nm, nabor);
+               }
+               else ++meas[nabor];
+            }
+         }
+         --num_left;
+      }
+   }
+   while (num_left > 0)                                                           /* :1245-1320 */
+   {
+      int index = b.head[b.maxm], measure = meas[index];
+      cf[index] = 1;
+      meas[index] = 0;
+      --num_left;
+      bk_remove(&b, measure, index);
+      for (j = ST.i[index]; j < ST.i[index + 1]; j++)
+      {
+         int nabor = ST.j[j];
+         if (cf[nabor] == 0)
+         {
+            cf[nabor] = -1;
+            bk_remove(&b, meas[nabor], nabor);
+            --num_left;
+            for (k = S->i[nabor]; k < S->i[nabor + 1]; k++)
+            {
+               int n2 = S->j[k];
+               if (cf[n2] == 0) { bk_remove(&b, meas[n2], n2); ++meas[n2]; bk_enter(&b, meas[n2], n2); }
+            }
+         }
+      }
+      for (j = S->i[index]; j < S->i[index + 1]; j++)
+      {
+         int nabor = S->j[j];
+         if (cf[nabor] == 0)
+         {
+            int m2 = meas[nabor];
+            bk_remove(&b, m2, nabor);
+            meas[nabor] = --m2;
+            if (m2 > 0) bk_enter(&b, m2, nabor);
+            else
+            {
+               cf[nabor] = -1;
+               --num_left;
+               for (k = S->i[nabor]; k < S->i[nabor + 1]; k++)
+               {
+                  int n2 = S->j[k];
+                  if (cf[n2] == 0) { bk_remove(&b, meas[n2], n2); ++meas[n2]; bk_enter(&b, meas[n2], n2); }
+               }
+            }
+         }
+      }
+   }
+   for (i = 0; i < n; i++) if (cf[i] == 3) cf[i] = 1;                            /* :1337-1343 SC_PT -> C_PT */
+   free(meas); free(b.head); free(b.tail); free(b.next); free(b.prev); csr_free(&ST);
+   return cf;
+}
+/* hypre_BoomerAMGCoarsenHMIS (:2774-2797): the first pass above, then PMIS seeded with its C points */
+static int g_coarsen_type = 8;                             /* 8 PMIS (ij -pmis), 10 HMIS (library and driver default) */
+static int *hmis(const csr_t *S, int agg2) { return pmis_init(S, 1, ruge_first_pass(S, agg2)); }
 
 /* ---- utilities/hypre_qsort.c:367-387 ---- */
 static void swap2(int *v, double *w, int i, int j) { int t = v[i]; v[i] = v[j]; v[j] = t; double s = w[i]; w[i] = w[j]; w[j] = s; }
@@ -305,7 +447,7 @@ static csr_t transpose(const csr_t *A)
    for (k = 0; k < A->nnz; k++) T.i[A->j[k] + 1]++;
    for (i = 0; i < A->m; i++) T.i[i + 1] += T.i[i];
    int *next = (int *) xmalloc(sizeof(int) * (A->m + 1)); memcpy(next, T.i, sizeof(int) * (A->m + 1));
-   for (i = 0; i < A->n; i++) for (k = A->i[i]; k < A->i[i + 1]; k++) { int p = next[A->j[k]]++; T.j[p] = i; T.a[p] = A->a[k]; }
+   for (i = 0; i < A->n; i++) for (k = A->i[i]; k < A->i[i + 1]; k++) { int p = next[A->j[k]]++; T.j[p] = i; if (A->a) T.a[p] = A->a[k]; }
    free(next);
    return T;
 }
@@ -713,12 +855,12 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    while (1)
    {
       csr_t S = strength(&g->A[l], theta, mrs);
-      int *cf = pmis(&S), n = g->A[l].n, nc = 0;
+      int *cf = g_coarsen_type == 10 ? hmis(&S, 0) : pmis(&S), n = g->A[l].n, nc = 0;
       if (l < g_agg_nl)
       {  /* second coarsening on the distance-two graph of the C points, then CorrectCFMarker (par_strength.c:2957-2974) */
          int nc1 = 0, cnt = 0;
          csr_t S2 = create2ndS(&S, cf, &nc1);
-         int *cfn = pmis_init(&S2, 3);
+         int *cfn = g_coarsen_type == 10 ? hmis(&S2, 1) : pmis_init(&S2, 3, NULL);
          for (i = 0; i < n; i++) if (cf[i] > 0) { if (cf[i] == 1) cf[i] = cfn[cnt++]; else { cf[i] = 1; cnt++; } }
          csr_free(&S2); free(cfn);
       }
@@ -1132,7 +1274,9 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-max_iter")) max_iter = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-matvec")) matvec_reps = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-o")) ofile = argv[++i];
-      else if (!strcmp(argv[i], "-pmis") || !strcmp(argv[i], "-nodump")) { }
+      else if (!strcmp(argv[i], "-pmis")) g_coarsen_type = 8;
+      else if (!strcmp(argv[i], "-hmis")) g_coarsen_type = 10;                           /* the driver default when -pmis is absent */
+      else if (!strcmp(argv[i], "-nodump")) { }
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-gs_blocks")) g_gs_blocks = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-agg_nl")) g_agg_nl = atoi(argv[++i]);

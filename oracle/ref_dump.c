@@ -225,6 +225,7 @@ int main(int argc, char **argv)
       else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-pmis")) pmis = 1;
+      else if (!strcmp(argv[i], "-hmis")) pmis = 0;                      /* coarsen_type 10, the default */
       else if (!strcmp(argv[i], "-rlx")) rlx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-Pmx")) Pmx = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-agg_nl")) agg_nl = atoi(argv[++i]);

@@ -38,6 +38,9 @@ MORE = {
     "lap7_11_gmres_gs1314.bin": (["-n", "11", "11", "11", "-pmis", "-solver", "3"], 1),
     # 2-D rotated anisotropic diffusion (GenerateRotate7pt): positive off-diagonals, strong diagonal coupling
     "rotate_24x20_a45_e001_rlx18.bin": (["-n", "24", "20", "1", "-rotate", "-alpha", "45", "-eps", "0.001", "-pmis", "-rlx", "18"], 1),
+    # the literal driver default: HMIS coarsening (coarsen_type 10 = Ruge-Stueben first pass + PMIS), 13/14 smoothing
+    "lap7_12_hmis_default.bin": (["-n", "12", "12", "12"], 1),
+    "aniso_11_hmis_agg1_rlx18.bin": (["-n", "11", "11", "11", "-c", "1", "1", "0.001", "-rlx", "18", "-agg_nl", "1"], 1),
     "rotate_20x20_a30_e01_agg1_gs.bin": (["-n", "20", "20", "1", "-rotate", "-alpha", "30", "-eps", "0.01", "-pmis", "-agg_nl", "1"], 1),
 }
 if __name__ == "__main__":

@@ -74,6 +74,9 @@ GOLDEN_MORE = {
     "lap7_11_gmres_gs1314.bin": (["-n", 11, 11, 11, "-pmis", "-solver", 3], True),
     # GenerateRotate7pt (par_rotate_7pt.c): 2-D rotated anisotropy
     "rotate_24x20_a45_e001_rlx18.bin": (["-n", 24, 20, 1, "-rotate", "-alpha", 45, "-eps", 0.001, "-pmis", "-rlx", 18], True),
+    # HMIS (par_coarsen.c:874-1330 first pass with the amg_linklist.c ordering, :2774 HMIS, :2279 PMIS CF_init 1)
+    "lap7_12_hmis_default.bin": (["-n", 12, 12, 12, "-hmis"], True),
+    "aniso_11_hmis_agg1_rlx18.bin": (["-n", 11, 11, 11, "-c", 1, 1, 0.001, "-rlx", 18, "-agg_nl", 1, "-hmis"], True),
     "rotate_20x20_a30_e01_agg1_gs.bin": (["-n", 20, 20, 1, "-rotate", "-alpha", 30, "-eps", 0.01, "-pmis", "-agg_nl", 1], True),
 }
 
@@ -210,3 +213,33 @@ def test_ij_call_stream_mirror_matches_the_reference_ij_interface(args, mode):
     assert np.array_equal(EI, ri) and np.array_equal(EJ, rj) and np.array_equal(Ea, ra)
     if mode == 2:
         assert ri[-1] > I[-1] and any(len(set(rj[ri[r]:ri[r + 1]])) < ri[r + 1] - ri[r] for r in range(3, I.size - 1, 7))   # duplicates survive
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args", [["-n", 17, 23, 9], ["-n", 12, 12, 12, "-27pt"], ["-n", 15, 14, 13, "-difconv", "-rlx", 18],
+                                  ["-n", 30, 26, 1, "-rotate", "-alpha", 60, "-eps", 0.01, "-rlx", 18],
+                                  ["-n", 14, 13, 12, "-perturb", 5, "-rlx", 18, "-agg_nl", 1], ["-n", 1, 30, 30], ["-n", 3, 3, 3]])
+def test_hmis_restatement_matches_live_reference(oracle_bin, args):
+    """the driver-default coarsening (HMIS): Ruge-Stueben first pass (FIFO per measure, largest measure first) followed by
+    PMIS seeded with its C points, aggressive levels included -- every dumped array equal to the reference build's"""
+    gold, _ = refio.run_ref(args)                       # no -pmis: coarsen_type 10
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "o.bin")
+        subprocess.run([oracle_bin] + [str(a) for a in args] + ["-hmis", "-o", path], check=True, capture_output=True)
+        mine = refio.read_dump(path)
+    for k in gold:
+        assert np.array_equal(gold[k], mine[k]), k
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+def test_config_1_literal_driver_default_known_answer(oracle_bin):
+    """BASELINE.json configs[0] as written, `ij -laplacian -n 50 50 50 -solver 1` (HMIS, 13/14): SURVEY.md 8c gives 8
+    iterations, 7.138942e-10, 8 levels -- reproduced by the reference build and, bit for bit, by the restatement"""
+    gold, out = refio.run_ref(["-n", 50, 50, 50])
+    assert "levels=8 iterations=8 relres=7.138942e-10" in out
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "o.bin")
+        subprocess.run([oracle_bin, "-n", "50", "50", "50", "-hmis", "-o", path], check=True, capture_output=True)
+        mine = refio.read_dump(path)
+    for k in gold:
+        assert np.array_equal(gold[k], mine[k]), k
