@@ -87,6 +87,7 @@ SIGNATURES = {
     "b200_amg_setup_times": (_i, [_vp, _dp]),
     "b200_strength": (_i, [_vp, _vp, _d, _d, C.POINTER(_vp)]),
     "b200_pmis": (_i, [_vp, _vp, _i, _vp]),
+    "b200_hmis": (_i, [_vp, _vp, _i, _vp]),
     "b200_extpi_interp": (_i, [_vp, _vp, _vp, _vp, _d, _i, C.POINTER(_vp)]),
     "b200_create_2nd_s": (_i, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_agg_coarsen": (_i, [_vp, _vp, _i, _vp]),
@@ -531,6 +532,13 @@ class Handle:
         n = S.dims[0]
         cf = self.zeros(n, np.int32)
         _chk(_lib.b200_pmis(self.p, S.p, seed, cf.ptr))
+        return cf
+
+    def hmis(self, S, seed=2747):
+        """hypre_BoomerAMGCoarsenHMIS: Ruge-Stueben first pass (one device thread) + PMIS seeded with its C points"""
+        n = S.dims[0]
+        cf = self.zeros(n, np.int32)
+        _chk(_lib.b200_hmis(self.p, S.p, seed, cf.ptr))
         return cf
 
     def extpi_interp(self, A, S, cf, trunc_factor=0.0, max_elmts=4):

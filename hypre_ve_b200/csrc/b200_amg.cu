@@ -215,7 +215,10 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   if (Apar->offd->ncols > 0) B200_FAIL("amg_setup: multi-rank setup not built yet (offd block must be empty)");
   auto &ip = amg->ip;
   auto &rp = amg->rp;
-  if (ip["CoarsenType"] != 8) B200_FAIL("only CoarsenType 8 (PMIS) is implemented on the B200 path");
+  if (ip["CoarsenType"] != 8 && ip["CoarsenType"] != 10)
+    B200_FAIL("only CoarsenType 8 (PMIS) and 10 (HMIS) are implemented on the B200 path");
+  if (ip["CoarsenType"] == 10 && ip["AggNumLevels"] > 0)
+    B200_FAIL("CoarsenType 10 (HMIS) with aggressive levels is not built on the B200 path: use CoarsenType 8 (PMIS)");
   if (ip["InterpType"] != 6) B200_FAIL("only InterpType 6 (extended+i) is implemented on the B200 path");
   // grid_relax_type[1] / [2] (par_amg.c:1650-1672); the coarsest grid is always Gaussian elimination (9)
   const int rdown = ip["RelaxType"], rup = ip["RelaxTypeUp"] >= 0 ? ip["RelaxTypeUp"] : ip["RelaxType"];
@@ -273,7 +276,8 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     int *cf = nullptr;
     B200_TRY(b200_dalloc<int>(h, &cf, fine_size));
     tm.start();
-    B200_TRY(b200_pmis_rows(h, S, seed, 0, cf, nullptr));  // :1114
+    if (ip["CoarsenType"] == 10) B200_TRY(b200_hmis(h, S, seed, cf));   // :1107 (sequential first pass, see b200_hmis.cu)
+    else B200_TRY(b200_pmis_rows(h, S, seed, 0, cf, nullptr));          // :1114
     const bool aggressive = level < ip["AggNumLevels"];
     if (aggressive) B200_TRY(b200_agg_coarsen(h, S, seed, cf));   // :1239-1256 + CorrectCFMarker :1592
     amg->times[1] += tm.stop();

@@ -188,6 +188,18 @@ __global__ void pmis_init_kernel(int n, const int *__restrict__ S_i, const int *
   // measure = #influences + hypre_Rand()   (par_indepset.c:56-59: i-th local row takes the (i+1)-th draw)
   int s = lcg_at(seed, (unsigned long long)(first_row + i + 1));
   double m = (double)colcnt[i] + ((double)s / 2147483647.0);
+  if (cf_init == 1) {               // HMIS: cf holds the Ruge-Stueben first pass (par_coarsen.c:2279-2309)
+    int c = cf[i];
+    if (c == -3) {
+      m = 0.0;                      // special F points stay out of the graph
+    } else {
+      if (c == -1) c = 0;           // every F point is undecided again
+      if (c == -2) c = (m >= 1.0 || S_i[i + 1] - S_i[i] > 0) ? 0 : -1;   // Z points stay F only if nothing connects them
+    }                               // C points (1) stay: they are the first independent set
+    cf[i] = c;
+    measure[i] = m;
+    return;
+  }
   if (S_i[i + 1] - S_i[i] == 0) {   // isolated point: SF_PT, measure 0; C_PT when CF_init is 3 (par_coarsen.c:2316-2328)
     cf[i] = (cf_init == 3) ? 1 : -3;
     m = 0.0;
@@ -236,6 +248,35 @@ __global__ void pmis_setcf_kernel(int n, const int *__restrict__ S_i, const int 
     if (c != 0) measure[i] = 0;                     // :2643-2647
   }
   cf_out[i] = c;
+}
+// First sweep of PMIS with CF_init 1 (HMIS): the graph holds the undecided nodes AND the first pass's C points; no
+// independent set is picked (`if (!CF_init || iter)`, :2420).  The reference updates CF_marker in place in index order
+// (:2543-2595), and here that order is visible: a C point whose measure is below 1 is turned into an F point when its
+// turn comes, so it still counts as a C neighbour for the nodes before it and no longer for the nodes after it.
+__global__ void pmis_setcf_first_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ S_j,
+                                        const double *__restrict__ measure, const int *__restrict__ cf_in,
+                                        int *__restrict__ cf_out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c = cf_in[i];
+  if (c == 0 || c == 1) {
+    if (measure[i] < 1) c = -1;
+    if (c > 0) {
+      c = 1;
+    } else {
+      for (int jS = S_i[i]; jS < S_i[i + 1]; jS++) {
+        const int j = S_j[jS];
+        if (cf_in[j] > 0 && !(measure[j] < 1 && j < i)) c = -1;
+      }
+    }
+  }
+  cf_out[i] = c;
+}
+// nodes that left the graph in that sweep lose their measure (:2643-2647)
+__global__ void pmis_clear_first_kernel(int n, const int *__restrict__ cf_before, const int *__restrict__ cf_after,
+                                        double *__restrict__ measure) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && (cf_before[i] == 0 || cf_before[i] == 1) && cf_after[i] != 0) measure[i] = 0;
 }
 __global__ void pmis_graph_kernel(int n, const int *__restrict__ cf, int *__restrict__ ingraph, int *__restrict__ count) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -625,7 +666,7 @@ int b200_pmis_rows(b200_handle h, b200_csr S, int seed, long long first_row, int
 // (par_amg_setup.c:1253): isolated rows become C points and the first sweep does not pick an independent set
 // (`if (!CF_init || iter)`, par_coarsen.c:2420)
 int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row, int cf_init, int *d_cf, int *iterations) {
-  if (cf_init != 0 && cf_init != 3) B200_FAIL("pmis: CF_init 0 or 3");
+  if (cf_init != 0 && cf_init != 1 && cf_init != 3) B200_FAIL("pmis: CF_init 0, 1 or 3");
   const int n = S->nrows;
   if (iterations) *iterations = 0;
   if (n == 0) return 0;
@@ -644,6 +685,14 @@ int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row
   pmis_init_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, colcnt, seed, first_row, measure, d_cf, cf_init);
   B200_LAUNCH_CHECK();
   int iter = 0;
+  if (cf_init == 1) {                               // the sweep seeded by the Ruge-Stueben C points (see the kernel)
+    pmis_setcf_first_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, d_cf, cf2);
+    B200_LAUNCH_CHECK();
+    pmis_clear_first_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf, cf2, measure);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(d_cf, cf2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    iter = 1;
+  }
   while (true) {
     B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
     pmis_graph_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf, ingraph, d_count);

@@ -177,6 +177,10 @@ int b200_strength(b200_handle h, b200_csr A, double theta, double max_row_sum, b
 /* hypre_BoomerAMGCoarsenPMISHost (par_coarsen.c:2031-2738) + IndepSetInit (par_indepset.c:32-63)
  * + hypre_Rand (utilities/random.c:49-106); writes CF marker {1,-1,-3} */
 int b200_pmis(b200_handle h, b200_csr S, int seed, int *d_cf);
+/* hypre_BoomerAMGCoarsenHMIS (par_coarsen.c:2774-2797; coarsen_type 10, the library and driver default): the
+ * Ruge-Stueben first pass (:1046-1330, sequential by definition -- one device thread walks the reference's measure lists)
+ * followed by PMIS seeded with its C points (CF_init 1).  d_cf receives 1 (C) / -1 (F) / -3 (isolated). */
+int b200_hmis(b200_handle h, b200_csr S, int seed, int *d_cf);
 /* hypre_BoomerAMGBuildExtPIInterpHost (par_lr_interp.c:1040-1925) followed by
  * hypre_BoomerAMGInterpTruncation (par_interp.c:2718 -> par_csr_matrix.c:2671-3060) */
 int b200_extpi_interp(b200_handle h, b200_csr A, b200_csr S, const int *d_cf,

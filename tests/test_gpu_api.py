@@ -193,10 +193,10 @@ def test_driver_default_galerkin_product(exe):
 
 
 def test_out_of_scope_configuration_is_rejected_loudly(exe):
-    """HMIS coarsening (the driver default) is not on the B200 path: Setup must fail, not fall back"""
-    rc, out = run([exe, "-laplacian", "-n", "8", "8", "8", "-solver", "1", "-rlx", "18", "-mod_rap2", "1"])
+    """classical modified interpolation (-interptype 0) is not on the B200 path: Setup must fail, not fall back"""
+    rc, out = run([exe, "-laplacian", "-n", "8", "8", "8", "-solver", "1", "-pmis", "-interptype", "0", "-rlx", "18", "-mod_rap2", "1"])
     assert rc != 0
-    assert "CoarsenType" in out and "hypre error flag" in out
+    assert "InterpType" in out and "hypre error flag" in out
 
 
 def test_matvec_loop(exe):
