@@ -17,4 +17,7 @@ def handle():
     import hypre_ve_b200 as hb
     h = hb.Handle(0)
     yield h
-    h.close()
+    try:
+        h.close()
+    except Exception as e:          # a context poisoned by a failing (xfail-guarded) case must not turn into a teardown error
+        print("handle.close():", e)
