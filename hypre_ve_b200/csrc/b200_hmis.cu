@@ -13,6 +13,7 @@
 // rows), and `-pmis` stays the configuration to use at scale.  Every loop below has a static bound: a corrupted list
 // ends the kernel with a status code instead of spinning.
 #include "b200_internal.h"
+#include "b200_hmis_body.h"
 
 int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row, int cf_init, int *d_cf, int *iterations);
 
@@ -26,100 +27,11 @@ __global__ void fill_int_kernel(int n, int v, int *__restrict__ x) {
   if (i < n) x[i] = v;
 }
 
-struct Lists {                  // one FIFO per measure value: the order hypre_enter_on_lists / hypre_remove_point keep
-  int *head, *tail, *next, *prev;
-  int nb, maxm, bad;
-  __device__ void enter(int m, int i) {
-    if (m < 0 || m >= nb) { bad = 1; return; }
-    next[i] = -1;
-    prev[i] = tail[m];
-    if (tail[m] >= 0) next[tail[m]] = i; else head[m] = i;
-    tail[m] = i;
-    if (m > maxm) maxm = m;
-  }
-  __device__ void remove(int m, int i) {
-    if (m < 0 || m >= nb) { bad = 1; return; }
-    const int p = prev[i], q = next[i];
-    if (p >= 0) next[p] = q; else head[m] = q;
-    if (q >= 0) prev[q] = p; else tail[m] = p;
-    for (int guard = 0; guard < nb && maxm > 0 && head[maxm] < 0; guard++) maxm--;
-  }
-};
-
-// markers as in par_coarsen.c:860-865: C_PT 1, F_PT -1, Z_PT -2, SF_PT -3, SC_PT 3, UNDECIDED 0
 __global__ void ruge_first_pass_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ S_j, const int *__restrict__ T_i,
                                        const int *__restrict__ T_j, int agg2, int nb, int *cf, int *meas, int *next, int *prev,
                                        int *head, int *tail, int *status) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Lists L{head, tail, next, prev, nb, 0, 0};
-  int num_left = 0;
-  for (int j = 0; j < n; j++) {                                   // :1130-1158, measures = row sums of S^T (:1056-1059)
-    meas[j] = T_i[j + 1] - T_i[j];
-    if (S_i[j + 1] - S_i[j] == 0) { cf[j] = agg2 ? 3 : -3; meas[j] = 0; }
-    else { cf[j] = 0; num_left++; }
-  }
-  for (int j = 0; j < n; j++) {                                   // :1179-1222
-    const int measure = meas[j];
-    if (cf[j] == -3 || cf[j] == 3) continue;
-    if (measure > 0) { L.enter(measure, j); continue; }
-    cf[j] = -2;                                                   // nothing depends on j: f_pnt = Z_PT
-    for (int k = S_i[j]; k < S_i[j + 1]; k++) {
-      const int nabor = S_j[k];
-      if (cf[nabor] == -3 || cf[nabor] == 3) continue;
-      if (nabor < j) {
-        int nm = meas[nabor];
-        if (nm > 0) L.remove(nm, nabor);
-        nm = ++meas[nabor];
-        L.enter(nm, nabor);
-      } else {
-        ++meas[nabor];
-      }
-    }
-    --num_left;
-  }
-  for (int step = 0; step < n && num_left > 0; step++) {          // :1245-1320, at most one C point per step
-    const int index = head[L.maxm];
-    if (index < 0 || index >= n) { L.bad = 2; break; }
-    const int measure = meas[index];
-    cf[index] = 1;
-    meas[index] = 0;
-    --num_left;
-    L.remove(measure, index);
-    for (int j = T_i[index]; j < T_i[index + 1]; j++) {           // the points that depend on the new C point become F
-      const int nabor = T_j[j];
-      if (cf[nabor] != 0) continue;
-      cf[nabor] = -1;
-      L.remove(meas[nabor], nabor);
-      --num_left;
-      for (int k = S_i[nabor]; k < S_i[nabor + 1]; k++) {         // ... and what they depend on gains a measure point
-        const int n2 = S_j[k];
-        if (cf[n2] != 0) continue;
-        L.remove(meas[n2], n2);
-        ++meas[n2];
-        L.enter(meas[n2], n2);
-      }
-    }
-    for (int j = S_i[index]; j < S_i[index + 1]; j++) {           // what the C point depends on loses a measure point
-      const int nabor = S_j[j];
-      if (cf[nabor] != 0) continue;
-      int m2 = meas[nabor];
-      L.remove(m2, nabor);
-      meas[nabor] = --m2;
-      if (m2 > 0) { L.enter(m2, nabor); continue; }
-      cf[nabor] = -1;
-      --num_left;
-      for (int k = S_i[nabor]; k < S_i[nabor + 1]; k++) {
-        const int n2 = S_j[k];
-        if (cf[n2] != 0) continue;
-        L.remove(meas[n2], n2);
-        ++meas[n2];
-        L.enter(meas[n2], n2);
-      }
-    }
-  }
-  for (int i = 0; i < n; i++)
-    if (cf[i] == 3) cf[i] = 1;                                    // :1337-1343 SC_PT -> C_PT
-  *status = L.bad ? L.bad : (num_left > 0 ? 3 : 0);
+  *status = b200_ruge_first_pass_body(n, S_i, S_j, T_i, T_j, agg2, nb, cf, meas, next, prev, head, tail);
 }
 }  // namespace
 

@@ -243,3 +243,34 @@ def test_config_1_literal_driver_default_known_answer(oracle_bin):
         mine = refio.read_dump(path)
     for k in gold:
         assert np.array_equal(gold[k], mine[k]), k
+
+
+HMIS_CASES = [["-n", 12, 12, 12, "-rlx", 18], ["-n", 9, 9, 9, "-27pt", "-rlx", 18], ["-n", 14, 13, 12, "-difconv", "-rlx", 18],
+              ["-n", 24, 20, 1, "-rotate", "-alpha", 45, "-eps", 0.001, "-rlx", 18], ["-n", 11, 10, 9, "-perturb", 8, "-rlx", 18, "-th", 0.5],
+              ["-n", 1, 1, 9, "-rlx", 18]]
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args", HMIS_CASES)
+def test_device_hmis_algorithm_replayed_on_the_host(args, tmp_path):
+    """No GPU here, so the two halves of the device HMIS are checked as far as a host can: (1) the text the device runs for
+    the sequential first pass (csrc/b200_hmis_body.h) is compiled for the host by tests/host_harness and must give the same
+    markers as the Python replay; (2) that replay followed by the replay of the device's PMIS sweeps (tests/hmis_emul.py)
+    must give the reference's CF markers on every level."""
+    import struct
+    import hmis_emul
+    exe = os.path.join(str(tmp_path), "ruge_body_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(ROOT, "tests", "host_harness", "ruge_body_check.cpp")], check=True)
+    d, _ = refio.run_ref(args + ["-keepT", 1])                     # no -pmis: the reference coarsens with HMIS
+    for l in range(int(d["hdr"][3]) - 1):
+        I, J, _, _ = refio.csr(d, "S", l)
+        n = I.size - 1
+        rs = hmis_emul.ruge(I, J, n)
+        fin, fout = os.path.join(str(tmp_path), "s.bin"), os.path.join(str(tmp_path), "cf.bin")
+        with open(fin, "wb") as f:
+            f.write(struct.pack("<ii", n, J.size)); f.write(I.astype(np.int32).tobytes()); f.write(J.astype(np.int32).tobytes())
+        subprocess.run([exe, fin, fout], check=True)
+        out = np.fromfile(fout, dtype=np.int32)
+        assert out[0] == 0 and np.array_equal(out[1:], rs), ("first pass", l)
+        cf, _ = hmis_emul.pmis_device_style(I, J, n, rs)
+        assert np.array_equal(cf, d["CF%d" % l]), ("CF", l)
