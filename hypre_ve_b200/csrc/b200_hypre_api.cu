@@ -255,13 +255,14 @@ static HYPRE_Int ij_set(HYPRE_IJMatrix m, HYPRE_Int nrows, HYPRE_Int *ncols, con
   if (!m) return err_arg(1);
   if (nrows == 0) return g_error_flag;
   if (nrows < 0) return err_arg(2);
-  if (!ncols) return err_arg(3);
   if (!rows) return err_arg(4);
   if (!cols) return err_arg(5);
   if (!values) return err_arg(6);
   if (!m->initialized || !m->ij) return err_arg(1);
   NEED_HANDLE();
   int rejected = 0;
+  std::vector<int> ones;
+  if (!ncols) { ones.assign((size_t)nrows, 1); ncols = ones.data(); }      // NULL = one entry per row (IJMatrix_parcsr.c:916)
   CALL(b200_ij_set_values(h, m->ij, nrows, ncols, rows, cols, values, add ? 1 : 0, &rejected), "HYPRE_IJMatrixSetValues");
   if (rejected) {
     // the reference stashes off-processor rows for the owner (IJMatrix_parcsr.c:1395-1450); with one rank per

@@ -846,7 +846,9 @@ static void cheby_solve(amg_t *g, int l, const double *f, double *u)
    }
    free(orig); free(r); free(v); free(tmp);
 }
-static int g_relax_down = 18, g_relax_up = 18;   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
+static int g_relax_down = 18, g_relax_up = 18;
+static int g_user_relax = -1;        /* hypre_ParAMGDataUserRelaxType: the -rlx value, -1 when only the library defaults are set */
+static int g_coarse_relax = 9;       /* grid_relax_type[3]: 9 = Gaussian elimination unless coarsening stalled (see amg_setup) */   /* grid_relax_type[1], [2] (par_amg.c:206-209, :1650-1672) */
 static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, int max_coarse)
 {
    int l = 0, i;
@@ -865,7 +867,12 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
          csr_free(&S2); free(cfn);
       }
       for (i = 0; i < n; i++) if (cf[i] == 1) nc++;
-      if (nc == 0 || nc == n) { csr_free(&S); free(cf); break; }
+      if (nc == 0 || nc == n)
+      {  /* no coarse grid: stop, and the coarsest solve becomes ONE sweep of grid_relax_type[0] -- the -rlx type, or 3 with
+            the library defaults (par_amg_setup.c:1484-1497, par_amg.c:2100-2102) */
+         g_coarse_relax = g_user_relax > -1 ? g_user_relax : 3;
+         csr_free(&S); free(cf); break;
+      }
       if (l < g_agg_nl) g->P[l] = multipass(&g->A[l], &S, cf, &nc);
       else g->P[l] = extpi(&g->A[l], &S, cf, pmax, &nc);
       for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;            /* par_lr_interp.c:1888-1894 */
@@ -897,7 +904,7 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    }
    g->V = (double *) xcalloc(g->A[0].n, sizeof(double));
    csr_t *Ac = &g->A[g->nl - 1];
-   if (Ac->n <= max_coarse)
+   if (Ac->n <= max_coarse && g_coarse_relax == 9 && g->nl > 1)
    {  /* par_gauss_elim.c:100-115 */
       int n = Ac->n, jj; g->ge_n = n; g->ge = (double *) xcalloc((size_t) n * n, sizeof(double));
       for (i = 0; i < n; i++) for (jj = Ac->i[i]; jj < Ac->i[i + 1]; jj++) g->ge[i * n + Ac->j[jj]] = Ac->a[jj];
@@ -973,6 +980,8 @@ static void cycle(amg_t *g, const double *f, double *u)
       const double *F = level ? g->F[level] : f; double *U = level ? g->U[level] : u;
       int num_sweep = (nl > 1) ? g_ns[cycle_param] : 1;
       int type = (cycle_param == 2) ? g_relax_up : g_relax_down;
+      if (nl == 1) type = g_user_relax > -1 ? g_user_relax : 6;        /* no coarsening at all: one sweep of the user's type, else 6 (par_cycle.c:289-300) */
+      else if (cycle_param == 3 && g_coarse_relax != 9) { type = g_coarse_relax; num_sweep = 1; }
       for (j = 0; j < num_sweep; j++)
       {
          if (level == nl - 1 && g->ge)
@@ -1316,6 +1325,7 @@ int main(int argc, char **argv)
       return 0;
    }
    if (rlx > -1) g_relax_down = g_relax_up = rlx; else { g_relax_down = 13; g_relax_up = 14; }
+   g_user_relax = rlx;
    amg_t g;
    double t0 = now();
    amg_setup(&g, A, th, mxrs, Pmx, 9);
@@ -1327,6 +1337,22 @@ int main(int argc, char **argv)
    t0 = now();
    double bi_prod = dot(N, b, b), eps = tol * tol, i_prod = 0, gamma, gamma_old, krylov_rel = 0;
    int it = 0;
+   if (solver_id == 0)
+   {  /* BoomerAMG as the solver: hypre_BoomerAMGSolve (par_amg_solve.c:143-311), cycles until ||f - A u|| / ||f|| < tol */
+      double rhs_norm = sqrt(dot(N, b, b)), resid, rel = 1.0;
+      memcpy(r, b, sizeof(double) * N); matvec(-1.0, &A, x, 1.0, r, r);
+      resid = sqrt(dot(N, r, r)); rel = rhs_norm ? resid / rhs_norm : resid;
+      norms[0] = resid;
+      while (rel >= tol && it < max_iter)
+      {
+         cycle(&g, b, x);
+         memcpy(r, b, sizeof(double) * N); matvec(-1.0, &A, x, 1.0, r, r);
+         resid = sqrt(dot(N, r, r)); rel = rhs_norm ? resid / rhs_norm : resid;
+         norms[++it] = resid;
+      }
+      krylov_rel = rel;
+      goto solved;
+   }
    if (solver_id == 3) { it = gmres(&g, &A, b, x, k_dim, tol, max_iter, norms, &krylov_rel); goto solved; }
    if (solver_id == 9) { it = bicgstab(&g, &A, b, x, tol, max_iter, norms, &krylov_rel); goto solved; }
    memcpy(r, b, sizeof(double) * N);
