@@ -310,3 +310,21 @@ def test_boomeramg_as_solver_restatement_matches_the_reference_driver(oracle_bin
                          env=dict(os.environ, OMP_NUM_THREADS="1")).stdout
     assert int(re.search(r"BoomerAMG Iterations = (\d+)", ref).group(1)) == int(its)
     assert re.search(r"Final Relative Residual Norm = (\S+)", ref).group(1) == rel
+
+
+@pytest.mark.parametrize("flags,its,levels,opc", [
+    (["-pmis"], 10, 7, 2.725555),                                               # default smoother 13/14 on one thread
+    (["-pmis", "-rlx", 18, "-agg_nl", 1], 27, 6, 1.306381),
+    (["-27pt", "-pmis"], 9, 6, 1.208921),
+    (["-27pt", "-pmis", "-rlx", 18], 14, 6, 1.208921),
+    (["-c", 1, 1, 0.001, "-pmis", "-agg_nl", 1, "-rlx", 18], 31, 9, 1.426037),
+    (["-difconv", "-pmis", "-agg_nl", 1, "-rlx", 18], 32, 6, 1.305040),
+    (["-hmis"], 8, 8, 3.153179),                                               # configs[0] as written
+])
+def test_survey_known_answers_at_50_cubed(oracle_bin, flags, its, levels, opc):
+    """SURVEY.md 8c, "known answers generated here" for `ij -n 50 50 50 -solver 1 ...` (np = 1): iteration counts, level counts
+    and operator complexities (sum of nnz(A_l) / nnz(A_0), the driver's "operator = " line) reproduced by the restatement"""
+    out = subprocess.run([oracle_bin, "-n", "50", "50", "50"] + [str(f) for f in flags], check=True, capture_output=True, text=True).stdout
+    assert "levels=%d iterations=%d " % (levels, its) in out, out
+    nnz = [int(x) for x in re.findall(r"level \d+ rows=\d+ nnz=(\d+)", out)]
+    assert abs(sum(nnz) / nnz[0] - opc) < 5e-7, sum(nnz) / nnz[0]
