@@ -951,6 +951,21 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
       return;
    }
    if (type == 16) { cheby_solve(g, l, f, u); return; }
+   if (type == 0)
+   {  /* weighted Jacobi, weight 1 (par_relax.c:139-248): every point from the previous iterate, zero diagonals skipped */
+      memcpy(v, u, sizeof(double) * n);
+      for (i = 0; i < n; i++)
+      {
+         if (A->a[A->i[i]] != 0.0)
+         {
+            double res = f[i];
+            for (j = A->i[i] + 1; j < A->i[i + 1]; j++) res -= A->a[j] * v[A->j[j]];
+            u[i] *= 0.0;                                  /* one_minus_weight */
+            u[i] += 1.0 * res / A->a[A->i[i]];
+         }
+      }
+      return;
+   }
    int classic = (type == 3 || type == 4 || type == 6);
    int fwd = (type == 3 || type == 13 || type == 6 || type == 8), bwd = (type == 4 || type == 14 || type == 6 || type == 8);
    if (!fwd && !bwd) { fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2); }
@@ -969,6 +984,7 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
 /* One multigrid cycle, parcsr_ls/par_cycle.c:180-622: the level-counter state machine (V: cycle_type 1, W: 2, F-cycle flag),
  * num_grid_sweeps[1..3] sweeps on the way down / up / on the coarsest grid (par_amg.c:1934-1962, :1990-2030). */
 static int g_ns[4] = { 1, 1, 1, 1 }, g_cycle_type = 1, g_fcycle = 0;
+static double g_cycle_op_count;     /* hypre_ParAMGDataCycleOpCount: nnz(A_level) per relaxation sweep of the last cycle (par_cycle.c:352) */
 static void cycle(amg_t *g, const double *f, double *u)
 {
    int i, j, k, nl = g->nl, level = 0, cycle_param = 1, not_finished = 1, fcycle_lev = nl - 2;
@@ -984,6 +1000,7 @@ static void cycle(amg_t *g, const double *f, double *u)
       else if (cycle_param == 3 && g_coarse_relax != 9) { type = g_coarse_relax; num_sweep = 1; }
       for (j = 0; j < num_sweep; j++)
       {
+         g_cycle_op_count += (double) g->A[level].i[g->A[level].n];
          if (level == nl - 1 && g->ge)
          {  /* grid_relax_type[3] = 9 (par_gauss_elim.c) */
             int n = g->ge_n; double *T = (double *) xmalloc(sizeof(double) * n * n), *b = (double *) xmalloc(sizeof(double) * n);
@@ -1260,7 +1277,7 @@ int main(int argc, char **argv)
 {
    int nx = 10, ny = 10, nz = 10, pt27 = 0, Pmx = 4, max_iter = 100, i, matvec_reps = 0, rlx = -1, perturb = 0;
    double cx = 1, cy = 1, cz = 1, th = 0.25, tol = 1e-8, mxrs = 1.0, ax = 1, ay = 1, az = 1;
-   int difconv = 0, atype = 0, solver_id = 1, k_dim = 5, rotate = 0;
+   int difconv = 0, atype = 0, solver_id = 1, k_dim = 5, rotate = 0, xisone = 0;
    double rot_alpha = 0., rot_eps = 1.;
    const char *ofile = NULL;
    for (i = 1; i < argc; i++)
@@ -1268,7 +1285,8 @@ int main(int argc, char **argv)
       if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
       else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
       else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
-      else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);     /* 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB */
+      else if (!strcmp(argv[i], "-xisone")) xisone = 1;                       /* ij.c:629: b = A * ones (solution of all ones) */
+      else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);     /* 0 AMG, 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB */
       else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
       else if (!strcmp(argv[i], "-rotate")) rotate = 1;
       else if (!strcmp(argv[i], "-alpha")) rot_alpha = atof(argv[++i]);
@@ -1316,6 +1334,7 @@ int main(int argc, char **argv)
    if (perturb) perturb_operator(N, A.i, A.j, A.a, (unsigned) perturb);
    double *b = (double *) xmalloc(sizeof(double) * N), *x = (double *) xcalloc(N, sizeof(double));
    for (i = 0; i < N; i++) b[i] = 1.0;
+   if (xisone) { double *ones = (double *) xmalloc(sizeof(double) * N); for (i = 0; i < N; i++) ones[i] = 1.0; matvec(1.0, &A, ones, 0.0, b, b); free(ones); }
    if (matvec_reps > 0)
    {
       double *y = (double *) xcalloc(N, sizeof(double)), t0;
@@ -1343,14 +1362,23 @@ int main(int argc, char **argv)
       memcpy(r, b, sizeof(double) * N); matvec(-1.0, &A, x, 1.0, r, r);
       resid = sqrt(dot(N, r, r)); rel = rhs_norm ? resid / rhs_norm : resid;
       norms[0] = resid;
+      double resid_init = resid;
       while (rel >= tol && it < max_iter)
       {
+         g_cycle_op_count = 0;                                            /* par_amg_solve.c:245 */
          cycle(&g, b, x);
          memcpy(r, b, sizeof(double) * N); matvec(-1.0, &A, x, 1.0, r, r);
          resid = sqrt(dot(N, r, r)); rel = rhs_norm ? resid / rhs_norm : resid;
          norms[++it] = resid;
       }
       krylov_rel = rel;
+      {  /* closing statistics of hypre_BoomerAMGSolve (par_amg_solve.c:327-391) */
+         double tc = 0, tv = 0;
+         for (i = 0; i < g.nl; i++) { tc += (double) g.A[i].i[g.A[i].n]; tv += (double) g.A[i].n; }
+         printf("amg_oracle: conv_factor=%f grid=%f operator=%f cycle=%f\n",
+                (it > 0 && resid_init) ? pow(resid / resid_init, 1.0 / (double) it) : 1.0, tv / (double) N, tc / (double) A.nnz,
+                g_cycle_op_count / (double) A.nnz);
+      }
       goto solved;
    }
    if (solver_id == 3) { it = gmres(&g, &A, b, x, k_dim, tol, max_iter, norms, &krylov_rel); goto solved; }

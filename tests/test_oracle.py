@@ -288,6 +288,14 @@ def test_reference_saved_known_answers_of_its_own_test_suite(oracle_bin):
     out = subprocess.run([oracle_bin, "-n", "2", "2", "2", "-agg_nl", "1", "-mxrs", "0.1", "-hmis", "-solver", "0"], check=True,
                          capture_output=True, text=True).stdout
     assert "levels=1 iterations=10 relres=7.834527e-09" in out
+    # default.saved lists the SAME four numbers for np = 1 (-pmis), np = 2 and np = 3 (-P 1 1 N -pmis1): the reference's own record
+    # that measures drawn from the global row index make the hierarchy independent of the partition -- the rule the
+    # row-partitioned device path follows.  The restatement (no truncation, relax 0, AMG as the solver, b = A*1)
+    # prints them digit for digit.
+    out = subprocess.run([oracle_bin, "-pmis", "-Pmx", "0", "-rlx", "0", "-xisone", "-solver", "0"], check=True, capture_output=True,
+                         text=True).stdout
+    assert "conv_factor=0.678738 grid=1.407000 operator=3.252344 cycle=6.499062" in out
+    assert "iterations=48 relres=8.350438e-09" in out
     if refio.have_ref():
         ij = os.path.join(ROOT, "oracle", "_ref", "ij")
         out = subprocess.run([ij, "-pmis", "-Pmx", "0", "-rlx", "0", "-xisone"], check=True, capture_output=True, text=True,
