@@ -37,6 +37,22 @@ static void csr_free(csr_t *A) { free(A->i); free(A->j); free(A->a); A->i = A->j
 /* ---- generators: parcsr_ls/par_laplace.c:124-300 and par_difconv.c:247-330 (7-pt: centre, z-,y-,x-,x+,y+,z+; v = centre,
  *      x-, y-, z-, x+, y+, z+ -- the Laplacian passes v[4..6] = v[1..3]) and
  *      parcsr_ls/par_laplace_27pt.c fill pass (centre, then (dz,dy,dx) lexicographic), 1 rank ---- */
+/* -P P Q R: the operator in the numbering a P x Q x R process grid gives it (hypre_map, par_laplace.c:363-387: boxes in
+ * rank order, lexicographic inside a box), i.e. the matrix an np = P*Q*R run holds, gathered.  Entries keep stencil order. */
+static int g_P[3] = { 1, 1, 1 };
+static void part1d(int length, int nprocs, int id, int *lo, int *hi)      /* hypre_GeneratePartitioning, seq_mv/genpart.c:18-38 */
+{
+   int size = length / nprocs, rest = length - size * nprocs;
+   *lo = id * size + (id < rest ? id : rest);
+   *hi = *lo + size + (id < rest ? 1 : 0);
+}
+static int owner1d(int i, int length, int nprocs) { int id, lo, hi; for (id = 0; id < nprocs; id++) { part1d(length, nprocs, id, &lo, &hi); if (i >= lo && i < hi) return id; } return nprocs - 1; }
+static int box_index(int nx, int ny, int nz, int ix, int iy, int iz)
+{
+   int p = owner1d(ix, nx, g_P[0]), q = owner1d(iy, ny, g_P[1]), r = owner1d(iz, nz, g_P[2]), xa, xb, ya, yb, za, zb;
+   part1d(nx, g_P[0], p, &xa, &xb); part1d(ny, g_P[1], q, &ya, &yb); part1d(nz, g_P[2], r, &za, &zb);
+   return za * nx * ny + ya * nx * (zb - za) + xa * (yb - ya) * (zb - za) + ((iz - za) * (yb - ya) + (iy - ya)) * (xb - xa) + (ix - xa);
+}
 static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
 {
    int n = nx * ny * nz, pass, ix, iy, iz, k;
@@ -74,6 +90,19 @@ static csr_t gen_laplace(int nx, int ny, int nz, int pt27, const double *v)
          }
       }
       if (!pass) A = csr_new(n, n, cnt, 1); else A.i[n] = cnt;
+   }
+   if (g_P[0] * g_P[1] * g_P[2] > 1)
+   {  /* renumber rows and columns into the process grid's order; every row keeps its entry order */
+      int *perm = (int *) xmalloc(sizeof(int) * n), *len = (int *) xcalloc(n + 1, sizeof(int)), row = 0, r, p;
+      csr_t B = csr_new(n, n, A.nnz, 1);
+      for (iz = 0; iz < nz; iz++) for (iy = 0; iy < ny; iy++) for (ix = 0; ix < nx; ix++, row++) perm[row] = box_index(nx, ny, nz, ix, iy, iz);
+      for (r = 0; r < n; r++) len[perm[r] + 1] = A.i[r + 1] - A.i[r];
+      for (r = 0; r < n; r++) len[r + 1] += len[r];
+      memcpy(B.i, len, sizeof(int) * (n + 1));
+      for (r = 0; r < n; r++)
+         for (p = 0, k = A.i[r]; k < A.i[r + 1]; k++, p++) { B.j[B.i[perm[r]] + p] = perm[A.j[k]]; B.a[B.i[perm[r]] + p] = A.a[k]; }
+      free(perm); free(len); csr_free(&A);
+      A = B;
    }
    return A;
 }
@@ -489,14 +518,25 @@ static int g_gs_blocks = 1;   /* the reference's num_threads = hypre_NumThreads(
 /* hypre_ParCSRComputeL1Norms (ams.c:571-760), which hands over to ...L1NormsThreads (ams.c:3398-3650) when
  * num_threads > 1: option 1 = sum |a_ij|; option 4 = |a_ii| + 0.5 * sum of |a_ij| over the entries OUTSIDE
  * the thread block [ns, ne) of row i (plus the offd block: none on one rank), truncated by Remark 6.2 */
+/* Gauss-Seidel blocks of a level: the reference's OpenMP threads split the rows evenly (par_relax.c:4400-4412); with -P the
+ * blocks are the RANKS of an np = P*Q*R run instead, i.e. each rank's own rows -- its box on the finest level, its C points
+ * on every coarser one (g_blk[level], filled by amg_setup) */
+static int *g_blk[64];
+static const int *g_blk_cur = NULL;
+static void block_range(int n, int T, int k, int *ns, int *ne)
+{
+   if (g_blk_cur) { *ns = g_blk_cur[k]; *ne = g_blk_cur[k + 1]; return; }
+   int size = n / T, rest = n - size * T;
+   if (k < rest) { *ns = k * size + k; *ne = (k + 1) * size + k + 1; }
+   else { *ns = k * size + rest; *ne = (k + 1) * size + rest; }
+}
 static double *l1_norms(const csr_t *A, int option)
 {
    double *l1 = (double *) xmalloc(sizeof(double) * A->n); int i, j, k, T = g_gs_blocks, n = A->n;
    for (k = 0; k < T; k++)
    {
-      int size = n / T, rest = n - size * T, ns, ne;
-      if (k < rest) { ns = k * size + k; ne = (k + 1) * size + k + 1; }
-      else { ns = k * size + rest; ne = (k + 1) * size + rest; }
+      int ns, ne;
+      block_range(n, T, k, &ns, &ne);
       for (i = ns; i < ne; i++)
       {
          double s = 0.0, d = 0.0;
@@ -877,6 +917,12 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
       else g->P[l] = extpi(&g->A[l], &S, cf, pmax, &nc);
       for (i = 0; i < n; i++) if (cf[i] == -3) cf[i] = -1;            /* par_lr_interp.c:1888-1894 */
       g->cf[l] = cf; g->S[l] = S;
+      if (g_blk[l])
+      {  /* the ranks keep their own C points: block k of the next level = the C points among block k's rows */
+         int T = g_gs_blocks, k, c = 0, r = 0;
+         g_blk[l + 1] = (int *) xcalloc(T + 1, sizeof(int));
+         for (k = 0; k < T; k++) { for (; r < g_blk[l][k + 1]; r++) if (cf[r] > 0) c++; g_blk[l + 1][k + 1] = c; }
+      }
       g->R[l] = transpose(&g->P[l]);                                  /* par_csr_triplemat.c:874-876 */
       if (g_mod_rap2)
       {  /* hypre_ParCSRMatrixRAPKT: R (A P), par_csr_triplemat.c:872-888 */
@@ -898,6 +944,7 @@ static void amg_setup(amg_t *g, csr_t A0, double theta, double mrs, int pmax, in
    for (i = 0; i < g->nl; i++)
    {
       int n = g->A[i].n;
+      g_blk_cur = g_blk[i];
       g->l1[i] = l1_norms(&g->A[i], g_relax_down == 18 ? 1 : (g_relax_down == 7 ? 5 : 4));      /* par_amg_setup.c:3018-3100 */
       g->F[i] = (double *) xcalloc(n, sizeof(double)); g->U[i] = (double *) xcalloc(n, sizeof(double));
       if (g_relax_down == 16 && (i < g->nl - 1 || g->A[i].n > max_coarse)) cheby_setup(g, i);      /* par_amg_setup.c:3137-3160 */
@@ -971,11 +1018,11 @@ static void relax(amg_t *g, int l, int type, const double *f, double *u)
    if (!fwd && !bwd) { fprintf(stderr, "amg_oracle: relax type %d not restated\n", type); exit(2); }
    double *tmp = (double *) xmalloc(sizeof(double) * n);
    memcpy(tmp, u, sizeof(double) * n);
+   g_blk_cur = g_blk[l];
    for (j = 0; j < T; j++)
    {
-      int size = n / T, rest = n - size * T, ns, ne;
-      if (j < rest) { ns = j * size + j; ne = (j + 1) * size + j + 1; }
-      else { ns = j * size + rest; ne = (j + 1) * size + rest; }
+      int ns, ne;
+      block_range(n, T, j, &ns, &ne);
       if (fwd) for (i = ns; i < ne; i++) gs_row(A, l1, f, u, tmp, ns, ne, i, classic);
       if (bwd) for (i = ne - 1; i > ns - 1; i--) gs_row(A, l1, f, u, tmp, ns, ne, i, classic);
    }
@@ -1285,6 +1332,7 @@ int main(int argc, char **argv)
       if (!strcmp(argv[i], "-n")) { nx = atoi(argv[++i]); ny = atoi(argv[++i]); nz = atoi(argv[++i]); }
       else if (!strcmp(argv[i], "-27pt")) pt27 = 1;
       else if (!strcmp(argv[i], "-c")) { cx = atof(argv[++i]); cy = atof(argv[++i]); cz = atof(argv[++i]); }
+      else if (!strcmp(argv[i], "-P")) { g_P[0] = atoi(argv[++i]); g_P[1] = atoi(argv[++i]); g_P[2] = atoi(argv[++i]); }
       else if (!strcmp(argv[i], "-xisone")) xisone = 1;                       /* ij.c:629: b = A * ones (solution of all ones) */
       else if (!strcmp(argv[i], "-solver")) solver_id = atoi(argv[++i]);     /* 0 AMG, 1 AMG-PCG, 3 AMG-GMRES, 9 AMG-BiCGSTAB */
       else if (!strcmp(argv[i], "-k")) k_dim = atoi(argv[++i]);
@@ -1330,6 +1378,17 @@ int main(int argc, char **argv)
       v[0] = -2 * (2 * ac + bc + 2 * cc); v[1] = 2 * ac + bc; v[2] = bc + 2 * cc; v[3] = -bc;
    }
    csr_t A = gen_laplace(nx, ny, nz, rotate ? 2 : pt27, v);
+   if (g_P[0] * g_P[1] * g_P[2] > 1)
+   {  /* -P: one Gauss-Seidel block per rank, in rank order (p fastest): the boxes of the process grid */
+      int T = g_P[0] * g_P[1] * g_P[2], k = 0, p, q, r, lo, hi, sx, sy, sz;
+      g_gs_blocks = T;
+      g_blk[0] = (int *) xcalloc(T + 1, sizeof(int));
+      for (r = 0; r < g_P[2]; r++) for (q = 0; q < g_P[1]; q++) for (p = 0; p < g_P[0]; p++, k++)
+      {
+         part1d(nx, g_P[0], p, &lo, &hi); sx = hi - lo; part1d(ny, g_P[1], q, &lo, &hi); sy = hi - lo; part1d(nz, g_P[2], r, &lo, &hi); sz = hi - lo;
+         g_blk[0][k + 1] = g_blk[0][k] + sx * sy * sz;
+      }
+   }
    int N = A.n;
    if (perturb) perturb_operator(N, A.i, A.j, A.a, (unsigned) perturb);
    double *b = (double *) xmalloc(sizeof(double) * N), *x = (double *) xcalloc(N, sizeof(double));
