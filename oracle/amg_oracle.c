@@ -1,15 +1,19 @@
 /* amg_oracle.c -- CPU RESTATEMENT (port) of the reference's hot path.  TEST INFRASTRUCTURE ONLY:
  * nothing under hypre_ve_b200/ includes, links or executes this file.
  *
- * A plain sequential C restatement of BoomerAMG-PCG for the in-scope configuration
- * (single rank, PMIS, ext+i interpolation with P_max_elmts truncation, modularized Galerkin
- * product, l1-Jacobi V(1,1), Gaussian elimination on the coarsest grid, PCG with the 2-norm test).
+ * A plain sequential C restatement of the BoomerAMG path on one rank: the generators (7-point, 27-point, convection-diffusion,
+ * rotated anisotropy; -P gives the numbering of a process grid), strength, PMIS and HMIS coarsening (-pmis / -hmis), aggressive
+ * levels with multipass interpolation, ext+i interpolation with P_max_elmts truncation, both Galerkin-product orders, the
+ * smoothers 0 / 7 / 18 (Jacobi family), 3 / 4 / 6 / 8 / 13 / 14 (hybrid Gauss-Seidel with thread or rank blocks) and 16
+ * (Chebyshev), V / W / F cycles, Gaussian elimination or the stalled-coarsening sweep on the coarsest grid, and the drivers
+ * -solver 0 (BoomerAMG alone), 1 (PCG, 2-norm test), 3 (GMRES(k)), 9 (BiCGSTAB).
  * Every routine cites the reference lines it follows (paths under /root/reference/src).
  *
  * PINNED: tests/test_oracle.py checks this program's output bit for bit (integers AND doubles)
  * against the golden dumps in tests/golden/, which were produced by the reference's own CPU build
  * (oracle/_ref/ref_dump, see tests/golden/make_golden.py), and -- where oracle/_ref exists --
- * against live reference runs.
+ * against live reference runs, the SURVEY's known answers, and the two single-process jobs of the reference's own regression
+ * suite (src/test/TEST_ij/default.saved, coarsening.saved).
  *
  * CLI and output format are those of oracle/ref_dump.c so the two can be diffed record by record.
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off: no FMA, like the reference's x86-64 build)
