@@ -347,3 +347,23 @@ def test_survey_known_answers_at_50_cubed(oracle_bin, flags, its, levels, opc):
     assert "levels=%d iterations=%d " % (levels, its) in out, out
     nnz = [int(x) for x in re.findall(r"level \d+ rows=\d+ nnz=(\d+)", out)]
     assert abs(sum(nnz) / nnz[0] - opc) < 5e-7, sum(nnz) / nnz[0]
+
+
+@pytest.mark.skipif(not refio.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,kw", [
+    (["-n", 7, 6, 5, "-difconv"], dict()),
+    (["-n", 7, 6, 5, "-difconv", "-a", 3, -2, 1, "-atype", 3], dict(a=(3, -2, 1), atype=3)),
+    (["-n", 7, 6, 5, "-difconv", "-a", 2, 1, 0, "-atype", 1, "-c", 1, 2, 0.5], dict(a=(2, 1, 0), atype=1, c=(1, 2, 0.5))),
+    (["-n", 7, 4, 5, "-difconv", "-atype", 2], dict(atype=2)),
+])
+def test_host_side_difconv_coefficients_equal_the_reference_drivers(args, kw):
+    """hypre_ve_b200.difconv_values (what ParCsr.difconv / DistMatrix.difconv hand to the generator kernel) against the seven
+    values BuildParDifConv computes (ij.c:8266-8409), read back from the operator the reference generated: bit-equal"""
+    import hypre_ve_b200 as hb
+    d, _ = refio.run_ref(args + ["-noamg"])
+    I, J, a, _ = refio.csr(d, "A", 0)
+    nx, ny, nz = args[1:4]
+    r = ((nz // 2) * ny + ny // 2) * nx + nx // 2                   # an interior row: centre, z-, y-, x-, x+, y+, z+
+    assert I[r + 1] - I[r] == 7
+    v = hb.difconv_values(nx, ny, nz, **kw)
+    assert list(a[I[r]:I[r + 1]]) == [v[0], v[3], v[2], v[1], v[4], v[5], v[6]]
