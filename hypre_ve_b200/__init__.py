@@ -37,6 +37,8 @@ SIGNATURES = {
     "b200_memcpy_d2d": (_i, [_vp, _vp, _vp, _sz]),
     "b200_memset": (_i, [_vp, _vp, _i, _sz]),
     "b200_launch_count": (C.c_longlong, []),
+    "b200_pool_trim": (_i, [_vp, C.POINTER(_sz)]),
+    "b200_pool_stats": (_i, [_vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(_sz)]),
     "b200_timer_start": (_i, [_vp]),
     "b200_timer_stop_ms": (_i, [_vp, _dp]),
     "b200_csr_create": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _i, C.POINTER(_vp)]),
@@ -103,6 +105,8 @@ SIGNATURES = {
     "b200_comm_create_single": (_i, [C.POINTER(_vp)]),
     "b200_comm_group_create": (_i, [_i, C.POINTER(_vp)]),
     "b200_comm_group_destroy": (_i, [_vp]),
+    "b200_comm_group_abort": (_i, [_vp]),
+    "b200_comm_abort": (_i, [_vp]),
     "b200_comm_create_threads": (_i, [_vp, _i, C.POINTER(_vp)]),
     "b200_comm_nccl_unique_id": (_i, [C.c_char_p]),
     "b200_comm_create_nccl": (_i, [_vp, _i, _i, C.c_char_p, C.POINTER(_vp)]),
@@ -602,10 +606,36 @@ class Handle:
                                       C.byref(its), C.byref(rel), _np_ptr(norms), C.byref(conv)))
         return its.value, rel.value, norms[: its.value + 1], conv.value
 
+    def trim(self):
+        """return the pool's entirely free slabs to the driver; returns the bytes released"""
+        n = _sz()
+        _chk(_lib.b200_pool_trim(self.p, C.byref(n)))
+        return n.value
+
+    def pool_stats(self):
+        """(reserved, in_use, peak) bytes of this handle's device pool"""
+        a, b, c = _sz(), _sz(), _sz()
+        _chk(_lib.b200_pool_stats(self.p, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
     def close(self):
+        """b200_finalize: returns every slab to the driver; objects created on this handle are dead afterwards"""
         if self.p:
-            _chk(_lib.b200_finalize(self.p))
-            self.p = None
+            p, self.p = self.p, None
+            _chk(_lib.b200_finalize(p))
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Comm:
@@ -645,6 +675,18 @@ class Comm:
         g = _vp()
         _chk(_lib.b200_comm_group_create(nranks, C.byref(g)))
         return g
+
+    @staticmethod
+    def group_abort(group):
+        _lib.b200_comm_group_abort(group)
+
+    @staticmethod
+    def group_destroy(group):
+        _lib.b200_comm_group_destroy(group)
+
+    def abort(self):
+        if self.p:
+            _lib.b200_comm_abort(self.p)
 
     @property
     def rank(self):

@@ -15,6 +15,7 @@
 #include "b200_internal.h"
 #include "b200_comm.h"
 #include <dlfcn.h>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <algorithm>
@@ -29,6 +30,7 @@ struct NcclApi {
   ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
   ncclResult_t (*Send)(const void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
@@ -38,14 +40,16 @@ struct NcclApi {
   bool ok = false;
 };
 static NcclApi g_nccl;
+static std::mutex g_nccl_mu;
 static int load_nccl() {
+  std::lock_guard<std::mutex> lk(g_nccl_mu);      // several rank threads may open communicators at once
   if (g_nccl.ok) return 0;
   void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);     // the copy torch has loaded, if any
   if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
   if (!lib) B200_FAIL("cannot dlopen libnccl.so.2 (import torch first, or put NCCL on LD_LIBRARY_PATH)");
 #define B200_SYM(name) *(void **)(&g_nccl.name) = dlsym(lib, "nccl" #name); if (!g_nccl.name) B200_FAIL("NCCL symbol nccl" #name " missing");
-  B200_SYM(GetUniqueId) B200_SYM(CommInitRank) B200_SYM(CommDestroy) B200_SYM(Send) B200_SYM(Recv)
+  B200_SYM(GetUniqueId) B200_SYM(CommInitRank) B200_SYM(CommDestroy) B200_SYM(CommAbort) B200_SYM(Send) B200_SYM(Recv)
   B200_SYM(GroupStart) B200_SYM(GroupEnd) B200_SYM(AllGather) B200_SYM(GetErrorString)
 #undef B200_SYM
   g_nccl.ok = true;
@@ -67,13 +71,30 @@ struct b200_comm_group_s {
   // mailbox: what each rank exposes for the current exchange
   std::vector<std::vector<b200_xfer>> sends;          // [rank] -> list of (peer, ptr, bytes)
   std::vector<const void *> host_ptr;                 // [rank] host pointer for allgather
-  void barrier() {
+  bool aborted = false;       // set by a rank that failed (b200_comm_group_abort): its peers return an error instead of waiting
+  int timeout_s = 300;        // B200_COMM_TIMEOUT_S: a peer that never arrives turns into an error, not a hang
+  // returns 0, or nonzero when the group was aborted / a peer did not arrive in time
+  int barrier() {
     std::unique_lock<std::mutex> lk(mu);
+    if (aborted) return 1;
     long long gen = generation;
-    if (++arrived == nranks) { arrived = 0; ++generation; cv.notify_all(); }
-    else cv.wait(lk, [&] { return generation != gen; });
+    if (++arrived == nranks) { arrived = 0; ++generation; cv.notify_all(); return 0; }
+    bool ok = cv.wait_for(lk, std::chrono::seconds(timeout_s), [&] { return generation != gen || aborted; });
+    if (!ok) { aborted = true; cv.notify_all(); return 2; }
+    return (generation != gen) ? 0 : 1;
+  }
+  void abort() {
+    std::lock_guard<std::mutex> lk(mu);
+    aborted = true;
+    cv.notify_all();
   }
 };
+#define B200_BARRIER(g)                                                                                          \
+  do {                                                                                                           \
+    int rb__ = (g)->barrier();                                                                                   \
+    if (rb__) B200_FAIL(rb__ == 2 ? "rank group: a peer did not reach the exchange in time (B200_COMM_TIMEOUT_S)" \
+                                  : "rank group aborted: another rank failed");                                  \
+  } while (0)
 
 struct b200_comm_s {
   int rank = 0, nranks = 1;
@@ -94,10 +115,13 @@ extern "C" int b200_comm_group_create(int nranks, b200_comm_group *out) {
   g->nranks = nranks;
   g->sends.resize(nranks);
   g->host_ptr.resize(nranks, nullptr);
+  if (const char *e = getenv("B200_COMM_TIMEOUT_S")) { int t = atoi(e); if (t > 0) g->timeout_s = t; }
   *out = g;
   return 0;
 }
 extern "C" int b200_comm_group_destroy(b200_comm_group g) { delete g; return 0; }
+// a rank that failed calls this so that its peers, blocked in (or arriving at) an exchange, return an error
+extern "C" int b200_comm_group_abort(b200_comm_group g) { if (g) g->abort(); return 0; }
 extern "C" int b200_comm_create_threads(b200_comm_group g, int rank, b200_comm *out) {
   if (!g || rank < 0 || rank >= g->nranks) B200_FAIL("bad group / rank");
   b200_comm_s *c = new b200_comm_s();
@@ -130,6 +154,12 @@ extern "C" int b200_comm_destroy(b200_handle h, b200_comm c) {
   delete c;
   return 0;
 }
+extern "C" int b200_comm_abort(b200_comm c) {
+  if (!c) return 0;
+  if (c->backend == 1 && c->nccl) { g_nccl.CommAbort(c->nccl); c->nccl = nullptr; }
+  if (c->backend == 2 && c->group) c->group->abort();
+  return 0;
+}
 extern "C" int b200_comm_rank(b200_comm c) { return c ? c->rank : 0; }
 extern "C" int b200_comm_size(b200_comm c) { return c ? c->nranks : 1; }
 
@@ -156,7 +186,7 @@ int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> 
   b200_comm_group_s *g = c->group;
   B200_CUDA(cudaStreamSynchronize(h->stream));           // my send buffers are complete
   g->sends[c->rank] = sends;
-  g->barrier();
+  B200_BARRIER(g);
   for (const auto &r : recvs) {
     if (!r.bytes) continue;
     const void *src = nullptr;
@@ -167,7 +197,7 @@ int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> 
     B200_CUDA(cudaMemcpyAsync(r.ptr, src, r.bytes, cudaMemcpyDeviceToDevice, h->stream));
   }
   B200_CUDA(cudaStreamSynchronize(h->stream));
-  g->barrier();                                          // senders may now reuse their buffers
+  B200_BARRIER(g);                                       // senders may now reuse their buffers
   return 0;
 }
 
@@ -177,9 +207,9 @@ int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_
   if (c->backend == 2) {
     b200_comm_group_s *g = c->group;
     g->host_ptr[c->rank] = mine;
-    g->barrier();
+    B200_BARRIER(g);
     for (int r = 0; r < c->nranks; r++) memcpy((char *)all + (size_t)r * bytes, g->host_ptr[r], bytes);
-    g->barrier();
+    B200_BARRIER(g);
     return 0;
   }
   const size_t need = bytes * (size_t)(c->nranks + 1);

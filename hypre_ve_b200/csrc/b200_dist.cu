@@ -1250,7 +1250,10 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
       return 0;
     }
     if (amg->gs) {
-      if (L.A->L->gs) return b200_gs_relax(h, L.A->L->gs, L.A->L, amg->relax_down, true, F, L.l1, U);
+      if (L.A->L->gs) {
+        if (L.A->halo->ng) B200_CUDA(cudaMemsetAsync(U + L.A->n_owned_cols, 0, sizeof(double) * (size_t)L.A->halo->ng, h->stream));
+        return b200_gs_relax(h, L.A->L->gs, L.A->L, amg->relax_down, true, F, L.l1, U);
+      }
       return 0;
     }
     if (L.n) {
@@ -1268,6 +1271,9 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
     auto relax = [&](dist_level &L, int type, const double *Fl, double *Ul, bool zero) -> int {
       b200_dist_matrix M = L.A;
       if (!zero && (M->halo->ng || M->halo->n_send)) B200_TRY(b200_halo_forward_f64(h, c, M->halo, Ul, Ul + M->n_owned_cols));
+      // zero iterate: the reference's Vext is all zeros for BOTH halves of a symmetric sweep (par_relax.c:3540-3570 builds
+      // it once per call); the backward half reads the ghost tail, which still holds the previous cycle's halo -> clear it
+      if (zero && M->halo->ng) B200_CUDA(cudaMemsetAsync(Ul + M->n_owned_cols, 0, sizeof(double) * (size_t)M->halo->ng, h->stream));
       return b200_gs_relax(h, M->L->gs, M->L, type, zero, Fl, L.l1, Ul);
     };
     U[0] = u;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cstdint>
+#include <atomic>
 #include <functional>
 #include <string>
 #include <vector>
@@ -65,7 +66,7 @@ struct b200_parcsr_s {
 };
 
 extern thread_local std::string g_b200_err;
-extern long long g_b200_launches;
+extern std::atomic<long long> g_b200_launches;   // incremented from several rank threads in the threads-as-ranks backend
 
 int b200_set_error(const char *file, int line, const char *msg);
 

@@ -16,6 +16,7 @@ struct b200_pool_s {
   static constexpr size_t ALIGN = 512;
   static constexpr size_t SLAB = (size_t)1 << 30;
   std::vector<void *> slabs;
+  std::vector<size_t> slab_size;
   std::map<char *, size_t> free_by_addr;              // address -> size
   std::multimap<size_t, char *> free_by_size;         // size -> address
   std::map<char *, size_t> used;                      // address -> size
@@ -58,11 +59,15 @@ int b200_pool_alloc(b200_handle h, void **out, size_t bytes) {
   size_t n = (bytes + b200_pool_s::ALIGN - 1) / b200_pool_s::ALIGN * b200_pool_s::ALIGN;
   auto it = P->free_by_size.lower_bound(n);
   if (it == P->free_by_size.end()) {
-    size_t slab = n > b200_pool_s::SLAB ? n : b200_pool_s::SLAB;
+    // slabs grow geometrically from 64 MiB to 1 GiB: a handle that only ever holds a small problem (one rank of a
+    // threads-as-ranks test, a coarse-level service) does not reserve a gigabyte, a large one reaches 1 GiB slabs after 5
+    size_t want = P->total < ((size_t)64 << 20) ? ((size_t)64 << 20) : (P->total > b200_pool_s::SLAB ? b200_pool_s::SLAB : P->total);
+    size_t slab = n > want ? n : want;
     void *s = nullptr;
     cudaError_t e = cudaMalloc(&s, slab);
     if (e != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e));
     P->slabs.push_back(s);
+    P->slab_size.push_back(slab);
     P->total += slab;
     P->free_by_addr[(char *)s] = slab;
     it = P->free_by_size.emplace(slab, (char *)s);
@@ -93,8 +98,41 @@ int b200_pool_free(b200_handle h, void *ptr) {
   return 0;
 }
 
+// Return every slab that is completely free to the driver (cudaFree synchronises the device: call it between
+// phases, never inside a timed region).  Long-lived handles (a test session, a service) call this after
+// destroying a hierarchy so that the high-water mark of one problem does not stay reserved for good.
+extern "C" int b200_pool_trim(b200_handle h, size_t *bytes_released) {
+  b200_pool_s *P = h->pool;
+  size_t released = 0;
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  for (size_t k = 0; k < P->slabs.size();) {
+    char *s = (char *)P->slabs[k];
+    auto it = P->free_by_addr.find(s);
+    // free blocks never coalesce across a slab start (add_free), so the slab is entirely free iff one free block covers it
+    size_t n = (it != P->free_by_addr.end()) ? it->second : 0;
+    bool whole = n == P->slab_size[k];
+    if (whole) {
+      P->erase_size(n, s);
+      P->free_by_addr.erase(it);
+      B200_CUDA(cudaFree(s));
+      P->total -= n;
+      released += n;
+      P->slabs.erase(P->slabs.begin() + k);
+      P->slab_size.erase(P->slab_size.begin() + k);
+    } else k++;
+  }
+  if (bytes_released) *bytes_released = released;
+  return 0;
+}
+extern "C" int b200_pool_stats(b200_handle h, size_t *reserved, size_t *in_use, size_t *peak) {
+  if (reserved) *reserved = h->pool->total;
+  if (in_use) *in_use = h->pool->in_use;
+  if (peak) *peak = h->pool->peak;
+  return 0;
+}
+
 thread_local std::string g_b200_err;
-long long g_b200_launches = 0;
+std::atomic<long long> g_b200_launches{0};
 
 int b200_set_error(const char *file, int line, const char *msg) {
   char buf[1024];
@@ -104,7 +142,7 @@ int b200_set_error(const char *file, int line, const char *msg) {
 }
 
 extern "C" const char *b200_last_error(void) { return g_b200_err.c_str(); }
-extern "C" long long b200_launch_count(void) { return g_b200_launches; }
+extern "C" long long b200_launch_count(void) { return g_b200_launches.load(); }
 
 extern "C" int b200_init(int device, b200_handle *out) {
   int ndev = 0;

