@@ -174,6 +174,10 @@ int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> 
     return 0;
   }
   if (c->backend == 1) {
+    bool any = false;
+    for (const auto &s : sends) any = any || s.bytes;
+    for (const auto &r : recvs) any = any || r.bytes;
+    if (!any) return 0;                                  // nothing to or from this rank: no NCCL call at all
     B200_NCCL(g_nccl.GroupStart());
     for (const auto &s : sends)
       if (s.bytes) B200_NCCL(g_nccl.Send(s.ptr, s.bytes, ncclInt8, s.peer, c->nccl, h->stream));

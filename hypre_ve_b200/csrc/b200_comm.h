@@ -24,6 +24,8 @@ struct b200_halo_s {
   int n_owned = 0;                       // ids owned by this rank: [first, first + n_owned)
   int first = 0;
   int ng = 0;                            // number of ghosts
+  bool any_traffic = false;              // some rank sends or receives under this plan: the exchange is collective, so a rank
+                                         // without ghosts and without send entries still takes part (rank-group backend)
   int *d_ghost_gid = nullptr;            // device, sorted [ng]
   std::vector<int> recv_cnt, recv_off;   // per peer, into the ghost array
   std::vector<int> send_cnt, send_off;   // per peer, into d_send_idx

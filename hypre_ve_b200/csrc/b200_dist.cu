@@ -304,6 +304,7 @@ int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, 
   std::vector<int> all((size_t)R * R);
   B200_TRY(b200_comm_allgather_host(h, c, p->recv_cnt.data(), sizeof(int) * R, all.data()));
   for (int r = 0; r < R; r++) { p->send_cnt[r] = all[(size_t)r * R + me]; p->send_off[r + 1] = p->send_off[r] + p->send_cnt[r]; }
+  for (size_t k = 0; k < all.size(); k++) if (all[k]) p->any_traffic = true;
   p->n_send = p->send_off[R];
   B200_TRY(b200_dalloc<int>(h, &p->d_send_idx, p->n_send));
   char *buf = nullptr;
@@ -679,7 +680,7 @@ extern "C" int b200_dist_matrix_download(b200_handle h, b200_dist_matrix M, int 
 // halo of x (job 1) straight into the ghost tail, then ONE kernel over [owned | ghost]
 static int dist_spmv(b200_handle h, b200_comm c, b200_dist_matrix M, double *x, double *y, int mode, double alpha, double beta,
                      const double *b, const double *d) {
-  if (M->halo->ng || M->halo->n_send) B200_TRY(b200_halo_forward_f64(h, c, M->halo, x, x + M->n_owned_cols));
+  if (M->halo->any_traffic) B200_TRY(b200_halo_forward_f64(h, c, M->halo, x, x + M->n_owned_cols));
   return b200_csr_spmv_epi(h, M->L, x, y, mode, alpha, beta, b, d);
 }
 extern "C" int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_dist_matrix M, double *d_x, double beta,
@@ -701,7 +702,7 @@ extern "C" int b200_dist_relax_gs(b200_handle h, b200_comm c, b200_dist_matrix M
   double *l1 = nullptr;
   B200_TRY(b200_dalloc<double>(h, &l1, M->n));
   B200_TRY(b200_l1_norms_blocks(h, A, 4, blocks, l1));
-  if (M->halo->ng || M->halo->n_send) B200_TRY(b200_halo_forward_f64(h, c, M->halo, d_u, d_u + M->n_owned_cols));
+  if (M->halo->any_traffic) B200_TRY(b200_halo_forward_f64(h, c, M->halo, d_u, d_u + M->n_owned_cols));
   B200_TRY(b200_gs_relax(h, A->gs, A, relax_type, false, d_f, l1, d_u));
   B200_TRY(b200_dfree(h, l1));
   return 0;
@@ -1270,7 +1271,7 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
     // in-place hybrid Gauss-Seidel smoothing: halo of u (old values for everything off rank), then the sweep
     auto relax = [&](dist_level &L, int type, const double *Fl, double *Ul, bool zero) -> int {
       b200_dist_matrix M = L.A;
-      if (!zero && (M->halo->ng || M->halo->n_send)) B200_TRY(b200_halo_forward_f64(h, c, M->halo, Ul, Ul + M->n_owned_cols));
+      if (!zero && M->halo->any_traffic) B200_TRY(b200_halo_forward_f64(h, c, M->halo, Ul, Ul + M->n_owned_cols));
       // zero iterate: the reference's Vext is all zeros for BOTH halves of a symmetric sweep (par_relax.c:3540-3570 builds
       // it once per call); the backward half reads the ghost tail, which still holds the previous cycle's halo -> clear it
       if (zero && M->halo->ng) B200_CUDA(cudaMemsetAsync(Ul + M->n_owned_cols, 0, sizeof(double) * (size_t)M->halo->ng, h->stream));

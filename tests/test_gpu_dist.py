@@ -459,10 +459,10 @@ def test_dist_amg_pcg_with_hybrid_gauss_seidel(handle, nranks, grid, dims, T):
     amg.destroy(); A.destroy()
 
 
-@pytest.mark.parametrize("nranks,dims,rlx", [(2, (12, 11, 10), 8), (3, (9, 8, 13), 8), (2, (12, 11, 10), -1), (2, (10, 9, 12), 6)])
+@pytest.mark.parametrize("nranks,dims,rlx", [(2, (12, 11, 10), 8), (3, (9, 8, 13), 8), (2, (12, 11, 10), -1), (4, (10, 9, 13), 13)])
 def test_nrank_hybrid_gs_pcg_history_equals_the_restatement(nranks, dims, rlx):
     """BoomerAMG-PCG across z-slab ranks with ONE Gauss-Seidel block per rank (the reference's mpirun -np N, one thread):
-    symmetric l1-GS 8 / classic 6 / the default 13-14.  The first sweep of every cycle starts from a zero iterate, so both
+    symmetric l1-GS 8 / forward l1-GS 13 / the default 13-14.  The first sweep of every cycle starts from a zero iterate, so both
     halves of a symmetric sweep must see zero ghosts (par_relax.c builds Vext once per call) -- the ghost tail still holds
     the previous cycle's halo.  Oracle: oracle/amg_oracle.c -P 1 1 N (rank-shaped blocks on every level, pinned against the
     reference's own np = 8 record in tests/test_oracle.py); iteration count equal, residual history to 1e-10."""
