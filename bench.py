@@ -5,8 +5,8 @@
     python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU build
 
 A step = one full pass of the hot path on BASELINE config 2 (`ij -laplacian -n 256 256 256
--solver 1 -pmis -interptype 6 -Pmx 4 -rlx 18 -mod_rap2 1`, rhs = 1, x0 = 0, tol 1e-8):
-BoomerAMG setup + PCG solve.  Prints ONE JSON line (rank 0).
+-solver 1 -pmis -rlx 18`: PMIS, ext+i with Pmx 4, l1-Jacobi, the library's default fused Galerkin
+order; rhs = 1, x0 = 0, tol 1e-8): BoomerAMG setup + PCG solve.  Prints ONE JSON line (rank 0).
 
   value        device-timed setup+solve seconds per step, matrix/rhs resident in HBM (CUDA events)
   e2e          the same through the C-ABI with HOST CSR/rhs buffers: H2D copy of A and b, setup,
@@ -14,12 +14,17 @@ BoomerAMG setup + PCG solve.  Prints ONE JSON line (rank 0).
   roofline     dominant kernel = the streaming CSR SpMV family (SpMV / residual / l1-Jacobi / P / R):
                timed live as a standalone y=A0*x loop (the `ij -solver -1` analogue),
                algorithmic bytes 12*nnz + 4*(N+1) + 16*N / CUDA-event time
-  cpu_baseline oracle/_ref (the reference compiled in place) timed on the host cores
+  roofline_solve  algorithmic bytes of ONE PCG iteration computed from the actual hierarchy (formula in
+               solve_bytes_per_iteration below = SURVEY.md 8d per operator application) / device time per iteration
+  cpu_baseline the UNMODIFIED reference driver oracle/_ref/ij (the reference compiled in place), same flags,
+               all host cores, "wall clock time" lines of test/ij.c:4301-4314
 
-Multi-GPU (N>1): one process per GPU under torchrun; rows partitioned over a P x Q x R process grid
-like `ij -P` (1x1x1, 2x1x1, 2x2x1, 2x2x2), weak scaling with 256^3 unknowns per GPU (config 5 at
-N=8: 512^3).  Halo exchange and Krylov reductions go over NCCL/NVLink inside libhypre_b200.so; torch
-only launches the ranks and broadcasts the NCCL unique id.
+Multi-GPU (N>1): one process per GPU under torchrun; weak scaling with 256^3 unknowns per GPU on the global
+grids 256x256x512 / 256x512x512 / 512^3 (config 5) for N = 2 / 4 / 8, rows partitioned like `ij -P 1 1 N`
+(z-slabs: the global numbering stays lexicographic, so hierarchy and iteration count are comparable with -- and in
+the tests bit-identical to -- the reference's np = 1 run of the same grid; `--grid box` selects 2x1x1 / 2x2x1 /
+2x2x2 boxes instead).  Halo exchange and Krylov reductions run inside libhypre_b200.so over NVLink; torch only
+launches the ranks and carries the communicator id.
 """
 import argparse
 import json
@@ -38,10 +43,51 @@ sys.path.insert(0, ROOT)
 N1 = 256                       # config 2 grid edge
 # the driver's own flags for config 2, `ij -n 256 256 256 -solver 1 -pmis -rlx 18`: Galerkin product in the library's
 # default fused order (ModuleRAP2 0; 22 iterations at 256^3), on one GPU and across ranks alike
-REF_ARGS = ["-pmis", "-rlx", "18", "-keepT", "1", "-nodump"]
-REF_ARGS_DIST = REF_ARGS
+REF_ARGS = ["-solver", "1", "-pmis", "-rlx", "18", "-keepT", "1"]
 WORKLOAD = ("ij 3D 7-pt Laplacian 256^3 BoomerAMG-PCG, PMIS + ext+i(Pmx 4) interp + l1-Jacobi, tol 1e-8 "
             "(ij -n 256 256 256 -solver 1 -pmis -rlx 18)")
+
+
+def global_dims(world, n1, grid):
+    """global grid and process grid of the weak-scaled job: n1^3 unknowns per GPU"""
+    if grid == "box":
+        from hypre_ve_b200 import launch
+        P, Q, R = launch.process_grid(world)
+        return (n1 * P, n1 * Q, n1 * R), (P, Q, R)
+    fx = {1: (1, 1, 1), 2: (1, 1, 2), 4: (1, 2, 2), 8: (2, 2, 2)}.get(world, (1, 1, world))
+    return (n1 * fx[0], n1 * fx[1], n1 * fx[2]), (1, 1, world)
+
+
+def reference_iterations(dims):
+    """PCG iteration count of the reference CPU build (np = 1) on this grid, from the committed table
+    tests/golden/reference_iterations.json (made by tests/golden/make_reference_iterations.py); None if not recorded"""
+    try:
+        tab = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_iterations.json")))["counts"]
+        return tab.get("%d %d %d" % tuple(dims))
+    except Exception:
+        return None
+
+
+def solve_bytes_per_iteration(levels):
+    """Algorithmic HBM bytes of one AMG-PCG iteration (every input array read once, every output written
+    once; FP64 values, int32 indices).  levels = [(N_l, nnz(A_l), nnz(P_l))...] (nnz(P) = 0 on the coarsest level).
+      per level l < L-1 of the V(1,1) cycle:
+        pre-smooth from a zero iterate   u = w f / l1                      24 N
+        residual  r = f - A u                                             12 nnzA + 4 N + 24 N
+        restrict  f_c = R r  (R = P^T stored)                             12 nnzP + 4 Nc + 8 N + 8 Nc
+        prolong   u += P e                                                12 nnzP + 4 N + 8 Nc + 16 N
+        post-smooth u = u + w (f - A u) / l1  (fused l1-Jacobi)           12 nnzA + 4 N + 32 N
+      coarsest level: dense Gaussian elimination on <= 9 unknowns (counted as 0)
+      PCG around it: s = A p (12 nnzA0 + 4 N + 16 N), <s,p> 16 N, x += a p 24 N, r -= a s 24 N, <r,z> and <r,r> 24 N,
+        p = z + b p 24 N"""
+    total = 0.0
+    for l, (n, nnz_a, nnz_p) in enumerate(levels[:-1]):
+        nc = levels[l + 1][0]
+        total += 24.0 * n + (12.0 * nnz_a + 28.0 * n) + (12.0 * nnz_p + 12.0 * nc + 8.0 * n) + (12.0 * nnz_p + 20.0 * n + 8.0 * nc) \
+            + (12.0 * nnz_a + 36.0 * n)
+    n0, nnz0, _ = levels[0]
+    total += 12.0 * nnz0 + 20.0 * n0 + (16.0 + 24.0 + 24.0 + 24.0 + 24.0) * n0
+    return total
 
 
 def spmv_traffic():
@@ -115,16 +161,19 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def run_reference(n1, threads, dist_flags=False):
-    """One setup+solve of the reference CPU build; returns (setup_s, solve_s, iterations)."""
-    exe = os.path.join(ROOT, "oracle", "_ref", "ref_dump")
+def run_reference(dims, threads, timeout=None):
+    """One setup+solve of the UNMODIFIED reference driver (oracle/_ref/ij = test/ij.c compiled in place against the
+    reference's own library); returns (setup_s, solve_s, iterations) from its wall-clock lines (ij.c:4301-4314)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ij")
     if not os.path.exists(exe):
-        raise RuntimeError("oracle/_ref/ref_dump missing: run __graft_entry__.build() where /root/reference exists")
+        raise RuntimeError("oracle/_ref/ij missing: run __graft_entry__.build() where /root/reference exists")
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false")
-    out = subprocess.run([exe, "-n", str(n1), str(n1), str(n1)] + (REF_ARGS_DIST if dist_flags else REF_ARGS), env=env, capture_output=True, text=True,
-                         check=True).stdout
-    m = re.search(r"iterations=(\d+) relres=(\S+) setup_s=(\S+) solve_s=(\S+)", out)
-    return float(m.group(3)), float(m.group(4)), int(m.group(1))
+    out = subprocess.run([exe, "-n"] + [str(d) for d in dims] + REF_ARGS, env=env, capture_output=True, text=True, check=True,
+                         timeout=timeout).stdout
+    m = re.search(r"PCG Setup:\s*\n\s*wall clock time = (\S+) seconds", out)
+    v = re.search(r"PCG Solve:\s*\n\s*wall clock time = (\S+) seconds", out)
+    k = re.search(r"^Iterations = (\d+)", out, re.M)
+    return float(m.group(1)), float(v.group(1)), int(k.group(1))
 
 
 def reference_arm(a):
@@ -132,57 +181,86 @@ def reference_arm(a):
     if rank != 0:
         return 0
     threads = host_threads()
-    # bounded sample: probe with 128^3, then use the full 256^3 workload only if K+W steps fit ~4 minutes
-    df = a.gpus > 1
-    s0, v0, _ = run_reference(128, threads, df)
-    est_full = 8.5 * (s0 + v0)
-    n1 = N1 if est_full * (a.steps + a.warmup) < 240 else 128
-    for _ in range(a.warmup):
-        run_reference(n1, threads, df)
-    t_set = t_sol = 0.0
-    its = 0
-    for _ in range(a.steps):
-        s, v, its = run_reference(n1, threads, df)
-        t_set += s
-        t_sol += v
-    # AMG-PCG work is linear in the number of unknowns; the N-GPU arm is weak-scaled (256^3 unknowns per GPU),
-    # so the same job on the host is N x 256^3 unknowns
-    scale = (N1 / n1) ** 3 * max(1, a.gpus)
-    per_step = (t_set + t_sol) / a.steps * scale
-    sample = "%d^3 run per step on all host threads, seconds scaled by %g (= unknown ratio) to the %d x 256^3 workload" % (
-        n1, scale, max(1, a.gpus))
-    if n1 == N1 and a.gpus <= 1:
-        sample = "full workload (256^3) per step"
-    line = {
-        "impl": "reference", "metric": "boomeramg_pcg_setup_plus_solve_seconds", "value": per_step, "unit": "s",
-        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": per_step * 1e3,
+    world = max(1, a.gpus)
+    dims, _ = global_dims(world, a.n, a.grid)
+    # bounded: probe with 128^3 (1/8 of one GPU's share), estimate the job linearly in the unknowns
+    s0, v0, _ = run_reference((128, 128, 128), threads)
+    est = (s0 + v0) * (dims[0] * dims[1] * dims[2]) / 128.0 ** 3 * 1.1
+    steps, warmup = a.steps, a.warmup
+    if est * (steps + warmup) > 240:          # the whole run must end within a few minutes: ONE real job, stated in the line
+        steps, warmup = 1, 0
+    base = {"impl": "reference", "metric": "boomeramg_pcg_setup_plus_solve_seconds", "unit": "s", "n_gpus": a.gpus}
+    if est > 400:
+        emit(dict(base, unavailable="the reference job %dx%dx%d is estimated at %.0f s on %d host threads (128^3 probe: %.2f s); "
+                                   "not run, and never extrapolated" % (dims + (est, threads, s0 + v0))))
+        return 0
+    try:
+        for _ in range(warmup):
+            run_reference(dims, threads, timeout=900)
+        t_set = t_sol = 0.0
+        its = 0
+        for _ in range(steps):
+            s_, v_, its = run_reference(dims, threads, timeout=900)
+            t_set += s_
+            t_sol += v_
+    except Exception as e:      # killed for memory, timeout: say so, never substitute a scaled number
+        emit(dict(base, unavailable="the reference job %dx%dx%d failed on this host: %s" % (dims + (str(e)[:200],))))
+        return 0
+    per_step = (t_set + t_sol) / steps
+    sample = "full workload %dx%dx%d per step, stock driver `ij -n ... %s`, %d step(s) after %d warm-up" % (
+        dims + (" ".join(REF_ARGS), steps, warmup))
+    line = dict(base, **{
+        "value": per_step, "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD if a.gpus <= 1 else WORKLOAD.replace("256^3", "%d x 256^3 (weak-scaled)" % a.gpus),
-                   "impl": "reference hypre 2.20 (SX-Aurora fork) CPU path, OpenMP, sequential MPI stubs"},
-        "setup_s": t_set / a.steps * scale, "solve_s": t_sol / a.steps * scale, "iterations": its,
+        "config": bench_config(world, a.n, a.grid),
+        "reference_impl": "hypre 2.20 (SX-Aurora fork) CPU path: unmodified test/ij.c, OpenMP, sequential MPI stubs (np = 1)",
+        "setup_s": t_set / steps, "solve_s": t_sol / steps, "iterations": its, "reference_iterations": its,
         "cpu_baseline": {"value": per_step, "unit": "s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": per_step, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }
+    })
     emit(line)
     return 0
 
 
+def workload_name(world, n1, grid):
+    if world <= 1:
+        return WORKLOAD if n1 == N1 else WORKLOAD.replace("256^3", "%d^3" % n1).replace("256 256 256", "%d %d %d" % (n1, n1, n1))
+    dims, pg = global_dims(world, n1, grid)
+    return ("ij 3D 7-pt Laplacian %dx%dx%d (%d^3 unknowns per GPU, -P %d %d %d) BoomerAMG-PCG, PMIS + ext+i(Pmx 4) interp + l1-Jacobi, "
+            "tol 1e-8 (ij -n %d %d %d -solver 1 -pmis -rlx 18)" % (dims + (n1,) + pg + dims))
+
+
+def bench_config(world, n1, grid):
+    """the `config` object: identical in this arm's line and in the reference arm's"""
+    dims, _ = global_dims(world, n1, grid)
+    return {"workload": workload_name(world, n1, grid), "global_grid": "%dx%dx%d" % dims, "unknowns_per_gpu": n1 ** 3,
+            "l2": "per-GPU operator (1.7 GB at 256^3) larger than the 126 MB L2; no flush needed"}
+
+
+def cpu_baseline_inline(dims, note):
+    """the reference driver on all host cores, one run of `dims` (reported baseline of this line)"""
+    threads = host_threads()
+    try:
+        s_, v_, cits = run_reference(dims, threads, timeout=600)
+        return {"value": s_ + v_, "unit": "s", "cores": threads, "kind": "reference",
+                "sample": "oracle/_ref/ij (unmodified reference driver), %s" % note,
+                "setup_s": s_, "solve_s": v_, "iterations": cits}
+    except Exception as e:      # the baseline is reporting only; never fail the GPU line for it
+        return {"value": None, "unit": "s", "cores": threads, "kind": "reference", "sample": "unavailable: %s" % str(e)[:200]}
+
+
 def main_dist(a, rank, world, local_rank):
-    """N > 1: row-partitioned BoomerAMG-PCG, 256^3 unknowns per GPU (weak scaling)."""
+    """N > 1: row-partitioned BoomerAMG-PCG, n1^3 unknowns per GPU (weak scaling)."""
     import torch
     import torch.distributed as dist
     import hypre_ve_b200 as hb
     from hypre_ve_b200 import launch
 
-    try:
-        P, Q, R = launch.process_grid(world)
-    except ValueError as e:
-        raise SystemExit(str(e))
     n1 = a.n
-    nx, ny, nz = n1 * P, n1 * Q, n1 * R
+    (nx, ny, nz), (P, Q, R) = global_dims(world, n1, a.grid)
     h = hb.Handle(local_rank)
-    # NCCL communicator of the library: rank 0 creates the id, torch.distributed broadcasts it
+    # communicator of the library: rank 0 creates the id, torch.distributed broadcasts it
     uid = launch.broadcast_bytes(hb.Comm.nccl_unique_id() if rank == 0 else b"", 0, 128, "cuda")
     comm = hb.Comm.nccl(h, world, rank, uid)
 
@@ -197,18 +275,26 @@ def main_dist(a, rank, world, local_rank):
     x = A.vector(0.0)
     prm = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
 
-    def step():
+    levels = []
+
+    def step(record=False):
         amg = hb.DistAmg(h, comm, prm, A)
         s_ms = amg.setup_ms
         h.fill(x, 0.0)
         h.timer_start()
         its, rel, _ = hb.dist_pcg(h, comm, A, amg, b, x, tol=1e-8, max_iter=100)
         v_ms = h.timer_stop_ms()
+        if record and not levels:
+            for l in range(amg.num_levels):
+                ia = amg.level_A(l).info
+                levels.append((ia["local_rows"], ia["local_nnz"], amg.level_P(l).info["local_nnz"] if l < amg.num_levels - 1 else 0))
         amg.destroy()
         return s_ms, v_ms, its, rel
 
-    for _ in range(a.warmup):
-        step()
+    for k in range(a.warmup):
+        step(record=(k == 0))
+    if not levels:
+        step(record=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = h.launch_count()
@@ -220,21 +306,29 @@ def main_dist(a, rank, world, local_rank):
         t_sol += v_ms
     barrier()
     launches = h.launch_count() - launches0
-    # end to end: the operator is generated on the device (no host matrix exists at 512^3); the host
-    # buffers of this path are the rhs (H2D) and the solution (D2H) of every rank
+    # end to end through the rows-from-the-caller entry point (b200_dist_matrix_create_from_host = IJ assembly per rank,
+    # hypre_IJMatrixAssembleParCSR): every rank's CSR rows (global column ids) and rhs start in pinned HOST memory,
+    # are uploaded inside the timed region, and x comes back to the host
+    gi, gj, ga = A.download()
+    t_i, t_j, t_a = (torch.from_numpy(v).pin_memory() for v in (gi, gj, ga))
+    hi, hj, ha = (t.numpy() for t in (t_i, t_j, t_a))
     hb_host = torch.ones(n, dtype=torch.float64).pin_memory().numpy()
     hx_host = torch.empty(n, dtype=torch.float64).pin_memory().numpy()
+    h2d = hi.nbytes + hj.nbytes + ha.nbytes + hb_host.nbytes
     e2e_ms = 0.0
+    e2e_its = 0
     for k in range(a.steps + 1):
         barrier()
         h.timer_start()
-        hb._chk(hb._lib.b200_memcpy_h2d(h.p, b.ptr, hb._np_ptr(hb_host), hb_host.nbytes))
-        amg = hb.DistAmg(h, comm, prm, A)
-        h.fill(x, 0.0)
-        hb.dist_pcg(h, comm, A, amg, b, x, tol=1e-8, max_iter=100)
-        hb._chk(hb._lib.b200_memcpy_d2h(h.p, hb._np_ptr(hx_host), x.ptr, hx_host.nbytes))
+        A2 = hb.DistMatrix.from_rows(h, comm, hi, hj, ha)
+        b2 = A2.vector(0.0)
+        x2 = A2.vector(0.0)
+        hb._chk(hb._lib.b200_memcpy_h2d(h.p, b2.ptr, hb._np_ptr(hb_host), hb_host.nbytes))
+        amg = hb.DistAmg(h, comm, prm, A2)
+        e2e_its, _, _ = hb.dist_pcg(h, comm, A2, amg, b2, x2, tol=1e-8, max_iter=100)
+        hb._chk(hb._lib.b200_memcpy_d2h(h.p, hb._np_ptr(hx_host), x2.ptr, hx_host.nbytes))
         ms = h.timer_stop_ms()
-        amg.destroy()
+        amg.destroy(); A2.destroy(); b2.free(); x2.free()
         if k > 0:
             e2e_ms += ms
     # distributed SpMV sweep (ij -solver -1 analogue): halo exchange + one kernel per repetition
@@ -251,29 +345,41 @@ def main_dist(a, rank, world, local_rank):
     sampler.join()
     per = launch.reduce_over_ranks([t_set / a.steps, t_sol / a.steps, e2e_ms / a.steps, spmv_ms], "max", "cuda")
     gn, gnnz = launch.reduce_over_ranks([float(n), float(nnz)], "sum", "cuda")
+    flat = [float(v) for lv in levels for v in lv] + [0.0] * (3 * 32 - 3 * len(levels))
+    glev = launch.reduce_over_ranks(flat, "sum", "cuda")
+    glevels = [tuple(glev[3 * l:3 * l + 3]) for l in range(len(levels))]
     set_s, sol_s, e2e_s, spmv_ms = per[0] / 1e3, per[1] / 1e3, per[2] / 1e3, per[3]
     spmv_bytes = 12.0 * gnnz + 4.0 * (gn + world) + 16.0 * gn
     peak, peak_src = peaks()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    it_bytes = solve_bytes_per_iteration(glevels)
+    it_gbs = it_bytes * its / sol_s / 1e9
+    ref_its = reference_iterations((nx, ny, nz)) if a.grid == "slab" else None
     line = {
         "metric": "boomeramg_pcg_setup_plus_solve_seconds", "value": set_s + sol_s, "unit": "s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": (set_s + sol_s) * 1e3,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "ij 3D 7-pt Laplacian %dx%dx%d (-P %d %d %d, %d^3 per GPU) BoomerAMG-PCG, PMIS + ext+i(Pmx 4) + "
-                               "l1-Jacobi, tol 1e-8" % (nx, ny, nz, P, Q, R, n1),
-                   "rows_per_gpu": n, "nnz_per_gpu": nnz, "global_rows": int(gn), "global_nnz": int(gnnz),
-                   "parallelism": "row-partitioned ParCSR, %d GPUs, halo + allreduce over NCCL" % world,
-                   "l2": "per-GPU operator (1.7 GB) larger than the 126 MB L2; no flush needed"},
+        "config": bench_config(world, n1, a.grid),
+        "problem": {"rows_per_gpu": n, "nnz_per_gpu": nnz, "global_rows": int(gn), "global_nnz": int(gnnz),
+                    "parallelism": "row-partitioned ParCSR (-P %d %d %d), %d GPUs, halo + reductions over NVLink" % (P, Q, R, world)},
         "setup_s": set_s, "solve_s": sol_s, "iterations": its, "final_rel_res": rel,
+        "reference_iterations": ref_its, "iterations_match_reference": (its == ref_its) if ref_its is not None else None,
+        "e2e_iterations": e2e_its,
         "spmv_gbs": achieved, "spmv_ms": spmv_ms,
         "roofline": {"bound": "hbm", "kernel": "halo exchange + spmv_pipe_kernel (y = A0*x, %d^3 per GPU)" % n1,
                      "achieved": achieved, "peak": peak * world, "peak_source": peak_src + " x n_gpus", "unit": "GB/s",
                      "frac": achieved / (peak * world), "algorithmic_bytes_per_launch": spmv_bytes / world, "traffic": None},
-        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": hb_host.nbytes * world, "d2h_bytes_per_step": hx_host.nbytes * world},
+        "roofline_solve": {"bound": "hbm", "what": "whole PCG iteration (V(1,1) cycle over %d levels + SpMV + BLAS-1), all GPUs" % len(glevels),
+                           "algorithmic_bytes_per_iteration": it_bytes, "ms_per_iteration": sol_s * 1e3 / max(1, its),
+                           "achieved": it_gbs, "peak": peak * world, "unit": "GB/s", "frac": it_gbs / (peak * world)},
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": hx_host.nbytes * world},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
     }
     if rank == 0:
+        if not a.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_inline((n1, n1, n1), "%d^3 = ONE GPU's share of this job (1/%d of the unknowns), "
+                                                       "seconds NOT scaled" % (n1, world))
         emit(line)
     A.destroy()
     dist.destroy_process_group()
@@ -287,18 +393,24 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--edge", dest="n", type=int, default=N1, help="grid edge per GPU (default: config 2, 256)")
+    ap.add_argument("--grid", choices=["slab", "box"], default="slab",
+                    help="N > 1: z-slabs (-P 1 1 N, lexicographic numbering = the reference's np = 1 job) or boxes (-P 2 2 2 ...)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     claim_stdout()
     if a.impl == "reference":
         return reference_arm(a)
 
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:
+        # kernels of one rank wait on flags that kernels of its neighbours raise (direct NVLink halos): load every kernel
+        # before the first launch, so that no first-time module load has to wait for a kernel that is itself waiting
+        os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
     import torch
     import torch.distributed as dist
     import hypre_ve_b200 as hb
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         torch.cuda.set_device(local_rank)
@@ -326,6 +438,8 @@ def main():
     h2d = hi.nbytes + hj.nbytes + ha.nbytes + hb_.nbytes
     d2h = hx.nbytes
 
+    levels = []
+
     def step_resident():
         amg = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
         h.timer_start()
@@ -336,6 +450,10 @@ def main():
         its, rel, _ = h.pcg(A, amg, b, x, tol=1e-8, max_iter=100)
         v_ms = h.timer_stop_ms()
         ph = amg.setup_times()
+        if not levels:
+            for l in range(amg.num_levels):
+                na, _, za = amg.level_A(l).dims
+                levels.append((na, za, amg.level_P(l).dims[2] if l < amg.num_levels - 1 else 0))
         amg.destroy()
         return s_ms, v_ms, its, rel, ph
 
@@ -395,15 +513,21 @@ def main():
     spmv_bytes = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * n
     peak, peak_src = peaks()
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
+    it_bytes = solve_bytes_per_iteration(levels)
+    it_gbs = it_bytes * its / sol_s / 1e9
+    ref_its = reference_iterations((n1, n1, n1))
     line = {
         "metric": "boomeramg_pcg_setup_plus_solve_seconds", "value": set_s + sol_s, "unit": "s",
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": (set_s + sol_s) * 1e3,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD if n1 == N1 else WORKLOAD.replace("256^3", "%d^3" % n1),
-                   "rows_per_gpu": n, "nnz_per_gpu": nnz,
-                   "parallelism": "1 GPU" if world == 1 else "replicas only (row-partitioned multi-GPU path not built yet)",
-                   "l2": "inputs (1.7 GB operator) larger than the 126 MB L2; no flush needed"},
+        "config": bench_config(1, n1, a.grid),
+        "problem": {"rows_per_gpu": n, "nnz_per_gpu": nnz, "parallelism": "1 GPU"},
         "setup_s": set_s, "solve_s": sol_s, "iterations": its, "final_rel_res": rel,
+        "reference_iterations": ref_its, "iterations_match_reference": (its == ref_its) if ref_its is not None else None,
+        "e2e_iterations": its_e,
+        "roofline_solve": {"bound": "hbm", "what": "whole PCG iteration (V(1,1) cycle over %d levels + SpMV + BLAS-1)" % len(levels),
+                           "algorithmic_bytes_per_iteration": it_bytes, "ms_per_iteration": sol_s * 1e3 / max(1, its),
+                           "achieved": it_gbs, "peak": peak, "unit": "GB/s", "frac": it_gbs / peak},
         "setup_phases_ms": dict(zip(["strength", "pmis", "interp", "trunc", "transpose", "rap", "l1_alloc", "total"],
                                     (phases / a.steps).round(3).tolist())),
         "spmv_gbs": achieved, "spmv_ms": spmv_ms,
@@ -415,15 +539,7 @@ def main():
         "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        try:
-            threads = host_threads()
-            s, v, cits = run_reference(128, threads)
-            line["cpu_baseline"] = {"value": (s + v) * 8.0, "unit": "s", "cores": threads, "kind": "reference",
-                                    "sample": "oracle/_ref/ref_dump, 128^3 sample (1/8 of the unknowns), seconds scaled by 8",
-                                    "setup_s_sample": s, "solve_s_sample": v, "iterations_sample": cits}
-        except Exception as e:      # the baseline is reporting only; never fail the GPU line for it
-            line["cpu_baseline"] = {"value": None, "unit": "s", "cores": host_threads(), "kind": "reference",
-                                    "sample": "unavailable: %s" % e}
+        line["cpu_baseline"] = cpu_baseline_inline((n1, n1, n1), "full workload %d^3, one run" % n1)
     if rank == 0:
         emit(line)
     A.destroy()

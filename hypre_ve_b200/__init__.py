@@ -106,6 +106,7 @@ SIGNATURES = {
     "b200_comm_group_create": (_i, [_i, C.POINTER(_vp)]),
     "b200_comm_group_destroy": (_i, [_vp]),
     "b200_comm_group_abort": (_i, [_vp]),
+    "b200_comm_threads_enable_p2p": (_i, [_vp, _vp]),
     "b200_comm_abort": (_i, [_vp]),
     "b200_comm_create_threads": (_i, [_vp, _i, C.POINTER(_vp)]),
     "b200_comm_nccl_unique_id": (_i, [C.c_char_p]),
@@ -654,6 +655,8 @@ class Comm:
     def threads(cls, handle, group, rank):
         p = _vp()
         _chk(_lib.b200_comm_create_threads(group, rank, C.byref(p)))
+        if os.environ.get("B200_P2P_THREADS") == "1":      # direct peer-to-peer halos / reductions between the rank threads
+            _chk(_lib.b200_comm_threads_enable_p2p(handle.p, p))
         return cls(handle, p)
 
     @classmethod

@@ -121,7 +121,7 @@ __global__ void jacobi_zero_kernel(size_t n, double w, const double *__restrict_
 // PCG vector updates with device-resident scalars (no host round trip between kernels)
 // sc[0]=gamma sc[1]=sdotp sc[2]=gamma_old sc[3]=i_prod sc[4]=alpha sc[5]=beta
 __global__ void pcg_alpha_kernel(double *sc) {
-  sc[4] = sc[0] / sc[1];          // alpha = gamma / <s,p>         (pcg.c:522)
+  sc[4] = (sc[1] != 0.0) ? sc[0] / sc[1] : 0.0;   // alpha = gamma / <s,p> (pcg.c:522); <s,p> = 0 is the error path (:516-521): x, r stay intact
   sc[2] = sc[0];                  // gamma_old = gamma             (pcg.c:530)
 }
 __global__ void pcg_update_xr_kernel(size_t n, const double *__restrict__ sc, const double *__restrict__ p,

@@ -18,6 +18,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
+#include <map>
 #include <algorithm>
 
 // ---- minimal NCCL ABI (nccl.h 2.27/2.28: stable since 2.x) -------------------------------------
@@ -96,6 +97,19 @@ struct b200_comm_group_s {
                                   : "rank group aborted: another rank failed");                                  \
   } while (0)
 
+struct b200_p2p_s {
+  bool ok = false;
+  size_t bytes = 0;
+  char *base = nullptr;                         // this rank's arena (cudaMalloc, outside the pool: IPC exports whole allocations)
+  std::vector<char *> peer;                     // peer[r]: rank r's arena in this rank's address space
+  std::vector<bool> opened;                     // peer[r] came from cudaIpcOpenMemHandle
+  std::map<size_t, size_t> free_by_off;         // symmetric first-fit allocator: offset -> size
+  std::vector<std::pair<size_t, size_t>> pending;   // released, reusable after the next quiescence point
+  unsigned long long seq = 0;                   // sequence number of the last flagged operation (same on every rank)
+  size_t ar_off = 0;                            // allreduce region: [2 parities][R][8 doubles] | arrival flags [R slots]
+  unsigned long long ar_count = 0;
+};
+
 struct b200_comm_s {
   int rank = 0, nranks = 1;
   int backend = 0;                 // 0 single, 1 nccl, 2 threads
@@ -103,6 +117,8 @@ struct b200_comm_s {
   b200_comm_group_s *group = nullptr;
   void *d_stage = nullptr;         // device staging for host allgather over NCCL
   size_t stage_bytes = 0;
+  b200_p2p_s p2p;
+  int device = 0;
 };
 
 extern "C" int b200_comm_create_single(b200_comm *out) {
@@ -129,6 +145,14 @@ extern "C" int b200_comm_create_threads(b200_comm_group g, int rank, b200_comm *
   *out = c;
   return 0;
 }
+static int p2p_init(b200_handle h, b200_comm c);
+// the rank threads of one process: peers are plain pointers on the same device.  Off unless B200_P2P_THREADS=1 (a kernel of
+// one rank then spins on a flag another rank's kernel raises from another stream of the SAME device, which needs both to be
+// resident at once -- true for the small test problems, not guaranteed under a profiler that serialises kernels)
+extern "C" int b200_comm_threads_enable_p2p(b200_handle h, b200_comm c) {
+  if (!c || c->backend != 2) B200_FAIL("enable_p2p: rank-group communicator expected");
+  return p2p_init(h, c);
+}
 extern "C" int b200_comm_nccl_unique_id(char *id128) {
   B200_TRY(load_nccl());
   ncclUniqueId id;
@@ -144,11 +168,26 @@ extern "C" int b200_comm_create_nccl(b200_handle h, int nranks, int rank, const 
   b200_comm_s *c = new b200_comm_s();
   c->rank = rank; c->nranks = nranks; c->backend = 1;
   B200_NCCL(g_nccl.CommInitRank(&c->nccl, nranks, id, rank));
+  c->device = h->device;
   *out = c;
+  const char *e = getenv("B200_P2P");
+  if (!(e && e[0] == '0')) B200_TRY(p2p_init(h, c));       // direct NVLink path for halos and reductions (falls back to NCCL)
   return 0;
+}
+static void p2p_shutdown(b200_comm c) {
+  b200_p2p_s &P = c->p2p;
+  for (size_t r = 0; r < P.peer.size(); r++)
+    if (P.opened.size() > r && P.opened[r] && P.peer[r]) cudaIpcCloseMemHandle(P.peer[r]);
+  if (P.base) cudaFree(P.base);
+  P = b200_p2p_s();
 }
 extern "C" int b200_comm_destroy(b200_handle h, b200_comm c) {
   if (!c) return 0;
+  if (c->p2p.base) {
+    cudaStreamSynchronize(h->stream);
+    if (c->nranks > 1 && !(c->backend == 2 && c->group->aborted)) { int z = 0; std::vector<int> all(c->nranks); b200_comm_allgather_host(h, c, &z, sizeof(int), all.data()); }
+    p2p_shutdown(c);
+  }
   if (c->d_stage) b200_dfree(h, c->d_stage);
   if (c->backend == 1 && c->nccl) g_nccl.CommDestroy(c->nccl);
   delete c;
@@ -234,7 +273,7 @@ int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_
 // k device-resident partial sums -> global sums on the host, added in rank order.  Over NCCL the partials go
 // device-to-device into the all-gather and come back with ONE copy + synchronisation (no host round trip first).
 int b200_comm_allreduce_sum_dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *h_out) {
-  if (k < 1 || (size_t)k * c->nranks > 64) B200_FAIL("allreduce_sum_dev: at most 64 values over all ranks");
+  if (k < 1 || (size_t)k * c->nranks > 1024) B200_FAIL("allreduce_sum_dev: at most 1024 values over all ranks");
   if (c->nranks == 1 || c->backend != 1) {
     B200_CUDA(cudaMemcpyAsync(h->h_pinned, d_vals, sizeof(double) * k, cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
@@ -245,8 +284,8 @@ int b200_comm_allreduce_sum_dev(b200_handle h, b200_comm c, const double *d_vals
   if (c->stage_bytes < need) {
     if (c->d_stage) B200_TRY(b200_dfree(h, c->d_stage));
     char *p = nullptr;
-    B200_TRY(b200_dalloc<char>(h, &p, 4096));
-    c->d_stage = p; c->stage_bytes = 4096;
+    B200_TRY(b200_dalloc<char>(h, &p, 8192));
+    c->d_stage = p; c->stage_bytes = 8192;
   }
   B200_NCCL(g_nccl.AllGather(d_vals, c->d_stage, sizeof(double) * k, ncclInt8, c->nccl, h->stream));
   B200_CUDA(cudaMemcpyAsync(h->h_pinned, c->d_stage, need, cudaMemcpyDeviceToHost, h->stream));
@@ -280,5 +319,220 @@ int b200_comm_allreduce_sum_ll(b200_handle h, b200_comm c, long long *vals, int 
     for (int r = 0; r < c->nranks; r++) s += all[(size_t)r * k + j];
     vals[j] = s;
   }
+  return 0;
+}
+
+
+// ---- direct peer-to-peer layer ------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// spin until *flag >= want; a peer that never arrives turns into a trap (an error at the next synchronisation), not a hang
+__device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, unsigned long long timeout_ns,
+                                          unsigned long long *dbg, int slot) {
+  if (ld_acquire_sys(flag) >= want) return;
+  const unsigned long long t0 = global_timer_ns();
+  unsigned spins = 0;
+  while (ld_acquire_sys(flag) < want) {
+    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+      if (dbg) { dbg[1] = slot; dbg[2] = want; dbg[3] = ld_acquire_sys(flag); dbg[0] = 3; __threadfence_system(); }
+      __trap();
+    }
+  }
+}
+
+struct ArArgs {
+  int R, me, k;
+  double *slot[B200_P2P_MAXPEER];                 // rank r's slot for MY contribution (parity applied by the host)
+  unsigned long long *flag[B200_P2P_MAXPEER];     // rank r's arrival flag for me
+  const double *mine;                             // my slots [R][8] (parity applied)
+  const unsigned long long *myflag;               // my arrival flags, slot r at myflag + r * B200_P2P_SLOT
+};
+// one warp: lane r pushes my k partials to rank r and raises its flag; then lane r waits for rank r's contribution and lane
+// j < k adds the R contributions in rank order (hypre_ParVectorInnerProd's Allreduce, par_vector.c:481-501, made deterministic)
+__global__ void allreduce_kernel(ArArgs a, const double *__restrict__ vals, unsigned long long seq, double *__restrict__ out,
+                                 unsigned long long timeout_ns, unsigned long long *dbg) {
+  const int lane = threadIdx.x;
+  if (lane < a.R) {
+    for (int j = 0; j < a.k; j++) a.slot[lane][j] = vals[j];
+    __threadfence_system();
+    st_release_sys(a.flag[lane], seq);
+    wait_flag(a.myflag + (size_t)lane * B200_P2P_SLOT, seq, timeout_ns, dbg, lane);
+  }
+  __syncwarp();
+  if (lane < a.k) {
+    double s = 0.0;
+    for (int r = 0; r < a.R; r++) s += __ldcv(a.mine + (size_t)r * 8 + lane);
+    out[lane] = s;
+  }
+}
+__global__ void sum_ranks_kernel(int R, int k, const double *__restrict__ all, double *__restrict__ out) {
+  const int j = threadIdx.x;
+  if (j >= k) return;
+  double s = 0.0;
+  for (int r = 0; r < R; r++) s += all[(size_t)r * k + j];
+  out[j] = s;
+}
+}  // namespace
+
+static unsigned long long p2p_timeout_ns() {
+  static const unsigned long long t = [] { const char *e = getenv("B200_P2P_TIMEOUT_S"); int s = e ? atoi(e) : 30; return (unsigned long long)(s > 0 ? s : 30) * 1000000000ull; }();
+  return t;
+}
+
+static int p2p_init(b200_handle h, b200_comm c) {
+  b200_p2p_s &P = c->p2p;
+  const int R = c->nranks, me = c->rank;
+  if (R < 2 || R > B200_P2P_MAXPEER) return 0;
+  size_t mb = 256;
+  if (const char *e = getenv("B200_P2P_ARENA_MB")) { int v = atoi(e); if (v > 0) mb = (size_t)v; }
+  P.bytes = mb << 20;
+  int good = 1;
+  if (cudaMalloc((void **)&P.base, P.bytes) != cudaSuccess) { cudaGetLastError(); good = 0; P.base = nullptr; }
+  if (good) { B200_CUDA(cudaMemsetAsync(P.base, 0, P.bytes, h->stream)); B200_CUDA(cudaStreamSynchronize(h->stream)); }
+  P.peer.assign(R, nullptr);
+  P.opened.assign(R, false);
+  if (c->backend == 2) {
+    std::vector<char *> all(R);
+    B200_TRY(b200_comm_allgather_host(h, c, &P.base, sizeof(char *), all.data()));
+    for (int r = 0; r < R; r++) { P.peer[r] = all[r]; if (!all[r]) good = 0; }
+  } else {
+    struct Rec { cudaIpcMemHandle_t hd; int ok; int dev; };
+    Rec mine;
+    memset(&mine, 0, sizeof mine);
+    mine.ok = good; mine.dev = c->device;
+    if (good && cudaIpcGetMemHandle(&mine.hd, P.base) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; }
+    std::vector<Rec> all(R);
+    B200_TRY(b200_comm_allgather_host(h, c, &mine, sizeof(Rec), all.data()));
+    for (int r = 0; r < R; r++) if (!all[r].ok) good = 0;
+    if (good) {
+      for (int r = 0; r < R && good; r++) {
+        if (r == me) { P.peer[r] = P.base; continue; }
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r].hd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); good = 0; break; }
+        P.peer[r] = (char *)q; P.opened[r] = true;
+      }
+    }
+  }
+  // the verdict is collective: one rank that cannot map a peer sends everybody to the NCCL path
+  std::vector<int> verdict(R);
+  B200_TRY(b200_comm_allgather_host(h, c, &good, sizeof(int), verdict.data()));
+  for (int r = 0; r < R; r++) if (!verdict[r]) good = 0;
+  if (!good) { p2p_shutdown(c); return 0; }
+  P.free_by_off.clear();
+  P.free_by_off[0] = P.bytes;
+  P.ok = true;
+  // allreduce region
+  const size_t ar_bytes = sizeof(double) * 2 * R * 8 + sizeof(unsigned long long) * B200_P2P_SLOT * R;
+  P.ar_off = b200_comm_p2p_alloc(h, c, ar_bytes);
+  if (P.ar_off == (size_t)-1) { p2p_shutdown(c); return 0; }
+  return 0;
+}
+
+bool b200_comm_p2p_ok(b200_comm c) { return c && c->p2p.ok; }
+char *b200_comm_p2p_base(b200_comm c, int rank) { return c->p2p.peer[rank]; }
+unsigned long long b200_comm_p2p_next_seq(b200_comm c) { return ++c->p2p.seq; }
+
+size_t b200_comm_p2p_alloc(b200_handle h, b200_comm c, size_t bytes) {
+  b200_p2p_s &P = c->p2p;
+  if (!P.ok) return (size_t)-1;
+  bytes = (bytes + 511) / 512 * 512;
+  auto first_fit = [&]() -> size_t {
+    for (auto it = P.free_by_off.begin(); it != P.free_by_off.end(); ++it)
+      if (it->second >= bytes) {
+        const size_t off = it->first, have = it->second;
+        P.free_by_off.erase(it);
+        if (have > bytes) P.free_by_off[off + bytes] = have - bytes;
+        return off;
+      }
+    return (size_t)-1;
+  };
+  size_t off = first_fit();
+  if (off == (size_t)-1 && !P.pending.empty()) {
+    // quiescence point: every rank has finished (and every peer has stopped writing to) what was released.  Every rank
+    // reaches this branch at the same allocation, because allocator state is identical on all ranks.
+    // Released regions are zeroed between two barriers, so free arena memory is always zero (flag slots start at 0).
+    cudaStreamSynchronize(h->stream);
+    int z = 0;
+    std::vector<int> all(c->nranks);
+    if (b200_comm_allgather_host(h, c, &z, sizeof(int), all.data())) return (size_t)-1;
+    for (auto &pr : P.pending) cudaMemsetAsync(P.base + pr.first, 0, pr.second, h->stream);
+    cudaStreamSynchronize(h->stream);
+    if (b200_comm_allgather_host(h, c, &z, sizeof(int), all.data())) return (size_t)-1;
+    for (auto &pr : P.pending) {
+      size_t o = pr.first, n = pr.second;
+      auto next = P.free_by_off.lower_bound(o);
+      if (next != P.free_by_off.end() && o + n == next->first) { n += next->second; next = P.free_by_off.erase(next); }
+      if (next != P.free_by_off.begin()) {
+        auto prev = std::prev(next);
+        if (prev->first + prev->second == o) { o = prev->first; n += prev->second; P.free_by_off.erase(prev); }
+      }
+      P.free_by_off[o] = n;
+    }
+    P.pending.clear();
+    off = first_fit();
+  }
+  return off;
+}
+void b200_comm_p2p_free(b200_comm c, size_t offset, size_t bytes) {
+  if (!c || !c->p2p.ok) return;
+  bytes = (bytes + 511) / 512 * 512;
+  c->p2p.pending.emplace_back(offset, bytes);
+}
+
+int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *d_out) {
+  if (k < 1 || k > 8) B200_FAIL("allreduce_sum_dev2dev: 1..8 values");
+  const int R = c->nranks;
+  if (R == 1) {
+    B200_CUDA(cudaMemcpyAsync(d_out, d_vals, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+  }
+  b200_p2p_s &P = c->p2p;
+  if (P.ok) {
+    const unsigned long long seq = ++P.seq;
+    const size_t par = (size_t)(P.ar_count++ & 1);
+    static const bool trace = [] { const char *e = getenv("B200_P2P_TRACE"); return e && e[0] == '1'; }();
+    if (trace) fprintf(stderr, "[p2p] rank %d seq %llu allreduce k %d par %zu\n", c->rank, seq, k, par);
+    const size_t slots = P.ar_off + sizeof(double) * par * R * 8, flags = P.ar_off + sizeof(double) * 2 * R * 8;
+    ArArgs a;
+    a.R = R; a.me = c->rank; a.k = k;
+    for (int r = 0; r < R; r++) {
+      a.slot[r] = reinterpret_cast<double *>(P.peer[r] + slots) + (size_t)c->rank * 8;
+      a.flag[r] = reinterpret_cast<unsigned long long *>(P.peer[r] + flags) + (size_t)c->rank * B200_P2P_SLOT;
+    }
+    a.mine = reinterpret_cast<const double *>(P.base + slots);
+    a.myflag = reinterpret_cast<const unsigned long long *>(P.base + flags);
+    allreduce_kernel<<<1, 32, 0, h->stream>>>(a, d_vals, seq, d_out, p2p_timeout_ns(), g_b200_p2p_dbg);
+    B200_LAUNCH_CHECK();
+    return 0;
+  }
+  if (c->backend != 1) {          // rank threads without the peer layer: through the host
+    double v[8];
+    B200_TRY(b200_comm_allreduce_sum_dev(h, c, d_vals, k, v));
+    B200_CUDA(cudaMemcpyAsync(d_out, v, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  const size_t need = sizeof(double) * (size_t)k * R;
+  if (c->stage_bytes < need) {
+    if (c->d_stage) B200_TRY(b200_dfree(h, c->d_stage));
+    char *q = nullptr;
+    B200_TRY(b200_dalloc<char>(h, &q, 4096));
+    c->d_stage = q; c->stage_bytes = 4096;
+  }
+  B200_NCCL(g_nccl.AllGather(d_vals, c->d_stage, sizeof(double) * k, ncclInt8, c->nccl, h->stream));
+  sum_ranks_kernel<<<1, 32, 0, h->stream>>>(R, k, reinterpret_cast<const double *>(c->d_stage), d_out);
+  B200_LAUNCH_CHECK();
   return 0;
 }

@@ -17,6 +17,26 @@ int b200_comm_allreduce_sum(b200_handle h, b200_comm c, double *vals, int k);
 int b200_comm_allreduce_sum_dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *h_out);
 int b200_comm_allreduce_sum_ll(b200_handle h, b200_comm c, long long *vals, int k);
 
+// ---- direct peer-to-peer layer (NVLink loads/stores, no NCCL call on the data path) -----------------------------------
+// Every rank owns an arena of the same size; all arenas are mapped into every rank's address space once, at communicator
+// creation (CUDA IPC between processes, plain pointers between the rank threads of one process).  The arena is a SYMMETRIC
+// heap: allocation and release are collective and deterministic, so an object sits at the same offset on every rank and the
+// address of a peer's copy is peer_base[r] + offset -- no per-object handshake.  Synchronisation is by sequence numbers
+// written with system-scope release stores: one counter per communicator, identical on all ranks because every rank runs
+// the same sequence of collective operations.
+#define B200_P2P_MAXPEER 16
+#define B200_P2P_SLOT 16             // flag slots are 128 bytes apart (unsigned long long [16])
+bool   b200_comm_p2p_ok(b200_comm c);
+// symmetric allocation; returns the offset or (size_t)-1 when the arena is exhausted (same answer on every rank)
+size_t b200_comm_p2p_alloc(b200_handle h, b200_comm c, size_t bytes);
+// released regions are reused only after a collective quiescence point (taken lazily by the next allocation)
+void   b200_comm_p2p_free(b200_comm c, size_t offset, size_t bytes);
+char  *b200_comm_p2p_base(b200_comm c, int rank);          // base of rank's arena in this rank's address space
+unsigned long long b200_comm_p2p_next_seq(b200_comm c);
+// k <= 8 device-resident partial sums -> global sums in device memory on every rank, added in rank order (deterministic);
+// one kernel, no host synchronisation.  Falls back to ncclAllGather + a summation kernel without the peer layer.
+int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *d_out);
+
 // Halo plan = hypre_ParCSRCommPkg (parcsr_mv/par_csr_communication.h:54-82) for one ghost set:
 // ghosts are the sorted global ids this rank reads but does not own; each ghost block is
 // contiguous per owner (owners own contiguous id ranges), so receives land in place.
@@ -32,6 +52,14 @@ struct b200_halo_s {
   int n_send = 0;
   int *d_send_idx = nullptr;             // device, local indices to pack [n_send]
   void *d_send_buf = nullptr;            // device staging, 8 bytes per send entry
+  // direct path (b200_halo_forward_f64): enabled lazily by the first forward exchange of doubles under this plan
+  b200_comm comm = nullptr;
+  std::vector<int> all_cnt;              // [R x R] all_cnt[r * R + s] = entries rank r receives from rank s
+  int p2p_state = 0;                     // 0 not tried, 1 enabled, -1 unavailable (NCCL path)
+  size_t p2p_off = 0, p2p_bytes = 0;     // symmetric region: [rbuf parity 0 | rbuf parity 1 | arrival flags | ack flags | counters]
+  int p2p_cap = 0;                       // doubles per parity buffer (max ghosts over the ranks, rounded up)
+  unsigned long long p2p_seq[2] = {0, 0};   // sequence numbers of the last two exchanges under this plan (ack targets)
+  unsigned long long p2p_count = 0;      // exchanges done under this plan (parity = count & 1)
 };
 
 // halo operations (b200_dist.cu)

@@ -305,6 +305,8 @@ int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, 
   B200_TRY(b200_comm_allgather_host(h, c, p->recv_cnt.data(), sizeof(int) * R, all.data()));
   for (int r = 0; r < R; r++) { p->send_cnt[r] = all[(size_t)r * R + me]; p->send_off[r + 1] = p->send_off[r] + p->send_cnt[r]; }
   for (size_t k = 0; k < all.size(); k++) if (all[k]) p->any_traffic = true;
+  p->comm = c;
+  p->all_cnt = all;
   p->n_send = p->send_off[R];
   B200_TRY(b200_dalloc<int>(h, &p->d_send_idx, p->n_send));
   char *buf = nullptr;
@@ -326,8 +328,165 @@ int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, 
 }
 void b200_halo_free(b200_handle h, b200_halo_s *p) {
   if (!p) return;
+  if (p->p2p_state == 1) b200_comm_p2p_free(p->comm, p->p2p_off, p->p2p_bytes);
   b200_dfree(h, p->d_ghost_gid); b200_dfree(h, p->d_send_idx); b200_dfree(h, p->d_send_buf);
   delete p;
+}
+
+// ---- direct halo exchange: pack-and-push into the neighbours' receive buffers over NVLink, flag, wait-and-copy -------------
+// (hypre_ParCSRCommHandleCreate job 1 + hypre_ParCSRCommHandleDestroy, par_csr_communication.c:307-631, without a message
+// library on the data path).  Exchange number k of a plan uses receive buffer k & 1; a sender overwrites a buffer only after
+// the receiver acknowledged the exchange that used it before (k - 2).
+namespace {
+struct PeerList {
+  int n;
+  int off[B200_P2P_MAXPEER + 1];                  // entry ranges of the peers in the send list / ghost array
+  double *buf[B200_P2P_MAXPEER];                  // push: where my block starts in the peer's receive buffer
+  unsigned long long *raise[B200_P2P_MAXPEER];    // flag to raise on the peer (push: arrival, pull: acknowledgement)
+  const unsigned long long *wait[B200_P2P_MAXPEER];   // local flag to wait on (push: acknowledgement, pull: arrival)
+};
+__device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_release(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long want, unsigned long long timeout_ns,
+                                         unsigned long long *dbg, int kind) {
+  if (p2p_ld_acquire(flag) >= want) return;
+  unsigned long long t0, t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
+  unsigned spins = 0;
+  while (p2p_ld_acquire(flag) < want) {
+    if ((++spins & 1023u) == 0) {
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) {                  // a peer that never arrives: an error at the next synchronisation, not a hang
+        if (dbg) { dbg[1] = threadIdx.x; dbg[2] = want; dbg[3] = p2p_ld_acquire(flag); dbg[0] = kind; __threadfence_system(); }
+        __trap();
+      }
+    }
+  }
+}
+// the last CTA of the grid raises the flags: every CTA fences its stores, then counts itself in
+__device__ __forceinline__ bool p2p_last_cta(unsigned *counter) {
+  __shared__ bool last;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(counter, 1u);
+    last = (t == gridDim.x - 1);
+    if (last) *counter = 0;
+  }
+  __syncthreads();
+  if (last) __threadfence_system();
+  return last;
+}
+__global__ void halo_push_kernel(int n_send, const int *__restrict__ idx, const double *__restrict__ src, PeerList P,
+                                 unsigned long long seq, unsigned long long ack_need, unsigned *counter,
+                                 unsigned long long timeout_ns, unsigned long long *dbg) {
+  if ((int)threadIdx.x < P.n && ack_need) p2p_wait(P.wait[threadIdx.x], ack_need, timeout_ns, dbg, 1);
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_send; k += gridDim.x * blockDim.x) {
+    int q = 0;
+    while (k >= P.off[q + 1]) q++;
+    P.buf[q][k - P.off[q]] = src[idx[k]];
+  }
+  if (p2p_last_cta(counter) && (int)threadIdx.x < P.n) p2p_st_release(P.raise[threadIdx.x], seq);
+}
+__global__ void halo_pull_kernel(int ng, const double *rbuf, double *__restrict__ ghost_out, PeerList P, unsigned long long seq,
+                                 unsigned *counter, unsigned long long timeout_ns, unsigned long long *dbg) {
+  if ((int)threadIdx.x < P.n) p2p_wait(P.wait[threadIdx.x], seq, timeout_ns, dbg, 2);
+  __syncthreads();
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ng; k += gridDim.x * blockDim.x) ghost_out[k] = __ldcv(rbuf + k);
+  if (p2p_last_cta(counter) && (int)threadIdx.x < P.n) p2p_st_release(P.raise[threadIdx.x], seq);
+}
+}  // namespace
+
+static unsigned long long halo_timeout_ns() {
+  static const unsigned long long t = [] { const char *e = getenv("B200_P2P_TIMEOUT_S"); int s = e ? atoi(e) : 30; return (unsigned long long)(s > 0 ? s : 30) * 1000000000ull; }();
+  return t;
+}
+
+// collective and deterministic: every rank takes the same decision from the plan's (allgathered) count matrix
+static void halo_p2p_enable(b200_handle h, b200_comm c, b200_halo_s *p) {
+  p->p2p_state = -1;
+  if (!b200_comm_p2p_ok(c)) return;
+  const int R = b200_comm_size(c);
+  int cap = 0, maxpeers = 0;
+  for (int r = 0; r < R; r++) {
+    int ng_r = 0, nrecv = 0, nsend = 0;
+    for (int s2 = 0; s2 < R; s2++) {
+      ng_r += p->all_cnt[(size_t)r * R + s2];
+      if (p->all_cnt[(size_t)r * R + s2]) nrecv++;
+      if (p->all_cnt[(size_t)s2 * R + r]) nsend++;
+    }
+    cap = std::max(cap, ng_r);
+    maxpeers = std::max(maxpeers, std::max(nrecv, nsend));
+  }
+  if (maxpeers > B200_P2P_MAXPEER) return;
+  cap = (cap + 31) & ~31;
+  const size_t slot = sizeof(unsigned long long) * B200_P2P_SLOT;
+  const size_t bytes = sizeof(double) * 2 * (size_t)cap + slot * R * 2 + slot * 2;
+  const size_t off = b200_comm_p2p_alloc(h, c, bytes);
+  if (off == (size_t)-1) return;
+  p->p2p_off = off; p->p2p_bytes = bytes; p->p2p_cap = cap; p->p2p_state = 1;
+}
+
+static int halo_forward_p2p(b200_handle h, b200_comm c, b200_halo_s *p, const double *owned, double *ghost_out) {
+  const int R = b200_comm_size(c), me = b200_comm_rank(c);
+  const size_t slot = sizeof(unsigned long long) * B200_P2P_SLOT;
+  const size_t off_arr = p->p2p_off + sizeof(double) * 2 * (size_t)p->p2p_cap, off_ack = off_arr + slot * R, off_cnt = off_ack + slot * R;
+  const unsigned long long seq = b200_comm_p2p_next_seq(c);
+  const size_t par = (size_t)(p->p2p_count & 1);
+  const unsigned long long ack_need = p->p2p_seq[par];       // the exchange that used this receive buffer before
+  p->p2p_seq[par] = seq;
+  p->p2p_count++;
+  char *mine = b200_comm_p2p_base(c, me);
+  static const bool trace = [] { const char *e = getenv("B200_P2P_TRACE"); return e && e[0] == '1'; }();
+  if (trace) fprintf(stderr, "[p2p] rank %d seq %llu halo plan %p off %zu cap %d par %zu ack_need %llu n_send %d ng %d\n", me, seq, (void *)p,
+                     p->p2p_off, p->p2p_cap, par, ack_need, p->n_send, p->ng);
+  if (p->n_send) {
+    PeerList L;
+    L.n = 0; L.off[0] = 0;
+    for (int r = 0; r < R; r++) {
+      if (!p->send_cnt[r]) continue;
+      char *pb = b200_comm_p2p_base(c, r);
+      int roff = 0;                                            // where my block starts in r's ghost array (ghosts sorted by owner)
+      for (int s2 = 0; s2 < me; s2++) roff += p->all_cnt[(size_t)r * R + s2];
+      L.buf[L.n] = reinterpret_cast<double *>(pb + p->p2p_off) + par * (size_t)p->p2p_cap + roff;
+      L.raise[L.n] = reinterpret_cast<unsigned long long *>(pb + off_arr + slot * me);
+      L.wait[L.n] = reinterpret_cast<const unsigned long long *>(mine + off_ack + slot * r);
+      L.off[L.n + 1] = L.off[L.n] + p->send_cnt[r];
+      L.n++;
+    }
+    int grid = b200_grid(p->n_send, 256);
+    if (grid > h->num_sm * 4) grid = h->num_sm * 4;
+    halo_push_kernel<<<grid, 256, 0, h->stream>>>(p->n_send, p->d_send_idx, owned, L, seq, ack_need,
+                                                  reinterpret_cast<unsigned *>(mine + off_cnt), halo_timeout_ns(), g_b200_p2p_dbg);
+    B200_LAUNCH_CHECK();
+  }
+  if (p->ng) {
+    PeerList L;
+    L.n = 0; L.off[0] = 0;
+    for (int r = 0; r < R; r++) {
+      if (!p->recv_cnt[r]) continue;
+      char *pb = b200_comm_p2p_base(c, r);
+      L.buf[L.n] = nullptr;
+      L.wait[L.n] = reinterpret_cast<const unsigned long long *>(mine + off_arr + slot * r);
+      L.raise[L.n] = reinterpret_cast<unsigned long long *>(pb + off_ack + slot * me);
+      L.off[L.n + 1] = L.off[L.n] + p->recv_cnt[r];
+      L.n++;
+    }
+    int grid = b200_grid(p->ng, 256);
+    if (grid > h->num_sm * 2) grid = h->num_sm * 2;
+    halo_pull_kernel<<<grid, 256, 0, h->stream>>>(p->ng, reinterpret_cast<const double *>(mine + p->p2p_off) + par * (size_t)p->p2p_cap,
+                                                  ghost_out, L, seq, reinterpret_cast<unsigned *>(mine + off_cnt + slot),
+                                                  halo_timeout_ns(), g_b200_p2p_dbg);
+    B200_LAUNCH_CHECK();
+  }
+  return 0;
 }
 
 template <class T>
@@ -346,7 +505,11 @@ static int halo_forward(b200_handle h, b200_comm c, b200_halo_s *p, const T *own
   return b200_comm_exchange(h, c, sends, recvs);
 }
 int b200_halo_forward_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *o, int *g) { return halo_forward<int>(h, c, p, o, g); }
-int b200_halo_forward_f64(b200_handle h, b200_comm c, b200_halo_s *p, const double *o, double *g) { return halo_forward<double>(h, c, p, o, g); }
+int b200_halo_forward_f64(b200_handle h, b200_comm c, b200_halo_s *p, const double *o, double *g) {
+  if (p->p2p_state == 0) halo_p2p_enable(h, c, p);        // first exchange of doubles under this plan: every rank is here
+  if (p->p2p_state == 1) return halo_forward_p2p(h, c, p, o, g);
+  return halo_forward<double>(h, c, p, o, g);
+}
 
 static int halo_reverse_i32(b200_handle h, b200_comm c, b200_halo_s *p, const int *ghost_in, int *owned, int op) {
   const int R = b200_comm_size(c);
@@ -1337,6 +1500,33 @@ static int dist_dot2(b200_handle h, b200_comm c, int n, const double *x1, const 
   return 0;
 }
 
+namespace {
+// device-resident PCG scalars: sc[0] gamma, sc[1] i_prod = <r,r>, sc[2] <s,p>, sc[3] gamma_old, sc[4] alpha, sc[5] beta
+__global__ void dpcg_alpha_kernel(double *sc) {
+  sc[4] = (sc[2] != 0.0) ? sc[0] / sc[2] : 0.0;   // alpha = gamma / <s,p> (pcg.c:522); <s,p> = 0 is the error path, x and r stay intact
+  sc[3] = sc[0];                                  // gamma_old = gamma (pcg.c:530)
+}
+__global__ void dpcg_beta_kernel(double *sc) { sc[5] = sc[0] / sc[3]; }   // beta = gamma / gamma_old (pcg.c:729)
+__global__ void dpcg_update_xr_kernel(size_t n, const double *__restrict__ sc, const double *__restrict__ p,
+                                      const double *__restrict__ s, double *__restrict__ x, double *__restrict__ r) {
+  const double alpha = sc[4];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) {
+    x[i] += alpha * p[i];         // pcg.c:534
+    r[i] += -alpha * s[i];        // pcg.c:539
+  }
+}
+__global__ void dpcg_update_p_kernel(size_t n, const double *__restrict__ sc, const double *__restrict__ s, double *__restrict__ p) {
+  const double beta = sc[5];
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = beta * p[i] + 1.0 * s[i];   // Scale then Axpy (pcg.c:734-735)
+}
+}  // namespace
+
+// hypre_PCGSolve across ranks (krylov/pcg.c:271-757, two_norm 1 as ij.c:3892-3897 sets it).  The three inner products of an
+// iteration are reduced device to device (rank-ordered sums over NVLink, b200_comm_allreduce_sum_dev2dev), alpha and beta are
+// formed on the device and the vector updates are fused, exactly like the single-GPU loop (b200_pcg_solve_ex): ONE host
+// synchronisation per iteration, for the convergence test.
 extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const double *d_b,
                                    double *d_x, double tol, int max_iter, int *iters_out, double *final_rel_res, double *h_norms) {
   if (!A || !A->L) B200_FAIL("dist_pcg: matrix not localized");
@@ -1345,45 +1535,71 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
   if (amg) cap = std::max(cap, amg->lv[0].cap);
   double *p = nullptr, *s = nullptr, *r = nullptr, *xx = nullptr, *sc = nullptr;
   B200_TRY(b200_dalloc<double>(h, &p, cap)); B200_TRY(b200_dalloc<double>(h, &s, cap)); B200_TRY(b200_dalloc<double>(h, &r, cap));
-  B200_TRY(b200_dalloc<double>(h, &xx, cap)); B200_TRY(b200_dalloc<double>(h, &sc, 8));
+  B200_TRY(b200_dalloc<double>(h, &xx, cap)); B200_TRY(b200_dalloc<double>(h, &sc, 16));
+  double *lp = sc + 8;                       // this rank's partial sums
+  double *hs = h->h_pinned;
   B200_CUDA(cudaMemsetAsync(p, 0, sizeof(double) * cap, h->stream));
   B200_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * cap, h->stream));
+  B200_CUDA(cudaMemsetAsync(sc, 0, sizeof(double) * 16, h->stream));
   B200_CUDA(cudaMemcpyAsync(xx, d_x, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
   auto precond = [&](const double *rhs, double *out) -> int {
     if (amg) return dist_cycle(h, c, amg, rhs, out);
     return b200_vec_copy(h, n, rhs, out);
   };
+  auto fetch = [&]() -> int {                 // the iteration's one host synchronisation
+    B200_CUDA(cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  const int vg = vgrid(h, n);
   int rc = 0, i = 0;
-  double bi_prod = 0, i_prod = 0, eps = tol * tol, gamma = 0, gamma_old = 0;
+  double bi_prod = 0, i_prod = 0, eps = tol * tol;
+  bool x_is_b = false;
   do {
-    if ((rc = dist_dot(h, c, n, d_b, d_b, sc, &bi_prod))) break;
-    if (!(bi_prod > 0.0)) { rc = b200_vec_copy(h, n, d_b, d_x); if (h_norms) h_norms[0] = 0.0; break; }
+    if ((rc = b200_vec_dot_dev(h, n, d_b, d_b, lp))) break;
+    if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 1))) break;
+    if ((rc = fetch())) break;
+    bi_prod = hs[1];
+    if (bi_prod != 0. && !(bi_prod / bi_prod == bi_prod / bi_prod)) {       // pcg.c:359-381
+      rc = b200_set_error(__FILE__, __LINE__, "hypre_PCGSolve: INFs and/or NaNs detected in input"); break;
+    }
+    if (!(bi_prod > 0.0)) {                                                 // pcg.c:403-416: b == 0 -> x = b
+      rc = b200_vec_copy(h, n, d_b, d_x); x_is_b = true; if (h_norms) h_norms[0] = 0.0; break;
+    }
     if ((rc = dist_spmv(h, c, A, xx, r, 0, -1.0, 1.0, d_b, nullptr))) break;       // r = b - A x
     if ((rc = precond(r, p))) break;
-    if (h_norms) { double t = 0; if ((rc = dist_dot2(h, c, n, r, p, r, r, sc, &gamma, &t))) break; h_norms[0] = std::sqrt(t); }
-    else if ((rc = dist_dot(h, c, n, r, p, sc, &gamma))) break;
+    if ((rc = b200_vec_dot_dev(h, n, r, p, lp))) break;                            // gamma = <r,p>
+    if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break;
+    if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break;
+    if (h_norms) { if ((rc = fetch())) break; h_norms[0] = std::sqrt(hs[1]); }
     while ((i + 1) <= max_iter) {
       i++;
-      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr))) break;   // s = A p
-      double sdotp = 0;
-      if ((rc = dist_dot(h, c, n, s, p, sc, &sdotp))) break;
-      if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }
-      const double alpha = gamma / sdotp;
-      gamma_old = gamma;
-      if ((rc = b200_vec_axpy(h, n, alpha, p, xx))) break;
-      if ((rc = b200_vec_axpy(h, n, -alpha, s, r))) break;
-      if ((rc = precond(r, s))) break;
-      if ((rc = dist_dot2(h, c, n, r, s, r, r, sc, &gamma, &i_prod))) break;
+      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr))) break;   // s = A p (pcg.c:512)
+      if ((rc = b200_vec_dot_dev(h, n, s, p, lp))) break;                          // <s,p> (pcg.c:515)
+      if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 2))) break;
+      dpcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
+      ++g_b200_launches;
+      dpcg_update_xr_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, p, s, xx, r);
+      ++g_b200_launches;
+      if ((rc = precond(r, s))) break;                                             // s = C r (pcg.c:568-569)
+      if ((rc = b200_vec_dot_dev(h, n, r, s, lp))) break;                          // gamma = <r,s> (pcg.c:572)
+      if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break;                      // i_prod = <r,r> (pcg.c:590)
+      if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break;
+      if ((rc = fetch())) break;
+      const double gamma = hs[0], sdotp = hs[2];
+      i_prod = hs[1];
+      if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }   // pcg.c:516-521
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;
       if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
-      const double beta = gamma / gamma_old;
-      if ((rc = b200_vec_scale(h, n, beta, p))) break;
-      if ((rc = b200_vec_axpy(h, n, 1.0, s, p))) break;
+      dpcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
+      ++g_b200_launches;
+      dpcg_update_p_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, s, p);
+      ++g_b200_launches;
     }
   } while (0);
   if (!rc) {
-    cudaMemcpyAsync(d_x, xx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream);
+    if (!x_is_b) cudaMemcpyAsync(d_x, xx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream);
     if (iters_out) *iters_out = i;
     if (final_rel_res) *final_rel_res = bi_prod > 0.0 ? std::sqrt(i_prod / bi_prod) : 0.0;
   }

@@ -26,7 +26,7 @@ struct b200_handle_s {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   // scratch for reductions (dot products): partial sums + pinned host landing zone
   double *d_partials = nullptr;
-  double *h_pinned = nullptr;   // 64 doubles, pinned
+  double *h_pinned = nullptr;   // 1024 doubles, pinned
   int     n_partials = 0;
 };
 
@@ -69,6 +69,7 @@ extern thread_local std::string g_b200_err;
 extern std::atomic<long long> g_b200_launches;   // incremented from several rank threads in the threads-as-ranks backend
 
 int b200_set_error(const char *file, int line, const char *msg);
+extern unsigned long long *g_b200_p2p_dbg;
 
 #define B200_FAIL(msg) return b200_set_error(__FILE__, __LINE__, (msg))
 #define B200_CUDA(call)                                                         \

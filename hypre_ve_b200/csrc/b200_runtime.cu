@@ -4,6 +4,7 @@
 #include "b200_internal.h"
 #include <cub/device/device_scan.cuh>
 #include <map>
+#include <mutex>
 
 // ------------------------------------------------------------------------------------------
 // Slab sub-allocator.  BoomerAMG setup allocates and frees hundreds of temporaries, several of
@@ -134,9 +135,18 @@ extern "C" int b200_pool_stats(b200_handle h, size_t *reserved, size_t *in_use, 
 thread_local std::string g_b200_err;
 std::atomic<long long> g_b200_launches{0};
 
+// pinned, device-visible diagnostic words: a peer-to-peer wait that times out records what it was waiting for before it
+// traps (the context is lost after the trap; pinned host memory is not)
+unsigned long long *g_b200_p2p_dbg = nullptr;
+
 int b200_set_error(const char *file, int line, const char *msg) {
   char buf[1024];
-  snprintf(buf, sizeof buf, "%s:%d: %s", file, line, msg);
+  if (g_b200_p2p_dbg && g_b200_p2p_dbg[0])
+    snprintf(buf, sizeof buf, "%s:%d: %s [peer-to-peer wait timed out: kind %llu (1 halo push/ack, 2 halo pull/arrival, 3 allreduce), "
+             "peer slot %llu, wanted sequence %llu, found %llu]", file, line, msg, g_b200_p2p_dbg[0], g_b200_p2p_dbg[1],
+             g_b200_p2p_dbg[2], g_b200_p2p_dbg[3]);
+  else
+    snprintf(buf, sizeof buf, "%s:%d: %s", file, line, msg);
   g_b200_err = buf;
   return 1;
 }
@@ -163,7 +173,15 @@ extern "C" int b200_init(int device, b200_handle *out) {
   h->pool = new b200_pool_s();
   h->n_partials = 4096;
   B200_CUDA(cudaMalloc(&h->d_partials, sizeof(double) * h->n_partials));
-  B200_CUDA(cudaMallocHost(&h->h_pinned, sizeof(double) * 64));
+  B200_CUDA(cudaMallocHost(&h->h_pinned, sizeof(double) * 1024));
+  {
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!g_b200_p2p_dbg) {
+      B200_CUDA(cudaHostAlloc((void **)&g_b200_p2p_dbg, sizeof(unsigned long long) * 8, cudaHostAllocPortable | cudaHostAllocMapped));
+      memset(g_b200_p2p_dbg, 0, sizeof(unsigned long long) * 8);
+    }
+  }
   *out = h;
   return 0;
 }

@@ -268,6 +268,10 @@ int b200_comm_group_destroy(b200_comm_group g);
  * B200_COMM_TIMEOUT_S seconds (default 300) aborts the group the same way */
 int b200_comm_group_abort(b200_comm_group g);
 int b200_comm_create_threads(b200_comm_group g, int rank, b200_comm *c);
+/* rank threads: switch the direct peer-to-peer path on (flags and receive buffers of the other rank threads are plain
+ * pointers on the same device); collective over the group.  The NCCL communicator enables it by itself (CUDA IPC over
+ * NVLink) unless B200_P2P=0.  Test hook for the protocol on a single-GPU box. */
+int b200_comm_threads_enable_p2p(b200_handle h, b200_comm c);
 int b200_comm_nccl_unique_id(char *id128);                       /* rank 0, then broadcast by the host  */
 int b200_comm_create_nccl(b200_handle h, int nranks, int rank, const char *id128, b200_comm *c);
 int b200_comm_destroy(b200_handle h, b200_comm c);

@@ -507,6 +507,25 @@ def test_a_failing_rank_fails_the_job_instead_of_hanging():
         run_ranks(3, fn)
 
 
+def test_direct_peer_to_peer_halos_and_reductions_between_rank_threads():
+    """The NVLink data path of the multi-GPU solve (halo pack-and-push into the neighbour's receive buffer + flags,
+    device-to-device rank-ordered reductions: b200_halo_forward_f64, b200_comm_allreduce_sum_dev2dev) run between the rank
+    threads of ONE GPU: a subset of this file is repeated in a child process with B200_P2P_THREADS=1.  The kernels of one rank
+    spin on flags raised by kernels on other streams of the same device, hence eager module loading and one hardware queue
+    per stream in the child's environment."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B200_P2P_THREADS="1", B200_P2P_TIMEOUT_S="20", CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32")
+    sel = ("test_zslab_partition_equals_reference_cpu_build or test_dist_matvec_matches_gathered or "
+           "test_nrank_hierarchy_equals_single_gpu or test_nrank_gmres_and_bicgstab_equal_single_gpu or "
+           "test_nrank_hybrid_gs_pcg_history_equals_the_restatement or test_dist_amg_pcg_with_hybrid_gauss_seidel")
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k", sel],
+                       env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=280)
+    assert p.returncode == 0, p.stdout[-3000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout, p.stdout[-1000:]
+
+
 def test_launch_helper_agrees_with_the_library_partition():
     """hypre_ve_b200.launch (host arithmetic, covered on CPU by tests/test_launch_gloo.py) describes the same
     row partition the library generates"""
