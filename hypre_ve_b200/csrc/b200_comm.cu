@@ -105,9 +105,7 @@ struct b200_p2p_s {
   std::vector<bool> opened;                     // peer[r] came from cudaIpcOpenMemHandle
   std::map<size_t, size_t> free_by_off;         // symmetric first-fit allocator: offset -> size
   std::vector<std::pair<size_t, size_t>> pending;   // released, reusable after the next quiescence point
-  unsigned long long seq = 0;                   // sequence number of the last flagged operation (same on every rank)
-  size_t ar_off = 0;                            // allreduce region: [2 parities][R][8 doubles] | arrival flags [R slots]
-  unsigned long long ar_count = 0;
+  size_t ar_off = 0;                            // allreduce region: [2 parities][R][16 doubles] | arrival flags [R slots] | count
 };
 
 struct b200_comm_s {
@@ -325,13 +323,13 @@ int b200_comm_allreduce_sum_ll(b200_handle h, b200_comm c, long long *vals, int 
 
 // ---- direct peer-to-peer layer ------------------------------------------------------------------------------------------
 namespace {
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {     // relaxed poll; wait_flag fences once
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
   unsigned long long t;
@@ -341,41 +339,64 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 // spin until *flag >= want; a peer that never arrives turns into a trap (an error at the next synchronisation), not a hang
 __device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsigned long long want, unsigned long long timeout_ns,
                                           unsigned long long *dbg, int slot) {
-  if (ld_acquire_sys(flag) >= want) return;
-  const unsigned long long t0 = global_timer_ns();
-  unsigned spins = 0;
-  while (ld_acquire_sys(flag) < want) {
-    if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
-      if (dbg) { dbg[1] = slot; dbg[2] = want; dbg[3] = ld_acquire_sys(flag); dbg[0] = 3; __threadfence_system(); }
-      __trap();
+  if (ld_acquire_sys(flag) < want) {
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys(flag) < want) {
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+        if (dbg) { dbg[1] = slot; dbg[2] = want; dbg[3] = ld_acquire_sys(flag); dbg[0] = 3; __threadfence_system(); }
+        __trap();
+      }
     }
   }
+  __threadfence_system();      // acquire
 }
 
+#define B200_AR_MAXK 16
 struct ArArgs {
-  int R, me, k;
-  double *slot[B200_P2P_MAXPEER];                 // rank r's slot for MY contribution (parity applied by the host)
-  unsigned long long *flag[B200_P2P_MAXPEER];     // rank r's arrival flag for me
-  const double *mine;                             // my slots [R][8] (parity applied)
-  const unsigned long long *myflag;               // my arrival flags, slot r at myflag + r * B200_P2P_SLOT
+  int R, me;
+  uint4 *slot[B200_P2P_MAXPEER];                  // rank r's slots for MY contribution (set 0; set 1 at + R * B200_AR_MAXK)
+  const uint4 *mine;                              // my slots [2][R][B200_AR_MAXK]
+  unsigned long long *cnt;                        // local: reductions completed on this communicator
 };
-// one warp: lane r pushes my k partials to rank r and raises its flag; then lane r waits for rank r's contribution and lane
-// j < k adds the R contributions in rank order (hypre_ParVectorInnerProd's Allreduce, par_vector.c:481-501, made deterministic)
-__global__ void allreduce_kernel(ArArgs a, const double *__restrict__ vals, unsigned long long seq, double *__restrict__ out,
+// One CTA of R x 16 threads: thread (r, j) pushes my j-th partial to rank r as two self-validating {32 data bits, sequence
+// number} words (no flag behind the data, hence no system-scope fence), then waits for rank r's j-th partial in its own slots;
+// thread j < k adds the R contributions in rank order (hypre_ParVectorInnerProd's Allreduce, par_vector.c:481-501, made
+// deterministic).  The reduction number lives in device memory (every argument is fixed: the kernel can sit in a CUDA graph);
+// reduction n uses slot set n & 1 -- rank A can only start n + 2 after it finished n + 1, which needed B's push of n + 1,
+// issued after B read n.
+__global__ void allreduce_kernel(ArArgs a, const double *__restrict__ vals, int k, double *__restrict__ out,
                                  unsigned long long timeout_ns, unsigned long long *dbg) {
-  const int lane = threadIdx.x;
-  if (lane < a.R) {
-    for (int j = 0; j < a.k; j++) a.slot[lane][j] = vals[j];
-    __threadfence_system();
-    st_release_sys(a.flag[lane], seq);
-    wait_flag(a.myflag + (size_t)lane * B200_P2P_SLOT, seq, timeout_ns, dbg, lane);
+  __shared__ double part[B200_P2P_MAXPEER][B200_AR_MAXK];
+  const int r = threadIdx.x / B200_AR_MAXK, j = threadIdx.x % B200_AR_MAXK;
+  const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(a.cnt);
+  const unsigned seq = (unsigned)(n + 1);
+  const size_t par = (size_t)(n & 1) * (size_t)a.R * B200_AR_MAXK;
+  __syncthreads();                                  // everybody has read n before thread 0 may bump it
+  if (r < a.R && j < k) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(vals[j]);
+    uint4 w = make_uint4((unsigned)bits, seq, (unsigned)(bits >> 32), seq);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(a.slot[r] + par + j), "r"(w.x), "r"(w.y), "r"(w.z), "r"(w.w) : "memory");
+    const uint4 *src = a.mine + par + (size_t)r * B200_AR_MAXK + j;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    for (;;) {
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "l"(src) : "memory");
+      if (w.y == seq && w.w == seq) break;
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+        if (dbg) { dbg[1] = r; dbg[2] = seq; dbg[3] = w.y; dbg[0] = 3; __threadfence_system(); }
+        __trap();
+      }
+    }
+    part[r][j] = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
   }
-  __syncwarp();
-  if (lane < a.k) {
+  __syncthreads();
+  if (threadIdx.x < k) {
     double s = 0.0;
-    for (int r = 0; r < a.R; r++) s += __ldcv(a.mine + (size_t)r * 8 + lane);
-    out[lane] = s;
+    for (int q = 0; q < a.R; q++) s += part[q][threadIdx.x];
+    out[threadIdx.x] = s;
   }
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(a.cnt) = n + 1;
 }
 __global__ void sum_ranks_kernel(int R, int k, const double *__restrict__ all, double *__restrict__ out) {
   const int j = threadIdx.x;
@@ -434,7 +455,7 @@ static int p2p_init(b200_handle h, b200_comm c) {
   P.free_by_off[0] = P.bytes;
   P.ok = true;
   // allreduce region
-  const size_t ar_bytes = sizeof(double) * 2 * R * 8 + sizeof(unsigned long long) * B200_P2P_SLOT * R;
+  const size_t ar_bytes = sizeof(uint4) * 2 * R * B200_AR_MAXK + sizeof(unsigned long long) * B200_P2P_SLOT;
   P.ar_off = b200_comm_p2p_alloc(h, c, ar_bytes);
   if (P.ar_off == (size_t)-1) { p2p_shutdown(c); return 0; }
   return 0;
@@ -442,7 +463,6 @@ static int p2p_init(b200_handle h, b200_comm c) {
 
 bool b200_comm_p2p_ok(b200_comm c) { return c && c->p2p.ok; }
 char *b200_comm_p2p_base(b200_comm c, int rank) { return c->p2p.peer[rank]; }
-unsigned long long b200_comm_p2p_next_seq(b200_comm c) { return ++c->p2p.seq; }
 
 size_t b200_comm_p2p_alloc(b200_handle h, b200_comm c, size_t bytes) {
   b200_p2p_s &P = c->p2p;
@@ -492,7 +512,7 @@ void b200_comm_p2p_free(b200_comm c, size_t offset, size_t bytes) {
 }
 
 int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *d_out) {
-  if (k < 1 || k > 8) B200_FAIL("allreduce_sum_dev2dev: 1..8 values");
+  if (k < 1 || k > B200_AR_MAXK) B200_FAIL("allreduce_sum_dev2dev: 1..16 values");
   const int R = c->nranks;
   if (R == 1) {
     B200_CUDA(cudaMemcpyAsync(d_out, d_vals, sizeof(double) * k, cudaMemcpyDeviceToDevice, h->stream));
@@ -500,25 +520,17 @@ int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_
   }
   b200_p2p_s &P = c->p2p;
   if (P.ok) {
-    const unsigned long long seq = ++P.seq;
-    const size_t par = (size_t)(P.ar_count++ & 1);
-    static const bool trace = [] { const char *e = getenv("B200_P2P_TRACE"); return e && e[0] == '1'; }();
-    if (trace) fprintf(stderr, "[p2p] rank %d seq %llu allreduce k %d par %zu\n", c->rank, seq, k, par);
-    const size_t slots = P.ar_off + sizeof(double) * par * R * 8, flags = P.ar_off + sizeof(double) * 2 * R * 8;
     ArArgs a;
-    a.R = R; a.me = c->rank; a.k = k;
-    for (int r = 0; r < R; r++) {
-      a.slot[r] = reinterpret_cast<double *>(P.peer[r] + slots) + (size_t)c->rank * 8;
-      a.flag[r] = reinterpret_cast<unsigned long long *>(P.peer[r] + flags) + (size_t)c->rank * B200_P2P_SLOT;
-    }
-    a.mine = reinterpret_cast<const double *>(P.base + slots);
-    a.myflag = reinterpret_cast<const unsigned long long *>(P.base + flags);
-    allreduce_kernel<<<1, 32, 0, h->stream>>>(a, d_vals, seq, d_out, p2p_timeout_ns(), g_b200_p2p_dbg);
+    a.R = R; a.me = c->rank;
+    for (int r = 0; r < R; r++) a.slot[r] = reinterpret_cast<uint4 *>(P.peer[r] + P.ar_off) + (size_t)c->rank * B200_AR_MAXK;
+    a.mine = reinterpret_cast<const uint4 *>(P.base + P.ar_off);
+    a.cnt = reinterpret_cast<unsigned long long *>(P.base + P.ar_off + sizeof(uint4) * 2 * R * B200_AR_MAXK);
+    allreduce_kernel<<<1, R * B200_AR_MAXK, 0, h->stream>>>(a, d_vals, k, d_out, p2p_timeout_ns(), g_b200_p2p_dbg);
     B200_LAUNCH_CHECK();
     return 0;
   }
   if (c->backend != 1) {          // rank threads without the peer layer: through the host
-    double v[8];
+    double v[B200_AR_MAXK];
     B200_TRY(b200_comm_allreduce_sum_dev(h, c, d_vals, k, v));
     B200_CUDA(cudaMemcpyAsync(d_out, v, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));

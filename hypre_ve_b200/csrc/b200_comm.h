@@ -32,7 +32,6 @@ size_t b200_comm_p2p_alloc(b200_handle h, b200_comm c, size_t bytes);
 // released regions are reused only after a collective quiescence point (taken lazily by the next allocation)
 void   b200_comm_p2p_free(b200_comm c, size_t offset, size_t bytes);
 char  *b200_comm_p2p_base(b200_comm c, int rank);          // base of rank's arena in this rank's address space
-unsigned long long b200_comm_p2p_next_seq(b200_comm c);
 // k <= 8 device-resident partial sums -> global sums in device memory on every rank, added in rank order (deterministic);
 // one kernel, no host synchronisation.  Falls back to ncclAllGather + a summation kernel without the peer layer.
 int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *d_out);
@@ -56,10 +55,9 @@ struct b200_halo_s {
   b200_comm comm = nullptr;
   std::vector<int> all_cnt;              // [R x R] all_cnt[r * R + s] = entries rank r receives from rank s
   int p2p_state = 0;                     // 0 not tried, 1 enabled, -1 unavailable (NCCL path)
-  size_t p2p_off = 0, p2p_bytes = 0;     // symmetric region: [rbuf parity 0 | rbuf parity 1 | arrival flags | ack flags | counters]
+  size_t p2p_off = 0, p2p_bytes = 0;     // symmetric region: [rbuf parity 0 | rbuf parity 1 | arrival flags | ack flags | local: count, CTA counters]
   int p2p_cap = 0;                       // doubles per parity buffer (max ghosts over the ranks, rounded up)
-  unsigned long long p2p_seq[2] = {0, 0};   // sequence numbers of the last two exchanges under this plan (ack targets)
-  unsigned long long p2p_count = 0;      // exchanges done under this plan (parity = count & 1)
+  void *p2p_args = nullptr;              // the exchange kernel's argument block (fixed for the life of the plan)
 };
 
 // halo operations (b200_dist.cu)

@@ -50,6 +50,9 @@ struct b200_dist_matrix_s {
   std::vector<int> row_starts, col_starts;   // ownership of rows / columns, size nranks+1
   b200_csr G = nullptr;         // local rows, GLOBAL column ids (setup form)
   b200_csr L = nullptr;         // local rows, localized columns [owned | ghosts] (solve form)
+  b200_csr Ls = nullptr;        // solve-phase copy of L with every row sorted by column (coarse Galerkin operators: the x gather
+                                // of neighbouring lanes then hits neighbouring lines).  L keeps the first-touch order
+                                // the next level's setup depends on.
   b200_halo_s *halo = nullptr;  // ghosts of L
 };
 
@@ -326,84 +329,114 @@ int b200_halo_build(b200_handle h, b200_comm c, const std::vector<int> &starts, 
   *out = p;
   return 0;
 }
+static void halo_args_delete(void *a);
 void b200_halo_free(b200_handle h, b200_halo_s *p) {
   if (!p) return;
-  if (p->p2p_state == 1) b200_comm_p2p_free(p->comm, p->p2p_off, p->p2p_bytes);
+  if (p->p2p_state == 1) { b200_comm_p2p_free(p->comm, p->p2p_off, p->p2p_bytes); halo_args_delete(p->p2p_args); }
   b200_dfree(h, p->d_ghost_gid); b200_dfree(h, p->d_send_idx); b200_dfree(h, p->d_send_buf);
   delete p;
 }
 
-// ---- direct halo exchange: pack-and-push into the neighbours' receive buffers over NVLink, flag, wait-and-copy -------------
+// ---- direct halo exchange: ONE kernel packs and pushes into the neighbours' receive buffers over NVLink, waits for its own
+// arrivals and copies them into the ghost tail ------------------------------------------------------------------------------
 // (hypre_ParCSRCommHandleCreate job 1 + hypre_ParCSRCommHandleDestroy, par_csr_communication.c:307-631, without a message
-// library on the data path).  Exchange number k of a plan uses receive buffer k & 1; a sender overwrites a buffer only after
-// the receiver acknowledged the exchange that used it before (k - 2).
+// library on the data path.)
+//
+// Protocol: every double travels as two self-validating 8-byte words {32 data bits, 32-bit sequence number}, written with
+// one 16-byte store.  The receiver polls the element itself until both halves carry the sequence number of this exchange: no
+// flag behind the data, hence NO system-scope fence on either side (a fence.sys costs microseconds with NVLink stores in
+// flight; the first version of this kernel spent most of its 20 us in them).  Exchange number k of a plan -- counted on the
+// device, in the plan's own region, so every kernel argument is fixed for the life of the plan and the exchange can sit in a
+// CUDA graph -- uses receive buffer k & 1 and sequence number k + 1; a sender overwrites a buffer only after the receiver
+// acknowledged the exchange that used it before (k - 2).  Acknowledgements are plain 8-byte counters.
 namespace {
-struct PeerList {
-  int n;
-  int off[B200_P2P_MAXPEER + 1];                  // entry ranges of the peers in the send list / ghost array
-  double *buf[B200_P2P_MAXPEER];                  // push: where my block starts in the peer's receive buffer
-  unsigned long long *raise[B200_P2P_MAXPEER];    // flag to raise on the peer (push: arrival, pull: acknowledgement)
-  const unsigned long long *wait[B200_P2P_MAXPEER];   // local flag to wait on (push: acknowledgement, pull: arrival)
+struct HaloArgs {
+  int n_push, n_pull, cap;
+  int send_off[B200_P2P_MAXPEER + 1];                  // entry ranges of the peers in the send list
+  uint4 *push_buf[B200_P2P_MAXPEER];                   // where my block starts in the peer's receive buffer (parity 0)
+  const unsigned long long *push_ack[B200_P2P_MAXPEER];   // my acknowledgement slot for that peer
+  unsigned long long *pull_ack[B200_P2P_MAXPEER];      // the source's acknowledgement slot for me
+  const uint4 *rbuf;                                   // my receive buffer (parity 0)
+  unsigned long long *cnt;                             // local: exchanges completed under this plan
+  unsigned *ctr;                                       // local: CTA counter
 };
-__device__ __forceinline__ unsigned long long p2p_ld_acquire(const unsigned long long *p) {
+__device__ __forceinline__ unsigned long long p2p_ld_relaxed(const unsigned long long *p) {
   unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void p2p_st_release(unsigned long long *p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void p2p_st_relaxed(unsigned long long *p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ void p2p_wait(const unsigned long long *flag, unsigned long long want, unsigned long long timeout_ns,
-                                         unsigned long long *dbg, int kind) {
-  if (p2p_ld_acquire(flag) >= want) return;
-  unsigned long long t0, t;
+__device__ __forceinline__ uint4 p2p_ld_pair(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void p2p_st_pair(uint4 *p, uint4 v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void p2p_timeout(unsigned long long t0, unsigned long long timeout_ns, unsigned long long *dbg, int kind,
+                                            unsigned long long want, unsigned long long have) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  if (t - t0 > timeout_ns) {                      // a peer that never arrives: an error at the next synchronisation, not a hang
+    if (dbg) { dbg[1] = threadIdx.x; dbg[2] = want; dbg[3] = have; dbg[0] = kind; __threadfence_system(); }
+    __trap();
+  }
+}
+// grid <= number of SMs: every CTA is resident, so a CTA that waits for a peer never keeps a sibling from being scheduled
+__global__ void __launch_bounds__(256)
+halo_exchange_kernel(int n_send, const int *__restrict__ idx, const double *__restrict__ src, int ng, double *__restrict__ ghost_out,
+                     HaloArgs a, unsigned long long timeout_ns, unsigned long long *dbg) {
+  const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(a.cnt);
+  const unsigned seq = (unsigned)(k + 1);
+  const unsigned long long ack_need = (k >= 2) ? k - 1 : 0;
+  const size_t par = (size_t)(k & 1) * (size_t)a.cap;
+  unsigned long long t0;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t0));
-  unsigned spins = 0;
-  while (p2p_ld_acquire(flag) < want) {
-    if ((++spins & 1023u) == 0) {
-      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) {                  // a peer that never arrives: an error at the next synchronisation, not a hang
-        if (dbg) { dbg[1] = threadIdx.x; dbg[2] = want; dbg[3] = p2p_ld_acquire(flag); dbg[0] = kind; __threadfence_system(); }
-        __trap();
-      }
+  if (n_send) {
+    if ((int)threadIdx.x < a.n_push && ack_need) {
+      unsigned spins = 0;
+      unsigned long long have;
+      while ((have = p2p_ld_relaxed(a.push_ack[threadIdx.x])) < ack_need)
+        if ((++spins & 1023u) == 0) p2p_timeout(t0, timeout_ns, dbg, 1, ack_need, have);
+    }
+    __syncthreads();
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_send; e += gridDim.x * blockDim.x) {
+      int q = 0;
+      while (e >= a.send_off[q + 1]) q++;
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(src[idx[e]]);
+      p2p_st_pair(a.push_buf[q] + par + (e - a.send_off[q]), make_uint4((unsigned)bits, seq, (unsigned)(bits >> 32), seq));
+    }
+  }
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < ng; e += gridDim.x * blockDim.x) {
+    const uint4 *slot = a.rbuf + par + e;
+    uint4 w = p2p_ld_pair(slot);
+    unsigned spins = 0;
+    while (w.y != seq || w.w != seq) {
+      if ((++spins & 1023u) == 0) p2p_timeout(t0, timeout_ns, dbg, 2, seq, w.y);
+      w = p2p_ld_pair(slot);
+    }
+    ghost_out[e] = __longlong_as_double((long long)(((unsigned long long)w.z << 32) | w.x));
+  }
+  // acknowledge and count: the last CTA has seen every sibling read k and finish its copies (loads have returned before the
+  // barrier; the device-scope fence keeps the acknowledgement behind them)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(a.ctr, 1u);
+    if (t == gridDim.x - 1) {
+      *a.ctr = 0;
+      __threadfence();
+      for (int q = 0; q < a.n_pull; q++) p2p_st_relaxed(a.pull_ack[q], k + 1);
+      *reinterpret_cast<volatile unsigned long long *>(a.cnt) = k + 1;
     }
   }
 }
-// the last CTA of the grid raises the flags: every CTA fences its stores, then counts itself in
-__device__ __forceinline__ bool p2p_last_cta(unsigned *counter) {
-  __shared__ bool last;
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(counter, 1u);
-    last = (t == gridDim.x - 1);
-    if (last) *counter = 0;
-  }
-  __syncthreads();
-  if (last) __threadfence_system();
-  return last;
-}
-__global__ void halo_push_kernel(int n_send, const int *__restrict__ idx, const double *__restrict__ src, PeerList P,
-                                 unsigned long long seq, unsigned long long ack_need, unsigned *counter,
-                                 unsigned long long timeout_ns, unsigned long long *dbg) {
-  if ((int)threadIdx.x < P.n && ack_need) p2p_wait(P.wait[threadIdx.x], ack_need, timeout_ns, dbg, 1);
-  __syncthreads();
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_send; k += gridDim.x * blockDim.x) {
-    int q = 0;
-    while (k >= P.off[q + 1]) q++;
-    P.buf[q][k - P.off[q]] = src[idx[k]];
-  }
-  if (p2p_last_cta(counter) && (int)threadIdx.x < P.n) p2p_st_release(P.raise[threadIdx.x], seq);
-}
-__global__ void halo_pull_kernel(int ng, const double *rbuf, double *__restrict__ ghost_out, PeerList P, unsigned long long seq,
-                                 unsigned *counter, unsigned long long timeout_ns, unsigned long long *dbg) {
-  if ((int)threadIdx.x < P.n) p2p_wait(P.wait[threadIdx.x], seq, timeout_ns, dbg, 2);
-  __syncthreads();
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < ng; k += gridDim.x * blockDim.x) ghost_out[k] = __ldcv(rbuf + k);
-  if (p2p_last_cta(counter) && (int)threadIdx.x < P.n) p2p_st_release(P.raise[threadIdx.x], seq);
-}
 }  // namespace
 
+static void halo_args_delete(void *a) { delete static_cast<HaloArgs *>(a); }
 static unsigned long long halo_timeout_ns() {
   static const unsigned long long t = [] { const char *e = getenv("B200_P2P_TIMEOUT_S"); int s = e ? atoi(e) : 30; return (unsigned long long)(s > 0 ? s : 30) * 1000000000ull; }();
   return t;
@@ -413,7 +446,7 @@ static unsigned long long halo_timeout_ns() {
 static void halo_p2p_enable(b200_handle h, b200_comm c, b200_halo_s *p) {
   p->p2p_state = -1;
   if (!b200_comm_p2p_ok(c)) return;
-  const int R = b200_comm_size(c);
+  const int R = b200_comm_size(c), me = b200_comm_rank(c);
   int cap = 0, maxpeers = 0;
   for (int r = 0; r < R; r++) {
     int ng_r = 0, nrecv = 0, nsend = 0;
@@ -428,64 +461,45 @@ static void halo_p2p_enable(b200_handle h, b200_comm c, b200_halo_s *p) {
   if (maxpeers > B200_P2P_MAXPEER) return;
   cap = (cap + 31) & ~31;
   const size_t slot = sizeof(unsigned long long) * B200_P2P_SLOT;
-  const size_t bytes = sizeof(double) * 2 * (size_t)cap + slot * R * 2 + slot * 2;
+  const size_t bytes = sizeof(uint4) * 2 * (size_t)cap + slot * R + slot * 2;
   const size_t off = b200_comm_p2p_alloc(h, c, bytes);
   if (off == (size_t)-1) return;
   p->p2p_off = off; p->p2p_bytes = bytes; p->p2p_cap = cap; p->p2p_state = 1;
+  // the kernel's argument block, fixed for the life of the plan
+  const size_t off_ack = off + sizeof(uint4) * 2 * (size_t)cap, off_loc = off_ack + slot * R;
+  char *mine = b200_comm_p2p_base(c, me);
+  HaloArgs *a = new HaloArgs();
+  memset(a, 0, sizeof *a);
+  a->cap = cap;
+  for (int r = 0; r < R; r++) {
+    if (!p->send_cnt[r]) continue;
+    char *pb = b200_comm_p2p_base(c, r);
+    int roff = 0;                                              // where my block starts in r's ghost array (ghosts sorted by owner)
+    for (int s2 = 0; s2 < me; s2++) roff += p->all_cnt[(size_t)r * R + s2];
+    const int q = a->n_push++;
+    a->push_buf[q] = reinterpret_cast<uint4 *>(pb + off) + roff;
+    a->push_ack[q] = reinterpret_cast<const unsigned long long *>(mine + off_ack + slot * r);
+    a->send_off[q + 1] = a->send_off[q] + p->send_cnt[r];
+  }
+  for (int r = 0; r < R; r++) {
+    if (!p->recv_cnt[r]) continue;
+    char *pb = b200_comm_p2p_base(c, r);
+    a->pull_ack[a->n_pull++] = reinterpret_cast<unsigned long long *>(pb + off_ack + slot * me);
+  }
+  a->rbuf = reinterpret_cast<const uint4 *>(mine + off);
+  a->cnt = reinterpret_cast<unsigned long long *>(mine + off_loc);
+  a->ctr = reinterpret_cast<unsigned *>(mine + off_loc + slot);
+  p->p2p_args = a;
 }
 
 static int halo_forward_p2p(b200_handle h, b200_comm c, b200_halo_s *p, const double *owned, double *ghost_out) {
-  const int R = b200_comm_size(c), me = b200_comm_rank(c);
-  const size_t slot = sizeof(unsigned long long) * B200_P2P_SLOT;
-  const size_t off_arr = p->p2p_off + sizeof(double) * 2 * (size_t)p->p2p_cap, off_ack = off_arr + slot * R, off_cnt = off_ack + slot * R;
-  const unsigned long long seq = b200_comm_p2p_next_seq(c);
-  const size_t par = (size_t)(p->p2p_count & 1);
-  const unsigned long long ack_need = p->p2p_seq[par];       // the exchange that used this receive buffer before
-  p->p2p_seq[par] = seq;
-  p->p2p_count++;
-  char *mine = b200_comm_p2p_base(c, me);
-  static const bool trace = [] { const char *e = getenv("B200_P2P_TRACE"); return e && e[0] == '1'; }();
-  if (trace) fprintf(stderr, "[p2p] rank %d seq %llu halo plan %p off %zu cap %d par %zu ack_need %llu n_send %d ng %d\n", me, seq, (void *)p,
-                     p->p2p_off, p->p2p_cap, par, ack_need, p->n_send, p->ng);
-  if (p->n_send) {
-    PeerList L;
-    L.n = 0; L.off[0] = 0;
-    for (int r = 0; r < R; r++) {
-      if (!p->send_cnt[r]) continue;
-      char *pb = b200_comm_p2p_base(c, r);
-      int roff = 0;                                            // where my block starts in r's ghost array (ghosts sorted by owner)
-      for (int s2 = 0; s2 < me; s2++) roff += p->all_cnt[(size_t)r * R + s2];
-      L.buf[L.n] = reinterpret_cast<double *>(pb + p->p2p_off) + par * (size_t)p->p2p_cap + roff;
-      L.raise[L.n] = reinterpret_cast<unsigned long long *>(pb + off_arr + slot * me);
-      L.wait[L.n] = reinterpret_cast<const unsigned long long *>(mine + off_ack + slot * r);
-      L.off[L.n + 1] = L.off[L.n] + p->send_cnt[r];
-      L.n++;
-    }
-    int grid = b200_grid(p->n_send, 256);
-    if (grid > h->num_sm * 4) grid = h->num_sm * 4;
-    halo_push_kernel<<<grid, 256, 0, h->stream>>>(p->n_send, p->d_send_idx, owned, L, seq, ack_need,
-                                                  reinterpret_cast<unsigned *>(mine + off_cnt), halo_timeout_ns(), g_b200_p2p_dbg);
-    B200_LAUNCH_CHECK();
-  }
-  if (p->ng) {
-    PeerList L;
-    L.n = 0; L.off[0] = 0;
-    for (int r = 0; r < R; r++) {
-      if (!p->recv_cnt[r]) continue;
-      char *pb = b200_comm_p2p_base(c, r);
-      L.buf[L.n] = nullptr;
-      L.wait[L.n] = reinterpret_cast<const unsigned long long *>(mine + off_arr + slot * r);
-      L.raise[L.n] = reinterpret_cast<unsigned long long *>(pb + off_ack + slot * me);
-      L.off[L.n + 1] = L.off[L.n] + p->recv_cnt[r];
-      L.n++;
-    }
-    int grid = b200_grid(p->ng, 256);
-    if (grid > h->num_sm * 2) grid = h->num_sm * 2;
-    halo_pull_kernel<<<grid, 256, 0, h->stream>>>(p->ng, reinterpret_cast<const double *>(mine + p->p2p_off) + par * (size_t)p->p2p_cap,
-                                                  ghost_out, L, seq, reinterpret_cast<unsigned *>(mine + off_cnt + slot),
-                                                  halo_timeout_ns(), g_b200_p2p_dbg);
-    B200_LAUNCH_CHECK();
-  }
+  if (!p->n_send && !p->ng) return 0;
+  const HaloArgs *a = static_cast<const HaloArgs *>(p->p2p_args);
+  int grid = b200_grid(std::max(p->n_send, p->ng), 256);
+  if (grid > h->num_sm) grid = h->num_sm;
+  halo_exchange_kernel<<<grid, 256, 0, h->stream>>>(p->n_send, p->d_send_idx, owned, p->ng, ghost_out, *a, halo_timeout_ns(),
+                                                    g_b200_p2p_dbg);
+  B200_LAUNCH_CHECK();
   return 0;
 }
 
@@ -805,6 +819,7 @@ extern "C" int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix M) {
   if (!M) return 0;
   B200_TRY(b200_csr_destroy(h, M->G));
   B200_TRY(b200_csr_destroy(h, M->L));
+  if (M->Ls) B200_TRY(b200_csr_destroy(h, M->Ls));
   b200_halo_free(h, M->halo);
   delete M;
   return 0;
@@ -842,9 +857,13 @@ extern "C" int b200_dist_matrix_download(b200_handle h, b200_dist_matrix M, int 
 
 // halo of x (job 1) straight into the ghost tail, then ONE kernel over [owned | ghost]
 static int dist_spmv(b200_handle h, b200_comm c, b200_dist_matrix M, double *x, double *y, int mode, double alpha, double beta,
-                     const double *b, const double *d) {
-  if (M->halo->any_traffic) B200_TRY(b200_halo_forward_f64(h, c, M->halo, x, x + M->n_owned_cols));
-  return b200_csr_spmv_epi(h, M->L, x, y, mode, alpha, beta, b, d);
+                     const double *b, const double *d, const char *what = "spmv", int level = -1) {
+  if (M->halo->any_traffic) {
+    b200_prof_scope ps(h, "halo", level);
+    B200_TRY(b200_halo_forward_f64(h, c, M->halo, x, x + M->n_owned_cols));
+  }
+  b200_prof_scope ps(h, what, level);
+  return b200_csr_spmv_epi(h, M->Ls ? M->Ls : M->L, x, y, mode, alpha, beta, b, d);
 }
 extern "C" int b200_dist_matvec(b200_handle h, b200_comm c, double alpha, b200_dist_matrix M, double *d_x, double beta,
                                 const double *d_b, double *d_y) {
@@ -1304,6 +1323,19 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_FAIL("coarsening stalled (coarse >= 0.75 fine): the reference switches to CLJP here, which is out of scope");
   }
   const int nl = (int)amg->lv.size();
+  // column-sorted solve copies of the coarse Galerkin operators (Jacobi-type smoothers only: the Gauss-Seidel kernels need
+  // the diagonal entry first)
+  {
+    static const bool no_sort = [] { const char *e = getenv("B200_NO_SORTED_COPY"); return e && e[0] == '1'; }();
+    for (int l = 1; l < nl - 1 && !amg->gs && !no_sort; l++) {
+      b200_dist_matrix M = amg->lv[l].A;
+      if ((double)M->L->nnz > 12.0 * M->n && !M->Ls) {
+        B200_TRY(b200_csr_sorted_copy(h, M->L, &M->Ls));
+        B200_TRY(b200_csr_build_plan(h, M->Ls));
+      }
+    }
+    mark("sorted solve copies");
+  }
   // vectors: capacity = owned + the largest ghost set any operator reads them with
   for (int l = 0; l < nl; l++) {
     dist_level &L = amg->lv[l];
@@ -1462,23 +1494,25 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
     dist_level &Lc = amg->lv[l + 1];
     double *ucur = (l == 0) ? L.T : L.U;
     if (L.n) {
+      b200_prof_scope ps(h, "presmooth", l);
       jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, ucur);
       B200_LAUNCH_CHECK();
     }
     U[l] = ucur;
-    B200_TRY(dist_spmv(h, c, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));        // Vtemp = F - A U
-    B200_TRY(dist_spmv(h, c, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr));      // F_{l+1} = R Vtemp
+    B200_TRY(dist_spmv(h, c, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr, "residual", l));        // Vtemp = F - A U
+    B200_TRY(dist_spmv(h, c, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr, "restrict", l));      // F_{l+1} = R Vtemp
   }
   {
     dist_level &L = amg->lv[nl - 1];
+    b200_prof_scope ps(h, "coarse solve", nl - 1);
     B200_TRY(coarse_solve(L, L.F, L.U));
     U[nl - 1] = L.U;
   }
   for (int l = nl - 2; l >= 0; l--) {
     dist_level &L = amg->lv[l];
-    B200_TRY(dist_spmv(h, c, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));           // U_l += P U_{l+1}
+    B200_TRY(dist_spmv(h, c, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr, "prolong", l));           // U_l += P U_{l+1}
     double *dst = (l == 0) ? u : L.T;
-    B200_TRY(dist_spmv(h, c, L.A, U[l], dst, 1, w, 0.0, F[l], L.l1));                      // l1-Jacobi post-sweep
+    B200_TRY(dist_spmv(h, c, L.A, U[l], dst, 1, w, 0.0, F[l], L.l1, "postsmooth", l));                   // l1-Jacobi post-sweep
     if (l > 0) { std::swap(L.U, L.T); U[l] = L.U; }
   }
   return 0;
@@ -1574,30 +1608,39 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
     if (h_norms) { if ((rc = fetch())) break; h_norms[0] = std::sqrt(hs[1]); }
     while ((i + 1) <= max_iter) {
       i++;
-      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr))) break;   // s = A p (pcg.c:512)
-      if ((rc = b200_vec_dot_dev(h, n, s, p, lp))) break;                          // <s,p> (pcg.c:515)
-      if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 2))) break;
-      dpcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
-      ++g_b200_launches;
-      dpcg_update_xr_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, p, s, xx, r);
-      ++g_b200_launches;
-      if ((rc = precond(r, s))) break;                                             // s = C r (pcg.c:568-569)
-      if ((rc = b200_vec_dot_dev(h, n, r, s, lp))) break;                          // gamma = <r,s> (pcg.c:572)
-      if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break;                      // i_prod = <r,r> (pcg.c:590)
-      if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break;
-      if ((rc = fetch())) break;
+      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr, "pcg s=Ap"))) break;   // s = A p (pcg.c:512)
+      { b200_prof_scope ps(h, "pcg dot");
+        if ((rc = b200_vec_dot_dev(h, n, s, p, lp))) break; }                      // <s,p> (pcg.c:515)
+      { b200_prof_scope ps(h, "pcg allreduce");
+        if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 2))) break; }
+      { b200_prof_scope ps(h, "pcg update x,r");
+        dpcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
+        ++g_b200_launches;
+        dpcg_update_xr_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, p, s, xx, r);
+        ++g_b200_launches; }
+      { b200_prof_scope ps(h, "pcg precond (whole cycle)");
+        if ((rc = precond(r, s))) break; }                                         // s = C r (pcg.c:568-569)
+      { b200_prof_scope ps(h, "pcg dot");
+        if ((rc = b200_vec_dot_dev(h, n, r, s, lp))) break;                        // gamma = <r,s> (pcg.c:572)
+        if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break; }                  // i_prod = <r,r> (pcg.c:590)
+      { b200_prof_scope ps(h, "pcg allreduce");
+        if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break; }
+      { b200_prof_scope ps(h, "pcg fetch+sync");
+        if ((rc = fetch())) break; }
       const double gamma = hs[0], sdotp = hs[2];
       i_prod = hs[1];
       if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }   // pcg.c:516-521
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;
       if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
+      b200_prof_scope ps(h, "pcg update p");
       dpcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
       ++g_b200_launches;
       dpcg_update_p_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, s, p);
       ++g_b200_launches;
     }
   } while (0);
+  b200_prof_report(h, "b200_dist_pcg_solve");
   if (!rc) {
     if (!x_is_b) cudaMemcpyAsync(d_x, xx, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream);
     if (iters_out) *iters_out = i;

@@ -17,6 +17,7 @@
 #define B200_SPMV_MAX_TILE 1024   // upper bound on the entries of one tile
 
 struct b200_pool_s;   // slab sub-allocator (b200_runtime.cu)
+struct b200_prof_s;   // region profiler (b200_runtime.cu)
 
 struct b200_handle_s {
   int device = 0;
@@ -28,6 +29,7 @@ struct b200_handle_s {
   double *d_partials = nullptr;
   double *h_pinned = nullptr;   // 1024 doubles, pinned
   int     n_partials = 0;
+  b200_prof_s *prof = nullptr;
 };
 
 // Device CSR block.  Arrays are over-allocated by B200_PAD entries so kernels may issue aligned
@@ -88,6 +90,18 @@ extern unsigned long long *g_b200_p2p_dbg;
     cudaError_t e__ = cudaGetLastError();                                        \
     if (e__ != cudaSuccess) return b200_set_error(__FILE__, __LINE__, cudaGetErrorString(e__)); \
   } while (0)
+
+// B200_PROF=1: CUDA-event timing of labelled regions on the handle's stream, summed per label and printed by
+// b200_prof_report (stderr).  Off by default: one predictable branch per region.
+struct b200_prof_s;
+void b200_prof_begin(b200_handle h, const char *label, int level);
+void b200_prof_end(b200_handle h);
+void b200_prof_report(b200_handle h, const char *title);
+struct b200_prof_scope {
+  b200_handle h;
+  b200_prof_scope(b200_handle h_, const char *label, int level = -1) : h(h_) { b200_prof_begin(h, label, level); }
+  ~b200_prof_scope() { b200_prof_end(h); }
+};
 
 // device allocation: slab sub-allocator owned by the handle.  All work of a handle runs on one
 // stream, so a freed block may be handed out again immediately (stream order keeps it safe).

@@ -132,6 +132,54 @@ extern "C" int b200_pool_stats(b200_handle h, size_t *reserved, size_t *in_use, 
   return 0;
 }
 
+// ---- region profiler (B200_PROF=1) -----------------------------------------------------------------------------------------
+struct b200_prof_s {
+  struct Rec { std::string label; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<size_t> open;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+static bool prof_on() {
+  static const bool on = [] { const char *e = getenv("B200_PROF"); return e && e[0] == '1'; }();
+  return on;
+}
+void b200_prof_begin(b200_handle h, const char *label, int level) {
+  if (!prof_on()) return;
+  if (!h->prof) h->prof = new b200_prof_s();
+  b200_prof_s::Rec r;
+  char buf[96];
+  if (level >= 0) { snprintf(buf, sizeof buf, "L%d %s", level, label); r.label = buf; } else r.label = label;
+  r.a = h->prof->get(); r.b = h->prof->get();
+  cudaEventRecord(r.a, h->stream);
+  h->prof->open.push_back(h->prof->recs.size());
+  h->prof->recs.push_back(r);
+}
+void b200_prof_end(b200_handle h) {
+  if (!prof_on() || !h->prof || h->prof->open.empty()) return;
+  cudaEventRecord(h->prof->recs[h->prof->open.back()].b, h->stream);
+  h->prof->open.pop_back();
+}
+void b200_prof_report(b200_handle h, const char *title) {
+  if (!prof_on() || !h->prof) return;
+  cudaStreamSynchronize(h->stream);
+  std::map<std::string, std::pair<double, int>> acc;
+  for (auto &r : h->prof->recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    acc[r.label].first += ms; acc[r.label].second++;
+    h->prof->pool.push_back(r.a); h->prof->pool.push_back(r.b);
+  }
+  h->prof->recs.clear(); h->prof->open.clear();
+  fprintf(stderr, "[b200 prof] %s (device %d)\n", title, h->device);
+  for (auto &kv : acc)
+    fprintf(stderr, "[b200 prof]   %-34s %10.3f ms  %6d calls  %9.2f us/call\n", kv.first.c_str(), kv.second.first, kv.second.second,
+            1e3 * kv.second.first / kv.second.second);
+}
+
 thread_local std::string g_b200_err;
 std::atomic<long long> g_b200_launches{0};
 
