@@ -369,10 +369,8 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
         if (!L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, ip["GSBlocks"], &L.A->gs));
       }
     }
-    if (l > 0) {
-      B200_TRY(b200_dalloc<double>(h, &L.F, L.n));
-      B200_TRY(b200_dalloc<double>(h, &L.U, L.n));
-    }
+    if (l > 0) B200_TRY(b200_dalloc<double>(h, &L.F, L.n));
+    B200_TRY(b200_dalloc<double>(h, &L.U, L.n));
     B200_TRY(b200_dalloc<double>(h, &L.T, L.n));
   }
   B200_TRY(b200_dalloc<double>(h, &amg->Vtemp, amg->lv[0].n));
@@ -519,27 +517,22 @@ static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bo
     B200_TRY(b200_vec_copy(h, L.n, L.T, u));
     return 0;
   }
+  // Every level keeps two buffers with fixed roles -- U: the pre-smoothed iterate, later the level's final iterate; T: the
+  // iterate after the coarse-grid correction -- so that the kernel arguments of a cycle never change from one application to
+  // the next (the PCG loop replays the whole iteration as a CUDA graph).
   for (int l = 0; l < nl - 1; l++) {
     b200_level &L = amg->lv[l];
     b200_level &Lc = amg->lv[l + 1];
-    double *ucur;
     const bool zero = (l > 0) || u_zero;          // coarse iterates start at 0 (par_cycle.c:538)
-    if (l == 0) {
-      ucur = L.T;                                 // pre-smoothed iterate lives in T so the last sweep can write u
-      if (zero) {
-        jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, f, L.l1, ucur);
-        B200_LAUNCH_CHECK();
-      } else {
-        B200_TRY(jacobi(h, L, w, f, u, ucur));
-      }
-    } else {
-      ucur = L.U;
-      jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, ucur);
+    if (zero) {
+      jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, L.U);
       B200_LAUNCH_CHECK();
+    } else {
+      B200_TRY(jacobi(h, L, w, f, u, L.U));
     }
-    U[l] = ucur;
+    U[l] = L.U;
     // Vtemp = F - A U (par_cycle.c:549) ; F_{l+1} = R Vtemp (:566)
-    B200_TRY(b200_csr_spmv_epi(h, L.As, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
+    B200_TRY(b200_csr_spmv_epi(h, L.As, L.U, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));
     B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr));
   }
   // coarsest level
@@ -556,15 +549,16 @@ static int amg_cycle(b200_handle h, b200_amg amg, const double *f, double *u, bo
   }
   for (int l = nl - 2; l >= 0; l--) {
     b200_level &L = amg->lv[l];
-    // U_l += P U_{l+1} (:602), in place: row r reads and writes only U_l[r]
-    B200_TRY(b200_csr_spmv_epi(h, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));
-    // post-smoothing sweep
-    double *dst = (l == 0) ? u : L.T;
-    B200_TRY(jacobi(h, L, w, F[l], U[l], dst));
-    if (l > 0) { std::swap(L.U, L.T); U[l] = L.U; }
+    // T_l = U_l + P U_{l+1} (:602)
+    B200_TRY(b200_csr_spmv_epi(h, L.P, U[l + 1], L.T, 0, 1.0, 1.0, L.U, nullptr));
+    // post-smoothing sweep: the level's final iterate
+    B200_TRY(jacobi(h, L, w, F[l], L.T, (l == 0) ? u : L.U));
   }
   return 0;
 }
+
+// the plain V(1,1) l1-Jacobi / Jacobi cycle above launches a fixed kernel sequence with fixed arguments
+static bool amg_cycle_is_static(b200_amg amg) { return !(amg->general_cycle && amg->lv.size() > 1) && !amg->gs; }
 
 __global__ void diag_scale_kernel(size_t n, const int *__restrict__ A_i, const double *__restrict__ A_a,
                                   const double *__restrict__ y, double *__restrict__ x) {
@@ -655,6 +649,7 @@ extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, con
     return b200_vec_copy(h, n, rhs, out);                 // identity preconditioner (hypre_ParKrylovIdentity)
   };
   int rc = 0, i = 0;
+  long long launches_per_graph = 0;
   double bi_prod = 0, i_prod = 0, eps = 0;
   do {
     if (two_norm) {
@@ -683,18 +678,51 @@ extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, con
       else { if ((rc = b200_vec_dot(h, n, r, p, &i_prod_0))) break; }
       h_norms[0] = std::sqrt(i_prod_0);
     }
-    while ((i + 1) <= max_iter) {                                           // :498
-      i++;
-      if ((rc = b200_parcsr_matvec(h, 1.0, A, p, 0.0, nullptr, s))) break;  // s = A p (:512)
-      if ((rc = b200_vec_dot_dev(h, n, s, p, sc + 1))) break;               // sdotp (:515)
+    // One iteration = [beta, p update] of the previous one + [s = A p, <s,p>, alpha, x/r update, s = C r, <r,s>, <r,r>, copy of
+    // the scalars to the host]: a fixed kernel sequence with fixed arguments.  Iteration 1 runs eagerly (everything lazily
+    // built is built), iteration 2 is captured into a CUDA graph while it runs, iterations 3.. replay it: one launch and one
+    // synchronisation per iteration instead of ~100 launches, a third of them on levels where the launch outlasts the kernel.
+    const bool graph_ok = b200_graph_enabled() && (!amg || amg_cycle_is_static(amg));
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_tried = false;
+    auto body = [&](bool with_beta) -> int {
+      if (with_beta) {
+        pcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
+        ++g_b200_launches;
+        pcg_update_p_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, s, p);
+        ++g_b200_launches;
+      }
+      B200_TRY(b200_parcsr_matvec(h, 1.0, A, p, 0.0, nullptr, s));          // s = A p (:512)
+      B200_TRY(b200_vec_dot_dev(h, n, s, p, sc + 1));                       // sdotp (:515)
       pcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
       ++g_b200_launches;
       pcg_update_xr_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, p, s, d_x, r);
       ++g_b200_launches;
-      if ((rc = precond(r, s))) break;                                      // s = C r (:568-569)
-      if ((rc = b200_vec_dot_dev(h, n, r, s, sc + 0))) break;               // gamma = <r,s> (:572)
-      if (two_norm) { if ((rc = b200_vec_dot_dev(h, n, r, r, sc + 3))) break; }   // i_prod = <r,r> (:590)
-      cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+      B200_TRY(precond(r, s));                                              // s = C r (:568-569)
+      B200_TRY(b200_vec_dot_dev(h, n, r, s, sc + 0));                       // gamma = <r,s> (:572)
+      if (two_norm) B200_TRY(b200_vec_dot_dev(h, n, r, r, sc + 3));         // i_prod = <r,r> (:590)
+      B200_CUDA(cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      return 0;
+    };
+    while ((i + 1) <= max_iter) {                                           // :498
+      i++;
+      if (i >= 2 && gexec) {
+        if ((rc = b200_graph_launch(h, gexec))) break;
+        g_b200_launches += launches_per_graph;
+      } else if (i == 2 && graph_ok && !graph_tried) {
+        graph_tried = true;
+        const long long l0 = g_b200_launches.load();
+        if ((rc = b200_graph_begin(h))) break;
+        rc = body(true);
+        cudaGraphExec_t ge = nullptr;
+        int rc2 = b200_graph_end(h, &ge);
+        if (rc || rc2) { if (!rc) rc = rc2; break; }
+        launches_per_graph = g_b200_launches.load() - l0;
+        if (ge) { gexec = ge; if ((rc = b200_graph_launch(h, gexec))) break; }
+        else { g_b200_launches -= launches_per_graph; if ((rc = body(true))) break; }      // capture refused: run it eagerly
+      } else {
+        if ((rc = body(i > 1))) break;
+      }
       if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = b200_set_error(__FILE__, __LINE__, "pcg sync failed"); break; }
       const double gamma = hs[0], sdotp = hs[1];
       i_prod = two_norm ? hs[3] : gamma;                                    // :589-592
@@ -702,11 +730,8 @@ extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, con
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;                                    // converged (:634, :672-676)
       if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
-      pcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
-      ++g_b200_launches;
-      pcg_update_p_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, s, p);
-      ++g_b200_launches;
     }
+    b200_graph_destroy(gexec);
   } while (0);
   if (!rc) {
     if (iters_out) *iters_out = i;

@@ -117,6 +117,7 @@ struct b200_comm_s {
   size_t stage_bytes = 0;
   b200_p2p_s p2p;
   int device = 0;
+  long long host_ops = 0;          // exchanges / gathers that went through NCCL or the host (not replayable in a CUDA graph)
 };
 
 extern "C" int b200_comm_create_single(b200_comm *out) {
@@ -201,7 +202,9 @@ extern "C" int b200_comm_rank(b200_comm c) { return c ? c->rank : 0; }
 extern "C" int b200_comm_size(b200_comm c) { return c ? c->nranks : 1; }
 
 // ---- the exchange primitive: every rank passes its sends and recvs (device pointers) -------------
+long long b200_comm_host_ops(b200_comm c) { return c ? c->host_ops : 0; }
 int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> &sends, const std::vector<b200_xfer> &recvs) {
+  c->host_ops++;
   if (c->nranks == 1) {
     // self messages only
     for (const auto &r : recvs)
@@ -244,6 +247,7 @@ int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> 
 
 // host allgather of `bytes` bytes per rank
 int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all) {
+  c->host_ops++;
   if (c->nranks == 1) { memcpy(all, mine, bytes); return 0; }
   if (c->backend == 2) {
     b200_comm_group_s *g = c->group;

@@ -34,6 +34,7 @@ void   b200_comm_p2p_free(b200_comm c, size_t offset, size_t bytes);
 char  *b200_comm_p2p_base(b200_comm c, int rank);          // base of rank's arena in this rank's address space
 // k <= 8 device-resident partial sums -> global sums in device memory on every rank, added in rank order (deterministic);
 // one kernel, no host synchronisation.  Falls back to ncclAllGather + a summation kernel without the peer layer.
+long long b200_comm_host_ops(b200_comm c);      // number of exchanges that did not stay on the device-only path
 int b200_comm_allreduce_sum_dev2dev(b200_handle h, b200_comm c, const double *d_vals, int k, double *d_out);
 
 // Halo plan = hypre_ParCSRCommPkg (parcsr_mv/par_csr_communication.h:54-82) for one ghost set:

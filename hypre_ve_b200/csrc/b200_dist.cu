@@ -1373,7 +1373,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       double *loc = nullptr;
       B200_TRY(b200_dalloc<double>(h, &loc, (size_t)Lc.n * ncg + 1));
       B200_TRY(b200_dalloc<double>(h, &amg->ge_A, (size_t)2 * ncg * ncg + 1));
-      B200_TRY(b200_dalloc<double>(h, &amg->ge_f, (size_t)2 * ncg + 1));
+      B200_TRY(b200_dalloc<double>(h, &amg->ge_f, (size_t)3 * ncg + 1));
       if (Lc.n) {
         dense_rows_kernel<<<b200_grid(Lc.n, 64), 64, 0, h->stream>>>(Lc.n, ncg, Lc.A->G->i, Lc.A->G->j, Lc.A->G->a, loc);
         B200_LAUNCH_CHECK();
@@ -1425,12 +1425,29 @@ extern "C" int b200_dist_amg_level_cf(b200_handle h, b200_dist_amg amg, int l, i
 }
 extern "C" int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms) { if (!amg) B200_FAIL("null"); *ms = amg->setup_ms; return 0; }
 
+__global__ void ge_scatter_kernel(int ncg, int first, int n, const double *__restrict__ f, double *__restrict__ out) {
+  const int j = threadIdx.x;
+  if (j < ncg) out[j] = (j >= first && j < first + n) ? f[j - first] : 0.0;
+}
+
 // one V(1,1) cycle across ranks (par_cycle.c:255-622); u is zero on entry (PCG clears it)
 static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const double *f, double *u /* capacity >= lv[0].cap */) {
   const int nl = (int)amg->lv.size();
   const double w = amg->relax_wt;
   const int me = b200_comm_rank(c), R = b200_comm_size(c);
   auto coarse_solve = [&](dist_level &L, const double *F, double *U) -> int {
+    if (amg->coarse_ge && amg->ge_n <= 16 && b200_comm_p2p_ok(c)) {
+      // Allgatherv of f (par_gauss_elim.c:264) as a rank-ordered device-to-device sum of vectors that are zero outside the
+      // rank's own rows (x + 0 is exact): one kernel, no message library, capturable in the iteration's CUDA graph
+      const int ncg = amg->ge_n;
+      ge_scatter_kernel<<<1, 32, 0, h->stream>>>(ncg, amg->ge_starts[me], L.n, F, amg->ge_f + 2 * ncg);
+      B200_LAUNCH_CHECK();
+      B200_TRY(b200_comm_allreduce_sum_dev2dev(h, c, amg->ge_f + 2 * ncg, ncg, amg->ge_f));
+      gselim_kernel2<<<1, 32, 0, h->stream>>>(ncg, amg->ge_A, amg->ge_A + (size_t)ncg * ncg, amg->ge_f, amg->ge_f + ncg);
+      B200_LAUNCH_CHECK();
+      if (L.n) B200_CUDA(cudaMemcpyAsync(U, amg->ge_f + ncg + amg->ge_starts[me], sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));
+      return 0;
+    }
     if (amg->coarse_ge) {
       const int ncg = amg->ge_n;
       std::vector<b200_xfer> sends, recvs;               // Allgatherv of f (par_gauss_elim.c:264)
@@ -1488,18 +1505,19 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
     }
     return 0;
   }
+  // Every level keeps two buffers with fixed roles -- U: the pre-smoothed iterate, later the level's final iterate; T: the
+  // iterate after the coarse-grid correction -- so the kernel arguments of a cycle never change (CUDA-graph replay in PCG).
   for (int l = 1; l < nl; l++) F[l] = amg->lv[l].F;
   for (int l = 0; l < nl - 1; l++) {
     dist_level &L = amg->lv[l];
     dist_level &Lc = amg->lv[l + 1];
-    double *ucur = (l == 0) ? L.T : L.U;
     if (L.n) {
       b200_prof_scope ps(h, "presmooth", l);
-      jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, ucur);
+      jacobi_zero_kernel2<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[l], L.l1, L.U);
       B200_LAUNCH_CHECK();
     }
-    U[l] = ucur;
-    B200_TRY(dist_spmv(h, c, L.A, ucur, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr, "residual", l));        // Vtemp = F - A U
+    U[l] = L.U;
+    B200_TRY(dist_spmv(h, c, L.A, L.U, amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr, "residual", l));        // Vtemp = F - A U
     B200_TRY(dist_spmv(h, c, L.R, amg->Vtemp, Lc.F, 0, 1.0, 0.0, nullptr, nullptr, "restrict", l));      // F_{l+1} = R Vtemp
   }
   {
@@ -1510,10 +1528,8 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
   }
   for (int l = nl - 2; l >= 0; l--) {
     dist_level &L = amg->lv[l];
-    B200_TRY(dist_spmv(h, c, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr, "prolong", l));           // U_l += P U_{l+1}
-    double *dst = (l == 0) ? u : L.T;
-    B200_TRY(dist_spmv(h, c, L.A, U[l], dst, 1, w, 0.0, F[l], L.l1, "postsmooth", l));                   // l1-Jacobi post-sweep
-    if (l > 0) { std::swap(L.U, L.T); U[l] = L.U; }
+    B200_TRY(dist_spmv(h, c, L.P, U[l + 1], L.T, 0, 1.0, 1.0, L.U, nullptr, "prolong", l));              // T_l = U_l + P U_{l+1}
+    B200_TRY(dist_spmv(h, c, L.A, L.T, (l == 0) ? u : L.U, 1, w, 0.0, F[l], L.l1, "postsmooth", l));     // l1-Jacobi post-sweep
   }
   return 0;
 }
@@ -1606,39 +1622,72 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
     if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break;
     if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break;
     if (h_norms) { if ((rc = fetch())) break; h_norms[0] = std::sqrt(hs[1]); }
-    while ((i + 1) <= max_iter) {
-      i++;
-      if ((rc = dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr, "pcg s=Ap"))) break;   // s = A p (pcg.c:512)
+    // One iteration = [beta, p update] of the previous one + [halo, s = A p, <s,p>, reduction, alpha, x/r update, the cycle,
+    // <r,s>, <r,r>, reduction, copy of the scalars to the host].  When every exchange of iteration 1 stayed on the device-only
+    // path (direct halos and reductions; a single rank trivially), the sequence is a fixed list of kernels with fixed arguments:
+    // iteration 2 is captured into a CUDA graph, iterations 3.. replay it.
+    auto body = [&](bool with_beta) -> int {
+      if (with_beta) {
+        b200_prof_scope ps(h, "pcg update p");
+        dpcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
+        ++g_b200_launches;
+        dpcg_update_p_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, s, p);
+        ++g_b200_launches;
+      }
+      B200_TRY(dist_spmv(h, c, A, p, s, 0, 1.0, 0.0, nullptr, nullptr, "pcg s=Ap"));     // s = A p (pcg.c:512)
       { b200_prof_scope ps(h, "pcg dot");
-        if ((rc = b200_vec_dot_dev(h, n, s, p, lp))) break; }                      // <s,p> (pcg.c:515)
+        B200_TRY(b200_vec_dot_dev(h, n, s, p, lp)); }                                    // <s,p> (pcg.c:515)
       { b200_prof_scope ps(h, "pcg allreduce");
-        if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 2))) break; }
+        B200_TRY(b200_comm_allreduce_sum_dev2dev(h, c, lp, 1, sc + 2)); }
       { b200_prof_scope ps(h, "pcg update x,r");
         dpcg_alpha_kernel<<<1, 1, 0, h->stream>>>(sc);
         ++g_b200_launches;
         dpcg_update_xr_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, p, s, xx, r);
         ++g_b200_launches; }
       { b200_prof_scope ps(h, "pcg precond (whole cycle)");
-        if ((rc = precond(r, s))) break; }                                         // s = C r (pcg.c:568-569)
+        B200_TRY(precond(r, s)); }                                                       // s = C r (pcg.c:568-569)
       { b200_prof_scope ps(h, "pcg dot");
-        if ((rc = b200_vec_dot_dev(h, n, r, s, lp))) break;                        // gamma = <r,s> (pcg.c:572)
-        if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break; }                  // i_prod = <r,r> (pcg.c:590)
+        B200_TRY(b200_vec_dot_dev(h, n, r, s, lp));                                      // gamma = <r,s> (pcg.c:572)
+        B200_TRY(b200_vec_dot_dev(h, n, r, r, lp + 1)); }                                // i_prod = <r,r> (pcg.c:590)
       { b200_prof_scope ps(h, "pcg allreduce");
-        if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break; }
+        B200_TRY(b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc)); }
+      B200_CUDA(cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      return 0;
+    };
+    cudaGraphExec_t gexec = nullptr;
+    bool graph_ok = b200_graph_enabled() && (!amg || !amg->gs), graph_tried = false;
+    long long launches_per_graph = 0;
+    while ((i + 1) <= max_iter) {
+      i++;
+      if (i >= 2 && gexec) {
+        if ((rc = b200_graph_launch(h, gexec))) break;
+        g_b200_launches += launches_per_graph;
+      } else if (i == 2 && graph_ok && !graph_tried) {
+        graph_tried = true;
+        const long long l0 = g_b200_launches.load();
+        if ((rc = b200_graph_begin(h))) break;
+        rc = body(true);
+        cudaGraphExec_t ge = nullptr;
+        int rc2 = b200_graph_end(h, &ge);
+        if (rc || rc2) { if (!rc) rc = rc2; break; }
+        launches_per_graph = g_b200_launches.load() - l0;
+        if (ge) { gexec = ge; if ((rc = b200_graph_launch(h, gexec))) break; }
+        else { g_b200_launches -= launches_per_graph; if ((rc = body(true))) break; }      // capture refused: run it eagerly
+      } else {
+        const long long ops0 = b200_comm_host_ops(c);
+        if ((rc = body(i > 1))) break;
+        if (b200_comm_host_ops(c) != ops0) graph_ok = false;                 // an exchange left the device-only path
+      }
       { b200_prof_scope ps(h, "pcg fetch+sync");
-        if ((rc = fetch())) break; }
+        if (cudaStreamSynchronize(h->stream) != cudaSuccess) { rc = b200_set_error(__FILE__, __LINE__, "pcg sync failed"); break; } }
       const double gamma = hs[0], sdotp = hs[2];
       i_prod = hs[1];
       if (sdotp == 0.0) { rc = b200_set_error(__FILE__, __LINE__, "Zero sdotp value in PCG"); break; }   // pcg.c:516-521
       if (h_norms) h_norms[i] = std::sqrt(i_prod);
       if (i_prod / bi_prod < eps) break;
       if (!(gamma > 2.2250738585072014e-308)) { rc = b200_set_error(__FILE__, __LINE__, "Subnormal gamma value in PCG"); break; }
-      b200_prof_scope ps(h, "pcg update p");
-      dpcg_beta_kernel<<<1, 1, 0, h->stream>>>(sc);
-      ++g_b200_launches;
-      dpcg_update_p_kernel<<<vg, 256, 0, h->stream>>>((size_t)n, sc, s, p);
-      ++g_b200_launches;
     }
+    b200_graph_destroy(gexec);
   } while (0);
   b200_prof_report(h, "b200_dist_pcg_solve");
   if (!rc) {

@@ -103,6 +103,15 @@ struct b200_prof_scope {
   ~b200_prof_scope() { b200_prof_end(h); }
 };
 
+// CUDA-graph replay of a fixed kernel sequence on the handle's stream (the PCG iteration: ~100 launches, a third of them on
+// levels with a few thousand rows where a launch costs more than the kernel).  begin/end bracket the sequence once, in relaxed
+// capture mode; launch replays it.  Off with B200_GRAPH=0 and whenever the region profiler is on.
+bool b200_graph_enabled();
+int b200_graph_begin(b200_handle h);
+int b200_graph_end(b200_handle h, cudaGraphExec_t *exec);      // *exec = nullptr when the capture was invalidated (caller falls back)
+int b200_graph_launch(b200_handle h, cudaGraphExec_t exec);
+void b200_graph_destroy(cudaGraphExec_t exec);
+
 // device allocation: slab sub-allocator owned by the handle.  All work of a handle runs on one
 // stream, so a freed block may be handed out again immediately (stream order keeps it safe).
 int b200_pool_alloc(b200_handle h, void **p, size_t bytes);

@@ -180,6 +180,31 @@ void b200_prof_report(b200_handle h, const char *title) {
             1e3 * kv.second.first / kv.second.second);
 }
 
+// ---- CUDA-graph replay ---------------------------------------------------------------------------------------------------------
+bool b200_graph_enabled() {
+  static const bool on = [] { const char *e = getenv("B200_GRAPH"); return !(e && e[0] == '0'); }();
+  return on && !prof_on();
+}
+int b200_graph_begin(b200_handle h) {
+  B200_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeRelaxed));
+  return 0;
+}
+int b200_graph_end(b200_handle h, cudaGraphExec_t *exec) {
+  *exec = nullptr;
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamEndCapture(h->stream, &g);
+  if (e != cudaSuccess || !g) { cudaGetLastError(); if (g) cudaGraphDestroy(g); return 0; }
+  e = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) { cudaGetLastError(); *exec = nullptr; }
+  return 0;
+}
+int b200_graph_launch(b200_handle h, cudaGraphExec_t exec) {
+  B200_CUDA(cudaGraphLaunch(exec, h->stream));
+  return 0;
+}
+void b200_graph_destroy(cudaGraphExec_t exec) { if (exec) cudaGraphExecDestroy(exec); }
+
 thread_local std::string g_b200_err;
 std::atomic<long long> g_b200_launches{0};
 
