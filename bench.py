@@ -273,7 +273,9 @@ def main_dist(a, rank, world, local_rank):
     n, nnz = inf["local_rows"], inf["local_nnz"]
     b = A.vector(1.0)
     x = A.vector(0.0)
-    prm = hb.Amg(h, ModuleRAP2=0)          # driver default: fused BuildCoarseOperatorKT order, (R A) P
+    # driver default Galerkin order (fused BuildCoarseOperatorKT, (R A) P); levels with at most --seq-threshold rows in total
+    # are replicated on every rank (HYPRE_BoomerAMGSetSeqThreshold, `ij -seq_th`): same hierarchy bit for bit, no exchanges there
+    prm = hb.Amg(h, ModuleRAP2=0, SeqThreshold=a.seq_threshold)
 
     levels = []
 
@@ -361,7 +363,8 @@ def main_dist(a, rank, world, local_rank):
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": bench_config(world, n1, a.grid),
         "problem": {"rows_per_gpu": n, "nnz_per_gpu": nnz, "global_rows": int(gn), "global_nnz": int(gnnz),
-                    "parallelism": "row-partitioned ParCSR (-P %d %d %d), %d GPUs, halo + reductions over NVLink" % (P, Q, R, world)},
+                    "parallelism": "row-partitioned ParCSR (-P %d %d %d), %d GPUs, halo + reductions over NVLink; levels <= %d rows "
+                                   "replicated (seq_threshold)" % (P, Q, R, world, a.seq_threshold)},
         "setup_s": set_s, "solve_s": sol_s, "iterations": its, "final_rel_res": rel,
         "reference_iterations": ref_its, "iterations_match_reference": (its == ref_its) if ref_its is not None else None,
         "e2e_iterations": e2e_its,
@@ -395,6 +398,8 @@ def main():
     ap.add_argument("--edge", dest="n", type=int, default=N1, help="grid edge per GPU (default: config 2, 256)")
     ap.add_argument("--grid", choices=["slab", "box"], default="slab",
                     help="N > 1: z-slabs (-P 1 1 N, lexicographic numbering = the reference's np = 1 job) or boxes (-P 2 2 2 ...)")
+    ap.add_argument("--seq-threshold", type=int, default=200000,
+                    help="N > 1: levels with at most this many rows in total are replicated on every rank (ij -seq_th); 0 = off")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     claim_stdout()

@@ -129,6 +129,7 @@ SIGNATURES = {
     "b200_dist_amg_num_levels": (_i, [_vp]),
     "b200_dist_amg_level_A": (_vp, [_vp, _i]),
     "b200_dist_amg_level_P": (_vp, [_vp, _i]),
+    "b200_dist_amg_level_view": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(_vp)]),
     "b200_dist_amg_level_cf": (_i, [_vp, _vp, _i, _vp]),
     "b200_dist_amg_setup_ms": (_i, [_vp, _dp]),
     "b200_dist_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
@@ -809,11 +810,16 @@ class DistAmg:
     def num_levels(self):
         return _lib.b200_dist_amg_num_levels(self.p)
 
+    def _view(self, l, what):
+        p = _vp()
+        _chk(_lib.b200_dist_amg_level_view(self.h.p, self.c.p, self.p, l, what, C.byref(p)))
+        return DistMatrix(self.h, self.c, p, owned=False)
+
     def level_A(self, l):
-        return DistMatrix(self.h, self.c, _vp(_lib.b200_dist_amg_level_A(self.p, l)), owned=False)
+        return self._view(l, 0)
 
     def level_P(self, l):
-        return DistMatrix(self.h, self.c, _vp(_lib.b200_dist_amg_level_P(self.p, l)), owned=False)
+        return self._view(l, 1)
 
     def level_cf(self, l):
         n = self.level_A(l).info["local_rows"]

@@ -56,7 +56,7 @@ struct b200_amg_s {
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
           {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"ChebyOrder", 2}, {"ChebyEigEst", 10},
           {"ChebyVariant", 0}, {"ChebyScale", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747},
-          {"NumSweepsDown", -1}, {"NumSweepsUp", -1}, {"NumSweepsCoarse", 1}, {"FCycle", 0}};
+          {"NumSweepsDown", -1}, {"NumSweepsUp", -1}, {"NumSweepsCoarse", 1}, {"FCycle", 0}, {"SeqThreshold", 0}};
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
           {"OuterWt", 1.0}, {"Tol", 0.0}, {"ChebyFraction", 0.3}};
   }
@@ -208,6 +208,8 @@ extern "C" int b200_amg_set_real(b200_amg amg, const char *name, double value) {
 }
 
 int b200_amg_get_int(b200_amg a, const char *name) { return a->ip.count(name) ? a->ip[name] : 0; }
+// copy every parameter of src into dst (the replicated coarse-level hierarchy of the row-partitioned setup, b200_dist.cu)
+int b200_amg_clone_params(b200_amg src, b200_amg dst) { dst->ip = src->ip; dst->rp = src->rp; return 0; }
 double b200_amg_get_real(b200_amg a, const char *name) { return a->rp.count(name) ? a->rp[name] : 0.0; }
 
 extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {

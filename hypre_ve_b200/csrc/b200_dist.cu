@@ -38,6 +38,8 @@ int b200_amg_get_int(b200_amg a, const char *name);
 int b200_pmis_dist_init(b200_handle h, b200_comm c, b200_csr S, b200_halo_s *halo, int seed, long long first_row, int cf_init,
                         int *d_cf_ext);
 double b200_amg_get_real(b200_amg a, const char *name);
+int b200_amg_clone_params(b200_amg src, b200_amg dst);
+int b200_amg_precond(b200_handle h, b200_amg amg, const double *d_rhs, double *d_out);
 
 // legacy diag/offd ParCSR hooks (b200_parcsr.cu): the multi-rank path is the b200_dist_* API
 int b200_halo_exchange(b200_handle, b200_parcsr, const double *) { B200_FAIL("use the b200_dist_* API for multi-rank operators"); }
@@ -914,6 +916,16 @@ struct b200_dist_amg_s {
   bool gs = false;                   // l1 hybrid Gauss-Seidel (8/13/14): Gauss-Seidel inside the rank's blocks,
   int relax_down = 18, relax_up = 18, gs_blocks = 1;   // pre-sweep values across blocks and ranks (par_relax.c:4352-4372)
   double setup_ms = 0;
+  // Replicated tail (hypre's seq_threshold, par_amg_setup.c:2880-2898 / par_amg.c hypre_seqAMGSetup): once a level has
+  // no more than SeqThreshold rows in total, it is gathered onto EVERY rank and everything below it is ONE single-GPU
+  // hierarchy built and cycled redundantly -- the same kernels on the same data give the same bits on every rank, and
+  // the levels where a halo exchange costs more than the kernels need no exchange at all.
+  b200_amg tail = nullptr;           // its level 0 is this hierarchy's level lv.size() - 1
+  b200_parcsr tailA = nullptr;
+  b200_halo_s *tail_plan = nullptr;  // brings every other rank's piece of the level's right-hand side
+  double *tail_F = nullptr, *tail_U = nullptr, *tail_G = nullptr;
+  int tail_N = 0, tail_first = 0, tail_rank = 0;
+  std::vector<b200_dist_matrix> views;   // per-level views handed out by the level accessors (owned here)
 };
 
 // distributed transpose of P (global coarse cols) -> R rows = local coarse, cols = global fine ids,
@@ -1027,6 +1039,92 @@ static b200_dist_matrix new_dist(int n, int first_row, int global_rows, const st
   return M;
 }
 
+namespace {
+__global__ void fix_rowptr_kernel(int n, const int *__restrict__ src, int add, int *__restrict__ dst) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) dst[k] = src[k] + add;
+}
+__global__ void iota_skip_kernel(int ng, int first, int n, int *__restrict__ out) {      // every id except [first, first + n)
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < ng) out[k] = k < first ? k : k + n;
+}
+}  // namespace
+
+// every rank receives the whole matrix (rows in global order, global column ids, entry order kept)
+static int gather_csr(b200_handle h, b200_comm c, b200_dist_matrix M, b200_csr *out) {
+  const int R = b200_comm_size(c);
+  const int N = M->global_rows, n = M->n;
+  const std::vector<int> &rs = M->row_starts;
+  int my_nnz = M->G->nnz;
+  std::vector<int> nz(R), nzs(R + 1, 0);
+  B200_TRY(b200_comm_allgather_host(h, c, &my_nnz, sizeof(int), nz.data()));
+  for (int r = 0; r < R; r++) nzs[r + 1] = nzs[r] + nz[r];
+  b200_csr F = nullptr;
+  B200_TRY(b200_csr_alloc(h, N, M->global_cols, nzs[R], true, &F));
+  int *tmp = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &tmp, (size_t)N + R));
+  std::vector<b200_xfer> s1, r1, s2, r2, s3, r3;
+  for (int r = 0; r < R; r++) {
+    const int nr = rs[r + 1] - rs[r];
+    s1.push_back({r, M->G->i, sizeof(int) * ((size_t)n + 1), 0});
+    r1.push_back({r, tmp + rs[r] + r, sizeof(int) * ((size_t)nr + 1), 0});
+    if (my_nnz) { s2.push_back({r, M->G->j, sizeof(int) * (size_t)my_nnz, 0}); s3.push_back({r, M->G->a, sizeof(double) * (size_t)my_nnz, 0}); }
+    if (nz[r]) { r2.push_back({r, F->j + nzs[r], sizeof(int) * (size_t)nz[r], 0}); r3.push_back({r, F->a + nzs[r], sizeof(double) * (size_t)nz[r], 0}); }
+  }
+  B200_TRY(b200_comm_exchange(h, c, s1, r1));
+  B200_TRY(b200_comm_exchange(h, c, s2, r2));
+  B200_TRY(b200_comm_exchange(h, c, s3, r3));
+  for (int r = 0; r < R; r++) {
+    const int nr = rs[r + 1] - rs[r] + (r == R - 1 ? 1 : 0);      // the last block also carries the closing pointer
+    if (nr) {
+      fix_rowptr_kernel<<<b200_grid(nr, 256), 256, 0, h->stream>>>(nr, tmp + rs[r] + r, nzs[r], F->i + rs[r]);
+      B200_LAUNCH_CHECK();
+    }
+  }
+  B200_CUDA(cudaStreamSynchronize(h->stream));
+  B200_TRY(b200_dfree(h, tmp));
+  *out = F;
+  return 0;
+}
+
+// levels >= `level` become one single-GPU hierarchy on every rank (see b200_dist_amg_s::tail)
+static int build_tail(b200_handle h, b200_comm c, b200_amg prm, b200_dist_amg amg, int level, int levels_left) {
+  dist_level &L = amg->lv[level];
+  b200_dist_matrix A = L.A;
+  b200_csr full = nullptr;
+  B200_TRY(gather_csr(h, c, A, &full));
+  b200_parcsr TA = new b200_parcsr_s();
+  TA->global_rows = TA->global_cols = A->global_rows;
+  TA->diag = full;
+  B200_TRY(b200_csr_build_plan(h, full));
+  B200_TRY(b200_csr_alloc(h, A->global_rows, 0, 0, true, &TA->offd));
+  B200_CUDA(cudaMemsetAsync(TA->offd->i, 0, sizeof(int) * ((size_t)A->global_rows + 1), h->stream));
+  amg->tailA = TA;
+  B200_TRY(b200_amg_create(&amg->tail));
+  B200_TRY(b200_amg_clone_params(prm, amg->tail));
+  B200_TRY(b200_amg_set_int(amg->tail, "MaxLevels", levels_left));
+  B200_TRY(b200_amg_set_int(amg->tail, "AggNumLevels", 0));
+  B200_TRY(b200_amg_set_int(amg->tail, "SeqThreshold", 0));
+  B200_TRY(b200_amg_set_int(amg->tail, "CoarsenType", 8));
+  B200_TRY(b200_amg_set_int(amg->tail, "MaxIter", 1));
+  B200_TRY(b200_amg_set_real(amg->tail, "Tol", 0.0));
+  B200_TRY(b200_amg_setup(h, amg->tail, TA));
+  // gather plan for the right-hand side: every id this rank does not own is a "ghost"
+  const int N = A->global_rows, n = A->n, first = A->first_row, ng = N - n;
+  int *gid = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &gid, (size_t)ng + 1));
+  if (ng) {
+    iota_skip_kernel<<<b200_grid(ng, 256), 256, 0, h->stream>>>(ng, first, n, gid);
+    B200_LAUNCH_CHECK();
+  }
+  B200_TRY(b200_halo_build(h, c, A->row_starts, gid, ng, &amg->tail_plan));
+  B200_TRY(b200_dalloc<double>(h, &amg->tail_F, (size_t)N + 8)); B200_TRY(b200_dalloc<double>(h, &amg->tail_U, (size_t)N + 8));
+  B200_TRY(b200_dalloc<double>(h, &amg->tail_G, (size_t)ng + 8));
+  B200_CUDA(cudaMemsetAsync(amg->tail_U, 0, sizeof(double) * ((size_t)N + 8), h->stream));
+  amg->tail_N = N; amg->tail_first = first; amg->tail_rank = b200_comm_rank(c);
+  return 0;
+}
+
 extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b200_dist_matrix A0, b200_dist_amg *out) {
   if (!prm || !A0) B200_FAIL("dist_amg_setup: null argument");
   if (b200_amg_get_int(prm, "CoarsenType") != 8 && b200_amg_get_int(prm, "CoarsenType") != 9)
@@ -1050,6 +1148,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   const double trunc = b200_amg_get_real(prm, "TruncFactor");
   const int pmax = b200_amg_get_int(prm, "PMaxElmts"), max_levels = b200_amg_get_int(prm, "MaxLevels");
   const int max_coarse = b200_amg_get_int(prm, "MaxCoarseSize"), seed = b200_amg_get_int(prm, "Seed");
+  const int seq_th = b200_amg_get_int(prm, "SeqThreshold");
   const int mod_rap2 = b200_amg_get_int(prm, "ModuleRAP2"), agg_nl = b200_amg_get_int(prm, "AggNumLevels");
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1082,6 +1181,12 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     const int n = A->n, ng = A->halo->ng;
     const long long fine_size = A->global_rows;
     tlevel = level;
+    if (R > 1 && jac && seq_th > 0 && level >= 1 && level >= b200_amg_get_int(prm, "AggNumLevels") && A->global_rows <= seq_th &&
+        A->global_rows > max_coarse) {
+      B200_TRY(build_tail(h, c, prm, amg, level, max_levels - level));
+      mark("replicated tail");
+      break;
+    }
     // --- strength + PMIS on the localized operator (par_amg_setup.c:1035,:1114) -----------------
     b200_csr S = nullptr;
     B200_TRY(b200_strength(h, A->L, theta, mrs, &S));
@@ -1366,7 +1471,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
   {
     dist_level &Lc = amg->lv[nl - 1];
     const int ncg = Lc.A->global_rows;
-    amg->coarse_ge = ncg <= max_coarse && ncg > 0;
+    amg->coarse_ge = ncg <= max_coarse && ncg > 0 && !amg->tail;
     if (amg->coarse_ge) {
       amg->ge_n = ncg;
       amg->ge_starts = Lc.A->row_starts;
@@ -1411,16 +1516,102 @@ extern "C" int b200_dist_amg_destroy(b200_handle h, b200_dist_amg amg) {
     B200_TRY(b200_dfree(h, L.F)); B200_TRY(b200_dfree(h, L.U)); B200_TRY(b200_dfree(h, L.T));
   }
   B200_TRY(b200_dfree(h, amg->Vtemp)); B200_TRY(b200_dfree(h, amg->ge_A)); B200_TRY(b200_dfree(h, amg->ge_f));
+  for (b200_dist_matrix v : amg->views) B200_TRY(b200_dist_matrix_destroy(h, v));
+  if (amg->tail) {
+    B200_TRY(b200_amg_destroy(h, amg->tail));
+    B200_TRY(b200_parcsr_destroy(h, amg->tailA));
+    b200_halo_free(h, amg->tail_plan);
+    B200_TRY(b200_dfree(h, amg->tail_F)); B200_TRY(b200_dfree(h, amg->tail_U)); B200_TRY(b200_dfree(h, amg->tail_G));
+  }
   delete amg;
   return 0;
 }
-extern "C" int b200_dist_amg_num_levels(b200_dist_amg amg) { return amg ? (int)amg->lv.size() : 0; }
-extern "C" b200_dist_matrix b200_dist_amg_level_A(b200_dist_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].A : nullptr; }
-extern "C" b200_dist_matrix b200_dist_amg_level_P(b200_dist_amg amg, int l) { return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].P : nullptr; }
+b200_csr b200_amg_level_A(b200_amg amg, int l);
+b200_csr b200_amg_level_P(b200_amg amg, int l);
+const int *b200_amg_level_CF(b200_amg amg, int l);
+int b200_amg_num_levels(b200_amg amg);
+
+// Levels of the replicated tail seen through the row-partitioned accessors: the tail's first level is partitioned like the
+// distributed level it was gathered from; deeper levels are reported whole by rank 0 and empty by the other ranks (any
+// contiguous partition describes a replicated matrix).
+static int tail_rows(b200_dist_amg amg, int tl, int me, int *r0, int *r1) {
+  const int n = b200_amg_level_A(amg->tail, tl)->nrows;
+  if (tl == 0) { *r0 = amg->tail_first; *r1 = amg->tail_first + amg->lv.back().n; }
+  else { *r0 = 0; *r1 = (me == 0) ? n : 0; }
+  return n;
+}
+static int tail_view(b200_handle h, b200_dist_amg amg, b200_csr src, int r0, int r1, b200_dist_matrix *out) {
+  const int n = r1 - r0;
+  int e0 = 0, e1 = 0;
+  if (n > 0) {
+    B200_CUDA(cudaMemcpyAsync(&e0, src->i + r0, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaMemcpyAsync(&e1, src->i + r1, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  b200_csr G = nullptr;
+  B200_TRY(b200_csr_alloc(h, n, src->ncols, e1 - e0, true, &G));
+  if (n > 0) {
+    fix_rowptr_kernel<<<b200_grid(n + 1, 256), 256, 0, h->stream>>>(n + 1, src->i + r0, -e0, G->i);
+    B200_LAUNCH_CHECK();
+    if (e1 > e0) {
+      B200_CUDA(cudaMemcpyAsync(G->j, src->j + e0, sizeof(int) * (size_t)(e1 - e0), cudaMemcpyDeviceToDevice, h->stream));
+      B200_CUDA(cudaMemcpyAsync(G->a, src->a + e0, sizeof(double) * (size_t)(e1 - e0), cudaMemcpyDeviceToDevice, h->stream));
+    }
+  } else {
+    B200_CUDA(cudaMemsetAsync(G->i, 0, sizeof(int), h->stream));
+  }
+  b200_dist_matrix M = new b200_dist_matrix_s();
+  M->n = n; M->first_row = r0; M->global_rows = src->nrows; M->global_cols = src->ncols; M->G = G;
+  amg->views.push_back(M);
+  *out = M;
+  return 0;
+}
+extern "C" int b200_dist_amg_num_levels(b200_dist_amg amg) {
+  if (!amg) return 0;
+  return (int)amg->lv.size() + (amg->tail ? b200_amg_num_levels(amg->tail) - 1 : 0);
+}
+extern "C" b200_dist_matrix b200_dist_amg_level_A(b200_dist_amg amg, int l) {
+  if (!amg || l < 0) return nullptr;
+  if (l < (int)amg->lv.size()) return amg->lv[l].A;
+  return nullptr;                     // tail levels: b200_dist_amg_level_view
+}
+extern "C" b200_dist_matrix b200_dist_amg_level_P(b200_dist_amg amg, int l) {
+  return (amg && l >= 0 && l < (int)amg->lv.size()) ? amg->lv[l].P : nullptr;     // tail levels: b200_dist_amg_level_view
+}
+// what = 0: A_l, 1: P_l, for any level including the replicated tail (views are owned by the hierarchy)
+extern "C" int b200_dist_amg_level_view(b200_handle h, b200_comm c, b200_dist_amg amg, int l, int what, b200_dist_matrix *out) {
+  if (!amg || !out) B200_FAIL("level_view: null argument");
+  *out = nullptr;
+  const int nd = (int)amg->lv.size();
+  if (l >= 0 && l < nd && what == 0) { *out = amg->lv[l].A; return 0; }
+  if (l >= 0 && l < nd && what == 1 && amg->lv[l].P) { *out = amg->lv[l].P; return 0; }
+  if (!amg->tail) B200_FAIL("level_view: no such level");
+  const int tl = l - (nd - 1);
+  if (tl < 0 || tl >= b200_amg_num_levels(amg->tail)) B200_FAIL("level_view: no such level");
+  b200_csr src = what == 0 ? b200_amg_level_A(amg->tail, tl) : b200_amg_level_P(amg->tail, tl);
+  if (!src) B200_FAIL("level_view: the coarsest level has no interpolation");
+  int r0 = 0, r1 = 0;
+  tail_rows(amg, tl, b200_comm_rank(c), &r0, &r1);
+  return tail_view(h, amg, src, r0, r1, out);
+}
 extern "C" int b200_dist_amg_level_cf(b200_handle h, b200_dist_amg amg, int l, int *h_cf) {
-  if (!amg || l < 0 || l >= (int)amg->lv.size() || !amg->lv[l].cf) B200_FAIL("no CF marker on this level");
-  B200_CUDA(cudaMemcpyAsync(h_cf, amg->lv[l].cf, sizeof(int) * (size_t)amg->lv[l].n, cudaMemcpyDeviceToHost, h->stream));
-  B200_CUDA(cudaStreamSynchronize(h->stream));
+  if (!amg || l < 0) B200_FAIL("no CF marker on this level");
+  const int nd = (int)amg->lv.size();
+  if (l < nd && amg->lv[l].cf) {
+    B200_CUDA(cudaMemcpyAsync(h_cf, amg->lv[l].cf, sizeof(int) * (size_t)amg->lv[l].n, cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    return 0;
+  }
+  if (!amg->tail) B200_FAIL("no CF marker on this level");
+  const int tl = l - (nd - 1);
+  const int *cf = b200_amg_level_CF(amg->tail, tl);
+  if (tl < 0 || !cf) B200_FAIL("no CF marker on this level");
+  int r0 = 0, r1 = 0;
+  tail_rows(amg, tl, amg->tail_rank, &r0, &r1);
+  if (r1 > r0) {
+    B200_CUDA(cudaMemcpyAsync(h_cf, cf + r0, sizeof(int) * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
   return 0;
 }
 extern "C" int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms) { if (!amg) B200_FAIL("null"); *ms = amg->setup_ms; return 0; }
@@ -1436,6 +1627,17 @@ static int dist_cycle(b200_handle h, b200_comm c, b200_dist_amg amg, const doubl
   const double w = amg->relax_wt;
   const int me = b200_comm_rank(c), R = b200_comm_size(c);
   auto coarse_solve = [&](dist_level &L, const double *F, double *U) -> int {
+    if (amg->tail) {
+      // gather the level's right-hand side on every rank, cycle the replicated hierarchy, keep this rank's rows
+      const int N = amg->tail_N, first = amg->tail_first, n = L.n;
+      if (amg->tail_plan->any_traffic) B200_TRY(b200_halo_forward_f64(h, c, amg->tail_plan, F, amg->tail_G));
+      if (first) B200_CUDA(cudaMemcpyAsync(amg->tail_F, amg->tail_G, sizeof(double) * (size_t)first, cudaMemcpyDeviceToDevice, h->stream));
+      if (n) B200_CUDA(cudaMemcpyAsync(amg->tail_F + first, F, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      if (N - first - n) B200_CUDA(cudaMemcpyAsync(amg->tail_F + first + n, amg->tail_G + first, sizeof(double) * (size_t)(N - first - n), cudaMemcpyDeviceToDevice, h->stream));
+      B200_TRY(b200_amg_precond(h, amg->tail, amg->tail_F, amg->tail_U));
+      if (n) B200_CUDA(cudaMemcpyAsync(U, amg->tail_U + first, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+      return 0;
+    }
     if (amg->coarse_ge && amg->ge_n <= 16 && b200_comm_p2p_ok(c)) {
       // Allgatherv of f (par_gauss_elim.c:264) as a rank-ordered device-to-device sum of vectors that are zero outside the
       // rank's own rows (x + 0 is exact): one kernel, no message library, capturable in the iteration's CUDA graph

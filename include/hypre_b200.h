@@ -316,6 +316,12 @@ int b200_dist_amg_num_levels(b200_dist_amg amg);
 b200_dist_matrix b200_dist_amg_level_A(b200_dist_amg amg, int level);
 b200_dist_matrix b200_dist_amg_level_P(b200_dist_amg amg, int level);
 int b200_dist_amg_level_cf(b200_handle h, b200_dist_amg amg, int level, int *h_cf);
+/* A_l (what 0) or P_l (what 1) of ANY level as this rank's block of rows with global column ids.  With SeqThreshold > 0
+ * (HYPRE_BoomerAMGSetSeqThreshold, par_amg.c; par_amg_setup.c:2880-2898) the levels whose global size is at most the
+ * threshold are gathered onto every rank and built / cycled redundantly as one single-GPU hierarchy; those levels are
+ * reported through views: the first replicated level in the partition of the distributed level it came from, deeper ones
+ * whole on rank 0 and empty elsewhere.  Views belong to the hierarchy. */
+int b200_dist_amg_level_view(b200_handle h, b200_comm c, b200_dist_amg amg, int level, int what, b200_dist_matrix *M);
 int b200_dist_amg_setup_ms(b200_dist_amg amg, double *ms);
 /* hypre_PCGSolve across ranks (dot products = deterministic rank-ordered sums) */
 int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix A, b200_dist_amg amg, const double *d_b,

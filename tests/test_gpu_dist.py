@@ -154,6 +154,21 @@ def test_nrank_fused_galerkin_order_equals_single_gpu(handle, nranks, grid, dims
     check_against_single_gpu(handle, nranks, grid, dims, stencil, ModuleRAP2=0)
 
 
+@pytest.mark.parametrize("nranks,grid,dims,stencil,seq,params", [
+    (2, (1, 1, 2), (12, 11, 10), 7, 500, {}),                 # level 1 (a few hundred rows) and below replicated
+    (4, (2, 2, 1), (13, 12, 9), 7, 100000, {}),               # everything below the finest level replicated
+    (8, (2, 2, 2), (14, 13, 12), 7, 120, dict(ModuleRAP2=0)),  # only the last levels
+    (3, (3, 1, 1), (10, 9, 8), 27, 200, dict(ModuleRAP2=0)),
+    (4, (1, 2, 2), (16, 14, 12), 7, 600, dict(AggNumLevels=1)),
+])
+def test_nrank_replicated_coarse_levels_equal_single_gpu(handle, nranks, grid, dims, stencil, seq, params):
+    """SeqThreshold (HYPRE_BoomerAMGSetSeqThreshold): levels with at most that many rows in total are gathered onto every
+    rank and built / cycled redundantly as one single-GPU hierarchy (no halo exchange below that level).  Every level --
+    distributed or replicated -- stays bit-identical to the single-GPU hierarchy of the gathered operator; iteration count
+    equal, residual history to 1e-10."""
+    check_against_single_gpu(handle, nranks, grid, dims, stencil, SeqThreshold=seq, **params)
+
+
 @pytest.mark.parametrize("nranks,grid,dims,stencil,agg", [
     (2, (1, 1, 2), (12, 11, 10), 7, 1), (3, (1, 3, 1), (14, 15, 9), 7, 1), (4, (2, 2, 1), (16, 14, 12), 7, 2),
     (8, (2, 2, 2), (16, 16, 16), 7, 1), (2, (2, 1, 1), (10, 9, 8), 27, 1),
@@ -518,6 +533,7 @@ def test_direct_peer_to_peer_halos_and_reductions_between_rank_threads():
     import sys
     env = dict(os.environ, B200_P2P_THREADS="1", B200_P2P_TIMEOUT_S="20", CUDA_MODULE_LOADING="EAGER", CUDA_DEVICE_MAX_CONNECTIONS="32")
     sel = ("test_zslab_partition_equals_reference_cpu_build or test_dist_matvec_matches_gathered or "
+           "test_nrank_replicated_coarse_levels_equal_single_gpu or "
            "test_nrank_hierarchy_equals_single_gpu or test_nrank_gmres_and_bicgstab_equal_single_gpu or "
            "test_nrank_hybrid_gs_pcg_history_equals_the_restatement or test_dist_amg_pcg_with_hybrid_gauss_seidel")
     p = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-p", "no:cacheprovider", "-k", sel],
