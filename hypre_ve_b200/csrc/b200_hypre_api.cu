@@ -77,7 +77,7 @@ struct hypre_IJMatrix_struct {
 struct hypre_IJVector_struct {
   int jlower = 0, jupper = -1;
   int object_type = -1;
-  bool initialized = false, dirty = false;
+  bool initialized = false, dirty = false, assembled_once = false;
   std::vector<double> host;
   hypre_ParVector_struct *object = nullptr;
 };
@@ -118,6 +118,9 @@ const Neutral kNeutral[] = {
     {"NumIsolatedFPoints", 0, "isolated F-points"},    {"NumInterpVectors", 0, "interpolation vectors (GSMG/RBM)"},
     {"GSMG", 0, "GSMG"},                               {"CoarsenCutFactor", 0, "coarsening cut factor"},
     {"Redundant", 0, "redundant coarse solves"},       {"SeqThreshold", 0, "sequential coarse AMG"},
+    {"ConvergeType", 0, "convergence on the relative residual change"},   {"Restriction", 0, "AIR restriction"},
+    {"ADropTol", 0, "dropping in the coarse operators"},                  {"InterpVecVariant", 0, "interpolation vectors (GSMG/RBM)"},
+    {"LevelNonGalerkinTolSet", 0, "non-Galerkin coarse operators"},       {"GridRelaxPointsSet", 0, "user relaxation point lists"},
 };
 
 int ndigits(long long number) {            // utilities/hypre_printf.c:115
@@ -238,6 +241,15 @@ HYPRE_Int HYPRE_IJMatrixSetObjectType(HYPRE_IJMatrix m, HYPRE_Int type) {
   m->object_type = type;
   return g_error_flag;
 }
+HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix m);
+HYPRE_Int HYPRE_IJMatrixInitialize_v2(HYPRE_IJMatrix m, HYPRE_Int /* HYPRE_MemoryLocation */) { return HYPRE_IJMatrixInitialize(m); }
+HYPRE_Int HYPRE_IJMatrixGetLocalRange(HYPRE_IJMatrix m, HYPRE_BigInt *ilower, HYPRE_BigInt *iupper, HYPRE_BigInt *jlower,
+                                      HYPRE_BigInt *jupper) {             // IJ_mv/HYPRE_IJMatrix.c:1042
+  if (!m) return err_arg(1);
+  if (!ilower || !iupper || !jlower || !jupper) return err_arg(2);
+  *ilower = m->ilower; *iupper = m->iupper; *jlower = m->jlower; *jupper = m->jupper;
+  return g_error_flag;
+}
 HYPRE_Int HYPRE_IJMatrixInitialize(HYPRE_IJMatrix m) {
   if (!m) return err_arg(1);
   if (m->object_type != HYPRE_PARCSR) return err_arg(1);             // HYPRE_IJMatrix.c:303-311
@@ -348,12 +360,32 @@ HYPRE_Int HYPRE_IJVectorInitialize(HYPRE_IJVector v) {
   v->dirty = false;
   return g_error_flag;
 }
+// The device copy is the truth once a solver has written it: before the first Set / AddTo after an Assemble the host mirror
+// is refreshed from the device, so a partial update does not revert the untouched entries to their pre-solve values.
+static HYPRE_Int ijvec_refresh_mirror(HYPRE_IJVector v) {
+  if (v->dirty || !v->assembled_once || v->host.empty() || !v->object) return 0;
+  NEED_HANDLE();
+  CALL(b200_memcpy_d2h(h, v->host.data(), v->object->d, sizeof(double) * v->host.size()), "HYPRE_IJVectorSetValues");
+  return 0;
+}
+HYPRE_Int HYPRE_IJVectorInitialize_v2(HYPRE_IJVector v, HYPRE_Int /* HYPRE_MemoryLocation: the object lives in HBM */) {
+  return HYPRE_IJVectorInitialize(v);
+}
+HYPRE_Int hypre_IJVectorZeroValues(HYPRE_IJVector v) {                 // IJ_mv/IJVector_parcsr.c: SetConstantValues(0)
+  if (!v || !v->initialized || !v->object) return err_arg(1);
+  NEED_HANDLE();
+  std::fill(v->host.begin(), v->host.end(), 0.0);
+  CALL(b200_vec_fill(h, v->object->n, 0.0, v->object->d), "hypre_IJVectorZeroValues");
+  v->dirty = false;
+  return g_error_flag;
+}
 HYPRE_Int HYPRE_IJVectorSetValues(HYPRE_IJVector v, HYPRE_Int nvalues, const HYPRE_BigInt *indices, const HYPRE_Complex *values) {
   if (!v) return err_arg(1);
   if (nvalues == 0) return g_error_flag;
   if (nvalues < 0) return err_arg(2);
   if (!values) return err_arg(4);
   if (!v->initialized) return err_arg(1);
+  if (ijvec_refresh_mirror(v)) return g_error_flag;
   for (int k = 0; k < nvalues; k++) {
     const int g = indices ? indices[k] : v->jlower + k;               // NULL indices = contiguous from jlower (IJVector_parcsr.c:374-390)
     if (g < v->jlower || g > v->jupper) continue;                     // off-rank entries are dropped on one rank
@@ -383,6 +415,7 @@ HYPRE_Int HYPRE_IJVectorAssemble(HYPRE_IJVector v) {
   if (v->dirty && !v->host.empty())
     CALL(b200_memcpy_h2d(h, v->object->d, v->host.data(), sizeof(double) * v->host.size()), "HYPRE_IJVectorAssemble");
   v->dirty = false;
+  v->assembled_once = true;
   return g_error_flag;
 }
 HYPRE_Int HYPRE_IJVectorGetValues(HYPRE_IJVector v, HYPRE_Int nvalues, const HYPRE_BigInt *indices, HYPRE_Complex *values) {
@@ -577,6 +610,10 @@ HYPRE_Int HYPRE_ParCSRMatrixGetDims(HYPRE_ParCSRMatrix A, HYPRE_BigInt *M, HYPRE
   *M = A->global_rows; *N = A->global_cols;
   return g_error_flag;
 }
+// hypre_ParCSRMatrixMigrate / hypre_ParVectorMigrate (parcsr_mv/par_csr_matrix.c, par_vector.c): the reference driver moves
+// the system "to the wanted memory space" before the solve (test/ij.c:3193-3195); objects of this library are born in HBM
+HYPRE_Int hypre_ParCSRMatrixMigrate(HYPRE_ParCSRMatrix A, HYPRE_Int) { return A ? g_error_flag : err_arg(1); }
+HYPRE_Int hypre_ParVectorMigrate(HYPRE_ParVector v, HYPRE_Int) { return v ? g_error_flag : err_arg(1); }
 HYPRE_Int HYPRE_ParCSRMatrixGetLocalRange(HYPRE_ParCSRMatrix A, HYPRE_BigInt *row_start, HYPRE_BigInt *row_end,
                                           HYPRE_BigInt *col_start, HYPRE_BigInt *col_end) {
   if (!A) return err_arg(1);
@@ -795,7 +832,41 @@ AMG_SETTER(SchwarzRlxWeight, HYPRE_Real, true)
 AMG_SETTER(EuLevel, HYPRE_Int, true)
 AMG_SETTER(EuBJ, HYPRE_Int, true)
 AMG_SETTER(EuSparseA, HYPRE_Real, true)
+// setters the unmodified reference driver (test/ij.c) calls for features outside this path: stored; the ones in kNeutral are
+// rejected at Setup unless left at the neutral value, the others are inert without their switch (par_amg.c stores them too)
+AMG_SETTER(ConvergeType, HYPRE_Int, true)
+AMG_SETTER(Restriction, HYPRE_Int, true)
+AMG_SETTER(StrongThresholdR, HYPRE_Real, v >= 0 && v <= 1.0)
+AMG_SETTER(ADropTol, HYPRE_Real, v >= 0)
+AMG_SETTER(ADropType, HYPRE_Int, true)
+AMG_SETTER(ILUType, HYPRE_Int, true)
+AMG_SETTER(ILULevel, HYPRE_Int, true)
+AMG_SETTER(ILUMaxRowNnz, HYPRE_Int, true)
+AMG_SETTER(ILUMaxIter, HYPRE_Int, true)
+AMG_SETTER(ILUDroptol, HYPRE_Real, true)
+AMG_SETTER(InterpVecVariant, HYPRE_Int, true)
+AMG_SETTER(InterpVecQMax, HYPRE_Int, true)
+AMG_SETTER(InterpVecAbsQTrunc, HYPRE_Real, true)
+AMG_SETTER(CoordDim, HYPRE_Int, true)
+AMG_SETTER(PlotGrids, HYPRE_Int, true)
 #undef AMG_SETTER
+HYPRE_Int HYPRE_BoomerAMGSetCoordinates(HYPRE_Solver s, float *) { return is_amg(s) ? g_error_flag : err_arg(1); }
+HYPRE_Int HYPRE_BoomerAMGSetPlotFileName(HYPRE_Solver s, const char *) { return is_amg(s) ? g_error_flag : err_arg(1); }
+HYPRE_Int HYPRE_BoomerAMGSetLevelNonGalerkinTol(HYPRE_Solver s, HYPRE_Real tol, HYPRE_Int) {
+  if (!is_amg(s)) return err_arg(1);
+  if (tol != 0.0) s->stored["LevelNonGalerkinTolSet"] = 1;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetGridRelaxPoints(HYPRE_Solver s, HYPRE_Int **points) {
+  if (!is_amg(s)) return err_arg(1);
+  if (points) s->stored["GridRelaxPointsSet"] = 1;
+  return g_error_flag;
+}
+HYPRE_Int HYPRE_BoomerAMGSetInterpVectors(HYPRE_Solver s, HYPRE_Int num, HYPRE_ParVector *) {
+  if (!is_amg(s)) return err_arg(1);
+  s->stored["NumInterpVectors"] = num;
+  return g_error_flag;
+}
 
 // number of Gauss-Seidel blocks per rank for the hybrid smoothers 3/4/6/8/13/14: what the OpenMP thread
 // count is to the reference (par_relax.c:4400-4412, hypre_NumThreads()); default 1

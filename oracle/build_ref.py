@@ -188,7 +188,30 @@ def main():
         if rc:
             print(out[-4000:])
             return 1
-    print("built", lib, "ij", "ref_dump" if os.path.exists(dump) else "")
+    # ---- drop-in boundary evidence (tests/test_gpu_refsrc.py) ----------------------------------------------------------------
+    # The reference's own programs, UNMODIFIED, compiled against the reference's own headers and linked against
+    # libhypre_b200.so FIRST, the reference library after it for everything outside the hot path (first
+    # definition in link order wins):   ij_on_b200  = src/test/ij.c,   ex5_on_b200 = src/examples/ex5.c.
+    # ex5 expects a real <mpi.h>; include/hypre_compat/mpi.h is a one-rank stand-in, force-included (no source change).
+    # ex5_on_b200 is compiled against the SHIM headers include/hypre_compat/HYPRE*.h instead of the reference's.
+    root = os.path.dirname(HERE)
+    b200_lib_dir = os.path.join(root, "hypre_ve_b200")
+    compat = os.path.join(root, "include", "hypre_compat")
+    if os.path.exists(os.path.join(b200_lib_dir, "libhypre_b200.so")):
+        both = ["-L" + b200_lib_dir, "-lhypre_b200", "-L" + OUT, "-lHYPRE_ref", "-Wl,-rpath,$ORIGIN/../../hypre_ve_b200",
+                "-Wl,-rpath,$ORIGIN", "-fopenmp", "-lm"]
+        ex5 = os.path.join(ref_src, "examples", "ex5.c")
+        stub = ["-include", os.path.join(compat, "mpi.h")]
+        for cmd in (
+            ["gcc"] + cflags + ["-DHYPRE_TIMING", os.path.join(ref_src, "test", "ij.c"), "-o", os.path.join(OUT, "ij_on_b200")] + both,
+            ["gcc"] + cflags + stub + [ex5, "-o", os.path.join(OUT, "ex5")] + link,
+            ["gcc", "-O2", "-w"] + stub + ["-I" + compat, ex5, "-o", os.path.join(OUT, "ex5_on_b200")] + both,
+        ):
+            rc, out, _ = run(cmd)
+            if rc:
+                print(out[-4000:])
+                return 1
+    print("built", lib, "ij", "ref_dump" if os.path.exists(dump) else "", "ij_on_b200 ex5 ex5_on_b200")
     return 0
 
 

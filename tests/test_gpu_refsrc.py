@@ -1,0 +1,73 @@
+"""The drop-in boundary, exercised with the reference's OWN programs, unmodified: `src/test/ij.c` and `src/examples/ex5.c`
+are compiled by oracle/build_ref.py (ij.c against the reference's own headers, ex5.c against the shim headers in
+include/hypre_compat/) and linked against libhypre_b200.so FIRST and the reference library second, so that every symbol of
+the hot path (HYPRE_IJ*, GenerateLaplacian, HYPRE_BoomerAMG*, HYPRE_ParCSRPCG*, HYPRE_PCG*, ...) binds to this library and
+the reference only serves what is out of scope (timing, hypre_printf, other solvers).  The result lines are compared with the
+same program linked against the reference library alone (oracle/_ref/ij, oracle/_ref/ex5)."""
+import os
+import re
+import subprocess
+
+import pytest
+
+import refio
+
+pytestmark = pytest.mark.gpu
+REF = os.path.join(refio.ROOT, "oracle", "_ref")
+
+
+def run(exe, flags, threads=1):
+    p = subprocess.run([os.path.join(REF, exe)] + [str(f) for f in flags], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       env=dict(os.environ, OMP_NUM_THREADS=str(threads)), timeout=280)
+    assert p.returncode == 0, p.stdout[-3000:]
+    return p.stdout
+
+
+def result(out):
+    its = int(re.findall(r"^(?:\w+ )?Iterations = (\d+)", out, re.M)[-1])          # "Iterations", "GMRES Iterations", "BoomerAMG Iterations"
+    rel = float(re.findall(r"Final (?:\w+ )?Relative Residual Norm = (\S+)", out)[-1])
+    return its, rel
+
+
+def test_the_binaries_bind_the_hot_path_to_this_library():
+    """dynamic symbol resolution of ij_on_b200: the hot-path entry points come from libhypre_b200.so"""
+    out = subprocess.run(["ldd", os.path.join(REF, "ij_on_b200")], stdout=subprocess.PIPE, text=True).stdout
+    assert "libhypre_b200.so" in out and "libHYPRE_ref.so" in out
+    assert out.index("libhypre_b200.so") < out.index("libHYPRE_ref.so")        # link order = lookup order
+    env = dict(os.environ, LD_DEBUG="bindings", OMP_NUM_THREADS="1")
+    p = subprocess.run([os.path.join(REF, "ij_on_b200"), "-n", "6", "6", "6", "-solver", "1", "-pmis", "-rlx", "18"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=280)
+    for sym in ("GenerateLaplacian", "HYPRE_BoomerAMGSetup", "HYPRE_BoomerAMGSolve", "HYPRE_PCGSolve", "HYPRE_IJVectorSetValues",
+                "HYPRE_ParCSRPCGCreate", "hypre_ParCSRMatrixMigrate"):
+        lines = [l for l in p.stderr.splitlines() if "symbol `%s'" % sym in l and "ij_on_b200" in l.split("to")[0]]
+        assert lines and all("libhypre_b200.so" in l for l in lines), (sym, lines[:2])
+
+
+@pytest.mark.parametrize("flags", [
+    ["-n", 30, 30, 30, "-solver", 1, "-pmis", "-rlx", 18],                  # config 2's flags at test size
+    ["-n", 24, 20, 16, "-solver", 1, "-pmis", "-rlx", 18, "-keepT", 1, "-mod_rap2", 1],
+    ["-laplacian", "-n", 50, 50, 50, "-solver", 1],                          # BASELINE.json configs[0], every default (HMIS, 13/14)
+    ["-n", 20, 20, 20, "-27pt", "-solver", 1, "-pmis", "-rlx", 18],
+    ["-n", 26, 26, 26, "-solver", 0, "-pmis", "-rlx", 18],                   # BoomerAMG alone
+    ["-n", 22, 21, 20, "-solver", 2],                                        # diagonally scaled PCG
+    ["-n", 18, 18, 18, "-difconv", "-a", 3, -2, 1, "-atype", 3, "-solver", 3, "-pmis", "-rlx", 18],   # AMG-GMRES, nonsymmetric
+])
+def test_unmodified_reference_driver_on_this_library(flags):
+    """src/test/ij.c, unmodified, linked against libhypre_b200.so: same iteration count and final residual as the same
+    program on the reference library (relative residuals agree to 1e-6 of their value: printed with 7 digits)"""
+    mine, ref = result(run("ij_on_b200", flags)), result(run("ij", flags))
+    assert mine[0] == ref[0], (mine, ref)
+    assert abs(mine[1] - ref[1]) <= 2e-6 * ref[1] + 1e-15, (mine, ref)
+
+
+def test_unmodified_reference_example_ex5_on_this_library():
+    """src/examples/ex5.c, unmodified, compiled against the shim headers include/hypre_compat/HYPRE*.h: the IJ assembly of the
+    2-D Laplacian + PCG (-solver 50) reproduce the reference build's iteration count and residual.  ex5's AMG choices
+    (-solver 0 / 1: Falgout coarsening + classical interpolation via SetOldDefault, CF relaxation) are outside this library's
+    scope and are refused loudly at setup."""
+    mine, ref = result(run("ex5_on_b200", ["-solver", 50, "-n", 40])), result(run("ex5", ["-solver", 50, "-n", 40]))
+    assert mine[0] == ref[0], (mine, ref)
+    assert abs(mine[1] - ref[1]) <= 2e-6 * ref[1] + 1e-15, (mine, ref)
+    p = subprocess.run([os.path.join(REF, "ex5_on_b200"), "-solver", "1", "-n", "20"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=120)
+    assert "implemented on the B200 path" in p.stdout, p.stdout[-1500:]
