@@ -56,7 +56,8 @@ struct b200_amg_s {
           {"RAP2", 0}, {"KeepTranspose", 1}, {"RelaxOrder", 0}, {"MaxIter", 1}, {"CycleType", 1},
           {"NumFunctions", 1}, {"MinIter", 0}, {"RelaxTypeUp", -1}, {"GSBlocks", 1}, {"ChebyOrder", 2}, {"ChebyEigEst", 10},
           {"ChebyVariant", 0}, {"ChebyScale", 1}, {"KeepS", 0}, {"PrintLevel", 0}, {"Seed", 2747},
-          {"NumSweepsDown", -1}, {"NumSweepsUp", -1}, {"NumSweepsCoarse", 1}, {"FCycle", 0}, {"SeqThreshold", 0}};
+          {"NumSweepsDown", -1}, {"NumSweepsUp", -1}, {"NumSweepsCoarse", 1}, {"FCycle", 0}, {"SeqThreshold", 0},
+          {"UserRelaxType", 0}};   // -1: the caller never chose a smoother (hypre_ParAMGDataUserRelaxType, par_amg.c:233)
     rp = {{"StrongThreshold", 0.25}, {"MaxRowSum", 1.0}, {"TruncFactor", 0.0}, {"RelaxWt", 1.0},
           {"OuterWt", 1.0}, {"Tol", 0.0}, {"ChebyFraction", 0.3}};
   }
@@ -219,15 +220,13 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   auto &rp = amg->rp;
   if (ip["CoarsenType"] != 8 && ip["CoarsenType"] != 10)
     B200_FAIL("only CoarsenType 8 (PMIS) and 10 (HMIS) are implemented on the B200 path");
-  if (ip["CoarsenType"] == 10 && ip["AggNumLevels"] > 0)
-    B200_FAIL("CoarsenType 10 (HMIS) with aggressive levels is not built on the B200 path: use CoarsenType 8 (PMIS)");
   if (ip["InterpType"] != 6) B200_FAIL("only InterpType 6 (extended+i) is implemented on the B200 path");
   // grid_relax_type[1] / [2] (par_amg.c:1650-1672); the coarsest grid is always Gaussian elimination (9)
-  const int rdown = ip["RelaxType"], rup = ip["RelaxTypeUp"] >= 0 ? ip["RelaxTypeUp"] : ip["RelaxType"];
+  int rdown = ip["RelaxType"], rup = ip["RelaxTypeUp"] >= 0 ? ip["RelaxTypeUp"] : ip["RelaxType"];
   auto is_gs = [](int t) { return t == 3 || t == 4 || t == 6 || t == 8 || t == 13 || t == 14; };
   auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
   auto is_jac = [](int t) { return t == 18 || t == 7; };
-  const bool cheby = rdown == 16 && rup == 16;
+  bool cheby = rdown == 16 && rup == 16;
   if (!((is_jac(rdown) && rup == rdown) || cheby || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
     B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), 7 (weighted Jacobi), 16 (Chebyshev), the l1 hybrid "
               "Gauss-Seidel family 8/13/14 and the hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
@@ -265,7 +264,7 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   L0.n = Apar->diag->nrows;
   amg->lv.push_back(L0);
   int level = 0;
-  bool not_finished = max_levels > 1;
+  bool not_finished = max_levels > 1, stalled = false;
   int *d_count = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_count, 1));
   while (not_finished) {                                   // par_amg_setup.c:889
@@ -281,7 +280,17 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     if (ip["CoarsenType"] == 10) B200_TRY(b200_hmis(h, S, seed, cf));   // :1107 (sequential first pass, see b200_hmis.cu)
     else B200_TRY(b200_pmis_rows(h, S, seed, 0, cf, nullptr));          // :1114
     const bool aggressive = level < ip["AggNumLevels"];
-    if (aggressive) B200_TRY(b200_agg_coarsen(h, S, seed, cf));   // :1239-1256 + CorrectCFMarker :1592
+    if (aggressive && ip["CoarsenType"] == 10) {
+      // HMIS second coarsening (measure_type + 3) is not built; a first pass that found no C point at all (no strong
+      // connections: TEST_ij/coarsening.jobs job 14) never gets there, so only a real second pass is refused
+      B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
+      count_c_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf, d_count);
+      B200_LAUNCH_CHECK();
+      int c1 = 0;
+      B200_CUDA(cudaMemcpyAsync(&c1, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      if (c1 > 0) B200_FAIL("CoarsenType 10 (HMIS) with aggressive levels is not built on the B200 path: use CoarsenType 8 (PMIS)");
+    } else if (aggressive) B200_TRY(b200_agg_coarsen(h, S, seed, cf));   // :1239-1256 + CorrectCFMarker :1592
     amg->times[1] += tm.stop();
     B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
     count_c_kernel<<<b200_grid(fine_size, 256), 256, 0, h->stream>>>(fine_size, cf, d_count);
@@ -290,6 +299,9 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     B200_CUDA(cudaMemcpyAsync(&coarse_size, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
     if (coarse_size == 0 || coarse_size == fine_size || coarse_size < min_coarse) {   // :1487-1560
+      // no coarse grid: stop coarsening, "and set the coarsest solve to be a single sweep of default smoother or smoother
+      // set by user" (:1484-1497: grid_relax_type[3] = grid_relax_type[0], one sweep) instead of Gaussian elimination
+      if (coarse_size == 0 || coarse_size == fine_size) stalled = true;
       B200_TRY(b200_csr_destroy(h, S));
       B200_TRY(b200_dfree(h, cf));
       break;
@@ -338,7 +350,18 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   const int nl = (int)amg->lv.size();
   // coarsest level: Gaussian elimination if small enough, else fall back to the smoother (:2909-2921)
   b200_level &Lc = amg->lv[nl - 1];
-  amg->coarse_ge = Lc.n <= max_coarse && Lc.n > 0;
+  amg->coarse_ge = Lc.n <= max_coarse && Lc.n > 0 && !stalled;
+  if (nl == 1) {
+    // "If no coarsening occurred, apply a simple smoother once ... use the user relax type (instead of 0)", 6 when the user
+    // chose none (par_cycle.c:289-300): never Gaussian elimination on a one-level hierarchy
+    const int t = ip["UserRelaxType"] == -1 ? 6 : rdown;
+    rdown = rup = t;
+    amg->relax_down = amg->relax_up = t;
+    amg->gs = !is_jac(t);
+    amg->coarse_ge = false;
+    amg->general_cycle = false;
+    cheby = (t == 16);
+  }
   if (amg->coarse_ge) {
     amg->ge_n = Lc.n;
     B200_TRY(b200_dalloc<double>(h, &amg->ge_A, (size_t)2 * Lc.n * Lc.n));

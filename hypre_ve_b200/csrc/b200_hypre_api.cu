@@ -951,6 +951,7 @@ HYPRE_Int HYPRE_BoomerAMGSetup(HYPRE_Solver s, HYPRE_ParCSRMatrix A, HYPRE_ParVe
   for (const char *k : ints) CALL(b200_amg_set_int(s->amg, k, (int)st[k]), "HYPRE_BoomerAMGSetup");
   for (const char *k : reals) CALL(b200_amg_set_real(s->amg, k, st[k]), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxType", rdown), "HYPRE_BoomerAMGSetup");
+  CALL(b200_amg_set_int(s->amg, "UserRelaxType", st["RelaxType"] < 0 ? -1 : rdown), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "RelaxTypeUp", rup), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "NumSweepsDown", st.count("CycleNumSweeps1") ? (int)st["CycleNumSweeps1"] : -1), "HYPRE_BoomerAMGSetup");
   CALL(b200_amg_set_int(s->amg, "NumSweepsUp", st.count("CycleNumSweeps2") ? (int)st["CycleNumSweeps2"] : -1), "HYPRE_BoomerAMGSetup");
