@@ -10,6 +10,7 @@
 //   relax_type 18 (l1-Jacobi, relax_order 0) on all levels, relax 9 (Gaussian elimination)
 //   on the coarsest, V(1,1) cycle, explicit restriction R = P^T (keepTranspose semantics).
 #include "b200_internal.h"
+#include <chrono>
 #include <cmath>
 #include <map>
 
@@ -267,7 +268,17 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   bool not_finished = max_levels > 1, stalled = false;
   int *d_count = nullptr;
   B200_TRY(b200_dalloc<int>(h, &d_count, 1));
+  const bool trace = getenv("B200_TRACE") != nullptr;
+  auto wall = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tlevel0 = 0;
+  if (trace) { cudaStreamSynchronize(h->stream); tlevel0 = wall(); }
   while (not_finished) {                                   // par_amg_setup.c:889
+    if (trace && level > 0) {
+      cudaStreamSynchronize(h->stream);
+      const double t = wall();
+      fprintf(stderr, "[b200 trace] single-GPU setup level %d -> %d: %.3f ms (rows %d)\n", level - 1, level, t - tlevel0, amg->lv[level - 1].n);
+      tlevel0 = t;
+    }
     b200_level &L = amg->lv[level];
     const int fine_size = L.n;
     b200_csr S = nullptr;
@@ -697,6 +708,14 @@ extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, con
     if ((rc = b200_parcsr_matvec(h, -1.0, A, d_x, 1.0, d_b, r))) break;
     if ((rc = precond(r, p))) break;                                        // p = C r
     if ((rc = b200_vec_dot_dev(h, n, r, p, sc + 0))) break;                 // gamma = <r,p> (:438)
+    {                                                                       // :440-462: INF -> NaN conversion on gamma
+      B200_CUDA(cudaMemcpyAsync(hs, sc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      const double gamma0 = hs[0];
+      if (gamma0 != 0. && !(gamma0 / gamma0 == gamma0 / gamma0)) {
+        rc = b200_set_error(__FILE__, __LINE__, "hypre_PCGSolve: INFs and/or NaNs detected in input"); break;
+      }
+    }
     if (h_norms) {
       double i_prod_0 = 0;
       if (two_norm) { if ((rc = b200_vec_dot(h, n, r, r, &i_prod_0))) break; }   // :466

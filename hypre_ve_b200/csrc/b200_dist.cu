@@ -1823,7 +1823,11 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
     if ((rc = b200_vec_dot_dev(h, n, r, p, lp))) break;                            // gamma = <r,p>
     if ((rc = b200_vec_dot_dev(h, n, r, r, lp + 1))) break;
     if ((rc = b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc))) break;
-    if (h_norms) { if ((rc = fetch())) break; h_norms[0] = std::sqrt(hs[1]); }
+    if ((rc = fetch())) break;
+    if (hs[0] != 0. && !(hs[0] / hs[0] == hs[0] / hs[0])) {                 // pcg.c:440-462: INF -> NaN conversion on gamma
+      rc = b200_set_error(__FILE__, __LINE__, "hypre_PCGSolve: INFs and/or NaNs detected in input"); break;
+    }
+    if (h_norms) h_norms[0] = std::sqrt(hs[1]);
     // One iteration = [beta, p update] of the previous one + [halo, s = A p, <s,p>, reduction, alpha, x/r update, the cycle,
     // <r,s>, <r,r>, reduction, copy of the scalars to the host].  When every exchange of iteration 1 stayed on the device-only
     // path (direct halos and reductions; a single rank trivially), the sequence is a fixed list of kernels with fixed arguments:

@@ -313,7 +313,45 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
       for (int p = lane; p < count; p += 32) ra[p] /= -diagonal;
     }
     __syncwarp();
-    // ---- truncation (lane 0 replays the sequential algorithm on the shared row) -------------
+    // ---- truncation ------------------------------------------------------------------------
+    // Fast path (no drop tolerance, at most 64 candidates): when the pmax largest |w| are pairwise distinct and distinct from
+    // every other entry, hypre_qsort2_abs (descending |w|) leaves exactly those at the front, in descending order, whatever it
+    // does with ties further down -- pmax warp-wide arg-max rounds instead of a one-lane quicksort.  Any tie that could touch
+    // the result (or a NaN) falls through to the exact replay below.
+    if (trunc_tol <= 0 && count > pmax && count <= 64 && pmax <= 32) {
+      const bool h0 = lane < count, h1 = lane + 32 < count;
+      const double v0 = h0 ? ra[lane] : 0.0, v1 = h1 ? ra[lane + 32] : 0.0;
+      const int k0 = h0 ? rj[lane] : 0, k1 = h1 ? rj[lane + 32] : 0;
+      double a0 = h0 ? fabs(v0) : -1.0, a1 = h1 ? fabs(v1) : -1.0;
+      bool ok = !__any_sync(FULL, (h0 && v0 != v0) || (h1 && v1 != v1));
+      double myv = 0.0;
+      int myk = 0;
+      for (int r = 0; r < pmax && ok; r++) {
+        double m = fmax(a0, a1);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) m = fmax(m, __shfl_xor_sync(FULL, m, off));
+        const unsigned b0 = __ballot_sync(FULL, a0 == m), b1 = __ballot_sync(FULL, a1 == m);
+        if (__popc(b0) + __popc(b1) != 1) { ok = false; break; }
+        const int src = b0 ? __ffs(b0) - 1 : __ffs(b1) - 1;
+        const double sv = __shfl_sync(FULL, b0 ? v0 : v1, src);
+        const int sk = __shfl_sync(FULL, b0 ? k0 : k1, src);
+        if (lane == r) { myv = sv; myk = sk; }
+        if (lane == src) { if (b0) a0 = -1.0; else a1 = -1.0; }
+      }
+      if (ok) {
+        double row_sum = 0;
+        if (lane == 0) for (int j = 0; j < count; j++) row_sum += ra[j];      // storage order (par_csr_matrix.c:2981-2990)
+        row_sum = __shfl_sync(FULL, row_sum, 0);
+        double scale = 0;
+        for (int r = 0; r < pmax; r++) scale += __shfl_sync(FULL, myv, r);    // kept entries in their sorted order
+        if (scale != 0. && scale != row_sum) myv *= row_sum / scale;
+        if (lane < pmax) { out_j[(size_t)i * pmax + lane] = myk; out_a[(size_t)i * pmax + lane] = myv; }
+        if (lane == 0) out_cnt[i] = pmax;
+        __syncwarp();
+        continue;
+      }
+    }
+    // exact replay: lane 0 runs the sequential algorithm on the shared row
     int len = count;
     if (lane == 0) {
       if (trunc_tol > 0) {

@@ -129,13 +129,14 @@ def test_spmv_256_cubed_linearity_and_symmetry(handle):
 
 def test_degenerate_inputs(handle):
     """edge cases the reference handles: tiny grids that never coarsen, 1-D chains, a zero right-hand side, and the
-    singular 1 x 1 x 1 operator (A = [0]: the reference flags "Zero sdotp value in PCG", pcg.c:516-521)"""
+    singular 1 x 1 x 1 operator (A = [0]: a one-level hierarchy is smoothed, never eliminated (par_cycle.c:289-300), the sweep
+    divides by the zero l1 norm and the reference returns at its INF/NaN check on gamma, pcg.c:440-462, with 0 iterations)"""
     import hypre_ve_b200 as hb
     A = hb.ParCsr.laplacian(handle, 1, 1, 1)
     amg = hb.Amg(handle)
     amg.setup(A)
     b1 = handle.zeros(1); handle.fill(b1, 1.0)
-    with pytest.raises(hb.B200Error, match="Zero sdotp"):
+    with pytest.raises(hb.B200Error, match="INFs and/or NaNs"):
         handle.pcg(A, amg, b1, handle.zeros(1), tol=1e-8, max_iter=10)
     amg.destroy(); A.destroy()
     for dims in ((1, 1, 2), (1, 1, 7), (40, 1, 1), (3, 3, 1)):
