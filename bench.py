@@ -90,6 +90,27 @@ def solve_bytes_per_iteration(levels):
     return total
 
 
+def setup_bytes(levels):
+    """Compulsory HBM bytes of the setup phases, from the actual hierarchy (every input array read once, every
+    output written once; FP64 values, int32 indices).  levels = [(N_l, nnz(A_l), nnz(P_l))...].  nnz(S_l) is bounded by
+    nnz(A_l) - N_l (no diagonal); the formulas are LOWER bounds of what an ideal one-pass kernel would move:
+      strength   per level: read A (12 nnzA + 4 N), write S (4 nnzS + 4 N)
+      pmis       per level: one sweep over S (4 nnzS + 4 N) + measures / markers (20 N)
+      interp     per level: read A (12 nnzA + 4 N), S (4 nnzS + 4 N), CF (4 N); write P (12 nnzP + 4 N)      [ext+i + truncation]
+      transpose  per level: read P (12 nnzP + 4 N), write R = P^T (12 nnzP + 4 Nc)
+      rap        per level: read R, A, P once (12 (nnzP + nnzA + nnzP) + 4 (Nc + 2 N)), write A_{l+1} (12 nnzA' + 4 Nc)"""
+    out = {"strength": 0.0, "pmis": 0.0, "interp": 0.0, "transpose": 0.0, "rap": 0.0}
+    for l, (n, za, zp) in enumerate(levels[:-1]):
+        nc, zc = levels[l + 1][0], levels[l + 1][1]
+        zs = max(za - n, 0)
+        out["strength"] += 12.0 * za + 4.0 * n + 4.0 * zs + 4.0 * n
+        out["pmis"] += 4.0 * zs + 4.0 * n + 20.0 * n
+        out["interp"] += 12.0 * za + 4.0 * n + 4.0 * zs + 4.0 * n + 4.0 * n + 12.0 * zp + 4.0 * n
+        out["transpose"] += 12.0 * zp + 4.0 * n + 12.0 * zp + 4.0 * nc
+        out["rap"] += 12.0 * (2.0 * zp + za) + 4.0 * (nc + 2.0 * n) + 12.0 * zc + 4.0 * nc
+    return out
+
+
 def spmv_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (None if absent)"""
     try:
@@ -165,8 +186,12 @@ def run_reference(dims, threads, timeout=None):
     """One setup+solve of the UNMODIFIED reference driver (oracle/_ref/ij = test/ij.c compiled in place against the
     reference's own library); returns (setup_s, solve_s, iterations) from its wall-clock lines (ij.c:4301-4314)."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ij")
+    if dims[0] * dims[1] * dims[2] > 100_000_000:
+        # one process holds the whole problem (no MPI here): past ~10^8 unknowns the reference's 32-bit counters overflow
+        # (`ij -n 512 512 512` segfaults), so the same driver from the reference's own --enable-bigint configuration runs it
+        exe = os.path.join(ROOT, "oracle", "_ref", "big", "ij_big")
     if not os.path.exists(exe):
-        raise RuntimeError("oracle/_ref/ij missing: run __graft_entry__.build() where /root/reference exists")
+        raise RuntimeError("%s missing: run __graft_entry__.build() where /root/reference exists" % os.path.relpath(exe, ROOT))
     env = dict(os.environ, OMP_NUM_THREADS=str(threads), OMP_PROC_BIND="false")
     out = subprocess.run([exe, "-n"] + [str(d) for d in dims] + REF_ARGS, env=env, capture_output=True, text=True, check=True,
                          timeout=timeout).stdout
@@ -207,8 +232,9 @@ def reference_arm(a):
         emit(dict(base, unavailable="the reference job %dx%dx%d failed on this host: %s" % (dims + (str(e)[:200],))))
         return 0
     per_step = (t_set + t_sol) / steps
-    sample = "full workload %dx%dx%d per step, stock driver `ij -n ... %s`, %d step(s) after %d warm-up" % (
-        dims + (" ".join(REF_ARGS), steps, warmup))
+    sample = "full workload %dx%dx%d per step, stock driver `ij -n ... %s`%s, %d step(s) after %d warm-up" % (
+        dims + (" ".join(REF_ARGS), " (the reference's --enable-bigint build: 64-bit counters)" if dims[0] * dims[1] * dims[2] > 100_000_000 else "",
+                steps, warmup))
     line = dict(base, **{
         "value": per_step, "steps": steps, "warmup": warmup, "ms_per_step": per_step * 1e3,
         "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -520,6 +546,7 @@ def main():
     achieved = spmv_bytes / (spmv_ms * 1e-3) / 1e9
     it_bytes = solve_bytes_per_iteration(levels)
     it_gbs = it_bytes * its / sol_s / 1e9
+    ph_ms = dict(zip(["strength", "pmis", "interp", "trunc", "transpose", "rap", "l1_alloc", "total"], (phases / a.steps).tolist()))
     ref_its = reference_iterations((n1, n1, n1))
     line = {
         "metric": "boomeramg_pcg_setup_plus_solve_seconds", "value": set_s + sol_s, "unit": "s",
@@ -535,6 +562,9 @@ def main():
                            "achieved": it_gbs, "peak": peak, "unit": "GB/s", "frac": it_gbs / peak},
         "setup_phases_ms": dict(zip(["strength", "pmis", "interp", "trunc", "transpose", "rap", "l1_alloc", "total"],
                                     (phases / a.steps).round(3).tolist())),
+        "setup_roofline": {k: {"ms": float(ph_ms[k]), "algorithmic_bytes": v, "achieved_gbs": v / (float(ph_ms[k]) * 1e-3) / 1e9 if ph_ms[k] > 0 else None,
+                               "frac": v / (float(ph_ms[k]) * 1e-3) / 1e9 / peak if ph_ms[k] > 0 else None}
+                           for k, v in setup_bytes(levels).items()},
         "spmv_gbs": achieved, "spmv_ms": spmv_ms,
         "roofline": {"bound": "hbm", "kernel": "spmv_pipe_kernel<1,2> (y = A0*x, 256^3 7-pt)", "achieved": achieved,
                      "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,

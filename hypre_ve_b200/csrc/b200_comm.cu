@@ -106,6 +106,7 @@ struct b200_p2p_s {
   std::map<size_t, size_t> free_by_off;         // symmetric first-fit allocator: offset -> size
   std::vector<std::pair<size_t, size_t>> pending;   // released, reusable after the next quiescence point
   size_t ar_off = 0;                            // allreduce region: [2 parities][R][16 doubles] | arrival flags [R slots] | count
+  size_t hg_off = 0;                            // small host all-gather region: [2 sets][R][64 words of 8 bytes] | count
 };
 
 struct b200_comm_s {
@@ -246,9 +247,15 @@ int b200_comm_exchange(b200_handle h, b200_comm c, const std::vector<b200_xfer> 
 }
 
 // host allgather of `bytes` bytes per rank
+static int host_allgather_p2p(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all, bool *done);
 int b200_comm_allgather_host(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all) {
   c->host_ops++;
   if (c->nranks == 1) { memcpy(all, mine, bytes); return 0; }
+  {
+    bool done = false;
+    B200_TRY(host_allgather_p2p(h, c, mine, bytes, all, &done));
+    if (done) return 0;
+  }
   if (c->backend == 2) {
     b200_comm_group_s *g = c->group;
     g->host_ptr[c->rank] = mine;
@@ -357,6 +364,43 @@ __device__ __forceinline__ void wait_flag(const unsigned long long *flag, unsign
 }
 
 #define B200_AR_MAXK 16
+#define B200_HG_WORDS 64          // small host all-gather: up to 256 bytes per rank, 4 payload bytes per self-validating word
+struct HgArgs {
+  int R, me, words;
+  unsigned long long *slot[B200_P2P_MAXPEER];     // rank r's slots for MY payload (set 0; set 1 at + R * B200_HG_WORDS)
+  const unsigned long long *mine;                 // my slots [2][R][B200_HG_WORDS]
+  unsigned long long *cnt;
+};
+// The setup phase gathers a few integers per rank hundreds of times (halo plans, row counts, global sums).  Through NCCL that
+// is a staging copy, a collective launch and a copy back per call; here ONE small kernel pushes the payload to every peer as
+// {4 data bytes, sequence number} words (no fence) and assembles the R payloads straight into pinned host memory.
+__global__ void host_allgather_kernel(HgArgs a, const unsigned *__restrict__ in /* pinned host */, unsigned *__restrict__ out /* pinned host */,
+                                      unsigned long long timeout_ns, unsigned long long *dbg) {
+  const int r = threadIdx.x / B200_HG_WORDS, w = threadIdx.x % B200_HG_WORDS;
+  const unsigned long long n = *reinterpret_cast<volatile unsigned long long *>(a.cnt);
+  const unsigned seq = (unsigned)(n + 1);
+  const size_t par = (size_t)(n & 1) * (size_t)a.R * B200_HG_WORDS;
+  __syncthreads();
+  if (r < a.R && w < a.words) {
+    const unsigned long long word = ((unsigned long long)seq << 32) | in[w];
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(a.slot[r] + par + w), "l"(word) : "memory");
+    const unsigned long long *src = a.mine + par + (size_t)r * B200_HG_WORDS + w;
+    const unsigned long long t0 = global_timer_ns();
+    unsigned spins = 0;
+    unsigned long long got;
+    for (;;) {
+      asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(src) : "memory");
+      if ((unsigned)(got >> 32) == seq) break;
+      if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > timeout_ns) {
+        if (dbg) { dbg[1] = r; dbg[2] = seq; dbg[3] = got >> 32; dbg[0] = 4; __threadfence_system(); }
+        __trap();
+      }
+    }
+    out[(size_t)r * a.words + w] = (unsigned)got;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long *>(a.cnt) = n + 1;
+}
 struct ArArgs {
   int R, me;
   uint4 *slot[B200_P2P_MAXPEER];                  // rank r's slots for MY contribution (set 0; set 1 at + R * B200_AR_MAXK)
@@ -416,6 +460,30 @@ static unsigned long long p2p_timeout_ns() {
   return t;
 }
 
+
+static int host_allgather_p2p(b200_handle h, b200_comm c, const void *mine, size_t bytes, void *all, bool *done) {
+  *done = false;
+  if (c->p2p.ok && c->p2p.hg_off && bytes > 0 && bytes <= 4 * B200_HG_WORDS && bytes * (size_t)c->nranks + 512 <= sizeof(double) * 1024) {
+    b200_p2p_s &P = c->p2p;
+    const int R = c->nranks, words = (int)((bytes + 3) / 4);
+    unsigned *pin_in = reinterpret_cast<unsigned *>(h->h_pinned), *pin_out = pin_in + 128;     // 512 bytes in, the rest out
+    pin_in[words - 1] = 0;
+    memcpy(pin_in, mine, bytes);
+    HgArgs a;
+    a.R = R; a.me = c->rank; a.words = words;
+    for (int r = 0; r < R; r++)
+      a.slot[r] = reinterpret_cast<unsigned long long *>(P.peer[r] + P.hg_off) + (size_t)c->rank * B200_HG_WORDS;
+    a.mine = reinterpret_cast<const unsigned long long *>(P.base + P.hg_off);
+    a.cnt = reinterpret_cast<unsigned long long *>(P.base + P.hg_off) + (size_t)2 * R * B200_HG_WORDS;
+    host_allgather_kernel<<<1, R * B200_HG_WORDS, 0, h->stream>>>(a, pin_in, pin_out, p2p_timeout_ns(), g_b200_p2p_dbg);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    for (int r = 0; r < R; r++) memcpy((char *)all + (size_t)r * bytes, pin_out + (size_t)r * words, bytes);
+    *done = true;
+  }
+  return 0;
+}
+
 static int p2p_init(b200_handle h, b200_comm c) {
   b200_p2p_s &P = c->p2p;
   const int R = c->nranks, me = c->rank;
@@ -462,6 +530,8 @@ static int p2p_init(b200_handle h, b200_comm c) {
   const size_t ar_bytes = sizeof(uint4) * 2 * R * B200_AR_MAXK + sizeof(unsigned long long) * B200_P2P_SLOT;
   P.ar_off = b200_comm_p2p_alloc(h, c, ar_bytes);
   if (P.ar_off == (size_t)-1) { p2p_shutdown(c); return 0; }
+  P.hg_off = b200_comm_p2p_alloc(h, c, sizeof(unsigned long long) * 2 * R * B200_HG_WORDS + sizeof(unsigned long long) * B200_P2P_SLOT);
+  if (P.hg_off == (size_t)-1) { p2p_shutdown(c); return 0; }
   return 0;
 }
 

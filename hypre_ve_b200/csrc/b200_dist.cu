@@ -1166,6 +1166,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     tlast = t;
   };
   mark(nullptr);
+  const long long host_ops0 = b200_comm_host_ops(c);
   b200_dist_amg amg = new b200_dist_amg_s();
   amg->relax_wt = b200_amg_get_real(prm, "RelaxWt");
   amg->gs = !jac; amg->relax_down = rdown; amg->relax_up = rup;
@@ -1495,6 +1496,8 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     }
   }
   mark("coarse gather");
+  if (trace) fprintf(stderr, "[b200 trace] rank %d setup used %lld host-synchronised collectives (exchanges + gathers)\n", b200_comm_rank(c),
+                     b200_comm_host_ops(c) - host_ops0);
   cudaEventRecord(e1, h->stream);
   cudaEventSynchronize(e1);
   float ms = 0;

@@ -123,7 +123,13 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("-j", type=int, default=os.cpu_count() or 4)
     ap.add_argument("--force", action="store_true")
+    ap.add_argument("--bigint", action="store_true",
+                    help="build oracle/_ref/big/{libHYPRE_ref_big.so, ij_big}: the reference's --enable-bigint configuration, needed by "
+                         "`ij -n 512 512 512` in one process (local nonzero counts pass 2^31)")
     a = ap.parse_args()
+    if a.bigint:
+        global OUT
+        OUT = os.path.join(OUT, "big")
     ref_src = os.path.join(a.ref, "src")
     if not os.path.isdir(ref_src):
         print("reference not present at %s; keeping prebuilt oracle/_ref" % a.ref)
@@ -133,7 +139,7 @@ def main():
     inc = ["-I" + os.path.join(HERE, "ref_config"), "-I" + ref_src]
     for d in LIB_DIRS + ["distributed_ls", "test", "struct_mv"]:
         inc.append("-I" + os.path.join(ref_src, d))
-    cflags = ["-O2", "-fopenmp", "-fPIC", "-w", "-DHAVE_CONFIG_H", "-DHYPRE_VE"] + inc
+    cflags = ["-O2", "-fopenmp", "-fPIC", "-w", "-DHAVE_CONFIG_H", "-DHYPRE_VE"] + (["-DB200_REF_BIGINT"] if a.bigint else []) + inc
 
     patched = {"parcsr_ls/par_relax.c", "distributed_ls/ParaSails/Matrix.c",
                "parcsr_mv/par_csr_matrix.c"}
@@ -170,12 +176,19 @@ def main():
                 print("FAILED:", cmd[-3], "\n", out[-2000:])
     if fails:
         return 1
-    lib = os.path.join(OUT, "libHYPRE_ref.so")
+    lib = os.path.join(OUT, "libHYPRE_ref_big.so" if a.bigint else "libHYPRE_ref.so")
     rc, out, _ = run(["gcc", "-shared", "-fopenmp", "-o", lib] + objs + ["-lm"])
     if rc:
         print(out[-4000:])
         return 1
-    link = ["-L" + OUT, "-lHYPRE_ref", "-Wl,-rpath,$ORIGIN", "-fopenmp", "-lm"]
+    link = ["-L" + OUT, "-lHYPRE_ref_big" if a.bigint else "-lHYPRE_ref", "-Wl,-rpath,$ORIGIN", "-fopenmp", "-lm"]
+    if a.bigint:
+        rc, out, _ = run(["gcc"] + cflags + ["-DHYPRE_TIMING", os.path.join(ref_src, "test", "ij.c"), "-o", os.path.join(OUT, "ij_big")] + link)
+        if rc:
+            print(out[-4000:])
+            return 1
+        print("built", lib, "ij_big")
+        return 0
     # the reference's own driver, unmodified
     rc, out, _ = run(["gcc"] + cflags + ["-DHYPRE_TIMING", os.path.join(ref_src, "test", "ij.c"),
                                           "-o", os.path.join(OUT, "ij")] + link)

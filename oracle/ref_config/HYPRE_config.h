@@ -22,4 +22,10 @@
 #define HYPRE_FMANGLE 0
 #define HYPRE_FMANGLE_BLAS 0
 #define HYPRE_FMANGLE_LAPACK 0
+/* oracle/build_ref.py --bigint: the reference's own --enable-bigint configuration (64-bit HYPRE_Int / HYPRE_BigInt).
+ * One process holds the whole problem here (no MPI), and at 512^3 unknowns the local nonzero counters pass 2^31: the default
+ * 32-bit build of the reference segfaults on `ij -n 512 512 512`.  Same algorithms, same random numbers, same results. */
+#ifdef B200_REF_BIGINT
+#define HYPRE_BIGINT 1
+#endif
 #endif

@@ -20,7 +20,9 @@ def main():
     v = sys.argv[1:]
     for k in range(0, len(v), 3):
         dims = v[k:k + 3]
-        out = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ij"), "-n"] + dims + tab["flags"].split(), capture_output=True,
+        big = int(dims[0]) * int(dims[1]) * int(dims[2]) > 100_000_000        # 32-bit counters overflow: the --enable-bigint build
+        exe = os.path.join(ROOT, "oracle", "_ref", "big", "ij_big") if big else os.path.join(ROOT, "oracle", "_ref", "ij")
+        out = subprocess.run([exe, "-n"] + dims + tab["flags"].split(), capture_output=True,
                              text=True, check=True, env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count()))).stdout
         tab["counts"][" ".join(dims)] = int(re.search(r"^Iterations = (\d+)", out, re.M).group(1))
         tab["final_rel_res"][" ".join(dims)] = float(re.search(r"Final Relative Residual Norm = (\S+)", out).group(1))
