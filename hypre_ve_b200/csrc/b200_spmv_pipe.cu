@@ -193,8 +193,42 @@ int launch_pipe2(b200_handle h, b200_csr A, const double *x, double *y, const Ep
     B200_CUDA(cudaFuncSetAttribute(spmv_pipe_kernel<G, NSTAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)maxb));
     attr_set.fetch_or(bit, std::memory_order_release);
   }
-  int per_sm = (int)((size_t)(227 * 1024) / (bytes + 1024));   // +1 KB: per-CTA reservation of the runtime
+  // Operators with an irregular x gather (G > 1: the coarse Galerkin operators, R) are bound by the L2 -> SM sector traffic of
+  // the gather, not by HBM: with the default carve-out (228 KB shared, 28 KB L1) every gathered sector comes from L2.  Asking
+  // for the 196 KB configuration leaves 60 KB of L1 for x at the price of one resident CTA (measured on the 256^3 hierarchy:
+  // A_2 229 -> 171 us, A_1 510 -> 496 us; profiles/README.md r2).  B200_SPMV_CARVEOUT=<percent> overrides (0 = default).
+  static const int carve_env = [] { const char *e = getenv("B200_SPMV_CARVEOUT"); return e ? atoi(e) : 75; }();
+  size_t smem_budget = (size_t)(227 * 1024);
+  if (carve_env > 0 && G > 1) {
+    static std::atomic<unsigned long long> carve_set{0};
+    if (!(carve_set.load(std::memory_order_acquire) & bit)) {
+      B200_CUDA(cudaFuncSetAttribute(spmv_pipe_kernel<G, NSTAGE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve_env));
+      carve_set.fetch_or(bit, std::memory_order_release);
+    }
+    // supported shared-memory configurations (KB per SM); the driver rounds the preference up to the next one
+    static const int cfg[] = {0, 8, 16, 32, 64, 100, 132, 164, 196, 228};
+    const int want = 256 * carve_env / 100;
+    int kb = 228;
+    for (int q : cfg) if (q >= want) { kb = q; break; }
+    smem_budget = (size_t)(kb - 1) * 1024;
+  }
+  int per_sm = (int)(smem_budget / (bytes + 1024));   // +1 KB: per-CTA reservation of the runtime
   if (per_sm > 2048 / NT) per_sm = 2048 / NT;
+  {
+    // persistent grid = exactly the CTAs that are resident at once: registers (40 per thread: 12 CTAs) bind before shared
+    // memory for the short-row operators (P, R), and a grid larger than one wave leaves a second, under-filled wave
+    static std::atomic<int> occ_cache[64];                // by stage size / 32 entries (scap is a multiple of 32, <= 1536)
+    std::atomic<int> &slot = occ_cache[(scap / 32) & 63];
+    int occ = slot.load(std::memory_order_relaxed);
+    if (occ == 0) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, spmv_pipe_kernel<G, NSTAGE>, NT, bytes) != cudaSuccess || occ < 1) {
+        cudaGetLastError();
+        occ = per_sm;
+      }
+      slot.store(occ, std::memory_order_relaxed);
+    }
+    if (per_sm > occ) per_sm = occ;
+  }
   if (per_sm < 1) per_sm = 1;
   int grid = h->num_sm * per_sm;
   if (grid > A->nblk) grid = A->nblk;
