@@ -743,8 +743,8 @@ extern "C" int b200_pcg_solve_ex(b200_handle h, b200_parcsr A, b200_amg amg, con
       pcg_update_xr_kernel<<<vgrid(h, n), 256, 0, h->stream>>>((size_t)n, sc, p, s, d_x, r);
       ++g_b200_launches;
       B200_TRY(precond(r, s));                                              // s = C r (:568-569)
-      B200_TRY(b200_vec_dot_dev(h, n, r, s, sc + 0));                       // gamma = <r,s> (:572)
-      if (two_norm) B200_TRY(b200_vec_dot_dev(h, n, r, r, sc + 3));         // i_prod = <r,r> (:590)
+      if (two_norm) B200_TRY(b200_vec_dot2_dev(h, n, r, s, sc + 0, sc + 3)); // gamma = <r,s> (:572), i_prod = <r,r> (:590): one pass over r
+      else B200_TRY(b200_vec_dot_dev(h, n, r, s, sc + 0));
       B200_CUDA(cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
       return 0;
     };

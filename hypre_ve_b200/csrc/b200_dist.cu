@@ -1856,8 +1856,7 @@ extern "C" int b200_dist_pcg_solve(b200_handle h, b200_comm c, b200_dist_matrix 
       { b200_prof_scope ps(h, "pcg precond (whole cycle)");
         B200_TRY(precond(r, s)); }                                                       // s = C r (pcg.c:568-569)
       { b200_prof_scope ps(h, "pcg dot");
-        B200_TRY(b200_vec_dot_dev(h, n, r, s, lp));                                      // gamma = <r,s> (pcg.c:572)
-        B200_TRY(b200_vec_dot_dev(h, n, r, r, lp + 1)); }                                // i_prod = <r,r> (pcg.c:590)
+        B200_TRY(b200_vec_dot2_dev(h, n, r, s, lp, lp + 1)); }                          // gamma = <r,s> (pcg.c:572), i_prod = <r,r> (:590)
       { b200_prof_scope ps(h, "pcg allreduce");
         B200_TRY(b200_comm_allreduce_sum_dev2dev(h, c, lp, 2, sc)); }
       B200_CUDA(cudaMemcpyAsync(hs, sc, 6 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

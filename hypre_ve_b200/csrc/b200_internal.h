@@ -155,6 +155,7 @@ int b200_cheby_setup(b200_handle h, b200_csr A, int eig_est, int order, double f
 int b200_cheby_solve(b200_handle h, b200_cheby_s *C, b200_csr As, bool zero, const double *f, double *u);
 int b200_cheby_destroy(b200_handle h, b200_cheby_s *c);
 int b200_reduce_sum_int(b200_handle h, const int *d_data, size_t n, long long *h_out);
+int b200_vec_dot2_dev(b200_handle h, int n, const double *x, const double *y, double *d_xy, double *d_xx);   // <x,y> and <x,x>, one pass
 // GMRES / BiCGSTAB written once over these operations (b200_krylov.cu); single GPU there, row-partitioned in b200_dist.cu
 struct b200_krylov_ops {
   int n = 0, cap = 0;          // owned entries; allocation length of a work vector (n + the ghost tail the operator reads)

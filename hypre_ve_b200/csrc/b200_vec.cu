@@ -36,18 +36,48 @@ __device__ __forceinline__ double block_sum(double s) {
   return t;   // valid in thread 0
 }
 
+// Fixed grid, fixed slices: deterministic for a given n.  128-bit loads, four of them in flight per thread and operand
+// (16N bytes stream at the HBM roof only with >= 100 KB in flight per SM).  TWO = 1 also accumulates <x,x> in the same
+// pass (PCG needs <r,s> and <r,r> at the same point: one read of r instead of two).
+template <int TWO>
 __global__ void __launch_bounds__(VT) dot_partial_kernel(size_t n, const double *__restrict__ x,
                                                           const double *__restrict__ y,
-                                                          double *__restrict__ partial) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
-  double s0 = 0.0, s1 = 0.0;
-  for (; i + stride < n; i += 2 * stride) {
-    s0 += x[i] * y[i];
-    s1 += x[i + stride] * y[i + stride];
+                                                          double *__restrict__ partial, double *__restrict__ partial2) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  double s = 0.0, q = 0.0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  size_t done = 0;
+  if (aligned) {
+    const size_t n2 = n / 2;
+    const double2 *x2 = reinterpret_cast<const double2 *>(x), *y2 = reinterpret_cast<const double2 *>(y);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+    size_t i = tid;
+    for (; i + 3 * stride < n2; i += 4 * stride) {
+      const double2 u0 = x2[i], u1 = x2[i + stride], u2 = x2[i + 2 * stride], u3 = x2[i + 3 * stride];
+      const double2 v0 = y2[i], v1 = y2[i + stride], v2 = y2[i + 2 * stride], v3 = y2[i + 3 * stride];
+      a0 += u0.x * v0.x; a0 += u0.y * v0.y; a1 += u1.x * v1.x; a1 += u1.y * v1.y;
+      a2 += u2.x * v2.x; a2 += u2.y * v2.y; a3 += u3.x * v3.x; a3 += u3.y * v3.y;
+      if (TWO) {
+        b0 += u0.x * u0.x; b0 += u0.y * u0.y; b1 += u1.x * u1.x; b1 += u1.y * u1.y;
+        b2 += u2.x * u2.x; b2 += u2.y * u2.y; b3 += u3.x * u3.x; b3 += u3.y * u3.y;
+      }
+    }
+    for (; i < n2; i += stride) {
+      const double2 u = x2[i], v = y2[i];
+      a0 += u.x * v.x; a0 += u.y * v.y;
+      if (TWO) { b0 += u.x * u.x; b0 += u.y * u.y; }
+    }
+    s = (a0 + a1) + (a2 + a3);
+    q = (b0 + b1) + (b2 + b3);
+    done = n2 * 2;
   }
-  if (i < n) s0 += x[i] * y[i];
-  double t = block_sum(s0 + s1);
+  for (size_t i = done + tid; i < n; i += stride) { s += x[i] * y[i]; if (TWO) q += x[i] * x[i]; }
+  double t = block_sum(s);
   if (threadIdx.x == 0) partial[blockIdx.x] = t;
+  if (TWO) {
+    double t2 = block_sum(q);
+    if (threadIdx.x == 0) partial2[blockIdx.x] = t2;
+  }
 }
 __global__ void __launch_bounds__(VT) dot_final_kernel(int np, const double *__restrict__ partial,
                                                         double *__restrict__ out) {
@@ -92,9 +122,28 @@ extern "C" int b200_vec_axpy(b200_handle h, int n, double a, const double *x, do
 int b200_vec_dot_dev(b200_handle h, int n, const double *x, const double *y, double *d_out) {
   int g = vec_grid(h, n > 0 ? n : 1);
   if (g > h->n_partials) g = h->n_partials;
-  dot_partial_kernel<<<g, VT, 0, h->stream>>>((size_t)(n > 0 ? n : 0), x, y, h->d_partials);
+  dot_partial_kernel<0><<<g, VT, 0, h->stream>>>((size_t)(n > 0 ? n : 0), x, y, h->d_partials, nullptr);
   B200_LAUNCH_CHECK();
   dot_final_kernel<<<1, VT, 0, h->stream>>>(g, h->d_partials, d_out);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// <x,y> -> d_out[0] and <x,x> -> d_out[stride2] in ONE pass over x (device-side results, no sync)
+__global__ void __launch_bounds__(VT) dot2_final_kernel(int np, const double *__restrict__ p1, const double *__restrict__ p2,
+                                                         double *__restrict__ out1, double *__restrict__ out2) {
+  double s = 0.0, q = 0.0;
+  for (int i = threadIdx.x; i < np; i += VT) { s += p1[i]; q += p2[i]; }
+  const double t = block_sum(s);
+  const double t2 = block_sum(q);
+  if (threadIdx.x == 0) { out1[0] = t; out2[0] = t2; }
+}
+int b200_vec_dot2_dev(b200_handle h, int n, const double *x, const double *y, double *d_xy, double *d_xx) {
+  int g = vec_grid(h, n > 0 ? n : 1);
+  if (g > h->n_partials / 2) g = h->n_partials / 2;
+  dot_partial_kernel<1><<<g, VT, 0, h->stream>>>((size_t)(n > 0 ? n : 0), x, y, h->d_partials, h->d_partials + h->n_partials / 2);
+  B200_LAUNCH_CHECK();
+  dot2_final_kernel<<<1, VT, 0, h->stream>>>(g, h->d_partials, h->d_partials + h->n_partials / 2, d_xy, d_xx);
   B200_LAUNCH_CHECK();
   return 0;
 }
@@ -103,7 +152,7 @@ extern "C" int b200_vec_dot(b200_handle h, int n, const double *x, const double 
   double *d_out = h->d_partials + (h->n_partials - 1);   // last slot is never used as a partial (g < n_partials)
   int g = vec_grid(h, n > 0 ? n : 1);
   if (g > h->n_partials - 1) g = h->n_partials - 1;
-  dot_partial_kernel<<<g, VT, 0, h->stream>>>((size_t)(n > 0 ? n : 0), x, y, h->d_partials);
+  dot_partial_kernel<0><<<g, VT, 0, h->stream>>>((size_t)(n > 0 ? n : 0), x, y, h->d_partials, nullptr);
   B200_LAUNCH_CHECK();
   dot_final_kernel<<<1, VT, 0, h->stream>>>(g, h->d_partials, d_out);
   B200_LAUNCH_CHECK();
