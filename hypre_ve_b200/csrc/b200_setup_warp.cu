@@ -14,6 +14,8 @@
 // memory; a row that does not fit raises a device flag and the caller redoes the stage with the
 // general HBM-scratch kernels of b200_setup.cu.
 #include "b200_internal.h"
+#include <map>
+#include <mutex>
 
 namespace {
 
@@ -731,6 +733,27 @@ inline int warp_grid(b200_handle h, int n, int blocks_per_sm) {
   long long cap = (long long)h->num_sm * blocks_per_sm;
   return (int)(need < cap ? (need > 0 ? need : 1) : cap);
 }
+// Grid of a grid-stride, warp-per-row kernel = exactly the CTAs that are resident at once (occupancy of THIS kernel with THIS
+// much dynamic shared memory, asked of the runtime and remembered).  A grid sized from a guessed blocks-per-SM constant that
+// exceeds the real occupancy (registers: 9 for extpi_warp_kernel<256>, 12 for spgemm_warp_kernel<256,32,2>) runs as one full
+// wave plus an under-filled one: ncu showed sm__warps_active 51 % on the level-0 (RA)P product.
+template <class K>
+int occ_grid(b200_handle h, K kernel, int n, size_t bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void *, size_t>, int> cache;
+  int occ = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const auto key = std::make_pair((const void *)kernel, bytes * 64 + (size_t)h->device);
+    auto it = cache.find(key);
+    if (it != cache.end()) occ = it->second;
+    else {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 32 * WPB, bytes) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 8; }
+      cache[key] = occ;
+    }
+  }
+  return warp_grid(h, n, occ);
+}
 inline int fill_grid(b200_handle h, size_t n) {
   size_t g = (n + 255) / 256, cap = (size_t)h->num_sm * 8;
   return (int)(g < cap ? (g ? g : 1) : cap);
@@ -811,7 +834,7 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
       constexpr int CAP = CAPV;                                                                                   \
       const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));        \
       B200_TRY(set_smem(extpi_warp_kernel<CAP>, bytes));                                                          \
-      extpi_warp_kernel<CAP><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                               \
+      extpi_warp_kernel<CAP><<<occ_grid(h, extpi_warp_kernel<CAP>, m, bytes), 32 * WPB, bytes, h->stream>>>(                               \
           m, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor, max_elmts, sj, sa, cnt, d_flag, rows);        \
     }
     if (m > 0) {
@@ -884,7 +907,7 @@ static int spgemm_fused_run(b200_handle h, b200_csr A, b200_csr B, int allsquare
       constexpr int CAP = CAPV;                                                                                   \
       const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));        \
       B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, 2>, bytes));                                                  \
-      spgemm_warp_kernel<CAP, GB, 2><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                       \
+      spgemm_warp_kernel<CAP, GB, 2><<<occ_grid(h, spgemm_warp_kernel<CAP, GB, 2>, m, bytes), 32 * WPB, bytes, h->stream>>>(                       \
           m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, diag_base, rows, cnt, off, sj, sa, d_flag,            \
           pass == 0 ? 512 : 0);                                                                                   \
     }
@@ -939,7 +962,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
     if (pass == 0) {
       constexpr int CAP = 256;
       const size_t bytes = (size_t)WPB * sizeof(int) * CAP;
-      spgemm_warp_kernel<CAP, GB, 0><<<warp_grid(h, n, 16), 32 * WPB, bytes, h->stream>>>(
+      spgemm_warp_kernel<CAP, GB, 0><<<occ_grid(h, spgemm_warp_kernel<CAP, GB, 0>, n, bytes), 32 * WPB, bytes, h->stream>>>(
           n, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, nullptr, cnt, nullptr, nullptr, nullptr, d_flag);
       B200_LAUNCH_CHECK();
     } else {
@@ -948,7 +971,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
       int *rows = nullptr, m = 0;
       B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
       if (m > 0) {
-        spgemm_warp_kernel<CAP, GB, 0><<<warp_grid(h, m, 6), 32 * WPB, bytes, h->stream>>>(
+        spgemm_warp_kernel<CAP, GB, 0><<<occ_grid(h, spgemm_warp_kernel<CAP, GB, 0>, m, bytes), 32 * WPB, bytes, h->stream>>>(
             m, A->i, A->j, nullptr, B->i, B->j, nullptr, allsquare, diag_base, rows, cnt, nullptr, nullptr, nullptr, d_flag);
         B200_LAUNCH_CHECK();
       }
@@ -978,7 +1001,7 @@ static int spgemm_warp_run(b200_handle h, b200_csr A, b200_csr B, int allsquare,
     B200_TRY(build_row_list(h, n, cnt, LO, CAP / 2, &rows, &m));                                                  \
     if (m > 0) {                                                                                                  \
       B200_TRY(set_smem(spgemm_warp_kernel<CAP, GB, 1>, bytes));                                               \
-      spgemm_warp_kernel<CAP, GB, 1><<<warp_grid(h, m, BPS), 32 * WPB, bytes, h->stream>>>(                    \
+      spgemm_warp_kernel<CAP, GB, 1><<<occ_grid(h, spgemm_warp_kernel<CAP, GB, 1>, m, bytes), 32 * WPB, bytes, h->stream>>>(                    \
           m, A->i, A->j, A->a, B->i, B->j, B->a, allsquare, diag_base, rows, cnt, C->i, C->j, C->a, d_flag);                 \
       B200_LAUNCH_CHECK();                                                                                        \
     }                                                                                                             \
