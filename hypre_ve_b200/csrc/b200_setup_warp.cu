@@ -103,10 +103,11 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
   constexpr int LIMIT = CAP / 2;      // max occupied slots (C-hat members + strong-F markers)
   extern __shared__ unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // per-warp layout: ra[LIMIT] doubles | keys[CAP] | vals[CAP] | rj[LIMIT]
-  unsigned char *base_p = smem_raw + (size_t)warp * (sizeof(double) * LIMIT + sizeof(int) * (2 * CAP + LIMIT));
+  // per-warp layout: ra[LIMIT] doubles | sumbuf[32] doubles | keys[CAP] | vals[CAP] | rj[LIMIT]
+  unsigned char *base_p = smem_raw + (size_t)warp * (sizeof(double) * (LIMIT + 32) + sizeof(int) * (2 * CAP + LIMIT));
   double *ra = reinterpret_cast<double *>(base_p);
-  int *keys = reinterpret_cast<int *>(base_p + sizeof(double) * LIMIT);
+  double *sumbuf = ra + LIMIT;
+  int *keys = reinterpret_cast<int *>(base_p + sizeof(double) * (LIMIT + 32));
   int *vals = keys + CAP;
   int *rj = vals + CAP;
   const unsigned ltmask = (1u << lane) - 1u;
@@ -276,10 +277,17 @@ extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_
               if (q == SELF || q >= 0) contrib = a;
             }
             if (k0 == b1) q0 = q;
-            // lane order == entry order; lanes with contrib == 0 would add an exact 0.0, so only the
-            // contributing lanes are visited
-            for (unsigned any = __ballot_sync(FULL, contrib != 0.0); any; any &= any - 1)
-              sum += __shfl_sync(FULL, contrib, __ffs(any) - 1);
+            // lane order == entry order; lanes with contrib == 0 would add an exact 0.0, so only the contributing
+            // values are summed: compacted into the warp's scratch in lane order, then added by every lane from
+            // broadcast reads (2 instructions per term instead of a find-first-set + two shuffles + bookkeeping)
+            const unsigned cmask = __ballot_sync(FULL, contrib != 0.0);
+            if (cmask) {
+              if (contrib != 0.0) sumbuf[__popc(cmask & ltmask)] = contrib;
+              __syncwarp();
+              const int nc = __popc(cmask);
+              for (int j = 0; j < nc; j++) sum += sumbuf[j];
+              __syncwarp();
+            }
           }
           if (sum != 0) {
             const double distribute = aij / sum;
@@ -832,7 +840,7 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
 #define B200_EXTPI_LAUNCH(CAPV, BPS)                                                                              \
     {                                                                                                             \
       constexpr int CAP = CAPV;                                                                                   \
-      const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2) + sizeof(int) * (2 * CAP + CAP / 2));        \
+      const size_t bytes = (size_t)WPB * (sizeof(double) * (CAP / 2 + 32) + sizeof(int) * (2 * CAP + CAP / 2));   \
       B200_TRY(set_smem(extpi_warp_kernel<CAP>, bytes));                                                          \
       extpi_warp_kernel<CAP><<<occ_grid(h, extpi_warp_kernel<CAP>, m, bytes), 32 * WPB, bytes, h->stream>>>(                               \
           m, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor, max_elmts, sj, sa, cnt, d_flag, rows);        \
