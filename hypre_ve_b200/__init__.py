@@ -96,6 +96,7 @@ SIGNATURES = {
     "b200_multipass_interp": (_i, [_vp, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_l1_norms": (_i, [_vp, _vp, _i, _vp]),
     "b200_l1_norms_blocks": (_i, [_vp, _vp, _i, _i, _vp]),
+    "b200_l1_norms_cf": (_i, [_vp, _vp, _vp, _vp]),
     "b200_relax_gs": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp]),
     "b200_pcg_solve": (_i, [_vp, _vp, _vp, _vp, _vp, _d, _i, _ip, _dp, _vp]),
     "b200_pcg_solve_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _ip, _dp, _vp]),

@@ -24,6 +24,7 @@ extern "C" int b200_multipass_interp(b200_handle h, b200_csr A, b200_csr S, int 
 struct b200_level {
   b200_csr A = nullptr;     // owned except level 0 (borrowed from the caller's ParCSR diag block)
   b200_csr As = nullptr;    // solve-phase operator: A itself on level 0, a column-sorted copy on the coarse levels
+  b200_parcsr Apar = nullptr;   // one-rank ParCSR view of A for the CG smoother (relax 15)
   b200_csr P = nullptr;     // interpolation to this level from the next coarser one
   b200_csr R = nullptr;     // P^T
   b200_csr S = nullptr;     // kept only when KeepS
@@ -43,6 +44,7 @@ struct b200_amg_s {
   int ge_n = 0;
   bool coarse_ge = false;
   bool gs = false;                // Gauss-Seidel family smoother (relax 3/4/6/8/13/14) instead of l1-Jacobi
+  bool cf_l1 = false;             // l1-Jacobi in C/F order (relax 18, relax_order 1: par_cycle.c:397-416)
   int relax_down = 18, relax_up = 18;
   int ns[4] = {1, 1, 1, 1};       // num_grid_sweeps[1..3]: down, up, coarsest (par_amg.c:1934-2030)
   int cycle_type = 1, fcycle = 0; // 1 = V, 2 = W (par_cycle.c:199-210); F-cycle flag
@@ -174,6 +176,7 @@ static int free_levels(b200_handle h, b200_amg amg) {
   for (size_t l = 0; l < amg->lv.size(); l++) {
     b200_level &L = amg->lv[l];
     if (L.As && L.As != L.A) B200_TRY(b200_csr_destroy(h, L.As));
+    if (L.Apar) { B200_TRY(b200_csr_destroy(h, L.Apar->offd)); delete L.Apar; L.Apar = nullptr; }
     if (l > 0) B200_TRY(b200_csr_destroy(h, L.A));
     B200_TRY(b200_csr_destroy(h, L.P));
     B200_TRY(b200_csr_destroy(h, L.R));
@@ -228,14 +231,23 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
   auto is_l1gs = [](int t) { return t == 8 || t == 13 || t == 14; };
   auto is_jac = [](int t) { return t == 18 || t == 7; };
   bool cheby = rdown == 16 && rup == 16;
+  // smoothers built from masked Jacobi half-sweeps or from PCG itself (par_cycle.c:397-460): FCF-Jacobi 17, the CG smoother 15,
+  // and l1-Jacobi in C/F order (relax 18 with RelaxOrder 1)
+  const bool fcf = rdown == 17 && rup == 17, cgs = rdown == 15 && rup == 15;
+  const bool cf_l1 = rdown == 18 && rup == 18 && ip["RelaxOrder"] == 1;
+  if (fcf || cgs || cf_l1) {
+    // handled below: in-place smoothers of the amg_cycle_gs family
+  } else
   if (!((is_jac(rdown) && rup == rdown) || cheby || (is_gs(rdown) && is_gs(rup) && is_l1gs(rdown) == is_l1gs(rup))))
     B200_FAIL("RelaxType: the B200 path implements 18 (l1-Jacobi), 7 (weighted Jacobi), 16 (Chebyshev), the l1 hybrid "
               "Gauss-Seidel family 8/13/14 and the hybrid Gauss-Seidel family 3/4/6 (down and up sweeps from the same family)");
-  if (!is_jac(rdown) && !cheby && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
+  if (!is_jac(rdown) && !cheby && !fcf && !cgs && rp["RelaxWt"] != 1.0) B200_FAIL("Gauss-Seidel smoothers: only relax_weight 1 is implemented");
   if (ip["GSBlocks"] < 1) B200_FAIL("GSBlocks must be >= 1");
-  amg->gs = !is_jac(rdown);                  // in-place smoothers (Gauss-Seidel family, Chebyshev) use amg_cycle_gs
+  amg->gs = !is_jac(rdown) || cf_l1;         // in-place smoothers (Gauss-Seidel family, Chebyshev, 15, 17, C/F l1-Jacobi) use amg_cycle_gs
   amg->relax_down = rdown; amg->relax_up = rup;
-  if (ip["RelaxOrder"] != 0) B200_FAIL("only RelaxOrder 0 is implemented on the B200 path");
+  amg->cf_l1 = cf_l1;
+  if (ip["RelaxOrder"] != 0 && !cf_l1 && !fcf && !cgs && !is_jac(rdown))
+    B200_FAIL("RelaxOrder 1 (C/F relaxation) is implemented for the l1-Jacobi smoother (RelaxType 18) only");
   if (ip["AggNumLevels"] < 0) B200_FAIL("AggNumLevels must be >= 0");
   // aggressive levels: second PMIS on the distance-two graph + multipass interpolation (agg_interp_type 4, the
   // reference default; agg_trunc_factor = agg_P_max_elmts = 0, num_paths 1), par_amg_setup.c:1239-1256, :1590-1605
@@ -391,15 +403,26 @@ extern "C" int b200_amg_setup(b200_handle h, b200_amg amg, b200_parcsr Apar) {
     if (L.P && !L.P->blk_row) B200_TRY(b200_csr_build_plan(h, L.P));
     if (L.R && !L.R->blk_row) B200_TRY(b200_csr_build_plan(h, L.R));
     if (l < nl - 1 || !amg->coarse_ge || rdown == 7) {
-      if (!amg->gs || is_l1gs(rdown)) {                // option 1: relax 18, 4: relax 8/13/14, 5 (= the diagonal): relax 7
+      if (!amg->gs || is_l1gs(rdown) || amg->cf_l1) {  // option 1: relax 18, 4: relax 8/13/14, 5 (= the diagonal): relax 7
+        const bool l1gs = amg->gs && !amg->cf_l1;
         B200_TRY(b200_dalloc<double>(h, &L.l1, L.n));
-        B200_TRY(b200_l1_norms_blocks(h, L.A, amg->gs ? 4 : (rdown == 7 ? 5 : 1), amg->gs ? ip["GSBlocks"] : 1, L.l1));
+        if (amg->cf_l1 && l < nl - 1 && L.cf) B200_TRY(b200_l1_norms_cf(h, L.A, L.cf, L.l1));      // par_amg_setup.c:3047-3050
+        else B200_TRY(b200_l1_norms_blocks(h, L.A, l1gs ? 4 : (rdown == 7 ? 5 : 1), l1gs ? ip["GSBlocks"] : 1, L.l1));
       }
     }
     if (cheby && (l < nl - 1 || !amg->coarse_ge))           // par_amg_setup.c:3137-3160
       B200_TRY(b200_cheby_setup(h, L.A, ip["ChebyEigEst"], ip["ChebyOrder"], rp["ChebyFraction"], ip["ChebyVariant"],
                                 ip["ChebyScale"], &L.cheby));
-    if ((l < nl - 1 || !amg->coarse_ge) && !cheby) {
+    if (rdown == 15 && (l < nl - 1 || !amg->coarse_ge)) {       // CG smoother: PCG on this level's operator (par_amg_setup.c:3165-3180)
+      L.Apar = new b200_parcsr_s();
+      L.Apar->global_rows = L.Apar->global_cols = L.n;
+      L.Apar->diag = L.A;
+      B200_TRY(b200_csr_alloc(h, L.n, 0, 0, true, &L.Apar->offd));
+      B200_CUDA(cudaMemsetAsync(L.Apar->offd->i, 0, sizeof(int) * ((size_t)L.n + 1), h->stream));
+      if (!L.A->blk_row) B200_TRY(b200_csr_build_plan(h, L.A));
+    }
+    const bool masked = rdown == 17 || rdown == 15 || amg->cf_l1;
+    if ((l < nl - 1 || !amg->coarse_ge) && !cheby && !masked) {
       if (amg->gs) {
         if (L.A->gs && b200_gs_plan_blocks(L.A->gs) != ip["GSBlocks"]) { B200_TRY(b200_gs_plan_destroy(h, L.A->gs)); L.A->gs = nullptr; }
         if (!L.A->gs) B200_TRY(b200_gs_plan_create(h, L.A, ip["GSBlocks"], &L.A->gs));
@@ -437,8 +460,66 @@ static int jacobi(b200_handle h, b200_level &L, double w, const double *f, const
 // (PCG clears the vector before every preconditioner application, pcg.c:434,:568), which lets
 // the first sweep on every level skip its SpMV: u + (f - A*0)/l1 == f/l1 exactly.
 // one in-place relaxation call: Gauss-Seidel family or Chebyshev
-static int gs_relax(b200_handle h, b200_level &L, int type, const double *f, double *u, bool zero) {
+// One Jacobi half-sweep over the rows whose CF marker equals `pt` (pt = 0: every row), reading the iterate from before the
+// sweep (`old`, the reference's Vtemp copy) and updating u in place; one thread per row, the row summed in storage order.
+//   mode 0, weighted Jacobi (hypre_BoomerAMGRelax type 0, par_relax.c:139-248): u_i = (1 - w) u_i + w (f_i - sum_{j != i} a_ij old_j) / a_ii
+//   mode 1, l1-Jacobi (hypre_ParCSRRelax_L1_Jacobi, par_relax_more.c:991-1161): u_i += w (f_i - sum_j a_ij old_j) / l1_i
+__global__ void masked_jacobi_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                                     const int *__restrict__ cf, int pt, int mode, double w, const double *__restrict__ f,
+                                     const double *__restrict__ l1, const double *__restrict__ old, double *__restrict__ u) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (pt != 0 && cf[i] != pt) return;
+  const int b = A_i[i], e = A_i[i + 1];
+  const double diag = A_a[b];
+  if (diag == 0.0) return;
+  double res = f[i];
+  for (int jj = b + (mode == 0 ? 1 : 0); jj < e; jj++) res -= A_a[jj] * old[A_j[jj]];
+  if (mode == 0) {
+    double v = u[i] * (1.0 - w);
+    v += w * res / diag;
+    u[i] = v;
+  } else {
+    u[i] += (w * res) / l1[i];
+  }
+}
+
+static int masked_sweep(b200_handle h, b200_level &L, int pt, int mode, double w, const double *f, double *u) {
+  B200_CUDA(cudaMemcpyAsync(L.T, u, sizeof(double) * (size_t)L.n, cudaMemcpyDeviceToDevice, h->stream));      // Vtemp = u
+  masked_jacobi_kernel<<<b200_grid(L.n, 128), 128, 0, h->stream>>>(L.n, L.A->i, L.A->j, L.A->a, L.cf, pt, mode, w, f, L.l1, L.T, u);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+// phase: 1 down sweep, 2 up sweep, 3 coarsest grid (par_cycle.c cycle_param)
+static int gs_relax(b200_handle h, b200_amg amg, b200_level &L, int type, const double *f, double *u, bool zero, int phase) {
   if (type == 16) return b200_cheby_solve(h, L.cheby, L.As, zero, f, u);      // par_cycle.c:440-452
+  if (type == 17 || type == 15 || (type == 18 && amg->cf_l1)) {
+    const double w = amg->rp["RelaxWt"];
+    if (zero) B200_CUDA(cudaMemsetAsync(u, 0, sizeof(double) * (size_t)L.n, h->stream));
+    if (type == 17) {                                                         // :451-464, hypre_BoomerAMGRelax_FCFJacobi
+      if (phase == 3 || !L.cf) return masked_sweep(h, L, 0, 0, w, f, u);      // coarsest grid: one plain Jacobi sweep
+      B200_TRY(masked_sweep(h, L, -1, 0, w, f, u));
+      B200_TRY(masked_sweep(h, L, 1, 0, w, f, u));
+      return masked_sweep(h, L, -1, 0, w, f, u);
+    }
+    if (type == 18) {                                                         // :397-416: C then F going down, F then C going up
+      if (phase == 3 || !L.cf) return masked_sweep(h, L, 0, 1, w, f, u);
+      B200_TRY(masked_sweep(h, L, phase == 1 ? 1 : -1, 1, w, f, u));
+      return masked_sweep(h, L, phase == 1 ? -1 : 1, 1, w, f, u);
+    }
+    // CG smoother (:439-445, hypre_ParCSRRelax_CG): num_sweep (= 1) iterations of unpreconditioned PCG in the 2-norm from u
+    b200_pcg_params prm;
+    prm.tol = 0.0; prm.a_tol = 0.0; prm.max_iter = 1; prm.two_norm = 1; prm.rel_change = 0; prm.recompute_residual = 0; prm.precond = 0;
+    int its = 0;
+    double rel = 0;
+    const int rc = b200_pcg_solve_ex(h, L.Apar, nullptr, &prm, f, u, &its, &rel, nullptr);
+    if (rc) {      // an iterate that is already exact stops the inner recurrence ("Zero sdotp" / "Subnormal gamma": the reference
+      const std::string msg = b200_last_error();          // flags it and carries on with u as it is, pcg.c:516-521, :680-690)
+      if (msg.find("sdotp") != std::string::npos || msg.find("gamma") != std::string::npos) return 0;
+    }
+    return rc;
+  }
   return b200_gs_relax(h, L.A->gs, L.A, type, zero, f, L.l1, u);
 }
 
@@ -451,7 +532,7 @@ static int amg_cycle_gs(b200_handle h, b200_amg amg, const double *f, double *u,
   for (int l = 1; l < nl; l++) { F[l] = amg->lv[l].F; U[l] = amg->lv[l].U; }
   for (int l = 0; l < nl - 1; l++) {
     b200_level &L = amg->lv[l];
-    B200_TRY(gs_relax(h, L, amg->relax_down, F[l], U[l], l > 0 || u_zero));
+    B200_TRY(gs_relax(h, amg, L, amg->relax_down, F[l], U[l], l > 0 || u_zero, 1));
     B200_TRY(b200_csr_spmv_epi(h, L.As, U[l], amg->Vtemp, 0, -1.0, 1.0, F[l], nullptr));             // :549
     B200_TRY(b200_csr_spmv_epi(h, L.R, amg->Vtemp, amg->lv[l + 1].F, 0, 1.0, 0.0, nullptr, nullptr)); // :566
   }
@@ -461,13 +542,13 @@ static int amg_cycle_gs(b200_handle h, b200_amg amg, const double *f, double *u,
       gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, F[nl - 1], U[nl - 1]);
       B200_LAUNCH_CHECK();
     } else {
-      B200_TRY(gs_relax(h, L, amg->relax_down, F[nl - 1], U[nl - 1], nl > 1 || u_zero));
+      B200_TRY(gs_relax(h, amg, L, amg->relax_down, F[nl - 1], U[nl - 1], nl > 1 || u_zero, 3));
     }
   }
   for (int l = nl - 2; l >= 0; l--) {
     b200_level &L = amg->lv[l];
     B200_TRY(b200_csr_spmv_epi(h, L.P, U[l + 1], U[l], 0, 1.0, 1.0, U[l], nullptr));                 // :602
-    B200_TRY(gs_relax(h, L, amg->relax_up, F[l], U[l], false));
+    B200_TRY(gs_relax(h, amg, L, amg->relax_up, F[l], U[l], false, 2));
   }
   return 0;
 }
@@ -496,7 +577,7 @@ static int amg_cycle_general(b200_handle h, b200_amg amg, const double *f, doubl
         gselim_kernel<<<1, 32, 0, h->stream>>>(amg->ge_n, amg->ge_A, amg->ge_A + (size_t)amg->ge_n * amg->ge_n, F[level], U[level]);
         B200_LAUNCH_CHECK();
       } else if (amg->gs) {
-        B200_TRY(gs_relax(h, L, type, F[level], U[level], zero[level] != 0));
+        B200_TRY(gs_relax(h, amg, L, type, F[level], U[level], zero[level] != 0, cycle_param));
       } else if (zero[level]) {
         jacobi_zero_kernel<<<vgrid(h, L.n), 256, 0, h->stream>>>((size_t)L.n, w, F[level], L.l1, U[level]);
         B200_LAUNCH_CHECK();

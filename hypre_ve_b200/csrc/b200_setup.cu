@@ -617,6 +617,21 @@ __global__ void l1_kernel(int n, int size, int rest, const int *__restrict__ A_i
   l1[i] = v;
 }
 
+// option 1 restricted to the entries whose column carries the row's own C/F marker: what hypre_ParCSRComputeL1Norms builds when
+// the cycle relaxes in C/F order (relax_order 1, par_amg_setup.c:3047-3050; hypre_CSRMatrixComputeRowSum with CF_i / CF_j,
+// csr_matop.c:1326-1352; the threaded variant ams.c:3495-3507 sums the same entries in the same order)
+__global__ void l1_cf_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
+                             const int *__restrict__ cf, double *__restrict__ l1) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cf[i];
+  double v = 0.0;
+  for (int j = A_i[i]; j < A_i[i + 1]; j++)
+    if (cf[A_j[j]] == c) v += 1.0 * fabs(A_a[j]);
+  if (A_i[i] < A_i[i + 1] && A_a[A_i[i]] < 0.0) v = -v;
+  l1[i] = v;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
@@ -1037,6 +1052,14 @@ extern "C" int b200_l1_norms_blocks(b200_handle h, b200_csr A, int option, int b
   if (A->nrows == 0) return 0;
   const int size = A->nrows / blocks, rest = A->nrows - size * blocks;
   l1_kernel<<<b200_grid(A->nrows, TB), TB, 0, h->stream>>>(A->nrows, size, rest, A->i, A->j, A->a, option, d_l1);
+  B200_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int b200_l1_norms_cf(b200_handle h, b200_csr A, const int *d_cf, double *d_l1) {
+  if (!A || !A->a || !d_cf) B200_FAIL("l1_norms_cf: matrix with values and a C/F marker required");
+  if (A->nrows == 0) return 0;
+  l1_cf_kernel<<<b200_grid(A->nrows, 256), 256, 0, h->stream>>>(A->nrows, A->i, A->j, A->a, d_cf, d_l1);
   B200_LAUNCH_CHECK();
   return 0;
 }

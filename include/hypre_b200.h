@@ -205,6 +205,9 @@ int b200_l1_norms(b200_handle h, b200_csr A, int option, double *d_l1);
 /* the same with the reference's thread blocks (hypre_ParCSRComputeL1NormsThreads, ams.c:3398-3650): option 4
  * adds half of every entry that lies outside the Gauss-Seidel block of its row */
 int b200_l1_norms_blocks(b200_handle h, b200_csr A, int option, int blocks, double *d_l1);
+/* option 1 with a C/F marker: only the entries whose column carries the row's own marker are summed -- the l1 norms of a
+ * cycle that relaxes in C/F order (relax_order 1: par_amg_setup.c:3047-3050, hypre_CSRMatrixComputeRowSum csr_matop.c:1326-1352) */
+int b200_l1_norms_cf(b200_handle h, b200_csr A, const int *d_cf, double *d_l1);
 
 /* hypre_BoomerAMGRelax (par_relax.c:30-5264) for the hybrid Gauss-Seidel family on one rank, relax_points 0,
  * relax_weight = omega = 1: types 3 / 4 / 6 (forward / backward / symmetric, u_i = res / a_ii) and the l1

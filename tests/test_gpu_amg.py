@@ -216,7 +216,7 @@ def test_vcycle_matches_reference_preconditioner(handle):
 def test_unsupported_configurations_fail_loudly(handle):
     import hypre_ve_b200 as hb
     A = hb.ParCsr.laplacian(handle, 8, 8, 8)
-    for k, v in [("CoarsenType", 6), ("InterpType", 0), ("RelaxType", 15), ("AggNumLevels", -1), ("RAP2", 1)]:
+    for k, v in [("CoarsenType", 6), ("InterpType", 0), ("RelaxType", 5), ("AggNumLevels", -1), ("RAP2", 1)]:
         amg = hb.Amg(handle)
         amg.set(k, v)
         with pytest.raises(hb.B200Error):

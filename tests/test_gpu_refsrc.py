@@ -51,6 +51,11 @@ def test_the_binaries_bind_the_hot_path_to_this_library():
     ["-n", 26, 26, 26, "-solver", 0, "-pmis", "-rlx", 18],                   # BoomerAMG alone
     ["-n", 22, 21, 20, "-solver", 2],                                        # diagonally scaled PCG
     ["-n", 18, 18, 18, "-difconv", "-a", 3, -2, 1, "-atype", 3, "-solver", 3, "-pmis", "-rlx", 18],   # AMG-GMRES, nonsymmetric
+    ["-n", 21, 20, 19, "-solver", 1, "-pmis", "-rlx", 18, "-CF", 1],         # l1-Jacobi in C/F order (relax_order 1)
+    ["-n", 21, 20, 19, "-solver", 1, "-pmis", "-rlx", 17],                   # FCF-Jacobi
+    ["-n", 16, 15, 14, "-27pt", "-solver", 1, "-pmis", "-rlx", 17, "-w", 0.8],
+    ["-n", 21, 20, 19, "-solver", 1, "-pmis", "-rlx", 15],                   # CG smoother
+    ["-n", 20, 20, 20, "-solver", 0, "-pmis", "-rlx", 18, "-CF", 1],         # BoomerAMG alone, C/F l1-Jacobi
 ])
 def test_unmodified_reference_driver_on_this_library(flags):
     """src/test/ij.c, unmodified, linked against libhypre_b200.so: same iteration count and final residual as the same
