@@ -178,6 +178,11 @@ __global__ void scale_copy_kernel(int n, double beta, const double *__restrict__
 }  // namespace
 
 bool b200_spmv_pipe_ok(b200_csr A);
+bool b200_spmv_dict_ok(b200_csr A);
+int b200_csr_build_dict(b200_handle h, b200_csr A);
+int b200_csr_drop_dict(b200_handle h, b200_csr A);
+int b200_csr_spmv_dict(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha, double beta,
+                       const double *b, const double *d);
 int b200_csr_spmv_pipe(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha, double beta,
                        const double *b, const double *d);
 
@@ -186,6 +191,7 @@ int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int
   if (A->nrows == 0) return 0;
   if (!A->blk_row) B200_TRY(b200_csr_build_plan(h, A));
   static const bool force_v1 = [] { const char *e = getenv("B200_SPMV_TWO_PHASE"); return e && e[0] == '1'; }();
+  if (!force_v1 && b200_spmv_dict_ok(A)) return b200_csr_spmv_dict(h, A, x, y, mode, alpha, beta, b, d);
   if (!force_v1 && b200_spmv_pipe_ok(A)) return b200_csr_spmv_pipe(h, A, x, y, mode, alpha, beta, b, d);
   Epi e{mode, alpha, beta, b, d};
   switch (A->group) {
@@ -209,6 +215,7 @@ int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data,
 }
 
 int b200_csr_build_plan(b200_handle h, b200_csr A) {
+  B200_TRY(b200_csr_drop_dict(h, A));
   if (A->blk_row) { B200_TRY(b200_dfree(h, A->blk_row)); A->blk_row = nullptr; }
   if (A->blk_ent) { B200_TRY(b200_dfree(h, A->blk_ent)); A->blk_ent = nullptr; }
   if (A->blk_meta) { B200_TRY(b200_dfree(h, A->blk_meta)); A->blk_meta = nullptr; }
@@ -278,6 +285,7 @@ int b200_csr_build_plan(b200_handle h, b200_csr A) {
     B200_CUDA(cudaStreamSynchronize(h->stream));
     B200_TRY(b200_dfree(h, d_max));
   }
+  B200_TRY(b200_csr_build_dict(h, A));       // stencil-structured operators: codes instead of columns / values (b200_spmv_dict.cu)
   return 0;
 }
 
@@ -323,6 +331,7 @@ extern "C" int b200_csr_destroy(b200_handle h, b200_csr A) {
   B200_TRY(b200_dfree(h, A->blk_row));
   B200_TRY(b200_dfree(h, A->blk_ent));
   B200_TRY(b200_dfree(h, A->blk_meta));
+  B200_TRY(b200_csr_drop_dict(h, A));
   B200_TRY(b200_gs_plan_destroy(h, A->gs));
   if (A->T) B200_TRY(b200_csr_destroy(h, A->T));
   delete A;

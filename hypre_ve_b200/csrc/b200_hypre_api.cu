@@ -400,6 +400,7 @@ HYPRE_Int HYPRE_IJVectorAddToValues(HYPRE_IJVector v, HYPRE_Int nvalues, const H
   if (nvalues < 0) return err_arg(2);
   if (!values) return err_arg(4);
   if (!v->initialized) return err_arg(1);
+  if (ijvec_refresh_mirror(v)) return g_error_flag;                     // a solve may have written the device copy since
   for (int k = 0; k < nvalues; k++) {
     const int g = indices ? indices[k] : v->jlower + k;
     if (g < v->jlower || g > v->jupper) continue;

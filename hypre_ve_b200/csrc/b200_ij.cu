@@ -314,6 +314,8 @@ extern "C" int b200_ij_assemble(b200_handle h, b200_ij ij, b200_parcsr *A_out, i
     B200_TRY(b200_dfree(h, miss));
     if (n_missing_out) *n_missing_out = hm;
     if (D->T) { B200_TRY(b200_csr_destroy(h, D->T)); D->T = nullptr; }      // cached transpose holds the old values
+    B200_TRY(b200_csr_drop_dict(h, D));                                     // and so does the dictionary-compressed solve copy
+    B200_TRY(b200_csr_build_dict(h, D));
   }
   b200_dfree(h, col_s); b200_dfree(h, blk_s); b200_dfree(h, val_s); b200_dfree(h, ptr);
   release_log(h, ij);

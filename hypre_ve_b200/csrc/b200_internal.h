@@ -50,6 +50,11 @@ struct b200_csr_s {
   int  group = 1;         // threads cooperating on one row in the reduce phase
   int  max_row = 0;
   int  tile = 0;          // entries per tile the plan was cut with
+  // dictionary-compressed solve copy (b200_spmv_dict.cu): one byte per entry instead of the column / the value
+  unsigned char *jc = nullptr, *ac = nullptr;   // [nnz (+pad)] codes into off_tab (column - row) / val_tab
+  int *off_tab = nullptr;                       // [256]
+  double *val_tab = nullptr;                    // [256]
+  int  dict_state = 0;    // 0: not looked at, 1: at least one dictionary exists, -1: none applies
   b200_gs_plan_s *gs = nullptr;   // built on first use by b200_relax_gs / the AMG setup
   b200_csr_s *T = nullptr;        // explicit transpose, built on first b200_csr_matvecT (diagT/offdT of the reference)
 };
@@ -130,6 +135,8 @@ static inline int b200_grid(size_t n, int block) { return (int)((n + block - 1) 
 
 // internal cross-file entry points
 int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data, b200_csr *A);
+int b200_csr_build_dict(b200_handle h, b200_csr A);     // b200_spmv_dict.cu; called by b200_csr_build_plan
+int b200_csr_drop_dict(b200_handle h, b200_csr A);      // after the values of A changed in place
 int b200_csr_build_plan(b200_handle h, b200_csr A);
 int b200_exclusive_scan_inplace(b200_handle h, int *d_data, size_t n);   // d_data[n] entries, in place
 int b200_gs_plan_create(b200_handle h, b200_csr A, int blocks, b200_gs_plan_s **out);
