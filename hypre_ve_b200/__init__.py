@@ -45,6 +45,8 @@ SIGNATURES = {
     "b200_csr_create_from_host": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, C.POINTER(_vp)]),
     "b200_csr_destroy": (_i, [_vp, _vp]),
     "b200_csr_dims": (_i, [_vp, _ip, _ip, _ip]),
+    "b200_csr_stream_bytes_per_entry": (_i, [_vp]),
+    "b200_dist_matrix_stream_bytes_per_entry": (_i, [_vp]),
     "b200_csr_download": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "b200_csr_matvec": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
     "b200_csr_matvecT": (_i, [_vp, _d, _vp, _vp, _d, _vp, _vp]),
@@ -236,6 +238,11 @@ class Csr:
         a, b, c = _i(), _i(), _i()
         _chk(_lib.b200_csr_dims(self.p, C.byref(a), C.byref(b), C.byref(c)))
         return a.value, b.value, c.value
+
+    @property
+    def stream_bytes_per_entry(self):
+        """12 (int32 column + FP64 value) or 9 / 5 / 2 with the dictionary-compressed solve copy"""
+        return _lib.b200_csr_stream_bytes_per_entry(self.p)
 
     def download(self, with_data=True):
         n, _, nnz = self.dims
@@ -712,6 +719,10 @@ class DistMatrix:
 
     def __init__(self, handle, comm, p, owned=True):
         self.h, self.c, self.p, self.owned = handle, comm, p, owned
+
+    @property
+    def stream_bytes_per_entry(self):
+        return _lib.b200_dist_matrix_stream_bytes_per_entry(self.p)
 
     @classmethod
     def laplacian(cls, handle, comm, nx, ny, nz, P, Q, R, stencil=7, c=(1.0, 1.0, 1.0)):

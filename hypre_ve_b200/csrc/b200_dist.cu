@@ -95,20 +95,6 @@ __global__ void pack_rows_kernel(int n, const int *__restrict__ idx, const int *
   for (int t = 0; t < len; t++) { bj[d + t] = A_j[s + t]; if (ba) ba[d + t] = A_a[s + t]; }
 }
 // ghost candidates: columns outside the owned range
-__global__ void flag_ghost_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, int *__restrict__ flag) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k > nnz) return;
-  if (k == nnz) { flag[nnz] = 0; return; }
-  const int c = j[k];
-  flag[k] = (c < first || c >= first + n_owned) ? 1 : 0;
-}
-__global__ void scatter_ghost_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, const int *__restrict__ pos,
-                                     int *__restrict__ out) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= nnz) return;
-  const int c = j[k];
-  if (c < first || c >= first + n_owned) out[pos[k]] = c;
-}
 // global -> extended local: owned -> c - first ; ghost -> n_owned + rank in the sorted ghost list
 __global__ void localize_kernel(int nnz, const int *__restrict__ jg, int first, int n_owned, int ng,
                                 const int *__restrict__ ghost, int *__restrict__ jl) {
@@ -233,6 +219,17 @@ inline int vgrid(b200_handle h, size_t n) {
   return (int)(g < cap ? (g ? g : 1) : cap);
 }
 
+// B200_TRACE2=1: stream-synchronised wall-clock time between consecutive calls on this thread, on stderr (setup diagnosis)
+void tr(b200_handle h, const char *tag) {
+  static const bool on = getenv("B200_TRACE2") != nullptr;
+  if (!on) return;
+  static thread_local double last = 0;
+  cudaStreamSynchronize(h->stream);
+  const double t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+  if (tag) fprintf(stderr, "[b200 tr2] dev %d %-28s %8.3f ms\n", h->device, tag, t - last);
+  last = t;
+}
+
 int sort_unique(b200_handle h, int *d_keys, int n, int **out, int *n_out) {
   *out = nullptr; *n_out = 0;
   if (n == 0) return 0;
@@ -259,27 +256,61 @@ int sort_unique(b200_handle h, int *d_keys, int n, int **out, int *n_out) {
   return 0;
 }
 
+// ids outside [first, first + n_owned): counted, then appended (any order: the list is sorted afterwards), one atomic per warp.
+// Two read-only passes over the column array instead of flag + scan + scatter over nnz-sized scratch.
+__global__ void ghost_count_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, int *__restrict__ count) {
+  const int stride = gridDim.x * blockDim.x;
+  int mine = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+    const int c = j[k];
+    mine += (c < first || c >= first + n_owned) ? 1 : 0;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, off);
+  if ((threadIdx.x & 31) == 0 && mine) atomicAdd(count, mine);
+}
+__global__ void ghost_append_kernel(int nnz, const int *__restrict__ j, int first, int n_owned, int *__restrict__ cursor,
+                                    int *__restrict__ out) {
+  const int stride = gridDim.x * blockDim.x;
+  const int lane = threadIdx.x & 31;
+  const int trips = (nnz + stride - 1) / stride;
+  for (int t = 0; t < trips; t++) {
+    const int k = t * stride + blockIdx.x * blockDim.x + threadIdx.x;
+    int c = 0;
+    bool g = false;
+    if (k < nnz) { c = j[k]; g = (c < first || c >= first + n_owned); }
+    const unsigned m = __ballot_sync(0xffffffffu, g);
+    if (m) {
+      int base = 0;
+      if (lane == __ffs(m) - 1) base = atomicAdd(cursor, __popc(m));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+      if (g) out[base + __popc(m & ((1u << lane) - 1u))] = c;
+    }
+  }
+}
 // sorted unique list of the column ids of G that fall outside [first, first + n_owned)
 int ghost_columns(b200_handle h, const int *d_j, int nnz, int first, int n_owned, int **ghost, int *ng) {
   *ghost = nullptr; *ng = 0;
   if (nnz == 0) return 0;
-  int *pos = nullptr;
-  B200_TRY(b200_dalloc<int>(h, &pos, (size_t)nnz + 1));
-  flag_ghost_kernel<<<b200_grid((size_t)nnz + 1, 256), 256, 0, h->stream>>>(nnz, d_j, first, n_owned, pos);
+  int *cnt = nullptr;
+  B200_TRY(b200_dalloc<int>(h, &cnt, 2));
+  B200_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * 2, h->stream));
+  const int want = b200_grid(nnz, 256), cap = h->num_sm * 8;
+  const int grid = want < cap ? want : cap;
+  ghost_count_kernel<<<grid, 256, 0, h->stream>>>(nnz, d_j, first, n_owned, cnt);
   B200_LAUNCH_CHECK();
-  B200_TRY(b200_exclusive_scan_inplace(h, pos, (size_t)nnz + 1));
   int m = 0;
-  B200_CUDA(cudaMemcpyAsync(&m, pos + nnz, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  B200_CUDA(cudaMemcpyAsync(&m, cnt, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
   if (m) {
     int *cand = nullptr;
     B200_TRY(b200_dalloc<int>(h, &cand, m));
-    scatter_ghost_kernel<<<b200_grid(nnz, 256), 256, 0, h->stream>>>(nnz, d_j, first, n_owned, pos, cand);
+    ghost_append_kernel<<<grid, 256, 0, h->stream>>>(nnz, d_j, first, n_owned, cnt + 1, cand);
     B200_LAUNCH_CHECK();
     B200_TRY(sort_unique(h, cand, m, ghost, ng));
     B200_TRY(b200_dfree(h, cand));
   }
-  B200_TRY(b200_dfree(h, pos));
+  B200_TRY(b200_dfree(h, cnt));
   return 0;
 }
 
@@ -551,6 +582,7 @@ int b200_halo_reverse_clear_i32(b200_handle h, b200_comm c, b200_halo_s *p, cons
 static int fetch_rows(b200_handle h, b200_comm c, b200_halo_s *p, b200_csr M, b200_csr *out) {
   const int R = b200_comm_size(c);
   const bool with_data = M->a != nullptr;
+  tr(h, nullptr);
   // owner side: lengths and packed entries of the requested rows
   int *slen = nullptr;
   B200_TRY(b200_dalloc<int>(h, &slen, (size_t)p->n_send + 1));
@@ -608,6 +640,7 @@ static int fetch_rows(b200_handle h, b200_comm c, b200_halo_s *p, b200_csr M, b2
   }
   B200_TRY(b200_dfree(h, slen)); B200_TRY(b200_dfree(h, glen)); B200_TRY(b200_dfree(h, bj)); B200_TRY(b200_dfree(h, ba));
   *out = E;
+  tr(h, "  fetch_rows");
   return 0;
 }
 
@@ -620,6 +653,36 @@ static int stack_rows(b200_handle h, b200_csr top, b200_csr bot, b200_csr *out) 
   concat_rowptr_kernel<<<b200_grid(m, 256), 256, 0, h->stream>>>(top->nrows, top->i, bot->nrows, bot->i, S->i);
   B200_LAUNCH_CHECK();
   if (top->nnz) B200_CUDA(cudaMemcpyAsync(S->j, top->j, sizeof(int) * (size_t)top->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  if (bot->nnz) B200_CUDA(cudaMemcpyAsync(S->j + top->nnz, bot->j, sizeof(int) * (size_t)bot->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  if (with_data) {
+    if (top->nnz) B200_CUDA(cudaMemcpyAsync(S->a, top->a, sizeof(double) * (size_t)top->nnz, cudaMemcpyDeviceToDevice, h->stream));
+    if (bot->nnz) B200_CUDA(cudaMemcpyAsync(S->a + top->nnz, bot->a, sizeof(double) * (size_t)bot->nnz, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  *out = S;
+  return 0;
+}
+
+// rows of `top` (columns in [owned | ghosts of the first ring], the localized form) with the ghost columns renumbered through
+// pos[] (their position in a larger extended index space), then the rows of `bot` (already in that space)
+namespace {
+__global__ void remap_cols_kernel(int nnz, const int *__restrict__ jl, int n_owned, const int *__restrict__ pos, int *__restrict__ out) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  const int c = jl[k];
+  out[k] = c < n_owned ? c : pos[c - n_owned];
+}
+}  // namespace
+static int stack_rows_remap(b200_handle h, b200_csr top, int n_owned, const int *d_pos, b200_csr bot, int ncols, b200_csr *out) {
+  const bool with_data = top->a != nullptr;
+  b200_csr S = nullptr;
+  B200_TRY(b200_csr_alloc(h, top->nrows + bot->nrows, ncols, top->nnz + bot->nnz, with_data, &S));
+  const int m = std::max(top->nrows, bot->nrows) + 1;
+  concat_rowptr_kernel<<<b200_grid(m, 256), 256, 0, h->stream>>>(top->nrows, top->i, bot->nrows, bot->i, S->i);
+  B200_LAUNCH_CHECK();
+  if (top->nnz) {
+    remap_cols_kernel<<<b200_grid(top->nnz, 256), 256, 0, h->stream>>>(top->nnz, top->j, n_owned, d_pos, S->j);
+    B200_LAUNCH_CHECK();
+  }
   if (bot->nnz) B200_CUDA(cudaMemcpyAsync(S->j + top->nnz, bot->j, sizeof(int) * (size_t)bot->nnz, cudaMemcpyDeviceToDevice, h->stream));
   if (with_data) {
     if (top->nnz) B200_CUDA(cudaMemcpyAsync(S->a, top->a, sizeof(double) * (size_t)top->nnz, cudaMemcpyDeviceToDevice, h->stream));
@@ -670,13 +733,32 @@ static int localize_copy(b200_handle h, b200_csr M, b200_halo_s *p, int first, i
   return 0;
 }
 
-// builds M->L and M->halo from M->G
-static int dist_localize(b200_handle h, b200_comm c, b200_dist_matrix M) {
+// builds M->L and M->halo from M->G.  plan = false: no SpMV plan (an operand of a product only).  consume = true: the columns
+// are localized in place and M->G is gone afterwards (nobody fetches rows of this matrix by global id any more; download and
+// info rebuild the global ids from the localized form) -- saves a copy of the whole matrix.
+static int dist_localize(b200_handle h, b200_comm c, b200_dist_matrix M, bool plan = true, bool consume = false) {
   int *ghost = nullptr, ng = 0;
+  tr(h, nullptr);
   B200_TRY(ghost_columns(h, M->G->j, M->G->nnz, M->first_col, M->n_owned_cols, &ghost, &ng));
+  tr(h, "  localize: ghost_columns");
   if (!ghost) B200_TRY(b200_dalloc<int>(h, &ghost, 1));
   B200_TRY(b200_halo_build(h, c, M->col_starts, ghost, ng, &M->halo));
-  B200_TRY(localize_copy(h, M->G, M->halo, M->first_col, M->n_owned_cols, true, &M->L));
+  tr(h, "  localize: halo_build");
+  if (consume) {
+    b200_csr G = M->G;
+    if (G->nnz) {
+      localize_kernel<<<b200_grid(G->nnz, 256), 256, 0, h->stream>>>(G->nnz, G->j, M->first_col, M->n_owned_cols, M->halo->ng,
+                                                                    M->halo->d_ghost_gid, G->j);
+      B200_LAUNCH_CHECK();
+    }
+    G->ncols = M->n_owned_cols + M->halo->ng;
+    if (plan && G->a) B200_TRY(b200_csr_build_plan(h, G));
+    M->L = G;
+    M->G = nullptr;
+  } else {
+    B200_TRY(localize_copy(h, M->G, M->halo, M->first_col, M->n_owned_cols, plan, &M->L));
+  }
+  tr(h, "  localize: copy+plan");
   return 0;
 }
 
@@ -817,6 +899,9 @@ extern "C" int b200_dist_generate_difconv(b200_handle h, b200_comm c, int nx, in
   return dist_generate(h, c, nx, ny, nz, P, Q, R, 70, values, out);
 }
 
+extern "C" int b200_csr_stream_bytes_per_entry(b200_csr A);
+extern "C" int b200_dist_matrix_stream_bytes_per_entry(b200_dist_matrix A) { return (A && A->L) ? b200_csr_stream_bytes_per_entry(A->L) : 0; }
+
 extern "C" int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix M) {
   if (!M) return 0;
   B200_TRY(b200_csr_destroy(h, M->G));
@@ -934,6 +1019,7 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
   const int R = b200_comm_size(c), me = b200_comm_rank(c);
   const int nnz = P->G->nnz, n = P->n;
   const int nc = coarse_starts[me + 1] - coarse_starts[me], cfirst = coarse_starts[me];
+  tr(h, nullptr);
   // owner of every entry's column; stable sort by owner keeps the (row, entry) order inside a bucket
   int *owner = nullptr, *rows = nullptr, *idx = nullptr, *owner_s = nullptr, *perm = nullptr, *d_starts = nullptr;
   B200_TRY(b200_dalloc<int>(h, &owner, nnz)); B200_TRY(b200_dalloc<int>(h, &rows, nnz)); B200_TRY(b200_dalloc<int>(h, &idx, nnz));
@@ -965,6 +1051,7 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
     ++g_b200_launches;
     B200_TRY(b200_dfree(h, tmp));
   }
+  tr(h, " T: owner+sort");
   std::vector<int> scnt(R + 1, 0);
   B200_CUDA(cudaMemcpyAsync(scnt.data(), cntr, sizeof(int) * R, cudaMemcpyDeviceToHost, h->stream));
   B200_CUDA(cudaStreamSynchronize(h->stream));
@@ -996,6 +1083,7 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
     }
     B200_TRY(b200_comm_exchange(h, c, sends, recvs));
   }
+  tr(h, " T: bucket+exchange");
   // received triplets are ordered by ascending fine row (rank blocks ascend); stable sort by local coarse column
   b200_csr T = nullptr;
   B200_TRY(b200_csr_alloc(h, nc, P->global_rows, m, true, &T));
@@ -1027,6 +1115,7 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
                   (void *)s_col, (void *)s_val, (void *)r_row, (void *)r_col, (void *)r_val})
     B200_TRY(b200_dfree(h, q));
   *out = T;
+  tr(h, " T: sort by column");
   return 0;
 }
 
@@ -1222,6 +1311,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     int nring = 0;
     auto build_extended = [&]() -> int {
     // rows of A and S for the ghost nodes, then the second ring of ghost ids they mention
+    tr(h, nullptr);
     b200_csr Sg = nullptr;                          // S with global column ids (to serve fetches)
     B200_TRY(b200_csr_alloc(h, n, A->global_cols, S->nnz, false, &Sg));
     B200_CUDA(cudaMemcpyAsync(Sg->i, S->i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
@@ -1231,6 +1321,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_LAUNCH_CHECK();
     }
     b200_csr Aext = nullptr, Sext = nullptr;
+    tr(h, " ext: globalize S");
     B200_TRY(fetch_rows(h, c, A->halo, A->G, &Aext));
     B200_TRY(fetch_rows(h, c, A->halo, Sg, &Sext));
     B200_TRY(b200_csr_destroy(h, Sg));
@@ -1248,7 +1339,9 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_dfree(h, cand));
       if (!ring) B200_TRY(b200_dalloc<int>(h, &ring, 1));
     }
+    tr(h, " ext: ring ids");
     B200_TRY(b200_halo_build(h, c, A->col_starts, ring, nring, &plan2));
+    tr(h, " ext: halo_build plan2");
     // Extended operators: rows [owned | U], columns [owned | U].  The row kernels address neighbour
     // ROWS by column id, so every id of U needs a row slot; only the first ring has entries (second-ring
     // rows are never dereferenced: the kernels visit rows of strong neighbours of owned rows only).
@@ -1261,28 +1354,24 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
                                                                plan2->d_ghost_gid, pos);
       B200_LAUNCH_CHECK();
     }
-    b200_csr AextU = nullptr, SextU = nullptr, Abig_g = nullptr, Sbig_g = nullptr;
+    // Only the fetched ghost rows carry global ids: they are localized against the new plan; the rank's own rows are taken
+    // from the localized operator (and from S, which was built on it) with their first-ring ghost columns renumbered
+    // through pos[] -- one pass over A and one over S instead of stacking the global forms and searching every column again.
+    b200_csr AextU = nullptr, SextU = nullptr, AextL = nullptr, SextL = nullptr;
     B200_TRY(spread_rows(h, Aext, pos, A->n_owned_cols, nring, &AextU));
     B200_TRY(spread_rows(h, Sext, pos, A->n_owned_cols, nring, &SextU));
-    B200_TRY(b200_dfree(h, pos));
     B200_TRY(b200_csr_destroy(h, Aext)); B200_TRY(b200_csr_destroy(h, Sext));
-    B200_TRY(stack_rows(h, A->G, AextU, &Abig_g));
-    {
-      b200_csr Sg2 = nullptr;                       // local S rows in global ids
-      B200_TRY(b200_csr_alloc(h, n, A->global_cols, S->nnz, false, &Sg2));
-      B200_CUDA(cudaMemcpyAsync(Sg2->i, S->i, sizeof(int) * ((size_t)n + 1), cudaMemcpyDeviceToDevice, h->stream));
-      if (S->nnz) {
-        globalize_kernel<<<b200_grid(S->nnz, 256), 256, 0, h->stream>>>(S->nnz, S->j, A->first_col, A->n_owned_cols,
-                                                                      A->halo->d_ghost_gid, Sg2->j);
-        B200_LAUNCH_CHECK();
-      }
-      B200_TRY(stack_rows(h, Sg2, SextU, &Sbig_g));
-      B200_TRY(b200_csr_destroy(h, Sg2));
-    }
+    tr(h, " ext: spread");
+    B200_TRY(localize_copy(h, AextU, plan2, A->first_col, A->n_owned_cols, false, &AextL));
+    B200_TRY(localize_copy(h, SextU, plan2, A->first_col, A->n_owned_cols, false, &SextL));
     B200_TRY(b200_csr_destroy(h, AextU)); B200_TRY(b200_csr_destroy(h, SextU));
-    B200_TRY(localize_copy(h, Abig_g, plan2, A->first_col, A->n_owned_cols, false, &Abig2));
-    B200_TRY(localize_copy(h, Sbig_g, plan2, A->first_col, A->n_owned_cols, false, &Sbig2));
-    B200_TRY(b200_csr_destroy(h, Abig_g)); B200_TRY(b200_csr_destroy(h, Sbig_g));
+    tr(h, " ext: localize ghost rows");
+    B200_TRY(stack_rows_remap(h, A->L, A->n_owned_cols, pos, AextL, A->n_owned_cols + nring, &Abig2));
+    tr(h, " ext: stack A");
+    B200_TRY(stack_rows_remap(h, S, A->n_owned_cols, pos, SextL, A->n_owned_cols + nring, &Sbig2));
+    tr(h, " ext: stack S");
+    B200_TRY(b200_csr_destroy(h, AextL)); B200_TRY(b200_csr_destroy(h, SextL));
+    B200_TRY(b200_dfree(h, pos));
       return 0;
     };
     auto extend_markers = [&](const int *cfv, const int *f2cv, int **cf_big_out, int **f2c_big_out) -> int {
@@ -1384,7 +1473,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_csr_destroy(h, Pext));
       B200_TRY(b200_csr_multiply_ex(h, A->L, Pbig, 0, 0, (int)coarse_size, &Qg));
       B200_TRY(b200_csr_destroy(h, Pbig));
-      B200_TRY(dist_localize(h, c, L.R));                         // ghosts of R = remote fine rows
+      B200_TRY(dist_localize(h, c, L.R, true, true));             // ghosts of R = remote fine rows; nobody fetches rows of R
       b200_csr Qext = nullptr, Qbig = nullptr;
       B200_TRY(fetch_rows(h, c, L.R->halo, Qg, &Qext));
       B200_TRY(stack_rows(h, Qg, Qext, &Qbig));
@@ -1394,7 +1483,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
     } else {
       // the library default, hypre_BoomerAMGBuildCoarseOperatorKT (par_rap.c): row ic of R*A first, then times P with
       // the diagonal entry created first -- (R*A)*P, rows of A and P fetched from their owners in global entry order
-      B200_TRY(dist_localize(h, c, L.R));
+      B200_TRY(dist_localize(h, c, L.R, true, true));
       b200_csr Aext = nullptr, Abig = nullptr, RAg = nullptr;
       B200_TRY(fetch_rows(h, c, L.R->halo, A->G, &Aext));
       B200_TRY(stack_rows(h, A->G, Aext, &Abig));
@@ -1405,7 +1494,7 @@ extern "C" int b200_dist_amg_setup(b200_handle h, b200_comm c, b200_amg prm, b20
       B200_TRY(b200_csr_destroy(h, Abig));
       b200_dist_matrix RAd = new_dist(nc, cstarts[me], (int)coarse_size, cstarts, A->first_col, A->n_owned_cols, A->global_cols,
                                       A->col_starts, RAg);
-      B200_TRY(dist_localize(h, c, RAd));
+      B200_TRY(dist_localize(h, c, RAd, false, true));          // operand of the next product only: no plan, in place
       b200_csr Pext = nullptr, Pbig = nullptr;
       B200_TRY(fetch_rows(h, c, RAd->halo, Pg, &Pext));
       B200_TRY(stack_rows(h, Pg, Pext, &Pbig));

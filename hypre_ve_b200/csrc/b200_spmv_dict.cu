@@ -404,6 +404,12 @@ int b200_csr_build_dict(b200_handle h, b200_csr A) {
   return 0;
 }
 
+extern "C" int b200_csr_stream_bytes_per_entry(b200_csr A) {
+  if (!A) return 0;
+  if (A->dict_state != 1) return 12;
+  return (A->jc ? 1 : 4) + (A->ac ? 1 : 8);
+}
+
 bool b200_spmv_dict_ok(b200_csr A) { return A->dict_state == 1 && (A->jc || A->ac); }
 
 int b200_csr_spmv_dict(b200_handle h, b200_csr A, const double *x, double *y, int mode, double alpha, double beta,

@@ -62,6 +62,10 @@ int b200_csr_create_from_host(b200_handle h, int nrows, int ncols, int nnz,
                               const int *h_i, const int *h_j, const double *h_a, b200_csr *A);
 int b200_csr_destroy(b200_handle h, b200_csr A);
 int b200_csr_dims(b200_csr A, int *nrows, int *ncols, int *nnz);
+/* bytes per entry the SpMV of A streams: 12 (int32 column + FP64 value), or 9 / 5 / 2 when the dictionary-compressed solve copy
+ * of a stencil-structured operator holds one byte in place of the column offset and / or the value (csrc/b200_spmv_dict.cu);
+ * same arithmetic as hypre_CSRMatrixMatvecOutOfPlace (seq_mv/csr_matvec.c:24-376), bit-identical results */
+int b200_csr_stream_bytes_per_entry(b200_csr A);
 int b200_csr_download(b200_handle h, b200_csr A, int *h_i, int *h_j, double *h_a);
 /* y = alpha*A*x + beta*b, x != y.   hypre_CSRMatrixMatvecOutOfPlace (seq_mv/csr_matvec.c:24-412),
  * device seam hypre_CSRMatrixMatvecDevice (seq_mv/csr_matvec_device.c:56-120). b may equal y. */
@@ -300,6 +304,8 @@ int b200_dist_matrix_create_from_host(b200_handle h, b200_comm c, int n_local, c
                                       const double *h_a, b200_dist_matrix *A);
 int b200_dist_matrix_create_from_ij(b200_handle h, b200_comm c, b200_ij ij, b200_dist_matrix *A);
 int b200_dist_matrix_destroy(b200_handle h, b200_dist_matrix A);
+/* b200_csr_stream_bytes_per_entry of this rank's localized block (the operand of hypre_ParCSRMatrixMatvec, par_csr_matvec.c:22-359) */
+int b200_dist_matrix_stream_bytes_per_entry(b200_dist_matrix A);
 int b200_dist_matrix_info(b200_dist_matrix A, int *local_rows, int *first_row, int *global_rows, int *local_nnz,
                           int *n_ghost, int *first_col, int *global_cols);
 /* local rows with GLOBAL column ids, entry order preserved (for parity tests) */
