@@ -625,18 +625,12 @@ static int fetch_rows(b200_handle h, b200_comm c, b200_halo_s *p, b200_csr M, b2
       const int rn = hg[p->recv_off[r + 1]] - hg[p->recv_off[r]], ro = hg[p->recv_off[r]];
       if (sn) sends.push_back({r, bj + so, sizeof(int) * (size_t)sn, 0});
       if (rn) recvs.push_back({r, E->j + ro, sizeof(int) * (size_t)rn, 0});
+      if (with_data) {                            // columns and values travel in ONE grouped exchange (second message per peer)
+        if (sn) sends.push_back({r, ba + so, sizeof(double) * (size_t)sn, 1});
+        if (rn) recvs.push_back({r, E->a + ro, sizeof(double) * (size_t)rn, 1});
+      }
     }
     B200_TRY(b200_comm_exchange(h, c, sends, recvs));
-    if (with_data) {
-      sends.clear(); recvs.clear();
-      for (int r = 0; r < R; r++) {
-        const int sn = hs[p->send_off[r + 1]] - hs[p->send_off[r]], so = hs[p->send_off[r]];
-        const int rn = hg[p->recv_off[r + 1]] - hg[p->recv_off[r]], ro = hg[p->recv_off[r]];
-        if (sn) sends.push_back({r, ba + so, sizeof(double) * (size_t)sn, 0});
-        if (rn) recvs.push_back({r, E->a + ro, sizeof(double) * (size_t)rn, 0});
-      }
-      B200_TRY(b200_comm_exchange(h, c, sends, recvs));
-    }
   }
   B200_TRY(b200_dfree(h, slen)); B200_TRY(b200_dfree(h, glen)); B200_TRY(b200_dfree(h, bj)); B200_TRY(b200_dfree(h, ba));
   *out = E;
@@ -1072,14 +1066,23 @@ static int dist_transpose(b200_handle h, b200_comm c, b200_dist_matrix P, const 
   int *r_row = nullptr, *r_col = nullptr;
   double *r_val = nullptr;
   B200_TRY(b200_dalloc<int>(h, &r_row, m)); B200_TRY(b200_dalloc<int>(h, &r_col, m)); B200_TRY(b200_dalloc<double>(h, &r_val, m));
-  for (int pass = 0; pass < 3; pass++) {
+  {
+    // the rank's own bucket (almost everything) is a device copy; rows, columns and values for the other ranks travel in ONE
+    // grouped exchange (three messages per peer)
     std::vector<b200_xfer> sends, recvs;
-    for (int r = 0; r < R; r++) {
-      const size_t es = pass == 2 ? sizeof(double) : sizeof(int);
-      char *sp = pass == 0 ? (char *)(s_row + soff[r]) : pass == 1 ? (char *)(s_col + soff[r]) : (char *)(s_val + soff[r]);
-      char *rp = pass == 0 ? (char *)(r_row + roff[r]) : pass == 1 ? (char *)(r_col + roff[r]) : (char *)(r_val + roff[r]);
-      if (scnt[r]) sends.push_back({r, sp, es * (size_t)scnt[r], 0});
-      if (rcnt[r]) recvs.push_back({r, rp, es * (size_t)rcnt[r], 0});
+    for (int pass = 0; pass < 3; pass++) {
+      for (int r = 0; r < R; r++) {
+        const size_t es = pass == 2 ? sizeof(double) : sizeof(int);
+        char *sp = pass == 0 ? (char *)(s_row + soff[r]) : pass == 1 ? (char *)(s_col + soff[r]) : (char *)(s_val + soff[r]);
+        char *rp = pass == 0 ? (char *)(r_row + roff[r]) : pass == 1 ? (char *)(r_col + roff[r]) : (char *)(r_val + roff[r]);
+        if (r == me) {
+          if (scnt[r] != rcnt[r]) B200_FAIL("transpose: own bucket size mismatch");
+          if (scnt[r]) B200_CUDA(cudaMemcpyAsync(rp, sp, es * (size_t)scnt[r], cudaMemcpyDeviceToDevice, h->stream));
+          continue;
+        }
+        if (scnt[r]) sends.push_back({r, sp, es * (size_t)scnt[r], pass});
+        if (rcnt[r]) recvs.push_back({r, rp, es * (size_t)rcnt[r], pass});
+      }
     }
     B200_TRY(b200_comm_exchange(h, c, sends, recvs));
   }
@@ -1181,7 +1184,9 @@ static int build_tail(b200_handle h, b200_comm c, b200_amg prm, b200_dist_amg am
   dist_level &L = amg->lv[level];
   b200_dist_matrix A = L.A;
   b200_csr full = nullptr;
+  tr(h, nullptr);
   B200_TRY(gather_csr(h, c, A, &full));
+  tr(h, " tail: gather_csr");
   b200_parcsr TA = new b200_parcsr_s();
   TA->global_rows = TA->global_cols = A->global_rows;
   TA->diag = full;
@@ -1197,7 +1202,9 @@ static int build_tail(b200_handle h, b200_comm c, b200_amg prm, b200_dist_amg am
   B200_TRY(b200_amg_set_int(amg->tail, "CoarsenType", 8));
   B200_TRY(b200_amg_set_int(amg->tail, "MaxIter", 1));
   B200_TRY(b200_amg_set_real(amg->tail, "Tol", 0.0));
+  tr(h, " tail: plan+params");
   B200_TRY(b200_amg_setup(h, amg->tail, TA));
+  tr(h, " tail: amg_setup");
   // gather plan for the right-hand side: every id this rank does not own is a "ghost"
   const int N = A->global_rows, n = A->n, first = A->first_row, ng = N - n;
   int *gid = nullptr;
@@ -1211,6 +1218,7 @@ static int build_tail(b200_handle h, b200_comm c, b200_amg prm, b200_dist_amg am
   B200_TRY(b200_dalloc<double>(h, &amg->tail_G, (size_t)ng + 8));
   B200_CUDA(cudaMemsetAsync(amg->tail_U, 0, sizeof(double) * ((size_t)N + 8), h->stream));
   amg->tail_N = N; amg->tail_first = first; amg->tail_rank = b200_comm_rank(c);
+  tr(h, " tail: rhs plan");
   return 0;
 }
 
