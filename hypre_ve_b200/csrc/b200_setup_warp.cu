@@ -906,10 +906,13 @@ static int spgemm_fused_run(b200_handle h, b200_csr A, b200_csr B, int allsquare
   B200_LAUNCH_CHECK();
   B200_CUDA(cudaMemsetAsync(cnt + n, 0, sizeof(int), h->stream));
   int flag = 1;
-  for (int pass = 0; pass < 4 && flag; pass++) {
+  // Small products (the coarse end of the hierarchy: a few thousand long rows) start with the 1024-slot table: occupancy is
+  // irrelevant there, and every size class that turns rows away costs a row list (scan + host round trip) and a flag round trip.
+  const int pass0 = (n <= 32768) ? 2 : 0;
+  for (int pass = pass0; pass < 4 && flag; pass++) {
     B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
     int *rows = nullptr, m = n;
-    if (pass > 0) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
+    if (pass > pass0) B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &rows, &m));
 #define B200_SPGEMM_FUSED(CAPV, BPS)                                                                              \
     {                                                                                                             \
       constexpr int CAP = CAPV;                                                                                   \
