@@ -38,12 +38,12 @@ __global__ void max_row_kernel(int n, const int *__restrict__ A_i, int *__restri
 // matrix stream is staged by bulk copies.  Banded stencils come out cheapest at G = 1 (lanes own
 // consecutive rows: their p-th columns are adjacent), irregular coarse operators at G = 16/32.
 __global__ void gather_cost_kernel(int nrows, const int *__restrict__ A_i, const int *__restrict__ A_j, int nwin,
-                                   int stride, unsigned long long *__restrict__ cost /* [6][2] */) {
+                                   int stride, int gi_lo, int gi_hi, unsigned long long *__restrict__ cost /* [6][2] */) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= nwin) return;
   const int rbase = (int)(((long long)w * stride) * 32);
-  for (int gi = 0; gi < 6; gi++) {
+  for (int gi = gi_lo; gi <= gi_hi; gi++) {         // only the lane counts the plan may pick
     const int G = 1 << gi, rows_per = 32 / G;
     unsigned long long wf = 0, ent = 0;
     for (int rb = 0; rb < G; rb++) {               // the 32 rows are covered by G passes of 32/G rows
@@ -231,19 +231,27 @@ int b200_csr_build_plan(b200_handle h, b200_csr A) {
     unsigned long long *d_cost = nullptr, h_cost[12];
     B200_TRY(b200_dalloc<unsigned long long>(h, &d_cost, 12));
     B200_CUDA(cudaMemsetAsync(d_cost, 0, sizeof(h_cost), h->stream));
-    gather_cost_kernel<<<b200_grid((size_t)nwin * 32, 128), 128, 0, h->stream>>>(A->nrows, A->i, A->j, nwin, stride, d_cost);
-    B200_LAUNCH_CHECK();
-    B200_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(h_cost), cudaMemcpyDeviceToHost, h->stream));
-    B200_CUDA(cudaStreamSynchronize(h->stream));
-    B200_TRY(b200_dfree(h, d_cost));
     // lanes-per-row must keep the CTA busy: a tile of MAX_TILE entries holds MAX_TILE/avg rows, so fewer
     // than avg*NT/MAX_TILE lanes per row would leave threads idle
     int gmin = 1;
     while (gmin < 32 && gmin * MAX_TILE < avg * NT) gmin <<= 1;
+    int gi_lo = 0, gi_hi = 0;
+    while ((1 << gi_lo) < gmin) gi_lo++;
+    gi_hi = gi_lo;
+    while (gi_hi < 5 && (2 << gi_hi) <= 2 * avg) gi_hi++;      // the selection loop below stops at the first g > gmin with g > 2 avg
+    static const bool eval_all = [] { const char *e = getenv("B200_PLAN_EVAL_ALL"); return e && e[0] == '1'; }();   // diagnosis
+    gather_cost_kernel<<<b200_grid((size_t)nwin * 32, 128), 128, 0, h->stream>>>(A->nrows, A->i, A->j, nwin, stride, eval_all ? 0 : gi_lo,
+                                                                             eval_all ? 5 : gi_hi, d_cost);
+    B200_LAUNCH_CHECK();
+    B200_CUDA(cudaMemcpyAsync(h_cost, d_cost, sizeof(h_cost), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_TRY(b200_dfree(h, d_cost));
     double best = 1e300;
     static const bool dbg2 = [] { const char *e = getenv("B200_DEBUG_PLAN"); return e && e[0] == '1'; }();
-    for (int gi = 0; gi < 6; gi++) {
+    for (int gi = eval_all ? 0 : gi_lo; gi <= (eval_all ? 5 : gi_hi); gi++) {
       const int g = 1 << gi;
+      if (eval_all && dbg2) fprintf(stderr, "[b200 plan]   (all) G=%d wavefronts/entry=%.3f\n", g, (double)h_cost[2 * gi] / (double)(h_cost[2 * gi + 1] ? h_cost[2 * gi + 1] : 1));
+      if (gi < gi_lo || gi > gi_hi) continue;
       if (g < gmin) continue;
       if (g > gmin && g > 2 * avg) break;          // more lanes than a row has entries: mostly idle
       const double c = (double)h_cost[2 * gi] / (double)(h_cost[2 * gi + 1] ? h_cost[2 * gi + 1] : 1);
@@ -256,7 +264,8 @@ int b200_csr_build_plan(b200_handle h, b200_csr A) {
   double per_pass = avg * (NT / G);
   int passes = per_pass > 0 ? (int)(MAX_TILE / per_pass) : 1;
   if (passes < 1) passes = 1;
-  if (passes * (NT / G) > 160) passes = 160 / (NT / G) > 0 ? 160 / (NT / G) : 1;   // row pointers staged per tile
+  static const int tile_rows = [] { const char *e = getenv("B200_SPMV_TILE_ROWS"); const int v = e ? atoi(e) : 160; return v < 32 ? 32 : (v > B200_SPMV_RCAP - 32 ? B200_SPMV_RCAP - 32 : v); }();
+  if (passes * (NT / G) > tile_rows) passes = tile_rows / (NT / G) > 0 ? tile_rows / (NT / G) : 1;   // row pointers staged per tile
   int tile = (int)(per_pass * passes * 0.97);
   if (tile > MAX_TILE) tile = MAX_TILE;
   if (tile < 128) tile = 128;

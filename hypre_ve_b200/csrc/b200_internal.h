@@ -14,6 +14,7 @@
 #define B200_NUM_SM_FALLBACK 148
 // streaming SpMV geometry shared by the row-block plan and both kernels
 #define B200_SPMV_NT 128          // threads per CTA
+#define B200_SPMV_RCAP 192        // row pointers staged per tile by the pipelined SpMV kernels (tiles of up to RCAP - 32 rows)
 #define B200_SPMV_MAX_TILE 1024   // upper bound on the entries of one tile
 
 struct b200_pool_s;   // slab sub-allocator (b200_runtime.cu)

@@ -249,6 +249,32 @@ __global__ void pmis_setcf_kernel(int n, const int *__restrict__ S_i, const int 
   }
   cf_out[i] = c;
 }
+// The same sweep with the NEXT sweep's graph flags and node count produced on the way (a node stays in the graph iff its new
+// marker is 0): saves the separate pass that rebuilt them.  ingraph[i] is read and written by thread i only.
+__global__ void pmis_setcf_graph_kernel(int n, const int *__restrict__ S_i, const int *__restrict__ S_j,
+                                        int *__restrict__ ingraph, double *__restrict__ measure,
+                                        const int *__restrict__ cf_in, int *__restrict__ cf_out, int *__restrict__ count) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int g = 0;
+  if (i < n) {
+    int c = cf_in[i];
+    if (ingraph[i]) {                                 // :2543-2595
+      if (measure[i] < 1) c = -1;
+      if (c > 0) {
+        c = 1;
+      } else {
+        for (int jS = S_i[i]; jS < S_i[i + 1]; jS++)
+          if (cf_in[S_j[jS]] > 0) c = -1;
+      }
+      if (c != 0) measure[i] = 0;                     // :2643-2647
+    }
+    cf_out[i] = c;
+    g = (c == 0) ? 1 : 0;
+    ingraph[i] = g;
+  }
+  unsigned b = __ballot_sync(0xffffffffu, g);
+  if ((threadIdx.x & 31) == 0 && b) atomicAdd(count, __popc(b));
+}
 // First sweep of PMIS with CF_init 1 (HMIS): the graph holds the undecided nodes AND the first pass's C points; no
 // independent set is picked (`if (!CF_init || iter)`, :2420).  The reference updates CF_marker in place in index order
 // (:2543-2595), and here that order is visible: a C point whose measure is below 1 is turned into an F point when its
@@ -690,7 +716,7 @@ int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row
   B200_TRY(b200_dalloc<int>(h, &colcnt, n));
   B200_TRY(b200_dalloc<int>(h, &ingraph, n));
   B200_TRY(b200_dalloc<int>(h, &cf2, n));
-  B200_TRY(b200_dalloc<int>(h, &d_count, 1));
+  B200_TRY(b200_dalloc<int>(h, &d_count, 2));
   B200_TRY(b200_dalloc<double>(h, &measure, n));
   B200_CUDA(cudaMemsetAsync(colcnt, 0, sizeof(int) * (size_t)n, h->stream));
   if (S->nnz) {
@@ -708,25 +734,29 @@ int b200_pmis_rows_init(b200_handle h, b200_csr S, int seed, long long first_row
     B200_CUDA(cudaMemcpyAsync(d_cf, cf2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
     iter = 1;
   }
-  while (true) {
-    B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int), h->stream));
-    pmis_graph_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf, ingraph, d_count);
-    B200_LAUNCH_CHECK();
+  // graph flags and node count of the first sweep; every later sweep gets them from the sweep before it
+  B200_CUDA(cudaMemsetAsync(d_count, 0, sizeof(int) * 2, h->stream));
+  pmis_graph_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf, ingraph, d_count);
+  B200_LAUNCH_CHECK();
+  int *cur = d_cf, *nxt = cf2;                      // markers ping-pong between the caller's array and the scratch
+  for (int k = 0;; k++) {
     int count = 0;
-    B200_CUDA(cudaMemcpyAsync(&count, d_count, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaMemcpyAsync(&count, d_count + (k & 1), sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
     if (count == 0) break;                          // :2399-2407
     if (!cf_init || iter) {
-      pmis_mark_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, measure, d_cf);
+      pmis_mark_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, measure, cur);
       B200_LAUNCH_CHECK();
-      pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, d_cf);
+      pmis_remove_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, measure, ingraph, cur);
       B200_LAUNCH_CHECK();
     }
-    pmis_setcf_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, ingraph, measure, d_cf, cf2);
+    B200_CUDA(cudaMemsetAsync(d_count + ((k + 1) & 1), 0, sizeof(int), h->stream));
+    pmis_setcf_graph_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, S->i, S->j, ingraph, measure, cur, nxt, d_count + ((k + 1) & 1));
     B200_LAUNCH_CHECK();
-    B200_CUDA(cudaMemcpyAsync(d_cf, cf2, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
+    std::swap(cur, nxt);
     if (++iter > 1000) B200_FAIL("PMIS did not terminate");
   }
+  if (cur != d_cf) B200_CUDA(cudaMemcpyAsync(d_cf, cur, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, h->stream));
   if (iterations) *iterations = iter;
   B200_TRY(b200_dfree(h, colcnt)); B200_TRY(b200_dfree(h, ingraph)); B200_TRY(b200_dfree(h, cf2));
   B200_TRY(b200_dfree(h, d_count)); B200_TRY(b200_dfree(h, measure));

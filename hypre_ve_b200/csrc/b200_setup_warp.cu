@@ -20,6 +20,9 @@
 namespace {
 
 constexpr int WPB = 4;                 // warps per CTA
+// extpi_warp_kernel: 56 registers unconstrained = 9 CTAs per SM; capped at 48 (10 CTAs, 20 bytes of spills) the coarse-level
+// interpolation is 1.3 ms faster at 256^3, at 40 (12 CTAs) the spills cost more than the occupancy brings (+3.5 ms)
+#define EXTPI_MIN_CTAS 10
 constexpr int NOTFOUND = -1;
 constexpr int STRONG_F = -2;
 constexpr int SELF = -3;
@@ -94,7 +97,7 @@ __device__ void qsort2_abs_smem(int *v, double *w, int left, int right) {
 // F neighbour's row is already in flight (software pipeline) while the current one is folded in.  The
 // arithmetic and its order are unchanged.
 template <int CAP>
-__global__ void __launch_bounds__(32 * WPB)
+__global__ void __launch_bounds__(32 * WPB, EXTPI_MIN_CTAS)
 extpi_warp_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
                   const int *__restrict__ S_i, const int *__restrict__ S_j, const int *__restrict__ cf,
                   const int *__restrict__ f2c, double trunc_tol, int pmax, int *__restrict__ out_j,

@@ -27,7 +27,7 @@ constexpr int DICT_MAX = 255;          // members per dictionary (codes are byte
 constexpr int DSLOTS = 1024;           // hash slots of the collecting sets
 constexpr int EMPTY_OFF = (int)0x80000000;
 constexpr unsigned long long EMPTY_VAL = 0xFFF8B200DEAD0001ull;   // a NaN payload no operator carries; if one does, no dictionary
-constexpr int RCAP = 192;
+constexpr int RCAP = B200_SPMV_RCAP;   // row pointers staged per tile (tiles with more rows read A_i from global)
 constexpr int DSCAP_MAX = 2048;
 
 __device__ __forceinline__ unsigned dhash(unsigned long long k) {

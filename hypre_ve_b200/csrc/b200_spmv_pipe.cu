@@ -54,7 +54,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
                : "memory");
 }
 
-constexpr int RCAP = 192;        // row pointers staged per tile (tiles with more rows read A_i from global)
+constexpr int RCAP = B200_SPMV_RCAP;   // row pointers staged per tile (tiles with more rows read A_i from global)
 
 // Per-tile latency chain kept short: tile metadata (one int4 per tile, prefetched one tile ahead),
 // row pointers (third bulk copy) and the epilogue operands of each thread's first row (prefetched
