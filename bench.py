@@ -329,10 +329,12 @@ def main_dist(a, rank, world, local_rank):
     launches0 = h.launch_count()
     barrier()
     t_set = t_sol = 0.0
+    step_ms = []
     for _ in range(a.steps):
         s_ms, v_ms, its, rel = step()
         t_set += s_ms
         t_sol += v_ms
+        step_ms.append((round(s_ms, 3), round(v_ms, 3)))
     barrier()
     launches = h.launch_count() - launches0
     # end to end through the rows-from-the-caller entry point (b200_dist_matrix_create_from_host = IJ assembly per rank,
@@ -394,6 +396,7 @@ def main_dist(a, rank, world, local_rank):
                     "parallelism": "row-partitioned ParCSR (-P %d %d %d), %d GPUs, halo + reductions over NVLink; levels <= %d rows "
                                    "replicated (seq_threshold)" % (P, Q, R, world, a.seq_threshold)},
         "setup_s": set_s, "solve_s": sol_s, "iterations": its, "final_rel_res": rel,
+        "rank0_step_ms": [{"setup": sm, "solve": vm} for sm, vm in step_ms],
         "reference_iterations": ref_its, "iterations_match_reference": (its == ref_its) if ref_its is not None else None,
         "e2e_iterations": e2e_its,
         "spmv_gbs": achieved, "spmv_ms": spmv_ms,
