@@ -295,9 +295,8 @@ spmv_dict_kernel(const int *__restrict__ A_i, const int *__restrict__ A_j, const
   }
 }
 
-template <bool DC, bool DV>
-int launch_dict(b200_handle h, b200_csr A, const double *x, double *y, const Epi &epi) {
-  constexpr int NSTAGE = 2;
+template <bool DC, bool DV, int NSTAGE>
+int launch_dict_n(b200_handle h, b200_csr A, const double *x, double *y, const Epi &epi) {
   constexpr int VB = DV ? 1 : 8, CB = DC ? 1 : 4;
   int scap = (A->tile + A->max_row + 16 + 31) & ~31;
   const size_t bytes = ((size_t)(VB + CB) * scap + sizeof(int) * RCAP) * NSTAGE + sizeof(unsigned long long) * NSTAGE;
@@ -324,6 +323,16 @@ int launch_dict(b200_handle h, b200_csr A, const double *x, double *y, const Epi
                                                                   reinterpret_cast<const int4 *>(A->blk_meta), A->nblk, scap, x, y, epi);
   B200_LAUNCH_CHECK();
   return 0;
+}
+
+// stages of the ring: a tile of codes is under 2 KB, so the ring can be deep without costing occupancy (B200_DICT_STAGES)
+template <bool DC, bool DV>
+int launch_dict(b200_handle h, b200_csr A, const double *x, double *y, const Epi &epi) {
+  static const int stages = [] { const char *e = getenv("B200_DICT_STAGES"); return e ? atoi(e) : 3; }();   // 256^3 7-pt: 2 -> 0.206, 3 -> 0.186, 4 -> 0.188, 6 -> 0.198 ms
+  if (stages >= 6) return launch_dict_n<DC, DV, 6>(h, A, x, y, epi);
+  if (stages >= 4) return launch_dict_n<DC, DV, 4>(h, A, x, y, epi);
+  if (stages == 3) return launch_dict_n<DC, DV, 3>(h, A, x, y, epi);
+  return launch_dict_n<DC, DV, 2>(h, A, x, y, epi);
 }
 
 }  // namespace
