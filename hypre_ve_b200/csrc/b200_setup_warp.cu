@@ -416,9 +416,11 @@ __global__ void __launch_bounds__(128)
 extpi_thread_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ A_j, const double *__restrict__ A_a,
                     const int *__restrict__ S_i, const int *__restrict__ S_j, const int *__restrict__ cf,
                     const int *__restrict__ f2c, double trunc_tol, int pmax, int *__restrict__ out_j,
-                    double *__restrict__ out_a, int *__restrict__ out_cnt, int *__restrict__ overflow) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+                    double *__restrict__ out_a, int *__restrict__ out_cnt, int *__restrict__ overflow,
+                    const int *__restrict__ rows) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const int i = rows ? rows[t] : t;              // list of the F rows: every lane of a warp has work
   const int c = cf[i];
   if (c >= 0) { out_j[(size_t)i * pmax] = f2c[i]; out_a[(size_t)i * pmax] = 1.0; out_cnt[i] = 1; return; }
   if (c == -3) { out_cnt[i] = 0; return; }
@@ -516,6 +518,16 @@ extpi_thread_kernel(int n, const int *__restrict__ A_i, const int *__restrict__ 
   }
   out_cnt[i] = len;
   for (int p = 0; p < len; p++) { out_j[(size_t)i * pmax + p] = key[p]; out_a[(size_t)i * pmax + p] = val[p]; }
+}
+
+// rows that need no work: C points interpolate from themselves, isolated F points (-3) get an empty row; F rows stay PENDING
+__global__ void extpi_trivial_rows_kernel(int n, const int *__restrict__ cf, const int *__restrict__ f2c, int pmax,
+                                          int *__restrict__ out_j, double *__restrict__ out_a, int *__restrict__ out_cnt) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = cf[i];
+  if (c >= 0) { out_j[(size_t)i * pmax] = f2c[i]; out_a[(size_t)i * pmax] = 1.0; out_cnt[i] = 1; }
+  else if (c == -3) out_cnt[i] = 0;
 }
 
 __global__ void strided_to_csr_kernel(int n, int stride, const int *__restrict__ P_i, const int *__restrict__ sj,
@@ -825,13 +837,25 @@ int b200_extpi_interp_warp(b200_handle h, b200_csr A, b200_csr S, const int *d_c
   if (stencil_rows) {
     // the dependent-load chain per row is short and thread-per-row keeps 32x more rows in flight than a warp per row
     B200_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), h->stream));
-    if (avg_row <= 10.0)
-      extpi_thread_kernel<32, 16><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
-                                                                          max_elmts, sj, sa, cnt, d_flag);
-    else
-      extpi_thread_kernel<64, 32><<<b200_grid(n, 128), 128, 0, h->stream>>>(n, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
-                                                                          max_elmts, sj, sa, cnt, d_flag);
-    B200_LAUNCH_CHECK();
+    // C rows and isolated rows are written by a streaming kernel; the row kernel then runs over the LIST of F rows, so that every
+    // lane of its warps has a row to build (a third of the lanes would otherwise retire at once and idle through the warp's work)
+    static const bool f_list = [] { const char *e = getenv("B200_EXTPI_F_LIST"); return !(e && e[0] == '0'); }();
+    int *frows = nullptr, nf = n;
+    if (f_list) {
+      extpi_trivial_rows_kernel<<<b200_grid(n, 256), 256, 0, h->stream>>>(n, d_cf, f2c, max_elmts, sj, sa, cnt);
+      B200_LAUNCH_CHECK();
+      B200_TRY(build_row_list(h, n, cnt, PENDING, PENDING, &frows, &nf));
+    }
+    if (nf > 0) {
+      if (avg_row <= 10.0)
+        extpi_thread_kernel<32, 16><<<b200_grid(nf, 128), 128, 0, h->stream>>>(nf, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
+                                                                             max_elmts, sj, sa, cnt, d_flag, frows);
+      else
+        extpi_thread_kernel<64, 32><<<b200_grid(nf, 128), 128, 0, h->stream>>>(nf, A->i, A->j, A->a, S->i, S->j, d_cf, f2c, trunc_factor,
+                                                                             max_elmts, sj, sa, cnt, d_flag, frows);
+      B200_LAUNCH_CHECK();
+    }
+    B200_TRY(b200_dfree(h, frows));
     B200_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
   }
