@@ -149,20 +149,42 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled during the timed region (what `nvidia-smi --query-gpu=clocks.sm,...` prints).
+    Read through NVML inside this process, initialised BEFORE the timed region: spawning one nvidia-smi per rank every 200 ms
+    meant N concurrent NVML start-ups enumerating all GPUs of the node, and on 4-GPU boxes the first timed solve intermittently
+    stalled for ~0.6 s (ranks spin on each other's exchanges, so one held-up launch holds up all).  Falls back to the nvidia-smi
+    command line when the NVML binding is missing."""
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
         self.gpu, self.rows, self.stop_flag = gpu, [], False
+        self.nvml = self.dev = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml, self.dev = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        except Exception:
+            self.nvml = self.dev = None
+
+    def sample_nvml(self):
+        nv = self.nvml
+        sm = nv.nvmlDeviceGetClockInfo(self.dev, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.dev, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.dev)
+        act = lambda bit: "Active" if (r & bit) else "Not Active"
+        return [str(sm), str(mx), act(0x8), act(0x40), act(0x20), act(0x4)]     # hw_slowdown, hw_thermal, sw_thermal, sw_power_cap
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
+                if self.nvml is not None:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                    self.rows.append([c.strip() for c in out.strip().split(",")])
             except Exception:
                 pass
             time.sleep(0.2)
@@ -173,7 +195,7 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k] == "Active"})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def host_threads():
