@@ -207,7 +207,7 @@ int b200_csr_spmv_epi(b200_handle h, b200_csr A, const double *x, double *y, int
 int b200_csr_alloc(b200_handle h, int nrows, int ncols, int nnz, bool with_data, b200_csr *out) {
   b200_csr A = new b200_csr_s();
   A->nrows = nrows; A->ncols = ncols; A->nnz = nnz; A->owns = true;
-  B200_TRY(b200_dalloc<int>(h, &A->i, (size_t)nrows + 1));
+  B200_TRY(b200_dalloc<int>(h, &A->i, (size_t)nrows + 1 + 4));      // + 4: the bulk copy of a tile's row pointers is rounded up to 16 bytes
   B200_TRY(b200_dalloc<int>(h, &A->j, (size_t)nnz + B200_PAD));
   if (with_data) B200_TRY(b200_dalloc<double>(h, &A->a, (size_t)nnz + B200_PAD));
   *out = A;
