@@ -162,9 +162,25 @@ class ClockSampler(threading.Thread):
         try:
             import pynvml
             pynvml.nvmlInit()
-            self.nvml, self.dev = pynvml, pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            dev = None
+            try:        # the CUDA ordinal is not the NVML index when CUDA_VISIBLE_DEVICES hides or reorders devices: go by UUID
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu).uuid)
+                dev = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+            except Exception:
+                dev = None
+            if dev is None:
+                dev = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+            self.nvml, self.dev = pynvml, dev
         except Exception:
             self.nvml = self.dev = None
+
+    def device_name(self):
+        try:
+            u = self.nvml.nvmlDeviceGetUUID(self.dev)
+            return u.decode() if isinstance(u, bytes) else str(u)
+        except Exception:
+            return None
 
     def sample_nvml(self):
         nv = self.nvml
@@ -195,7 +211,8 @@ class ClockSampler(threading.Thread):
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k] == "Active"})
         return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
+                "reasons": reasons, "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi",
+                "device": self.device_name()}
 
 
 def host_threads():
